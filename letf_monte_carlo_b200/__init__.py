@@ -1,0 +1,9 @@
+"""letf_monte_carlo_b200 - B200-native LETF Monte Carlo path engine.
+
+Drop-in for the hot path of djbm10/LETF-Monte-Carlo
+(`letf.mc_runner.parallel_monte_carlo_fixed` -> `simulate_single_path_fixed` ->
+`run_strategy_fixed`); everything else of the reference is out of scope.
+"""
+from . import abi, config  # noqa: F401
+
+__all__ = ["abi", "config"]

@@ -1,0 +1,212 @@
+// letf_math.cuh — precision-templated math + counter-based RNG for the fused LETF path kernel.
+//
+// Two arithmetic modes (template parameter R):
+//   double : parity mode, reference arithmetic (the reference is float64 NumPy throughout)
+//   float  : throughput mode, MUFU fast paths on the device
+// Everything here is __host__ __device__ so the identical source also compiles with a plain
+// host compiler for the test-only emulation build (tests/emu); the product only ever runs
+// the device side.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LETF_HD __host__ __device__ __forceinline__
+#define LETF_HDN __host__ __device__ __noinline__
+#else
+#define LETF_HD inline
+#define LETF_HDN
+#endif
+
+namespace letf {
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (c0,c1,c2,c3), key = (k0,k1).
+struct U4 { uint32_t x, y, z, w; };
+
+LETF_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  lo = a * b;
+  hi = __umulhi(a, b);
+#else
+  uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+
+LETF_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0, l0, h1, l1;
+    mulhilo(0xD2511F53u, c.x, h0, l0);
+    mulhilo(0xCD9E8D57u, c.z, h1, l1);
+    U4 n;
+    n.x = h1 ^ c.y ^ k0;
+    n.y = l1;
+    n.z = h0 ^ c.w ^ k1;
+    n.w = l0;
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// stream tags (counter word 3 = tag << 8 | sub-block)
+enum : uint32_t {
+  STREAM_START = 1, STREAM_SPELL = 2, STREAM_MKT0 = 3, STREAM_MKT1 = 4, STREAM_STRESS = 5,
+  STREAM_JUMP = 6, STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T */
+};
+
+struct RngKey {
+  uint32_t k0, k1;   // user seed
+  uint32_t t0, t1;   // sim_id (trial id with the antithetic bit cleared)
+};
+
+LETF_HD U4 rng_block(const RngKey& k, uint32_t day, uint32_t stream, uint32_t sub = 0) {
+  U4 c;
+  c.x = k.t0; c.y = k.t1; c.z = day; c.w = (stream << 8) | sub;
+  return philox4x32_10(c, k.k0, k.k1);
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename R> struct Mth;
+
+template <> struct Mth<double> {
+  typedef double T;
+  static LETF_HD double sqrt_(double x) { return ::sqrt(x); }
+  static LETF_HD double rsqrt_(double x) { return 1.0 / ::sqrt(x); }
+  static LETF_HD double log_(double x) { return ::log(x); }
+  static LETF_HD double tanh_(double x) { return ::tanh(x); }
+  static LETF_HD double pow_(double x, double y) { return ::pow(x, y); }
+  static LETF_HD double abs_(double x) { return ::fabs(x); }
+  static LETF_HD double div_(double a, double b) { return a / b; }
+  static LETF_HD double u01(uint32_t a) { return ((double)a + 0.5) * 2.3283064365386963e-10; }
+  static LETF_HD double u01_16(uint32_t a) { return ((double)a + 0.5) * (1.0 / 65536.0); }
+  static LETF_HD double u01_12(uint32_t a) { return ((double)a + 0.5) * (1.0 / 4096.0); }
+  static LETF_HD void box_muller(uint32_t a, uint32_t b, double& n0, double& n1) {
+    double r = ::sqrt(-2.0 * ::log(u01(a)));
+    double th = 6.283185307179586476925 * u01(b);
+    n0 = r * ::cos(th);
+    n1 = r * ::sin(th);
+  }
+};
+
+template <> struct Mth<float> {
+  typedef float T;
+#if defined(__CUDA_ARCH__)
+  static LETF_HD float sqrt_(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static LETF_HD float rsqrt_(float x) { return rsqrtf(x); }
+  static LETF_HD float log_(float x) { return __logf(x); }
+  static LETF_HD float tanh_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static LETF_HD float pow_(float x, float y) { return __powf(x, y); }
+  static LETF_HD float div_(float a, float b) { return __fdividef(a, b); }
+#else
+  static LETF_HD float sqrt_(float x) { return ::sqrtf(x); }
+  static LETF_HD float rsqrt_(float x) { return 1.0f / ::sqrtf(x); }
+  static LETF_HD float log_(float x) { return ::logf(x); }
+  static LETF_HD float tanh_(float x) { return ::tanhf(x); }
+  static LETF_HD float pow_(float x, float y) { return ::powf(x, y); }
+  static LETF_HD float div_(float a, float b) { return a / b; }
+#endif
+  static LETF_HD float abs_(float x) { return ::fabsf(x); }
+  // (a + 0.5) * 2^-32, never 0; may round to exactly 1 (log -> 0, harmless)
+  static LETF_HD float u01(uint32_t a) { return fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+  static LETF_HD float u01_16(uint32_t a) { return fmaf((float)a, 1.0f / 65536.0f, 0.5f / 65536.0f); }
+  static LETF_HD float u01_12(uint32_t a) { return fmaf((float)a, 1.0f / 4096.0f, 0.5f / 4096.0f); }
+  static LETF_HD void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float u = u01(a);
+    // angle in [-pi, pi): signed reinterpretation of the second word
+    float th = (float)(int32_t)b * 1.4629180792671596e-9f;  // 2*pi / 2^32
+#if defined(__CUDA_ARCH__)
+    float r = sqrt_(-1.3862943611198906f * __log2f(u));      // sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u)
+    n0 = r * __cosf(th);
+    n1 = r * __sinf(th);
+#else
+    float r = ::sqrtf(-2.0f * ::logf(u));
+    n0 = r * ::cosf(th);
+    n1 = r * ::sinf(th);
+#endif
+  }
+};
+
+template <typename R> LETF_HD R rmax(R a, R b) { return a > b ? a : b; }   // python max(a, b) for non-NaN b
+template <typename R> LETF_HD R rmin(R a, R b) { return a < b ? a : b; }
+template <typename R> LETF_HD R clipr(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); } // NaN passes through
+template <typename R> LETF_HD bool isnan_(R x) { return x != x; }
+template <typename R> LETF_HD bool isfinite_(R x) { return (x - x) == (R)0; }
+
+// ------------------------------------------------------------------------------------------
+// chi-square(nu) and Student-t(df) samplers.
+//
+// Fast path (2*shape integral, nu an integer <= 11): Gamma(k/2) = -ln(prod of floor(k/2) uniforms)
+// (+ N^2/2 when k is odd), i.e. exact in distribution and branch-free:
+//     chi2(k) = -2 ln(U_1 ... U_m) + [k odd] N^2,  m = k / 2
+// The m uniforms are cut from two 32-bit words: 32 bits each for m <= 2, 16 bits for m <= 4,
+// 12 bits for m == 5.  General nu (calibrated joint models, calibration.py:399, give nu in
+// [3.2, 12]): Marsaglia-Tsang (2000) squeeze/rejection with extra Philox blocks per retry.
+template <typename R>
+LETF_HD R chi2_int_fast(int k, uint32_t wa, uint32_t wb, R nrm) {
+  typedef Mth<R> M;
+  int m = k >> 1;
+  R prod = (R)1;
+  if (m == 1) prod = M::u01(wa);
+  else if (m == 2) prod = M::u01(wa) * M::u01(wb);
+  else if (m == 3) prod = M::u01_16(wa >> 16) * M::u01_16(wa & 0xFFFFu) * M::u01_16(wb >> 16);
+  else if (m == 4) prod = M::u01_16(wa >> 16) * M::u01_16(wa & 0xFFFFu) * M::u01_16(wb >> 16) * M::u01_16(wb & 0xFFFFu);
+  else if (m == 5) prod = M::u01_12(wa >> 20) * M::u01_12((wa >> 8) & 0xFFFu) * M::u01_12(wb >> 20) *
+                          M::u01_12((wb >> 8) & 0xFFFu) * M::u01_12(((wa & 0xFFu) << 4) | (wb & 0xFu));
+  R g = m > 0 ? (R)-2 * M::log_(prod) : (R)0;
+  if (k & 1) g += nrm * nrm;
+  return g;
+}
+
+// Marsaglia-Tsang gamma(shape a >= 1) * 2 = chi2(2a).  First attempt uses (n0, u0) supplied by the
+// caller's block; retries pull blocks (stream, sub = 1, 2, ...).
+template <typename R>
+LETF_HD R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+  typedef Mth<R> M;
+  R a = (R)0.5 * nu;
+  R d = a - (R)(1.0 / 3.0);
+  R c = M::rsqrt_((R)9 * d);
+  R x = n0;
+  uint32_t uw = u0w;
+  for (uint32_t sub = 1; sub < 64; sub++) {
+    R v = (R)1 + c * x;
+    if (v > (R)0) {
+      v = v * v * v;
+      R u = M::u01(uw);
+      R x2 = x * x;
+      if (u < (R)1 - (R)0.0331 * x2 * x2) return (R)2 * d * v;
+      if (M::log_(u) < (R)0.5 * x2 + d * ((R)1 - v + M::log_(v))) return (R)2 * d * v;
+    }
+    U4 b = rng_block(key, day, stream, sub);
+    R dump;
+    M::box_muller(b.x, b.y, x, dump);
+    uw = b.z;
+  }
+  return (R)2 * d;  // unreachable in practice (acceptance > 95 % per attempt)
+}
+
+struct DfInfo {      // host-precomputed per distribution
+  int fast_k;        // integer dof in [1, 11] -> fast path, else 0
+};
+
+LETF_HD int df_fast_k(double df) {
+  double r = ::floor(df + 0.5);
+  return (::fabs(df - r) < 1e-12 && r >= 1.0 && r <= 11.0) ? (int)r : 0;
+}
+
+// Student-t(df) from one Philox block: N0 / sqrt(chi2(df) / df).
+template <typename R>
+LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint32_t day, uint32_t stream) {
+  typedef Mth<R> M;
+  R n0, n1;
+  M::box_muller(b.x, b.y, n0, n1);
+  R c2 = fast_k ? chi2_int_fast<R>(fast_k, b.z, b.w, n1)
+                : chi2_marsaglia_tsang<R>(df, n1, b.z, key, day, stream);
+  return n0 * M::sqrt_(M::div_(df, rmax(c2, (R)1e-30)));
+}
+
+}  // namespace letf
