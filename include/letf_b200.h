@@ -282,9 +282,20 @@ int letf_run(LetfEngine* e, void* stream, uint64_t seed, int64_t first_trial,
 int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_trials,
                   int rng_mode, const LetfTape* host_tape, const LetfOutputs* host_out);
 
-/* Histogram / moment reduction of per-trial outputs (device pointers). */
+/* Histogram / moment reduction of per-trial outputs (device pointers).  letf_reduce ACCUMULATES
+ * into `summary` (so several launches / trial ranges can be folded); letf_summary_reset zeroes the
+ * bins, moments and counters and sets the extrema to +/-inf. */
+int letf_summary_reset(LetfEngine* e, void* stream, const LetfSummary* summary);
 int letf_reduce(LetfEngine* e, void* stream, const LetfOutputs* out, int64_t n_trials,
                 const LetfSummary* summary);
+
+/* Trade_List of ONE trial / ONE taxable strategy (trade.py:83-91), host buffers of capacity `cap`:
+ * the trial is re-simulated (same seed or same tape) with the journal log switched on.  This is
+ * what the host tax path needs for its <= 50 sampled trials per strategy (reporting.py:457-467).
+ * action: +1 BUY, -1 SELL.  *count receives the number of entries (may exceed cap). */
+int letf_trade_list_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode,
+                         const LetfTape* host_tape, int cap, int32_t* day, int32_t* asset,
+                         int32_t* action, double* shares, double* price, int32_t* count);
 
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info);
 

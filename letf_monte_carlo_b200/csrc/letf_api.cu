@@ -1,0 +1,509 @@
+// letf_api.cu — the C-ABI of include/letf_b200.h: engine lifecycle, kernel selection, launches,
+// host-buffer convenience entry points.  No CPU compute path exists in this library: every
+// entry point that produces path results launches a device kernel or fails.
+//
+// Reference seam replaced:
+//   letf/mc_runner.py:155-165          loky fan-out                  -> letf_run / letf_run_host
+//   letf/simulation/engine.py:423-619  simulate_single_path_fixed    -> the fused path kernel
+//   letf/strategy.py:55                run_strategy_fixed(df, ...)   -> letf_run_strategies
+//   letf/trade.py:83-91                TradeJournal.get_full_trades  -> letf_trade_list_host
+//   letf/reporting.py:358-376          percentile / win-rate inputs  -> letf_reduce
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+#include "letf_kernels.cuh"
+
+namespace letf {
+
+// ---- kernel registry (filled by the static registrars in inst_*.cu) -------------------------
+static std::vector<KernelEntry>& registry() {
+  static std::vector<KernelEntry> r;
+  return r;
+}
+void register_kernel(const KernelEntry& e) { registry().push_back(e); }
+int kernel_count() { return (int)registry().size(); }
+const KernelEntry* kernel_at(int i) { return &registry()[i]; }
+
+cudaError_t launch_reduce(const LetfOutputs& out, const LetfSummary& sm, int64_t n, int n_strat, double w0,
+                          double years, int sm_count, cudaStream_t st);
+cudaError_t launch_summary_reset(const LetfSummary& sm, int n_strat, cudaStream_t st);
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return LETF_ERR_CUDA;
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return fail_cuda(_e, #call);  \
+  } while (0)
+
+constexpr uint32_t kNeedRingP = (1u << LETF_ST_SMA) | (1u << LETF_ST_SMA_BAND) | (1u << LETF_ST_COMPOSITE) |
+                                (1u << LETF_ST_ADAPTIVE_VOL) | (1u << LETF_ST_CONVEX_VOL) |
+                                (1u << LETF_ST_META_ENSEMBLE) | (1u << LETF_ST_CONVICTION);
+constexpr uint32_t kNeedRingS = (1u << LETF_ST_MOM_VOL_CONV) | (1u << LETF_ST_CONVICTION);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace letf
+
+using namespace letf;
+
+struct LetfEngine {
+  LetfParams params;
+  int device = 0, precision = 0, sm_count = 0;
+  int32_t* dev_dur[2] = {nullptr, nullptr};
+  std::vector<int32_t> host_dur[2];
+  uint32_t type_mask = 0;
+  bool any_taxable = false;
+  DevBuf xscr, ringP, ringS, ringA;          // per-thread scratch of the fused kernel
+  DevBuf stage_tape, stage_out, stage_log;   // device staging of the *_host entry points
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  LetfLaunchInfo info;
+  std::mutex mu;
+};
+
+namespace letf {
+
+struct LogArgs {
+  int64_t trial = -1; int strategy = -1; int cap = 0;
+  int32_t* count = nullptr; int32_t* day = nullptr; int32_t* asset = nullptr; int32_t* action = nullptr;
+  double* shares = nullptr; double* price = nullptr;
+};
+
+static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask) {
+  const KernelEntry* best = nullptr;
+  for (int i = 0; i < kernel_count(); i++) {
+    const KernelEntry* k = kernel_at(i);
+    if (k->precision != e->precision || k->market != market) continue;
+    if (need_io && !k->tapeio) continue;
+    if (k->ns < n_strat || (tmask & ~k->tm)) continue;
+    if (!best) { best = k; continue; }
+    // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
+    int a = k->ns * 64 + __builtin_popcount(k->tm) * 2 + k->tapeio;
+    int b = best->ns * 64 + __builtin_popcount(best->tm) * 2 + best->tapeio;
+    if (a < b) best = k;
+  }
+  return best;
+}
+
+template <typename R, int NS>
+static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, uint64_t seed, int64_t first,
+                        int64_t n, int rng_mode, const LetfTape* tape, const LetfOutputs* out,
+                        const LetfSeries* series, const LogArgs& lg) {
+  cudaFuncAttributes fa;
+  int max_blocks = 0;
+  CK(ke->attrs(&fa, &max_blocks));
+  if (max_blocks < 1) return fail(LETF_ERR_CUDA, std::string("kernel ") + ke->name + " cannot be resident on this device");
+  // persistent grid: every resident thread owns ceil(n / nthreads) trials; shrink the grid so that
+  // all waves are full (equal-length trials: a partial last wave costs a whole trial time)
+  const int64_t resident = (int64_t)e->sm_count * max_blocks * kBlock;
+  const int64_t waves = (n + resident - 1) / resident;
+  const int64_t per_wave = (n + waves - 1) / waves;
+  int64_t grid = (per_wave + kBlock - 1) / kBlock;
+  if (grid < 1) grid = 1;
+  const int64_t nthreads = grid * kBlock;
+
+  static thread_local KArgs<R, NS> ka;
+  memset(&ka, 0, sizeof(ka));
+  convert_params<R, NS>(e->params, e->dev_dur, ka.p);
+  if (series) { ka.series = *series; ka.p.T = series->sim_days; ka.p.buffer = 0; ka.p.random_start = 0; }
+  if (tape) ka.tape = *tape;
+  ka.out = *out;
+  ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.tape_first = 0;
+  ka.rng_mode = rng_mode; ka.nthreads = nthreads;
+  ka.log_trial = lg.trial; ka.log_strategy = lg.strategy; ka.log_cap = lg.cap;
+  ka.log_count = lg.count; ka.log_day = lg.day; ka.log_asset = lg.asset; ka.log_action = lg.action;
+  ka.log_shares = lg.shares; ka.log_price = lg.price;
+
+  const int G = e->params.sim_days + e->params.buffer_days;
+  size_t scratch = 0;
+  if (ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching && G > 0) {
+    size_t b = (size_t)G * 3 * (size_t)nthreads * sizeof(R);
+    cudaError_t ce = e->xscr.reserve(b);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
+    ka.xscr = (R*)e->xscr.p; scratch += b;
+  }
+  if (ke->tm & kNeedRingP) { size_t b = (size_t)kRingP * nthreads * sizeof(R); CK(e->ringP.reserve(b)); ka.ringP = (R*)e->ringP.p; scratch += b; }
+  if (ke->tm & kNeedRingS) { size_t b = (size_t)kRingS * nthreads * sizeof(R); CK(e->ringS.reserve(b)); ka.ringS = (R*)e->ringS.p; scratch += b; }
+  if (ke->tm & kVolTypes) { size_t b = (size_t)kRingA * nthreads * sizeof(R); CK(e->ringA.reserve(b)); ka.ringA = (R*)e->ringA.p; scratch += b; }
+
+  CK(cudaEventRecord(e->ev0, st));
+  CK(ke->launch(&ka, (int)grid, st));
+  CK(cudaEventRecord(e->ev1, st));
+  e->timed = true;
+  e->info.grid = (int)grid; e->info.block = kBlock; e->info.regs_per_thread = fa.numRegs;
+  e->info.kernel_launches = 1; e->info.scratch_bytes = (int64_t)scratch; e->info.sm_count = e->sm_count;
+  return LETF_OK;
+}
+
+static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed, int64_t first, int64_t n,
+                      int rng_mode, const LetfTape* tape, const LetfOutputs* out, const LetfSeries* series,
+                      const LogArgs& lg) {
+  if (!e) return fail(LETF_ERR_INVALID, "null engine");
+  if (!out || !out->final_wealth || !out->max_dd || !out->num_trades) return fail(LETF_ERR_INVALID, "outputs: final_wealth, max_dd and num_trades are required");
+  if (n < 0 || first < 0) return fail(LETF_ERR_INVALID, "negative trial range");
+  if (out->n_trials < n) return fail(LETF_ERR_INVALID, "outputs.n_trials smaller than n_trials");
+  if (rng_mode < LETF_RNG_PHILOX || rng_mode > LETF_RNG_PHILOX_RECORD) return fail(LETF_ERR_INVALID, "bad rng_mode");
+  if (rng_mode != LETF_RNG_PHILOX && market != kMarketSeries) {
+    if (!tape) return fail(LETF_ERR_INVALID, "rng_mode needs a tape");
+    const int G = e->params.sim_days + e->params.buffer_days;
+    if (tape->gen_days != G || tape->sim_days != e->params.sim_days) return fail(LETF_ERR_INVALID, "tape day counts do not match the engine parameters");
+    int64_t last = first + n - 1;
+    int64_t need = n > 0 ? (e->params.antithetic_pairs ? (last >> 1) : last) + 1 : 0;
+    if (tape->n_tapes < need) return fail(LETF_ERR_INVALID, "tape has fewer columns than the trial range needs");
+  }
+  if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
+  const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
+  const bool need_io = rng_mode != LETF_RNG_PHILOX || want_journal || lg.count != nullptr || market == kMarketSeries;
+  const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask);
+  if (!ke) return fail(LETF_ERR_INVALID, "no kernel instantiation for this (precision, market, strategies) combination");
+  CK(cudaSetDevice(e->device));
+#define GO(R, NS) return launch_typed<R, NS>(e, ke, st, seed, first, n, rng_mode, tape, out, series, lg)
+  if (ke->precision == LETF_PREC_F64) {
+    if (ke->ns == 32) GO(double, 32);
+  } else {
+    if (ke->ns == 4) GO(float, 4);
+    if (ke->ns == 8) GO(float, 8);
+    if (ke->ns == 32) GO(float, 32);
+  }
+#undef GO
+  return fail(LETF_ERR_INVALID, "kernel registry holds an unsupported slot count");
+}
+
+// ---- 3x3 symmetric eigen-decomposition (cyclic Jacobi), for letf_nearest_psd3 -----------------
+static void jacobi3(double a[3][3], double v[3][3], double w[3]) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) v[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+      if (fabs(a[p][q]) < 1e-300) continue;
+      double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < 3; k++) { double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
+      for (int k = 0; k < 3; k++) { double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
+      for (int k = 0; k < 3; k++) { double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
+    }
+  }
+  for (int i = 0; i < 3; i++) w[i] = a[i][i];
+}
+
+}  // namespace letf
+
+// ================================================================================================
+extern "C" {
+
+int letf_abi_version(void) { return LETF_ABI_VERSION; }
+const char* letf_last_error(void) { return g_err.c_str(); }
+
+int letf_create(const LetfParams* params, int device, int precision, LetfEngine** out) {
+  if (!params || !out) return fail(LETF_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (precision != LETF_PREC_F64 && precision != LETF_PREC_F32) return fail(LETF_ERR_INVALID, "bad precision");
+  const char* err = validate_params(*params);
+  if (err) return fail(LETF_ERR_INVALID, err);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(LETF_ERR_INVALID, "no such CUDA device");
+  CK(cudaSetDevice(device));
+  LetfEngine* e = new (std::nothrow) LetfEngine();
+  if (!e) return fail(LETF_ERR_NOMEM, "host allocation failed");
+  e->params = *params;
+  e->device = device; e->precision = precision;
+  memset(&e->info, 0, sizeof(e->info));
+  cudaDeviceProp prop;
+  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) { delete e; return fail_cuda(ce, "cudaGetDeviceProperties"); }
+  e->sm_count = prop.multiProcessorCount;
+  e->info.sm_count = e->sm_count;
+  for (int r = 0; r < 2; r++) {
+    int nd = params->n_duration[r];
+    if (nd > 0) {
+      if (!params->duration_samples[r]) { delete e; return fail(LETF_ERR_INVALID, "n_duration > 0 with null duration_samples"); }
+      e->host_dur[r].assign(params->duration_samples[r], params->duration_samples[r] + nd);
+      ce = cudaMalloc((void**)&e->dev_dur[r], sizeof(int32_t) * nd);
+      if (ce == cudaSuccess) ce = cudaMemcpy(e->dev_dur[r], e->host_dur[r].data(), sizeof(int32_t) * nd, cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) { letf_destroy(e); return fail_cuda(ce, "duration samples upload"); }
+      e->params.duration_samples[r] = e->host_dur[r].data();
+    } else e->params.duration_samples[r] = nullptr;
+  }
+  e->type_mask = strategy_type_mask(*params);
+  for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
+  ce = cudaEventCreate(&e->ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);
+  if (ce != cudaSuccess) { letf_destroy(e); return fail_cuda(ce, "cudaEventCreate"); }
+  *out = e;
+  return LETF_OK;
+}
+
+void letf_destroy(LetfEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
+  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release();
+  e->stage_tape.release(); e->stage_out.release(); e->stage_log.release();
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+}
+
+int letf_run(LetfEngine* e, void* stream, uint64_t seed, int64_t first_trial, int64_t n_trials, int rng_mode,
+             const LetfTape* tape, const LetfOutputs* out) {
+  if (!e) return fail(LETF_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return launch_any(e, e->params.market_mode, (cudaStream_t)stream, seed, first_trial, n_trials, rng_mode, tape, out,
+                    nullptr, LogArgs());
+}
+
+int letf_run_strategies(LetfEngine* e, void* stream, const LetfSeries* series, const LetfOutputs* out) {
+  if (!e || !series) return fail(LETF_ERR_INVALID, "null argument");
+  if (series->sim_days < 0 || series->n_paths < 0) return fail(LETF_ERR_INVALID, "bad series shape");
+  if (!series->asset_ret[4]) return fail(LETF_ERR_INVALID, "series needs SPY_Ret (signals read SPY_Price)");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return launch_any(e, kMarketSeries, (cudaStream_t)stream, 0, 0, series->n_paths, LETF_RNG_PHILOX, nullptr, out, series,
+                    LogArgs());
+}
+
+int letf_summary_reset(LetfEngine* e, void* stream, const LetfSummary* sm) {
+  if (!e || !sm || !sm->hist || !sm->moments || !sm->extrema || !sm->counters) return fail(LETF_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(e->device));
+  CK(launch_summary_reset(*sm, e->params.n_strategies, (cudaStream_t)stream));
+  e->info.kernel_launches = 1;
+  return LETF_OK;
+}
+
+int letf_reduce(LetfEngine* e, void* stream, const LetfOutputs* out, int64_t n_trials, const LetfSummary* sm) {
+  if (!e || !out || !sm || !sm->hist || !sm->moments || !sm->extrema || !sm->counters) return fail(LETF_ERR_INVALID, "null argument");
+  if (n_trials < 0 || n_trials > out->n_trials) return fail(LETF_ERR_INVALID, "bad n_trials");
+  for (int q = 0; q < LETF_N_METRICS; q++) if (!(sm->hist_hi[q] > sm->hist_lo[q])) return fail(LETF_ERR_INVALID, "histogram range must have hi > lo");
+  if (sm->bench_strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "bench_strategy out of range");
+  CK(cudaSetDevice(e->device));
+  CK(launch_reduce(*out, *sm, n_trials, e->params.n_strategies, e->params.initial_capital, e->params.sim_years,
+                   e->sm_count, (cudaStream_t)stream));
+  e->info.kernel_launches = n_trials > 0 ? 1 : 0;
+  return LETF_OK;
+}
+
+int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
+  if (!e || !info) return fail(LETF_ERR_INVALID, "null argument");
+  if (e->timed) {
+    CK(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->info.last_kernel_ms = ms;
+  }
+  *info = e->info;
+  return LETF_OK;
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct TapeLayout { size_t off[12]; size_t bytes[12]; size_t total; };
+static TapeLayout tape_layout(const LetfTape& t) {
+  const size_t n = (size_t)t.n_tapes, G = (size_t)t.gen_days, T = (size_t)t.sim_days, K = (size_t)t.max_spells;
+  const size_t b[12] = {4 * n, 4 * K * n, 8 * G * 3 * n, 8 * G * n, 8 * G * n, 8 * G * n,
+                        8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * LETF_N_ASSETS * T * n};
+  TapeLayout L; size_t o = 0;
+  for (int i = 0; i < 12; i++) { L.off[i] = o; L.bytes[i] = b[i]; o += align256(b[i]); }
+  L.total = o;
+  return L;
+}
+static void** tape_field(LetfTape& t, int i) {
+  switch (i) {
+    case 0: return (void**)&t.start_offset; case 1: return (void**)&t.spells; case 2: return (void**)&t.x;
+    case 3: return (void**)&t.chi2; case 4: return (void**)&t.vix_n; case 5: return (void**)&t.irx_n;
+    case 6: return (void**)&t.liq_n; case 7: return (void**)&t.cred_n; case 8: return (void**)&t.jump_u;
+    case 9: return (void**)&t.jump_t; case 10: return (void**)&t.sign; default: return (void**)&t.te_t;
+  }
+}
+
+// stage a host tape on the device.  upload: copy host -> device (tape mode); otherwise zero-fill (record mode)
+static int stage_tape(LetfEngine* e, const LetfTape* host, bool upload, LetfTape* dev) {
+  *dev = *host;
+  LetfTape h = *host;
+  TapeLayout L = tape_layout(h);
+  cudaError_t ce = e->stage_tape.reserve(L.total ? L.total : 256);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "tape staging: " + std::string(cudaGetErrorString(ce))); }
+  for (int i = 0; i < 12; i++) {
+    void* hp = *tape_field(h, i);
+    char* dp = (char*)e->stage_tape.p + L.off[i];
+    *tape_field(*dev, i) = dp;
+    if (!hp) return fail(LETF_ERR_INVALID, "host tape has a null array");
+    if (L.bytes[i] == 0) continue;
+    if (upload) CK(cudaMemcpy(dp, hp, L.bytes[i], cudaMemcpyHostToDevice));
+    else CK(cudaMemset(dp, 0, L.bytes[i]));
+  }
+  return LETF_OK;
+}
+static int unstage_tape(LetfEngine* e, const LetfTape* host) {
+  LetfTape h = *host;
+  TapeLayout L = tape_layout(h);
+  for (int i = 0; i < 12; i++) {
+    void* hp = *tape_field(h, i);
+    if (L.bytes[i]) CK(cudaMemcpy(hp, (char*)e->stage_tape.p + L.off[i], L.bytes[i], cudaMemcpyDeviceToHost));
+  }
+  return LETF_OK;
+}
+
+struct OutLayout { size_t off[9]; size_t bytes[9]; size_t total; };
+static OutLayout out_layout(const LetfOutputs& o, int S, int64_t n) {
+  const size_t s = (size_t)(S > 0 ? S : 1), m = (size_t)n;
+  const size_t b[9] = {8 * s * m, 8 * s * m, 4 * s * m, o.journal_count ? 4 * s * m : 0, o.journal_volume ? 8 * s * m : 0,
+                       o.start_offset ? 4 * m : 0, 4 * m /* flags always */, o.regime_days ? 4 * 2 * m : 0, o.jump_days ? 4 * m : 0};
+  OutLayout L; size_t off = 0;
+  for (int i = 0; i < 9; i++) { L.off[i] = off; L.bytes[i] = b[i]; off += align256(b[i]); }
+  L.total = off;
+  return L;
+}
+
+int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_trials, int rng_mode,
+                  const LetfTape* host_tape, const LetfOutputs* host_out) {
+  if (!e || !host_out) return fail(LETF_ERR_INVALID, "null argument");
+  if (n_trials < 0 || host_out->n_trials < n_trials) return fail(LETF_ERR_INVALID, "outputs.n_trials smaller than n_trials");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  LetfTape dtape; const LetfTape* tp = nullptr;
+  if (rng_mode != LETF_RNG_PHILOX) {
+    if (!host_tape) return fail(LETF_ERR_INVALID, "rng_mode needs a tape");
+    int rc = stage_tape(e, host_tape, rng_mode == LETF_RNG_TAPE, &dtape);
+    if (rc) return rc;
+    tp = &dtape;
+  }
+  const int S = e->params.n_strategies;
+  OutLayout L = out_layout(*host_out, S, n_trials);
+  cudaError_t ce = e->stage_out.reserve(L.total ? L.total : 256);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "output staging: " + std::string(cudaGetErrorString(ce))); }
+  char* base = (char*)e->stage_out.p;
+  LetfOutputs dout;
+  dout.n_trials = n_trials;     // device columns are packed [S][n_trials]
+  dout.final_wealth = (double*)(base + L.off[0]); dout.max_dd = (double*)(base + L.off[1]);
+  dout.num_trades = (int32_t*)(base + L.off[2]);
+  dout.journal_count = L.bytes[3] ? (int32_t*)(base + L.off[3]) : nullptr;
+  dout.journal_volume = L.bytes[4] ? (double*)(base + L.off[4]) : nullptr;
+  dout.start_offset = L.bytes[5] ? (int32_t*)(base + L.off[5]) : nullptr;
+  dout.flags = (uint32_t*)(base + L.off[6]);
+  dout.regime_days = L.bytes[7] ? (int32_t*)(base + L.off[7]) : nullptr;
+  dout.jump_days = L.bytes[8] ? (int32_t*)(base + L.off[8]) : nullptr;
+  int rc = launch_any(e, e->params.market_mode, (cudaStream_t)0, seed, first_trial, n_trials, rng_mode, tp, &dout, nullptr, LogArgs());
+  if (rc) return rc;
+  if (n_trials == 0) return LETF_OK;
+  // device [S][n] -> host [S][N] (row pitch = host capacity)
+  const size_t n = (size_t)n_trials, N = (size_t)host_out->n_trials;
+  CK(cudaMemcpy2D(host_out->final_wealth, N * 8, dout.final_wealth, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(host_out->max_dd, N * 8, dout.max_dd, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(host_out->num_trades, N * 4, dout.num_trades, n * 4, n * 4, S, cudaMemcpyDeviceToHost));
+  if (dout.journal_count) CK(cudaMemcpy2D(host_out->journal_count, N * 4, dout.journal_count, n * 4, n * 4, S, cudaMemcpyDeviceToHost));
+  if (dout.journal_volume) CK(cudaMemcpy2D(host_out->journal_volume, N * 8, dout.journal_volume, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
+  if (dout.start_offset) CK(cudaMemcpy(host_out->start_offset, dout.start_offset, n * 4, cudaMemcpyDeviceToHost));
+  if (dout.regime_days) CK(cudaMemcpy2D(host_out->regime_days, N * 4, dout.regime_days, n * 4, n * 4, 2, cudaMemcpyDeviceToHost));
+  if (dout.jump_days) CK(cudaMemcpy(host_out->jump_days, dout.jump_days, n * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> fl(n);
+  CK(cudaMemcpy(fl.data(), dout.flags, n * 4, cudaMemcpyDeviceToHost));
+  if (host_out->flags) memcpy(host_out->flags, fl.data(), n * 4);
+  if (rng_mode == LETF_RNG_PHILOX_RECORD) { rc = unstage_tape(e, host_tape); if (rc) return rc; }
+  int64_t bad = 0;
+  for (size_t i = 0; i < n; i++) if (fl[i] & (LETF_FLAG_NONFINITE_RET | LETF_FLAG_BAD_VIX)) bad++;
+  if (bad) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "%lld of %lld trials generated non-finite returns or VIX <= 0 (reference raises ValueError, engine.py:486-498)",
+             (long long)bad, (long long)n_trials);
+    return fail(LETF_ERR_NONFINITE, msg);
+  }
+  return LETF_OK;
+}
+
+int letf_trade_list_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode,
+                         const LetfTape* host_tape, int cap, int32_t* day, int32_t* asset, int32_t* action,
+                         double* shares, double* price, int32_t* count) {
+  if (!e || !count) return fail(LETF_ERR_INVALID, "null argument");
+  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  if (cap < 0 || (cap > 0 && (!day || !asset || !action || !shares || !price))) return fail(LETF_ERR_INVALID, "bad log buffers");
+  if (rng_mode == LETF_RNG_PHILOX_RECORD) return fail(LETF_ERR_INVALID, "trade list replay does not record");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  *count = 0;
+  if (!e->params.strategies[strategy].taxable) return LETF_OK;   // engine.py:571: journal only for TAXABLE_IDS
+  LetfTape dtape; const LetfTape* tp = nullptr;
+  if (rng_mode == LETF_RNG_TAPE) {
+    if (!host_tape) return fail(LETF_ERR_INVALID, "rng_mode needs a tape");
+    int rc = stage_tape(e, host_tape, true, &dtape);
+    if (rc) return rc;
+    tp = &dtape;
+  }
+  const int S = e->params.n_strategies;
+  const size_t c = (size_t)(cap > 0 ? cap : 1);
+  size_t o_cnt = 0, o_day = 256, o_asset = o_day + align256(4 * c), o_act = o_asset + align256(4 * c),
+         o_sh = o_act + align256(4 * c), o_pr = o_sh + align256(8 * c), o_out = o_pr + align256(8 * c);
+  size_t total = o_out + align256(8 * S) * 2 + align256(4 * S) + 256;
+  cudaError_t ce = e->stage_log.reserve(total);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "log staging"); }
+  char* base = (char*)e->stage_log.p;
+  CK(cudaMemset(base, 0, 256));
+  LogArgs lg;
+  lg.trial = trial; lg.strategy = strategy; lg.cap = cap;
+  lg.count = (int32_t*)(base + o_cnt); lg.day = (int32_t*)(base + o_day); lg.asset = (int32_t*)(base + o_asset);
+  lg.action = (int32_t*)(base + o_act); lg.shares = (double*)(base + o_sh); lg.price = (double*)(base + o_pr);
+  LetfOutputs dout; memset(&dout, 0, sizeof(dout));
+  dout.n_trials = 1;
+  dout.final_wealth = (double*)(base + o_out); dout.max_dd = (double*)(base + o_out + align256(8 * S));
+  dout.num_trades = (int32_t*)(base + o_out + 2 * align256(8 * S));
+  dout.flags = (uint32_t*)(base + o_out + 2 * align256(8 * S) + align256(4 * S));
+  int rc = launch_any(e, e->params.market_mode, (cudaStream_t)0, seed, trial, 1, rng_mode, tp, &dout, nullptr, lg);
+  if (rc) return rc;
+  int32_t nlog = 0;
+  CK(cudaMemcpy(&nlog, lg.count, 4, cudaMemcpyDeviceToHost));
+  *count = nlog;
+  size_t m = (size_t)(nlog < cap ? nlog : cap);
+  if (m) {
+    CK(cudaMemcpy(day, lg.day, 4 * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(asset, lg.asset, 4 * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(action, lg.action, 4 * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(shares, lg.shares, 8 * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(price, lg.price, 8 * m, cudaMemcpyDeviceToHost));
+  }
+  return LETF_OK;
+}
+
+int letf_nearest_psd3(const double in[9], double out[9]) {
+  if (!in || !out) return fail(LETF_ERR_INVALID, "null argument");
+  double a[3][3], v[3][3], w[3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = 0.5 * (in[i * 3 + j] + in[j * 3 + i]);
+  jacobi3(a, v, w);
+  for (int i = 0; i < 3; i++) if (w[i] < 1e-8) w[i] = 1e-8;       // utils.py:45
+  double m[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += v[i][k] * w[k] * v[j][k];
+    m[i][j] = s;
+  }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[i * 3 + j] = m[i][j] / (sqrt(m[i][i]) * sqrt(m[j][j]));
+  return LETF_OK;
+}
+
+}  // extern "C"

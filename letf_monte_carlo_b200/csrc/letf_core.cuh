@@ -1,0 +1,828 @@
+// letf_core.cuh — one Monte Carlo trial, streamed day by day with all state in registers
+// (plus three per-thread history rings and, for moment matching, a per-thread return scratch
+// in HBM).  This is the body of the fused kernel; reference call stack: SURVEY.md 3.2.
+//
+//   regime path        engine.py:255-302          RegimeGen
+//   joint-t GARCH/DCC  calibration.py:480-590     JointState::step
+//   parametric-t       engine.py:81-97
+//   VIX / IRX          engine.py:100-123
+//   stress + jumps     calibration.py:787-830, engine.py:502-512
+//   financing          engine.py:320-349, calibration.py:833-857, utils.py:169-216
+//   tracking error     engine.py:157-203
+//   ETF composition    engine.py:360-420
+//   frame + validity   engine.py:537-562
+//   strategies         strategy.py:55-1277        StrategyBank
+//   per-trial stats    engine.py:578-590
+#pragma once
+#include "letf_params.cuh"
+#include "letf_rolling.cuh"
+
+namespace letf {
+
+template <typename R, int NS> struct KArgs {
+  DevParams<R, NS> p;
+  LetfTape tape;            // device pointers (tape / record modes)
+  LetfOutputs out;          // device pointers
+  LetfSeries series;        // MARKET == 3 only: caller-supplied frame (run_strategy_fixed seam)
+  uint64_t seed;
+  int64_t first_trial, n_trials, tape_first;
+  int rng_mode;
+  int pad;
+  R* xscr;                  // [G][3][nthreads]   moment-matching scratch
+  R* ringP;                 // [kRingP][nthreads]
+  R* ringS;                 // [kRingS][nthreads]
+  R* ringA;                 // [kRingA][nthreads]
+  int64_t nthreads;
+  // optional journal log of ONE trial / ONE strategy (Trade_List replay)
+  int64_t log_trial; int log_strategy; int log_cap;
+  int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
+};
+
+LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+#define TM_HAS(t) ((TM >> (t)) & 1u)
+constexpr int kMarketSeries = 3;
+constexpr uint32_t kVolTypes = (1u << LETF_ST_VOL_TARGETING) | (1u << LETF_ST_ADAPTIVE_VOL) | (1u << LETF_ST_DOWNSIDE_VOL) |
+                               (1u << LETF_ST_CONVEX_VOL) | (1u << LETF_ST_VOL_VELOCITY) | (1u << LETF_ST_VOL_MOM) |
+                               (1u << LETF_ST_SKEW_CONVEX) | (1u << LETF_ST_META_ENSEMBLE) | (1u << LETF_ST_REGIME_ASYMMETRIC) |
+                               (1u << LETF_ST_SKEW_KELLY) | (1u << LETF_ST_MOM_VOL_CONV) | (1u << LETF_ST_CONVICTION);
+
+// ------------------------------------------------------------------------------------------
+// max-drawdown tracker.  fp64: the reference's formula on the equity curve (engine.py:581-586).
+// fp32: q = W / running_max evolves as q <- min(1, q * (1 + ret)), no division, no fp64.
+template <typename R> struct Drawdown;
+template <> struct Drawdown<double> {
+  double rm, mn;
+  LETF_HD void init(double w0) { rm = w0; mn = 0.0; }
+  LETF_HD void step(double w, double) {
+    if (w > rm) rm = w;
+    double dd = (w - rm) / (rm > 0 ? rm : 1.0);
+    if (dd < mn) mn = dd;
+  }
+  LETF_HD double value() const { return ::fabs(mn); }
+};
+template <> struct Drawdown<float> {
+  float q, qmin;
+  LETF_HD void init(double) { q = 1.0f; qmin = 1.0f; }
+  LETF_HD void step(double, float growth) {
+    q = fminf(1.0f, q * growth);
+    qmin = fminf(qmin, q);
+  }
+  LETF_HD double value() const { return (double)(1.0f - qmin); }
+};
+
+// ------------------------------------------------------------------------------------------
+template <typename R, int NS, int MARKET, bool TAPEIO, uint32_t TM>
+struct Trial {
+  typedef Mth<R> M;
+  static constexpr bool EXACT = sizeof(R) == 8;
+  static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
+  static constexpr bool HAS_VOL = (TM & kVolTypes) != 0;
+  static constexpr bool HAS_SMA200 = TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND) || TM_HAS(LETF_ST_COMPOSITE) ||
+                                     TM_HAS(LETF_ST_ADAPTIVE_VOL) || TM_HAS(LETF_ST_CONVEX_VOL) || TM_HAS(LETF_ST_META_ENSEMBLE);
+  static constexpr bool HAS_SMA100 = TM_HAS(LETF_ST_CONVICTION);
+  static constexpr bool HAS_RSI = TM_HAS(LETF_ST_COMPOSITE);
+  static constexpr bool HAS_MOM = TM_HAS(LETF_ST_MOM_VOL_CONV) || TM_HAS(LETF_ST_CONVICTION);
+  static constexpr bool HAS_V5 = TM_HAS(LETF_ST_VOL_VELOCITY) || TM_HAS(LETF_ST_META_ENSEMBLE) || TM_HAS(LETF_ST_REGIME_ASYMMETRIC) || TM_HAS(LETF_ST_CONVICTION);
+  static constexpr bool HAS_V10 = TM_HAS(LETF_ST_MOM_VOL_CONV);
+  static constexpr bool HAS_V20 = TM_HAS(LETF_ST_VOL_TARGETING) || TM_HAS(LETF_ST_ADAPTIVE_VOL) || TM_HAS(LETF_ST_CONVEX_VOL) ||
+                                  TM_HAS(LETF_ST_VOL_VELOCITY) || TM_HAS(LETF_ST_VOL_MOM) || TM_HAS(LETF_ST_SKEW_CONVEX) ||
+                                  TM_HAS(LETF_ST_META_ENSEMBLE) || TM_HAS(LETF_ST_SKEW_KELLY);
+  static constexpr bool HAS_V60 = TM_HAS(LETF_ST_REGIME_ASYMMETRIC) || TM_HAS(LETF_ST_MOM_VOL_CONV) || TM_HAS(LETF_ST_CONVICTION);
+  static constexpr bool HAS_DV20 = TM_HAS(LETF_ST_DOWNSIDE_VOL) || TM_HAS(LETF_ST_META_ENSEMBLE) || TM_HAS(LETF_ST_SKEW_KELLY) || TM_HAS(LETF_ST_CONVICTION);
+  static constexpr bool HAS_SKEW = TM_HAS(LETF_ST_SKEW_CONVEX) || TM_HAS(LETF_ST_SKEW_KELLY);
+  static constexpr bool HAS_MEAN60 = TM_HAS(LETF_ST_SKEW_KELLY);
+  static constexpr bool HAS_VOLMOM = TM_HAS(LETF_ST_VOL_MOM);
+  static constexpr bool NEED_RINGP = HAS_SMA200 || HAS_SMA100 || HAS_RSI;
+  static constexpr bool NEED_RINGS = HAS_MOM;
+  static constexpr bool NEED_RINGA = HAS_VOL;
+
+  const KArgs<R, NS>& ka;
+  const DevParams<R, NS>& p;
+  int64_t k, col, lane, tcol, nt;
+  bool use_tape, rec, anti;
+  RngKey key;
+  uint32_t flags;
+
+  LETF_HD Trial(const KArgs<R, NS>& a, int64_t trial, int64_t column, int64_t ln)
+      : ka(a), p(a.p), k(trial), col(column), lane(ln) {
+    int64_t sim_id = p.antithetic ? (k & ~(int64_t)1) : k;
+    anti = p.antithetic && (k & 1);
+    tcol = (p.antithetic ? (k >> 1) : k) - a.tape_first;
+    nt = a.tape.n_tapes;
+    use_tape = TAPEIO && a.rng_mode == LETF_RNG_TAPE;
+    rec = TAPEIO && a.rng_mode == LETF_RNG_PHILOX_RECORD;
+    key.k0 = (uint32_t)a.seed; key.k1 = (uint32_t)(a.seed >> 32);
+    key.t0 = (uint32_t)sim_id; key.t1 = (uint32_t)((uint64_t)sim_id >> 32);
+    flags = 0;
+  }
+
+  // ---- tape helpers -------------------------------------------------------------------
+  LETF_HD R tp_get(const double* a, int64_t row) const { return (R)a[row * nt + tcol]; }
+  LETF_HD void tp_put(double* a, int64_t row, R v) const { a[row * nt + tcol] = (double)v; }
+
+  // ---- regime path ---------------------------------------------------------------------
+  struct RegimeGen { int cur, left, ks; };
+  LETF_HD void regime_init(RegimeGen& g) const { g.cur = 0; g.left = 0; g.ks = 0; }
+  LETF_HD int draw_spell(int ks, int cur) {
+    const int G = p.T + p.buffer;
+    int spell;
+    if (use_tape) {
+      if (ks >= ka.tape.max_spells) { flags |= LETF_FLAG_SPELL_OVERFLOW; spell = G; }
+      else spell = ka.tape.spells[(int64_t)ks * nt + tcol];
+    } else {
+      U4 b = rng_block(key, (uint32_t)ks, STREAM_SPELL);
+      if (p.n_dur[cur] > 0) spell = p.dur[cur][mulhi32(b.y, (uint32_t)p.n_dur[cur])];
+      else {
+        R q = M::log_(M::u01(b.x)) / p.log_pstay[cur];   // inverse CDF of the geometric dwell time
+        spell = q < (R)G ? (int)q + 1 : G;
+      }
+      if (rec && ks < ka.tape.max_spells) ka.tape.spells[(int64_t)ks * nt + tcol] = spell;
+    }
+    return spell < 1 ? 1 : spell;
+  }
+  LETF_HD int regime_next(RegimeGen& g) {
+    if (MARKET == LETF_MARKET_NORMAL) return 0;
+    if (g.left == 0) {
+      if (g.ks > 0 && p.flip[g.cur]) g.cur ^= 1;
+      g.left = draw_spell(g.ks, g.cur);
+      g.ks++;
+    }
+    g.left--;
+    return g.cur;
+  }
+
+  // ---- market generators -----------------------------------------------------------------
+  struct JointState { R h[3], q[6], pz[3]; int prev_reg; };
+
+  // one generated day of the raw (pre moment-matching) underlying returns x[3] = SPY, QQQ, TLT.
+  // Also returns the two "phase-2" normals of the day (VIX noise, IRX noise) when WANT_AUX.
+  template <bool WANT_X, bool WANT_AUX>
+  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n) {
+    R z0 = 0, z1 = 0, z2 = 0, nchi = 0;
+    uint32_t cw0 = 0, cw1 = 0;
+    if (use_tape) {
+      if (WANT_X) { z0 = tp_get(ka.tape.x, (int64_t)g * 3 + 0); z1 = tp_get(ka.tape.x, (int64_t)g * 3 + 1); z2 = tp_get(ka.tape.x, (int64_t)g * 3 + 2); }
+      if (WANT_AUX && MARKET != LETF_MARKET_NORMAL) { vix_n = tp_get(ka.tape.vix_n, g); irx_n = tp_get(ka.tape.irx_n, g); }
+    } else {
+      if (WANT_X && MARKET != LETF_MARKET_PARAM_T) {
+        U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
+        M::box_muller(b0.x, b0.y, z0, z1);
+        M::box_muller(b0.z, b0.w, z2, nchi);
+      }
+      if (WANT_X && MARKET == LETF_MARKET_PARAM_T) {
+        for (int c = 0; c < 3; c++) {
+          U4 b = rng_block(key, (uint32_t)g, STREAM_PT0 + c);
+          R t = student_t_block<R>(b, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
+          if (c == 0) z0 = t; else if (c == 1) z1 = t; else z2 = t;
+        }
+      }
+      if (MARKET != LETF_MARKET_NORMAL && (WANT_AUX || (WANT_X && MARKET == LETF_MARKET_JOINT_T))) {
+        U4 b1 = rng_block(key, (uint32_t)g, STREAM_MKT1);
+        if (WANT_AUX) M::box_muller(b1.x, b1.y, vix_n, irx_n);
+        cw0 = b1.z; cw1 = b1.w;
+      }
+      if (rec) {
+        if (WANT_X) { tp_put(ka.tape.x, (int64_t)g * 3 + 0, z0); tp_put(ka.tape.x, (int64_t)g * 3 + 1, z1); tp_put(ka.tape.x, (int64_t)g * 3 + 2, z2); }
+        if (WANT_AUX && MARKET != LETF_MARKET_NORMAL) { tp_put(ka.tape.vix_n, g, vix_n); tp_put(ka.tape.irx_n, g, irx_n); }
+      }
+    }
+    if (!WANT_X) return;
+    if (MARKET == LETF_MARKET_NORMAL) {
+      x[0] = p.n_mu[0] + p.n_ch[0] * z0;
+      x[1] = p.n_mu[1] + (p.n_ch[1] * z0 + p.n_ch[2] * z1);
+      x[2] = p.n_mu[2] + (p.n_ch[3] * z0 + p.n_ch[4] * z1 + p.n_ch[5] * z2);
+    } else if (MARKET == LETF_MARKET_PARAM_T) {
+      const R* C = p.pt_chol[reg];
+      R xa = C[0] * z0 + C[1] * z1 + C[2] * z2;
+      R xb = C[3] * z0 + C[4] * z1 + C[5] * z2;
+      R xc = C[6] * z0 + C[7] * z1 + C[8] * z2;
+      x[0] = p.reg_mean[reg] + p.reg_std[reg] * xa;
+      x[1] = (R)1.15 * x[0] + (R)0.006 * xb;
+      x[2] = (R)-0.12 * x[0] + (R)0.004 * xc;
+    } else {
+      const DevJoint<R>& jp = p.joint[reg];
+      // chi-square mixing variable (calibration.py:565)
+      R u;
+      if (use_tape) u = tp_get(ka.tape.chi2, g);
+      else {
+        u = jp.nu_fast_k ? chi2_int_fast<R>(jp.nu_fast_k, cw0, cw1, nchi)
+                         : chi2_marsaglia_tsang<R>(jp.nu, nchi, cw0, key, (uint32_t)g, STREAM_MKT1);
+        if (rec) tp_put(ka.tape.chi2, g, u);
+      }
+      // GARCH / DCC recursions (calibration.py:532-548)
+      if (g == 0) {
+        for (int a = 0; a < 3; a++) js.h[a] = jp.lv[a];
+        for (int a = 0; a < 6; a++) js.q[a] = jp.rb[a];
+      } else if (reg != js.prev_reg) {
+        const R bl = (R)0.10;
+        for (int a = 0; a < 3; a++) js.h[a] = bl * jp.lv[a] + ((R)1 - bl) * js.h[a];
+        for (int a = 0; a < 6; a++) js.q[a] = bl * jp.rb[a] + ((R)1 - bl) * js.q[a];
+      } else {
+        for (int a = 0; a < 3; a++) {
+          R hn = jp.one_m_ab * jp.lv[a] + jp.alpha * (js.pz[a] * js.pz[a]) * js.h[a] + jp.beta * js.h[a];
+          js.h[a] = hn < (R)1e-10 ? (R)1e-10 : hn;
+        }
+        js.q[0] = jp.one_m_dcc * jp.rb[0] + jp.dcc_a * (js.pz[0] * js.pz[0]) + jp.dcc_b * js.q[0];
+        js.q[1] = jp.one_m_dcc * jp.rb[1] + jp.dcc_a * (js.pz[1] * js.pz[0]) + jp.dcc_b * js.q[1];
+        js.q[2] = jp.one_m_dcc * jp.rb[2] + jp.dcc_a * (js.pz[1] * js.pz[1]) + jp.dcc_b * js.q[2];
+        js.q[3] = jp.one_m_dcc * jp.rb[3] + jp.dcc_a * (js.pz[2] * js.pz[0]) + jp.dcc_b * js.q[3];
+        js.q[4] = jp.one_m_dcc * jp.rb[4] + jp.dcc_a * (js.pz[2] * js.pz[1]) + jp.dcc_b * js.q[4];
+        js.q[5] = jp.one_m_dcc * jp.rb[5] + jp.dcc_a * (js.pz[2] * js.pz[2]) + jp.dcc_b * js.q[5];
+      }
+      js.prev_reg = reg;
+      R zz[3];
+      R sh0 = M::sqrt_(js.h[0]), sh1 = M::sqrt_(js.h[1]), sh2 = M::sqrt_(js.h[2]);
+      if (EXACT) {
+        // cov_t = outer(sqrt h) * Q / outer(d, d), then its Cholesky factor (calibration.py:556-561)
+        R d0 = M::sqrt_(rmax(js.q[0], (R)1e-12)), d1 = M::sqrt_(rmax(js.q[2], (R)1e-12)), d2 = M::sqrt_(rmax(js.q[5], (R)1e-12));
+        R c00 = (sh0 * sh0) * (js.q[0] / (d0 * d0)), c10 = (sh1 * sh0) * (js.q[1] / (d1 * d0));
+        R c11 = (sh1 * sh1) * (js.q[2] / (d1 * d1)), c20 = (sh2 * sh0) * (js.q[3] / (d2 * d0));
+        R c21 = (sh2 * sh1) * (js.q[4] / (d2 * d1)), c22 = (sh2 * sh2) * (js.q[5] / (d2 * d2));
+        R l00 = M::sqrt_(c00), l10 = c10 / l00, l20 = c20 / l00;
+        R l11 = M::sqrt_(c11 - l10 * l10), l21 = (c21 - l20 * l10) / l11;
+        R l22 = M::sqrt_(c22 - l20 * l20 - l21 * l21);
+        zz[0] = l00 * z0;
+        zz[1] = l10 * z0 + l11 * z1;
+        zz[2] = l20 * z0 + l21 * z1 + l22 * z2;
+      } else {
+        // same factor written as diag(sqrt h) * chol(R_t) with R_t unit-diagonal: fewer operations
+        R i0 = M::rsqrt_(rmax(js.q[0], (R)1e-12)), i1 = M::rsqrt_(rmax(js.q[2], (R)1e-12)), i2 = M::rsqrt_(rmax(js.q[5], (R)1e-12));
+        R r10 = js.q[1] * i1 * i0, r20 = js.q[3] * i2 * i0, r21 = js.q[4] * i2 * i1;
+        R l11 = M::sqrt_(rmax((R)1 - r10 * r10, (R)0));
+        R l21 = M::div_(r21 - r20 * r10, rmax(l11, (R)1e-20));
+        R l22 = M::sqrt_(rmax((R)1 - r20 * r20 - l21 * l21, (R)0));
+        zz[0] = sh0 * z0;
+        zz[1] = sh1 * (r10 * z0 + l11 * z1);
+        zz[2] = sh2 * (r20 * z0 + l21 * z1 + l22 * z2);
+      }
+      if (anti) { zz[0] = -zz[0]; zz[1] = -zz[1]; zz[2] = -zz[2]; }
+      R scale = M::sqrt_(M::div_(jp.nu, rmax(u, (R)1e-12)));
+      for (int a = 0; a < 3; a++) {
+        R xx = jp.mu[a] + zz[a] * scale;
+        R xc = clipr(xx, (R)-0.95, (R)4.0);
+        js.pz[a] = (xc - jp.mu[a]) / M::sqrt_(rmax(js.h[a], (R)1e-10));
+        x[a] = xc;
+      }
+    }
+  }
+
+  // ---- strategy bank ------------------------------------------------------------------------
+  struct Signals {          // state "as of yesterday" (pandas .shift(1)) unless noted
+    RollSum<R, EXACT> sma200, sma100, gain14, loss14, mom126, mean60;
+    RollVar<R, EXACT> v5, v10, v20, v60, dv20;
+    RollSkew<R, EXACT> sk60;
+    R volhist[6];           // shifted 20-day vol series, newest first (pct_change(5))
+    R P_prev, vix_prev;
+    int cP, cS, cA;         // ring cursors = day index modulo ring depth
+  };
+
+  struct Slot {
+    double W;               // equity (always fp64: 7 560 multiplicative steps)
+    Drawdown<R> dd;
+    R aux;                  // prev_alloc | position | composite state
+    int trades;
+  };
+  struct SlotJ { double pos[3]; double vol; int cnt; };
+
+  LETF_HD void jlog(SlotJ& j, int which, int s, int day, int asset, R new_alloc, double pv, R price) {
+    // trade.py:20-73
+    if (price <= (R)0) return;
+    double target = (double)new_alloc * pv / (double)price;
+    double ch = target - j.pos[which];
+    if (::fabs(ch) < 0.001) return;
+    double sh = ch > 0 ? ch : ::fabs(ch);
+    if (TAPEIO && ka.log_count && ka.log_trial == k && ka.log_strategy == s) {
+      int n = *ka.log_count;
+      if (n < ka.log_cap) {
+        ka.log_day[n] = day; ka.log_asset[n] = asset; ka.log_action[n] = ch > 0 ? 1 : -1;
+        ka.log_shares[n] = sh; ka.log_price[n] = (double)price;
+      }
+      *ka.log_count = n + 1;
+    }
+    j.cnt++;
+    j.vol += sh * (double)price;
+    j.pos[which] = target;
+  }
+
+  // run the whole trial ---------------------------------------------------------------------
+  LETF_HD void run() {
+    const int G = p.T + p.buffer;
+    const int64_t nth = ka.nthreads;
+    const R V = (R)15.874507866387544;   // sqrt(252)
+
+    // ---- start offset (random_start.py:33-57)
+    int so = 0;
+    if (MARKET != kMarketSeries && p.random_start) {
+      if (use_tape) so = ka.tape.start_offset[tcol];
+      else {
+        U4 b = rng_block(key, 0, STREAM_START);
+        so = p.min_offset + (int)mulhi32(b.x, (uint32_t)p.offset_range);
+        if (rec) ka.tape.start_offset[tcol] = so;
+      }
+    }
+
+    // ---- pass 1 (moment matching only): raw joint returns -> scratch, column means (calibration.py:579-588)
+    R shift[3] = {(R)0, (R)0, (R)0};
+    const bool two_pass = MARKET == LETF_MARKET_JOINT_T && p.mm;
+    const int T = MARKET == kMarketSeries ? ka.series.sim_days : p.T;
+    JointState js;
+    js.prev_reg = 0;
+    for (int a = 0; a < 3; a++) { js.h[a] = 0; js.pz[a] = 0; }
+    for (int a = 0; a < 6; a++) js.q[a] = 0;
+    if (two_pass && G > 0) {
+      RegimeGen rg; regime_init(rg);
+      R sum[3] = {0, 0, 0}, cmp[3] = {0, 0, 0};
+      for (int g = 0; g < G; g++) {
+        int reg = regime_next(rg);
+        R x[3], d0, d1;
+        market_day<true, false>(g, reg, js, x, d0, d1);
+        for (int a = 0; a < 3; a++) {
+          ka.xscr[((int64_t)g * 3 + a) * nth + lane] = x[a];
+          R y = x[a] - cmp[a], t = sum[a] + y;      // Kahan: stays within an ulp of numpy's pairwise mean
+          cmp[a] = (t - sum[a]) - y; sum[a] = t;
+        }
+      }
+      for (int a = 0; a < 3; a++) shift[a] = (p.mm_theo[a] - sum[a] / (R)G) * (R)0.1;
+    }
+
+    // ---- pass 2 state
+    RegimeGen rg; regime_init(rg);
+    R vix = p.const_vix;
+    // stress / tracking-error / price state
+    R liq = 0, cred = 0;
+    R te_prev[kAssets], bias[kAssets], cp[kAssets];
+    for (int a = 0; a < kAssets; a++) { te_prev[a] = 0; bias[a] = 0; cp[a] = 1; }
+    double cp_tlt = 1.0;
+    R vmin = (R)INFINITY, vmax = (R)-INFINITY;
+    bool bad = false;
+    int reg_days1 = 0, jump_days = 0;
+
+    Slot slot[NS];
+    SlotJ sj[JOURNAL ? NS : 1];
+    R pv[kPortMax][kAssets];
+    for (int s = 0; s < NS; s++) { slot[s].W = (double)p.W0; slot[s].dd.init((double)p.W0); slot[s].aux = 0; slot[s].trades = 0; }
+    if (JOURNAL) for (int s = 0; s < NS; s++) { sj[s].pos[0] = sj[s].pos[1] = sj[s].pos[2] = 0; sj[s].vol = 0; sj[s].cnt = 0; }
+    for (int s = 0; s < NS; s++)
+      if (TM_HAS(LETF_ST_PORTFOLIO) && s < p.n_strat && p.strat[s].type == LETF_ST_PORTFOLIO)
+        for (int a = 0; a < kAssets; a++) pv[p.strat[s].port][a] = p.W0 * p.strat[s].w[a];
+    Signals sg;
+    sg.sma200.init(); sg.sma100.init(); sg.gain14.init(); sg.loss14.init(); sg.mom126.init(); sg.mean60.init();
+    sg.v5.init(); sg.v10.init(); sg.v20.init(); sg.v60.init(); sg.dv20.init(); sg.sk60.init();
+    for (int i = 0; i < 6; i++) sg.volhist[i] = nan_<R>();
+    sg.P_prev = nan_<R>(); sg.vix_prev = nan_<R>(); sg.cP = sg.cS = sg.cA = 0;
+
+    // ---- burn-in: generated days before the window (only the VIX recursion consumes them)
+    for (int g = 0; g < so; g++) {
+      int reg = regime_next(rg);
+      R x[3] = {0, 0, 0}, vn = 0, in = 0;
+      if (two_pass) {
+        market_day<false, true>(g, reg, js, x, vn, in);
+        x[0] = ka.xscr[((int64_t)g * 3 + 0) * nth + lane] + shift[0];
+      } else {
+        market_day<true, true>(g, reg, js, x, vn, in);
+      }
+      if (MARKET != LETF_MARKET_NORMAL) vix = vix_step(g, reg, vix, x[0], vn);
+    }
+
+    // ---- the simulated window
+    for (int i = 0; i < T; i++) {
+      const int g = so + i;
+      const int64_t sn = ka.series.n_paths;
+      const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
+      R x[3] = {0, 0, 0}, vn = 0, in = 0;
+      if (MARKET == kMarketSeries) {
+        vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
+        x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
+      } else if (two_pass) {
+        market_day<false, true>(g, reg, js, x, vn, in);
+        for (int a = 0; a < 3; a++) x[a] = ka.xscr[((int64_t)g * 3 + a) * nth + lane] + shift[a];
+      } else {
+        market_day<true, true>(g, reg, js, x, vn, in);
+      }
+      R rf = p.const_rf;
+      if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
+        vix = vix_step(g, reg, vix, x[0], vn);
+        R irx = clipr(p.irx_base[reg] + ((R)0 + (R)0.5 * in), (R)0, (R)15);   // engine.py:117-123
+        rf = clipr(irx, (R)0, (R)20) / (R)100;                                // engine.py:516
+      }
+      R spy = x[0], qqq = x[1], tlt = x[2];
+      if (!isfinite_(spy) || !isfinite_(qqq) || !isfinite_(tlt)) flags |= LETF_FLAG_NONFINITE_RET;
+      if (!isfinite_(vix) || vix <= (R)0) flags |= LETF_FLAG_BAD_VIX;
+      reg_days1 += reg;
+      vmin = rmin(vmin, vix); vmax = rmax(vmax, vix);
+
+      // ---- latent stress + jump overlay (calibration.py:787-830, engine.py:502-512)
+      if (MARKET != kMarketSeries && p.has_stress) {
+        const DevStress<R>& sp = p.stress[reg];
+        R jump = 0, sign = 1;
+        if (i == 0) {
+          liq = sp.liq_mu; cred = sp.cr_mu;      // no draws on the first day (calibration.py:798-803)
+          if (rec) { tp_put(ka.tape.liq_n, 0, 0); tp_put(ka.tape.cred_n, 0, 0); tp_put(ka.tape.jump_u, 0, 1); tp_put(ka.tape.jump_t, 0, 0); tp_put(ka.tape.sign, 0, 1); }
+        } else {
+          R ln, cn, ju;
+          U4 b; b.x = b.y = b.z = b.w = 0;
+          if (use_tape) { ln = tp_get(ka.tape.liq_n, i); cn = tp_get(ka.tape.cred_n, i); ju = tp_get(ka.tape.jump_u, i); sign = tp_get(ka.tape.sign, i); }
+          else {
+            b = rng_block(key, (uint32_t)g, STREAM_STRESS);
+            M::box_muller(b.x, b.y, ln, cn);
+            ju = (R)(b.z >> 8) * (R)(1.0 / 16777216.0);    // U[0,1) on a 24-bit grid, like numpy's float32 path
+            sign = (b.w & 1u) ? (R)1 : (R)-1;
+            if (rec) { tp_put(ka.tape.liq_n, i, ln); tp_put(ka.tape.cred_n, i, cn); tp_put(ka.tape.jump_u, i, ju); tp_put(ka.tape.sign, i, sign); }
+          }
+          liq = clipr(sp.liq_mu + sp.liq_phi * (liq - sp.liq_mu) + ((R)0 + sp.liq_sigma * ln), (R)0, (R)3);
+          cred = clipr(sp.cr_mu + sp.cr_phi * (cred - sp.cr_mu) + ((R)0 + sp.cr_sigma * cn), (R)0, (R)3);
+          R vamp = rmax((vix - (R)25) / (R)30, (R)0);
+          R jp = clipr(sp.jbase + (R)0.008 * vamp + (R)0.003 * liq, (R)0, (R)0.01);
+          if (ju < jp || rec) {
+            // record mode draws the jump size every day: antithetic twins share a tape column but
+            // may jump on different days, so the column must hold the variate either twin would use
+            R t5;
+            if (use_tape) t5 = tp_get(ka.tape.jump_t, i);
+            else {
+              U4 bj = rng_block(key, (uint32_t)g, STREAM_JUMP);
+              t5 = student_t_block<R>(bj, (R)5, 5, key, (uint32_t)g, STREAM_JUMP);
+              if (rec) tp_put(ka.tape.jump_t, i, t5);
+            }
+            if (ju < jp) {
+              jump = M::abs_(t5) * sp.jscale;
+              if (jump > (R)0) jump_days++;
+            }
+          }
+        }
+        R sjv = jump * sign;
+        spy = clipr(spy - sjv, (R)-0.95, (R)3.0);
+        qqq = clipr(qqq - (R)1.12 * sjv, (R)-0.95, (R)4.0);
+      }
+
+      // ---- financing spread shared by all assets (engine.py:328-342, calibration.py:833-857)
+      R spread_common = 0;
+      if (MARKET != kMarketSeries && p.has_funding) {
+        R irx_level = rf * (R)100;
+        R term = p.has_stress ? (R)1.25 - (R)1.1 * clipr(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
+        R tnx = irx_level + term;
+        R sv = rmax(vix - (R)20, (R)0);
+        R inv = rmax(-(tnx - irx_level), (R)0);
+        R spd = p.f_base + p.f_vix * sv + p.f_inv * inv;
+        if (p.has_stress) spd += p.f_liq * clipr(liq, (R)0, (R)3) + p.f_cr * clipr(cred, (R)0, (R)3);
+        spread_common = clipr(spd, p.f_min, p.f_max);
+      }
+      const R vmult = clipr(M::sqrt_(vix / (R)20), (R)0.5, (R)1.5);
+      const R rmult = reg == 0 ? (R)1 : (R)1.15;
+
+      // ---- the six ETF layers (engine.py:360-420)
+      R ret[kAssets];
+#pragma unroll
+      for (int a = 0; a < kAssets; a++) {
+        ret[a] = 0;
+        R er;
+        if (MARKET == kMarketSeries) {
+          if (!ka.series.asset_ret[a]) continue;
+          er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
+        } else {
+          if (!((p.asset_mask >> a) & 1)) continue;
+          const DevAsset<R>& ap = p.assets[a];
+          R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
+          R u = ap.beta_applies ? ub * ap.beta : ub;
+          R spread = p.has_funding ? spread_common : ap.borrow_spread;
+          R borrow = 0;
+          if (ap.bl > (R)0) borrow = ap.bl * rmax(rf + spread, (R)0) / (R)252;
+          R lev = ap.lev * u - ap.er_daily - borrow;
+          R te_raw = 0;
+          if (i >= 1) {
+            R innov;
+            if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)a * T + i);
+            else {
+              U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + a);
+              innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + a);
+              if (rec) tp_put(ka.tape.te_t, (int64_t)a * T + i, innov);
+            }
+            innov *= ap.te_base * vmult * rmult * (R)1;
+            R ds = u < (R)0 ? ap.te_down : (R)0.98;
+            R mm = ((R)1 + (R)0.3 * M::abs_(u)) * ds;
+            te_raw = ap.te_rho * te_prev[a] + ap.te_arw * innov * mm;
+          } else if (rec) tp_put(ka.tape.te_t, (int64_t)a * T, 0);
+          te_prev[a] = te_raw;
+          const R alpha = (R)(2.0 / 127.0);
+          bias[a] = alpha * te_raw + ((R)1 - alpha) * bias[a];
+          R te = te_raw - bias[a];
+          if (ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(te / ap.te_clip);
+          er = clipr(lev + te, (R)-0.999, (R)10);
+        }
+        ret[a] = er;
+        cp[a] = i == 0 ? ((R)1 + er) : cp[a] * ((R)1 + er);
+        R pr = cp[a] * (R)100;
+        if (!isfinite_(er) || !isfinite_(pr) || !(pr > (R)0)) bad = true;
+      }
+      {
+        cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
+        if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
+      }
+      const R cash = p.cash_daily[reg];
+      const R Pspy = cp[4] * (R)100;
+
+      // ---- signals as of yesterday, then roll the windows forward with today's values
+      R s_sma200 = nan_<R>(), s_sma200f = nan_<R>(), s_sma100 = nan_<R>(), s_rsi = nan_<R>(), s_mom = nan_<R>();
+      R s_v5 = nan_<R>(), s_v10 = nan_<R>(), s_v20 = nan_<R>(), s_v20f = nan_<R>(), s_v60 = nan_<R>();
+      R s_dv20 = nan_<R>(), s_dv20f = nan_<R>(), s_sk = nan_<R>(), s_mean60 = nan_<R>(), s_vm = nan_<R>(), s_v20_today = nan_<R>();
+      const R P_prev = sg.P_prev, vix_prev = sg.vix_prev;
+      const R ra = ret[p.sig_asset];
+      if (i >= 1) {
+        if (HAS_SMA200) { s_sma200 = sg.sma200.mean(1); s_sma200f = sg.sma200.mean(200); }
+        if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
+        if (HAS_RSI) {
+          R gm = sg.gain14.mean(14), lm = sg.loss14.mean(14);
+          R rs = gm / lm;
+          s_rsi = (R)100 - ((R)100 / ((R)1 + rs));
+        }
+        if (HAS_MOM) s_mom = sg.mom126.sum(1);
+        if (HAS_V5) s_v5 = sg.v5.stdev(1) * V;
+        if (HAS_V10) s_v10 = sg.v10.stdev(1) * V;
+        if (HAS_V20) { s_v20 = sg.v20.stdev(1) * V; s_v20f = sg.v20.stdev(20) * V; }
+        if (HAS_V60) s_v60 = sg.v60.stdev(1) * V;
+        if (HAS_DV20) { s_dv20 = sg.dv20.stdev(1) * V; s_dv20f = sg.dv20.stdev(20) * V; }
+        if (HAS_SKEW) s_sk = sg.sk60.skew(1);
+        if (HAS_MEAN60) s_mean60 = sg.mean60.mean(1) * (R)252;
+      }
+      if (HAS_VOLMOM) {
+        // vol_slow.pct_change(5): shifted 20-day vol today vs five rows earlier
+        for (int q = 5; q >= 1; q--) sg.volhist[q] = sg.volhist[q - 1];
+        sg.volhist[0] = s_v20;
+        s_vm = sg.volhist[0] / sg.volhist[5] - (R)1;
+      }
+      // roll forward (pandas: removals first, then the new observation)
+      if (NEED_RINGP) {
+        R* ring = ka.ringP + lane;
+        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(ring[(int64_t)sg.cP * nth]); sg.sma200.add(Pspy); }
+        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(ring[(int64_t)c * nth]); } sg.sma100.add(Pspy); }
+        if (HAS_RSI) {
+          if (i >= 14) {
+            R dg = 0, dl = -(R)0;
+            if (i >= 15) {
+              int c1 = sg.cP - 14; if (c1 < 0) c1 += kRingP;
+              int c2 = sg.cP - 15; if (c2 < 0) c2 += kRingP;
+              R dlt = ring[(int64_t)c1 * nth] - ring[(int64_t)c2 * nth];
+              dg = dlt > (R)0 ? dlt : (R)0;
+              dl = -(dlt < (R)0 ? dlt : (R)0);
+            }
+            sg.gain14.remove(dg); sg.loss14.remove(dl);
+          }
+          R dlt = i == 0 ? nan_<R>() : Pspy - P_prev;
+          sg.gain14.add(dlt > (R)0 ? dlt : (R)0);
+          sg.loss14.add(-(dlt < (R)0 ? dlt : (R)0));
+        }
+        ring[(int64_t)sg.cP * nth] = Pspy;
+        sg.cP = sg.cP + 1 == kRingP ? 0 : sg.cP + 1;
+      }
+      if (NEED_RINGS) {
+        R* ring = ka.ringS + lane;
+        if (i >= 126) sg.mom126.remove(ring[(int64_t)sg.cS * nth]);
+        sg.mom126.add(ret[4]);
+        ring[(int64_t)sg.cS * nth] = ret[4];
+        sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
+      }
+      if (NEED_RINGA) {
+        R* ring = ka.ringA + lane;
+        R r60 = 0, r20 = 0, r10 = 0, r5 = 0;
+        if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[(int64_t)sg.cA * nth];
+        if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[(int64_t)c * nth]; }
+        if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[(int64_t)c * nth]; }
+        if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[(int64_t)c * nth]; }
+        if (HAS_V5) { if (i >= 5) sg.v5.remove(r5); sg.v5.add(ra); }
+        if (HAS_V10) { if (i >= 10) sg.v10.remove(r10); sg.v10.add(ra); }
+        if (HAS_V20) { if (i >= 20) sg.v20.remove(r20); sg.v20.add(ra); }
+        if (HAS_V60) { if (i >= 60) sg.v60.remove(r60); sg.v60.add(ra); }
+        if (HAS_DV20) { if (i >= 20) sg.dv20.remove(r20 < (R)0 ? r20 : (R)0); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
+        if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
+        if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
+        ring[(int64_t)sg.cA * nth] = ra;
+        sg.cA = sg.cA + 1 == kRingA ? 0 : sg.cA + 1;
+        if (TM_HAS(LETF_ST_VOL_TARGETING)) s_v20_today = sg.v20.stdev(20) * V;   // strategy.py:255 (unshifted)
+      }
+      sg.P_prev = Pspy; sg.vix_prev = vix;
+
+      // ---- strategy rules (strategy.py:55-1277) + running statistics (engine.py:578-590)
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        if (s >= p.n_strat) break;
+        const DevStrategy<R>& st = p.strat[s];
+        Slot& sl = slot[s];
+        const int ty = st.type;
+        R growth = (R)1;          // W_i / W_{i-1}
+        bool act = i >= 1;        // active strategies leave equity[0] = W0
+        if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) {
+          if (ty == LETF_ST_BENCHMARK) { growth = (R)1 + ret[st.asset]; sl.W = EXACT ? (double)p.W0 * (double)cp[st.asset] : sl.W * (1.0 + (double)ret[st.asset]); }
+          else { growth = (R)1 + tlt; sl.W = EXACT ? (double)p.W0 * cp_tlt : sl.W * (1.0 + (double)tlt); }
+          act = false;
+          if (i == 0) sl.dd.init(sl.W); else sl.dd.step(sl.W, growth);
+          continue;
+        }
+        if (!act) continue;
+        R r_strat = 0;
+        if (TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND)) if (ty == LETF_ST_SMA || ty == LETF_ST_SMA_BAND) {
+          R thr = ty == LETF_ST_SMA ? s_sma200 : s_sma200 * ((R)1 - st.p[1]);
+          bool buy = P_prev >= thr, sell = P_prev < thr;
+          int pos_prev = (int)sl.aux, pos = pos_prev == 0 ? (buy ? 1 : 0) : (sell ? 0 : 1);
+          r_strat = pos == 1 ? ret[st.asset] : cash;
+          if (pos != pos_prev) {
+            sl.trades++;
+            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * p.assets[st.asset].lev * M::abs_(ret[st.asset]) + (R)0;
+          }
+          sl.aux = (R)pos;
+        }
+        if (TM_HAS(LETF_ST_PORTFOLIO)) if (ty == LETF_ST_PORTFOLIO) {
+          R* pvv = pv[st.port];
+          R total = 0;
+          for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = pvv[a] * ((R)1 + ret[a]); total += pvv[a]; }
+          double w_new = (double)total;
+          if (i % (int)st.p[0] == 0) {
+            R wt = 0, lt = 0;
+            for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) {
+              R cw = pvv[a] / total;
+              wt += M::abs_(cw - st.w[a]);
+              R tl = p.assets[a].lev, emb = (R)1;
+              if (tl > (R)1) {
+                R uu = ret[a] / tl;
+                emb = M::abs_((R)1 + tl * uu) > (R)0.01 ? tl * ((R)1 + uu) / ((R)1 + tl * uu) : tl;
+              }
+              lt += M::abs_(emb - tl) / tl * cw;
+            }
+            R turn = wt + lt;
+            if (p.apply_costs && turn > (R)0.01) { total -= turn * p.rebalance_cost * total; w_new = (double)total; }
+            for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = total * st.w[a]; sl.trades++; }
+          }
+          growth = (R)(w_new / sl.W);
+          sl.W = w_new;
+          sl.dd.step(sl.W, growth);
+          continue;
+        }
+        if (TM_HAS(LETF_ST_COMPOSITE)) if (ty == LETF_ST_COMPOSITE) {
+          int score = (P_prev > s_sma200f ? 1 : 0) + (((R)40 < s_rsi && s_rsi < (R)80) ? 1 : 0) + (vix_prev < st.p[2] ? 1 : 0);
+          int target = score == 3 ? 2 : (score == 2 ? 1 : 0);
+          r_strat = target == 2 ? ret[st.asset] : (target == 1 ? ret[st.asset2] : cash);
+          if (target != (int)sl.aux) {
+            sl.trades++;
+            if (JOURNAL && st.taxable) {
+              int ta = target == 2 ? st.asset : (target == 1 ? st.asset2 : 4);
+              // journal keyed by asset NAME in the reference: legs that alias the same ticker share a position
+              int which = ta == st.asset ? 0 : (ta == st.asset2 ? 1 : 2);
+              jlog(sj[s], which, s, i, ta, target == 0 ? (R)0 : (R)1, sl.W, cp[ta] * (R)100);
+            }
+            sl.aux = (R)target;
+          }
+        }
+        if (HAS_VOL) if ((kVolTypes >> ty) & 1u) {
+          R alloc = 0, thresh = (R)0.0001;
+          bool sticky = false, cashleg = true, skip = false;
+          switch (ty) {
+            case LETF_ST_VOL_TARGETING: {
+              R cv = s_v20_today;
+              alloc = (isnan_(cv) || cv < (R)0.01) ? (R)1 : clipr(st.p[0] / cv, (R)0.2, (R)2.0);
+              cashleg = false;
+            } break;
+            case LETF_ST_ADAPTIVE_VOL: {
+              R cv = s_v20f, cs = s_sma200f;
+              if (isnan_(cv) || isnan_(cs) || cv < (R)0.001) skip = true;
+              else alloc = clipr((P_prev > cs ? st.p[0] : st.p[1]) / cv, (R)0, (R)1);
+            } break;
+            case LETF_ST_DOWNSIDE_VOL: {
+              R dv = s_dv20f;
+              alloc = (isnan_(dv) || dv < (R)0.001) ? (R)1 : clipr(st.p[0] / dv, (R)0, (R)1.5);
+            } break;
+            case LETF_ST_CONVEX_VOL: {
+              R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
+              R al = st.p[0] / v;
+              if (P_prev > s_sma200) al = M::pow_(al, st.p[1]);
+              alloc = clipr(al, (R)0, (R)1);
+            } break;
+            case LETF_ST_VOL_VELOCITY: {
+              R ev = s_v5 > s_v20 ? s_v5 : s_v20;       // python max(vol_slow, vol_fast)
+              if (isnan_(ev) || ev < (R)0.001) ev = (R)0.5;
+              alloc = clipr(st.p[0] / ev, (R)0, (R)1);
+            } break;
+            case LETF_ST_VOL_MOM: {
+              R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
+              R al = st.p[0] / v;
+              if (!isnan_(s_vm) && s_vm < (R)-0.10) al *= (R)1.2;
+              if (!isnan_(s_vm) && s_vm > (R)0.10) al *= (R)0.7;
+              alloc = clipr(al, (R)0, (R)1);
+            } break;
+            case LETF_ST_SKEW_CONVEX: {
+              R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
+              R al = st.p[0] / v;
+              if (!isnan_(s_sk) && s_sk > (R)0) al = M::pow_(al, (R)1.3);
+              else if (!isnan_(s_sk) && s_sk < (R)-0.5) al *= (R)0.5;
+              alloc = clipr(al, (R)0, (R)1);
+            } break;
+            case LETF_ST_META_ENSEMBLE: {
+              R dv = s_dv20; if (isnan_(dv) || dv < (R)0.001) dv = (R)0.25;
+              R al = st.p[0] / dv;
+              if (P_prev > s_sma200) al = M::pow_(al, (R)1.2);
+              if (s_v5 > (R)1.5 * s_v20) al *= (R)0.5;
+              alloc = clipr(al, (R)0, (R)1);
+            } break;
+            case LETF_ST_REGIME_ASYMMETRIC: {
+              R vr = s_v5 / s_v60;
+              bool crisis = (vix > st.p[2]) || (vr > st.p[3]);
+              R tv = crisis ? st.p[1] : st.p[0];
+              alloc = (isnan_(s_v5) || s_v5 < (R)0.001) ? (R)0.5 : clipr(tv / s_v5, (R)0, (R)1.2);
+            } break;
+            case LETF_ST_SKEW_KELLY: {
+              R vol = s_v20, dv = s_dv20, sk = s_sk, mr = s_mean60;
+              if (isnan_(vol) || vol < (R)0.001) vol = (R)0.25;
+              if (isnan_(dv) || dv < (R)0.001) dv = vol * (R)0.6;
+              if (isnan_(sk)) sk = 0;
+              if (isnan_(mr)) mr = (R)0.08;
+              R ev, pen;
+              if (sk < (R)-0.5) { ev = dv * (R)1.5; pen = (R)0.6; }
+              else if (sk < (R)0) { ev = dv * (R)1.2; pen = (R)0.8; }
+              else if (sk > (R)0.5) { ev = vol * (R)0.9; pen = (R)1.2; }
+              else { ev = vol; pen = (R)1; }
+              R ks = (R)1;
+              if (ev > (R)0.01) { ks = (mr - (R)0.03) / (ev * ev); ks = ks * st.p[3]; ks = clipr(ks, (R)0.2, (R)2.0); }
+              alloc = clipr((st.p[0] / ev) * pen * (ks / (R)1.5), (R)0, (R)1.5);
+            } break;
+            case LETF_ST_MOM_VOL_CONV: {
+              R mom = s_mom, vf = s_v10, vs = s_v60;
+              if (isnan_(mom)) mom = 0;
+              if (isnan_(vf) || vf < (R)0.001) vf = (R)0.30;
+              if (isnan_(vs) || vs < (R)0.001) vs = (R)0.25;
+              R mmul = mom > st.p[4] ? (R)1.3 : (mom > (R)0 ? (R)1.0 : (R)0.5);
+              R ratio = vf / vs, vm, ev;
+              if (ratio < (R)0.8) { vm = (R)1.2; ev = vf; } else if (ratio > (R)1.3) { vm = (R)0.6; ev = vf; } else { vm = (R)1.0; ev = vs; }
+              alloc = clipr(st.p[0] * (mmul * vm) / ev, (R)0, (R)1.5);
+            } break;
+            case LETF_ST_CONVICTION: {
+              R mom = s_mom, dv = s_dv20, vf = s_v5, vs = s_v60;
+              if (isnan_(mom)) mom = 0;
+              if (isnan_(dv) || dv < (R)0.001) dv = (R)0.20;
+              if (isnan_(vf) || vf < (R)0.001) vf = (R)0.30;
+              if (isnan_(vs) || vs < (R)0.001) vs = (R)0.25;
+              R ms = mom > (R)0.15 ? (R)1.0 : (mom > (R)0.05 ? (R)0.7 : (mom > (R)0 ? (R)0.4 : (R)0));
+              R ts = P_prev > s_sma100 ? (R)0.5 : (R)0;
+              R ratio = vf / vs;
+              R vsc = ratio < (R)0.9 ? (R)0.5 : (ratio < (R)1.2 ? (R)0.3 : (R)0);
+              R conv = ms + ts + vsc;
+              alloc = clipr((st.p[0] / dv) * ((R)0.3 + (conv * (R)0.55)), (R)0, (R)1.5);
+              thresh = st.p[4]; sticky = true;
+            } break;
+            default: break;
+          }
+          if (skip) { sl.dd.step(sl.W, (R)1); continue; }
+          R prev_alloc = sl.aux;
+          R turnover = M::abs_(alloc - prev_alloc), cost = 0;
+          if (turnover > thresh) {
+            sl.trades++;
+            if (JOURNAL && st.taxable) jlog(sj[s], 0, s, i, st.asset, alloc, sl.W, cp[st.asset] * (R)100);
+            cost = turnover * (R)0.0003;
+            sl.aux = alloc;
+          } else {
+            if (sticky) alloc = prev_alloc; else sl.aux = alloc;
+          }
+          r_strat = cashleg ? (alloc * ret[st.asset]) + (((R)1 - alloc) * cash) : ret[st.asset] * alloc;
+          if (p.apply_costs) r_strat -= cost;
+        }
+        growth = (R)1 + r_strat;
+        sl.W = sl.W * (1.0 + (double)r_strat);
+        sl.dd.step(sl.W, growth);
+      }
+    }
+
+    // ---- per-trial outputs (engine.py:578-603)
+    if (T == 0 || bad || !(vmin >= (R)5) || !(vmax <= (R)120)) flags |= LETF_FLAG_REPAIRED;
+    const int64_t N = ka.out.n_trials;
+    for (int s = 0; s < NS; s++) {
+      if (s >= p.n_strat) break;
+      double fw = T > 0 ? slot[s].W : 0.0;
+      ka.out.final_wealth[(int64_t)s * N + col] = fw;
+      ka.out.max_dd[(int64_t)s * N + col] = T > 1 ? slot[s].dd.value() : 0.0;
+      ka.out.num_trades[(int64_t)s * N + col] = slot[s].trades;
+      if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = JOURNAL ? sj[s].cnt : 0;
+      if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = JOURNAL ? sj[s].vol : 0.0;
+    }
+    if (ka.out.start_offset) ka.out.start_offset[col] = so;
+    if (ka.out.flags) ka.out.flags[col] = flags;
+    if (ka.out.regime_days) { ka.out.regime_days[col] = T - reg_days1; ka.out.regime_days[N + col] = reg_days1; }
+    if (ka.out.jump_days) ka.out.jump_days[col] = jump_days;
+  }
+
+  // VIX recursion (engine.py:100-115)
+  LETF_HD R vix_step(int g, int reg, R vix_prev, R spy_ret, R noise) const {
+    if (g == 0) return p.vix_base[reg];
+    const DevVix<R>& v = p.vix[reg];
+    R shock = rmax(-spy_ret, (R)0) / v.denom;
+    R vj = v.jump_scale * rmax((R)0, shock - v.jump_thr);
+    R cand = v.phi * vix_prev + v.drift + vj + ((R)0 + v.noise_std * noise);
+    return cand > (R)10 ? cand : (R)10;
+  }
+};
+
+#undef TM_HAS
+
+}  // namespace letf

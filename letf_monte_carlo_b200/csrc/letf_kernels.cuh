@@ -1,0 +1,68 @@
+// letf_kernels.cuh — the fused path kernel (one thread = one trial at a time, persistent
+// grid-stride over trials) and the registry that lets the C-ABI layer pick an instantiation.
+#pragma once
+#include <cuda_runtime.h>
+#include "letf_core.cuh"
+
+namespace letf {
+
+constexpr int kBlock = 128;
+
+template <typename R, int NS, int MARKET, bool TAPEIO, uint32_t TM, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) letf_path_kernel(const __grid_constant__ KArgs<R, NS> ka) {
+  const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t j = lane; j < ka.n_trials; j += ka.nthreads) {
+    Trial<R, NS, MARKET, TAPEIO, TM> t(ka, ka.first_trial + j, j, lane);
+    t.run();
+  }
+}
+
+// type-erased launcher table -----------------------------------------------------------------
+struct KernelEntry {
+  int precision;      // LETF_PREC_*
+  int ns;             // strategy slots compiled in
+  int market;         // LETF_MARKET_* (3 = caller-supplied series)
+  int tapeio;         // 1: can read / record tapes and keeps the trade journal
+  uint32_t tm;        // strategy types compiled in
+  const char* name;
+  cudaError_t (*launch)(const void* kargs, int grid, cudaStream_t st);
+  cudaError_t (*attrs)(cudaFuncAttributes* a, int* max_blocks_per_sm);
+  size_t kargs_size;
+};
+
+void register_kernel(const KernelEntry& e);
+int kernel_count();
+const KernelEntry* kernel_at(int i);
+
+template <typename R, int NS, int MARKET, bool TAPEIO, uint32_t TM, int MINB>
+struct KernelImpl {
+  static cudaError_t launch(const void* kargs, int grid, cudaStream_t st) {
+    letf_path_kernel<R, NS, MARKET, TAPEIO, TM, MINB><<<grid, kBlock, 0, st>>>(*(const KArgs<R, NS>*)kargs);
+    return cudaGetLastError();
+  }
+  static cudaError_t attrs(cudaFuncAttributes* a, int* mb) {
+    cudaError_t e = cudaFuncGetAttributes(a, letf_path_kernel<R, NS, MARKET, TAPEIO, TM, MINB>);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_path_kernel<R, NS, MARKET, TAPEIO, TM, MINB>, kBlock, 0);
+  }
+};
+
+#define LETF_INSTANTIATE(ID, R, PREC, NS, MARKET, TAPEIO, TM, MINB)                                      \
+  namespace {                                                                                            \
+  struct Reg_##ID {                                                                                      \
+    Reg_##ID() {                                                                                         \
+      typedef letf::KernelImpl<R, NS, MARKET, TAPEIO, TM, MINB> K;                                       \
+      letf::KernelEntry e = {PREC, NS, MARKET, TAPEIO ? 1 : 0, TM, #ID, &K::launch, &K::attrs,           \
+                             sizeof(letf::KArgs<R, NS>)};                                                \
+      letf::register_kernel(e);                                                                          \
+    }                                                                                                    \
+  } reg_##ID;                                                                                            \
+  }
+
+constexpr uint32_t TM_ALL = (1u << LETF_ST__COUNT) - 1u;
+constexpr uint32_t TM_BENCH = (1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT);
+// BASELINE.json config 4: benchmarks + SMA switch + 60/40 portfolio + threshold-rebalanced S19
+constexpr uint32_t TM_C4 = TM_BENCH | (1u << LETF_ST_SMA) | (1u << LETF_ST_SMA_BAND) | (1u << LETF_ST_PORTFOLIO) |
+                           (1u << LETF_ST_CONVICTION);
+
+}  // namespace letf

@@ -1,0 +1,189 @@
+// letf_params.cuh — device-side parameter block (precision R) and its host-side construction
+// from the public POD LetfParams.  Everything constant per run is folded here once.
+#pragma once
+#include "../../include/letf_b200.h"
+#include <string.h>
+#include "letf_math.cuh"
+
+namespace letf {
+
+constexpr int kAssets = LETF_N_ASSETS;
+constexpr int kPortMax = 2;      // portfolio-type strategies per launch
+constexpr int kRingP = 200;      // SPY price history   (SMA 200 / 100, RSI 14)
+constexpr int kRingS = 126;      // SPY return history  (momentum 126)
+constexpr int kRingA = 60;       // signal-asset return history (vol 5/10/20/60, skew 60)
+
+template <typename R> struct DevAsset {
+  R lev, bl, er_daily, borrow_spread, te_base, te_df, te_rho, te_arw, te_down, te_clip, beta;
+  int und, beta_applies, te_fast_k, pad;
+};
+
+template <typename R> struct DevJoint {
+  R mu[3], lv[3];
+  R rb[6];            // lower triangle of nearest_psd(corr): 00 10 11 20 21 22
+  R nu, alpha, beta, one_m_ab, dcc_a, dcc_b, one_m_dcc;
+  int nu_fast_k, pad;
+};
+
+template <typename R> struct DevVix { R phi, drift /* (1-phi)*target */, noise_std, jump_thr, jump_scale, denom; };
+template <typename R> struct DevStress { R liq_mu, liq_phi, liq_sigma, cr_mu, cr_phi, cr_sigma, jbase, jscale; };
+
+template <typename R> struct DevStrategy {
+  int type, asset, asset2, taxable, port, pad;
+  R w[kAssets];
+  R p[LETF_STRAT_NPARAM];
+};
+
+template <typename R, int NS> struct DevParams {
+  int market_mode, T, buffer, random_start, min_offset, offset_range, antithetic, mm, institutional,
+      has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset;
+  R W0, sim_years;
+  int flip[2];
+  R log_pstay[2];
+  int n_dur[2];
+  const int32_t* dur[2];
+  R reg_mean[2], reg_std[2];
+  DevJoint<R> joint[2];
+  R mm_theo[3];
+  R pt_chol[2][9];
+  R pt_df; int pt_fast_k, pad0;
+  R n_mu[3], n_ch[6];      // normal market: lower-triangular Cholesky 00 10 11 20 21 22
+  R const_vix, const_rf;
+  DevVix<R> vix[2];
+  R vix_base[2], irx_base[2];
+  DevStress<R> stress[2];
+  R f_base, f_vix, f_inv, f_liq, f_cr, f_min, f_max;
+  DevAsset<R> assets[kAssets];
+  R cash_daily[2], spread_cost[2], rebalance_cost;
+  DevStrategy<R> strat[NS];
+};
+
+#ifndef LETF_DEVICE_ONLY
+// ---- host: validate + convert -------------------------------------------------------------
+inline const char* validate_params(const LetfParams& s) {
+  if (s.abi_version != LETF_ABI_VERSION) return "abi_version mismatch";
+  if (s.market_mode < 0 || s.market_mode > 2) return "bad market_mode";
+  if (s.sim_days < 0 || s.buffer_days < 0) return "negative day count";
+  if (s.n_strategies < 0 || s.n_strategies > LETF_MAX_STRATEGIES) return "bad n_strategies";
+  if (s.random_start && s.buffer_days <= 0) return "random_start needs buffer_days > 0";
+  if (s.market_mode == LETF_MARKET_JOINT_T)
+    for (int r = 0; r < 2; r++) if (!(s.joint[r].nu >= 2.0)) return "joint nu must be >= 2";
+  int sig_asset = -1, nport = 0;
+  for (int k = 0; k < s.n_strategies; k++) {
+    const LetfStrategyParams& q = s.strategies[k];
+    const double* p = q.p;
+    auto is = [&](int i, double v) { return p[i] == v; };
+    switch (q.type) {
+      case LETF_ST_BENCHMARK: case LETF_ST_BENCHMARK_TLT: break;
+      case LETF_ST_SMA: case LETF_ST_SMA_BAND: if (!is(0, 200)) return "sma_period must be 200"; break;
+      case LETF_ST_PORTFOLIO: if (++nport > kPortMax) return "too many portfolio strategies"; if (p[0] < 1) return "rebalance_freq < 1"; break;
+      case LETF_ST_VOL_TARGETING: if (!is(1, 20)) return "vol_targeting lookback must be 20"; break;
+      case LETF_ST_COMPOSITE: if (!is(0, 200) || !is(1, 14)) return "composite windows must be 200/14"; break;
+      case LETF_ST_ADAPTIVE_VOL: if (!is(2, 20) || !is(3, 200)) return "adaptive_vol windows must be 20/200"; break;
+      case LETF_ST_DOWNSIDE_VOL: if (!is(1, 20)) return "downside_vol lookback must be 20"; break;
+      case LETF_ST_CONVEX_VOL: if (!is(2, 200)) return "convex_vol sma_period must be 200"; break;
+      case LETF_ST_VOL_VELOCITY: case LETF_ST_VOL_MOM: case LETF_ST_SKEW_CONVEX: case LETF_ST_META_ENSEMBLE: break;
+      case LETF_ST_REGIME_ASYMMETRIC: if (!is(4, 5) || !is(5, 60)) return "regime_asymmetric lookbacks must be 5/60"; break;
+      case LETF_ST_SKEW_KELLY: if (!is(1, 60) || !is(2, 20)) return "skew_kelly lookbacks must be 60/20"; break;
+      case LETF_ST_MOM_VOL_CONV: if (!is(1, 126) || !is(2, 10) || !is(3, 60)) return "mom_vol_convergence lookbacks must be 126/10/60"; break;
+      case LETF_ST_CONVICTION: if (!is(1, 126) || !is(2, 20) || !is(3, 100)) return "conviction lookbacks must be 126/20/100"; break;
+      default: return "unknown strategy type";
+    }
+    bool uses_sig = q.type >= LETF_ST_VOL_TARGETING && q.type <= LETF_ST_CONVICTION && q.type != LETF_ST_COMPOSITE;
+    if (q.type != LETF_ST_PORTFOLIO && q.type != LETF_ST_BENCHMARK_TLT && (q.asset < 0 || q.asset >= kAssets)) return "bad strategy asset";
+    if (q.type == LETF_ST_COMPOSITE && (q.asset2 < 0 || q.asset2 >= kAssets)) return "bad defensive asset";
+    if (uses_sig) {
+      if (sig_asset >= 0 && sig_asset != q.asset) return "all volatility-signal strategies must trade the same asset";
+      sig_asset = q.asset;
+    }
+  }
+  return nullptr;
+}
+
+inline uint32_t strategy_type_mask(const LetfParams& s) {
+  uint32_t m = 0;
+  for (int k = 0; k < s.n_strategies; k++) m |= 1u << s.strategies[k].type;
+  return m;
+}
+
+template <typename R, int NS>
+inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS>& d) {
+  memset(&d, 0, sizeof(d));
+  d.market_mode = s.market_mode; d.T = s.sim_days; d.buffer = s.buffer_days; d.random_start = s.random_start;
+  d.min_offset = s.buffer_days / 4 < 50 ? s.buffer_days / 4 : 50;
+  d.offset_range = s.buffer_days - d.min_offset;
+  d.antithetic = s.antithetic_pairs; d.mm = s.moment_matching && s.market_mode == LETF_MARKET_JOINT_T;
+  d.institutional = s.institutional; d.has_vix = s.has_vix_dynamics; d.has_stress = s.has_stress;
+  d.has_funding = s.has_funding && s.institutional; d.asset_mask = s.asset_mask; d.n_strat = s.n_strategies;
+  d.apply_costs = s.apply_costs;
+  d.W0 = (R)s.initial_capital; d.sim_years = (R)s.sim_years;
+  d.sig_asset = 0;
+  for (int r = 0; r < 2; r++) {
+    d.flip[r] = s.transition[r][1 - r] > 0 ? 1 : 0;
+    double ps = s.transition[r][r]; ps = ps < 0.80 ? 0.80 : (ps > 0.995 ? 0.995 : ps);
+    d.log_pstay[r] = (R)::log(ps);
+    d.n_dur[r] = s.n_duration[r]; d.dur[r] = dev_dur[r];
+    d.reg_mean[r] = (R)s.regime_daily_mean[r]; d.reg_std[r] = (R)s.regime_daily_std[r];
+    const LetfJointRegime& j = s.joint[r];
+    DevJoint<R>& q = d.joint[r];
+    double nu = j.nu, alpha = j.garch_alpha, beta = j.garch_beta;
+    double tvs = nu > 2.0 ? (nu - 2.0) / nu : 0.5;
+    for (int a = 0; a < 3; a++) {
+      q.mu[a] = (R)j.mu[a];
+      double lv = j.cov[a][a] * tvs; if (lv < 1e-8) lv = 1e-8;
+      q.lv[a] = (R)lv;
+    }
+    double ea = nu > 2.0 ? alpha * nu / (nu - 2.0) : alpha * 2.0;
+    if (ea + beta >= 1.0) { double b2 = 0.98 - ea; beta = 0.70 > b2 ? 0.70 : b2; }
+    q.rb[0] = (R)j.rbar[0][0]; q.rb[1] = (R)j.rbar[1][0]; q.rb[2] = (R)j.rbar[1][1];
+    q.rb[3] = (R)j.rbar[2][0]; q.rb[4] = (R)j.rbar[2][1]; q.rb[5] = (R)j.rbar[2][2];
+    q.nu = (R)nu; q.alpha = (R)alpha; q.beta = (R)beta; q.one_m_ab = (R)(1 - alpha - beta);
+    q.dcc_a = (R)j.dcc_a; q.dcc_b = (R)j.dcc_b; q.one_m_dcc = (R)(1 - j.dcc_a - j.dcc_b);
+    q.nu_fast_k = df_fast_k(nu);
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) d.pt_chol[r][a * 3 + b] = (R)s.param_t_chol[r][a][b];
+    const LetfVixRegime& v = s.vix[r];
+    d.vix[r].phi = (R)v.phi; d.vix[r].drift = (R)((1 - v.phi) * v.target); d.vix[r].noise_std = (R)v.noise_std;
+    d.vix[r].jump_thr = (R)v.jump_threshold; d.vix[r].jump_scale = (R)v.jump_scale;
+    d.vix[r].denom = (R)(s.regime_daily_std[r] > 1e-4 ? s.regime_daily_std[r] : 1e-4);
+    d.vix_base[r] = (R)s.vix_base[r]; d.irx_base[r] = (R)s.irx_base[r];
+    const LetfStressRegime& t = s.stress[r];
+    DevStress<R>& u = d.stress[r];
+    u.liq_mu = (R)t.liq_mu; u.liq_phi = (R)t.liq_phi; u.liq_sigma = (R)t.liq_sigma;
+    u.cr_mu = (R)t.credit_mu; u.cr_phi = (R)t.credit_phi; u.cr_sigma = (R)t.credit_sigma;
+    u.jbase = (R)t.jump_base_prob; u.jscale = (R)t.jump_scale;
+    d.cash_daily[r] = (R)(s.cash_rate[r] / 252); d.spread_cost[r] = (R)(s.base_spread_bps[r] / 10000);
+  }
+  for (int a = 0; a < 3; a++) d.mm_theo[a] = (R)((s.joint[0].mu[a] + s.joint[1].mu[a]) / 2.0);
+  d.pt_df = (R)s.param_t_df; d.pt_fast_k = df_fast_k(s.param_t_df);
+  for (int a = 0; a < 3; a++) d.n_mu[a] = (R)s.normal_mu[a];
+  d.n_ch[0] = (R)s.normal_chol[0][0]; d.n_ch[1] = (R)s.normal_chol[1][0]; d.n_ch[2] = (R)s.normal_chol[1][1];
+  d.n_ch[3] = (R)s.normal_chol[2][0]; d.n_ch[4] = (R)s.normal_chol[2][1]; d.n_ch[5] = (R)s.normal_chol[2][2];
+  d.const_vix = (R)s.const_vix; d.const_rf = (R)s.const_rf;
+  d.f_base = (R)s.funding.base; d.f_vix = (R)s.funding.beta_vix; d.f_inv = (R)s.funding.beta_inv_curve;
+  d.f_liq = (R)s.funding.beta_liquidity; d.f_cr = (R)s.funding.beta_credit;
+  d.f_min = (R)s.funding.min_spread; d.f_max = (R)s.funding.max_spread;
+  for (int a = 0; a < kAssets; a++) {
+    const LetfAssetParams& x = s.assets[a];
+    DevAsset<R>& y = d.assets[a];
+    y.lev = (R)x.leverage; y.bl = (R)(x.leverage - 1.0); y.er_daily = (R)(x.expense_ratio / 252);
+    y.borrow_spread = (R)x.borrow_spread; y.te_base = (R)x.te_base; y.te_df = (R)x.te_df; y.te_rho = (R)x.te_rho;
+    double q = 1 - x.te_rho * x.te_rho; if (q < 1e-6) q = 1e-6;
+    y.te_arw = (R)::sqrt(q); y.te_down = (R)x.te_downside; y.te_clip = (R)x.te_clip; y.beta = (R)x.beta;
+    y.und = x.underlying; y.beta_applies = x.beta_applies; y.te_fast_k = df_fast_k(x.te_df);
+  }
+  d.rebalance_cost = (R)s.rebalance_cost;
+  int nport = 0;
+  for (int k = 0; k < s.n_strategies && k < NS; k++) {
+    const LetfStrategyParams& x = s.strategies[k];
+    DevStrategy<R>& y = d.strat[k];
+    y.type = x.type; y.asset = x.asset; y.asset2 = x.asset2; y.taxable = x.taxable;
+    y.port = x.type == LETF_ST_PORTFOLIO ? nport++ : -1;
+    for (int a = 0; a < kAssets; a++) y.w[a] = (R)x.weights[a];
+    for (int i = 0; i < LETF_STRAT_NPARAM; i++) y.p[i] = (R)x.p[i];
+    bool uses_sig = x.type >= LETF_ST_VOL_TARGETING && x.type <= LETF_ST_CONVICTION && x.type != LETF_ST_COMPOSITE;
+    if (uses_sig) d.sig_asset = x.asset;
+  }
+}
+#endif  // LETF_DEVICE_ONLY
+
+}  // namespace letf

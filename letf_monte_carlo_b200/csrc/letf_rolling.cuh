@@ -1,0 +1,131 @@
+// letf_rolling.cuh — streaming (one value in, one value out) forms of the pandas rolling
+// statistics the reference's strategy rules are written with (letf/strategy.py).
+//
+// EXACT = true reproduces pandas' own online algorithms (removal before addition, Kahan
+// compensated sums, Welford variance with compensated mean update, the
+// "all values in the window identical" short-cuts), so that fp64 parity-mode signals agree
+// with the reference to the last bits and trade decisions are identical.
+// EXACT = false (fp32 throughput mode) drops the compensation terms.
+#pragma once
+#include "letf_math.cuh"
+
+namespace letf {
+
+template <typename R> LETF_HD R nan_() { return (R)NAN; }
+
+// rolling sum / mean ------------------------------------------------------------------------
+template <typename R, bool EXACT> struct RollSum {
+  R s, ca, cr, prev;
+  int nobs, ncs, neg;
+  LETF_HD void init() { s = ca = cr = (R)0; prev = nan_<R>(); nobs = ncs = neg = 0; }
+  LETF_HD void remove(R v) {
+    nobs--;
+    if (EXACT) { R y = -v - cr, t = s + y; cr = t - s - y; s = t; if (v < (R)0) neg--; }
+    else s -= v;
+  }
+  LETF_HD void add(R v) {
+    nobs++;
+    if (EXACT) {
+      R y = v - ca, t = s + y; ca = t - s - y; s = t;
+      if (v < (R)0) neg++;
+      ncs = (v == prev) ? ncs + 1 : 1;
+      prev = v;
+    } else s += v;
+  }
+  LETF_HD R sum(int mp) const {
+    if (nobs < mp) return nan_<R>();
+    if (EXACT && ncs >= nobs) return prev * (R)nobs;
+    return s;
+  }
+  LETF_HD R mean(int mp) const {
+    if (nobs < mp || nobs <= 0) return nan_<R>();
+    R r = s / (R)nobs;
+    if (EXACT) {
+      if (ncs >= nobs) r = prev;
+      else if (neg == 0 && r < (R)0) r = (R)0;
+      else if (neg == nobs && r > (R)0) r = (R)0;
+    }
+    return r;
+  }
+};
+
+// rolling variance (ddof = 1) -----------------------------------------------------------------
+template <typename R, bool EXACT> struct RollVar {
+  R mean, ssq, ca, cr, prev;
+  int nobs, ncs;
+  LETF_HD void init() { mean = ssq = ca = cr = (R)0; prev = nan_<R>(); nobs = ncs = 0; }
+  LETF_HD void remove(R v) {
+    nobs--;
+    if (nobs) {
+      if (EXACT) {
+        R pm = mean - cr, y = v - cr, t = y - mean;
+        cr = t + mean - y;
+        mean = mean - t / (R)nobs;
+        ssq = ssq - (v - pm) * (v - mean);
+      } else {
+        R pm = mean, t = v - mean;
+        mean = mean - t / (R)nobs;
+        ssq = ssq - (v - pm) * (v - mean);
+      }
+    } else { mean = (R)0; ssq = (R)0; }
+  }
+  LETF_HD void add(R v) {
+    nobs++;
+    if (EXACT) {
+      ncs = (v == prev) ? ncs + 1 : 1;
+      prev = v;
+      R pm = mean - ca, y = v - ca, t = y - mean;
+      ca = t + mean - y;
+      mean = mean + t / (R)nobs;
+      ssq = ssq + (v - pm) * (v - mean);
+    } else {
+      R pm = mean, t = v - mean;
+      mean = mean + t / (R)nobs;
+      ssq = ssq + (v - pm) * (v - mean);
+    }
+  }
+  // rolling(w, min_periods = mp).std()
+  LETF_HD R stdev(int mp) const {
+    if (nobs < mp || nobs <= 1) return nan_<R>();
+    if (EXACT && ncs >= nobs) return (R)0;
+    R r = ssq / (R)(nobs - 1);
+    if (r < (R)0) r = (R)0;
+    return Mth<R>::sqrt_(r);
+  }
+};
+
+// rolling skew (bias-corrected G1) + the window mean, from online central moments -----------------
+template <typename R, bool EXACT> struct RollSkew {
+  R mean, m2, m3, prev;
+  int nobs, ncs;
+  LETF_HD void init() { mean = m2 = m3 = (R)0; prev = nan_<R>(); nobs = ncs = 0; }
+  LETF_HD void remove(R v) {
+    int nn = nobs - 1;
+    if (nn == 0) { mean = m2 = m3 = (R)0; }
+    else {
+      R delta = v - mean, dn = delta / (R)nn, term1 = delta * dn * (R)nobs;
+      m3 = m3 - (term1 * dn * (R)(nobs + 1) - (R)3 * dn * m2);
+      mean = mean - dn;
+      m2 = m2 - term1;
+    }
+    nobs = nn;
+  }
+  LETF_HD void add(R v) {
+    int nn = nobs + 1;
+    R delta = v - mean, dn = delta / (R)nn, term1 = delta * dn * (R)nobs;
+    m3 = m3 + term1 * dn * (R)(nn - 2) - (R)3 * dn * m2;
+    m2 = m2 + term1;
+    mean = mean + dn;
+    nobs = nn;
+    if (EXACT) { ncs = (v == prev) ? ncs + 1 : 1; prev = v; }
+  }
+  LETF_HD R skew(int mp) const {
+    if (nobs < mp || nobs < 3) return nan_<R>();
+    R d = (R)nobs, B = m2 / d;
+    if (EXACT && ncs >= nobs) return (R)0;
+    if (B <= (R)1e-14) return nan_<R>();
+    return Mth<R>::sqrt_(d * (d - (R)1)) / (d - (R)2) * (m3 / d) / (B * Mth<R>::sqrt_(B));
+  }
+};
+
+}  // namespace letf

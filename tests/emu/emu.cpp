@@ -1,0 +1,58 @@
+// Host emulation of the fused kernel's per-trial body (TEST-ONLY build).
+//
+// letf_core.cuh is written __host__ __device__; compiling it with the host compiler lets the
+// CPU test-suite exercise the *kernel source* (fp64 and fp32 instantiations, tape / Philox /
+// record modes) against the oracle without a GPU.  It is never part of the product: the
+// shipped library contains only the device kernels and has no CPU path.
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../letf_monte_carlo_b200/csrc/letf_core.cuh"
+
+using namespace letf;
+
+template <typename R, int MARKET>
+static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* out, uint64_t seed,
+                 int64_t first, int64_t n, int rng_mode, int64_t log_trial, int log_strategy, int log_cap,
+                 int32_t* log_count, int32_t* log_day, int32_t* log_asset, int32_t* log_action,
+                 double* log_shares, double* log_price) {
+  constexpr int NS = LETF_MAX_STRATEGIES;
+  static KArgs<R, NS> ka;
+  const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
+  convert_params<R, NS>(*sp, dd, ka.p);
+  if (tape) ka.tape = *tape; else memset(&ka.tape, 0, sizeof(ka.tape));
+  ka.out = *out;
+  ka.seed = seed; ka.first_trial = first; ka.n_trials = n;
+  ka.tape_first = 0;
+  ka.rng_mode = rng_mode;
+  const int G = sp->sim_days + sp->buffer_days;
+  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 3), rp(kRingP), rs(kRingS), ra(kRingA);
+  ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
+  ka.nthreads = 1;
+  ka.log_trial = log_trial; ka.log_strategy = log_strategy; ka.log_cap = log_cap;
+  ka.log_count = log_count; ka.log_day = log_day; ka.log_asset = log_asset; ka.log_action = log_action;
+  ka.log_shares = log_shares; ka.log_price = log_price;
+  for (int64_t j = 0; j < n; j++) {
+    Trial<R, NS, MARKET, true, 0xFFFFFFFFu> t(ka, first + j, j, 0);
+    t.run();
+  }
+  return 0;
+}
+
+extern "C" int letf_emu_run(const LetfParams* sp, int precision, const LetfTape* tape, const LetfOutputs* out,
+                            uint64_t seed, int64_t first, int64_t n, int rng_mode,
+                            int64_t log_trial, int log_strategy, int log_cap, int32_t* log_count,
+                            int32_t* log_day, int32_t* log_asset, int32_t* log_action, double* log_shares,
+                            double* log_price) {
+  const char* err = validate_params(*sp);
+  if (err) return -1;
+#define GO(R, MK) return run_t<R, MK>(sp, tape, out, seed, first, n, rng_mode, log_trial, log_strategy, log_cap, log_count, log_day, log_asset, log_action, log_shares, log_price)
+  if (precision == LETF_PREC_F64) {
+    if (sp->market_mode == 0) GO(double, 0); else if (sp->market_mode == 1) GO(double, 1); else GO(double, 2);
+  } else {
+    if (sp->market_mode == 0) GO(float, 0); else if (sp->market_mode == 1) GO(float, 1); else GO(float, 2);
+  }
+#undef GO
+}
+
+extern "C" const char* letf_emu_validate(const LetfParams* sp) { return validate_params(*sp); }

@@ -1,0 +1,63 @@
+"""Loader for the TEST-ONLY host emulation of the kernel body (see emu.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from letf_monte_carlo_b200 import abi
+from oracle.oracle import HostOutputs
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+LIB = os.path.join(_BUILD, "libletf_emu.so")
+_lib = None
+
+
+def build(force=False):
+    os.makedirs(_BUILD, exist_ok=True)
+    src = os.path.join(_HERE, "emu.cpp")
+    csrc = os.path.join(_HERE, "..", "..", "letf_monte_carlo_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    deps.append(os.path.join(_HERE, "..", "..", "include", "letf_b200.h"))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, src],
+                       check=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.letf_emu_run.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Tape), C.POINTER(abi.Outputs),
+                                   C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int] + \
+                                  [C.c_void_p] * 6
+        L.letf_emu_run.restype = C.c_int
+        L.letf_emu_validate.argtypes = [C.POINTER(abi.Params)]
+        L.letf_emu_validate.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, first=0, n=None, log=None):
+    n_all = tape.n_tapes * (2 if params.antithetic_pairs else 1)
+    n = n_all - first if n is None else n
+    out = HostOutputs(params.n_strategies, n)
+    ts = tape.as_struct()
+    args = [-1, -1, 0] + [None] * 6
+    if log is not None:
+        trial, strat, cap = log
+        bufs = {"count": np.zeros(1, np.int32), "day": np.zeros(cap, np.int32), "asset": np.zeros(cap, np.int32),
+                "action": np.zeros(cap, np.int32), "shares": np.zeros(cap), "price": np.zeros(cap)}
+        args = [trial, strat, cap] + [bufs[k].ctypes.data for k in ("count", "day", "asset", "action", "shares", "price")]
+    rc = lib().letf_emu_run(C.byref(params), precision, C.byref(ts), C.byref(out.as_struct()), seed, first, n,
+                            rng_mode, *args)
+    if rc != 0:
+        raise RuntimeError(f"emu rc={rc}: {lib().letf_emu_validate(C.byref(params))}")
+    if log is not None:
+        out.log = bufs
+    return out
