@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py - LETF path-days/sec on N B200s (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+
+A "step" is one pass of the hot path over one batch: the fused path kernel over this rank's trials
+(Philox draws generated on the device), the summary reduction kernel, and - for N > 1 - the NCCL
+allreduce of the summary buffers.  N = 1 workload: BASELINE.json configs[1] ("c2": TQQQ/UPRO/SSO with
+expense ratio + borrow cost + tracking error, 100k trials x 7,560 days).  N > 1: the same number of
+trials PER GPU (weak scaling), trial ids globally unique.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/letf_oracle.c, every
+variate drawn by a conventional CPU generator) with all host threads, on a bounded sample of the same
+workload.  (The reference itself is pure Python and is not importable on the GPU box.)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LETF path-days/sec"
+UNIT = "path-days/s"
+
+# algorithmic lane-instructions per path-day (Philox4x32-10, inverse-CDF / Box-Muller
+# normals, gamma-based chi2 / Student-t, compounding + drawdown per tracked equity); restated in DESIGN.md
+WORKLOADS = {
+    "c2": dict(desc="BASELINE configs[1]: TQQQ/UPRO/SSO, expense ratio + borrow cost + AR(1) Student-t tracking error, "
+                    "correlated normal SPY/QQQ shocks, buy&hold, 100k trials x 7560 days",
+               trials=100_000, years=30, lane_ops=470, mufu=14),
+    "c3": dict(desc="BASELINE configs[2]: regime-switching multivariate-t GARCH/DCC QQQ/SPY/TLT, VIX/IRX, stress + jumps, "
+                    "antithetic, moment matching, random start; 1M trials x 7560 days",
+               trials=1_000_000, years=30, lane_ops=520 * (7560 + 1260) / 7560, mufu=22),
+    "c4": dict(desc="BASELINE configs[3]: C3 market + TQQQ/TMF/SPY layers, S1 S2 S4 S5 S6 S19, per GPU 1.25M trials x 7560 days",
+               trials=1_250_000, years=30, lane_ops=1130, mufu=40),
+}
+
+
+def build_workload(name):
+    from letf_monte_carlo_b200 import synthetic
+    from letf_monte_carlo_b200.params import build_params
+    if name == "c2":
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                        USE_ANTITHETIC_VARIATES=False)
+        sids = ["S1", "B_UPRO", "S3"]
+        model = synthetic.normal_regime_model("c2")
+    elif name == "c3":
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+        sids = ["S2", "B_QQQ", "B_TLT"]
+        model = synthetic.fallback_regime_model("default")
+    elif name == "c4":
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+        sids = ["S1", "S2", "S4", "S5", "S6", "S19"]
+        model = synthetic.fallback_regime_model("default")
+    else:
+        raise KeyError(name)
+    params, keep = build_params(sids, WORKLOADS[name]["years"], model, ns)
+    return ns, model, sids, params, keep
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "sm_max_mhz": d["sm_max_mhz"], "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_rate(params, budget_s, threads, seed=1):
+    """path-days/s of the CPU port (oracle) incl. its own random draws, `threads` host threads,
+    on as many trials as fit in ~budget_s seconds.  Returns (rate, n_trials, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    orc.lib()
+    T = params.sim_days
+    chunk = 4
+
+    def work(i):
+        tp = orc.fill_tape(params, chunk, seed * 100003 + i, max_spells=512)
+        orc.run(params, tp)
+        return chunk * (2 if params.antithetic_pairs else 1)
+
+    t0 = time.perf_counter(); k = work(0); dt1 = time.perf_counter() - t0          # calibration chunk
+    n_chunks = max(threads, int(budget_s / max(dt1, 1e-4)) * threads)
+    n_chunks = min(n_chunks, 4096)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        done = sum(ex.map(work, range(1, n_chunks + 1)))
+    dt = time.perf_counter() - t0
+    return done * T / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ns, model, sids, params, keep = build_workload(args.workload)
+    threads = os.cpu_count() or 1
+    wl = WORKLOADS[args.workload]
+    per_step_budget = 2.0
+    for _ in range(args.warmup):
+        cpu_port_rate(params, 0.2, threads)
+    rates, n_done, secs = [], 0, 0.0
+    for s in range(args.steps):
+        r, n, dt = cpu_port_rate(params, per_step_budget, threads, seed=s + 2)
+        rates.append(r); n_done += n; secs += dt
+    value = n_done * params.sim_days / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "trials_per_step_sample": n_done // max(args.steps, 1),
+                   "sim_days": params.sim_days},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_done} trials x {params.sim_days} days of the same workload over {args.steps} steps, "
+                                   f"oracle/letf_oracle.c (plain C restatement of the reference's NumPy path, xoshiro + "
+                                   f"polar/Marsaglia-Tsang draws), {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from letf_monte_carlo_b200 import abi
+    from letf_monte_carlo_b200.distributed import allreduce_summary
+    from letf_monte_carlo_b200.engine import PathEngine
+    from letf_monte_carlo_b200.mc_runner import parallel_monte_carlo_fixed
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws != args.gpus:
+        if ws == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ns, model, sids, params, keep = build_workload(args.workload)
+    wl = WORKLOADS[args.workload]
+    n = int(args.trials or wl["trials"])          # per GPU (weak scaling)
+    T = params.sim_days
+    first = rank * n
+    eng = PathEngine(params, keep, precision=args.precision, device=local)
+    out = None
+    sm = eng.new_summary(bench_strategy=-1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(ev=None):
+        nonlocal out
+        flush.zero_()
+        if ev:
+            ev[0].record()
+        out = eng.run(n, first_trial=first, seed=args.seed, out=out)
+        if ev:
+            ev[1].record()
+        eng.reset_summary(sm)
+        eng.reduce(out, sm)
+        if ws > 1:
+            allreduce_summary(sm.hist, sm.moments, sm.extrema, sm.counters)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.25)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launches
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    launches = eng.launches - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = clk.stop() if rank == 0 else None
+    info = eng.launch_info()
+
+    # ---- end to end through the public API: host in, host out, engine created per call
+    h2d = ctypes.sizeof(abi.Params)
+    S = len(sids)
+    d2h = n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
+    ns.NUM_SIMULATIONS = n * ws
+    ns.GPU_SEED = args.seed
+    e2e_steps = max(1, min(args.steps, 5))
+    parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local, verbose=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local,
+                                         verbose=False)
+        med = float(np.median(res[sids[0]].final_wealth))     # the step's result is read on the host
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = e2e_steps
+
+    t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms, e2e_s = (float(x) for x in t.cpu())
+
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = total_ms / args.steps
+        value = ws * n * T / (ms_per_step * 1e-3)
+        sm_count = info["sm_count"]
+        peak_lane = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e12               # T lane-ops/s at max clock
+        achieved = n * T * wl["lane_ops"] / (kern_ms * 1e-3) / 1e12
+        out_bytes = d2h
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "trials_per_gpu": n, "sim_days": T,
+                       "strategies": sids, "parallelism": f"trials sharded over {ws} GPU(s), no data-path collective; "
+                                                          f"summary allreduce (NCCL) per step",
+                       "rng": "on-device Philox4x32-10 keyed by (seed, sim_id, day, stream)",
+                       "l2": "256 MiB memset between steps (inside the timed region); the path kernel reads no HBM inputs",
+                       "kernel": {"grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"],
+                                  "scratch_bytes": info["scratch_bytes"]}},
+            "clocks": clocks,
+            "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed (engine created per call, host results)",
+                    "steps": e2e_steps, "median_final_wealth": med},
+            "gpu_launches": launches + e2e_launches,
+            "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
+                         "traffic": None, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
+                         "lane_ops_per_path_day": wl["lane_ops"], "units_per_launch": n * T,
+                         "peak_def": f"{sm_count} SMs x 128 FP32/INT lanes x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})",
+                         "frac_at_observed_clock": (achieved / (sm_count * 128 * clocks["sm_mhz"] * 1e6 / 1e12)
+                                                    if clocks and clocks.get("sm_mhz") else None),
+                         "hbm": {"achieved_gbs": out_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                                 "note": "outputs only; paths never round-trip HBM"}},
+        }
+        if ws == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            rate, nt, dt = cpu_port_rate(params, 1.5, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{nt} trials x {T} days of the same workload in {dt:.1f} s, oracle/letf_oracle.c "
+                                              f"incl. its own CPU random draws, {threads} threads"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--trials", type=int, default=0, help="trials per GPU (default: the workload's)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--seed", type=int, default=20240229)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

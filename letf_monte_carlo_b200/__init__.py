@@ -5,5 +5,7 @@ Drop-in for the hot path of djbm10/LETF-Monte-Carlo
 `run_strategy_fixed`); everything else of the reference is out of scope.
 """
 from . import abi, config  # noqa: F401
+from .mc_runner import parallel_monte_carlo_fixed  # noqa: F401
+from .trade import TAXABLE_IDS, ROTH_IDS, TradeJournal  # noqa: F401
 
-__all__ = ["abi", "config"]
+__all__ = ["abi", "config", "parallel_monte_carlo_fixed", "TAXABLE_IDS", "ROTH_IDS", "TradeJournal"]

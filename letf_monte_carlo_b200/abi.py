@@ -159,7 +159,8 @@ class Series(C.Structure):
 
 ENGINE_SYMBOLS = (
     "letf_create", "letf_destroy", "letf_last_error", "letf_abi_version", "letf_run",
-    "letf_run_host", "letf_reduce", "letf_launch_info", "letf_run_strategies", "letf_nearest_psd3",
+    "letf_run_host", "letf_summary_reset", "letf_reduce", "letf_trade_list_host", "letf_launch_info",
+    "letf_run_strategies", "letf_nearest_psd3",
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -195,8 +196,13 @@ def load_engine_library(path: str | None = None):
     lib.letf_run.restype = i32
     lib.letf_run_host.argtypes = [vp, u64, i64, i64, i32, C.POINTER(Tape), C.POINTER(Outputs)]
     lib.letf_run_host.restype = i32
+    lib.letf_summary_reset.argtypes = [vp, vp, C.POINTER(Summary)]
+    lib.letf_summary_reset.restype = i32
     lib.letf_reduce.argtypes = [vp, vp, C.POINTER(Outputs), i64, C.POINTER(Summary)]
     lib.letf_reduce.restype = i32
+    lib.letf_trade_list_host.argtypes = [vp, u64, i64, i32, i32, C.POINTER(Tape), i32, vp, vp, vp, vp, vp,
+                                         C.POINTER(C.c_int32)]
+    lib.letf_trade_list_host.restype = i32
     lib.letf_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     lib.letf_launch_info.restype = i32
     lib.letf_run_strategies.argtypes = [vp, vp, C.POINTER(Series), C.POINTER(Outputs)]

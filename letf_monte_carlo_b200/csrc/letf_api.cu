@@ -343,7 +343,7 @@ static void** tape_field(LetfTape& t, int i) {
   }
 }
 
-// stage a host tape on the device.  upload: copy host -> device (tape mode); otherwise zero-fill (record mode)
+// stage a host tape on the device (host -> device copy of every array)
 static int stage_tape(LetfEngine* e, const LetfTape* host, bool upload, LetfTape* dev) {
   *dev = *host;
   LetfTape h = *host;
@@ -356,8 +356,9 @@ static int stage_tape(LetfEngine* e, const LetfTape* host, bool upload, LetfTape
     *tape_field(*dev, i) = dp;
     if (!hp) return fail(LETF_ERR_INVALID, "host tape has a null array");
     if (L.bytes[i] == 0) continue;
-    if (upload) CK(cudaMemcpy(dp, hp, L.bytes[i], cudaMemcpyHostToDevice));
-    else CK(cudaMemset(dp, 0, L.bytes[i]));
+    // record mode uploads too: entries the run does not consume keep the caller's values
+    (void)upload;
+    CK(cudaMemcpy(dp, hp, L.bytes[i], cudaMemcpyHostToDevice));
   }
   return LETF_OK;
 }

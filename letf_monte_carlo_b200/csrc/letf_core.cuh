@@ -311,6 +311,18 @@ struct Trial {
     j.pos[which] = target;
   }
 
+  // pandas recomputes a rolling-variance window from scratch when a removal collapses it
+  // (letf_rolling.cuh): re-add the w-1 surviving observations, oldest first, from the return ring
+  // (cursor = slot today's return will be written to).  Rare: the window just became constant.
+  LETF_HDN void revar(RollVar<R, EXACT>& rv, const R* ring, int cursor, int w, bool downside) const {
+    rv.init();
+    for (int j = w - 1; j >= 1; j--) {
+      int c = cursor - j; if (c < 0) c += kRingA;
+      R v = ring[(int64_t)c * ka.nthreads];
+      rv.add(downside ? (v < (R)0 ? v : (R)0) : v);
+    }
+  }
+
   // run the whole trial ---------------------------------------------------------------------
   LETF_HD void run() {
     const int G = p.T + p.buffer;
@@ -594,11 +606,11 @@ struct Trial {
         if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[(int64_t)c * nth]; }
         if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[(int64_t)c * nth]; }
         if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[(int64_t)c * nth]; }
-        if (HAS_V5) { if (i >= 5) sg.v5.remove(r5); sg.v5.add(ra); }
-        if (HAS_V10) { if (i >= 10) sg.v10.remove(r10); sg.v10.add(ra); }
-        if (HAS_V20) { if (i >= 20) sg.v20.remove(r20); sg.v20.add(ra); }
-        if (HAS_V60) { if (i >= 60) sg.v60.remove(r60); sg.v60.add(ra); }
-        if (HAS_DV20) { if (i >= 20) sg.dv20.remove(r20 < (R)0 ? r20 : (R)0); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
+        if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar(sg.v5, ring, sg.cA, 5, false); sg.v5.add(ra); }
+        if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar(sg.v10, ring, sg.cA, 10, false); sg.v10.add(ra); }
+        if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar(sg.v20, ring, sg.cA, 20, false); sg.v20.add(ra); }
+        if (HAS_V60) { if (i >= 60 && sg.v60.remove(r60)) revar(sg.v60, ring, sg.cA, 60, false); sg.v60.add(ra); }
+        if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar(sg.dv20, ring, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
         if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
         if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
         ring[(int64_t)sg.cA * nth] = ra;

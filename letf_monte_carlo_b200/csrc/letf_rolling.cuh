@@ -50,11 +50,16 @@ template <typename R, bool EXACT> struct RollSum {
 };
 
 // rolling variance (ddof = 1) -----------------------------------------------------------------
+// pandas 3.0.2 roll_var: Welford add/remove with Kahan-compensated mean updates; when a removal
+// collapses the sum of squared deviations (ssq_after < 1e3 * eps * ssq_before, e.g. the window
+// became all-identical) pandas recomputes the window from scratch.  remove() reports that case
+// and the caller re-adds the surviving window from its history ring (see Trial::revar).
 template <typename R, bool EXACT> struct RollVar {
-  R mean, ssq, ca, cr, prev;
-  int nobs, ncs;
-  LETF_HD void init() { mean = ssq = ca = cr = (R)0; prev = nan_<R>(); nobs = ncs = 0; }
-  LETF_HD void remove(R v) {
+  R mean, ssq, ca, cr;
+  int nobs;
+  LETF_HD void init() { mean = ssq = ca = cr = (R)0; nobs = 0; }
+  LETF_HD bool remove(R v) {
+    const R before = ssq;
     nobs--;
     if (nobs) {
       if (EXACT) {
@@ -68,12 +73,13 @@ template <typename R, bool EXACT> struct RollVar {
         ssq = ssq - (v - pm) * (v - mean);
       }
     } else { mean = (R)0; ssq = (R)0; }
+    if (EXACT) return ssq < (R)(1e3 * 2.220446049250313e-16) * before;
+    if (ssq < (R)0) ssq = (R)0;      // fp32: keep the state non-negative instead of recomputing
+    return false;
   }
   LETF_HD void add(R v) {
     nobs++;
     if (EXACT) {
-      ncs = (v == prev) ? ncs + 1 : 1;
-      prev = v;
       R pm = mean - ca, y = v - ca, t = y - mean;
       ca = t + mean - y;
       mean = mean + t / (R)nobs;
@@ -87,7 +93,6 @@ template <typename R, bool EXACT> struct RollVar {
   // rolling(w, min_periods = mp).std()
   LETF_HD R stdev(int mp) const {
     if (nobs < mp || nobs <= 1) return nan_<R>();
-    if (EXACT && ncs >= nobs) return (R)0;
     R r = ssq / (R)(nobs - 1);
     if (r < (R)0) r = (R)0;
     return Mth<R>::sqrt_(r);

@@ -1,0 +1,49 @@
+"""Trial sharding and the one exchange step of the path.
+
+Trials are independent pure functions of (seed, trial id), so ranks simulate disjoint
+contiguous trial ranges with no communication; the only collective is the reduction of the
+summary buffers (histogram bins, moments, counters: SUM; extrema: MIN / MAX) at the end.
+`torch.distributed` is the plumbing (NCCL over NVLink on the GPU box, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+import os
+
+
+def world():
+    """(rank, world_size) from torch.distributed if initialised, else from the torchrun env."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_range(n_trials: int, rank: int, world_size: int, pair_aligned: bool = True):
+    """Contiguous trial range [lo, hi) of `rank`.  With antithetic pairing the boundaries are kept
+    even so that twins (2k, 2k+1), which share their sim_id, stay on one GPU."""
+    unit = 2 if pair_aligned else 1
+    units = (n_trials + unit - 1) // unit
+    base, extra = divmod(units, world_size)
+    lo_u = rank * base + min(rank, extra)
+    hi_u = lo_u + base + (1 if rank < extra else 0)
+    return min(lo_u * unit, n_trials), min(hi_u * unit, n_trials)
+
+
+def allreduce_summary(hist, moments, extrema, counters, group=None):
+    """In-place reduction of the letf_reduce buffers across ranks.
+    extrema[..., 0] holds minima, extrema[..., 1] maxima."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    # one MAX collective for both extrema: negate the minima
+    packed = extrema.clone()
+    packed[..., 0].neg_()
+    dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=group)
+    packed[..., 0].neg_()
+    extrema.copy_(packed)

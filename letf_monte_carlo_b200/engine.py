@@ -1,0 +1,239 @@
+"""`PathEngine`: Python handle of the CUDA path engine (thin wrapper of the C-ABI).
+
+PyTorch is used only for device memory, the current stream and (in mc_runner / bench)
+`torch.distributed`; every result is produced by the kernels in `libletf_b200.so`.
+There is no CPU fallback: constructing a PathEngine without the built library or
+without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .outputs import DeviceOutputs, HostOutputs
+from .tape import HostTape
+
+_PREC = {"f64": abi.PREC_F64, "f32": abi.PREC_F32, abi.PREC_F64: abi.PREC_F64, abi.PREC_F32: abi.PREC_F32}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"letf engine error {code}: {msg}")
+        self.code = code
+
+
+class NonFiniteTrials(ValueError):
+    """Some trial produced non-finite returns or VIX <= 0; the reference raises ValueError
+    out of the trial (engine.py:486-498)."""
+
+
+def default_device() -> int:
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class DeviceTape:
+    """A HostTape uploaded to the device (torch tensors keep the memory alive)."""
+
+    def __init__(self, host: HostTape, device):
+        import torch
+        self.host = host
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(a)).to(device) for k, a in host.arrays().items()}
+
+    def as_struct(self) -> abi.Tape:
+        s = abi.Tape()
+        h = self.host
+        s.n_tapes, s.gen_days, s.sim_days, s.max_spells = h.n_tapes, h.gen_days, h.sim_days, h.max_spells
+        for k, t in self.t.items():
+            setattr(s, k, t.data_ptr())
+        return s
+
+    def to_host(self) -> HostTape:
+        for k, t in self.t.items():
+            getattr(self.host, k)[...] = t.cpu().numpy()
+        return self.host
+
+
+class DeviceSummary:
+    """Histogram / moment buffers of `letf_reduce` (sum/min/max-reducible across GPUs)."""
+
+    def __init__(self, n_strategies: int, device, lo=(-20.0, -1.0, 0.0), hi=(10.0, 2.0, 1.0), bench_strategy=-1):
+        import torch
+        S = max(int(n_strategies), 1)
+        self.n_strategies = int(n_strategies)
+        self.hist = torch.zeros((S, abi.N_METRICS, abi.HIST_BINS), dtype=torch.int64, device=device)
+        self.moments = torch.zeros((S, abi.N_METRICS, 2), dtype=torch.float64, device=device)
+        self.extrema = torch.zeros((S, abi.N_METRICS, 2), dtype=torch.float64, device=device)
+        self.extrema[:, :, 0] = float("inf")
+        self.extrema[:, :, 1] = float("-inf")
+        self.counters = torch.zeros((S, 4), dtype=torch.int64, device=device)
+        self.lo, self.hi = tuple(map(float, lo)), tuple(map(float, hi))
+        self.bench_strategy = int(bench_strategy)
+
+    def as_struct(self) -> abi.Summary:
+        s = abi.Summary()
+        s.hist, s.moments = self.hist.data_ptr(), self.moments.data_ptr()
+        s.extrema, s.counters = self.extrema.data_ptr(), self.counters.data_ptr()
+        for q in range(abi.N_METRICS):
+            s.hist_lo[q], s.hist_hi[q] = self.lo[q], self.hi[q]
+        s.bench_strategy = self.bench_strategy
+        return s
+
+    def bin_edges(self, metric: int) -> np.ndarray:
+        return np.linspace(self.lo[metric], self.hi[metric], abi.HIST_BINS + 1)
+
+
+class PathEngine:
+    def __init__(self, params: abi.Params, keep=(), precision="f32", device: int | None = None):
+        import torch
+        self._lib = abi.load_engine_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("PathEngine needs a CUDA device (B200 / sm_100a); there is no CPU path")
+        self.device_index = default_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.params = params
+        self._keep = list(keep)
+        self.precision = _PREC[precision]
+        h = C.c_void_p()
+        rc = self._lib.letf_create(C.byref(params), self.device_index, self.precision, C.byref(h))
+        self._check(rc)
+        self._h = h
+        self.launches = 0          # kernels launched through this handle (bench.py reports it)
+
+    # ------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc == abi.OK:
+            return
+        msg = (self._lib.letf_last_error() or b"").decode()
+        if rc == abi.ERR_NONFINITE:
+            raise NonFiniteTrials(msg)
+        raise EngineError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.letf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def n_strategies(self):
+        return int(self.params.n_strategies)
+
+    def _stream(self, stream):
+        import torch
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        return C.c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------------------------
+    def run(self, n_trials: int, *, first_trial: int = 0, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
+            tape: DeviceTape | None = None, out: DeviceOutputs | None = None, journal: bool = False,
+            stream=None) -> DeviceOutputs:
+        """Simulate trials [first_trial, first_trial + n_trials) into device buffers (asynchronous)."""
+        if out is None:
+            out = DeviceOutputs(self.n_strategies, n_trials, self.device, journal=journal)
+        ts = tape.as_struct() if tape is not None else None
+        rc = self._lib.letf_run(self._h, self._stream(stream), seed, first_trial, n_trials, rng_mode,
+                                C.byref(ts) if ts is not None else None, C.byref(out.as_struct()))
+        self._check(rc)
+        self.launches += 1 if n_trials > 0 else 0
+        return out
+
+    def run_host(self, n_trials: int, *, first_trial: int = 0, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
+                 tape: HostTape | None = None, out: HostOutputs | None = None, journal: bool = False,
+                 raise_nonfinite: bool = True) -> HostOutputs:
+        """Same with host (numpy) buffers: copies in, runs, copies out, synchronises."""
+        if out is None:
+            out = HostOutputs(self.n_strategies, n_trials, journal=journal)
+        ts = tape.as_struct() if tape is not None else None
+        rc = self._lib.letf_run_host(self._h, seed, first_trial, n_trials, rng_mode,
+                                     C.byref(ts) if ts is not None else None, C.byref(out.as_struct()))
+        self.launches += 1 if n_trials > 0 else 0
+        if rc == abi.ERR_NONFINITE and not raise_nonfinite:
+            return out
+        self._check(rc)
+        return out
+
+    def run_strategies(self, asset_ret: dict, *, tlt_ret=None, vix=None, regime=None, journal: bool = False,
+                       stream=None) -> DeviceOutputs:
+        """Strategy rules on caller-supplied series (`run_strategy_fixed` seam, strategy.py:55).
+        asset_ret: {asset name: [T][n] array-like}; all arrays day-major."""
+        import torch
+        dev = self.device
+
+        def up(a, dt):
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(device=dev, dtype=dt).contiguous()
+
+        tens = {k: up(v, torch.float64) for k, v in asset_ret.items()}
+        first = next(iter(tens.values()))
+        T, n = int(first.shape[0]), int(first.shape[1])
+        s = abi.Series()
+        s.n_paths, s.sim_days = n, T
+        for name, t in tens.items():
+            assert tuple(t.shape) == (T, n)
+            s.asset_ret[abi.ASSET_INDEX[name]] = t.data_ptr()
+        tl, vx, rg = up(tlt_ret, torch.float64), up(vix, torch.float64), up(regime, torch.int32)
+        s.tlt_ret = tl.data_ptr() if tl is not None else None
+        s.vix = vx.data_ptr() if vx is not None else None
+        s.regime = rg.data_ptr() if rg is not None else None
+        out = DeviceOutputs(self.n_strategies, n, dev, journal=journal)
+        rc = self._lib.letf_run_strategies(self._h, self._stream(stream), C.byref(s), C.byref(out.as_struct()))
+        self._check(rc)
+        self.launches += 1 if n > 0 else 0
+        torch.cuda.current_stream(dev).synchronize()   # inputs above must outlive the kernel
+        return out
+
+    def new_summary(self, **kw) -> DeviceSummary:
+        return DeviceSummary(self.n_strategies, self.device, **kw)
+
+    def reduce(self, out: DeviceOutputs, summary: DeviceSummary, n_trials: int | None = None, stream=None):
+        n = out.n if n_trials is None else n_trials
+        rc = self._lib.letf_reduce(self._h, self._stream(stream), C.byref(out.as_struct()), n,
+                                   C.byref(summary.as_struct()))
+        self._check(rc)
+        self.launches += 1 if n > 0 else 0
+        return summary
+
+    def reset_summary(self, summary: DeviceSummary, stream=None):
+        self._check(self._lib.letf_summary_reset(self._h, self._stream(stream), C.byref(summary.as_struct())))
+        self.launches += 1
+
+    def trade_list(self, trial: int, strategy: int, *, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
+                   tape: HostTape | None = None, cap: int = 1 << 16) -> list[dict]:
+        """`Trade_List` of one trial / one taxable strategy (trade.py:83-91), by replaying the trial."""
+        day, asset, action = (np.zeros(cap, np.int32) for _ in range(3))
+        shares, price = np.zeros(cap), np.zeros(cap)
+        cnt = C.c_int32(0)
+        ts = tape.as_struct() if tape is not None else None
+        rc = self._lib.letf_trade_list_host(self._h, seed, trial, strategy, rng_mode,
+                                            C.byref(ts) if ts is not None else None, cap, day.ctypes.data,
+                                            asset.ctypes.data, action.ctypes.data, shares.ctypes.data,
+                                            price.ctypes.data, C.byref(cnt))
+        self._check(rc)
+        self.launches += 1
+        if cnt.value > cap:
+            return self.trade_list(trial, strategy, seed=seed, rng_mode=rng_mode, tape=tape, cap=cnt.value)
+        return [{"day_index": int(day[i]), "asset": abi.ASSET_NAMES[asset[i]],
+                 "action": "BUY" if action[i] > 0 else "SELL", "shares": float(shares[i]),
+                 "price": float(price[i]), "dollar_amount": float(shares[i] * price[i])}
+                for i in range(cnt.value)]
+
+    def launch_info(self) -> dict:
+        li = abi.LaunchInfo()
+        self._check(self._lib.letf_launch_info(self._h, C.byref(li)))
+        return {k: getattr(li, k) for k, _ in abi.LaunchInfo._fields_}

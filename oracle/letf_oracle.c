@@ -12,7 +12,7 @@
  * the live reference, run with a tape-replaying numpy Generator, and this file
  * see identical shocks.  Parity status: PINNED against outputs of the live
  * reference generated in the authoring container (oracle/make_golden.py ->
- * tests/golden/*.json); the reference itself ships no golden vectors for this
+ * tests/golden/ *.json); the reference itself ships no golden vectors for this
  * path.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
@@ -21,8 +21,9 @@
  *
  * The pandas rolling kernels below restate pandas 3.0.2
  * (_libs/window/aggregations: Kahan add/remove sum+mean, Welford add/remove
- * variance, removals before additions); they were checked bit-for-bit against
- * pandas in the authoring container (tests/test_oracle_rolling.py).
+ * variance with a from-scratch recompute when a removal collapses the variance, removals before
+ * additions); tests/test_oracle_rolling.py checks them bit-for-bit against pandas, including
+ * series with long runs of identical values (the clipped "downside" returns).
  */
 #include "../include/letf_b200.h"
 
@@ -120,41 +121,46 @@ void orc_roll_mean(const double* x, int n, int w, int mp, double* out) {
   }
 }
 
-/* rolling(w, min_periods=mp).std(), ddof=1 */
+/* rolling(w, min_periods=mp).std(), ddof=1.
+ * pandas 3.0.2 roll_var as observed (the wheel ships no .pyx; behaviour established by black-box
+ * probing, tests/test_oracle_rolling.py): Welford add/remove with Kahan-compensated mean updates,
+ * removals before additions; and when a removal collapses the sum of squared deviations
+ * (ssq_after < 1e3 * DBL_EPSILON * ssq_before, which includes going negative) the whole window is
+ * recomputed from scratch.  No "all values identical" shortcut (older pandas had one). */
+static void var_add(double v, long* nobs, double* mean, double* ssq, double* ca) {
+  (*nobs)++;
+  double pm = *mean - *ca;
+  double y = v - *ca;
+  double t = y - *mean;
+  *ca = t + *mean - y;
+  *mean = *mean + t / (double)(*nobs);
+  *ssq = *ssq + (v - pm) * (v - *mean);
+}
 void orc_roll_std(const double* x, int n, int w, int mp, double* out) {
-  long nobs = 0, ncs = 0;
-  double mean = 0.0, ssq = 0.0, ca = 0.0, cr = 0.0, prev = NA;
+  long nobs = 0;
+  double mean = 0.0, ssq = 0.0, ca = 0.0, cr = 0.0;
   for (int i = 0; i < n; i++) {
     if (i - w >= 0) {
       double v = x[i - w];
+      double before = ssq;
       nobs--;
       if (nobs) {
         double pm = mean - cr;
         double y = v - cr;
         double t = y - mean;
         cr = t + mean - y;
-        double delta = t;
-        mean = mean - delta / (double)nobs;
+        mean = mean - t / (double)nobs;
         ssq = ssq - (v - pm) * (v - mean);
       } else { mean = 0.0; ssq = 0.0; }
+      if (ssq < 1e3 * 2.220446049250313e-16 * before) {
+        nobs = 0; mean = 0.0; ssq = 0.0; ca = 0.0; cr = 0.0;
+        for (int j = i - w + 1; j < i; j++) var_add(x[j], &nobs, &mean, &ssq, &ca);
+      }
     }
-    double v = x[i];
-    nobs++;
-    if (v == prev) ncs++; else ncs = 1;
-    prev = v;
-    {
-      double pm = mean - ca;
-      double y = v - ca;
-      double t = y - mean;
-      ca = t + mean - y;
-      double delta = t;
-      mean = nobs ? mean + delta / (double)nobs : 0.0;
-      ssq = ssq + (v - pm) * (v - mean);
-    }
+    var_add(x[i], &nobs, &mean, &ssq, &ca);
     if (nobs >= mp && nobs > 1) {
-      double r;
-      if (ncs >= nobs) r = 0.0;
-      else { r = ssq / (double)(nobs - 1); if (r < 0) r = 0.0; }
+      double r = ssq / (double)(nobs - 1);
+      if (r < 0) r = 0.0;
       out[i] = sqrt(r);
     } else out[i] = NA;
   }
@@ -279,7 +285,7 @@ static int run_strategy(const LetfParams* p, const LetfStrategyParams* sp, const
   const double* spy_ret = f->ret[4];
   const double* cash = f->cash;
   double* a0 = wk, *a1 = wk + T, *a2 = wk + 2 * T, *a3 = wk + 3 * T, *a4 = wk + 4 * T,
-        *a5 = wk + 5 * T, *a6 = wk + 6 * T, *a7 = wk + 7 * T;
+        *a5 = wk + 5 * T, *a6 = wk + 6 * T;
   const int apply_costs = p->apply_costs;
 
 #define VOLSTEP(ALLOC, THRESH, STICKY, CASHLEG)                                         \

@@ -9,6 +9,7 @@ import numpy as np
 
 from letf_monte_carlo_b200 import abi
 from letf_monte_carlo_b200.tape import HostTape
+from letf_monte_carlo_b200.outputs import HostOutputs  # noqa: F401  (numpy-backed LetfOutputs)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libletf_oracle.so")
@@ -58,36 +59,6 @@ def lib():
             f.restype = None
         _lib = L
     return _lib
-
-
-class HostOutputs:
-    """numpy-backed LetfOutputs ([S][n] structure-of-arrays)."""
-
-    def __init__(self, n_strategies: int, n: int):
-        S = max(int(n_strategies), 1)
-        self.n = int(n)
-        self.final_wealth = np.zeros((S, n))
-        self.max_dd = np.zeros((S, n))
-        self.num_trades = np.zeros((S, n), np.int32)
-        self.journal_count = np.zeros((S, n), np.int32)
-        self.journal_volume = np.zeros((S, n))
-        self.start_offset = np.zeros(n, np.int32)
-        self.flags = np.zeros(n, np.uint32)
-        self.regime_days = np.zeros((2, n), np.int32)
-        self.jump_days = np.zeros(n, np.int32)
-
-    def as_struct(self) -> abi.Outputs:
-        o = abi.Outputs()
-        o.n_trials = self.n
-        for k in ("final_wealth", "max_dd", "num_trades", "journal_count", "journal_volume",
-                  "start_offset", "flags", "regime_days", "jump_days"):
-            setattr(o, k, getattr(self, k).ctypes.data)
-        return o
-
-    def as_dict(self):
-        return {k: getattr(self, k) for k in ("final_wealth", "max_dd", "num_trades", "journal_count",
-                                               "journal_volume", "start_offset", "flags", "regime_days",
-                                               "jump_days")}
 
 
 def run(params: abi.Params, tape: HostTape, first: int = 0, n: int | None = None) -> HostOutputs:

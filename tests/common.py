@@ -1,0 +1,56 @@
+"""Shared helpers of the test-suite: golden-case loading and comparison rules."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import numpy as np
+
+from letf_monte_carlo_b200 import abi  # noqa: F401
+from oracle import make_golden as mg
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json")))
+GOLDEN_NAMES = [os.path.basename(f)[:-5] for f in GOLDEN_FILES]
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN_DIR, name + ".json")) as f:
+        doc = json.load(f)
+    return doc
+
+
+def case_inputs(doc):
+    """(config namespace, regime_model, params, keepalive, tape) of a golden case."""
+    return mg.case_inputs(doc["case"])
+
+
+def expected_arrays(doc):
+    sids = doc["case"]["strategies"]
+    exp = doc["expected"]
+    fw = np.array([exp[s]["final_wealth"] for s in sids])
+    dd = np.array([exp[s]["max_dd"] for s in sids])
+    nt = np.array([exp[s]["num_trades"] for s in sids])
+    jc = np.array([exp[s]["journal_count"] for s in sids])
+    jv = np.array([exp[s]["journal_volume"] for s in sids])
+    return fw, dd, nt, jc, jv
+
+
+def assert_matches_reference(out, doc, rtol, dd_atol, exact_counts=True, journal=True):
+    """out: HostOutputs-like.  Integer work (regime days, start offsets, trade and journal counts)
+    must be identical; wealth within rtol (relative), drawdown within dd_atol (absolute)."""
+    fw, dd, nt, jc, jv = expected_arrays(doc)
+    meta = doc["meta"]
+    np.testing.assert_allclose(out.final_wealth, fw, rtol=rtol, atol=0)
+    np.testing.assert_allclose(out.max_dd, dd, rtol=0, atol=dd_atol)
+    if exact_counts:
+        np.testing.assert_array_equal(out.num_trades, nt)
+        if journal and out.journal_count is not None:
+            np.testing.assert_array_equal(out.journal_count, jc)
+            np.testing.assert_allclose(out.journal_volume, jv, rtol=max(rtol, 1e-12), atol=1e-9)
+    np.testing.assert_array_equal(out.start_offset, np.array(meta["start_offset"]))
+    np.testing.assert_array_equal(out.regime_days.T, np.array(meta["regime_days"]))
+    np.testing.assert_array_equal(out.jump_days, np.array(meta["jump_days"]))
+    rep = (out.flags & abi.FLAG_REPAIRED) != 0
+    np.testing.assert_array_equal(rep, np.array(meta["repaired"]))

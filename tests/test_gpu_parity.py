@@ -1,0 +1,338 @@
+"""Parity of the CUDA path (through the C-ABI of include/letf_b200.h) with the oracle and with
+the golden vectors generated from the live reference.  Runs on the B200 box (-m gpu).
+
+Bars (north star): shared pre-drawn shocks -> regime-state sequences (regime day counts, start
+offsets, jump days) and trade / journal counts bit-exact, terminal wealth <= 1e-6 relative with
+fp64 accumulation (we hold 1e-11); fp32 throughput mode has its own stated tolerance; on-device
+Philox draws must match the reference's distributions (KS) and summary quantiles.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from letf_monte_carlo_b200 import abi, synthetic
+from letf_monte_carlo_b200.params import build_params
+from letf_monte_carlo_b200.tape import HostTape, make_tape
+from oracle import oracle as orc
+from tests.common import GOLDEN_NAMES, assert_matches_reference, case_inputs, expected_arrays, load_case
+
+pytestmark = pytest.mark.gpu
+ALL19 = ["S%d" % i for i in range(1, 20)]
+
+
+def _engine(params, keep, precision):
+    from letf_monte_carlo_b200.engine import PathEngine
+    return PathEngine(params, keep, precision=precision, device=0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_f64_tape_matches_reference_golden(name, engine_lib):
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    n = tape.n_tapes * (2 if params.antithetic_pairs else 1)
+    with _engine(params, keep, "f64") as eng:
+        out = eng.run_host(n, rng_mode=abi.RNG_TAPE, tape=tape, journal=True)
+    assert_matches_reference(out, doc, rtol=1e-11, dd_atol=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_f64_tape_matches_oracle_all_outputs(name, engine_lib):
+    """device buffers (letf_run) instead of the host convenience path, compared field by field"""
+    import torch
+    from letf_monte_carlo_b200.engine import DeviceTape
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    n = tape.n_tapes * (2 if params.antithetic_pairs else 1)
+    o = orc.run(params, tape)
+    with _engine(params, keep, "f64") as eng:
+        dt = DeviceTape(tape, eng.device)
+        out = eng.run(n, rng_mode=abi.RNG_TAPE, tape=dt, journal=True)
+        torch.cuda.synchronize()
+        h = out.to_host()
+    np.testing.assert_allclose(h.final_wealth, o.final_wealth, rtol=1e-11)
+    np.testing.assert_allclose(h.max_dd, o.max_dd, atol=1e-12)
+    for k in ("num_trades", "journal_count", "start_offset", "flags", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(h, k), getattr(o, k), err_msg=k)
+    np.testing.assert_allclose(h.journal_volume, o.journal_volume, rtol=1e-11, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1"])
+def test_f32_tape_close_to_reference(name, engine_lib):
+    """fp32 throughput mode on the same tape: 2e-4 relative on terminal wealth over <= 5 years,
+    1e-4 absolute on drawdown, < 2 % of (strategy, trial) cells with a different trade count."""
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    n = tape.n_tapes * (2 if params.antithetic_pairs else 1)
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run_host(n, rng_mode=abi.RNG_TAPE, tape=tape, journal=True)
+    assert_matches_reference(out, doc, rtol=2e-4, dd_atol=1e-4, exact_counts=False)
+    assert np.mean(out.num_trades != expected_arrays(doc)[2]) < 0.02
+
+
+def test_constant_window_corner(engine_lib):
+    from tests.test_kernel_emulation import drifty_case
+    params, keep, tape = drifty_case(years=3, n=64, seed=11)
+    o = orc.run(params, tape)
+    with _engine(params, keep, "f64") as eng:
+        out = eng.run_host(64, rng_mode=abi.RNG_TAPE, tape=tape, journal=True)
+    np.testing.assert_allclose(out.final_wealth, o.final_wealth, rtol=1e-11)
+    np.testing.assert_array_equal(out.num_trades, o.num_trades)
+    np.testing.assert_array_equal(out.journal_count, o.journal_count)
+
+
+@pytest.mark.parametrize("variant,years,precision", [("default", 2, "f64"), ("vix_te", 1, "f64"), ("no_joint", 1, "f64"),
+                                                     ("durations", 1, "f64"), ("normal_c2", 3, "f64")])
+def test_philox_record_replays_through_oracle(variant, years, precision, engine_lib):
+    """the on-device Philox path records the variates it consumed; the oracle on that tape must agree"""
+    sids = ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"]
+    doc = {"case": dict(variant=variant, years=years, n_tapes=40, seed=0, cfg={}, strategies=sids)}
+    ns, model, params, keep, _ = case_inputs(doc)
+    n_t = 40
+    n = n_t * (2 if params.antithetic_pairs else 1)
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    with _engine(params, keep, precision) as eng:
+        out = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec, journal=True)
+        plain = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX, journal=True)
+    assert not (out.flags & abi.FLAG_SPELL_OVERFLOW).any()
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(out.final_wealth, o.final_wealth, rtol=1e-10)
+    np.testing.assert_array_equal(out.num_trades, o.num_trades)
+    np.testing.assert_array_equal(out.journal_count, o.journal_count)
+    np.testing.assert_array_equal(out.regime_days, o.regime_days)
+    np.testing.assert_array_equal(out.jump_days, o.jump_days)
+    np.testing.assert_array_equal(out.flags, o.flags)
+    np.testing.assert_array_equal(plain.final_wealth, out.final_wealth)
+    np.testing.assert_array_equal(plain.num_trades, out.num_trades)
+
+
+def test_partition_invariance_and_kernel_variants(engine_lib):
+    """results are a pure function of (seed, trial id): independent of the launch partition and of
+    which instantiation (lean benchmark build vs the all-strategies build) runs them"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    model = synthetic.fallback_regime_model("default")
+    p_lean, k1 = build_params(["S1", "S2", "S3"], 1, model, ns)
+    p_full, k2 = build_params(["S1", "S2", "S3", "S4", "S19"], 1, model, ns)
+    p_full.asset_mask = p_lean.asset_mask
+    n = 3000
+    with _engine(p_lean, k1, "f32") as e1, _engine(p_full, k2, "f32") as e2:
+        a = e1.run_host(n, seed=7)
+        b0 = e1.run_host(1000, seed=7, first_trial=0)
+        b1 = e1.run_host(2000, seed=7, first_trial=1000)
+        c = e2.run_host(n, seed=7)
+        assert e1.launch_info()["regs_per_thread"] < e2.launch_info()["regs_per_thread"]
+    np.testing.assert_array_equal(a.final_wealth[:, :1000], b0.final_wealth)
+    np.testing.assert_array_equal(a.final_wealth[:, 1000:], b1.final_wealth)
+    np.testing.assert_array_equal(a.max_dd[:, 1000:], b1.max_dd)
+    # same shocks through a different instantiation: tiny fp32 reassociation differences only
+    np.testing.assert_allclose(c.final_wealth[:3], a.final_wealth, rtol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_philox_draw_distributions_on_device(precision, engine_lib):
+    doc = {"case": dict(variant="vix_te", years=2, n_tapes=1, seed=0, cfg={}, strategies=["S1", "S2"])}
+    ns, model, params, keep, _ = case_inputs(doc)
+    params.asset_mask = 0x3F
+    n_t = 64
+    G, T = params.sim_days + params.buffer_days, params.sim_days
+    rec = HostTape(n_t, G, T, 512)
+    with _engine(params, keep, precision) as eng:
+        eng.run_host(2 * n_t, seed=99, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+    reg = rec.regime_full(params)
+
+    def ks(sample, dist, alpha=1e-4):
+        d, p = stats.kstest(sample, dist.cdf)
+        assert p > alpha, (d, p)
+
+    ks(rec.x.ravel(), stats.norm)
+    used = np.arange(G)[:, None] < (rec.start_offset[None, :] + T)
+    used[0] = False
+    ks(rec.vix_n[used], stats.norm)
+    ks(rec.irx_n[used], stats.norm)
+    for r in (0, 1):
+        ks(rec.chi2[reg == r], stats.chi2(params.joint[r].nu))
+    ks(rec.liq_n[1:].ravel(), stats.norm)
+    ks(rec.jump_u[1:].ravel(), stats.uniform)
+    ks(rec.jump_t[1:].ravel(), stats.t(5))
+    for a in range(abi.N_ASSETS):
+        ks(rec.te_t[a, 1:].ravel(), stats.t(params.assets[a].te_df))
+
+
+def test_config1_vol_drag_known_answer(engine_lib):
+    """validation.py:18-87 (BASELINE config 1): 10 000 paths x 252 days, zero drift, sigma 15 %, L = 3:
+    median annual return within 1.5 % (abs) of -0.5 L^2 sigma^2 = -10.125 %; and L = 2 (validation.py:90-188)
+    within 2 % of -4.5 %."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False, LETF_CONFIGS=synthetic.pure_leverage_assets())
+    ns.ASSETS = ns.LETF_CONFIGS
+    params, keep = build_params(["B_UPRO", "S3", "S2"], 1, synthetic.normal_regime_model("c1"), ns)
+    for precision in ("f32", "f64"):
+        with _engine(params, keep, precision) as eng:
+            out = eng.run_host(10000, seed=42)
+        ann = out.final_wealth / params.initial_capital - 1.0
+        assert abs(np.median(ann[0]) - (-0.10125)) < 0.015
+        assert abs(np.median(ann[1]) - (-0.045)) < 0.02
+        assert abs(np.median(ann[2]) - (-0.01125)) < 0.02
+        assert (out.flags == 0).all()
+
+
+def test_quantiles_match_reference_distribution(engine_lib):
+    """summary-quantile agreement of Philox runs with the reference's arithmetic on numpy draws
+    (validation.py:45-57 vectorised): two-sample KS on terminal wealth, 1e5 paths each"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False, LETF_CONFIGS=synthetic.pure_leverage_assets())
+    ns.ASSETS = ns.LETF_CONFIGS
+    params, keep = build_params(["B_UPRO"], 1, synthetic.normal_regime_model("c1"), ns)
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run_host(100000, seed=1)
+    rng = np.random.default_rng(42)
+    r = rng.normal(0, 0.15 / np.sqrt(252), (100000, 252))
+    ref = 1e4 * np.prod(1 + 3.0 * r, axis=1)
+    d, p = stats.ks_2samp(out.final_wealth[0], ref)
+    assert p > 1e-3, (d, p)
+    for q in (10, 25, 50, 75, 90):
+        a, b = np.percentile(out.final_wealth[0], q), np.percentile(ref, q)
+        assert abs(a / b - 1) < 0.01
+
+
+def test_run_strategies_matches_oracle(engine_lib):
+    """run_strategy_fixed seam: strategy rules on caller-supplied series (strategy.py:55)"""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    T, n = 600, 24
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(ALL19, T / 252, synthetic.fallback_regime_model(), ns)
+    rets = {a: np.ascontiguousarray(rng.standard_t(4, (T, n)) * s) for a, s in
+            zip(abi.ASSET_NAMES, (0.03, 0.03, 0.02, 0.025, 0.01, 0.013))}
+    vix = np.ascontiguousarray(15 + 10 * rng.random((T, n)))
+    regime = np.ascontiguousarray((rng.random((T, n)) < 0.2).astype(np.int32))
+    tlt = np.ascontiguousarray(rng.normal(0, 0.008, (T, n)))
+    from oracle.oracle import HostOutputs
+    o = HostOutputs(params.n_strategies, n)
+    s = abi.Series()
+    s.n_paths, s.sim_days = n, T
+    for a, name in enumerate(abi.ASSET_NAMES):
+        s.asset_ret[a] = rets[name].ctypes.data
+    s.tlt_ret, s.vix, s.regime = tlt.ctypes.data, vix.ctypes.data, regime.ctypes.data
+    assert orc.lib().letf_oracle_run_strategies(C.byref(params), C.byref(s), C.byref(o.as_struct())) == 0
+    with _engine(params, keep, "f64") as eng:
+        h = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, journal=True).to_host()
+    np.testing.assert_allclose(h.final_wealth, o.final_wealth, rtol=1e-11)
+    np.testing.assert_allclose(h.max_dd, o.max_dd, atol=1e-12)
+    np.testing.assert_array_equal(h.num_trades, o.num_trades)
+    np.testing.assert_array_equal(h.journal_count, o.journal_count)
+
+
+def test_trade_list_replay_matches_oracle(engine_lib):
+    doc = load_case("inst_1y")
+    ns, model, params, keep, tape = case_inputs(doc)
+    sids = doc["case"]["strategies"]
+    with _engine(params, keep, "f64") as eng:
+        for sid in ("S7", "S8", "S13", "S19"):
+            s = sids.index(sid)
+            got = eng.trade_list(3, s, rng_mode=abi.RNG_TAPE, tape=tape)
+            ref = orc.trade_list(params, tape, 3, s)
+            assert len(got) == len(ref) == doc["expected"][sid]["journal_count"][3]
+            for g, r in zip(got, ref):
+                assert (g["day_index"], g["asset"], g["action"]) == (r["day_index"], r["asset"], r["action"])
+                assert abs(g["shares"] / r["shares"] - 1) < 1e-10 and abs(g["price"] / r["price"] - 1) < 1e-10
+        assert eng.trade_list(3, sids.index("S4"), rng_mode=abi.RNG_TAPE, tape=tape) == []   # not in TAXABLE_IDS
+
+
+def test_reduce_matches_numpy(engine_lib):
+    import torch
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(["S1", "S2", "S3", "S4"], 1, synthetic.fallback_regime_model(), ns)
+    n = 20000
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run(n, seed=3)
+        sm = eng.new_summary(bench_strategy=1)
+        eng.reduce(out, sm, n_trials=n // 2)
+        eng.reduce(out_slice(out, n // 2, n), sm)          # accumulates
+        torch.cuda.synchronize()
+        h = out.to_host()
+        hist = sm.hist.cpu().numpy(); mom = sm.moments.cpu().numpy(); ext = sm.extrema.cpu().numpy()
+        cnt = sm.counters.cpu().numpy()
+        eng.reset_summary(sm)
+        torch.cuda.synchronize()
+        assert int(sm.hist.sum()) == 0 and int(sm.counters.sum()) == 0
+    W0, years = params.initial_capital, params.sim_years
+    for s in range(4):
+        w = h.final_wealth[s]
+        # a switch on a -99.9 % day can push S4's equity below zero (ret = r - cost, strategy.py:140-150);
+        # the reduction clamps such ratios into the first bin (letf_reduce.cu)
+        ratio = w / W0
+        metrics = [np.log10(np.maximum(ratio, 1e-300)), np.maximum(ratio, 0.0) ** (1 / years) - 1, h.max_dd[s]]
+        for q, m in enumerate(metrics):
+            ref, _ = np.histogram(np.clip(m, sm.lo[q], np.nextafter(sm.hi[q], -np.inf)), bins=sm.bin_edges(q))
+            assert np.abs(hist[s, q] - ref).sum() <= 4          # bin-edge rounding only
+            assert hist[s, q].sum() == n
+            np.testing.assert_allclose(mom[s, q, 0], m.sum(), rtol=1e-9)
+            np.testing.assert_allclose(mom[s, q, 1], (m * m).sum(), rtol=1e-9)
+            np.testing.assert_allclose(ext[s, q], [m.min(), m.max()], rtol=1e-12)
+        assert cnt[s, 0] == n
+        assert cnt[s, 1] == int((w > h.final_wealth[1]).sum())       # wins vs S2 by trial index
+        assert cnt[s, 2] == int(h.num_trades[s].sum())
+
+
+def out_slice(out, lo, hi):
+    """view of columns [lo, hi) of a DeviceOutputs as a new struct-compatible object"""
+    from letf_monte_carlo_b200.outputs import DeviceOutputs, FIELDS
+    v = DeviceOutputs.__new__(DeviceOutputs)
+    v.n_strategies = out.n_strategies
+    v.n = hi - lo
+    for k in FIELDS:
+        t = getattr(out, k)
+        setattr(v, k, None if t is None else t[..., lo:hi].contiguous())
+    return v
+
+
+def test_errors_are_reported_not_swallowed(engine_lib):
+    from letf_monte_carlo_b200.engine import EngineError, NonFiniteTrials, PathEngine
+    ns = synthetic.config_namespace()
+    params, keep = build_params(["S1"], 1, synthetic.fallback_regime_model(), ns)
+    with _engine(params, keep, "f32") as eng:
+        with pytest.raises(EngineError):
+            eng.run_host(4, rng_mode=abi.RNG_TAPE, tape=None)            # tape mode without a tape
+        small = HostTape(1, 10, 5, 4)
+        with pytest.raises(EngineError):
+            eng.run_host(2, rng_mode=abi.RNG_TAPE, tape=small)           # wrong day counts
+    bad = build_params(["S4"], 1, synthetic.fallback_regime_model(), ns)[0]
+    bad.strategies[0].p[0] = 150.0                                       # unsupported SMA window
+    with pytest.raises(EngineError):
+        PathEngine(bad, (), precision="f32", device=0)
+    # non-finite generated returns -> the reference raises ValueError out of the trial
+    nf, k = build_params(["S2"], 1, synthetic.fallback_regime_model(), ns)
+    nf.joint[0].mu[0] = float("nan")
+    with _engine(nf, k, "f32") as eng:
+        with pytest.raises(NonFiniteTrials):
+            eng.run_host(8, seed=1)
+
+
+def test_full_size_properties_config2(engine_lib):
+    """BASELINE config 2 at its full size (100k trials x 7 560 days, TQQQ/UPRO/SSO with expense,
+    borrow and tracking error): size-independent properties."""
+    import torch
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False)
+    params, keep = build_params(["S1", "B_UPRO", "S3"], 30, synthetic.normal_regime_model("c2"), ns)
+    n = 100000
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run(n, seed=2024)
+        halves = [eng.run(n // 2, seed=2024, first_trial=f) for f in (0, n // 2)]
+        torch.cuda.synchronize()
+        h = out.to_host()
+        h0, h1 = (x.to_host() for x in halves)
+    np.testing.assert_array_equal(h.final_wealth, np.concatenate([h0.final_wealth, h1.final_wealth], axis=1))
+    assert (h.flags == 0).all() and np.isfinite(h.final_wealth).all() and (h.final_wealth > 0).all()
+    assert (h.max_dd >= 0).all() and (h.max_dd < 1).all() and (h.num_trades == 0).all()
+    # E[log growth] per day = L mu - L^2 sigma^2 / 2 - ER/252 - borrow + O(mu^2): known answer within 5 se
+    T = params.sim_days
+    vol = np.array([0.16, 0.24]) / np.sqrt(252); mu = np.array([0.08, 0.10]) / 252
+    for s, (a, u) in enumerate((("TQQQ", 1), ("UPRO", 0), ("SSO", 0))):
+        c = ns.ASSETS[a]; L = c["leverage"]
+        cost = c["expense_ratio"] / 252 + (L - 1) * (0.045 + c["borrow_spread"]) / 252
+        m = L * mu[u] - cost
+        g = m - 0.5 * (L * vol[u]) ** 2 - 0.5 * m * m            # second-order log expansion
+        lg = np.log(h.final_wealth[s] / params.initial_capital) / T
+        se = L * vol[u] / np.sqrt(T * n)
+        assert abs(lg.mean() - g) < 5 * se + 2e-6, (a, lg.mean(), g, se)

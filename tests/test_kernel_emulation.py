@@ -1,0 +1,142 @@
+"""The fused kernel's per-trial body (csrc/letf_core.cuh), compiled for the HOST by tests/emu
+(test-only build), against the oracle and the golden vectors.  This exercises the kernel
+*source* on the CPU box; the same comparisons run on the device in test_gpu_parity.py."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from letf_monte_carlo_b200 import abi, synthetic
+from letf_monte_carlo_b200.params import build_params
+from letf_monte_carlo_b200.tape import HostTape, make_tape
+from oracle import oracle as orc
+from tests.common import GOLDEN_NAMES, assert_matches_reference, case_inputs, load_case
+from tests.emu import emu
+
+ALL19 = ["S%d" % i for i in range(1, 20)]
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_f64_kernel_body_reproduces_reference(name):
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    out = emu.run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE)
+    # streaming fp64 vs the reference's array arithmetic: <= 1e-6 is the north-star bound, we hold 1e-11
+    assert_matches_reference(out, doc, rtol=1e-11, dd_atol=1e-12)
+
+
+def drifty_case(years=3, n=12, seed=7):
+    """iid-normal market with mu = 1.2 sigma: runs of >= 20 non-negative returns are common, so the
+    downside-vol windows hit pandas' recompute-on-collapse corner (oracle: orc_roll_std)."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False)
+    model = synthetic.normal_regime_model("c2")
+    vol = np.array([0.16, 0.24, 0.12]) / np.sqrt(252)
+    model["synthetic_normal"]["mu"] = list(1.2 * vol)
+    params, keep = build_params(ALL19, years, model, ns)
+    return params, keep, make_tape(params, n, seed)
+
+
+def test_f64_constant_window_corner_matches_oracle():
+    params, keep, tape = drifty_case()
+    o = orc.run(params, tape)
+    e = emu.run(params, tape, precision=abi.PREC_F64)
+    np.testing.assert_allclose(e.final_wealth, o.final_wealth, rtol=1e-12)
+    np.testing.assert_array_equal(e.num_trades, o.num_trades)
+    np.testing.assert_array_equal(e.journal_count, o.journal_count)
+    assert o.num_trades[9].min() > 0      # S10 (downside vol) traded
+
+
+@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1"])
+def test_f32_kernel_body_close_to_reference(name):
+    """throughput mode (fp32 shocks / returns / signals, fp64 wealth compounding) on the SAME tape:
+    stated tolerance 2e-4 relative on terminal wealth over <= 5 years, 1e-4 absolute on drawdown."""
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    out = emu.run(params, tape, precision=abi.PREC_F32, rng_mode=abi.RNG_TAPE)
+    assert_matches_reference(out, doc, rtol=2e-4, dd_atol=1e-4, exact_counts=False)
+    fw, dd, nt, jc, jv = __import__("tests.common", fromlist=["x"]).expected_arrays(doc)
+    assert np.mean(out.num_trades != nt) < 0.02
+
+
+@pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2)])
+def test_philox_record_replays_through_oracle(variant, years):
+    """RNG_PHILOX_RECORD writes every variate it consumes; feeding that tape to the oracle must give
+    the same results -> the Philox path consumes draws exactly where the tape semantics say."""
+    case = dict(variant=variant, years=years, n_tapes=3, seed=0, cfg={},
+                strategies=ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"])
+    doc = {"case": case}
+    ns, model, params, keep, _ = case_inputs(doc)
+    G = params.sim_days + params.buffer_days
+    rec = HostTape(3, G, params.sim_days, 256)
+    n = 6 if params.antithetic_pairs else 3
+    e = emu.run(params, rec, precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX_RECORD, seed=1234, n=n)
+    assert not (e.flags & abi.FLAG_SPELL_OVERFLOW).any()
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(e.final_wealth, o.final_wealth, rtol=1e-11)
+    np.testing.assert_array_equal(e.num_trades, o.num_trades)
+    np.testing.assert_array_equal(e.start_offset, o.start_offset)
+    np.testing.assert_array_equal(e.regime_days, o.regime_days)
+    np.testing.assert_array_equal(e.jump_days, o.jump_days)
+    # pure Philox mode (nothing recorded) is the same computation
+    p = emu.run(params, HostTape(1, G, params.sim_days, 1), precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX,
+                seed=1234, n=n)
+    np.testing.assert_array_equal(p.final_wealth, e.final_wealth)
+
+
+def test_philox_trials_are_pure_functions_of_seed_and_id():
+    doc = {"case": dict(variant="default", years=0.5, n_tapes=1, seed=0, cfg={}, strategies=["S1", "S2", "S4", "S19"])}
+    ns, model, params, keep, _ = case_inputs(doc)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    a = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=5, first=0, n=8)
+    b = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=5, first=4, n=4)
+    c = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=6, first=0, n=8)
+    np.testing.assert_array_equal(a.final_wealth[:, 4:], b.final_wealth)
+    np.testing.assert_array_equal(a.num_trades[:, 4:], b.num_trades)
+    assert not np.array_equal(a.final_wealth, c.final_wealth)
+    # antithetic twins share the start offset and regime path (mc_runner.py:145-153)
+    np.testing.assert_array_equal(a.start_offset[0::2], a.start_offset[1::2])
+    np.testing.assert_array_equal(a.regime_days[:, 0::2], a.regime_days[:, 1::2])
+
+
+def _ks(sample, cdf, alpha=1e-4):
+    d, p = stats.kstest(sample, cdf)
+    assert p > alpha, (d, p)
+
+
+@pytest.mark.parametrize("precision", [abi.PREC_F64, abi.PREC_F32])
+def test_philox_draw_distributions(precision):
+    """north star: on-device draws must match the reference's distributions (KS).  The recorded
+    variates of the institutional generator: N(0,1), chi2(nu_regime), U[0,1), t(5), t(te_df)."""
+    doc = {"case": dict(variant="vix_te", years=2, n_tapes=1, seed=0, cfg={}, strategies=["S1", "S2"])}
+    ns, model, params, keep, _ = case_inputs(doc)
+    params.asset_mask = 0x3F
+    n_t = 24
+    G, T = params.sim_days + params.buffer_days, params.sim_days
+    rec = HostTape(n_t, G, T, 512)
+    emu.run(params, rec, precision=precision, rng_mode=abi.RNG_PHILOX_RECORD, seed=99, n=2 * n_t)
+    reg = rec.regime_full(params)
+    _ks(rec.x.ravel(), stats.norm.cdf)
+    # VIX / IRX noise is only consumed up to the end of the window (g < start_offset + T)
+    used = np.arange(G)[:, None] < (rec.start_offset[None, :] + T)
+    assert (rec.vix_n[~used] == 0).all()
+    used[0] = False                                  # no VIX draw on generated day 0 (engine.py:103)
+    _ks(rec.vix_n[used], stats.norm.cdf)
+    _ks(rec.irx_n[used], stats.norm.cdf)
+    for r in (0, 1):
+        _ks(rec.chi2[reg == r], stats.chi2(params.joint[r].nu).cdf)
+    _ks(rec.liq_n[1:].ravel(), stats.norm.cdf)
+    _ks(rec.cred_n[1:].ravel(), stats.norm.cdf)
+    _ks(rec.jump_u[1:].ravel(), stats.uniform.cdf)
+    _ks(rec.jump_t[1:].ravel(), stats.t(5).cdf)
+    assert abs(np.mean(rec.sign[1:] > 0) - 0.5) < 0.01
+    for a in range(abi.N_ASSETS):       # df: 4.0, 6.5 (Marsaglia-Tsang), 7.0, 5, 10, 10
+        _ks(rec.te_t[a, 1:].ravel(), stats.t(params.assets[a].te_df).cdf)
+    # independence across streams / days: no correlation between the components of one day
+    c = np.corrcoef(np.stack([rec.x[:, 0].ravel(), rec.x[:, 1].ravel(), rec.x[:, 2].ravel(),
+                              rec.chi2.ravel(), np.where(used, rec.vix_n, rec.x[:, 0] * 0 + np.random.default_rng(1).standard_normal(used.shape)).ravel()]))
+    assert np.abs(c - np.eye(5)).max() < 0.01
+    # dwell times: geometric with p = 1 - clip(p_stay, .80, .995)
+    sp0 = rec.spells[0::2][:8].ravel().astype(float)
+    _ks(sp0 - np.random.default_rng(0).random(sp0.size), stats.expon(scale=-1 / np.log(0.99)).cdf, alpha=1e-5)
+    so = rec.start_offset
+    assert so.min() >= 50 and so.max() < 1260
