@@ -1,0 +1,147 @@
+"""Host-side logic: parameter packing from the reference's dicts, trial sharding, result views,
+and the one exchange step (summary allreduce) over gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from letf_monte_carlo_b200 import abi, synthetic
+from letf_monte_carlo_b200 import config as cfg
+from letf_monte_carlo_b200.distributed import shard_range
+from letf_monte_carlo_b200.params import UnsupportedConfig, build_params, nearest_psd_matrix
+from letf_monte_carlo_b200.trade import TAXABLE_IDS, TradeJournal
+
+
+def test_config_surface_matches_reference_names():
+    for name in ("INITIAL_CAPITAL", "ASSETS", "LETF_CONFIGS", "BASE_SPREAD_BPS", "REBALANCE_COST_PER_DOLLAR",
+                 "CASH_RATE_BY_REGIME", "N_WORKERS", "NUM_SIMULATIONS", "USE_ANTITHETIC_VARIATES", "USE_MOMENT_MATCHING",
+                 "USE_GPU", "N_REGIMES", "STUDENT_T_DF", "SIM_ENGINE_MODE", "USE_RANDOM_START", "RANDOM_START_METHOD",
+                 "RANDOM_START_BUFFER_YEARS", "STRATEGIES"):
+        assert hasattr(cfg, name), name
+    assert list(cfg.STRATEGIES) == ["S%d" % i for i in range(1, 20)]
+    assert list(cfg.ASSETS) == list(abi.ASSET_NAMES)
+    assert TAXABLE_IDS == ["S%d" % i for i in range(7, 20)]
+
+
+def test_build_params_defaults():
+    ns = synthetic.config_namespace()
+    p, keep = build_params(list(cfg.STRATEGIES), 10, synthetic.fallback_regime_model(), ns)
+    assert p.sim_days == 2520 and p.buffer_days == 1260 and p.random_start == 1 and p.antithetic_pairs == 1
+    assert p.market_mode == abi.MARKET_JOINT_T and p.moment_matching == 1 and p.has_stress == 1 and p.has_funding == 1
+    assert p.n_strategies == 19 and p.asset_mask == 0b011101      # TQQQ, SSO, TMF, SPY
+    assert [p.strategies[k].taxable for k in range(19)] == [0] * 6 + [1] * 13
+    assert p.strategies[5].weights[0] == 0.6 and p.strategies[5].weights[3] == 0.4
+    r = np.array([[p.joint[0].rbar[i][j] for j in range(3)] for i in range(3)])
+    np.testing.assert_allclose(np.diag(r), 1.0)
+    np.testing.assert_allclose(r, nearest_psd_matrix([[1, .9, -.2], [.9, 1, -.18], [-.2, -.18, 1]]), atol=1e-15)
+
+
+def test_build_params_dispatch_and_rejections():
+    ns = synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid")
+    p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model(), ns)
+    assert p.market_mode == abi.MARKET_PARAM_T and p.has_stress == 0 and p.has_funding == 0   # engine.py:81-97
+    p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model("no_joint"), synthetic.config_namespace())
+    assert p.market_mode == abi.MARKET_PARAM_T and p.has_stress == 1
+    with pytest.raises(UnsupportedConfig):
+        build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(RANDOM_START_METHOD="regime"))
+    with pytest.raises(UnsupportedConfig):
+        build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(N_REGIMES=3))
+    tm = np.array([[2.0, 0.0], [0.5, 0.5]])       # row normalisation of engine.py:264-272
+    m = synthetic.fallback_regime_model(); m["transition_matrix"] = tm
+    p, _ = build_params(["S1"], 1, m, synthetic.config_namespace())
+    assert p.transition[0][0] == 1.0 and p.transition[0][1] == 0.0
+
+
+def test_shard_range_partitions_trials():
+    for n in (0, 1, 7, 200, 1001, 10_000_000):
+        for ws in (1, 2, 3, 8):
+            for pair in (True, False):
+                parts = [shard_range(n, r, ws, pair) for r in range(ws)]
+                assert parts[0][0] == 0 and parts[-1][1] == n
+                assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+                if pair:
+                    assert all(lo % 2 == 0 for lo, hi in parts if hi > lo)
+                sizes = [hi - lo for lo, hi in parts]
+                assert max(sizes) - min(sizes) <= (3 if pair else 1)
+
+
+def test_trade_journal_semantics():
+    """trade.py:20-73"""
+    j = TradeJournal()
+    j.log_allocation_change(5, "TQQQ", 0.0, 0.5, 10000.0, 50.0)      # buy 100 shares
+    j.log_allocation_change(6, "TQQQ", 0.5, 0.5, 10000.0, 50.0)      # |delta| < 0.001 -> no entry
+    j.log_allocation_change(7, "TQQQ", 0.5, 0.2, 11000.0, 55.0)      # sell down to 40 shares
+    j.log_allocation_change(8, "TQQQ", 0.2, 0.4, 11000.0, 0.0)       # price <= 0 -> ignored
+    t = j.get_full_trades()
+    assert [(x["day_index"], x["action"]) for x in t] == [(5, "BUY"), (7, "SELL")]
+    assert t[0]["shares"] == 100.0 and abs(t[1]["shares"] - 60.0) < 1e-12
+    assert j.get_summary()["count"] == 2
+
+
+def test_result_views_behave_like_reference_dicts():
+    from letf_monte_carlo_b200.mc_runner import MonteCarloRun
+    from letf_monte_carlo_b200.outputs import HostOutputs
+
+    class FakeEngine:
+        params = abi.Params()
+
+        def trade_list(self, trial, s, seed=0):
+            return [{"day_index": 1, "asset": "TQQQ", "action": "BUY", "shares": 1.0, "price": 1.0, "dollar_amount": 1.0}]
+
+    out = HostOutputs(2, 5)
+    out.final_wealth[:] = np.arange(10).reshape(2, 5) + 1.0
+    out.num_trades[:] = 30
+    out.flags[2] = abi.FLAG_REPAIRED
+    run = MonteCarloRun(FakeEngine(), out, ["S2", "S7"], 10, seed=1, first_trial=0, n_local=5, n_total=5, taxable_ids=["S7"])
+    assert list(run) == ["S2", "S7"] and len(run["S2"]) == 5
+    r = run["S7"][3]
+    assert r["Final_Wealth"] == 9.0 and r["Num_Trades"] == 30 and r["Trades_Per_Year"] == 3.0
+    assert r.get("Max_DD", 0) == 0.0 and r.get("Nope", 7) == 7
+    assert len(r.get("Trade_List", [])) == 1 and run["S2"][3].get("Trade_List", []) == []
+    assert run["S2"][2]["Metadata"]["layer_checks"]["repaired_after_validation"] is True
+    # reporting.py:358: [r['Final_Wealth'] for r in results]
+    assert [x["Final_Wealth"] for x in run["S2"]] == [1.0, 2.0, 3.0, 4.0, 5.0]
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, ws, port, q):
+    import torch
+    import torch.distributed as dist
+    from letf_monte_carlo_b200.distributed import allreduce_summary, shard_range as sr, world
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    assert world() == (rank, ws)
+    n = 1001
+    lo, hi = sr(n, rank, ws)
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=n)                                    # the same "per-trial metric" on every rank
+    mine = x[lo:hi]
+    edges = np.linspace(-5, 5, 65)
+    hist = torch.from_numpy(np.histogram(mine, edges)[0].astype(np.int64)).reshape(1, 1, -1).clone()
+    mom = torch.tensor([[[mine.sum(), (mine ** 2).sum()]]], dtype=torch.float64)
+    ext = torch.tensor([[[mine.min(), mine.max()]]], dtype=torch.float64)
+    cnt = torch.tensor([[len(mine), 0, 0, 0]], dtype=torch.int64)
+    allreduce_summary(hist, mom, ext, cnt)
+    ok = (np.array_equal(hist.numpy().ravel(), np.histogram(x, edges)[0]) and abs(float(mom[0, 0, 0]) - x.sum()) < 1e-9
+          and float(ext[0, 0, 0]) == x.min() and float(ext[0, 0, 1]) == x.max() and int(cnt[0, 0]) == n)
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_summary_allreduce_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
