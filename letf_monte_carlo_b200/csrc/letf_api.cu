@@ -94,23 +94,24 @@ struct LogArgs {
   double* shares = nullptr; double* price = nullptr;
 };
 
-static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask) {
+static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask,
+                                       int n_assets) {
   const KernelEntry* best = nullptr;
   for (int i = 0; i < kernel_count(); i++) {
     const KernelEntry* k = kernel_at(i);
     if (k->precision != e->precision || k->market != market) continue;
     if (need_io && !k->tapeio) continue;
-    if (k->ns < n_strat || (tmask & ~k->tm)) continue;
+    if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
     if (!best) { best = k; continue; }
     // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
-    int a = k->ns * 64 + __builtin_popcount(k->tm) * 2 + k->tapeio;
-    int b = best->ns * 64 + __builtin_popcount(best->tm) * 2 + best->tapeio;
+    int a = k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio;
+    int b = best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio;
     if (a < b) best = k;
   }
   return best;
 }
 
-template <typename R, int NS>
+template <typename R, int NS, int NA>
 static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, uint64_t seed, int64_t first,
                         int64_t n, int rng_mode, const LetfTape* tape, const LetfOutputs* out,
                         const LetfSeries* series, const LogArgs& lg) {
@@ -120,6 +121,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   if (max_blocks < 1) return fail(LETF_ERR_CUDA, std::string("kernel ") + ke->name + " cannot be resident on this device");
   // persistent grid: every resident thread owns ceil(n / nthreads) trials; shrink the grid so that
   // all waves are full (equal-length trials: a partial last wave costs a whole trial time)
+  const int kBlock = ke->block;
   const int64_t resident = (int64_t)e->sm_count * max_blocks * kBlock;
   const int64_t waves = (n + resident - 1) / resident;
   const int64_t per_wave = (n + waves - 1) / waves;
@@ -127,9 +129,9 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   if (grid < 1) grid = 1;
   const int64_t nthreads = grid * kBlock;
 
-  static thread_local KArgs<R, NS> ka;
+  static thread_local KArgs<R, NS, NA> ka;
   memset(&ka, 0, sizeof(ka));
-  convert_params<R, NS>(e->params, e->dev_dur, ka.p);
+  convert_params<R, NS, NA>(e->params, e->dev_dur, ka.p);
   if (series) { ka.series = *series; ka.p.T = series->sim_days; ka.p.buffer = 0; ka.p.random_start = 0; }
   if (tape) ka.tape = *tape;
   ka.out = *out;
@@ -179,16 +181,18 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
   if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
   const bool need_io = rng_mode != LETF_RNG_PHILOX || want_journal || lg.count != nullptr || market == kMarketSeries;
-  const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask);
+  // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
+  const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
+  const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);
   if (!ke) return fail(LETF_ERR_INVALID, "no kernel instantiation for this (precision, market, strategies) combination");
   CK(cudaSetDevice(e->device));
-#define GO(R, NS) return launch_typed<R, NS>(e, ke, st, seed, first, n, rng_mode, tape, out, series, lg)
+#define GO(R, NS, NA) return launch_typed<R, NS, NA>(e, ke, st, seed, first, n, rng_mode, tape, out, series, lg)
   if (ke->precision == LETF_PREC_F64) {
-    if (ke->ns == 32) GO(double, 32);
+    if (ke->ns == 32 && ke->na == 6) GO(double, 32, 6);
   } else {
-    if (ke->ns == 4) GO(float, 4);
-    if (ke->ns == 8) GO(float, 8);
-    if (ke->ns == 32) GO(float, 32);
+    if (ke->ns == 4 && ke->na == 3) GO(float, 4, 3);
+    if (ke->ns == 8 && ke->na == 6) GO(float, 8, 6);
+    if (ke->ns == 32 && ke->na == 6) GO(float, 32, 6);
   }
 #undef GO
   return fail(LETF_ERR_INVALID, "kernel registry holds an unsupported slot count");

@@ -19,8 +19,8 @@
 
 namespace letf {
 
-template <typename R, int NS> struct KArgs {
-  DevParams<R, NS> p;
+template <typename R, int NS, int NA> struct KArgs {
+  DevParams<R, NS, NA> p;
   LetfTape tape;            // device pointers (tape / record modes)
   LetfOutputs out;          // device pointers
   LetfSeries series;        // MARKET == 3 only: caller-supplied frame (run_strategy_fixed seam)
@@ -66,10 +66,13 @@ template <> struct Drawdown<double> {
     if (dd < mn) mn = dd;
   }
   LETF_HD double value() const { return ::fabs(mn); }
+  LETF_HD void init_open() { rm = 0; mn = 0; }
 };
 template <> struct Drawdown<float> {
   float q, qmin;
   LETF_HD void init(double) { q = 1.0f; qmin = 1.0f; }
+  // branch-free start: the first step maps q = +inf to min(1, inf * g) = 1 for any g > 0
+  LETF_HD void init_open() { q = INFINITY; qmin = 1.0f; }
   LETF_HD void step(double, float growth) {
     q = fminf(1.0f, q * growth);
     qmin = fminf(qmin, q);
@@ -78,12 +81,13 @@ template <> struct Drawdown<float> {
 };
 
 // ------------------------------------------------------------------------------------------
-template <typename R, int NS, int MARKET, bool TAPEIO, uint32_t TM>
+template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM>
 struct Trial {
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
   static constexpr bool HAS_VOL = (TM & kVolTypes) != 0;
+  static constexpr bool HAS_ACTIVE = (TM & ~((1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT))) != 0;
   static constexpr bool HAS_SMA200 = TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND) || TM_HAS(LETF_ST_COMPOSITE) ||
                                      TM_HAS(LETF_ST_ADAPTIVE_VOL) || TM_HAS(LETF_ST_CONVEX_VOL) || TM_HAS(LETF_ST_META_ENSEMBLE);
   static constexpr bool HAS_SMA100 = TM_HAS(LETF_ST_CONVICTION);
@@ -103,14 +107,14 @@ struct Trial {
   static constexpr bool NEED_RINGS = HAS_MOM;
   static constexpr bool NEED_RINGA = HAS_VOL;
 
-  const KArgs<R, NS>& ka;
-  const DevParams<R, NS>& p;
+  const KArgs<R, NS, NA>& ka;
+  const DevParams<R, NS, NA>& p;
   int64_t k, col, lane, tcol, nt;
   bool use_tape, rec, anti;
   RngKey key;
   uint32_t flags;
 
-  LETF_HD Trial(const KArgs<R, NS>& a, int64_t trial, int64_t column, int64_t ln)
+  LETF_HD Trial(const KArgs<R, NS, NA>& a, int64_t trial, int64_t column, int64_t ln)
       : ka(a), p(a.p), k(trial), col(column), lane(ln) {
     int64_t sim_id = p.antithetic ? (k & ~(int64_t)1) : k;
     anti = p.antithetic && (k & 1);
@@ -174,7 +178,8 @@ struct Trial {
       if (WANT_X && MARKET != LETF_MARKET_PARAM_T) {
         U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
         M::box_muller(b0.x, b0.y, z0, z1);
-        M::box_muller(b0.z, b0.w, z2, nchi);
+        // the iid-normal shapes only need the third shock when a TLT-based series is computed
+        if (MARKET != LETF_MARKET_NORMAL || TAPEIO || p.need_tlt) M::box_muller(b0.z, b0.w, z2, nchi);
       }
       if (WANT_X && MARKET == LETF_MARKET_PARAM_T) {
         for (int c = 0; c < 3; c++) {
@@ -369,10 +374,15 @@ struct Trial {
     R vix = p.const_vix;
     // stress / tracking-error / price state
     R liq = 0, cred = 0;
-    R te_prev[kAssets], bias[kAssets], cp[kAssets];
-    for (int a = 0; a < kAssets; a++) { te_prev[a] = 0; bias[a] = 0; cp[a] = 1; }
+    static_assert(NA == kAssets || (!HAS_ACTIVE && MARKET != kMarketSeries), "compacted asset slots are for buy&hold-only builds");
+    R te_prev[NA], bias[NA];
+    double cp[NA];                   // cumulative growth of each ETF series (price / 100), always fp64
+    Drawdown<R> ddA[NA], ddT;        // buy&hold statistics live on the asset, not on a strategy slot
+    for (int a = 0; a < NA; a++) { te_prev[a] = 0; bias[a] = 0; cp[a] = 1.0; ddA[a].init_open(); }
+    ddT.init_open();
     double cp_tlt = 1.0;
     R vmin = (R)INFINITY, vmax = (R)-INFINITY;
+    R chk = 0;                       // fp32 mode: sticky non-finite detector (x * 0 accumulates NaN for inf / NaN)
     bool bad = false;
     int reg_days1 = 0, jump_days = 0;
 
@@ -425,10 +435,16 @@ struct Trial {
         rf = clipr(irx, (R)0, (R)20) / (R)100;                                // engine.py:516
       }
       R spy = x[0], qqq = x[1], tlt = x[2];
-      if (!isfinite_(spy) || !isfinite_(qqq) || !isfinite_(tlt)) flags |= LETF_FLAG_NONFINITE_RET;
-      if (!isfinite_(vix) || vix <= (R)0) flags |= LETF_FLAG_BAD_VIX;
-      reg_days1 += reg;
-      vmin = rmin(vmin, vix); vmax = rmax(vmax, vix);
+      if (EXACT) {
+        if (!isfinite_(spy) || !isfinite_(qqq) || !isfinite_(tlt)) flags |= LETF_FLAG_NONFINITE_RET;
+      } else {
+        chk = M::fma_(spy, (R)0, chk); chk = M::fma_(qqq, (R)0, chk); chk = M::fma_(tlt, (R)0, chk);
+      }
+      if (MARKET != LETF_MARKET_NORMAL) {             // constant VIX / regime 0 in the iid-normal shapes: checked once below
+        if (!isfinite_(vix) || vix <= (R)0) flags |= LETF_FLAG_BAD_VIX;
+        reg_days1 += reg;
+        vmin = rmin(vmin, vix); vmax = rmax(vmax, vix);
+      }
 
       // ---- latent stress + jump overlay (calibration.py:787-830, engine.py:502-512)
       if (MARKET != kMarketSeries && p.has_stress) {
@@ -485,59 +501,92 @@ struct Trial {
         if (p.has_stress) spd += p.f_liq * clipr(liq, (R)0, (R)3) + p.f_cr * clipr(cred, (R)0, (R)3);
         spread_common = clipr(spd, p.f_min, p.f_max);
       }
-      const R vmult = clipr(M::sqrt_(vix / (R)20), (R)0.5, (R)1.5);
+      const R vmult = clipr(M::sqrt_(EXACT ? vix / (R)20 : vix * (R)0.05), (R)0.5, (R)1.5);
       const R rmult = reg == 0 ? (R)1 : (R)1.15;
+      const R vrmult = vmult * rmult;
 
       // ---- the six ETF layers (engine.py:360-420)
       R ret[kAssets];
 #pragma unroll
-      for (int a = 0; a < kAssets; a++) {
-        ret[a] = 0;
+      for (int a = 0; a < kAssets; a++) ret[a] = 0;
+#pragma unroll
+      for (int a = 0; a < NA; a++) {             // a = slot; aid = asset id (identical when NA == 6)
+        const int aid = NA == kAssets ? a : p.act_id[a];
         R er;
         if (MARKET == kMarketSeries) {
           if (!ka.series.asset_ret[a]) continue;
           er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
         } else {
-          if (!((p.asset_mask >> a) & 1)) continue;
-          const DevAsset<R>& ap = p.assets[a];
+          if (!p.act_on[a]) continue;
+          const DevAsset<R>& ap = p.act[a];
           R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
-          R u = ap.beta_applies ? ub * ap.beta : ub;
+          R u = EXACT ? (ap.beta_applies ? ub * ap.beta : ub) : ub * ap.beta_eff;
           R spread = p.has_funding ? spread_common : ap.borrow_spread;
-          R borrow = 0;
-          if (ap.bl > (R)0) borrow = ap.bl * rmax(rf + spread, (R)0) / (R)252;
-          R lev = ap.lev * u - ap.er_daily - borrow;
+          R lev;
+          if (!EXACT && MARKET == LETF_MARKET_NORMAL) {
+            lev = ap.lev * u - ap.carry_const;            // constant rf, no funding model: the carry is invariant
+          } else if (EXACT) {
+            R borrow = 0;
+            if (ap.bl > (R)0) borrow = ap.bl * rmax(rf + spread, (R)0) / (R)252;
+            lev = ap.lev * u - ap.er_daily - borrow;
+          } else {
+            lev = ap.lev * u - (ap.er_daily + ap.bl_252 * rmax(rf + spread, (R)0));
+          }
           R te_raw = 0;
-          if (i >= 1) {
+          if (TAPEIO ? i >= 1 : true) {      // Philox-only builds draw on day 0 too and discard it below (no branch)
             R innov;
-            if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)a * T + i);
+            if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)aid * T + i);
             else {
-              U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + a);
-              innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + a);
-              if (rec) tp_put(ka.tape.te_t, (int64_t)a * T + i, innov);
+              U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
+              innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
+              if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);
             }
-            innov *= ap.te_base * vmult * rmult * (R)1;
             R ds = u < (R)0 ? ap.te_down : (R)0.98;
             R mm = ((R)1 + (R)0.3 * M::abs_(u)) * ds;
-            te_raw = ap.te_rho * te_prev[a] + ap.te_arw * innov * mm;
-          } else if (rec) tp_put(ka.tape.te_t, (int64_t)a * T, 0);
+            if (EXACT) {
+              innov *= ap.te_base * vmult * rmult * (R)1;
+              te_raw = ap.te_rho * te_prev[a] + ap.te_arw * innov * mm;
+            } else {
+              te_raw = ap.te_rho * te_prev[a] + (innov * vrmult) * (ap.te_scale * mm);
+              if (!TAPEIO) te_raw = i >= 1 ? te_raw : (R)0;
+            }
+          } else if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T, 0);
           te_prev[a] = te_raw;
           const R alpha = (R)(2.0 / 127.0);
           bias[a] = alpha * te_raw + ((R)1 - alpha) * bias[a];
           R te = te_raw - bias[a];
-          if (ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(te / ap.te_clip);
-          er = clipr(lev + te, (R)-0.999, (R)10);
+          if (ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
+          er = EXACT ? clipr(lev + te, (R)-0.999, (R)10) : clipfast(lev + te, (R)-0.999, (R)10);
         }
-        ret[a] = er;
-        cp[a] = i == 0 ? ((R)1 + er) : cp[a] * ((R)1 + er);
-        R pr = cp[a] * (R)100;
-        if (!isfinite_(er) || !isfinite_(pr) || !(pr > (R)0)) bad = true;
+        if (NA == kAssets) ret[a] = er;
+        if (EXACT) {
+          cp[a] = i == 0 ? (1.0 + (double)er) : cp[a] * (1.0 + (double)er);
+          double pr = cp[a] * 100.0;
+          if (!isfinite_(er) || !isfinite_(pr) || !(pr > 0.0)) bad = true;
+        } else {
+          cp[a] = ::fma(cp[a], (double)er, cp[a]);      // a NaN return or a product that reached 0 stays there
+        }
+        if (p.act_bench[a]) {                           // strategy.py:85-95 buy & hold: W = W0 * cumprod(1 + r)
+          if (EXACT) {
+            if (i == 0) ddA[a].init((double)p.W0 * cp[a]);
+            else ddA[a].step((double)p.W0 * cp[a], (R)1 + er);
+          } else ddA[a].step(0.0, (R)1 + er);           // starts "open" (q = inf): day 0 lands on q = 1
+        }
       }
       {
-        cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
-        if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
+        if (EXACT) {
+          cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
+          if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
+        } else if (p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
+        if (p.bench_tlt) {
+          if (EXACT) {
+            if (i == 0) ddT.init((double)p.W0 * cp_tlt);
+            else ddT.step((double)p.W0 * cp_tlt, (R)1 + tlt);
+          } else ddT.step(0.0, (R)1 + tlt);
+        }
       }
       const R cash = p.cash_daily[reg];
-      const R Pspy = cp[4] * (R)100;
+      const R Pspy = NA == kAssets ? (R)(cp[NA == kAssets ? 4 : 0] * 100.0) : (R)100;
 
       // ---- signals as of yesterday, then roll the windows forward with today's values
       R s_sma200 = nan_<R>(), s_sma200f = nan_<R>(), s_sma100 = nan_<R>(), s_rsi = nan_<R>(), s_mom = nan_<R>();
@@ -620,6 +669,8 @@ struct Trial {
       sg.P_prev = Pspy; sg.vix_prev = vix;
 
       // ---- strategy rules (strategy.py:55-1277) + running statistics (engine.py:578-590)
+      // (buy & hold needs no slot work: its equity is W0 * cp[asset], tracked above)
+      if (HAS_ACTIVE && i >= 1)           // active strategies leave equity[0] = W0
 #pragma unroll
       for (int s = 0; s < NS; s++) {
         if (s >= p.n_strat) break;
@@ -627,15 +678,7 @@ struct Trial {
         Slot& sl = slot[s];
         const int ty = st.type;
         R growth = (R)1;          // W_i / W_{i-1}
-        bool act = i >= 1;        // active strategies leave equity[0] = W0
-        if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) {
-          if (ty == LETF_ST_BENCHMARK) { growth = (R)1 + ret[st.asset]; sl.W = EXACT ? (double)p.W0 * (double)cp[st.asset] : sl.W * (1.0 + (double)ret[st.asset]); }
-          else { growth = (R)1 + tlt; sl.W = EXACT ? (double)p.W0 * cp_tlt : sl.W * (1.0 + (double)tlt); }
-          act = false;
-          if (i == 0) sl.dd.init(sl.W); else sl.dd.step(sl.W, growth);
-          continue;
-        }
-        if (!act) continue;
+        if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) continue;
         R r_strat = 0;
         if (TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND)) if (ty == LETF_ST_SMA || ty == LETF_ST_SMA_BAND) {
           R thr = ty == LETF_ST_SMA ? s_sma200 : s_sma200 * ((R)1 - st.p[1]);
@@ -684,7 +727,7 @@ struct Trial {
               int ta = target == 2 ? st.asset : (target == 1 ? st.asset2 : 4);
               // journal keyed by asset NAME in the reference: legs that alias the same ticker share a position
               int which = ta == st.asset ? 0 : (ta == st.asset2 ? 1 : 2);
-              jlog(sj[s], which, s, i, ta, target == 0 ? (R)0 : (R)1, sl.W, cp[ta] * (R)100);
+              jlog(sj[s], which, s, i, ta, target == 0 ? (R)0 : (R)1, sl.W, (R)(cp[ta] * 100.0));
             }
             sl.aux = (R)target;
           }
@@ -791,7 +834,7 @@ struct Trial {
           R turnover = M::abs_(alloc - prev_alloc), cost = 0;
           if (turnover > thresh) {
             sl.trades++;
-            if (JOURNAL && st.taxable) jlog(sj[s], 0, s, i, st.asset, alloc, sl.W, cp[st.asset] * (R)100);
+            if (JOURNAL && st.taxable) jlog(sj[s], 0, s, i, st.asset, alloc, sl.W, (R)(cp[st.asset] * 100.0));
             cost = turnover * (R)0.0003;
             sl.aux = alloc;
           } else {
@@ -807,20 +850,44 @@ struct Trial {
     }
 
     // ---- per-trial outputs (engine.py:578-603)
+    if (MARKET == LETF_MARKET_NORMAL) {       // constant VIX, regime 0
+      if (T > 0) { vmin = vmax = vix; if (!isfinite_(vix) || vix <= (R)0) flags |= LETF_FLAG_BAD_VIX; }
+    }
+    if (!EXACT) {
+      // fp32 mode defers the per-day validity checks: non-finite values and exhausted products are sticky
+      if (chk != (R)0) flags |= LETF_FLAG_NONFINITE_RET;
+      for (int a = 0; a < NA; a++) {
+        bool on = MARKET == kMarketSeries ? ka.series.asset_ret[a] != nullptr : p.act_on[a] != 0;
+        if (on && T > 0 && !(cp[a] > 0.0 && isfinite_(cp[a]))) bad = true;
+      }
+      if (p.bench_tlt && T > 0 && !(cp_tlt > 0.0 && isfinite_(cp_tlt))) bad = true;
+    }
     if (T == 0 || bad || !(vmin >= (R)5) || !(vmax <= (R)120)) flags |= LETF_FLAG_REPAIRED;
     const int64_t N = ka.out.n_trials;
     for (int s = 0; s < NS; s++) {
       if (s >= p.n_strat) break;
+      const int ty = p.strat[s].type;
       double fw = T > 0 ? slot[s].W : 0.0;
+      double md = T > 1 ? slot[s].dd.value() : 0.0;
+      if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) {
+        double c = 1.0; Drawdown<R> d = ddT;
+        if (ty == LETF_ST_BENCHMARK_TLT) c = cp_tlt;
+        else {
+#pragma unroll
+          for (int a = 0; a < NA; a++) if (p.act_on[a] && p.act_id[a] == p.strat[s].asset) { c = cp[a]; d = ddA[a]; }
+        }
+        fw = T > 0 ? (double)p.W0 * c : 0.0;
+        md = T > 1 ? d.value() : 0.0;
+      }
       ka.out.final_wealth[(int64_t)s * N + col] = fw;
-      ka.out.max_dd[(int64_t)s * N + col] = T > 1 ? slot[s].dd.value() : 0.0;
+      ka.out.max_dd[(int64_t)s * N + col] = md;
       ka.out.num_trades[(int64_t)s * N + col] = slot[s].trades;
       if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = JOURNAL ? sj[s].cnt : 0;
       if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = JOURNAL ? sj[s].vol : 0.0;
     }
     if (ka.out.start_offset) ka.out.start_offset[col] = so;
     if (ka.out.flags) ka.out.flags[col] = flags;
-    if (ka.out.regime_days) { ka.out.regime_days[col] = T - reg_days1; ka.out.regime_days[N + col] = reg_days1; }
+    if (ka.out.regime_days) { ka.out.regime_days[col] = T - reg_days1; ka.out.regime_days[N + col] = reg_days1; }   // NORMAL: reg_days1 stays 0
     if (ka.out.jump_days) ka.out.jump_days[col] = jump_days;
   }
 

@@ -82,6 +82,7 @@ template <> struct Mth<double> {
   static LETF_HD double pow_(double x, double y) { return ::pow(x, y); }
   static LETF_HD double abs_(double x) { return ::fabs(x); }
   static LETF_HD double div_(double a, double b) { return a / b; }
+  static LETF_HD double fma_(double a, double b, double c) { return ::fma(a, b, c); }
   static LETF_HD double u01(uint32_t a) { return ((double)a + 0.5) * 2.3283064365386963e-10; }
   static LETF_HD double u01_16(uint32_t a) { return ((double)a + 0.5) * (1.0 / 65536.0); }
   static LETF_HD double u01_12(uint32_t a) { return ((double)a + 0.5) * (1.0 / 4096.0); }
@@ -98,19 +99,22 @@ template <> struct Mth<float> {
 #if defined(__CUDA_ARCH__)
   static LETF_HD float sqrt_(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float rsqrt_(float x) { return rsqrtf(x); }
-  static LETF_HD float log_(float x) { return __logf(x); }
+  static LETF_HD float log2_(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  static LETF_HD float log_(float x) { return 0.6931471805599453f * log2_(x); }
   static LETF_HD float tanh_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float pow_(float x, float y) { return __powf(x, y); }
   static LETF_HD float div_(float a, float b) { return __fdividef(a, b); }
 #else
   static LETF_HD float sqrt_(float x) { return ::sqrtf(x); }
   static LETF_HD float rsqrt_(float x) { return 1.0f / ::sqrtf(x); }
+  static LETF_HD float log2_(float x) { return ::log2f(x); }
   static LETF_HD float log_(float x) { return ::logf(x); }
   static LETF_HD float tanh_(float x) { return ::tanhf(x); }
   static LETF_HD float pow_(float x, float y) { return ::powf(x, y); }
   static LETF_HD float div_(float a, float b) { return a / b; }
 #endif
   static LETF_HD float abs_(float x) { return ::fabsf(x); }
+  static LETF_HD float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
   // (a + 0.5) * 2^-32, never 0; may round to exactly 1 (log -> 0, harmless)
   static LETF_HD float u01(uint32_t a) { return fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
   static LETF_HD float u01_16(uint32_t a) { return fmaf((float)a, 1.0f / 65536.0f, 0.5f / 65536.0f); }
@@ -120,9 +124,12 @@ template <> struct Mth<float> {
     // angle in [-pi, pi): signed reinterpretation of the second word
     float th = (float)(int32_t)b * 1.4629180792671596e-9f;  // 2*pi / 2^32
 #if defined(__CUDA_ARCH__)
-    float r = sqrt_(-1.3862943611198906f * __log2f(u));      // sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u)
-    n0 = r * __cosf(th);
-    n1 = r * __sinf(th);
+    float r = sqrt_(-1.3862943611198906f * log2_(u));        // sqrt(-2 ln u) = sqrt(-2 ln2 * log2 u)
+    float cs, sn;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(th));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(th));
+    n0 = r * cs;
+    n1 = r * sn;
 #else
     float r = ::sqrtf(-2.0f * ::logf(u));
     n0 = r * ::cosf(th);
@@ -134,6 +141,9 @@ template <> struct Mth<float> {
 template <typename R> LETF_HD R rmax(R a, R b) { return a > b ? a : b; }   // python max(a, b) for non-NaN b
 template <typename R> LETF_HD R rmin(R a, R b) { return a < b ? a : b; }
 template <typename R> LETF_HD R clipr(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); } // NaN passes through
+// clip for values that are known not to be NaN-significant (fp32 hot path): two FMNMX
+LETF_HD float clipfast(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+LETF_HD double clipfast(double x, double lo, double hi) { return clipr(x, lo, hi); }
 template <typename R> LETF_HD bool isnan_(R x) { return x != x; }
 template <typename R> LETF_HD bool isfinite_(R x) { return (x - x) == (R)0; }
 
@@ -149,6 +159,10 @@ template <typename R> LETF_HD bool isfinite_(R x) { return (x - x) == (R)0; }
 template <typename R>
 LETF_HD R chi2_int_fast(int k, uint32_t wa, uint32_t wb, R nrm) {
   typedef Mth<R> M;
+  if (k == 5) {                        // cfg.ASSETS default for the LETFs: one uniform compare on the hot path
+    R g5 = (R)-2 * M::log_(M::u01(wa) * M::u01(wb));
+    return g5 + nrm * nrm;
+  }
   int m = k >> 1;
   R prod = (R)1;
   if (m == 1) prod = M::u01(wa);
@@ -206,7 +220,8 @@ LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint
   M::box_muller(b.x, b.y, n0, n1);
   R c2 = fast_k ? chi2_int_fast<R>(fast_k, b.z, b.w, n1)
                 : chi2_marsaglia_tsang<R>(df, n1, b.z, key, day, stream);
-  return n0 * M::sqrt_(M::div_(df, rmax(c2, (R)1e-30)));
+  if (sizeof(R) == 8) return n0 * M::sqrt_(M::div_(df, rmax(c2, (R)1e-30)));
+  return n0 * (M::sqrt_(df) * M::rsqrt_(rmax(c2, (R)1e-30)));   // sqrt(df) is loop-invariant: one MUFU per variate
 }
 
 }  // namespace letf

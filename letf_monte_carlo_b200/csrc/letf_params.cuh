@@ -15,6 +15,10 @@ constexpr int kRingA = 60;       // signal-asset return history (vol 5/10/20/60,
 
 template <typename R> struct DevAsset {
   R lev, bl, er_daily, borrow_spread, te_base, te_df, te_rho, te_arw, te_down, te_clip, beta;
+  R bl_252;          // max(leverage - 1, 0) / 252      (fp32 fast path of utils.py:169-216)
+  R beta_eff;        // beta if it applies, else exactly 1
+  R carry_const;     // iid-normal market: expense/252 + borrow at the constant rate (loop invariant)
+  R te_scale;        // te_base * sqrt(1 - rho^2)
   int und, beta_applies, te_fast_k, pad;
 };
 
@@ -34,9 +38,10 @@ template <typename R> struct DevStrategy {
   R p[LETF_STRAT_NPARAM];
 };
 
-template <typename R, int NS> struct DevParams {
+template <typename R, int NS, int NA> struct DevParams {
   int market_mode, T, buffer, random_start, min_offset, offset_range, antithetic, mm, institutional,
-      has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset;
+      has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset,
+      bench_mask /* assets tracked for a buy&hold strategy */, bench_tlt, need_tlt;
   R W0, sim_years;
   int flip[2];
   R log_pstay[2];
@@ -54,6 +59,11 @@ template <typename R, int NS> struct DevParams {
   DevStress<R> stress[2];
   R f_base, f_vix, f_inv, f_liq, f_cr, f_min, f_max;
   DevAsset<R> assets[kAssets];
+  // the ETF series this launch computes: NA == 6 -> slot j is asset j (act_on = mask bit);
+  // NA < 6 -> the active assets compacted into the first n_act slots (lean buy&hold builds)
+  DevAsset<R> act[NA];
+  int act_id[NA], act_on[NA], act_bench[NA];
+  int n_act, pad_a;
   R cash_daily[2], spread_cost[2], rebalance_cost;
   DevStrategy<R> strat[NS];
 };
@@ -106,8 +116,8 @@ inline uint32_t strategy_type_mask(const LetfParams& s) {
   return m;
 }
 
-template <typename R, int NS>
-inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS>& d) {
+template <typename R, int NS, int NA>
+inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS, NA>& d) {
   memset(&d, 0, sizeof(d));
   d.market_mode = s.market_mode; d.T = s.sim_days; d.buffer = s.buffer_days; d.random_start = s.random_start;
   d.min_offset = s.buffer_days / 4 < 50 ? s.buffer_days / 4 : 50;
@@ -170,6 +180,13 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     double q = 1 - x.te_rho * x.te_rho; if (q < 1e-6) q = 1e-6;
     y.te_arw = (R)::sqrt(q); y.te_down = (R)x.te_downside; y.te_clip = (R)x.te_clip; y.beta = (R)x.beta;
     y.und = x.underlying; y.beta_applies = x.beta_applies; y.te_fast_k = df_fast_k(x.te_df);
+    y.bl_252 = (R)(x.leverage > 1.0 ? (x.leverage - 1.0) / 252 : 0.0);
+    y.beta_eff = x.beta_applies ? (R)x.beta : (R)1;
+    {
+      double rate = s.const_rf + x.borrow_spread; if (!(rate > 0.0)) rate = 0.0;
+      y.carry_const = (R)(x.expense_ratio / 252 + (x.leverage > 1.0 ? (x.leverage - 1.0) * rate / 252 : 0.0));
+    }
+    y.te_scale = (R)(x.te_base * ::sqrt(q));
   }
   d.rebalance_cost = (R)s.rebalance_cost;
   int nport = 0;
@@ -182,6 +199,21 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     for (int i = 0; i < LETF_STRAT_NPARAM; i++) y.p[i] = (R)x.p[i];
     bool uses_sig = x.type >= LETF_ST_VOL_TARGETING && x.type <= LETF_ST_CONVICTION && x.type != LETF_ST_COMPOSITE;
     if (uses_sig) d.sig_asset = x.asset;
+    if (x.type == LETF_ST_BENCHMARK) d.bench_mask |= 1 << x.asset;
+    if (x.type == LETF_ST_BENCHMARK_TLT) d.bench_tlt = 1;
+  }
+  d.need_tlt = d.bench_tlt;
+  for (int a = 0; a < kAssets; a++) if (((s.asset_mask >> a) & 1) && s.assets[a].underlying == 2) d.need_tlt = 1;
+  d.n_act = 0;
+  for (int a = 0; a < kAssets; a++) {
+    const bool on = (s.asset_mask >> a) & 1;
+    if (NA == kAssets) {
+      d.act[a] = d.assets[a]; d.act_id[a] = a; d.act_on[a] = on; d.act_bench[a] = (d.bench_mask >> a) & 1;
+      d.n_act = kAssets;
+    } else if (on && d.n_act < NA) {
+      int j = d.n_act++;
+      d.act[j] = d.assets[a]; d.act_id[j] = a; d.act_on[j] = 1; d.act_bench[j] = (d.bench_mask >> a) & 1;
+    }
   }
 }
 #endif  // LETF_DEVICE_ONLY

@@ -118,10 +118,14 @@ def pack_strategy(sid: str, conf: Mapping, taxable_ids: Sequence[str]) -> abi.St
     return sp
 
 
+_NEEDS_SPY = {abi.STRATEGY_TYPES[k] for k in ("sma", "sma_band", "composite", "adaptive_vol", "convex_vol",
+                                                 "meta_ensemble", "mom_vol_convergence", "conviction_compounder")}
+
+
 def strategy_asset_mask(sp: abi.StrategyParams) -> int:
-    """ETF series a strategy reads (SPY is always needed: SPY_Price / SPY_Ret signals)."""
-    m = 1 << 4
+    """ETF series a strategy reads (SPY_Price / SPY_Ret are signals of the SMA / trend / momentum rules)."""
     t = sp.type
+    m = (1 << 4) if t in _NEEDS_SPY else 0
     if t == abi.STRATEGY_TYPES["portfolio"]:
         for a in range(abi.N_ASSETS):
             if sp.weights[a] != 0.0:
@@ -296,7 +300,7 @@ def build_params(strategy_ids: Sequence[str], time_horizon: float, regime_model:
     if len(strategy_ids) > abi.MAX_STRATEGIES:
         raise UnsupportedConfig(f"at most {abi.MAX_STRATEGIES} strategies per launch")
     p.n_strategies = len(strategy_ids)
-    mask = 1 << 4
+    mask = 0
     for k, sid in enumerate(strategy_ids):
         sp = pack_strategy(sid, cfg.STRATEGIES[sid], taxable_ids)
         p.strategies[k] = sp

@@ -17,9 +17,10 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
                  int32_t* log_count, int32_t* log_day, int32_t* log_asset, int32_t* log_action,
                  double* log_shares, double* log_price) {
   constexpr int NS = LETF_MAX_STRATEGIES;
-  static KArgs<R, NS> ka;
+  constexpr int NA = kAssets;
+  static KArgs<R, NS, NA> ka;
   const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
-  convert_params<R, NS>(*sp, dd, ka.p);
+  convert_params<R, NS, NA>(*sp, dd, ka.p);
   if (tape) ka.tape = *tape; else memset(&ka.tape, 0, sizeof(ka.tape));
   ka.out = *out;
   ka.seed = seed; ka.first_trial = first; ka.n_trials = n;
@@ -33,7 +34,7 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
   ka.log_count = log_count; ka.log_day = log_day; ka.log_asset = log_asset; ka.log_action = log_action;
   ka.log_shares = log_shares; ka.log_price = log_price;
   for (int64_t j = 0; j < n; j++) {
-    Trial<R, NS, MARKET, true, 0xFFFFFFFFu> t(ka, first + j, j, 0);
+    Trial<R, NS, NA, MARKET, true, 0xFFFFFFFFu> t(ka, first + j, j, 0);
     t.run();
   }
   return 0;

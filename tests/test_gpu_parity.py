@@ -324,7 +324,7 @@ def test_full_size_properties_config2(engine_lib):
         h0, h1 = (x.to_host() for x in halves)
     np.testing.assert_array_equal(h.final_wealth, np.concatenate([h0.final_wealth, h1.final_wealth], axis=1))
     assert (h.flags == 0).all() and np.isfinite(h.final_wealth).all() and (h.final_wealth > 0).all()
-    assert (h.max_dd >= 0).all() and (h.max_dd < 1).all() and (h.num_trades == 0).all()
+    assert (h.max_dd >= 0).all() and (h.max_dd <= 1).all() and (h.num_trades == 0).all()
     # E[log growth] per day = L mu - L^2 sigma^2 / 2 - ER/252 - borrow + O(mu^2): known answer within 5 se
     T = params.sim_days
     vol = np.array([0.16, 0.24]) / np.sqrt(252); mu = np.array([0.08, 0.10]) / 252
