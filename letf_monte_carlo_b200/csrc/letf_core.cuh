@@ -167,7 +167,7 @@ struct Trial {
 
   // one generated day of the raw (pre moment-matching) underlying returns x[3] = SPY, QQQ, TLT.
   // Also returns the two "phase-2" normals of the day (VIX noise, IRX noise) when WANT_AUX.
-  template <bool WANT_X, bool WANT_AUX>
+  template <bool WANT_X, bool WANT_AUX, bool FASTM = false>
   LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n) {
     R z0 = 0, z1 = 0, z2 = 0, nchi = 0;
     uint32_t cw0 = 0, cw1 = 0;
@@ -179,7 +179,7 @@ struct Trial {
         U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
         M::box_muller(b0.x, b0.y, z0, z1);
         // the iid-normal shapes only need the third shock when a TLT-based series is computed
-        if (MARKET != LETF_MARKET_NORMAL || TAPEIO || p.need_tlt) M::box_muller(b0.z, b0.w, z2, nchi);
+        if (!FASTM && (MARKET != LETF_MARKET_NORMAL || TAPEIO || p.need_tlt)) M::box_muller(b0.z, b0.w, z2, nchi);
       }
       if (WANT_X && MARKET == LETF_MARKET_PARAM_T) {
         for (int c = 0; c < 3; c++) {
@@ -329,7 +329,14 @@ struct Trial {
   }
 
   // run the whole trial ---------------------------------------------------------------------
+  // FAST: loop-unswitched variant of the lean buy&hold builds (all slots active, t(5) tracking error,
+  // no tanh cap, no TLT): the day step is one basic block, so the scheduler can interleave the
+  // independent Philox blocks and asset chains.
   LETF_HD void run() {
+    if (NA < kAssets && MARKET == LETF_MARKET_NORMAL && !TAPEIO && p.fast_layers) run_t<true>();
+    else run_t<false>();
+  }
+  template <bool FAST> LETF_HD void run_t() {
     const int G = p.T + p.buffer;
     const int64_t nth = ka.nthreads;
     const R V = (R)15.874507866387544;   // sqrt(252)
@@ -426,7 +433,7 @@ struct Trial {
         market_day<false, true>(g, reg, js, x, vn, in);
         for (int a = 0; a < 3; a++) x[a] = ka.xscr[((int64_t)g * 3 + a) * nth + lane] + shift[a];
       } else {
-        market_day<true, true>(g, reg, js, x, vn, in);
+        market_day<true, true, FAST>(g, reg, js, x, vn, in);
       }
       R rf = p.const_rf;
       if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
@@ -447,7 +454,7 @@ struct Trial {
       }
 
       // ---- latent stress + jump overlay (calibration.py:787-830, engine.py:502-512)
-      if (MARKET != kMarketSeries && p.has_stress) {
+      if (MARKET != kMarketSeries && MARKET != LETF_MARKET_NORMAL && p.has_stress) {   // params.py: no stress model with the iid-normal shapes
         const DevStress<R>& sp = p.stress[reg];
         R jump = 0, sign = 1;
         if (i == 0) {
@@ -491,7 +498,7 @@ struct Trial {
 
       // ---- financing spread shared by all assets (engine.py:328-342, calibration.py:833-857)
       R spread_common = 0;
-      if (MARKET != kMarketSeries && p.has_funding) {
+      if (!FAST && MARKET != kMarketSeries && p.has_funding) {
         R irx_level = rf * (R)100;
         R term = p.has_stress ? (R)1.25 - (R)1.1 * clipr(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
         R tnx = irx_level + term;
@@ -517,13 +524,13 @@ struct Trial {
           if (!ka.series.asset_ret[a]) continue;
           er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
         } else {
-          if (!p.act_on[a]) continue;
+          if (!FAST && !p.act_on[a]) continue;
           const DevAsset<R>& ap = p.act[a];
           R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
           R u = EXACT ? (ap.beta_applies ? ub * ap.beta : ub) : ub * ap.beta_eff;
-          R spread = p.has_funding ? spread_common : ap.borrow_spread;
+          R spread = (!FAST && p.has_funding) ? spread_common : ap.borrow_spread;
           R lev;
-          if (!EXACT && MARKET == LETF_MARKET_NORMAL) {
+          if (!EXACT && MARKET == LETF_MARKET_NORMAL && (FAST || !p.has_funding)) {
             lev = ap.lev * u - ap.carry_const;            // constant rf, no funding model: the carry is invariant
           } else if (EXACT) {
             R borrow = 0;
@@ -538,7 +545,8 @@ struct Trial {
             if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)aid * T + i);
             else {
               U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
-              innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
+              innov = FAST ? student_t5<R>(b)
+                           : student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
               if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);
             }
             R ds = u < (R)0 ? ap.te_down : (R)0.98;
@@ -555,7 +563,7 @@ struct Trial {
           const R alpha = (R)(2.0 / 127.0);
           bias[a] = alpha * te_raw + ((R)1 - alpha) * bias[a];
           R te = te_raw - bias[a];
-          if (ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
+          if (!FAST && ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
           er = EXACT ? clipr(lev + te, (R)-0.999, (R)10) : clipfast(lev + te, (R)-0.999, (R)10);
         }
         if (NA == kAssets) ret[a] = er;
@@ -566,7 +574,7 @@ struct Trial {
         } else {
           cp[a] = ::fma(cp[a], (double)er, cp[a]);      // a NaN return or a product that reached 0 stays there
         }
-        if (p.act_bench[a]) {                           // strategy.py:85-95 buy & hold: W = W0 * cumprod(1 + r)
+        if (FAST || p.act_bench[a]) {                   // strategy.py:85-95 buy & hold: W = W0 * cumprod(1 + r)
           if (EXACT) {
             if (i == 0) ddA[a].init((double)p.W0 * cp[a]);
             else ddA[a].step((double)p.W0 * cp[a], (R)1 + er);
@@ -577,8 +585,8 @@ struct Trial {
         if (EXACT) {
           cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
           if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
-        } else if (p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
-        if (p.bench_tlt) {
+        } else if (!FAST && p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
+        if (!FAST && p.bench_tlt) {
           if (EXACT) {
             if (i == 0) ddT.init((double)p.W0 * cp_tlt);
             else ddT.step((double)p.W0 * cp_tlt, (R)1 + tlt);

@@ -212,6 +212,18 @@ LETF_HD int df_fast_k(double df) {
   return (::fabs(df - r) < 1e-12 && r >= 1.0 && r <= 11.0) ? (int)r : 0;
 }
 
+// Student-t(5) from one Philox block, straight-line (the default tracking-error dof of the LETFs):
+// N0 * sqrt(5) * rsqrt(-2 ln(U1 U2) + N1^2).  Same arithmetic as student_t_block with fast_k == 5.
+template <typename R>
+LETF_HD R student_t5(const U4& b) {
+  typedef Mth<R> M;
+  R n0, n1;
+  M::box_muller(b.x, b.y, n0, n1);
+  R c2 = (R)-2 * M::log_(M::u01(b.z) * M::u01(b.w)) + n1 * n1;
+  if (sizeof(R) == 8) return n0 * M::sqrt_(M::div_((R)5, rmax(c2, (R)1e-30)));
+  return n0 * (M::sqrt_((R)5) * M::rsqrt_(rmax(c2, (R)1e-30)));
+}
+
 // Student-t(df) from one Philox block: N0 / sqrt(chi2(df) / df).
 template <typename R>
 LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint32_t day, uint32_t stream) {

@@ -41,7 +41,8 @@ template <typename R> struct DevStrategy {
 template <typename R, int NS, int NA> struct DevParams {
   int market_mode, T, buffer, random_start, min_offset, offset_range, antithetic, mm, institutional,
       has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset,
-      bench_mask /* assets tracked for a buy&hold strategy */, bench_tlt, need_tlt;
+      bench_mask /* assets tracked for a buy&hold strategy */, bench_tlt, need_tlt,
+      fast_layers /* every slot active, t(5) tracking error, no tanh cap, no TLT: straight-line day step */, pad_f;
   R W0, sim_years;
   int flip[2];
   R log_pstay[2];
@@ -204,9 +205,11 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
   }
   d.need_tlt = d.bench_tlt;
   for (int a = 0; a < kAssets; a++) if (((s.asset_mask >> a) & 1) && s.assets[a].underlying == 2) d.need_tlt = 1;
+  d.fast_layers = (NA < kAssets) && !d.need_tlt && !d.has_funding && s.market_mode == LETF_MARKET_NORMAL;
   d.n_act = 0;
   for (int a = 0; a < kAssets; a++) {
     const bool on = (s.asset_mask >> a) & 1;
+    if (on && (d.assets[a].te_fast_k != 5 || d.assets[a].te_clip > (R)0 || !((d.bench_mask >> a) & 1))) d.fast_layers = 0;
     if (NA == kAssets) {
       d.act[a] = d.assets[a]; d.act_id[a] = a; d.act_on[a] = on; d.act_bench[a] = (d.bench_mask >> a) & 1;
       d.n_act = kAssets;
@@ -215,6 +218,7 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
       d.act[j] = d.assets[a]; d.act_id[j] = a; d.act_on[j] = 1; d.act_bench[j] = (d.bench_mask >> a) & 1;
     }
   }
+  if (d.n_act != NA) d.fast_layers = 0;
 }
 #endif  // LETF_DEVICE_ONLY
 

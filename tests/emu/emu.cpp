@@ -56,4 +56,25 @@ extern "C" int letf_emu_run(const LetfParams* sp, int precision, const LetfTape*
 #undef GO
 }
 
+// the lean buy&hold build (compacted asset slots, loop-unswitched FAST day step), Philox only
+extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n,
+                                 int* used_fast) {
+  if (validate_params(*sp) || sp->market_mode != LETF_MARKET_NORMAL) return -1;
+  constexpr int NS = 4, NA = 3;
+  constexpr uint32_t TMB = (1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT);
+  if (sp->n_strategies > NS || __builtin_popcount((unsigned)sp->asset_mask & 0x3Fu) > NA) return -2;
+  static KArgs<float, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  const int32_t* dd[2] = {nullptr, nullptr};
+  convert_params<float, NS, NA>(*sp, dd, ka.p);
+  ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
+  ka.log_trial = -1;
+  if (used_fast) *used_fast = ka.p.fast_layers;
+  for (int64_t j = 0; j < n; j++) {
+    Trial<float, NS, NA, LETF_MARKET_NORMAL, false, TMB> t(ka, first + j, j, 0);
+    t.run();
+  }
+  return 0;
+}
+
 extern "C" const char* letf_emu_validate(const LetfParams* sp) { return validate_params(*sp); }

@@ -37,6 +37,9 @@ def lib():
                                    C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int] + \
                                   [C.c_void_p] * 6
         L.letf_emu_run.restype = C.c_int
+        L.letf_emu_run_lean.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64,
+                                        C.POINTER(C.c_int)]
+        L.letf_emu_run_lean.restype = C.c_int
         L.letf_emu_validate.argtypes = [C.POINTER(abi.Params)]
         L.letf_emu_validate.restype = C.c_char_p
         _lib = L
@@ -61,3 +64,13 @@ def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, fir
     if log is not None:
         out.log = bufs
     return out
+
+
+def run_lean(params, n, seed=0, first=0):
+    """lean buy&hold build (NA = 3 compacted slots); returns (outputs, used_fast_variant)"""
+    out = HostOutputs(params.n_strategies, n)
+    fast = C.c_int(0)
+    rc = lib().letf_emu_run_lean(C.byref(params), C.byref(out.as_struct()), seed, first, n, C.byref(fast))
+    if rc != 0:
+        raise RuntimeError(f"emu lean rc={rc}")
+    return out, bool(fast.value)

@@ -336,3 +336,27 @@ def test_full_size_properties_config2(engine_lib):
         lg = np.log(h.final_wealth[s] / params.initial_capital) / T
         se = L * vol[u] / np.sqrt(T * n)
         assert abs(lg.mean() - g) < 5 * se + 2e-6, (a, lg.mean(), g, se)
+
+
+def test_lean_fast_kernel_vs_generic_and_oracle(engine_lib):
+    """bench.py's c2 workload runs the lean buy&hold build with the loop-unswitched FAST day step.
+    Chain of evidence on the device: FAST (Philox) == generic fp32 build recording the same counters
+    (fp32 reassociation only), and the oracle replaying that recorded tape agrees with both."""
+    sids = ["S1", "B_UPRO", "S3"]
+    doc = {"case": dict(variant="normal_c2", years=5, n_tapes=256, seed=0, cfg={}, strategies=sids)}
+    ns, model, params, keep, _ = case_inputs(doc)
+    n = 256
+    rec = HostTape(n, params.sim_days, params.sim_days, 1)
+    with _engine(params, keep, "f32") as eng:
+        lean = eng.run_host(n, seed=31337)
+        regs_lean = eng.launch_info()["regs_per_thread"]
+        gen = eng.run_host(n, seed=31337, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+        regs_gen = eng.launch_info()["regs_per_thread"]
+    assert regs_lean < regs_gen                      # two different instantiations really ran
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=5e-5)
+    np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=5e-6)
+    np.testing.assert_allclose(gen.final_wealth, o.final_wealth, rtol=2e-4)
+    np.testing.assert_allclose(lean.final_wealth, o.final_wealth, rtol=2e-4)
+    np.testing.assert_allclose(lean.max_dd, o.max_dd, atol=1e-4)
+    assert (lean.flags == 0).all() and (o.flags == 0).all()

@@ -140,3 +140,35 @@ def test_philox_draw_distributions(precision):
     _ks(sp0 - np.random.default_rng(0).random(sp0.size), stats.expon(scale=-1 / np.log(0.99)).cdf, alpha=1e-5)
     so = rec.start_offset
     assert so.min() >= 50 and so.max() < 1260
+
+
+def _c2_params(sids, years=2, **assets_override):
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False)
+    for a, kv in assets_override.items():
+        ns.ASSETS[a].update(kv)
+    ns.LETF_CONFIGS = ns.ASSETS
+    return build_params(sids, years, synthetic.normal_regime_model("c2"), ns)
+
+
+def test_lean_fast_variant_matches_generic_build():
+    """The loop-unswitched straight-line day step of the lean buy&hold build (what bench.py's c2 workload
+    runs) against the generic build on the same Philox counters: same draws, fp32 reassociation only."""
+    sids = ["S1", "B_UPRO", "S3"]
+    params, keep = _c2_params(sids)
+    dummy = HostTape(1, params.sim_days, params.sim_days, 1)
+    lean, fast = emu.run_lean(params, 64, seed=77)
+    assert fast
+    gen = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=77, n=64)
+    np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=2e-5)
+    np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=2e-6)
+    np.testing.assert_array_equal(lean.flags, gen.flags)
+    # and against fp64 on the same counters (fp64 Box-Muller / log differ in the last bits of each variate)
+    g64 = emu.run(params, dummy, precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX, seed=77, n=64)
+    np.testing.assert_allclose(lean.final_wealth, g64.final_wealth, rtol=5e-3)
+    # non-default tracking-error dof -> the lean build must fall back to its general loop, same results
+    p2, k2 = _c2_params(sids, UPRO={"tracking_error_df": 7})
+    lean2, fast2 = emu.run_lean(p2, 16, seed=78)
+    assert not fast2
+    gen2 = emu.run(p2, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=78, n=16)
+    np.testing.assert_allclose(lean2.final_wealth, gen2.final_wealth, rtol=2e-5)
