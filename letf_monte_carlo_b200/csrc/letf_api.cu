@@ -240,10 +240,10 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
   e->params = *params;
   e->device = device; e->precision = precision;
   memset(&e->info, 0, sizeof(e->info));
-  cudaDeviceProp prop;
-  cudaError_t ce = cudaGetDeviceProperties(&prop, device);
-  if (ce != cudaSuccess) { delete e; return fail_cuda(ce, "cudaGetDeviceProperties"); }
-  e->sm_count = prop.multiProcessorCount;
+  int sms = 0;
+  cudaError_t ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (ce != cudaSuccess) { delete e; return fail_cuda(ce, "cudaDeviceGetAttribute"); }
+  e->sm_count = sms;
   e->info.sm_count = e->sm_count;
   for (int r = 0; r < 2; r++) {
     int nd = params->n_duration[r];

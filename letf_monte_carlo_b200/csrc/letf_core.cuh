@@ -67,6 +67,7 @@ template <> struct Drawdown<double> {
   }
   LETF_HD double value() const { return ::fabs(mn); }
   LETF_HD void init_open() { rm = 0; mn = 0; }
+  LETF_HD void step_ret(double) {}
 };
 template <> struct Drawdown<float> {
   float q, qmin;
@@ -75,6 +76,11 @@ template <> struct Drawdown<float> {
   LETF_HD void init_open() { q = INFINITY; qmin = 1.0f; }
   LETF_HD void step(double, float growth) {
     q = fminf(1.0f, q * growth);
+    qmin = fminf(qmin, q);
+  }
+  // same with growth = 1 + ret folded into one FMA
+  LETF_HD void step_ret(float ret) {
+    q = fminf(1.0f, fmaf(q, ret, q));
     qmin = fminf(qmin, q);
   }
   LETF_HD double value() const { return (double)(1.0f - qmin); }
@@ -511,6 +517,9 @@ struct Trial {
       const R vmult = clipr(M::sqrt_(EXACT ? vix / (R)20 : vix * (R)0.05), (R)0.5, (R)1.5);
       const R rmult = reg == 0 ? (R)1 : (R)1.15;
       const R vrmult = vmult * rmult;
+      // FAST: day 0 carries no tracking error (engine.py:184 starts at i = 1); te_prev is 0 there, so zeroing the
+      // innovation scale once per day replaces a select per asset
+      const R vrlive = FAST ? (i >= 1 ? vrmult : (R)0) : vrmult;
 
       // ---- the six ETF layers (engine.py:360-420)
       R ret[kAssets];
@@ -528,6 +537,7 @@ struct Trial {
           const DevAsset<R>& ap = p.act[a];
           R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
           R u = EXACT ? (ap.beta_applies ? ub * ap.beta : ub) : ub * ap.beta_eff;
+          if (FAST) u = M::fma_(ap.w_spy, spy, ap.w_qqq * qqq);   // no TLT series in this loop; 0 * finite is exact
           R spread = (!FAST && p.has_funding) ? spread_common : ap.borrow_spread;
           R lev;
           if (!EXACT && MARKET == LETF_MARKET_NORMAL && (FAST || !p.has_funding)) {
@@ -555,8 +565,8 @@ struct Trial {
               innov *= ap.te_base * vmult * rmult * (R)1;
               te_raw = ap.te_rho * te_prev[a] + ap.te_arw * innov * mm;
             } else {
-              te_raw = ap.te_rho * te_prev[a] + (innov * vrmult) * (ap.te_scale * mm);
-              if (!TAPEIO) te_raw = i >= 1 ? te_raw : (R)0;
+              te_raw = ap.te_rho * te_prev[a] + (innov * vrlive) * (ap.te_scale * mm);
+              if (!TAPEIO && !FAST) te_raw = i >= 1 ? te_raw : (R)0;
             }
           } else if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T, 0);
           te_prev[a] = te_raw;
@@ -578,7 +588,7 @@ struct Trial {
           if (EXACT) {
             if (i == 0) ddA[a].init((double)p.W0 * cp[a]);
             else ddA[a].step((double)p.W0 * cp[a], (R)1 + er);
-          } else ddA[a].step(0.0, (R)1 + er);           // starts "open" (q = inf): day 0 lands on q = 1
+          } else ddA[a].step_ret(er);                   // starts "open" (q = inf): day 0 lands on q = 1
         }
       }
       {
@@ -590,7 +600,7 @@ struct Trial {
           if (EXACT) {
             if (i == 0) ddT.init((double)p.W0 * cp_tlt);
             else ddT.step((double)p.W0 * cp_tlt, (R)1 + tlt);
-          } else ddT.step(0.0, (R)1 + tlt);
+          } else ddT.step_ret(tlt);
         }
       }
       const R cash = p.cash_daily[reg];

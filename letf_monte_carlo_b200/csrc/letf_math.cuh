@@ -78,6 +78,7 @@ template <> struct Mth<double> {
   static LETF_HD double sqrt_(double x) { return ::sqrt(x); }
   static LETF_HD double rsqrt_(double x) { return 1.0 / ::sqrt(x); }
   static LETF_HD double log_(double x) { return ::log(x); }
+  static LETF_HD double neg2log_(double x) { return -2.0 * ::log(x); }
   static LETF_HD double tanh_(double x) { return ::tanh(x); }
   static LETF_HD double pow_(double x, double y) { return ::pow(x, y); }
   static LETF_HD double abs_(double x) { return ::fabs(x); }
@@ -86,6 +87,15 @@ template <> struct Mth<double> {
   static LETF_HD double u01(uint32_t a) { return ((double)a + 0.5) * 2.3283064365386963e-10; }
   static LETF_HD double u01_16(uint32_t a) { return ((double)a + 0.5) * (1.0 / 65536.0); }
   static LETF_HD double u01_12(uint32_t a) { return ((double)a + 0.5) * (1.0 / 4096.0); }
+  static LETF_HD double bm_parts(uint32_t a, uint32_t b, double& cs, double& sn) {
+    double th = 6.283185307179586476925 * u01(b);
+    cs = ::cos(th); sn = ::sin(th);
+    return -2.0 * ::log(u01(a));
+  }
+  static LETF_HD double bm_cos(uint32_t a, uint32_t b, double& cs) {
+    cs = ::cos(6.283185307179586476925 * u01(b));
+    return -2.0 * ::log(u01(a));
+  }
   static LETF_HD void box_muller(uint32_t a, uint32_t b, double& n0, double& n1) {
     double r = ::sqrt(-2.0 * ::log(u01(a)));
     double th = 6.283185307179586476925 * u01(b);
@@ -98,9 +108,10 @@ template <> struct Mth<float> {
   typedef float T;
 #if defined(__CUDA_ARCH__)
   static LETF_HD float sqrt_(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-  static LETF_HD float rsqrt_(float x) { return rsqrtf(x); }
+  static LETF_HD float rsqrt_(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float log2_(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float log_(float x) { return 0.6931471805599453f * log2_(x); }
+  static LETF_HD float neg2log_(float x) { return -1.3862943611198906f * log2_(x); }   // -2 ln x, one multiply
   static LETF_HD float tanh_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float pow_(float x, float y) { return __powf(x, y); }
   static LETF_HD float div_(float a, float b) { return __fdividef(a, b); }
@@ -109,6 +120,7 @@ template <> struct Mth<float> {
   static LETF_HD float rsqrt_(float x) { return 1.0f / ::sqrtf(x); }
   static LETF_HD float log2_(float x) { return ::log2f(x); }
   static LETF_HD float log_(float x) { return ::logf(x); }
+  static LETF_HD float neg2log_(float x) { return -2.0f * ::logf(x); }
   static LETF_HD float tanh_(float x) { return ::tanhf(x); }
   static LETF_HD float pow_(float x, float y) { return ::powf(x, y); }
   static LETF_HD float div_(float a, float b) { return a / b; }
@@ -119,6 +131,29 @@ template <> struct Mth<float> {
   static LETF_HD float u01(uint32_t a) { return fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
   static LETF_HD float u01_16(uint32_t a) { return fmaf((float)a, 1.0f / 65536.0f, 0.5f / 65536.0f); }
   static LETF_HD float u01_12(uint32_t a) { return fmaf((float)a, 1.0f / 4096.0f, 0.5f / 4096.0f); }
+  // squared radius L = -2 ln U and the unit direction (cos, sin) of a Box-Muller pair
+  static LETF_HD float bm_parts(uint32_t a, uint32_t b, float& cs, float& sn) {
+    float th = (float)(int32_t)b * 1.4629180792671596e-9f;
+#if defined(__CUDA_ARCH__)
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(th));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(th));
+    return -1.3862943611198906f * log2_(u01(a));
+#else
+    cs = ::cosf(th); sn = ::sinf(th);
+    return -2.0f * ::logf(u01(a));
+#endif
+  }
+  // squared radius and cos only (the sine enters the t-variate as sin^2 = 1 - cos^2)
+  static LETF_HD float bm_cos(uint32_t a, uint32_t b, float& cs) {
+    float th = (float)(int32_t)b * 1.4629180792671596e-9f;
+#if defined(__CUDA_ARCH__)
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(th));
+    return -1.3862943611198906f * log2_(u01(a));
+#else
+    cs = ::cosf(th);
+    return -2.0f * ::logf(u01(a));
+#endif
+  }
   static LETF_HD void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     float u = u01(a);
     // angle in [-pi, pi): signed reinterpretation of the second word
@@ -217,17 +252,27 @@ LETF_HD int df_fast_k(double df) {
 template <typename R>
 LETF_HD R student_t5(const U4& b) {
   typedef Mth<R> M;
-  R n0, n1;
-  M::box_muller(b.x, b.y, n0, n1);
-  R c2 = (R)-2 * M::log_(M::u01(b.z) * M::u01(b.w)) + n1 * n1;
-  if (sizeof(R) == 8) return n0 * M::sqrt_(M::div_((R)5, rmax(c2, (R)1e-30)));
-  return n0 * (M::sqrt_((R)5) * M::rsqrt_(rmax(c2, (R)1e-30)));
+  if (sizeof(R) == 8) {
+    R n0, n1;
+    M::box_muller(b.x, b.y, n0, n1);
+    R c2 = (R)-2 * M::log_(M::u01(b.z) * M::u01(b.w)) + n1 * n1;
+    return n0 * M::sqrt_(M::div_((R)5, rmax(c2, (R)1e-30)));
+  }
+  // fp32: with L = -2 ln U (the squared Box-Muller radius), N0 = sqrt(L) cos, N1^2 = L sin^2, so
+  //   t = cos * sqrt(5 L / c2) = cos * (5 L) * rsqrt(5 L * c2),   sin^2 = 1 - cos^2
+  // -> 4 MUFU (lg2, cos, lg2, rsq)
+  R cs;
+  R L = M::bm_cos(b.x, b.y, cs);
+  R c2 = M::fma_(L, M::fma_(-cs, cs, (R)1), M::neg2log_(M::u01(b.z) * M::u01(b.w)));
+  R x5 = (R)5 * L;
+  return cs * (x5 * M::rsqrt_(rmax(x5 * c2, (R)1e-30)));
 }
 
 // Student-t(df) from one Philox block: N0 / sqrt(chi2(df) / df).
 template <typename R>
 LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
+  if (sizeof(R) == 4 && fast_k == 5) return student_t5<R>(b);
   R n0, n1;
   M::box_muller(b.x, b.y, n0, n1);
   R c2 = fast_k ? chi2_int_fast<R>(fast_k, b.z, b.w, n1)

@@ -17,6 +17,7 @@ template <typename R> struct DevAsset {
   R lev, bl, er_daily, borrow_spread, te_base, te_df, te_rho, te_arw, te_down, te_clip, beta;
   R bl_252;          // max(leverage - 1, 0) / 252      (fp32 fast path of utils.py:169-216)
   R beta_eff;        // beta if it applies, else exactly 1
+  R w_spy, w_qqq;    // beta_eff on the series' own underlying, 0 on the other (FAST loop: u = w_spy*spy + w_qqq*qqq)
   R carry_const;     // iid-normal market: expense/252 + borrow at the constant rate (loop invariant)
   R te_scale;        // te_base * sqrt(1 - rho^2)
   int und, beta_applies, te_fast_k, pad;
@@ -183,6 +184,8 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     y.und = x.underlying; y.beta_applies = x.beta_applies; y.te_fast_k = df_fast_k(x.te_df);
     y.bl_252 = (R)(x.leverage > 1.0 ? (x.leverage - 1.0) / 252 : 0.0);
     y.beta_eff = x.beta_applies ? (R)x.beta : (R)1;
+    y.w_spy = x.underlying == 0 ? y.beta_eff : (R)0;
+    y.w_qqq = x.underlying == 1 ? y.beta_eff : (R)0;
     {
       double rate = s.const_rf + x.borrow_spread; if (!(rate > 0.0)) rate = 0.0;
       y.carry_const = (R)(x.expense_ratio / 252 + (x.leverage > 1.0 ? (x.leverage - 1.0) * rate / 252 : 0.0));

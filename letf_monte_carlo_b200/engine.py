@@ -153,10 +153,10 @@ class PathEngine:
 
     def run_host(self, n_trials: int, *, first_trial: int = 0, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
                  tape: HostTape | None = None, out: HostOutputs | None = None, journal: bool = False,
-                 raise_nonfinite: bool = True) -> HostOutputs:
+                 raise_nonfinite: bool = True, pinned: bool = False) -> HostOutputs:
         """Same with host (numpy) buffers: copies in, runs, copies out, synchronises."""
         if out is None:
-            out = HostOutputs(self.n_strategies, n_trials, journal=journal)
+            out = HostOutputs(self.n_strategies, n_trials, journal=journal, pinned=pinned)
         ts = tape.as_struct() if tape is not None else None
         rc = self._lib.letf_run_host(self._h, seed, first_trial, n_trials, rng_mode,
                                      C.byref(ts) if ts is not None else None, C.byref(out.as_struct()))

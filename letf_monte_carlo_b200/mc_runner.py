@@ -104,6 +104,32 @@ class MonteCarloRun(dict):
                 "engine": "letf_monte_carlo_b200"}
 
 
+_ENGINES: dict = {}      # (parameter bytes, precision, device) -> PathEngine; the handle owns device scratch worth reusing
+_ENGINE_CACHE_MAX = 8
+
+
+def _engine_for(params, keep, precision, device):
+    """Engines are pure functions of their parameter block, so repeated calls (one per horizon in
+    letf.run(), letf/__init__.py:150-162) reuse the handle instead of re-creating device state."""
+    import ctypes as C
+    from .engine import PathEngine, default_device
+    dev = default_device() if device is None else int(device)
+    probe = type(params)()
+    C.memmove(C.byref(probe), C.byref(params), C.sizeof(params))
+    durs = []
+    for r in range(2):
+        nd = int(params.n_duration[r])
+        durs.append(bytes(C.string_at(params.duration_samples[r], 4 * nd)) if nd > 0 else b"")
+        probe.duration_samples[r] = None                   # host pointers are not part of the identity
+    key = (bytes(probe), tuple(durs), str(precision), dev)
+    eng = _ENGINES.get(key)
+    if eng is None or eng._h is None:
+        while len(_ENGINES) >= _ENGINE_CACHE_MAX:
+            _ENGINES.pop(next(iter(_ENGINES))).close()
+        eng = _ENGINES[key] = PathEngine(params, keep, precision=precision, device=dev)
+    return eng
+
+
 def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correlation_matrices,
                                historical_df=None, *, cfg=None, precision=None, seed=None, device=None,
                                verbose=True):
@@ -125,6 +151,7 @@ def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correla
     if verbose and rank == 0:
         print(f"\n{'=' * 80}\nMONTE CARLO: {n_total:,} sims x {time_horizon}Y  "
               f"[B200 path engine, {precision}, {ws} GPU(s)]\n{'=' * 80}")
-    eng = PathEngine(params, keep, precision=precision, device=device if device is not None else getattr(cfg, "GPU_DEVICE", None))
-    out = eng.run_host(hi - lo, first_trial=lo, seed=seed)      # raises NonFiniteTrials like the reference's ValueError
+    eng = _engine_for(params, keep, precision, device if device is not None else getattr(cfg, "GPU_DEVICE", None))
+    # raises NonFiniteTrials like the reference's ValueError; results land in page-locked host arrays
+    out = eng.run_host(hi - lo, first_trial=lo, seed=seed, pinned=True)
     return MonteCarloRun(eng, out, strategy_ids, time_horizon, seed, lo, hi - lo, n_total, TAXABLE_IDS)

@@ -15,20 +15,30 @@ FIELDS = ("final_wealth", "max_dd", "num_trades", "journal_count", "journal_volu
 _OPTIONAL_JOURNAL = ("journal_count", "journal_volume")
 
 
+def _host_array(shape, dtype, pinned):
+    if pinned:
+        import torch
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.uint32: torch.int32}[dtype]
+        a = torch.zeros(shape, dtype=tdt, pin_memory=True).numpy()      # page-locked: device->host at full PCIe rate
+        return a.view(np.uint32) if dtype is np.uint32 else a
+    return np.zeros(shape, dtype)
+
+
 class HostOutputs:
-    def __init__(self, n_strategies: int, n: int, journal: bool = True):
+    def __init__(self, n_strategies: int, n: int, journal: bool = True, pinned: bool = False):
         S = max(int(n_strategies), 1)
         self.n = int(n)
         self.n_strategies = int(n_strategies)
-        self.final_wealth = np.zeros((S, n))
-        self.max_dd = np.zeros((S, n))
-        self.num_trades = np.zeros((S, n), np.int32)
-        self.journal_count = np.zeros((S, n), np.int32) if journal else None
-        self.journal_volume = np.zeros((S, n)) if journal else None
-        self.start_offset = np.zeros(n, np.int32)
-        self.flags = np.zeros(n, np.uint32)
-        self.regime_days = np.zeros((2, n), np.int32)
-        self.jump_days = np.zeros(n, np.int32)
+        z = lambda shape, dt: _host_array(shape, dt, pinned)
+        self.final_wealth = z((S, n), np.float64)
+        self.max_dd = z((S, n), np.float64)
+        self.num_trades = z((S, n), np.int32)
+        self.journal_count = z((S, n), np.int32) if journal else None
+        self.journal_volume = z((S, n), np.float64) if journal else None
+        self.start_offset = z(n, np.int32)
+        self.flags = z(n, np.uint32)
+        self.regime_days = z((2, n), np.int32)
+        self.jump_days = z(n, np.int32)
 
     def as_struct(self) -> abi.Outputs:
         o = abi.Outputs()
