@@ -185,6 +185,10 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if ws != args.gpus:
         if ws == 1 and args.gpus > 1:
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
@@ -288,7 +292,8 @@ def run_b200(args):
                                   "scratch_bytes": info["scratch_bytes"]}},
             "clocks": clocks,
             "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed (engine created per call, host results)",
+                    "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed: parameter dicts in, host result arrays out "
+                           "(engine handle cached across calls, page-locked outputs)",
                     "steps": e2e_steps, "median_final_wealth": med},
             "gpu_launches": launches + e2e_launches,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
@@ -306,7 +311,10 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{nt} trials x {T} days of the same workload in {dt:.1f} s, oracle/letf_oracle.c "
                                               f"incl. its own CPU random draws, {threads} threads"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     eng.close()
     if ws > 1:
         dist.barrier()

@@ -150,7 +150,7 @@ struct Trial {
       U4 b = rng_block(key, (uint32_t)ks, STREAM_SPELL);
       if (p.n_dur[cur] > 0) spell = p.dur[cur][mulhi32(b.y, (uint32_t)p.n_dur[cur])];
       else {
-        R q = M::log_(M::u01(b.x)) / p.log_pstay[cur];   // inverse CDF of the geometric dwell time
+        R q = M::div_(M::log_(M::u01(b.x)), p.log_pstay[cur]);   // inverse CDF of the geometric dwell time
         spell = q < (R)G ? (int)q + 1 : G;
       }
       if (rec && ks < ka.tape.max_spells) ka.tape.spells[(int64_t)ks * nt + tcol] = spell;
@@ -278,7 +278,7 @@ struct Trial {
       for (int a = 0; a < 3; a++) {
         R xx = jp.mu[a] + zz[a] * scale;
         R xc = clipr(xx, (R)-0.95, (R)4.0);
-        js.pz[a] = (xc - jp.mu[a]) / M::sqrt_(rmax(js.h[a], (R)1e-10));
+        js.pz[a] = EXACT ? (xc - jp.mu[a]) / M::sqrt_(rmax(js.h[a], (R)1e-10)) : (xc - jp.mu[a]) * M::rsqrt_(rmax(js.h[a], (R)1e-10));
         x[a] = xc;
       }
     }
@@ -445,7 +445,7 @@ struct Trial {
       if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
         vix = vix_step(g, reg, vix, x[0], vn);
         R irx = clipr(p.irx_base[reg] + ((R)0 + (R)0.5 * in), (R)0, (R)15);   // engine.py:117-123
-        rf = clipr(irx, (R)0, (R)20) / (R)100;                                // engine.py:516
+        rf = EXACT ? clipr(irx, (R)0, (R)20) / (R)100 : clipr(irx, (R)0, (R)20) * (R)0.01;                                // engine.py:516
       }
       R spy = x[0], qqq = x[1], tlt = x[2];
       if (EXACT) {
@@ -479,7 +479,7 @@ struct Trial {
           }
           liq = clipr(sp.liq_mu + sp.liq_phi * (liq - sp.liq_mu) + ((R)0 + sp.liq_sigma * ln), (R)0, (R)3);
           cred = clipr(sp.cr_mu + sp.cr_phi * (cred - sp.cr_mu) + ((R)0 + sp.cr_sigma * cn), (R)0, (R)3);
-          R vamp = rmax((vix - (R)25) / (R)30, (R)0);
+          R vamp = rmax(EXACT ? (vix - (R)25) / (R)30 : (vix - (R)25) * (R)(1.0 / 30.0), (R)0);
           R jp = clipr(sp.jbase + (R)0.008 * vamp + (R)0.003 * liq, (R)0, (R)0.01);
           if (ju < jp || rec) {
             // record mode draws the jump size every day: antithetic twins share a tape column but
@@ -617,8 +617,8 @@ struct Trial {
         if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
         if (HAS_RSI) {
           R gm = sg.gain14.mean(14), lm = sg.loss14.mean(14);
-          R rs = gm / lm;
-          s_rsi = (R)100 - ((R)100 / ((R)1 + rs));
+          R rs = M::div_(gm, lm);
+          s_rsi = (R)100 - M::div_((R)100, (R)1 + rs);
         }
         if (HAS_MOM) s_mom = sg.mom126.sum(1);
         if (HAS_V5) s_v5 = sg.v5.stdev(1) * V;
@@ -633,7 +633,7 @@ struct Trial {
         // vol_slow.pct_change(5): shifted 20-day vol today vs five rows earlier
         for (int q = 5; q >= 1; q--) sg.volhist[q] = sg.volhist[q - 1];
         sg.volhist[0] = s_v20;
-        s_vm = sg.volhist[0] / sg.volhist[5] - (R)1;
+        s_vm = M::div_(sg.volhist[0], sg.volhist[5]) - (R)1;
       }
       // roll forward (pandas: removals first, then the new observation)
       if (NEED_RINGP) {
@@ -717,20 +717,20 @@ struct Trial {
           if (i % (int)st.p[0] == 0) {
             R wt = 0, lt = 0;
             for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) {
-              R cw = pvv[a] / total;
+              R cw = M::div_(pvv[a], total);
               wt += M::abs_(cw - st.w[a]);
               R tl = p.assets[a].lev, emb = (R)1;
               if (tl > (R)1) {
-                R uu = ret[a] / tl;
-                emb = M::abs_((R)1 + tl * uu) > (R)0.01 ? tl * ((R)1 + uu) / ((R)1 + tl * uu) : tl;
+                R uu = M::div_(ret[a], tl);
+                emb = M::abs_((R)1 + tl * uu) > (R)0.01 ? M::div_(tl * ((R)1 + uu), (R)1 + tl * uu) : tl;
               }
-              lt += M::abs_(emb - tl) / tl * cw;
+              lt += M::div_(M::abs_(emb - tl), tl) * cw;
             }
             R turn = wt + lt;
             if (p.apply_costs && turn > (R)0.01) { total -= turn * p.rebalance_cost * total; w_new = (double)total; }
             for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = total * st.w[a]; sl.trades++; }
           }
-          growth = (R)(w_new / sl.W);
+          growth = EXACT ? (R)(w_new / sl.W) : M::div_((R)w_new, (R)sl.W);
           sl.W = w_new;
           sl.dd.step(sl.W, growth);
           continue;
@@ -756,55 +756,55 @@ struct Trial {
           switch (ty) {
             case LETF_ST_VOL_TARGETING: {
               R cv = s_v20_today;
-              alloc = (isnan_(cv) || cv < (R)0.01) ? (R)1 : clipr(st.p[0] / cv, (R)0.2, (R)2.0);
+              alloc = (isnan_(cv) || cv < (R)0.01) ? (R)1 : clipr(M::div_(st.p[0], cv), (R)0.2, (R)2.0);
               cashleg = false;
             } break;
             case LETF_ST_ADAPTIVE_VOL: {
               R cv = s_v20f, cs = s_sma200f;
               if (isnan_(cv) || isnan_(cs) || cv < (R)0.001) skip = true;
-              else alloc = clipr((P_prev > cs ? st.p[0] : st.p[1]) / cv, (R)0, (R)1);
+              else alloc = clipr(M::div_(P_prev > cs ? st.p[0] : st.p[1], cv), (R)0, (R)1);
             } break;
             case LETF_ST_DOWNSIDE_VOL: {
               R dv = s_dv20f;
-              alloc = (isnan_(dv) || dv < (R)0.001) ? (R)1 : clipr(st.p[0] / dv, (R)0, (R)1.5);
+              alloc = (isnan_(dv) || dv < (R)0.001) ? (R)1 : clipr(M::div_(st.p[0], dv), (R)0, (R)1.5);
             } break;
             case LETF_ST_CONVEX_VOL: {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
-              R al = st.p[0] / v;
+              R al = M::div_(st.p[0], v);
               if (P_prev > s_sma200) al = M::pow_(al, st.p[1]);
               alloc = clipr(al, (R)0, (R)1);
             } break;
             case LETF_ST_VOL_VELOCITY: {
               R ev = s_v5 > s_v20 ? s_v5 : s_v20;       // python max(vol_slow, vol_fast)
               if (isnan_(ev) || ev < (R)0.001) ev = (R)0.5;
-              alloc = clipr(st.p[0] / ev, (R)0, (R)1);
+              alloc = clipr(M::div_(st.p[0], ev), (R)0, (R)1);
             } break;
             case LETF_ST_VOL_MOM: {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
-              R al = st.p[0] / v;
+              R al = M::div_(st.p[0], v);
               if (!isnan_(s_vm) && s_vm < (R)-0.10) al *= (R)1.2;
               if (!isnan_(s_vm) && s_vm > (R)0.10) al *= (R)0.7;
               alloc = clipr(al, (R)0, (R)1);
             } break;
             case LETF_ST_SKEW_CONVEX: {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
-              R al = st.p[0] / v;
+              R al = M::div_(st.p[0], v);
               if (!isnan_(s_sk) && s_sk > (R)0) al = M::pow_(al, (R)1.3);
               else if (!isnan_(s_sk) && s_sk < (R)-0.5) al *= (R)0.5;
               alloc = clipr(al, (R)0, (R)1);
             } break;
             case LETF_ST_META_ENSEMBLE: {
               R dv = s_dv20; if (isnan_(dv) || dv < (R)0.001) dv = (R)0.25;
-              R al = st.p[0] / dv;
+              R al = M::div_(st.p[0], dv);
               if (P_prev > s_sma200) al = M::pow_(al, (R)1.2);
               if (s_v5 > (R)1.5 * s_v20) al *= (R)0.5;
               alloc = clipr(al, (R)0, (R)1);
             } break;
             case LETF_ST_REGIME_ASYMMETRIC: {
-              R vr = s_v5 / s_v60;
+              R vr = M::div_(s_v5, s_v60);
               bool crisis = (vix > st.p[2]) || (vr > st.p[3]);
               R tv = crisis ? st.p[1] : st.p[0];
-              alloc = (isnan_(s_v5) || s_v5 < (R)0.001) ? (R)0.5 : clipr(tv / s_v5, (R)0, (R)1.2);
+              alloc = (isnan_(s_v5) || s_v5 < (R)0.001) ? (R)0.5 : clipr(M::div_(tv, s_v5), (R)0, (R)1.2);
             } break;
             case LETF_ST_SKEW_KELLY: {
               R vol = s_v20, dv = s_dv20, sk = s_sk, mr = s_mean60;
@@ -818,8 +818,8 @@ struct Trial {
               else if (sk > (R)0.5) { ev = vol * (R)0.9; pen = (R)1.2; }
               else { ev = vol; pen = (R)1; }
               R ks = (R)1;
-              if (ev > (R)0.01) { ks = (mr - (R)0.03) / (ev * ev); ks = ks * st.p[3]; ks = clipr(ks, (R)0.2, (R)2.0); }
-              alloc = clipr((st.p[0] / ev) * pen * (ks / (R)1.5), (R)0, (R)1.5);
+              if (ev > (R)0.01) { ks = M::div_(mr - (R)0.03, ev * ev); ks = ks * st.p[3]; ks = clipr(ks, (R)0.2, (R)2.0); }
+              alloc = clipr(M::div_(st.p[0], ev) * pen * M::div_(ks, (R)1.5), (R)0, (R)1.5);
             } break;
             case LETF_ST_MOM_VOL_CONV: {
               R mom = s_mom, vf = s_v10, vs = s_v60;
@@ -827,9 +827,9 @@ struct Trial {
               if (isnan_(vf) || vf < (R)0.001) vf = (R)0.30;
               if (isnan_(vs) || vs < (R)0.001) vs = (R)0.25;
               R mmul = mom > st.p[4] ? (R)1.3 : (mom > (R)0 ? (R)1.0 : (R)0.5);
-              R ratio = vf / vs, vm, ev;
+              R ratio = M::div_(vf, vs), vm, ev;
               if (ratio < (R)0.8) { vm = (R)1.2; ev = vf; } else if (ratio > (R)1.3) { vm = (R)0.6; ev = vf; } else { vm = (R)1.0; ev = vs; }
-              alloc = clipr(st.p[0] * (mmul * vm) / ev, (R)0, (R)1.5);
+              alloc = clipr(M::div_(st.p[0] * (mmul * vm), ev), (R)0, (R)1.5);
             } break;
             case LETF_ST_CONVICTION: {
               R mom = s_mom, dv = s_dv20, vf = s_v5, vs = s_v60;
@@ -839,10 +839,10 @@ struct Trial {
               if (isnan_(vs) || vs < (R)0.001) vs = (R)0.25;
               R ms = mom > (R)0.15 ? (R)1.0 : (mom > (R)0.05 ? (R)0.7 : (mom > (R)0 ? (R)0.4 : (R)0));
               R ts = P_prev > s_sma100 ? (R)0.5 : (R)0;
-              R ratio = vf / vs;
+              R ratio = M::div_(vf, vs);
               R vsc = ratio < (R)0.9 ? (R)0.5 : (ratio < (R)1.2 ? (R)0.3 : (R)0);
               R conv = ms + ts + vsc;
-              alloc = clipr((st.p[0] / dv) * ((R)0.3 + (conv * (R)0.55)), (R)0, (R)1.5);
+              alloc = clipr(M::div_(st.p[0], dv) * ((R)0.3 + (conv * (R)0.55)), (R)0, (R)1.5);
               thresh = st.p[4]; sticky = true;
             } break;
             default: break;
@@ -913,7 +913,7 @@ struct Trial {
   LETF_HD R vix_step(int g, int reg, R vix_prev, R spy_ret, R noise) const {
     if (g == 0) return p.vix_base[reg];
     const DevVix<R>& v = p.vix[reg];
-    R shock = rmax(-spy_ret, (R)0) / v.denom;
+    R shock = M::div_(rmax(-spy_ret, (R)0), v.denom);
     R vj = v.jump_scale * rmax((R)0, shock - v.jump_thr);
     R cand = v.phi * vix_prev + v.drift + vj + ((R)0 + v.noise_std * noise);
     return cand > (R)10 ? cand : (R)10;

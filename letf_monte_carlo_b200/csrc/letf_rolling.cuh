@@ -39,7 +39,7 @@ template <typename R, bool EXACT> struct RollSum {
   }
   LETF_HD R mean(int mp) const {
     if (nobs < mp || nobs <= 0) return nan_<R>();
-    R r = s / (R)nobs;
+    R r = Mth<R>::div_(s, (R)nobs);
     if (EXACT) {
       if (ncs >= nobs) r = prev;
       else if (neg == 0 && r < (R)0) r = (R)0;
@@ -69,7 +69,7 @@ template <typename R, bool EXACT> struct RollVar {
         ssq = ssq - (v - pm) * (v - mean);
       } else {
         R pm = mean, t = v - mean;
-        mean = mean - t / (R)nobs;
+        mean = mean - Mth<R>::div_(t, (R)nobs);
         ssq = ssq - (v - pm) * (v - mean);
       }
     } else { mean = (R)0; ssq = (R)0; }
@@ -86,14 +86,14 @@ template <typename R, bool EXACT> struct RollVar {
       ssq = ssq + (v - pm) * (v - mean);
     } else {
       R pm = mean, t = v - mean;
-      mean = mean + t / (R)nobs;
+      mean = mean + Mth<R>::div_(t, (R)nobs);
       ssq = ssq + (v - pm) * (v - mean);
     }
   }
   // rolling(w, min_periods = mp).std()
   LETF_HD R stdev(int mp) const {
     if (nobs < mp || nobs <= 1) return nan_<R>();
-    R r = ssq / (R)(nobs - 1);
+    R r = Mth<R>::div_(ssq, (R)(nobs - 1));
     if (r < (R)0) r = (R)0;
     return Mth<R>::sqrt_(r);
   }
@@ -108,7 +108,7 @@ template <typename R, bool EXACT> struct RollSkew {
     int nn = nobs - 1;
     if (nn == 0) { mean = m2 = m3 = (R)0; }
     else {
-      R delta = v - mean, dn = delta / (R)nn, term1 = delta * dn * (R)nobs;
+      R delta = v - mean, dn = Mth<R>::div_(delta, (R)nn), term1 = delta * dn * (R)nobs;
       m3 = m3 - (term1 * dn * (R)(nobs + 1) - (R)3 * dn * m2);
       mean = mean - dn;
       m2 = m2 - term1;
@@ -117,7 +117,7 @@ template <typename R, bool EXACT> struct RollSkew {
   }
   LETF_HD void add(R v) {
     int nn = nobs + 1;
-    R delta = v - mean, dn = delta / (R)nn, term1 = delta * dn * (R)nobs;
+    R delta = v - mean, dn = Mth<R>::div_(delta, (R)nn), term1 = delta * dn * (R)nobs;
     m3 = m3 + term1 * dn * (R)(nn - 2) - (R)3 * dn * m2;
     m2 = m2 + term1;
     mean = mean + dn;
@@ -126,10 +126,11 @@ template <typename R, bool EXACT> struct RollSkew {
   }
   LETF_HD R skew(int mp) const {
     if (nobs < mp || nobs < 3) return nan_<R>();
-    R d = (R)nobs, B = m2 / d;
+    R d = (R)nobs, B = Mth<R>::div_(m2, d);
     if (EXACT && ncs >= nobs) return (R)0;
     if (B <= (R)1e-14) return nan_<R>();
-    return Mth<R>::sqrt_(d * (d - (R)1)) / (d - (R)2) * (m3 / d) / (B * Mth<R>::sqrt_(B));
+    typedef Mth<R> M_;
+    return M_::div_(M_::div_(M_::sqrt_(d * (d - (R)1)), d - (R)2) * M_::div_(m3, d), B * M_::sqrt_(B));
   }
 };
 

@@ -54,3 +54,34 @@ def assert_matches_reference(out, doc, rtol, dd_atol, exact_counts=True, journal
     np.testing.assert_array_equal(out.jump_days, np.array(meta["jump_days"]))
     rep = (out.flags & abi.FLAG_REPAIRED) != 0
     np.testing.assert_array_equal(rep, np.array(meta["repaired"]))
+
+
+def reference_distribution():
+    """terminal statistics of the LIVE reference run with its own NumPy streams
+    (oracle/make_reference_distribution.py -> tests/golden/ref_distribution_2y.npz)"""
+    d = np.load(os.path.join(GOLDEN_DIR, "ref_distribution_2y.npz"))
+    return {k: d[k] for k in d.files}
+
+
+def assert_same_distribution(ref, out, sids, p_min=1e-3):
+    """two-sample KS on terminal wealth and max drawdown per strategy, summary quantiles of wealth (rank agreement),
+    mean trade counts within 3 %, regime / jump / repair statistics within sampling error"""
+    from scipy import stats
+    for k, s in enumerate(sids):
+        a, b = ref["final_wealth"][k], out.final_wealth[k]
+        assert stats.ks_2samp(a, b).pvalue > p_min, (s, "final wealth")
+        assert stats.ks_2samp(ref["max_dd"][k], out.max_dd[k]).pvalue > p_min, (s, "max drawdown")
+        for q in (10, 25, 40, 50, 60, 75, 90):       # reporting.py:361-366 percentiles
+            # the reference's q-th percentile must sit at the q-th percentile of our sample, +- 4 points
+            # (its own sampling error at n = 2 400 is ~ 1 point; wealth spans decades, so compare ranks)
+            qa = np.percentile(a, q)
+            rank = 100.0 * np.mean(b <= qa)
+            assert abs(rank - q) < 4.0, (s, q, qa, rank)
+        ta, tb = ref["num_trades"][k].mean(), out.num_trades[k].mean()
+        assert abs(tb - ta) <= 0.03 * max(ta, 1.0), (s, ta, tb)
+    n_ref = len(ref["high_vol_days"])
+    hv = out.regime_days[1]
+    assert abs(hv.mean() - ref["high_vol_days"].mean()) < 5 * ref["high_vol_days"].std() / np.sqrt(n_ref / 2)
+    assert abs(out.jump_days.mean() - ref["jump_days"].mean()) < 0.25
+    rep = ((out.flags & abi.FLAG_REPAIRED) != 0).mean()
+    assert abs(rep - ref["repaired"].mean()) < 0.06

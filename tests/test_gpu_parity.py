@@ -360,3 +360,17 @@ def test_lean_fast_kernel_vs_generic_and_oracle(engine_lib):
     np.testing.assert_allclose(lean.final_wealth, o.final_wealth, rtol=2e-4)
     np.testing.assert_allclose(lean.max_dd, o.max_dd, atol=1e-4)
     assert (lean.flags == 0).all() and (o.flags == 0).all()
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_philox_distribution_matches_live_reference(precision, engine_lib):
+    """KS + summary-quantile agreement of on-device Philox runs with the LIVE reference's own NumPy streams
+    (tests/golden/ref_distribution_2y.npz: 2 400 trials, institutional_v1 defaults, 2 years, 10 strategies)."""
+    from tests.common import assert_same_distribution, reference_distribution
+    ref = reference_distribution()
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, float(ref["years"]), synthetic.fallback_regime_model("default"), ns)
+    with _engine(params, keep, precision) as eng:
+        out = eng.run_host(40000, seed=2718)
+    assert_same_distribution(ref, out, sids)

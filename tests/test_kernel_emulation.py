@@ -172,3 +172,17 @@ def test_lean_fast_variant_matches_generic_build():
     assert not fast2
     gen2 = emu.run(p2, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=78, n=16)
     np.testing.assert_allclose(lean2.final_wealth, gen2.final_wealth, rtol=2e-5)
+
+
+def test_philox_distribution_matches_live_reference():
+    """north star: 'On-device Philox draws must match the reference's distributions by KS test and
+    summary-quantile agreement' - the reference side is the LIVE reference with its own PCG64 streams
+    (2 400 trials, institutional_v1 defaults, 2-year horizon, 10 strategies)."""
+    from tests.common import assert_same_distribution, reference_distribution
+    ref = reference_distribution()
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, float(ref["years"]), synthetic.fallback_regime_model("default"), ns)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    out = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=11, n=8000)
+    assert_same_distribution(ref, out, sids)
