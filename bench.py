@@ -43,6 +43,9 @@ WORKLOADS = {
                trials=1_000_000, years=30, lane_ops=520 * (7560 + 1260) / 7560, mufu=22),
     "c4": dict(desc="BASELINE configs[3]: C3 market + TQQQ/TMF/SPY layers, S1 S2 S4 S5 S6 S19, per GPU 1.25M trials x 7560 days",
                trials=1_250_000, years=30, lane_ops=1130, mufu=40),
+    "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
+                         "200k trials x 7560 days per GPU",
+                    trials=200_000, years=30, lane_ops=2600, mufu=60),
 }
 
 
@@ -61,6 +64,10 @@ def build_workload(name):
     elif name == "c4":
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
         sids = ["S1", "S2", "S4", "S5", "S6", "S19"]
+        model = synthetic.fallback_regime_model("default")
+    elif name == "sweep19":
+        ns = synthetic.config_namespace()
+        sids = ["S%d" % i for i in range(1, 20)]
         model = synthetic.fallback_regime_model("default")
     else:
         raise KeyError(name)

@@ -1,3 +1,3 @@
 // one instantiation of the fused path kernel per translation unit (parallel builds)
 #include "letf_kernels.cuh"
-LETF_INSTANTIATE(f32_joint_t_bench, float, LETF_PREC_F32, 4, 3, 2, false, letf::TM_BENCH, 64, 8)
+LETF_INSTANTIATE(f32_joint_t_bench, float, LETF_PREC_F32, 4, 3, 2, false, letf::TM_BENCH, 0, 0, 64, 8)

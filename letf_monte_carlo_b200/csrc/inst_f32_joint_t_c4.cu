@@ -1,3 +1,3 @@
 // one instantiation of the fused path kernel per translation unit (parallel builds)
 #include "letf_kernels.cuh"
-LETF_INSTANTIATE(f32_joint_t_c4, float, LETF_PREC_F32, 8, 6, 2, false, letf::TM_C4, 128, 1)
+LETF_INSTANTIATE(f32_joint_t_c4, float, LETF_PREC_F32, 8, 6, 2, false, letf::slot_list_mask(1), 1, 25, 128, 1)

@@ -102,10 +102,17 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (k->precision != e->precision || k->market != market) continue;
     if (need_io && !k->tapeio) continue;
     if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
+    if (k->am && k->am != e->params.asset_mask) continue;
+    if (k->list) {      // typed slots: the strategy list must be exactly the one compiled in
+      bool same = slot_list_count(k->list) == n_strat;
+      for (int s = 0; same && s < n_strat; s++) same = slot_list_type(k->list, s) == e->params.strategies[s].type;
+      if (!same) continue;
+    }
     if (!best) { best = k; continue; }
     // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
-    int a = k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio;
-    int b = best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio;
+    // typed-slot builds first, then fewer slots / series / rules, no tape plumbing
+    int a = (k->list ? 0 : 100000) + k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio;
+    int b = (best->list ? 0 : 100000) + best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio;
     if (a < b) best = k;
   }
   return best;
@@ -144,7 +151,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
   if (ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching && G > 0) {
-    size_t b = (size_t)G * 3 * (size_t)nthreads * sizeof(R);
+    size_t b = (size_t)G * 4 * (size_t)nthreads * sizeof(R);
     cudaError_t ce = e->xscr.reserve(b);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
     ka.xscr = (R*)e->xscr.p; scratch += b;

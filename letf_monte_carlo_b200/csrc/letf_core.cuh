@@ -14,6 +14,8 @@
 //   strategies         strategy.py:55-1277        StrategyBank
 //   per-trial stats    engine.py:578-590
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "letf_params.cuh"
 #include "letf_rolling.cuh"
 
@@ -28,7 +30,9 @@ template <typename R, int NS, int NA> struct KArgs {
   int64_t first_trial, n_trials, tape_first;
   int rng_mode;
   int pad;
-  R* xscr;                  // [G][3][nthreads]   moment-matching scratch
+  R* xscr;                  // [nthreads][G][4]   moment-matching scratch: one aligned 4-vector per generated day,
+                            // thread-major (each lane streams its own column; window days are offset by the
+                            // lane's random start, so a day-major layout cannot coalesce the second pass)
   R* ringP;                 // [kRingP][nthreads]
   R* ringS;                 // [kRingS][nthreads]
   R* ringA;                 // [kRingA][nthreads]
@@ -44,6 +48,62 @@ LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #else
   return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Typed strategy-slot lists: builds in which slot s runs ONE compile-time rule, so each rule's code
+// exists once and no per-day type dispatch is left.  list 0 = dynamic dispatch on p.strat[s].type.
+//   1: BASELINE config 4 sweep        S1 S2 S4 S5 S6 S19
+//   2: the reference's default sweep  S1 ... S19 in cfg.STRATEGIES order (letf/config.py:348-437)
+// -2 marks an empty slot.
+LETF_HD constexpr int slot_list_type(int list, int s) {
+  if (list == 1) {
+    switch (s) {
+      case 0: case 1: return LETF_ST_BENCHMARK;
+      case 2: return LETF_ST_SMA;
+      case 3: return LETF_ST_SMA_BAND;
+      case 4: return LETF_ST_PORTFOLIO;
+      case 5: return LETF_ST_CONVICTION;
+      default: return -2;
+    }
+  }
+  if (list == 2) {
+    switch (s) {
+      case 0: case 1: case 2: return LETF_ST_BENCHMARK;
+      case 3: return LETF_ST_SMA;
+      case 4: return LETF_ST_SMA_BAND;
+      case 5: return LETF_ST_PORTFOLIO;
+      case 6: return LETF_ST_VOL_TARGETING;
+      case 7: return LETF_ST_COMPOSITE;
+      case 8: return LETF_ST_ADAPTIVE_VOL;
+      case 9: return LETF_ST_DOWNSIDE_VOL;
+      case 10: return LETF_ST_CONVEX_VOL;
+      case 11: return LETF_ST_VOL_VELOCITY;
+      case 12: return LETF_ST_VOL_MOM;
+      case 13: return LETF_ST_SKEW_CONVEX;
+      case 14: return LETF_ST_META_ENSEMBLE;
+      case 15: return LETF_ST_REGIME_ASYMMETRIC;
+      case 16: return LETF_ST_SKEW_KELLY;
+      case 17: return LETF_ST_MOM_VOL_CONV;
+      case 18: return LETF_ST_CONVICTION;
+      default: return -2;
+    }
+  }
+  return -1;
+}
+LETF_HD constexpr int slot_list_count(int list) {
+  int n = 0;
+  for (int s = 0; s < LETF_MAX_STRATEGIES; s++) if (slot_list_type(list, s) >= 0) n = s + 1;
+  return n;
+}
+LETF_HD constexpr uint32_t slot_list_mask(int list) {
+  uint32_t m = 0;
+  for (int s = 0; s < LETF_MAX_STRATEGIES; s++) if (slot_list_type(list, s) >= 0) m |= 1u << slot_list_type(list, s);
+  return m;
+}
+template <int LIST, typename F, int... S>
+LETF_HD void for_typed_slots(F& f, std::integer_sequence<int, S...>) {
+  (f(S, std::integral_constant<int, slot_list_type(LIST, S)>{}), ...);
 }
 
 #define TM_HAS(t) ((TM >> (t)) & 1u)
@@ -87,8 +147,9 @@ template <> struct Drawdown<float> {
 };
 
 // ------------------------------------------------------------------------------------------
-template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM>
+template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int LIST = 0, int AM = 0>
 struct Trial {
+  // LIST: typed slot list (0 = dynamic); AM: compile-time asset mask (0 = p.act_on at run time)
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
@@ -359,6 +420,8 @@ struct Trial {
     }
 
     // ---- pass 1 (moment matching only): raw joint returns -> scratch, column means (calibration.py:579-588)
+    struct alignas(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) X4 { R x, y, z, w; };
+    X4* const xs = (X4*)ka.xscr + (int64_t)lane * (p.T + p.buffer);
     R shift[3] = {(R)0, (R)0, (R)0};
     const bool two_pass = MARKET == LETF_MARKET_JOINT_T && p.mm;
     const int T = MARKET == kMarketSeries ? ka.series.sim_days : p.T;
@@ -373,8 +436,9 @@ struct Trial {
         int reg = regime_next(rg);
         R x[3], d0, d1;
         market_day<true, false>(g, reg, js, x, d0, d1);
+        X4 v; v.x = x[0]; v.y = x[1]; v.z = x[2]; v.w = (R)0;
+        xs[g] = v;
         for (int a = 0; a < 3; a++) {
-          ka.xscr[((int64_t)g * 3 + a) * nth + lane] = x[a];
           R y = x[a] - cmp[a], t = sum[a] + y;      // Kahan: stays within an ulp of numpy's pairwise mean
           cmp[a] = (t - sum[a]) - y; sum[a] = t;
         }
@@ -402,8 +466,13 @@ struct Trial {
     Slot slot[NS];
     SlotJ sj[JOURNAL ? NS : 1];
     R pv[kPortMax][kAssets];
+#pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++) { slot[s].W = (double)p.W0; slot[s].dd.init((double)p.W0); slot[s].aux = 0; slot[s].trades = 0; }
-    if (JOURNAL) for (int s = 0; s < NS; s++) { sj[s].pos[0] = sj[s].pos[1] = sj[s].pos[2] = 0; sj[s].vol = 0; sj[s].cnt = 0; }
+    if (JOURNAL) {
+#pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
+      for (int s = 0; s < NS; s++) { sj[s].pos[0] = sj[s].pos[1] = sj[s].pos[2] = 0; sj[s].vol = 0; sj[s].cnt = 0; }
+    }
+#pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++)
       if (TM_HAS(LETF_ST_PORTFOLIO) && s < p.n_strat && p.strat[s].type == LETF_ST_PORTFOLIO)
         for (int a = 0; a < kAssets; a++) pv[p.strat[s].port][a] = p.W0 * p.strat[s].w[a];
@@ -419,7 +488,7 @@ struct Trial {
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
       if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
-        x[0] = ka.xscr[((int64_t)g * 3 + 0) * nth + lane] + shift[0];
+        x[0] = xs[g].x + shift[0];
       } else {
         market_day<true, true>(g, reg, js, x, vn, in);
       }
@@ -437,7 +506,8 @@ struct Trial {
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
       } else if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
-        for (int a = 0; a < 3; a++) x[a] = ka.xscr[((int64_t)g * 3 + a) * nth + lane] + shift[a];
+        const X4 v = xs[g];
+        x[0] = v.x + shift[0]; x[1] = v.y + shift[1]; x[2] = v.z + shift[2];
       } else {
         market_day<true, true, FAST>(g, reg, js, x, vn, in);
       }
@@ -533,7 +603,7 @@ struct Trial {
           if (!ka.series.asset_ret[a]) continue;
           er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
         } else {
-          if (!FAST && !p.act_on[a]) continue;
+          if (AM != 0 && NA == kAssets ? !((AM >> a) & 1) : (!FAST && !p.act_on[a])) continue;
           const DevAsset<R>& ap = p.act[a];
           R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
           R u = EXACT ? (ap.beta_applies ? ub * ap.beta : ub) : ub * ap.beta_eff;
@@ -688,15 +758,15 @@ struct Trial {
 
       // ---- strategy rules (strategy.py:55-1277) + running statistics (engine.py:578-590)
       // (buy & hold needs no slot work: its equity is W0 * cp[asset], tracked above)
-      if (HAS_ACTIVE && i >= 1)           // active strategies leave equity[0] = W0
-#pragma unroll
-      for (int s = 0; s < NS; s++) {
-        if (s >= p.n_strat) break;
+      auto slot_body = [&](const int s, auto tyc_) {
+        constexpr int TYC = decltype(tyc_)::value;      // this slot's compile-time rule (typed lists), -1 = dynamic, -2 = empty
+        if (TYC == -2 || TYC == LETF_ST_BENCHMARK || TYC == LETF_ST_BENCHMARK_TLT) return;
+        if (TYC < 0 && s >= p.n_strat) return;
         const DevStrategy<R>& st = p.strat[s];
         Slot& sl = slot[s];
-        const int ty = st.type;
+        const int ty = TYC >= 0 ? TYC : st.type;
         R growth = (R)1;          // W_i / W_{i-1}
-        if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) continue;
+        if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) return;
         R r_strat = 0;
         if (TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND)) if (ty == LETF_ST_SMA || ty == LETF_ST_SMA_BAND) {
           R thr = ty == LETF_ST_SMA ? s_sma200 : s_sma200 * ((R)1 - st.p[1]);
@@ -733,7 +803,7 @@ struct Trial {
           growth = EXACT ? (R)(w_new / sl.W) : M::div_((R)w_new, (R)sl.W);
           sl.W = w_new;
           sl.dd.step(sl.W, growth);
-          continue;
+          return;
         }
         if (TM_HAS(LETF_ST_COMPOSITE)) if (ty == LETF_ST_COMPOSITE) {
           int score = (P_prev > s_sma200f ? 1 : 0) + (((R)40 < s_rsi && s_rsi < (R)80) ? 1 : 0) + (vix_prev < st.p[2] ? 1 : 0);
@@ -754,59 +824,59 @@ struct Trial {
           R alloc = 0, thresh = (R)0.0001;
           bool sticky = false, cashleg = true, skip = false;
           switch (ty) {
-            case LETF_ST_VOL_TARGETING: {
+            case LETF_ST_VOL_TARGETING: if (TM_HAS(LETF_ST_VOL_TARGETING)) {
               R cv = s_v20_today;
               alloc = (isnan_(cv) || cv < (R)0.01) ? (R)1 : clipr(M::div_(st.p[0], cv), (R)0.2, (R)2.0);
               cashleg = false;
             } break;
-            case LETF_ST_ADAPTIVE_VOL: {
+            case LETF_ST_ADAPTIVE_VOL: if (TM_HAS(LETF_ST_ADAPTIVE_VOL)) {
               R cv = s_v20f, cs = s_sma200f;
               if (isnan_(cv) || isnan_(cs) || cv < (R)0.001) skip = true;
               else alloc = clipr(M::div_(P_prev > cs ? st.p[0] : st.p[1], cv), (R)0, (R)1);
             } break;
-            case LETF_ST_DOWNSIDE_VOL: {
+            case LETF_ST_DOWNSIDE_VOL: if (TM_HAS(LETF_ST_DOWNSIDE_VOL)) {
               R dv = s_dv20f;
               alloc = (isnan_(dv) || dv < (R)0.001) ? (R)1 : clipr(M::div_(st.p[0], dv), (R)0, (R)1.5);
             } break;
-            case LETF_ST_CONVEX_VOL: {
+            case LETF_ST_CONVEX_VOL: if (TM_HAS(LETF_ST_CONVEX_VOL)) {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
               R al = M::div_(st.p[0], v);
               if (P_prev > s_sma200) al = M::pow_(al, st.p[1]);
               alloc = clipr(al, (R)0, (R)1);
             } break;
-            case LETF_ST_VOL_VELOCITY: {
+            case LETF_ST_VOL_VELOCITY: if (TM_HAS(LETF_ST_VOL_VELOCITY)) {
               R ev = s_v5 > s_v20 ? s_v5 : s_v20;       // python max(vol_slow, vol_fast)
               if (isnan_(ev) || ev < (R)0.001) ev = (R)0.5;
               alloc = clipr(M::div_(st.p[0], ev), (R)0, (R)1);
             } break;
-            case LETF_ST_VOL_MOM: {
+            case LETF_ST_VOL_MOM: if (TM_HAS(LETF_ST_VOL_MOM)) {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
               R al = M::div_(st.p[0], v);
               if (!isnan_(s_vm) && s_vm < (R)-0.10) al *= (R)1.2;
               if (!isnan_(s_vm) && s_vm > (R)0.10) al *= (R)0.7;
               alloc = clipr(al, (R)0, (R)1);
             } break;
-            case LETF_ST_SKEW_CONVEX: {
+            case LETF_ST_SKEW_CONVEX: if (TM_HAS(LETF_ST_SKEW_CONVEX)) {
               R v = s_v20; if (isnan_(v) || v < (R)0.001) v = (R)0.5;
               R al = M::div_(st.p[0], v);
               if (!isnan_(s_sk) && s_sk > (R)0) al = M::pow_(al, (R)1.3);
               else if (!isnan_(s_sk) && s_sk < (R)-0.5) al *= (R)0.5;
               alloc = clipr(al, (R)0, (R)1);
             } break;
-            case LETF_ST_META_ENSEMBLE: {
+            case LETF_ST_META_ENSEMBLE: if (TM_HAS(LETF_ST_META_ENSEMBLE)) {
               R dv = s_dv20; if (isnan_(dv) || dv < (R)0.001) dv = (R)0.25;
               R al = M::div_(st.p[0], dv);
               if (P_prev > s_sma200) al = M::pow_(al, (R)1.2);
               if (s_v5 > (R)1.5 * s_v20) al *= (R)0.5;
               alloc = clipr(al, (R)0, (R)1);
             } break;
-            case LETF_ST_REGIME_ASYMMETRIC: {
+            case LETF_ST_REGIME_ASYMMETRIC: if (TM_HAS(LETF_ST_REGIME_ASYMMETRIC)) {
               R vr = M::div_(s_v5, s_v60);
               bool crisis = (vix > st.p[2]) || (vr > st.p[3]);
               R tv = crisis ? st.p[1] : st.p[0];
               alloc = (isnan_(s_v5) || s_v5 < (R)0.001) ? (R)0.5 : clipr(M::div_(tv, s_v5), (R)0, (R)1.2);
             } break;
-            case LETF_ST_SKEW_KELLY: {
+            case LETF_ST_SKEW_KELLY: if (TM_HAS(LETF_ST_SKEW_KELLY)) {
               R vol = s_v20, dv = s_dv20, sk = s_sk, mr = s_mean60;
               if (isnan_(vol) || vol < (R)0.001) vol = (R)0.25;
               if (isnan_(dv) || dv < (R)0.001) dv = vol * (R)0.6;
@@ -821,7 +891,7 @@ struct Trial {
               if (ev > (R)0.01) { ks = M::div_(mr - (R)0.03, ev * ev); ks = ks * st.p[3]; ks = clipr(ks, (R)0.2, (R)2.0); }
               alloc = clipr(M::div_(st.p[0], ev) * pen * M::div_(ks, (R)1.5), (R)0, (R)1.5);
             } break;
-            case LETF_ST_MOM_VOL_CONV: {
+            case LETF_ST_MOM_VOL_CONV: if (TM_HAS(LETF_ST_MOM_VOL_CONV)) {
               R mom = s_mom, vf = s_v10, vs = s_v60;
               if (isnan_(mom)) mom = 0;
               if (isnan_(vf) || vf < (R)0.001) vf = (R)0.30;
@@ -831,7 +901,7 @@ struct Trial {
               if (ratio < (R)0.8) { vm = (R)1.2; ev = vf; } else if (ratio > (R)1.3) { vm = (R)0.6; ev = vf; } else { vm = (R)1.0; ev = vs; }
               alloc = clipr(M::div_(st.p[0] * (mmul * vm), ev), (R)0, (R)1.5);
             } break;
-            case LETF_ST_CONVICTION: {
+            case LETF_ST_CONVICTION: if (TM_HAS(LETF_ST_CONVICTION)) {
               R mom = s_mom, dv = s_dv20, vf = s_v5, vs = s_v60;
               if (isnan_(mom)) mom = 0;
               if (isnan_(dv) || dv < (R)0.001) dv = (R)0.20;
@@ -847,7 +917,7 @@ struct Trial {
             } break;
             default: break;
           }
-          if (skip) { sl.dd.step(sl.W, (R)1); continue; }
+          if (skip) { sl.dd.step(sl.W, (R)1); return; }
           R prev_alloc = sl.aux;
           R turnover = M::abs_(alloc - prev_alloc), cost = 0;
           if (turnover > thresh) {
@@ -864,6 +934,13 @@ struct Trial {
         growth = (R)1 + r_strat;
         sl.W = sl.W * (1.0 + (double)r_strat);
         sl.dd.step(sl.W, growth);
+      };
+      if (HAS_ACTIVE && i >= 1) {         // active strategies leave equity[0] = W0
+        if (LIST != 0) for_typed_slots<LIST>(slot_body, std::make_integer_sequence<int, NS>{});
+        else {
+#pragma unroll(NS <= 8 ? NS : 1)
+          for (int s = 0; s < NS; s++) slot_body(s, std::integral_constant<int, -1>{});
+        }
       }
     }
 
@@ -882,6 +959,7 @@ struct Trial {
     }
     if (T == 0 || bad || !(vmin >= (R)5) || !(vmax <= (R)120)) flags |= LETF_FLAG_REPAIRED;
     const int64_t N = ka.out.n_trials;
+#pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++) {
       if (s >= p.n_strat) break;
       const int ty = p.strat[s].type;

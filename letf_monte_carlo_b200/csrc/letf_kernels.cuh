@@ -6,11 +6,11 @@
 
 namespace letf {
 
-template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int BLK, int MINB>
+template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int LIST, int AM, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_constant__ KArgs<R, NS, NA> ka) {
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (int64_t j = lane; j < ka.n_trials; j += ka.nthreads) {
-    Trial<R, NS, NA, MARKET, TAPEIO, TM> t(ka, ka.first_trial + j, j, lane);
+    Trial<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM> t(ka, ka.first_trial + j, j, lane);
     t.run();
   }
 }
@@ -23,6 +23,8 @@ struct KernelEntry {
   int market;         // LETF_MARKET_* (3 = caller-supplied series)
   int tapeio;         // 1: can read / record tapes and keeps the trade journal
   uint32_t tm;        // strategy types compiled in
+  int list;           // typed slot list (slot_list_type), 0 = dynamic dispatch
+  int am;             // compile-time asset mask, 0 = run time
   int block;          // threads per block
   const char* name;
   cudaError_t (*launch)(const void* kargs, int grid, cudaStream_t st);
@@ -34,25 +36,26 @@ void register_kernel(const KernelEntry& e);
 int kernel_count();
 const KernelEntry* kernel_at(int i);
 
-template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int BLK, int MINB>
+template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int LIST, int AM, int BLK, int MINB>
 struct KernelImpl {
   static cudaError_t launch(const void* kargs, int grid, cudaStream_t st) {
-    letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<R, NS, NA>*)kargs);
+    letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<R, NS, NA>*)kargs);
     return cudaGetLastError();
   }
   static cudaError_t attrs(cudaFuncAttributes* a, int* mb) {
-    cudaError_t e = cudaFuncGetAttributes(a, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, BLK, MINB>);
+    cudaError_t e = cudaFuncGetAttributes(a, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, BLK, MINB>, BLK, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>, BLK, 0);
   }
 };
 
-#define LETF_INSTANTIATE(ID, R, PREC, NS, NA, MARKET, TAPEIO, TM, BLK, MINB)                             \
+#define LETF_INSTANTIATE(ID, R, PREC, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB)                   \
   namespace {                                                                                            \
   struct Reg_##ID {                                                                                      \
     Reg_##ID() {                                                                                         \
-      typedef letf::KernelImpl<R, NS, NA, MARKET, TAPEIO, TM, BLK, MINB> K;                              \
-      letf::KernelEntry e = {PREC, NS, NA, MARKET, TAPEIO ? 1 : 0, TM, BLK, #ID, &K::launch, &K::attrs,  \
+      typedef letf::KernelImpl<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB> K;                    \
+      letf::KernelEntry e = {PREC, NS, NA, MARKET, TAPEIO ? 1 : 0, TM, LIST, AM, BLK, #ID, &K::launch,   \
+                             &K::attrs,                                                                  \
                              sizeof(letf::KArgs<R, NS, NA>)};                                                \
       letf::register_kernel(e);                                                                          \
     }                                                                                                    \

@@ -114,7 +114,8 @@ template <> struct Mth<float> {
   static LETF_HD float neg2log_(float x) { return -1.3862943611198906f * log2_(x); }   // -2 ln x, one multiply
   static LETF_HD float tanh_(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   static LETF_HD float pow_(float x, float y) { return __powf(x, y); }
-  static LETF_HD float div_(float a, float b) { return __fdividef(a, b); }
+  // a / b as one MUFU.RCP and one multiply (div.approx carries a range fix-up we do not need: |b| << 2^126 here)
+  static LETF_HD float div_(float a, float b) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return a * r; }
 #else
   static LETF_HD float sqrt_(float x) { return ::sqrtf(x); }
   static LETF_HD float rsqrt_(float x) { return 1.0f / ::sqrtf(x); }
@@ -214,7 +215,7 @@ LETF_HD R chi2_int_fast(int k, uint32_t wa, uint32_t wb, R nrm) {
 // Marsaglia-Tsang gamma(shape a >= 1) * 2 = chi2(2a).  First attempt uses (n0, u0) supplied by the
 // caller's block; retries pull blocks (stream, sub = 1, 2, ...).
 template <typename R>
-LETF_HD R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+LETF_HDN R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
   R a = (R)0.5 * nu;
   R d = a - (R)(1.0 / 3.0);

@@ -27,7 +27,7 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
   ka.tape_first = 0;
   ka.rng_mode = rng_mode;
   const int G = sp->sim_days + sp->buffer_days;
-  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 3), rp(kRingP), rs(kRingS), ra(kRingA);
+  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 4 + 4), rp(kRingP), rs(kRingS), ra(kRingA);
   ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
   ka.nthreads = 1;
   ka.log_trial = log_trial; ka.log_strategy = log_strategy; ka.log_cap = log_cap;
@@ -75,6 +75,35 @@ extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, u
     t.run();
   }
   return 0;
+}
+
+// typed-slot builds (one compile-time rule per slot, compile-time asset mask), Philox only, fp32
+template <int NS, int LIST, int AM>
+static int run_typed(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
+  constexpr int NA = kAssets;
+  if (sp->n_strategies != slot_list_count(LIST) || sp->asset_mask != AM || sp->market_mode != LETF_MARKET_JOINT_T) return -2;
+  for (int s = 0; s < sp->n_strategies; s++) if (sp->strategies[s].type != slot_list_type(LIST, s)) return -3;
+  static KArgs<float, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
+  convert_params<float, NS, NA>(*sp, dd, ka.p);
+  ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
+  ka.log_trial = -1;
+  const int G = sp->sim_days + sp->buffer_days;
+  std::vector<float> xscr((size_t)(G > 0 ? G : 1) * 4 + 4), rp(kRingP), rs(kRingS), ra(kRingA);
+  ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
+  for (int64_t j = 0; j < n; j++) {
+    Trial<float, NS, NA, LETF_MARKET_JOINT_T, false, slot_list_mask(LIST), LIST, AM> t(ka, first + j, j, 0);
+    t.run();
+  }
+  return 0;
+}
+extern "C" int letf_emu_run_typed(const LetfParams* sp, int list, const LetfOutputs* out, uint64_t seed, int64_t first,
+                                  int64_t n) {
+  if (validate_params(*sp)) return -1;
+  if (list == 1) return run_typed<8, 1, 25>(sp, out, seed, first, n);
+  if (list == 2) return run_typed<32, 2, 29>(sp, out, seed, first, n);
+  return -4;
 }
 
 extern "C" const char* letf_emu_validate(const LetfParams* sp) { return validate_params(*sp); }

@@ -40,6 +40,8 @@ def lib():
         L.letf_emu_run_lean.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64,
                                         C.POINTER(C.c_int)]
         L.letf_emu_run_lean.restype = C.c_int
+        L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
+        L.letf_emu_run_typed.restype = C.c_int
         L.letf_emu_validate.argtypes = [C.POINTER(abi.Params)]
         L.letf_emu_validate.restype = C.c_char_p
         _lib = L
@@ -74,3 +76,12 @@ def run_lean(params, n, seed=0, first=0):
     if rc != 0:
         raise RuntimeError(f"emu lean rc={rc}")
     return out, bool(fast.value)
+
+
+def run_typed(params, slot_list, n, seed=0, first=0):
+    """typed-slot build (csrc slot_list_type): 1 = config-4 sweep, 2 = the default 19-strategy sweep"""
+    out = HostOutputs(params.n_strategies, n)
+    rc = lib().letf_emu_run_typed(C.byref(params), slot_list, C.byref(out.as_struct()), seed, first, n)
+    if rc != 0:
+        raise RuntimeError(f"emu typed rc={rc}")
+    return out

@@ -374,3 +374,29 @@ def test_philox_distribution_matches_live_reference(precision, engine_lib):
     with _engine(params, keep, precision) as eng:
         out = eng.run_host(40000, seed=2718)
     assert_same_distribution(ref, out, sids)
+
+
+@pytest.mark.parametrize("sids", [["S1", "S2", "S4", "S5", "S6", "S19"], ALL19], ids=["c4_list", "sweep19_list"])
+def test_typed_slot_kernels_vs_generic_and_oracle(sids, engine_lib):
+    """The typed-slot builds (one compile-time rule per slot; BASELINE config 4 and the reference's default
+    19-strategy sweep) against the generic fp32 build recording the same Philox counters, and the oracle
+    replaying that tape."""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    n_t = 128
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    with _engine(params, keep, "f32") as eng:
+        typed = eng.run_host(2 * n_t, seed=99)
+        regs_typed = eng.launch_info()["regs_per_thread"]
+        gen = eng.run_host(2 * n_t, seed=99, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+    o = orc.run(params, rec)
+    # same source expressions, different instantiation: fp32 contraction differences only
+    np.testing.assert_allclose(typed.final_wealth, gen.final_wealth, rtol=2e-3)
+    assert np.mean(typed.num_trades != gen.num_trades) < 0.01
+    np.testing.assert_array_equal(typed.regime_days, gen.regime_days)
+    np.testing.assert_array_equal(typed.start_offset, o.start_offset)
+    # fp32 signals vs the fp64 oracle on identical shocks: wealth within 1 % except the skew-driven rules
+    rel = np.abs(typed.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
+    assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97, (np.median(rel), np.mean(rel < 1e-2))
+    assert np.mean(typed.num_trades != o.num_trades) < 0.03
+    assert regs_typed > 0

@@ -186,3 +186,19 @@ def test_philox_distribution_matches_live_reference():
     dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
     out = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=11, n=8000)
     assert_same_distribution(ref, out, sids)
+
+
+@pytest.mark.parametrize("slot_list,sids", [(1, ["S1", "S2", "S4", "S5", "S6", "S19"]), (2, ALL19)])
+def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
+    """one compile-time rule per slot + compile-time asset mask (the c4 and default-sweep builds) must
+    compute exactly what the dynamically dispatched generic build computes on the same Philox counters"""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    typed = emu.run_typed(params, slot_list, 48, seed=5)
+    gen = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=5, n=48)
+    np.testing.assert_array_equal(typed.final_wealth, gen.final_wealth)
+    np.testing.assert_array_equal(typed.max_dd, gen.max_dd)
+    np.testing.assert_array_equal(typed.num_trades, gen.num_trades)
+    np.testing.assert_array_equal(typed.flags, gen.flags)
+    np.testing.assert_array_equal(typed.regime_days, gen.regime_days)
