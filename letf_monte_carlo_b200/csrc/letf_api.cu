@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <new>
 #include <string>
@@ -108,6 +109,9 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
       for (int s = 0; same && s < n_strat; s++) same = slot_list_type(k->list, s) == e->params.strategies[s].type;
       if (!same) continue;
     }
+    // tuning aid: LETF_KERNEL=<instantiation name> pins an eligible build
+    const char* pin = getenv("LETF_KERNEL");
+    if (pin && *pin && !strcmp(pin, k->name)) return k;
     if (!best) { best = k; continue; }
     // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
     // typed-slot builds first, then fewer slots / series / rules, no tape plumbing

@@ -106,6 +106,15 @@ LETF_HD void for_typed_slots(F& f, std::integer_sequence<int, S...>) {
   (f(S, std::integral_constant<int, slot_list_type(LIST, S)>{}), ...);
 }
 
+// v[a] for a run-time asset index without forcing the array into local memory: a select chain
+// (in the unrolled builds `a` is loop-invariant and uniform, so this is a handful of predicated moves)
+template <typename R> LETF_HD R pick6(const R (&v)[LETF_N_ASSETS], int a) {
+  R r = v[0];
+#pragma unroll
+  for (int j = 1; j < LETF_N_ASSETS; j++) r = a == j ? v[j] : r;
+  return r;
+}
+
 #define TM_HAS(t) ((TM >> (t)) & 1u)
 constexpr int kMarketSeries = 3;
 constexpr uint32_t kVolTypes = (1u << LETF_ST_VOL_TARGETING) | (1u << LETF_ST_ADAPTIVE_VOL) | (1u << LETF_ST_DOWNSIDE_VOL) |
@@ -360,6 +369,7 @@ struct Trial {
     Drawdown<R> dd;
     R aux;                  // prev_alloc | position | composite state
     int trades;
+    R pv[kAssets];          // portfolio rule: dollar position per asset (strategy.py:155-241); unused elsewhere
   };
   struct SlotJ { double pos[3]; double vol; int cnt; };
 
@@ -465,7 +475,6 @@ struct Trial {
 
     Slot slot[NS];
     SlotJ sj[JOURNAL ? NS : 1];
-    R pv[kPortMax][kAssets];
 #pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++) { slot[s].W = (double)p.W0; slot[s].dd.init((double)p.W0); slot[s].aux = 0; slot[s].trades = 0; }
     if (JOURNAL) {
@@ -475,7 +484,7 @@ struct Trial {
 #pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++)
       if (TM_HAS(LETF_ST_PORTFOLIO) && s < p.n_strat && p.strat[s].type == LETF_ST_PORTFOLIO)
-        for (int a = 0; a < kAssets; a++) pv[p.strat[s].port][a] = p.W0 * p.strat[s].w[a];
+        for (int a = 0; a < kAssets; a++) slot[s].pv[a] = p.W0 * p.strat[s].w[a];
     Signals sg;
     sg.sma200.init(); sg.sma100.init(); sg.gain14.init(); sg.loss14.init(); sg.mom126.init(); sg.mean60.init();
     sg.v5.init(); sg.v10.init(); sg.v20.init(); sg.v60.init(); sg.dv20.init(); sg.sk60.init();
@@ -496,9 +505,31 @@ struct Trial {
     }
 
     // ---- the simulated window
+    // software prefetch: the scratch vector of day g + 1 and the ring entries this day retires are requested at the
+    // top of the day, a whole day step ahead of their use (the loads are otherwise a fully exposed L2 round trip)
+    X4 vnext; vnext.x = vnext.y = vnext.z = vnext.w = (R)0;
+    if (two_pass && T > 0) vnext = xs[so];
     for (int i = 0; i < T; i++) {
       const int g = so + i;
       const int64_t sn = ka.series.n_paths;
+      const X4 vcur = vnext;
+      if (two_pass && i + 1 < T) vnext = xs[g + 1];
+      R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0;
+      if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
+        if (NEED_RINGP) {
+          const R* ring = ka.ringP + lane;
+          if (HAS_SMA200 && i >= 200) pf_p200 = ring[(int64_t)sg.cP * nth];
+          if (HAS_SMA100 && i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; pf_p100 = ring[(int64_t)c * nth]; }
+        }
+        if (NEED_RINGS && i >= 126) pf_s126 = (ka.ringS + lane)[(int64_t)sg.cS * nth];
+        if (NEED_RINGA) {
+          const R* ring = ka.ringA + lane;
+          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) pf_r60 = ring[(int64_t)sg.cA * nth];
+          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; pf_r20 = ring[(int64_t)c * nth]; }
+          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; pf_r10 = ring[(int64_t)c * nth]; }
+          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; pf_r5 = ring[(int64_t)c * nth]; }
+        }
+      }
       const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
       if (MARKET == kMarketSeries) {
@@ -506,8 +537,7 @@ struct Trial {
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
       } else if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
-        const X4 v = xs[g];
-        x[0] = v.x + shift[0]; x[1] = v.y + shift[1]; x[2] = v.z + shift[2];
+        x[0] = vcur.x + shift[0]; x[1] = vcur.y + shift[1]; x[2] = vcur.z + shift[2];
       } else {
         market_day<true, true, FAST>(g, reg, js, x, vn, in);
       }
@@ -681,7 +711,7 @@ struct Trial {
       R s_v5 = nan_<R>(), s_v10 = nan_<R>(), s_v20 = nan_<R>(), s_v20f = nan_<R>(), s_v60 = nan_<R>();
       R s_dv20 = nan_<R>(), s_dv20f = nan_<R>(), s_sk = nan_<R>(), s_mean60 = nan_<R>(), s_vm = nan_<R>(), s_v20_today = nan_<R>();
       const R P_prev = sg.P_prev, vix_prev = sg.vix_prev;
-      const R ra = ret[p.sig_asset];
+      const R ra = pick6(ret, p.sig_asset);
       if (i >= 1) {
         if (HAS_SMA200) { s_sma200 = sg.sma200.mean(1); s_sma200f = sg.sma200.mean(200); }
         if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
@@ -708,8 +738,8 @@ struct Trial {
       // roll forward (pandas: removals first, then the new observation)
       if (NEED_RINGP) {
         R* ring = ka.ringP + lane;
-        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(ring[(int64_t)sg.cP * nth]); sg.sma200.add(Pspy); }
-        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(ring[(int64_t)c * nth]); } sg.sma100.add(Pspy); }
+        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(EXACT ? ring[(int64_t)sg.cP * nth] : pf_p200); sg.sma200.add(Pspy); }
+        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(EXACT ? ring[(int64_t)c * nth] : pf_p100); } sg.sma100.add(Pspy); }
         if (HAS_RSI) {
           if (i >= 14) {
             R dg = 0, dl = -(R)0;
@@ -731,18 +761,20 @@ struct Trial {
       }
       if (NEED_RINGS) {
         R* ring = ka.ringS + lane;
-        if (i >= 126) sg.mom126.remove(ring[(int64_t)sg.cS * nth]);
+        if (i >= 126) sg.mom126.remove(EXACT ? ring[(int64_t)sg.cS * nth] : pf_s126);
         sg.mom126.add(ret[4]);
         ring[(int64_t)sg.cS * nth] = ret[4];
         sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
       }
       if (NEED_RINGA) {
         R* ring = ka.ringA + lane;
-        R r60 = 0, r20 = 0, r10 = 0, r5 = 0;
-        if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[(int64_t)sg.cA * nth];
-        if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[(int64_t)c * nth]; }
-        if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[(int64_t)c * nth]; }
-        if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[(int64_t)c * nth]; }
+        R r60 = pf_r60, r20 = pf_r20, r10 = pf_r10, r5 = pf_r5;
+        if (EXACT) {
+          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[(int64_t)sg.cA * nth];
+          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[(int64_t)c * nth]; }
+          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[(int64_t)c * nth]; }
+          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[(int64_t)c * nth]; }
+        }
         if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar(sg.v5, ring, sg.cA, 5, false); sg.v5.add(ra); }
         if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar(sg.v10, ring, sg.cA, 10, false); sg.v10.add(ra); }
         if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar(sg.v20, ring, sg.cA, 20, false); sg.v20.add(ra); }
@@ -772,15 +804,15 @@ struct Trial {
           R thr = ty == LETF_ST_SMA ? s_sma200 : s_sma200 * ((R)1 - st.p[1]);
           bool buy = P_prev >= thr, sell = P_prev < thr;
           int pos_prev = (int)sl.aux, pos = pos_prev == 0 ? (buy ? 1 : 0) : (sell ? 0 : 1);
-          r_strat = pos == 1 ? ret[st.asset] : cash;
+          r_strat = pos == 1 ? pick6(ret, st.asset) : cash;
           if (pos != pos_prev) {
             sl.trades++;
-            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * p.assets[st.asset].lev * M::abs_(ret[st.asset]) + (R)0;
+            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * p.assets[st.asset].lev * M::abs_(pick6(ret, st.asset)) + (R)0;
           }
           sl.aux = (R)pos;
         }
         if (TM_HAS(LETF_ST_PORTFOLIO)) if (ty == LETF_ST_PORTFOLIO) {
-          R* pvv = pv[st.port];
+          R* pvv = sl.pv;
           R total = 0;
           for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = pvv[a] * ((R)1 + ret[a]); total += pvv[a]; }
           double w_new = (double)total;
@@ -808,7 +840,7 @@ struct Trial {
         if (TM_HAS(LETF_ST_COMPOSITE)) if (ty == LETF_ST_COMPOSITE) {
           int score = (P_prev > s_sma200f ? 1 : 0) + (((R)40 < s_rsi && s_rsi < (R)80) ? 1 : 0) + (vix_prev < st.p[2] ? 1 : 0);
           int target = score == 3 ? 2 : (score == 2 ? 1 : 0);
-          r_strat = target == 2 ? ret[st.asset] : (target == 1 ? ret[st.asset2] : cash);
+          r_strat = target == 2 ? pick6(ret, st.asset) : (target == 1 ? pick6(ret, st.asset2) : cash);
           if (target != (int)sl.aux) {
             sl.trades++;
             if (JOURNAL && st.taxable) {
@@ -928,7 +960,7 @@ struct Trial {
           } else {
             if (sticky) alloc = prev_alloc; else sl.aux = alloc;
           }
-          r_strat = cashleg ? (alloc * ret[st.asset]) + (((R)1 - alloc) * cash) : ret[st.asset] * alloc;
+          r_strat = cashleg ? (alloc * pick6(ret, st.asset)) + (((R)1 - alloc) * cash) : pick6(ret, st.asset) * alloc;
           if (p.apply_costs) r_strat -= cost;
         }
         growth = (R)1 + r_strat;

@@ -88,7 +88,7 @@ inline const char* validate_params(const LetfParams& s) {
     switch (q.type) {
       case LETF_ST_BENCHMARK: case LETF_ST_BENCHMARK_TLT: break;
       case LETF_ST_SMA: case LETF_ST_SMA_BAND: if (!is(0, 200)) return "sma_period must be 200"; break;
-      case LETF_ST_PORTFOLIO: if (++nport > kPortMax) return "too many portfolio strategies"; if (p[0] < 1) return "rebalance_freq < 1"; break;
+      case LETF_ST_PORTFOLIO: ++nport; if (p[0] < 1) return "rebalance_freq < 1"; break;
       case LETF_ST_VOL_TARGETING: if (!is(1, 20)) return "vol_targeting lookback must be 20"; break;
       case LETF_ST_COMPOSITE: if (!is(0, 200) || !is(1, 14)) return "composite windows must be 200/14"; break;
       case LETF_ST_ADAPTIVE_VOL: if (!is(2, 20) || !is(3, 200)) return "adaptive_vol windows must be 20/200"; break;
