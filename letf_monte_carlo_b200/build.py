@@ -59,11 +59,16 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
         results = list(ex.map(lambda s: _compile(s, force), srcs))
     objs = [o for o, _ in results]
     rebuilt = any(c for _, c in results)
-    if rebuilt or force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+    manifest = os.path.join(OBJ, "link.manifest")
+    want = "\n".join(sorted(os.path.basename(o) for o in objs))
+    have = open(manifest).read() if os.path.exists(manifest) else ""
+    if rebuilt or force or want != have or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        with open(manifest, "w") as f:
+            f.write(want)
     if verbose:
         print(f"built {LIB} from {len(objs)} objects ({sum(c for _, c in results)} recompiled)", file=sys.stderr)
     return LIB
