@@ -106,7 +106,12 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (k->am && k->am != e->params.asset_mask) continue;
     if (k->list) {      // typed slots: the strategy list must be exactly the one compiled in
       bool same = slot_list_count(k->list) == n_strat;
-      for (int s = 0; same && s < n_strat; s++) same = slot_list_type(k->list, s) == e->params.strategies[s].type;
+      for (int s = 0; same && s < n_strat; s++) {
+        same = slot_list_type(k->list, s) == e->params.strategies[s].type;
+        const int as = slot_list_asset(k->list, s);
+        if (same && as >= 0) same = e->params.strategies[s].asset == as;
+        if (same && e->params.strategies[s].type == LETF_ST_COMPOSITE) same = e->params.strategies[s].asset2 == 4;
+      }
       if (!same) continue;
     }
     // tuning aid: LETF_KERNEL=<instantiation name> pins an eligible build
@@ -139,6 +144,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   int64_t grid = (per_wave + kBlock - 1) / kBlock;
   if (grid < 1) grid = 1;
   const int64_t nthreads = grid * kBlock;
+  if ((int64_t)kRingP * nthreads >= ((int64_t)1 << 32)) return fail(LETF_ERR_INVALID, "grid too large for 32-bit ring offsets");
 
   static thread_local KArgs<R, NS, NA> ka;
   memset(&ka, 0, sizeof(ka));

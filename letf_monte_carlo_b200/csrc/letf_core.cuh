@@ -91,6 +91,12 @@ LETF_HD constexpr int slot_list_type(int list, int s) {
   }
   return -1;
 }
+// every rule of the typed lists trades TQQQ (S8's defensive leg: SPY), cfg.STRATEGIES (config.py:348-437);
+// buy & hold slots read their asset at run time (they do no per-day work)
+LETF_HD constexpr int slot_list_asset(int list, int s) {
+  const int t = slot_list_type(list, s);
+  return (list != 0 && t >= 0 && t != LETF_ST_BENCHMARK && t != LETF_ST_BENCHMARK_TLT && t != LETF_ST_PORTFOLIO) ? 0 : -1;
+}
 LETF_HD constexpr int slot_list_count(int list) {
   int n = 0;
   for (int s = 0; s < LETF_MAX_STRATEGIES; s++) if (slot_list_type(list, s) >= 0) n = s + 1;
@@ -103,7 +109,7 @@ LETF_HD constexpr uint32_t slot_list_mask(int list) {
 }
 template <int LIST, typename F, int... S>
 LETF_HD void for_typed_slots(F& f, std::integer_sequence<int, S...>) {
-  (f(S, std::integral_constant<int, slot_list_type(LIST, S)>{}), ...);
+  (f(S, std::integral_constant<int, slot_list_type(LIST, S)>{}, std::integral_constant<int, slot_list_asset(LIST, S)>{}), ...);
 }
 
 // v[a] for a run-time asset index without forcing the array into local memory: a select chain
@@ -416,6 +422,8 @@ struct Trial {
   template <bool FAST> LETF_HD void run_t() {
     const int G = p.T + p.buffer;
     const int64_t nth = ka.nthreads;
+    const uint32_t nth32 = (uint32_t)ka.nthreads;             // ring rows: depth * nthreads < 2^32 elements (checked by the host)
+    auto roff = [nth32](int c) { return (uint32_t)c * nth32; };
     const R V = (R)15.874507866387544;   // sqrt(252)
 
     // ---- start offset (random_start.py:33-57)
@@ -518,16 +526,16 @@ struct Trial {
       if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
         if (NEED_RINGP) {
           const R* ring = ka.ringP + lane;
-          if (HAS_SMA200 && i >= 200) pf_p200 = ring[(int64_t)sg.cP * nth];
-          if (HAS_SMA100 && i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; pf_p100 = ring[(int64_t)c * nth]; }
+          if (HAS_SMA200 && i >= 200) pf_p200 = ring[roff(sg.cP)];
+          if (HAS_SMA100 && i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; pf_p100 = ring[roff(c)]; }
         }
-        if (NEED_RINGS && i >= 126) pf_s126 = (ka.ringS + lane)[(int64_t)sg.cS * nth];
+        if (NEED_RINGS && i >= 126) pf_s126 = (ka.ringS + lane)[roff(sg.cS)];
         if (NEED_RINGA) {
           const R* ring = ka.ringA + lane;
-          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) pf_r60 = ring[(int64_t)sg.cA * nth];
-          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; pf_r20 = ring[(int64_t)c * nth]; }
-          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; pf_r10 = ring[(int64_t)c * nth]; }
-          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; pf_r5 = ring[(int64_t)c * nth]; }
+          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) pf_r60 = ring[roff(sg.cA)];
+          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; pf_r20 = ring[roff(c)]; }
+          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; pf_r10 = ring[roff(c)]; }
+          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; pf_r5 = ring[roff(c)]; }
         }
       }
       const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
@@ -544,8 +552,8 @@ struct Trial {
       R rf = p.const_rf;
       if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
         vix = vix_step(g, reg, vix, x[0], vn);
-        R irx = clipr(p.irx_base[reg] + ((R)0 + (R)0.5 * in), (R)0, (R)15);   // engine.py:117-123
-        rf = EXACT ? clipr(irx, (R)0, (R)20) / (R)100 : clipr(irx, (R)0, (R)20) * (R)0.01;                                // engine.py:516
+        R irx = clipx(p.irx_base[reg] + ((R)0 + (R)0.5 * in), (R)0, (R)15);   // engine.py:117-123
+        rf = EXACT ? clipx(irx, (R)0, (R)20) / (R)100 : clipx(irx, (R)0, (R)20) * (R)0.01;                                // engine.py:516
       }
       R spy = x[0], qqq = x[1], tlt = x[2];
       if (EXACT) {
@@ -577,10 +585,10 @@ struct Trial {
             sign = (b.w & 1u) ? (R)1 : (R)-1;
             if (rec) { tp_put(ka.tape.liq_n, i, ln); tp_put(ka.tape.cred_n, i, cn); tp_put(ka.tape.jump_u, i, ju); tp_put(ka.tape.sign, i, sign); }
           }
-          liq = clipr(sp.liq_mu + sp.liq_phi * (liq - sp.liq_mu) + ((R)0 + sp.liq_sigma * ln), (R)0, (R)3);
-          cred = clipr(sp.cr_mu + sp.cr_phi * (cred - sp.cr_mu) + ((R)0 + sp.cr_sigma * cn), (R)0, (R)3);
+          liq = clipx(sp.liq_mu + sp.liq_phi * (liq - sp.liq_mu) + ((R)0 + sp.liq_sigma * ln), (R)0, (R)3);
+          cred = clipx(sp.cr_mu + sp.cr_phi * (cred - sp.cr_mu) + ((R)0 + sp.cr_sigma * cn), (R)0, (R)3);
           R vamp = rmax(EXACT ? (vix - (R)25) / (R)30 : (vix - (R)25) * (R)(1.0 / 30.0), (R)0);
-          R jp = clipr(sp.jbase + (R)0.008 * vamp + (R)0.003 * liq, (R)0, (R)0.01);
+          R jp = clipx(sp.jbase + (R)0.008 * vamp + (R)0.003 * liq, (R)0, (R)0.01);
           if (ju < jp || rec) {
             // record mode draws the jump size every day: antithetic twins share a tape column but
             // may jump on different days, so the column must hold the variate either twin would use
@@ -606,15 +614,15 @@ struct Trial {
       R spread_common = 0;
       if (!FAST && MARKET != kMarketSeries && p.has_funding) {
         R irx_level = rf * (R)100;
-        R term = p.has_stress ? (R)1.25 - (R)1.1 * clipr(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
+        R term = p.has_stress ? (R)1.25 - (R)1.1 * clipx(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
         R tnx = irx_level + term;
         R sv = rmax(vix - (R)20, (R)0);
         R inv = rmax(-(tnx - irx_level), (R)0);
         R spd = p.f_base + p.f_vix * sv + p.f_inv * inv;
-        if (p.has_stress) spd += p.f_liq * clipr(liq, (R)0, (R)3) + p.f_cr * clipr(cred, (R)0, (R)3);
-        spread_common = clipr(spd, p.f_min, p.f_max);
+        if (p.has_stress) spd += p.f_liq * clipx(liq, (R)0, (R)3) + p.f_cr * clipx(cred, (R)0, (R)3);
+        spread_common = clipx(spd, p.f_min, p.f_max);
       }
-      const R vmult = clipr(M::sqrt_(EXACT ? vix / (R)20 : vix * (R)0.05), (R)0.5, (R)1.5);
+      const R vmult = clipx(M::sqrt_(EXACT ? vix / (R)20 : vix * (R)0.05), (R)0.5, (R)1.5);
       const R rmult = reg == 0 ? (R)1 : (R)1.15;
       const R vrmult = vmult * rmult;
       // FAST: day 0 carries no tracking error (engine.py:184 starts at i = 1); te_prev is 0 there, so zeroing the
@@ -711,7 +719,7 @@ struct Trial {
       R s_v5 = nan_<R>(), s_v10 = nan_<R>(), s_v20 = nan_<R>(), s_v20f = nan_<R>(), s_v60 = nan_<R>();
       R s_dv20 = nan_<R>(), s_dv20f = nan_<R>(), s_sk = nan_<R>(), s_mean60 = nan_<R>(), s_vm = nan_<R>(), s_v20_today = nan_<R>();
       const R P_prev = sg.P_prev, vix_prev = sg.vix_prev;
-      const R ra = pick6(ret, p.sig_asset);
+      const R ra = LIST != 0 ? ret[0] : pick6(ret, p.sig_asset);
       if (i >= 1) {
         if (HAS_SMA200) { s_sma200 = sg.sma200.mean(1); s_sma200f = sg.sma200.mean(200); }
         if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
@@ -738,15 +746,15 @@ struct Trial {
       // roll forward (pandas: removals first, then the new observation)
       if (NEED_RINGP) {
         R* ring = ka.ringP + lane;
-        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(EXACT ? ring[(int64_t)sg.cP * nth] : pf_p200); sg.sma200.add(Pspy); }
-        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(EXACT ? ring[(int64_t)c * nth] : pf_p100); } sg.sma100.add(Pspy); }
+        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(EXACT ? ring[roff(sg.cP)] : pf_p200); sg.sma200.add(Pspy); }
+        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(EXACT ? ring[roff(c)] : pf_p100); } sg.sma100.add(Pspy); }
         if (HAS_RSI) {
           if (i >= 14) {
             R dg = 0, dl = -(R)0;
             if (i >= 15) {
               int c1 = sg.cP - 14; if (c1 < 0) c1 += kRingP;
               int c2 = sg.cP - 15; if (c2 < 0) c2 += kRingP;
-              R dlt = ring[(int64_t)c1 * nth] - ring[(int64_t)c2 * nth];
+              R dlt = ring[roff(c1)] - ring[roff(c2)];
               dg = dlt > (R)0 ? dlt : (R)0;
               dl = -(dlt < (R)0 ? dlt : (R)0);
             }
@@ -756,24 +764,24 @@ struct Trial {
           sg.gain14.add(dlt > (R)0 ? dlt : (R)0);
           sg.loss14.add(-(dlt < (R)0 ? dlt : (R)0));
         }
-        ring[(int64_t)sg.cP * nth] = Pspy;
+        ring[roff(sg.cP)] = Pspy;
         sg.cP = sg.cP + 1 == kRingP ? 0 : sg.cP + 1;
       }
       if (NEED_RINGS) {
         R* ring = ka.ringS + lane;
-        if (i >= 126) sg.mom126.remove(EXACT ? ring[(int64_t)sg.cS * nth] : pf_s126);
+        if (i >= 126) sg.mom126.remove(EXACT ? ring[roff(sg.cS)] : pf_s126);
         sg.mom126.add(ret[4]);
-        ring[(int64_t)sg.cS * nth] = ret[4];
+        ring[roff(sg.cS)] = ret[4];
         sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
       }
       if (NEED_RINGA) {
         R* ring = ka.ringA + lane;
         R r60 = pf_r60, r20 = pf_r20, r10 = pf_r10, r5 = pf_r5;
         if (EXACT) {
-          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[(int64_t)sg.cA * nth];
-          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[(int64_t)c * nth]; }
-          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[(int64_t)c * nth]; }
-          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[(int64_t)c * nth]; }
+          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[roff(sg.cA)];
+          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[roff(c)]; }
+          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[roff(c)]; }
+          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[roff(c)]; }
         }
         if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar(sg.v5, ring, sg.cA, 5, false); sg.v5.add(ra); }
         if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar(sg.v10, ring, sg.cA, 10, false); sg.v10.add(ra); }
@@ -782,7 +790,7 @@ struct Trial {
         if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar(sg.dv20, ring, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
         if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
         if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
-        ring[(int64_t)sg.cA * nth] = ra;
+        ring[roff(sg.cA)] = ra;
         sg.cA = sg.cA + 1 == kRingA ? 0 : sg.cA + 1;
         if (TM_HAS(LETF_ST_VOL_TARGETING)) s_v20_today = sg.v20.stdev(20) * V;   // strategy.py:255 (unshifted)
       }
@@ -790,13 +798,16 @@ struct Trial {
 
       // ---- strategy rules (strategy.py:55-1277) + running statistics (engine.py:578-590)
       // (buy & hold needs no slot work: its equity is W0 * cp[asset], tracked above)
-      auto slot_body = [&](const int s, auto tyc_) {
+      auto slot_body = [&](const int s, auto tyc_, auto asc_) {
         constexpr int TYC = decltype(tyc_)::value;      // this slot's compile-time rule (typed lists), -1 = dynamic, -2 = empty
+        constexpr int ASC = decltype(asc_)::value;      // its compile-time traded asset, -1 = read p.strat[s].asset
         if (TYC == -2 || TYC == LETF_ST_BENCHMARK || TYC == LETF_ST_BENCHMARK_TLT) return;
         if (TYC < 0 && s >= p.n_strat) return;
         const DevStrategy<R>& st = p.strat[s];
         Slot& sl = slot[s];
         const int ty = TYC >= 0 ? TYC : st.type;
+        const R r_asset = ASC >= 0 ? ret[ASC >= 0 ? ASC : 0] : pick6(ret, st.asset);     // return of the traded asset
+        const R lev_asset = ASC >= 0 ? p.assets[ASC >= 0 ? ASC : 0].lev : p.assets[st.asset].lev;
         R growth = (R)1;          // W_i / W_{i-1}
         if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) return;
         R r_strat = 0;
@@ -804,21 +815,26 @@ struct Trial {
           R thr = ty == LETF_ST_SMA ? s_sma200 : s_sma200 * ((R)1 - st.p[1]);
           bool buy = P_prev >= thr, sell = P_prev < thr;
           int pos_prev = (int)sl.aux, pos = pos_prev == 0 ? (buy ? 1 : 0) : (sell ? 0 : 1);
-          r_strat = pos == 1 ? pick6(ret, st.asset) : cash;
+          r_strat = pos == 1 ? r_asset : cash;
           if (pos != pos_prev) {
             sl.trades++;
-            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * p.assets[st.asset].lev * M::abs_(pick6(ret, st.asset)) + (R)0;
+            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * lev_asset * M::abs_(r_asset) + (R)0;
           }
           sl.aux = (R)pos;
         }
         if (TM_HAS(LETF_ST_PORTFOLIO)) if (ty == LETF_ST_PORTFOLIO) {
           R* pvv = sl.pv;
           R total = 0;
-          for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = pvv[a] * ((R)1 + ret[a]); total += pvv[a]; }
+#define LETF_PORT_ASSET(a) ((AM == 0 || ((AM >> (a)) & 1)) && st.w[a] != (R)0)
+          for (int a = 0; a < kAssets; a++) if (LETF_PORT_ASSET(a)) { pvv[a] = pvv[a] * ((R)1 + ret[a]); total += pvv[a]; }
           double w_new = (double)total;
-          if (i % (int)st.p[0] == 0) {
+          // i % rebalance_freq == 0 (strategy.py:182) as a countdown kept in the slot's spare field
+          sl.aux += (R)1;
+          const bool rebalance = sl.aux >= st.p[0];
+          if (rebalance) sl.aux = (R)0;
+          if (rebalance) {
             R wt = 0, lt = 0;
-            for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) {
+            for (int a = 0; a < kAssets; a++) if (LETF_PORT_ASSET(a)) {
               R cw = M::div_(pvv[a], total);
               wt += M::abs_(cw - st.w[a]);
               R tl = p.assets[a].lev, emb = (R)1;
@@ -830,8 +846,9 @@ struct Trial {
             }
             R turn = wt + lt;
             if (p.apply_costs && turn > (R)0.01) { total -= turn * p.rebalance_cost * total; w_new = (double)total; }
-            for (int a = 0; a < kAssets; a++) if (st.w[a] != (R)0) { pvv[a] = total * st.w[a]; sl.trades++; }
+            for (int a = 0; a < kAssets; a++) if (LETF_PORT_ASSET(a)) { pvv[a] = total * st.w[a]; sl.trades++; }
           }
+#undef LETF_PORT_ASSET
           growth = EXACT ? (R)(w_new / sl.W) : M::div_((R)w_new, (R)sl.W);
           sl.W = w_new;
           sl.dd.step(sl.W, growth);
@@ -840,7 +857,7 @@ struct Trial {
         if (TM_HAS(LETF_ST_COMPOSITE)) if (ty == LETF_ST_COMPOSITE) {
           int score = (P_prev > s_sma200f ? 1 : 0) + (((R)40 < s_rsi && s_rsi < (R)80) ? 1 : 0) + (vix_prev < st.p[2] ? 1 : 0);
           int target = score == 3 ? 2 : (score == 2 ? 1 : 0);
-          r_strat = target == 2 ? pick6(ret, st.asset) : (target == 1 ? pick6(ret, st.asset2) : cash);
+          r_strat = target == 2 ? r_asset : (target == 1 ? (ASC >= 0 ? ret[4] : pick6(ret, st.asset2)) : cash);
           if (target != (int)sl.aux) {
             sl.trades++;
             if (JOURNAL && st.taxable) {
@@ -960,7 +977,7 @@ struct Trial {
           } else {
             if (sticky) alloc = prev_alloc; else sl.aux = alloc;
           }
-          r_strat = cashleg ? (alloc * pick6(ret, st.asset)) + (((R)1 - alloc) * cash) : pick6(ret, st.asset) * alloc;
+          r_strat = cashleg ? (alloc * r_asset) + (((R)1 - alloc) * cash) : r_asset * alloc;
           if (p.apply_costs) r_strat -= cost;
         }
         growth = (R)1 + r_strat;
@@ -971,7 +988,7 @@ struct Trial {
         if (LIST != 0) for_typed_slots<LIST>(slot_body, std::make_integer_sequence<int, NS>{});
         else {
 #pragma unroll(NS <= 8 ? NS : 1)
-          for (int s = 0; s < NS; s++) slot_body(s, std::integral_constant<int, -1>{});
+          for (int s = 0; s < NS; s++) slot_body(s, std::integral_constant<int, -1>{}, std::integral_constant<int, -1>{});
         }
       }
     }

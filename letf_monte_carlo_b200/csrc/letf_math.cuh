@@ -174,12 +174,17 @@ template <> struct Mth<float> {
   }
 };
 
-template <typename R> LETF_HD R rmax(R a, R b) { return a > b ? a : b; }   // python max(a, b) for non-NaN b
-template <typename R> LETF_HD R rmin(R a, R b) { return a < b ? a : b; }
+LETF_HD double rmax(double a, double b) { return a > b ? a : b; }   // python max(a, b) for non-NaN b
+LETF_HD double rmin(double a, double b) { return a < b ? a : b; }
+LETF_HD float rmax(float a, float b) { return fmaxf(a, b); }        // same result whenever b is not NaN (it never is here)
+LETF_HD float rmin(float a, float b) { return fminf(a, b); }
 template <typename R> LETF_HD R clipr(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); } // NaN passes through
 // clip for values that are known not to be NaN-significant (fp32 hot path): two FMNMX
 LETF_HD float clipfast(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 LETF_HD double clipfast(double x, double lo, double hi) { return clipr(x, lo, hi); }
+// clip of quantities that are finite by construction: exact NaN-preserving form in fp64, two FMNMX in fp32
+LETF_HD float clipx(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+LETF_HD double clipx(double x, double lo, double hi) { return clipr(x, lo, hi); }
 template <typename R> LETF_HD bool isnan_(R x) { return x != x; }
 template <typename R> LETF_HD bool isfinite_(R x) { return (x - x) == (R)0; }
 
