@@ -286,6 +286,13 @@ def run_b200(args):
         peak_lane = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e12               # T lane-ops/s at max clock
         achieved = n * T * wl["lane_ops"] / (kern_ms * 1e-3) / 1e12
         out_bytes = d2h
+        ncu_c = {}
+        try:
+            ncu_c = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json"))).get(args.workload, {})
+        except Exception:
+            pass
+        traffic = ncu_c.get("dram_bytes_per_launch") if n == wl["trials"] else None
+        exe = ncu_c.get("executed_warp_instr_per_path_day")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,7 +311,9 @@ def run_b200(args):
                     "steps": e2e_steps, "median_final_wealth": med},
             "gpu_launches": launches + e2e_launches,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
-                         "traffic": None, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
+                         "traffic": traffic, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
+                         "issue_slot_frac_executed": (n * T * exe / (kern_ms * 1e-3) / 1e12 / peak_lane) if exe else None,
+                         "ncu": ncu_c.get("source"),
                          "lane_ops_per_path_day": wl["lane_ops"], "units_per_launch": n * T,
                          "peak_def": f"{sm_count} SMs x 128 FP32/INT lanes x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})",
                          "frac_at_observed_clock": (achieved / (sm_count * 128 * clocks["sm_mhz"] * 1e6 / 1e12)

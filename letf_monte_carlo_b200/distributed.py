@@ -38,8 +38,12 @@ def allreduce_summary(hist, moments, extrema, counters, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+    import torch
+    # bins and counters are both int64 SUM: one collective on a packed buffer
+    packed_i = torch.cat([hist.reshape(-1), counters.reshape(-1)])
+    dist.all_reduce(packed_i, op=dist.ReduceOp.SUM, group=group)
+    hist.copy_(packed_i[:hist.numel()].view_as(hist))
+    counters.copy_(packed_i[hist.numel():].view_as(counters))
     dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
     # one MAX collective for both extrema: negate the minima
     packed = extrema.clone()

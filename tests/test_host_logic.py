@@ -145,3 +145,26 @@ def test_summary_allreduce_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_summary_table_matches_reference_definitions():
+    """reporting.py:353-388 on plain arrays; histogram quantiles agree to bin width"""
+    from letf_monte_carlo_b200.summary import histogram_quantile, summary_table
+    rng = np.random.default_rng(0)
+    n, years = 5001, 10
+    res = {"S2": [{"Final_Wealth": float(w), "Max_DD": float(d), "Trades_Per_Year": 0.0}
+                  for w, d in zip(1e4 * np.exp(rng.normal(0.6, 0.5, n)), rng.uniform(0.1, 0.6, n))],
+           "S4": [{"Final_Wealth": float(w), "Max_DD": float(d), "Trades_Per_Year": float(t)}
+                  for w, d, t in zip(1e4 * np.exp(rng.normal(0.4, 1.2, n)), rng.uniform(0.2, 0.9, n), rng.integers(0, 9, n))]}
+    rows = {r["id"]: r for r in summary_table(res, years)}
+    w2 = np.array([r["Final_Wealth"] for r in res["S2"]]); w4 = np.array([r["Final_Wealth"] for r in res["S4"]])
+    assert rows["S4"]["p25"] == np.percentile(w4, 25) and rows["S4"]["median"] == np.median(w4)
+    assert rows["S4"]["cagr"] == (np.median(w4) / 1e4) ** (1 / years) - 1
+    assert rows["S4"]["win"] == sum(a > b for a, b in zip(w4, w2)) / n * 100
+    assert rows["S4"]["dd"] == np.median([r["Max_DD"] for r in res["S4"]])
+    assert abs(rows["S4"]["trades"] - np.mean([r["Trades_Per_Year"] for r in res["S4"]])) < 1e-12
+    assert list(summary_table(res, years))[0]["id"] == "S2"          # sorted by median wealth
+    x = np.log10(w4 / 1e4)
+    h, _ = np.histogram(x, bins=4096, range=(-20, 10))
+    for q in (10, 50, 90):
+        assert abs(histogram_quantile(h, -20, 10, q) - np.percentile(x, q)) < 2 * 30 / 4096
