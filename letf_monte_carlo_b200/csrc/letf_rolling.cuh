@@ -100,37 +100,42 @@ template <typename R, bool EXACT> struct RollVar {
 };
 
 // rolling skew (bias-corrected G1) + the window mean, from online central moments -----------------
+// The moment state is kept in fp64 in BOTH precisions: the add/remove updates of m2 / m3 cancel
+// catastrophically in fp32 (1-3 % wealth error on the skew-driven rules over 10 years, measured);
+// it is ~25 fp64 operations per day and only in builds that carry a skew rule (S14, S17).
 template <typename R, bool EXACT> struct RollSkew {
-  R mean, m2, m3, prev;
+  double mean, m2, m3;
+  R prev;
   int nobs, ncs;
-  LETF_HD void init() { mean = m2 = m3 = (R)0; prev = nan_<R>(); nobs = ncs = 0; }
-  LETF_HD void remove(R v) {
+  LETF_HD void init() { mean = m2 = m3 = 0.0; prev = nan_<R>(); nobs = ncs = 0; }
+  LETF_HD void remove(R vr) {
+    const double v = (double)vr;
     int nn = nobs - 1;
-    if (nn == 0) { mean = m2 = m3 = (R)0; }
+    if (nn == 0) { mean = m2 = m3 = 0.0; }
     else {
-      R delta = v - mean, dn = Mth<R>::div_(delta, (R)nn), term1 = delta * dn * (R)nobs;
-      m3 = m3 - (term1 * dn * (R)(nobs + 1) - (R)3 * dn * m2);
+      double delta = v - mean, dn = delta / (double)nn, term1 = delta * dn * (double)nobs;
+      m3 = m3 - (term1 * dn * (double)(nobs + 1) - 3.0 * dn * m2);
       mean = mean - dn;
       m2 = m2 - term1;
     }
     nobs = nn;
   }
-  LETF_HD void add(R v) {
+  LETF_HD void add(R vr) {
+    const double v = (double)vr;
     int nn = nobs + 1;
-    R delta = v - mean, dn = Mth<R>::div_(delta, (R)nn), term1 = delta * dn * (R)nobs;
-    m3 = m3 + term1 * dn * (R)(nn - 2) - (R)3 * dn * m2;
+    double delta = v - mean, dn = delta / (double)nn, term1 = delta * dn * (double)nobs;
+    m3 = m3 + term1 * dn * (double)(nn - 2) - 3.0 * dn * m2;
     m2 = m2 + term1;
     mean = mean + dn;
     nobs = nn;
-    if (EXACT) { ncs = (v == prev) ? ncs + 1 : 1; prev = v; }
+    if (EXACT) { ncs = (vr == prev) ? ncs + 1 : 1; prev = vr; }
   }
   LETF_HD R skew(int mp) const {
     if (nobs < mp || nobs < 3) return nan_<R>();
-    R d = (R)nobs, B = Mth<R>::div_(m2, d);
+    double d = (double)nobs, B = m2 / d;
     if (EXACT && ncs >= nobs) return (R)0;
-    if (B <= (R)1e-14) return nan_<R>();
-    typedef Mth<R> M_;
-    return M_::div_(M_::div_(M_::sqrt_(d * (d - (R)1)), d - (R)2) * M_::div_(m3, d), B * M_::sqrt_(B));
+    if (B <= 1e-14) return nan_<R>();
+    return (R)(::sqrt(d * (d - 1.0)) / (d - 2.0) * (m3 / d) / (B * ::sqrt(B)));
   }
 };
 
