@@ -307,7 +307,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed: parameter dicts in, host result arrays out "
-                           "(engine handle cached across calls, page-locked outputs)",
+                           "(engine handle cached across calls; results staged through the library's pinned buffer)",
                     "steps": e2e_steps, "median_final_wealth": med},
             "gpu_launches": launches + e2e_launches,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,

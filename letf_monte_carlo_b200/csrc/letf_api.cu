@@ -68,6 +68,22 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// page-locked host staging: device -> pinned at full PCIe rate, then a plain memcpy into the caller's
+// (pageable) arrays; allocating / freeing pinned memory per call costs milliseconds and synchronises
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace letf
 
 using namespace letf;
@@ -81,6 +97,7 @@ struct LetfEngine {
   bool any_taxable = false;
   DevBuf xscr, ringP, ringS, ringA;          // per-thread scratch of the fused kernel
   DevBuf stage_tape, stage_out, stage_log;   // device staging of the *_host entry points
+  PinBuf pin_out;                            // pinned mirror of stage_out
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   LetfLaunchInfo info;
@@ -135,20 +152,23 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   int max_blocks = 0;
   CK(ke->attrs(&fa, &max_blocks));
   if (max_blocks < 1) return fail(LETF_ERR_CUDA, std::string("kernel ") + ke->name + " cannot be resident on this device");
-  // persistent grid: every resident thread owns ceil(n / nthreads) trials; shrink the grid so that
-  // all waves are full (equal-length trials: a partial last wave costs a whole trial time)
+  static thread_local KArgs<R, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  convert_params<R, NS, NA>(e->params, e->dev_dur, ka.p);
+  // persistent grid: every resident thread owns ceil(n / nthreads) work items; shrink the grid so that
+  // all waves are full (equal-length trials: a partial last wave costs a whole trial time).  A work item is
+  // one trial, or `upt` interleaved trials in the straight-line fast path (letf_fast.cuh).
   const int kBlock = ke->block;
+  const int upt = (ke->upt > 1 && ka.p.fast_layers && rng_mode == LETF_RNG_PHILOX && !series) ? ke->upt : 1;
+  const int64_t items = (n + upt - 1) / upt;
   const int64_t resident = (int64_t)e->sm_count * max_blocks * kBlock;
-  const int64_t waves = (n + resident - 1) / resident;
-  const int64_t per_wave = (n + waves - 1) / waves;
+  const int64_t waves = (items + resident - 1) / resident;
+  const int64_t per_wave = (items + waves - 1) / waves;
   int64_t grid = (per_wave + kBlock - 1) / kBlock;
   if (grid < 1) grid = 1;
   const int64_t nthreads = grid * kBlock;
   if ((int64_t)kRingP * nthreads >= ((int64_t)1 << 32)) return fail(LETF_ERR_INVALID, "grid too large for 32-bit ring offsets");
 
-  static thread_local KArgs<R, NS, NA> ka;
-  memset(&ka, 0, sizeof(ka));
-  convert_params<R, NS, NA>(e->params, e->dev_dur, ka.p);
   if (series) { ka.series = *series; ka.p.T = series->sim_days; ka.p.buffer = 0; ka.p.random_start = 0; }
   if (tape) ka.tape = *tape;
   ka.out = *out;
@@ -287,7 +307,7 @@ void letf_destroy(LetfEngine* e) {
   cudaSetDevice(e->device);
   for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
   e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release();
-  e->stage_tape.release(); e->stage_out.release(); e->stage_log.release();
+  e->stage_tape.release(); e->stage_out.release(); e->stage_log.release(); e->pin_out.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -435,19 +455,23 @@ int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_t
   int rc = launch_any(e, e->params.market_mode, (cudaStream_t)0, seed, first_trial, n_trials, rng_mode, tp, &dout, nullptr, LogArgs());
   if (rc) return rc;
   if (n_trials == 0) return LETF_OK;
-  // device [S][n] -> host [S][N] (row pitch = host capacity)
+  // one device -> pinned copy of the whole staging block, then scatter device [S][n] -> host [S][N]
+  // (row pitch = host capacity) with plain memcpy
   const size_t n = (size_t)n_trials, N = (size_t)host_out->n_trials;
-  CK(cudaMemcpy2D(host_out->final_wealth, N * 8, dout.final_wealth, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy2D(host_out->max_dd, N * 8, dout.max_dd, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy2D(host_out->num_trades, N * 4, dout.num_trades, n * 4, n * 4, S, cudaMemcpyDeviceToHost));
-  if (dout.journal_count) CK(cudaMemcpy2D(host_out->journal_count, N * 4, dout.journal_count, n * 4, n * 4, S, cudaMemcpyDeviceToHost));
-  if (dout.journal_volume) CK(cudaMemcpy2D(host_out->journal_volume, N * 8, dout.journal_volume, n * 8, n * 8, S, cudaMemcpyDeviceToHost));
-  if (dout.start_offset) CK(cudaMemcpy(host_out->start_offset, dout.start_offset, n * 4, cudaMemcpyDeviceToHost));
-  if (dout.regime_days) CK(cudaMemcpy2D(host_out->regime_days, N * 4, dout.regime_days, n * 4, n * 4, 2, cudaMemcpyDeviceToHost));
-  if (dout.jump_days) CK(cudaMemcpy(host_out->jump_days, dout.jump_days, n * 4, cudaMemcpyDeviceToHost));
-  std::vector<uint32_t> fl(n);
-  CK(cudaMemcpy(fl.data(), dout.flags, n * 4, cudaMemcpyDeviceToHost));
-  if (host_out->flags) memcpy(host_out->flags, fl.data(), n * 4);
+  ce = e->pin_out.reserve(L.total ? L.total : 256);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "pinned staging: " + std::string(cudaGetErrorString(ce))); }
+  CK(cudaMemcpyAsync(e->pin_out.p, base, L.total, cudaMemcpyDeviceToHost, (cudaStream_t)0));
+  CK(cudaStreamSynchronize((cudaStream_t)0));
+  const char* hb = (const char*)e->pin_out.p;
+  auto rows = [&](void* dst, int field, size_t elem, int nrows) {
+    if (!dst || !L.bytes[field]) return;
+    for (int r = 0; r < nrows; r++) memcpy((char*)dst + (size_t)r * N * elem, hb + L.off[field] + (size_t)r * n * elem, n * elem);
+  };
+  rows(host_out->final_wealth, 0, 8, S); rows(host_out->max_dd, 1, 8, S); rows(host_out->num_trades, 2, 4, S);
+  rows(host_out->journal_count, 3, 4, S); rows(host_out->journal_volume, 4, 8, S);
+  rows(host_out->start_offset, 5, 4, 1); rows(host_out->flags, 6, 4, 1); rows(host_out->regime_days, 7, 4, 2);
+  rows(host_out->jump_days, 8, 4, 1);
+  const uint32_t* fl = (const uint32_t*)(hb + L.off[6]);
   if (rng_mode == LETF_RNG_PHILOX_RECORD) { rc = unstage_tape(e, host_tape); if (rc) return rc; }
   int64_t bad = 0;
   for (size_t i = 0; i < n; i++) if (fl[i] & (LETF_FLAG_NONFINITE_RET | LETF_FLAG_BAD_VIX)) bad++;

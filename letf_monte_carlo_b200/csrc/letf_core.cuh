@@ -250,7 +250,7 @@ struct Trial {
   // one generated day of the raw (pre moment-matching) underlying returns x[3] = SPY, QQQ, TLT.
   // Also returns the two "phase-2" normals of the day (VIX noise, IRX noise) when WANT_AUX.
   template <bool WANT_X, bool WANT_AUX, bool FASTM = false>
-  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n) {
+  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n, const U4 pre0 = U4()) {
     R z0 = 0, z1 = 0, z2 = 0, nchi = 0;
     uint32_t cw0 = 0, cw1 = 0;
     if (use_tape) {
@@ -258,7 +258,7 @@ struct Trial {
       if (WANT_AUX && MARKET != LETF_MARKET_NORMAL) { vix_n = tp_get(ka.tape.vix_n, g); irx_n = tp_get(ka.tape.irx_n, g); }
     } else {
       if (WANT_X && MARKET != LETF_MARKET_PARAM_T) {
-        U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
+        U4 b0 = FASTM ? pre0 : rng_block(key, (uint32_t)g, STREAM_MKT0);   // FAST: drawn with the day's other blocks
         M::box_muller(b0.x, b0.y, z0, z1);
         // the iid-normal shapes only need the third shock when a TLT-based series is computed
         if (!FASTM && (MARKET != LETF_MARKET_NORMAL || TAPEIO || p.need_tlt)) M::box_muller(b0.z, b0.w, z2, nchi);
@@ -540,14 +540,26 @@ struct Trial {
       }
       const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
+      U4 bte[NA];                                       // FAST: the series' tracking-error blocks of this day
       if (MARKET == kMarketSeries) {
         vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
       } else if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
         x[0] = vcur.x + shift[0]; x[1] = vcur.y + shift[1]; x[2] = vcur.z + shift[2];
+      } else if (FAST) {
+        // all Philox blocks of the day (market + one per series) with interleaved rounds
+        uint32_t streams[NA + 1];
+        U4 blk[NA + 1];
+        streams[0] = STREAM_MKT0;
+#pragma unroll
+        for (int a = 0; a < NA; a++) streams[a + 1] = STREAM_TE0 + (uint32_t)p.act_id[a];
+        rng_blocks<NA + 1>(key, (uint32_t)g, streams, blk);
+#pragma unroll
+        for (int a = 0; a < NA; a++) bte[a] = blk[a + 1];
+        market_day<true, true, true>(g, reg, js, x, vn, in, blk[0]);
       } else {
-        market_day<true, true, FAST>(g, reg, js, x, vn, in);
+        market_day<true, true, false>(g, reg, js, x, vn, in);
       }
       R rf = p.const_rf;
       if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
@@ -662,7 +674,7 @@ struct Trial {
             R innov;
             if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)aid * T + i);
             else {
-              U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
+              U4 b = FAST ? bte[a] : rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
               innov = FAST ? student_t5<R>(b)
                            : student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
               if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);

@@ -1,0 +1,115 @@
+// letf_fast.cuh — the straight-line day step of the lean buy&hold builds, U trials per thread.
+//
+// Same computation as Trial::run_t<FAST> (letf_core.cuh) for the shapes DevParams::fast_layers admits
+// (iid-normal market, every compacted slot active, t(5) tracking error, no tanh cap, no funding model, no
+// TLT series, buy&hold only): reference layers engine.py:360-420, statistics engine.py:578-590.
+// It exists for instruction-level parallelism: BASELINE configs[1] has 100 000 trials, i.e. only ~5 warps
+// per scheduler, and one trial's day step is a handful of long dependent chains (10 Philox rounds, then
+// lg2 -> rsqrt -> FMA chains per series).  Interleaving U = 2 independent trials in one thread doubles the
+// independent chains the scheduler sees while the grid still fits in one wave (ceil(n / U) threads).
+// Philox counters, draw order and arithmetic are those of run_t<FAST>, so results agree to fp32 contraction.
+#pragma once
+#include "letf_core.cuh"
+
+namespace letf {
+
+template <int NS, int NA, int U>
+struct FastLayers {
+  typedef float R;
+  typedef Mth<float> M;
+
+  // trial[u] / col[u]: global trial id and output column; live[u]: false for the padding lane of an odd tail
+  static __device__ __forceinline__ void run(const KArgs<R, NS, NA>& ka, const int64_t (&trial)[U],
+                                             const int64_t (&col)[U], const bool (&live)[U]) {
+    const DevParams<R, NS, NA>& p = ka.p;
+    const int T = p.T;
+    RngKey key[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t sim_id = p.antithetic ? (trial[u] & ~(int64_t)1) : trial[u];
+      key[u].k0 = (uint32_t)ka.seed; key[u].k1 = (uint32_t)(ka.seed >> 32);
+      key[u].t0 = (uint32_t)sim_id; key[u].t1 = (uint32_t)((uint64_t)sim_id >> 32);
+    }
+    R te_prev[U][NA], bias[U][NA], q[U][NA], qmin[U][NA], chk[U];
+    double cp[U][NA];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      chk[u] = 0.0f;
+#pragma unroll
+      for (int a = 0; a < NA; a++) { te_prev[u][a] = 0.0f; bias[u][a] = 0.0f; q[u][a] = INFINITY; qmin[u][a] = 1.0f; cp[u][a] = 1.0; }
+    }
+    const R vix = p.const_vix;
+    const R vrmult = clipx(M::sqrt_(vix * 0.05f), 0.5f, 1.5f) * 1.0f;      // regime 0 (engine.py:178-181)
+    uint32_t streams[NA + 1];
+    streams[0] = STREAM_MKT0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) streams[a + 1] = STREAM_TE0 + (uint32_t)p.act_id[a];
+    const R alpha = (R)(2.0 / 127.0);
+
+    for (int i = 0; i < T; i++) {
+      U4 blk[U][NA + 1];
+#pragma unroll
+      for (int u = 0; u < U; u++) rng_blocks<NA + 1>(key[u], (uint32_t)i, streams, blk[u]);
+      const R vrlive = i >= 1 ? vrmult : 0.0f;          // no tracking error on day 0 (engine.py:184)
+      R spy[U], qqq[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        R z0, z1;
+        M::box_muller(blk[u][0].x, blk[u][0].y, z0, z1);
+        spy[u] = p.n_mu[0] + p.n_ch[0] * z0;
+        qqq[u] = p.n_mu[1] + (p.n_ch[1] * z0 + p.n_ch[2] * z1);
+        chk[u] = fmaf(spy[u], 0.0f, chk[u]); chk[u] = fmaf(qqq[u], 0.0f, chk[u]);
+      }
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        const DevAsset<R>& ap = p.act[a];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const R un = fmaf(ap.w_spy, spy[u], ap.w_qqq * qqq[u]);
+          const R lev = ap.lev * un - ap.carry_const;
+          const R innov = student_t5<R>(blk[u][a + 1]);
+          const R ds = un < 0.0f ? ap.te_down : 0.98f;
+          const R mm = (1.0f + 0.3f * fabsf(un)) * ds;
+          const R te_raw = ap.te_rho * te_prev[u][a] + (innov * vrlive) * (ap.te_scale * mm);
+          te_prev[u][a] = te_raw;
+          bias[u][a] = alpha * te_raw + (1.0f - alpha) * bias[u][a];
+          const R er = clipfast(lev + (te_raw - bias[u][a]), -0.999f, 10.0f);
+          cp[u][a] = ::fma(cp[u][a], (double)er, cp[u][a]);
+          q[u][a] = fminf(1.0f, fmaf(q[u][a], er, q[u][a]));
+          qmin[u][a] = fminf(qmin[u][a], q[u][a]);
+        }
+      }
+    }
+
+    // per-trial outputs (engine.py:578-603); validity as in run_t: constant VIX, sticky non-finite / exhausted products
+    const int64_t N = ka.out.n_trials;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!live[u]) continue;
+      uint32_t flags = 0;
+      bool bad = false;
+      if (T > 0 && (!isfinite_(vix) || vix <= 0.0f)) flags |= LETF_FLAG_BAD_VIX;
+      if (chk[u] != 0.0f) flags |= LETF_FLAG_NONFINITE_RET;
+#pragma unroll
+      for (int a = 0; a < NA; a++) if (T > 0 && !(cp[u][a] > 0.0 && isfinite_(cp[u][a]))) bad = true;
+      if (T == 0 || bad || !(vix >= 5.0f) || !(vix <= 120.0f)) flags |= LETF_FLAG_REPAIRED;
+      for (int s = 0; s < NS; s++) {
+        if (s >= p.n_strat) break;
+        double c = 1.0; R qm = 1.0f;
+#pragma unroll
+        for (int a = 0; a < NA; a++) if (p.act_id[a] == p.strat[s].asset) { c = cp[u][a]; qm = qmin[u][a]; }
+        ka.out.final_wealth[(int64_t)s * N + col[u]] = T > 0 ? (double)p.W0 * c : 0.0;
+        ka.out.max_dd[(int64_t)s * N + col[u]] = T > 1 ? (double)(1.0f - qm) : 0.0;
+        ka.out.num_trades[(int64_t)s * N + col[u]] = 0;
+        if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col[u]] = 0;
+        if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col[u]] = 0.0;
+      }
+      if (ka.out.start_offset) ka.out.start_offset[col[u]] = 0;
+      if (ka.out.flags) ka.out.flags[col[u]] = flags;
+      if (ka.out.regime_days) { ka.out.regime_days[col[u]] = T; ka.out.regime_days[N + col[u]] = 0; }
+      if (ka.out.jump_days) ka.out.jump_days[col[u]] = 0;
+    }
+  }
+};
+
+}  // namespace letf

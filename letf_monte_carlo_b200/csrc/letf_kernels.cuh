@@ -3,12 +3,35 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "letf_core.cuh"
+#include "letf_fast.cuh"
 
 namespace letf {
+
+// trials per thread of the straight-line fast path (letf_fast.cuh); 1 = the build has none
+template <typename R, int NA, int MARKET, bool TAPEIO>
+LETF_HD constexpr int fast_upt() { return (sizeof(R) == 4 && NA < kAssets && MARKET == LETF_MARKET_NORMAL && !TAPEIO) ? 2 : 1; }
 
 template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int LIST, int AM, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_constant__ KArgs<R, NS, NA> ka) {
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int UPT = fast_upt<R, NA, MARKET, TAPEIO>();
+  if constexpr (UPT > 1) {
+    if (ka.p.fast_layers && ka.rng_mode == LETF_RNG_PHILOX) {     // host sized the grid for ceil(n / UPT) threads
+      for (int64_t j = lane; j < ka.n_trials; j += (int64_t)UPT * ka.nthreads) {
+        int64_t trial[UPT], col[UPT];
+        bool live[UPT];
+#pragma unroll
+        for (int u = 0; u < UPT; u++) {
+          col[u] = j + (int64_t)u * ka.nthreads;
+          live[u] = col[u] < ka.n_trials;
+          if (!live[u]) col[u] = j;                   // padding lane recomputes trial j and stores nothing
+          trial[u] = ka.first_trial + col[u];
+        }
+        FastLayers<NS, NA, UPT>::run(ka, trial, col, live);
+      }
+      return;
+    }
+  }
   for (int64_t j = lane; j < ka.n_trials; j += ka.nthreads) {
     Trial<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM> t(ka, ka.first_trial + j, j, lane);
     t.run();
@@ -26,6 +49,7 @@ struct KernelEntry {
   int list;           // typed slot list (slot_list_type), 0 = dynamic dispatch
   int am;             // compile-time asset mask, 0 = run time
   int block;          // threads per block
+  int upt;            // trials per thread when DevParams::fast_layers applies (letf_fast.cuh), else 1
   const char* name;
   cudaError_t (*launch)(const void* kargs, int grid, cudaStream_t st);
   cudaError_t (*attrs)(cudaFuncAttributes* a, int* max_blocks_per_sm);
@@ -54,7 +78,8 @@ struct KernelImpl {
   struct Reg_##ID {                                                                                      \
     Reg_##ID() {                                                                                         \
       typedef letf::KernelImpl<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB> K;                    \
-      letf::KernelEntry e = {PREC, NS, NA, MARKET, TAPEIO ? 1 : 0, TM, LIST, AM, BLK, #ID, &K::launch,   \
+      letf::KernelEntry e = {PREC, NS, NA, MARKET, TAPEIO ? 1 : 0, TM, LIST, AM, BLK,                    \
+                             letf::fast_upt<R, NA, MARKET, TAPEIO>(), #ID, &K::launch,                   \
                              &K::attrs,                                                                  \
                              sizeof(letf::KArgs<R, NS, NA>)};                                                \
       letf::register_kernel(e);                                                                          \

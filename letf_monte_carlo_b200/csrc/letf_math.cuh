@@ -70,6 +70,36 @@ LETF_HD U4 rng_block(const RngKey& k, uint32_t day, uint32_t stream, uint32_t su
   return philox4x32_10(c, k.k0, k.k1);
 }
 
+// N independent blocks of one (trial, day) with their rounds interleaved in program order: the 10 rounds of a
+// block are a dependent IMAD.WIDE -> LOP3 chain (~10 cycles per round), N chains side by side keep the
+// multiplier and logic pipes busy from a single warp.  Same values as N calls of rng_block.
+template <int N>
+LETF_HD void rng_blocks(const RngKey& k, uint32_t day, const uint32_t (&stream)[N], U4 (&out)[N]) {
+  U4 c[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) { c[j].x = k.t0; c[j].y = k.t1; c[j].z = day; c[j].w = stream[j] << 8; }
+  uint32_t k0 = k.k0, k1 = k.k1;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, c[j].x, h0, l0);
+      mulhilo(0xCD9E8D57u, c[j].z, h1, l1);
+      U4 n;
+      n.x = h1 ^ c[j].y ^ k0;
+      n.y = l1;
+      n.z = h0 ^ c[j].w ^ k1;
+      n.w = l0;
+      c[j] = n;
+    }
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) out[j] = c[j];
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename R> struct Mth;
 

@@ -152,6 +152,6 @@ def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correla
         print(f"\n{'=' * 80}\nMONTE CARLO: {n_total:,} sims x {time_horizon}Y  "
               f"[B200 path engine, {precision}, {ws} GPU(s)]\n{'=' * 80}")
     eng = _engine_for(params, keep, precision, device if device is not None else getattr(cfg, "GPU_DEVICE", None))
-    # raises NonFiniteTrials like the reference's ValueError; results land in page-locked host arrays
-    out = eng.run_host(hi - lo, first_trial=lo, seed=seed, pinned=True)
+    # raises NonFiniteTrials like the reference's ValueError (the C-ABI stages through its own pinned buffer)
+    out = eng.run_host(hi - lo, first_trial=lo, seed=seed)
     return MonteCarloRun(eng, out, strategy_ids, time_horizon, seed, lo, hi - lo, n_total, TAXABLE_IDS)
