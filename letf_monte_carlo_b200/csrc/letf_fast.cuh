@@ -19,7 +19,7 @@ struct FastLayers {
   typedef Mth<float> M;
 
   // trial[u] / col[u]: global trial id and output column; live[u]: false for the padding lane of an odd tail
-  static __device__ __forceinline__ void run(const KArgs<R, NS, NA>& ka, const int64_t (&trial)[U],
+  static LETF_HD void run(const KArgs<R, NS, NA>& ka, const int64_t (&trial)[U],
                                              const int64_t (&col)[U], const bool (&live)[U]) {
     const DevParams<R, NS, NA>& p = ka.p;
     const int T = p.T;

@@ -163,6 +163,13 @@ def test_lean_fast_variant_matches_generic_build():
     np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=2e-5)
     np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=2e-6)
     np.testing.assert_array_equal(lean.flags, gen.flags)
+    # the launch form (two interleaved trials per thread, odd tail) computes the same thing as run_t<FAST>
+    two, fast2 = emu.run_lean(params, 63, seed=77, two_per_thread=True)
+    assert fast2
+    np.testing.assert_allclose(two.final_wealth, lean.final_wealth[:, :63], rtol=1e-6)
+    np.testing.assert_allclose(two.max_dd, lean.max_dd[:, :63], atol=1e-6)
+    np.testing.assert_array_equal(two.flags, lean.flags[:63])
+    np.testing.assert_array_equal(two.regime_days, lean.regime_days[:, :63])
     # and against fp64 on the same counters (fp64 Box-Muller / log differ in the last bits of each variate)
     g64 = emu.run(params, dummy, precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX, seed=77, n=64)
     np.testing.assert_allclose(lean.final_wealth, g64.final_wealth, rtol=5e-3)
