@@ -400,3 +400,31 @@ def test_typed_slot_kernels_vs_generic_and_oracle(sids, engine_lib):
     assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97, (np.median(rel), np.mean(rel < 1e-2))
     assert np.mean(typed.num_trades != o.num_trades) < 0.03
     assert regs_typed > 0
+
+
+def test_edge_sizes_and_offsets(engine_lib):
+    """empty launch, single trial, odd trial counts and odd first_trial with antithetic pairing, the tail of the
+    two-trials-per-thread fast path"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(["S1", "S2", "S4"], 1, synthetic.fallback_regime_model("default"), ns)
+    with _engine(params, keep, "f32") as eng:
+        assert eng.run_host(0).final_wealth.shape == (3, 0)
+        whole = eng.run_host(11, seed=5)
+        one = eng.run_host(1, seed=5, first_trial=7)
+        odd = eng.run_host(4, seed=5, first_trial=3)
+    np.testing.assert_array_equal(one.final_wealth[:, 0], whole.final_wealth[:, 7])
+    np.testing.assert_array_equal(odd.final_wealth, whole.final_wealth[:, 3:7])
+    np.testing.assert_array_equal(odd.num_trades, whole.num_trades[:, 3:7])
+    np.testing.assert_array_equal(whole.start_offset[0::2][:5], whole.start_offset[1::2])     # twins share sim_id
+    # fast path (c2 shape): odd counts exercise the padding lane
+    ns2 = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                     USE_ANTITHETIC_VARIATES=False)
+    p2, k2 = build_params(["S1", "B_UPRO", "S3"], 1, synthetic.normal_regime_model("c2"), ns2)
+    with _engine(p2, k2, "f32") as eng:
+        a = eng.run_host(1001, seed=9)
+        b = eng.run_host(1, seed=9, first_trial=1000)
+        c = eng.run_host(64, seed=9, first_trial=500)
+    np.testing.assert_array_equal(a.final_wealth[:, 1000], b.final_wealth[:, 0])
+    np.testing.assert_array_equal(a.final_wealth[:, 500:564], c.final_wealth)
+    np.testing.assert_array_equal(a.max_dd[:, 500:564], c.max_dd)
+    assert (a.flags == 0).all() and (a.regime_days[0] == p2.sim_days).all()
