@@ -249,19 +249,29 @@ struct Trial {
 
   // one generated day of the raw (pre moment-matching) underlying returns x[3] = SPY, QQQ, TLT.
   // Also returns the two "phase-2" normals of the day (VIX noise, IRX noise) when WANT_AUX.
-  template <bool WANT_X, bool WANT_AUX, bool FASTM = false>
-  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n, const U4 pre0 = U4()) {
+  template <bool WANT_X, bool WANT_AUX>
+  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n) {
     R z0 = 0, z1 = 0, z2 = 0, nchi = 0;
     uint32_t cw0 = 0, cw1 = 0;
     if (use_tape) {
       if (WANT_X) { z0 = tp_get(ka.tape.x, (int64_t)g * 3 + 0); z1 = tp_get(ka.tape.x, (int64_t)g * 3 + 1); z2 = tp_get(ka.tape.x, (int64_t)g * 3 + 2); }
       if (WANT_AUX && MARKET != LETF_MARKET_NORMAL) { vix_n = tp_get(ka.tape.vix_n, g); irx_n = tp_get(ka.tape.irx_n, g); }
     } else {
-      if (WANT_X && MARKET != LETF_MARKET_PARAM_T) {
-        U4 b0 = FASTM ? pre0 : rng_block(key, (uint32_t)g, STREAM_MKT0);   // FAST: drawn with the day's other blocks
+      if (WANT_X && MARKET == LETF_MARKET_NORMAL) {
+        // iid-normal shapes: the SPY / QQQ shocks of days 2j and 2j+1 share one block (words x,y / z,w of
+        // (j, STREAM_MKT_PAIR)); the third shock has its own block and is drawn only when a TLT-based
+        // series is computed (letf_fast.cuh consumes the same layout two days per iteration)
+        U4 bp = rng_block(key, (uint32_t)g >> 1, STREAM_MKT_PAIR);
+        if (g & 1) M::box_muller(bp.z, bp.w, z0, z1); else M::box_muller(bp.x, bp.y, z0, z1);
+        if (TAPEIO || p.need_tlt) {
+          U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
+          M::box_muller(b0.z, b0.w, z2, nchi);
+        }
+      }
+      if (WANT_X && MARKET == LETF_MARKET_JOINT_T) {
+        U4 b0 = rng_block(key, (uint32_t)g, STREAM_MKT0);
         M::box_muller(b0.x, b0.y, z0, z1);
-        // the iid-normal shapes only need the third shock when a TLT-based series is computed
-        if (!FASTM && (MARKET != LETF_MARKET_NORMAL || TAPEIO || p.need_tlt)) M::box_muller(b0.z, b0.w, z2, nchi);
+        M::box_muller(b0.z, b0.w, z2, nchi);
       }
       if (WANT_X && MARKET == LETF_MARKET_PARAM_T) {
         for (int c = 0; c < 3; c++) {
@@ -412,14 +422,8 @@ struct Trial {
   }
 
   // run the whole trial ---------------------------------------------------------------------
-  // FAST: loop-unswitched variant of the lean buy&hold builds (all slots active, t(5) tracking error,
-  // no tanh cap, no TLT): the day step is one basic block, so the scheduler can interleave the
-  // independent Philox blocks and asset chains.
+  // (the loop-unswitched straight-line form of the lean buy&hold shapes lives in letf_fast.cuh)
   LETF_HD void run() {
-    if (NA < kAssets && MARKET == LETF_MARKET_NORMAL && !TAPEIO && p.fast_layers) run_t<true>();
-    else run_t<false>();
-  }
-  template <bool FAST> LETF_HD void run_t() {
     const int G = p.T + p.buffer;
     const int64_t nth = ka.nthreads;
     const uint32_t nth32 = (uint32_t)ka.nthreads;             // ring rows: depth * nthreads < 2^32 elements (checked by the host)
@@ -540,26 +544,14 @@ struct Trial {
       }
       const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
-      U4 bte[NA];                                       // FAST: the series' tracking-error blocks of this day
       if (MARKET == kMarketSeries) {
         vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
       } else if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
         x[0] = vcur.x + shift[0]; x[1] = vcur.y + shift[1]; x[2] = vcur.z + shift[2];
-      } else if (FAST) {
-        // all Philox blocks of the day (market + one per series) with interleaved rounds
-        uint32_t streams[NA + 1];
-        U4 blk[NA + 1];
-        streams[0] = STREAM_MKT0;
-#pragma unroll
-        for (int a = 0; a < NA; a++) streams[a + 1] = STREAM_TE0 + (uint32_t)p.act_id[a];
-        rng_blocks<NA + 1>(key, (uint32_t)g, streams, blk);
-#pragma unroll
-        for (int a = 0; a < NA; a++) bte[a] = blk[a + 1];
-        market_day<true, true, true>(g, reg, js, x, vn, in, blk[0]);
       } else {
-        market_day<true, true, false>(g, reg, js, x, vn, in);
+        market_day<true, true>(g, reg, js, x, vn, in);
       }
       R rf = p.const_rf;
       if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
@@ -624,7 +616,7 @@ struct Trial {
 
       // ---- financing spread shared by all assets (engine.py:328-342, calibration.py:833-857)
       R spread_common = 0;
-      if (!FAST && MARKET != kMarketSeries && p.has_funding) {
+      if (MARKET != kMarketSeries && p.has_funding) {
         R irx_level = rf * (R)100;
         R term = p.has_stress ? (R)1.25 - (R)1.1 * clipx(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
         R tnx = irx_level + term;
@@ -637,9 +629,6 @@ struct Trial {
       const R vmult = clipx(M::sqrt_(EXACT ? vix / (R)20 : vix * (R)0.05), (R)0.5, (R)1.5);
       const R rmult = reg == 0 ? (R)1 : (R)1.15;
       const R vrmult = vmult * rmult;
-      // FAST: day 0 carries no tracking error (engine.py:184 starts at i = 1); te_prev is 0 there, so zeroing the
-      // innovation scale once per day replaces a select per asset
-      const R vrlive = FAST ? (i >= 1 ? vrmult : (R)0) : vrmult;
 
       // ---- the six ETF layers (engine.py:360-420)
       R ret[kAssets];
@@ -653,14 +642,13 @@ struct Trial {
           if (!ka.series.asset_ret[a]) continue;
           er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
         } else {
-          if (AM != 0 && NA == kAssets ? !((AM >> a) & 1) : (!FAST && !p.act_on[a])) continue;
+          if (AM != 0 && NA == kAssets ? !((AM >> a) & 1) : !p.act_on[a]) continue;
           const DevAsset<R>& ap = p.act[a];
           R ub = ap.und == 1 ? qqq : (ap.und == 2 ? tlt : spy);
           R u = EXACT ? (ap.beta_applies ? ub * ap.beta : ub) : ub * ap.beta_eff;
-          if (FAST) u = M::fma_(ap.w_spy, spy, ap.w_qqq * qqq);   // no TLT series in this loop; 0 * finite is exact
-          R spread = (!FAST && p.has_funding) ? spread_common : ap.borrow_spread;
+          R spread = p.has_funding ? spread_common : ap.borrow_spread;
           R lev;
-          if (!EXACT && MARKET == LETF_MARKET_NORMAL && (FAST || !p.has_funding)) {
+          if (!EXACT && MARKET == LETF_MARKET_NORMAL && !p.has_funding) {
             lev = ap.lev * u - ap.carry_const;            // constant rf, no funding model: the carry is invariant
           } else if (EXACT) {
             R borrow = 0;
@@ -674,9 +662,8 @@ struct Trial {
             R innov;
             if (use_tape) innov = tp_get(ka.tape.te_t, (int64_t)aid * T + i);
             else {
-              U4 b = FAST ? bte[a] : rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
-              innov = FAST ? student_t5<R>(b)
-                           : student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
+              U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
+              innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
               if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);
             }
             R ds = u < (R)0 ? ap.te_down : (R)0.98;
@@ -685,15 +672,15 @@ struct Trial {
               innov *= ap.te_base * vmult * rmult * (R)1;
               te_raw = ap.te_rho * te_prev[a] + ap.te_arw * innov * mm;
             } else {
-              te_raw = ap.te_rho * te_prev[a] + (innov * vrlive) * (ap.te_scale * mm);
-              if (!TAPEIO && !FAST) te_raw = i >= 1 ? te_raw : (R)0;
+              te_raw = ap.te_rho * te_prev[a] + (innov * vrmult) * (ap.te_scale * mm);
+              if (!TAPEIO) te_raw = i >= 1 ? te_raw : (R)0;
             }
           } else if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T, 0);
           te_prev[a] = te_raw;
           const R alpha = (R)(2.0 / 127.0);
           bias[a] = alpha * te_raw + ((R)1 - alpha) * bias[a];
           R te = te_raw - bias[a];
-          if (!FAST && ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
+          if (ap.te_clip > (R)0) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
           er = EXACT ? clipr(lev + te, (R)-0.999, (R)10) : clipfast(lev + te, (R)-0.999, (R)10);
         }
         if (NA == kAssets) ret[a] = er;
@@ -704,7 +691,7 @@ struct Trial {
         } else {
           cp[a] = ::fma(cp[a], (double)er, cp[a]);      // a NaN return or a product that reached 0 stays there
         }
-        if (FAST || p.act_bench[a]) {                   // strategy.py:85-95 buy & hold: W = W0 * cumprod(1 + r)
+        if (p.act_bench[a]) {                   // strategy.py:85-95 buy & hold: W = W0 * cumprod(1 + r)
           if (EXACT) {
             if (i == 0) ddA[a].init((double)p.W0 * cp[a]);
             else ddA[a].step((double)p.W0 * cp[a], (R)1 + er);
@@ -715,8 +702,8 @@ struct Trial {
         if (EXACT) {
           cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
           if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
-        } else if (!FAST && p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
-        if (!FAST && p.bench_tlt) {
+        } else if (p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
+        if (p.bench_tlt) {
           if (EXACT) {
             if (i == 0) ddT.init((double)p.W0 * cp_tlt);
             else ddT.step((double)p.W0 * cp_tlt, (R)1 + tlt);

@@ -40,22 +40,22 @@ struct FastLayers {
     }
     const R vix = p.const_vix;
     const R vrmult = clipx(M::sqrt_(vix * 0.05f), 0.5f, 1.5f) * 1.0f;      // regime 0 (engine.py:178-181)
-    uint32_t streams[NA + 1];
-    streams[0] = STREAM_MKT0;
+    uint32_t streams[NA];
 #pragma unroll
-    for (int a = 0; a < NA; a++) streams[a + 1] = STREAM_TE0 + (uint32_t)p.act_id[a];
+    for (int a = 0; a < NA; a++) streams[a] = STREAM_TE0 + (uint32_t)p.act_id[a];
     const R alpha = (R)(2.0 / 127.0);
 
-    for (int i = 0; i < T; i++) {
-      U4 blk[U][NA + 1];
+    // one simulated day of all U trials; (wa, wb) = the two market words of the day
+    auto day = [&](const int i, const uint32_t (&wa)[U], const uint32_t (&wb)[U]) {
+      U4 blk[U][NA];
 #pragma unroll
-      for (int u = 0; u < U; u++) rng_blocks<NA + 1>(key[u], (uint32_t)i, streams, blk[u]);
+      for (int u = 0; u < U; u++) rng_blocks<NA>(key[u], (uint32_t)i, streams, blk[u]);
       const R vrlive = i >= 1 ? vrmult : 0.0f;          // no tracking error on day 0 (engine.py:184)
       R spy[U], qqq[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         R z0, z1;
-        M::box_muller(blk[u][0].x, blk[u][0].y, z0, z1);
+        M::box_muller(wa[u], wb[u], z0, z1);
         spy[u] = p.n_mu[0] + p.n_ch[0] * z0;
         qqq[u] = p.n_mu[1] + (p.n_ch[1] * z0 + p.n_ch[2] * z1);
         chk[u] = fmaf(spy[u], 0.0f, chk[u]); chk[u] = fmaf(qqq[u], 0.0f, chk[u]);
@@ -67,7 +67,7 @@ struct FastLayers {
         for (int u = 0; u < U; u++) {
           const R un = fmaf(ap.w_spy, spy[u], ap.w_qqq * qqq[u]);
           const R lev = ap.lev * un - ap.carry_const;
-          const R innov = student_t5<R>(blk[u][a + 1]);
+          const R innov = student_t5<R>(blk[u][a]);
           const R ds = un < 0.0f ? ap.te_down : 0.98f;
           const R mm = (1.0f + 0.3f * fabsf(un)) * ds;
           const R te_raw = ap.te_rho * te_prev[u][a] + (innov * vrlive) * (ap.te_scale * mm);
@@ -79,6 +79,25 @@ struct FastLayers {
           qmin[u][a] = fminf(qmin[u][a], q[u][a]);
         }
       }
+    };
+
+    // days 2j and 2j+1 share the market block (j, STREAM_MKT_PAIR): words x,y then z,w (letf_core.cuh market_day)
+    int i = 0;
+    for (; i + 1 < T; i += 2) {
+      uint32_t w0[U], w1[U], w2[U], w3[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const U4 bp = rng_block(key[u], (uint32_t)i >> 1, STREAM_MKT_PAIR);
+        w0[u] = bp.x; w1[u] = bp.y; w2[u] = bp.z; w3[u] = bp.w;
+      }
+      day(i, w0, w1);
+      day(i + 1, w2, w3);
+    }
+    if (i < T) {
+      uint32_t w0[U], w1[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { const U4 bp = rng_block(key[u], (uint32_t)i >> 1, STREAM_MKT_PAIR); w0[u] = bp.x; w1[u] = bp.y; }
+      day(i, w0, w1);
     }
 
     // per-trial outputs (engine.py:578-603); validity as in run_t: constant VIX, sticky non-finite / exhausted products

@@ -56,7 +56,8 @@ LETF_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 // stream tags (counter word 3 = tag << 8 | sub-block)
 enum : uint32_t {
   STREAM_START = 1, STREAM_SPELL = 2, STREAM_MKT0 = 3, STREAM_MKT1 = 4, STREAM_STRESS = 5,
-  STREAM_JUMP = 6, STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T */
+  STREAM_JUMP = 6, STREAM_MKT_PAIR = 7 /* iid-normal market: one block per two days */,
+  STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T */
 };
 
 struct RngKey {

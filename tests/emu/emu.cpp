@@ -59,7 +59,7 @@ extern "C" int letf_emu_run(const LetfParams* sp, int precision, const LetfTape*
 
 // the lean buy&hold build (compacted asset slots, loop-unswitched FAST day step), Philox only
 extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n,
-                                 int* used_fast, int two_per_thread) {
+                                 int* used_fast, int two_per_thread, int force_generic) {
   if (validate_params(*sp) || sp->market_mode != LETF_MARKET_NORMAL) return -1;
   constexpr int NS = 4, NA = 3;
   constexpr uint32_t TMB = (1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT);
@@ -71,12 +71,20 @@ extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, u
   ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
   ka.log_trial = -1;
   if (used_fast) *used_fast = ka.p.fast_layers;
-  if (two_per_thread && ka.p.fast_layers) {
+  if (two_per_thread && ka.p.fast_layers && !force_generic) {
     // the launch form of the fast path: two interleaved trials per thread (letf_fast.cuh), incl. an odd tail
     for (int64_t j = 0; j < n; j += 2) {
       int64_t trial[2] = {first + j, first + (j + 1 < n ? j + 1 : j)}, col[2] = {j, j + 1 < n ? j + 1 : j};
       bool live[2] = {true, j + 1 < n};
       FastLayers<NS, NA, 2>::run(ka, trial, col, live);
+    }
+    return 0;
+  }
+  if (ka.p.fast_layers && !two_per_thread && !force_generic) {
+    for (int64_t j = 0; j < n; j++) {
+      int64_t trial[1] = {first + j}, col[1] = {j};
+      bool live[1] = {true};
+      FastLayers<NS, NA, 1>::run(ka, trial, col, live);
     }
     return 0;
   }

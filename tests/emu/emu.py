@@ -38,7 +38,7 @@ def lib():
                                   [C.c_void_p] * 6
         L.letf_emu_run.restype = C.c_int
         L.letf_emu_run_lean.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64,
-                                        C.POINTER(C.c_int), C.c_int]
+                                        C.POINTER(C.c_int), C.c_int, C.c_int]
         L.letf_emu_run_lean.restype = C.c_int
         L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_typed.restype = C.c_int
@@ -68,13 +68,14 @@ def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, fir
     return out
 
 
-def run_lean(params, n, seed=0, first=0, two_per_thread=False):
+def run_lean(params, n, seed=0, first=0, two_per_thread=False, force_generic=False):
     """lean buy&hold build (NA = 3 compacted slots); returns (outputs, used_fast_variant).
-    two_per_thread: the launch form of the fast path (letf_fast.cuh) instead of Trial::run_t<FAST>"""
+    default: the straight-line fast path (letf_fast.cuh) with one trial per call when the shape admits it;
+    two_per_thread: its launch form; force_generic: the lean build's general loop (Trial::run)"""
     out = HostOutputs(params.n_strategies, n)
     fast = C.c_int(0)
     rc = lib().letf_emu_run_lean(C.byref(params), C.byref(out.as_struct()), seed, first, n, C.byref(fast),
-                                 1 if two_per_thread else 0)
+                                 1 if two_per_thread else 0, 1 if force_generic else 0)
     if rc != 0:
         raise RuntimeError(f"emu lean rc={rc}")
     return out, bool(fast.value)

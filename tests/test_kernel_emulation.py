@@ -163,7 +163,10 @@ def test_lean_fast_variant_matches_generic_build():
     np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=2e-5)
     np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=2e-6)
     np.testing.assert_array_equal(lean.flags, gen.flags)
-    # the launch form (two interleaved trials per thread, odd tail) computes the same thing as run_t<FAST>
+    # the lean build's general loop (what runs when the shape is not admitted) on the same counters
+    slow, _ = emu.run_lean(params, 64, seed=77, force_generic=True)
+    np.testing.assert_allclose(lean.final_wealth, slow.final_wealth, rtol=2e-5)
+    # the launch form (two interleaved trials per thread, odd tail) computes the same thing
     two, fast2 = emu.run_lean(params, 63, seed=77, two_per_thread=True)
     assert fast2
     np.testing.assert_allclose(two.final_wealth, lean.final_wealth[:, :63], rtol=1e-6)
