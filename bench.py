@@ -43,6 +43,10 @@ WORKLOADS = {
                trials=1_000_000, years=30, lane_ops=520 * (7560 + 1260) / 7560, mufu=22),
     "c4": dict(desc="BASELINE configs[3]: C3 market + TQQQ/TMF/SPY layers, S1 S2 S4 S5 S6 S19, per GPU 1.25M trials x 7560 days",
                trials=1_250_000, years=30, lane_ops=1130, mufu=40),
+    "c5": dict(desc="BASELINE configs[4]: horizon/leverage grid, L = 3 / 2 / 1 (UPRO / SSO / SPY) on one SPY-like underlying, horizons "
+                    "1 2 5 10 20 30 40 y, 4.762M trials per horizon and GPU, per-cell wealth / CAGR / max-drawdown histograms + moments "
+                    "reduced on device and allreduced",
+               trials=4_762_000, years=None, lane_ops=400, mufu=12, horizons=[1, 2, 5, 10, 20, 30, 40]),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "200k trials x 7560 days per GPU",
                     trials=200_000, years=30, lane_ops=2600, mufu=60),
@@ -65,6 +69,13 @@ def build_workload(name):
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
         sids = ["S1", "S2", "S4", "S5", "S6", "S19"]
         model = synthetic.fallback_regime_model("default")
+    elif name == "c5":
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                        USE_ANTITHETIC_VARIATES=False)
+        sids = ["B_UPRO", "S3", "S2"]
+        model = synthetic.normal_regime_model("c2")
+        params, keep = build_params(sids, 40, model, ns)
+        return ns, model, sids, params, keep
     elif name == "sweep19":
         ns = synthetic.config_namespace()
         sids = ["S%d" % i for i in range(1, 20)]
@@ -337,6 +348,92 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_c5(args):
+    """BASELINE configs[4]: a step = one evaluation of the whole horizon/leverage grid (7 launches, 7 on-device
+    reductions, per-cell summary allreduce); only histograms / moments / counters ever leave the device."""
+    import torch
+    import torch.distributed as dist
+    from letf_monte_carlo_b200.grid import HorizonGrid
+
+    rank = int(os.environ.get("RANK", "0")); ws = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ns, model, sids, params, keep = build_workload("c5")
+    wl = WORKLOADS["c5"]
+    n = int(args.trials or wl["trials"])
+    grid = HorizonGrid(wl["horizons"], sids, model, ns, precision=args.precision, device=local)
+    path_days = grid.path_days(n)                      # per GPU and step
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        grid.run(n * ws, seed=args.seed)
+    barrier()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start(); time.sleep(0.25)
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = grid.launches
+    barrier()
+    t0e.record()
+    for _ in range(args.steps):
+        grid.run(n * ws, seed=args.seed)
+    t1e.record()
+    barrier()
+    total_ms = t0e.elapsed_time(t1e)
+    launches = grid.launches - l0
+    clocks = clk.stop() if rank == 0 else None
+    # end to end: the grid evaluated and its summary table read on the host
+    barrier()
+    t0 = time.perf_counter()
+    rows = grid.run(n * ws, seed=args.seed + 1).table()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    d2h = sum(int(sm.hist.numel() * 8 + sm.counters.numel() * 8 + sm.moments.numel() * 8) for sm in grid.summaries)
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = (float(x) for x in t.cpu())
+    if rank == 0:
+        pk = peaks()
+        ms = total_ms / args.steps
+        peak_lane = 148 * 128 * pk["sm_max_mhz"] * 1e6 / 1e12
+        achieved = path_days * wl["lane_ops"] / (ms * 1e-3) / 1e12
+        med30 = [r for r in rows if r["horizon"] == 30.0]
+        line = {"metric": METRIC, "value": ws * path_days / (ms * 1e-3), "unit": UNIT, "n_gpus": ws, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"c5: {wl['desc']}", "trials_per_horizon_per_gpu": n, "horizons_years": wl["horizons"],
+                           "strategies": sids, "path_days_per_gpu_step": path_days,
+                           "l2": "outputs of each launch (>= 95 MB) exceed nothing the next launch reads; the path kernels read no HBM inputs"},
+                "clocks": clocks,
+                "e2e": {"value": ws * path_days / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 7 * ctypes.sizeof(type(params)),
+                        "d2h_bytes_per_step": d2h, "api": "letf_monte_carlo_b200.grid.HorizonGrid.run(...).table()",
+                        "median_wealth_30y": {r["id"]: r["p50"] for r in med30}},
+                "gpu_launches": launches + 14,
+                "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
+                             "traffic": None, "kernel": "letf_path_kernel (7 launches) + letf_reduce_kernel",
+                             "lane_ops_per_path_day": wl["lane_ops"], "units_per_launch": path_days,
+                             "note": "whole-step time (reductions included), not a single launch"}}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    grid.close()
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,6 +449,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_b200(args)
 

@@ -159,7 +159,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   // all waves are full (equal-length trials: a partial last wave costs a whole trial time).  A work item is
   // one trial, or `upt` interleaved trials in the straight-line fast path (letf_fast.cuh).
   const int kBlock = ke->block;
-  const int upt = (ke->upt > 1 && ka.p.fast_layers && rng_mode == LETF_RNG_PHILOX && !series) ? ke->upt : 1;
+  const int upt = (ke->upt > 1 && fast_pattern_compiled<NA>(ka.p.fast_layers) && rng_mode == LETF_RNG_PHILOX && !series) ? ke->upt : 1;
   const int64_t items = (n + upt - 1) / upt;
   const int64_t resident = (int64_t)e->sm_count * max_blocks * kBlock;
   const int64_t waves = (items + resident - 1) / resident;

@@ -13,7 +13,8 @@
 
 namespace letf {
 
-template <int NS, int NA, int U>
+// K10: bitmask of the slots whose tracking-error innovations are t(10) (the others are t(5))
+template <int NS, int NA, int U, int K10 = 0>
 struct FastLayers {
   typedef float R;
   typedef Mth<float> M;
@@ -67,7 +68,7 @@ struct FastLayers {
         for (int u = 0; u < U; u++) {
           const R un = fmaf(ap.w_spy, spy[u], ap.w_qqq * qqq[u]);
           const R lev = ap.lev * un - ap.carry_const;
-          const R innov = student_t5<R>(blk[u][a]);
+          const R innov = ((K10 >> a) & 1) ? student_t10<R>(blk[u][a]) : student_t5<R>(blk[u][a]);
           const R ds = un < 0.0f ? ap.te_down : 0.98f;
           const R mm = (1.0f + 0.3f * fabsf(un)) * ds;
           const R te_raw = ap.te_rho * te_prev[u][a] + (innov * vrlive) * (ap.te_scale * mm);
@@ -130,5 +131,16 @@ struct FastLayers {
     }
   }
 };
+
+// DevParams::fast_layers codes with a compiled-in straight-line loop: all t(5) (BASELINE config 2) and
+// "last slot t(10)" (config 5: UPRO / SSO / SPY).  Any other admitted pattern runs the general loop.
+template <int NA> LETF_HD constexpr bool fast_pattern_compiled(int code) { return code == 1 || code == 1 + (1 << (NA - 1)); }
+
+template <int NS, int NA, int U>
+LETF_HD void fast_layers_run(const KArgs<float, NS, NA>& ka, const int64_t (&trial)[U], const int64_t (&col)[U],
+                             const bool (&live)[U]) {
+  if (ka.p.fast_layers == 1) FastLayers<NS, NA, U, 0>::run(ka, trial, col, live);
+  else FastLayers<NS, NA, U, 1 << (NA - 1)>::run(ka, trial, col, live);
+}
 
 }  // namespace letf

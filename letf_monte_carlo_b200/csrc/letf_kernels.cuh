@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int UPT = fast_upt<R, NA, MARKET, TAPEIO>();
   if constexpr (UPT > 1) {
-    if (ka.p.fast_layers && ka.rng_mode == LETF_RNG_PHILOX) {     // host sized the grid for ceil(n / UPT) threads
+    if (fast_pattern_compiled<NA>(ka.p.fast_layers) && ka.rng_mode == LETF_RNG_PHILOX) {   // grid sized for ceil(n / UPT) threads
       for (int64_t j = lane; j < ka.n_trials; j += (int64_t)UPT * ka.nthreads) {
         int64_t trial[UPT], col[UPT];
         bool live[UPT];
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
           if (!live[u]) col[u] = j;                   // padding lane recomputes trial j and stores nothing
           trial[u] = ka.first_trial + col[u];
         }
-        FastLayers<NS, NA, UPT>::run(ka, trial, col, live);
+        fast_layers_run<NS, NA, UPT>(ka, trial, col, live);
       }
       return;
     }

@@ -305,11 +305,32 @@ LETF_HD R student_t5(const U4& b) {
   return cs * (x5 * M::rsqrt_(rmax(x5 * c2, (R)1e-30)));
 }
 
+// Student-t(10), straight-line (cfg.ASSETS default for the unlevered SPY / QQQ series): chi2(10) = -2 ln of
+// five uniforms (12 bits each, cut from two words exactly as chi2_int_fast does), no N1^2 term:
+//   t = cos * sqrt(10 L / c2) = cos * (10 L) * rsqrt(10 L * c2)
+template <typename R>
+LETF_HD R student_t10(const U4& b) {
+  typedef Mth<R> M;
+  const uint32_t wa = b.z, wb = b.w;
+  R prod = M::u01_12(wa >> 20) * M::u01_12((wa >> 8) & 0xFFFu) * M::u01_12(wb >> 20) *
+           M::u01_12((wb >> 8) & 0xFFFu) * M::u01_12(((wa & 0xFFu) << 4) | (wb & 0xFu));
+  if (sizeof(R) == 8) {
+    R n0, n1;
+    M::box_muller(b.x, b.y, n0, n1);
+    return n0 * M::sqrt_(M::div_((R)10, rmax((R)-2 * M::log_(prod), (R)1e-30)));
+  }
+  R cs;
+  R L = M::bm_cos(b.x, b.y, cs);
+  R x10 = (R)10 * L;
+  return cs * (x10 * M::rsqrt_(rmax(x10 * M::neg2log_(prod), (R)1e-30)));
+}
+
 // Student-t(df) from one Philox block: N0 / sqrt(chi2(df) / df).
 template <typename R>
 LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
   if (sizeof(R) == 4 && fast_k == 5) return student_t5<R>(b);
+  if (sizeof(R) == 4 && fast_k == 10) return student_t10<R>(b);
   R n0, n1;
   M::box_muller(b.x, b.y, n0, n1);
   R c2 = fast_k ? chi2_int_fast<R>(fast_k, b.z, b.w, n1)

@@ -43,7 +43,8 @@ template <typename R, int NS, int NA> struct DevParams {
   int market_mode, T, buffer, random_start, min_offset, offset_range, antithetic, mm, institutional,
       has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset,
       bench_mask /* assets tracked for a buy&hold strategy */, bench_tlt, need_tlt,
-      fast_layers /* every slot active, t(5) tracking error, no tanh cap, no TLT: straight-line day step */, pad_f;
+      fast_layers /* 0, or 1 + bitmask of the slots whose tracking error is t(10) (others t(5)): every slot active,
+                     no tanh cap, no funding model, no TLT series -> straight-line day step (letf_fast.cuh) */, pad_f;
   R W0, sim_years;
   int flip[2];
   R log_pstay[2];
@@ -212,7 +213,8 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
   d.n_act = 0;
   for (int a = 0; a < kAssets; a++) {
     const bool on = (s.asset_mask >> a) & 1;
-    if (on && (d.assets[a].te_fast_k != 5 || d.assets[a].te_clip > (R)0 || !((d.bench_mask >> a) & 1))) d.fast_layers = 0;
+    if (on && ((d.assets[a].te_fast_k != 5 && d.assets[a].te_fast_k != 10) || d.assets[a].te_clip > (R)0 ||
+               !((d.bench_mask >> a) & 1))) d.fast_layers = 0;
     if (NA == kAssets) {
       d.act[a] = d.assets[a]; d.act_id[a] = a; d.act_on[a] = on; d.act_bench[a] = (d.bench_mask >> a) & 1;
       d.n_act = kAssets;
@@ -222,6 +224,7 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     }
   }
   if (d.n_act != NA) d.fast_layers = 0;
+  if (d.fast_layers) for (int j = 0; j < NA; j++) if (d.act[j].te_fast_k == 10) d.fast_layers += 1 << j;
 }
 #endif  // LETF_DEVICE_ONLY
 

@@ -70,21 +70,22 @@ extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, u
   convert_params<float, NS, NA>(*sp, dd, ka.p);
   ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
   ka.log_trial = -1;
-  if (used_fast) *used_fast = ka.p.fast_layers;
-  if (two_per_thread && ka.p.fast_layers && !force_generic) {
+  const bool fast_ok = fast_pattern_compiled<NA>(ka.p.fast_layers);
+  if (used_fast) *used_fast = fast_ok ? ka.p.fast_layers : 0;
+  if (two_per_thread && fast_ok && !force_generic) {
     // the launch form of the fast path: two interleaved trials per thread (letf_fast.cuh), incl. an odd tail
     for (int64_t j = 0; j < n; j += 2) {
       int64_t trial[2] = {first + j, first + (j + 1 < n ? j + 1 : j)}, col[2] = {j, j + 1 < n ? j + 1 : j};
       bool live[2] = {true, j + 1 < n};
-      FastLayers<NS, NA, 2>::run(ka, trial, col, live);
+      fast_layers_run<NS, NA, 2>(ka, trial, col, live);
     }
     return 0;
   }
-  if (ka.p.fast_layers && !two_per_thread && !force_generic) {
+  if (fast_ok && !two_per_thread && !force_generic) {
     for (int64_t j = 0; j < n; j++) {
       int64_t trial[1] = {first + j}, col[1] = {j};
       bool live[1] = {true};
-      FastLayers<NS, NA, 1>::run(ka, trial, col, live);
+      fast_layers_run<NS, NA, 1>(ka, trial, col, live);
     }
     return 0;
   }

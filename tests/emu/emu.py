@@ -78,7 +78,7 @@ def run_lean(params, n, seed=0, first=0, two_per_thread=False, force_generic=Fal
                                  1 if two_per_thread else 0, 1 if force_generic else 0)
     if rc != 0:
         raise RuntimeError(f"emu lean rc={rc}")
-    return out, bool(fast.value)
+    return out, int(fast.value)
 
 
 def run_typed(params, slot_list, n, seed=0, first=0):

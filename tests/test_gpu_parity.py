@@ -428,3 +428,36 @@ def test_edge_sizes_and_offsets(engine_lib):
     np.testing.assert_array_equal(a.final_wealth[:, 500:564], c.final_wealth)
     np.testing.assert_array_equal(a.max_dd[:, 500:564], c.max_dd)
     assert (a.flags == 0).all() and (a.regime_days[0] == p2.sim_days).all()
+
+
+def test_horizon_leverage_grid_config5(engine_lib):
+    """BASELINE configs[4] shape at a small size: per-cell histogram quantiles (device reduction) agree with exact
+    percentiles of the per-trial outputs, the vol-drag ordering holds, and the straight-line t(5)/t(10) loop ran."""
+    from letf_monte_carlo_b200.grid import HorizonGrid
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False)
+    sids = ["B_UPRO", "S3", "S2"]
+    model = synthetic.normal_regime_model("c2")
+    grid = HorizonGrid([1, 5, 10], sids, model, ns, precision="f32", device=0)
+    n = 20000
+    rows = grid.run(n, seed=4).table()
+    assert len(rows) == 9 and all(r["valid"] == n for r in rows)
+    assert grid.engines[0].launch_info()["regs_per_thread"] > 128          # the two-trials-per-thread build
+    for h, eng in zip(grid.horizons, grid.engines):
+        exact = eng.run_host(n, seed=4)
+        for s, sid in enumerate(sids):
+            row = next(r for r in rows if r["horizon"] == h and r["id"] == sid)
+            for q in (10, 50, 90):
+                want = np.percentile(exact.final_wealth[s], q)
+                assert abs(np.log10(row[f"p{q}"] / want)) < 2 * 30 / 4096, (h, sid, q)
+            assert abs(row["dd_median"] - np.median(exact.max_dd[s])) < 2 / 4096
+    # mean log-growth per day against the closed form L mu - costs - (L sigma)^2 / 2 (second order in the drift)
+    g = {(r["horizon"], r["id"]): r["mean_log10_growth"] * np.log(10) / (252 * r["horizon"]) for r in rows}
+    vol, mu = 0.16 / np.sqrt(252), 0.08 / 252
+    for sid, a in (("B_UPRO", "UPRO"), ("S3", "SSO"), ("S2", "SPY")):
+        c = ns.ASSETS[a]; L = c["leverage"]
+        m = L * mu - c["expense_ratio"] / 252 - (L - 1) * (0.045 + c["borrow_spread"]) / 252
+        want = m - 0.5 * (L * vol) ** 2 - 0.5 * m * m
+        se = L * vol / np.sqrt(2520 * n)
+        assert abs(g[(10.0, sid)] - want) < 5 * se + 2e-6, (sid, g[(10.0, sid)], want)
+    grid.close()

@@ -212,3 +212,17 @@ def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
     np.testing.assert_array_equal(typed.num_trades, gen.num_trades)
     np.testing.assert_array_equal(typed.flags, gen.flags)
     np.testing.assert_array_equal(typed.regime_days, gen.regime_days)
+
+
+def test_lean_fast_variant_config5_shape():
+    """BASELINE config 5 cell: L = 3 / 2 / 1 on one SPY-like underlying (UPRO, SSO, SPY rows of cfg.ASSETS;
+    SPY's tracking error is t(10)) -> the "last slot t(10)" straight-line loop against the general loop"""
+    sids = ["B_UPRO", "S3", "S2"]
+    params, keep = _c2_params(sids, years=2)
+    fast, code = emu.run_lean(params, 33, seed=3)
+    assert code == 1 + 4                       # slots UPRO, SSO, SPY: third one is t(10)
+    two, _ = emu.run_lean(params, 33, seed=3, two_per_thread=True)
+    slow, _ = emu.run_lean(params, 33, seed=3, force_generic=True)
+    np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-5)
+    np.testing.assert_allclose(two.final_wealth, fast.final_wealth, rtol=1e-6)
+    np.testing.assert_allclose(fast.max_dd, slow.max_dd, atol=2e-6)
