@@ -120,7 +120,12 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (k->precision != e->precision || k->market != market) continue;
     if (need_io && !k->tapeio) continue;
     if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
-    if (k->am && k->am != e->params.asset_mask) continue;
+    if (k->am) {        // compile-time asset mask: same series, default tracking-error dof (config.py:62-135)
+      bool ok = k->am == e->params.asset_mask;
+      for (int a = 0; ok && a < kAssets; a++)
+        if ((k->am >> a) & 1) ok = df_fast_k(e->params.assets[a].te_df) == (a >= 4 ? 10 : 5);
+      if (!ok) continue;
+    }
     if (k->list) {      // typed slots: the strategy list must be exactly the one compiled in
       bool same = slot_list_count(k->list) == n_strat;
       for (int s = 0; same && s < n_strat; s++) {
