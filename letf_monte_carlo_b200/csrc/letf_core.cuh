@@ -321,6 +321,15 @@ struct Trial {
         const R bl = (R)0.10;
         for (int a = 0; a < 3; a++) js.h[a] = bl * jp.lv[a] + ((R)1 - bl) * js.h[a];
         for (int a = 0; a < 6; a++) js.q[a] = bl * jp.rb[a] + ((R)1 - bl) * js.q[a];
+      } else if (!EXACT) {
+        // same recursions with the per-regime constants folded on the host: 3 operations per element
+        for (int a = 0; a < 3; a++) js.h[a] = rmax(M::fma_(js.h[a], M::fma_(jp.alpha, js.pz[a] * js.pz[a], jp.beta), jp.c0[a]), (R)1e-10);
+        js.q[0] = M::fma_(jp.dcc_b, js.q[0], M::fma_(jp.dcc_a, js.pz[0] * js.pz[0], jp.c1[0]));
+        js.q[1] = M::fma_(jp.dcc_b, js.q[1], M::fma_(jp.dcc_a, js.pz[1] * js.pz[0], jp.c1[1]));
+        js.q[2] = M::fma_(jp.dcc_b, js.q[2], M::fma_(jp.dcc_a, js.pz[1] * js.pz[1], jp.c1[2]));
+        js.q[3] = M::fma_(jp.dcc_b, js.q[3], M::fma_(jp.dcc_a, js.pz[2] * js.pz[0], jp.c1[3]));
+        js.q[4] = M::fma_(jp.dcc_b, js.q[4], M::fma_(jp.dcc_a, js.pz[2] * js.pz[1], jp.c1[4]));
+        js.q[5] = M::fma_(jp.dcc_b, js.q[5], M::fma_(jp.dcc_a, js.pz[2] * js.pz[2], jp.c1[5]));
       } else {
         for (int a = 0; a < 3; a++) {
           R hn = jp.one_m_ab * jp.lv[a] + jp.alpha * (js.pz[a] * js.pz[a]) * js.h[a] + jp.beta * js.h[a];
@@ -335,7 +344,13 @@ struct Trial {
       }
       js.prev_reg = reg;
       R zz[3];
-      R sh0 = M::sqrt_(js.h[0]), sh1 = M::sqrt_(js.h[1]), sh2 = M::sqrt_(js.h[2]);
+      R ih[3] = {(R)0, (R)0, (R)0};      // fp32: 1 / sqrt(max(h, 1e-10)), shared by the factor and by prev_z
+      R sh0, sh1, sh2;
+      if (EXACT) { sh0 = M::sqrt_(js.h[0]); sh1 = M::sqrt_(js.h[1]); sh2 = M::sqrt_(js.h[2]); }
+      else {
+        for (int a = 0; a < 3; a++) ih[a] = M::rsqrt_(rmax(js.h[a], (R)1e-10));
+        sh0 = js.h[0] * ih[0]; sh1 = js.h[1] * ih[1]; sh2 = js.h[2] * ih[2];
+      }
       if (EXACT) {
         // cov_t = outer(sqrt h) * Q / outer(d, d), then its Cholesky factor (calibration.py:556-561)
         R d0 = M::sqrt_(rmax(js.q[0], (R)1e-12)), d1 = M::sqrt_(rmax(js.q[2], (R)1e-12)), d2 = M::sqrt_(rmax(js.q[5], (R)1e-12));
@@ -352,19 +367,21 @@ struct Trial {
         // same factor written as diag(sqrt h) * chol(R_t) with R_t unit-diagonal: fewer operations
         R i0 = M::rsqrt_(rmax(js.q[0], (R)1e-12)), i1 = M::rsqrt_(rmax(js.q[2], (R)1e-12)), i2 = M::rsqrt_(rmax(js.q[5], (R)1e-12));
         R r10 = js.q[1] * i1 * i0, r20 = js.q[3] * i2 * i0, r21 = js.q[4] * i2 * i1;
-        R l11 = M::sqrt_(rmax((R)1 - r10 * r10, (R)0));
-        R l21 = M::div_(r21 - r20 * r10, rmax(l11, (R)1e-20));
+        const R s11 = rmax((R)1 - r10 * r10, (R)0);
+        const R il11 = M::rsqrt_(rmax(s11, (R)1e-30));
+        R l11 = s11 * il11;                                        // sqrt(s11)
+        R l21 = (r21 - r20 * r10) * il11;
         R l22 = M::sqrt_(rmax((R)1 - r20 * r20 - l21 * l21, (R)0));
         zz[0] = sh0 * z0;
         zz[1] = sh1 * (r10 * z0 + l11 * z1);
         zz[2] = sh2 * (r20 * z0 + l21 * z1 + l22 * z2);
       }
       if (anti) { zz[0] = -zz[0]; zz[1] = -zz[1]; zz[2] = -zz[2]; }
-      R scale = M::sqrt_(M::div_(jp.nu, rmax(u, (R)1e-12)));
+      R scale = EXACT ? M::sqrt_(M::div_(jp.nu, rmax(u, (R)1e-12))) : jp.sqrt_nu * M::rsqrt_(rmax(u, (R)1e-12));
       for (int a = 0; a < 3; a++) {
         R xx = jp.mu[a] + zz[a] * scale;
         R xc = clipr(xx, (R)-0.95, (R)4.0);
-        js.pz[a] = EXACT ? (xc - jp.mu[a]) / M::sqrt_(rmax(js.h[a], (R)1e-10)) : (xc - jp.mu[a]) * M::rsqrt_(rmax(js.h[a], (R)1e-10));
+        js.pz[a] = EXACT ? (xc - jp.mu[a]) / M::sqrt_(rmax(js.h[a], (R)1e-10)) : (xc - jp.mu[a]) * ih[a];
         x[a] = xc;
       }
     }

@@ -27,6 +27,8 @@ template <typename R> struct DevJoint {
   R mu[3], lv[3];
   R rb[6];            // lower triangle of nearest_psd(corr): 00 10 11 20 21 22
   R nu, alpha, beta, one_m_ab, dcc_a, dcc_b, one_m_dcc;
+  // fp32 fast path: (1 - alpha - beta) * lv[a], (1 - dcc_a - dcc_b) * rbar[k], sqrt(nu) folded once per regime
+  R c0[3], c1[6], sqrt_nu;
   int nu_fast_k, pad;
 };
 
@@ -153,6 +155,9 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     q.nu = (R)nu; q.alpha = (R)alpha; q.beta = (R)beta; q.one_m_ab = (R)(1 - alpha - beta);
     q.dcc_a = (R)j.dcc_a; q.dcc_b = (R)j.dcc_b; q.one_m_dcc = (R)(1 - j.dcc_a - j.dcc_b);
     q.nu_fast_k = df_fast_k(nu);
+    for (int a = 0; a < 3; a++) q.c0[a] = (R)((1 - alpha - beta) * (double)q.lv[a]);
+    for (int a = 0; a < 6; a++) q.c1[a] = (R)((1 - j.dcc_a - j.dcc_b) * (double)q.rb[a]);
+    q.sqrt_nu = (R)::sqrt(nu);
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) d.pt_chol[r][a * 3 + b] = (R)s.param_t_chol[r][a][b];
     const LetfVixRegime& v = s.vix[r];
     d.vix[r].phi = (R)v.phi; d.vix[r].drift = (R)((1 - v.phi) * v.target); d.vix[r].noise_std = (R)v.noise_std;
