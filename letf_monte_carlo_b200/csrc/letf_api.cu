@@ -186,7 +186,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
   if (ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching && G > 0) {
-    size_t b = (size_t)G * 4 * (size_t)nthreads * sizeof(R);
+    size_t b = ((size_t)G * 4 + (size_t)((G + 3) & ~3)) * (size_t)nthreads * sizeof(R);   // day vectors + the IRX-normal column (letf_core.cuh AUXSCR)
     cudaError_t ce = e->xscr.reserve(b);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
     ka.xscr = (R*)e->xscr.p; scratch += b;

@@ -461,6 +461,14 @@ struct Trial {
     // ---- pass 1 (moment matching only): raw joint returns -> scratch, column means (calibration.py:579-588)
     struct alignas(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) X4 { R x, y, z, w; };
     X4* const xs = (X4*)ka.xscr + (int64_t)lane * (p.T + p.buffer);
+    // Philox-only fp32 builds: pass 1 already holds the day's second market block (its z,w words feed the chi-square),
+    // so it also turns the x,y words into the VIX / IRX normals and keeps them (w word of the day's vector + a second
+    // per-thread column behind the vectors); pass 2 and the burn-in then draw no market block at all
+    constexpr bool AUXSCR = !EXACT && !TAPEIO && MARKET == LETF_MARKET_JOINT_T && LIST != 2;   // (the 19-rule build has no registers to spare)
+    // (the column is written four days at a time from registers: 4-byte stores would each dirty a sector of their own
+    //  and come back from L2 as read-modify-write traffic; its per-thread stride is G rounded up to a multiple of 4)
+    const int Gp = (p.T + p.buffer + 3) & ~3;
+    R* const is = (R*)ka.xscr + (int64_t)4 * (p.T + p.buffer) * ka.nthreads + (int64_t)lane * Gp;
     R shift[3] = {(R)0, (R)0, (R)0};
     const bool two_pass = MARKET == LETF_MARKET_JOINT_T && p.mm;
     const int T = MARKET == kMarketSeries ? ka.series.sim_days : p.T;
@@ -471,16 +479,26 @@ struct Trial {
     if (two_pass && G > 0) {
       RegimeGen rg; regime_init(rg);
       R sum[3] = {0, 0, 0}, cmp[3] = {0, 0, 0};
+      X4 ib; ib.x = ib.y = ib.z = ib.w = (R)0;
       for (int g = 0; g < G; g++) {
         int reg = regime_next(rg);
-        R x[3], d0, d1;
-        market_day<true, false>(g, reg, js, x, d0, d1);
-        X4 v; v.x = x[0]; v.y = x[1]; v.z = x[2]; v.w = (R)0;
+        R x[3], d0 = 0, d1 = 0;
+        if (AUXSCR) market_day<true, true>(g, reg, js, x, d0, d1);
+        else market_day<true, false>(g, reg, js, x, d0, d1);
+        X4 v; v.x = x[0]; v.y = x[1]; v.z = x[2]; v.w = d0;
         xs[g] = v;
+        if (AUXSCR) {
+          ib.x = ib.y; ib.y = ib.z; ib.z = ib.w; ib.w = d1;
+          if ((g & 3) == 3) *(X4*)(is + (g - 3)) = ib;
+        }
         for (int a = 0; a < 3; a++) {
           R y = x[a] - cmp[a], t = sum[a] + y;      // Kahan: stays within an ulp of numpy's pairwise mean
           cmp[a] = (t - sum[a]) - y; sum[a] = t;
         }
+      }
+      if (AUXSCR && (G & 3)) {          // the last G % 4 days: shift them to the front of a final, padded vector
+        for (int r = G & 3; r < 4; r++) { ib.x = ib.y; ib.y = ib.z; ib.z = ib.w; ib.w = (R)0; }
+        *(X4*)(is + (G & ~3)) = ib;
       }
       for (int a = 0; a < 3; a++) shift[a] = (p.mm_theo[a] - sum[a] / (R)G) * (R)0.1;
     }
@@ -524,7 +542,10 @@ struct Trial {
     for (int g = 0; g < so; g++) {
       int reg = regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
-      if (two_pass) {
+      if (two_pass && AUXSCR) {
+        const X4 v = xs[g];
+        x[0] = v.x + shift[0]; vn = v.w;
+      } else if (two_pass) {
         market_day<false, true>(g, reg, js, x, vn, in);
         x[0] = xs[g].x + shift[0];
       } else {
@@ -537,12 +558,14 @@ struct Trial {
     // software prefetch: the scratch vector of day g + 1 and the ring entries this day retires are requested at the
     // top of the day, a whole day step ahead of their use (the loads are otherwise a fully exposed L2 round trip)
     X4 vnext; vnext.x = vnext.y = vnext.z = vnext.w = (R)0;
-    if (two_pass && T > 0) vnext = xs[so];
+    R inext = (R)0;
+    if (two_pass && T > 0) { vnext = xs[so]; if (AUXSCR) inext = is[so]; }
     for (int i = 0; i < T; i++) {
       const int g = so + i;
       const int64_t sn = ka.series.n_paths;
       const X4 vcur = vnext;
-      if (two_pass && i + 1 < T) vnext = xs[g + 1];
+      const R icur = inext;
+      if (two_pass && i + 1 < T) { vnext = xs[g + 1]; if (AUXSCR) inext = is[g + 1]; }
       R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0;
       if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
         if (NEED_RINGP) {
@@ -565,7 +588,8 @@ struct Trial {
         vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
       } else if (two_pass) {
-        market_day<false, true>(g, reg, js, x, vn, in);
+        if (AUXSCR) { vn = vcur.w; in = icur; }
+        else market_day<false, true>(g, reg, js, x, vn, in);
         x[0] = vcur.x + shift[0]; x[1] = vcur.y + shift[1]; x[2] = vcur.z + shift[2];
       } else {
         market_day<true, true>(g, reg, js, x, vn, in);

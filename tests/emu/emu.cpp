@@ -28,7 +28,7 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
   ka.tape_first = 0;
   ka.rng_mode = rng_mode;
   const int G = sp->sim_days + sp->buffer_days;
-  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 4 + 4), rp(kRingP), rs(kRingS), ra(kRingA);
+  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 5 + 8), rp(kRingP), rs(kRingS), ra(kRingA);
   ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
   ka.nthreads = 1;
   ka.log_trial = log_trial; ka.log_strategy = log_strategy; ka.log_cap = log_cap;
@@ -109,7 +109,7 @@ static int run_typed(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
   ka.log_trial = -1;
   const int G = sp->sim_days + sp->buffer_days;
-  std::vector<float> xscr((size_t)(G > 0 ? G : 1) * 4 + 4), rp(kRingP), rs(kRingS), ra(kRingA);
+  std::vector<float> xscr((size_t)(G > 0 ? G : 1) * 5 + 8), rp(kRingP), rs(kRingS), ra(kRingA);
   ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
   for (int64_t j = 0; j < n; j++) {
     Trial<float, NS, NA, LETF_MARKET_JOINT_T, false, slot_list_mask(LIST), LIST, AM> t(ka, first + j, j, 0);
