@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LETF_ABI_VERSION 1
+#define LETF_ABI_VERSION 2
 
 #define LETF_N_ASSETS 6
 #define LETF_N_UNDERLYINGS 3
@@ -54,7 +54,10 @@ enum {
   LETF_MARKET_NORMAL = 0,   /* iid correlated normals, fixed regime 0, constant VIX / rf
                                (validation.py:45-57 and the config-2/5 synthetic shapes) */
   LETF_MARKET_PARAM_T = 1,  /* regime-switching Cholesky Student-t, engine.py:81-97 */
-  LETF_MARKET_JOINT_T = 2   /* institutional_v1 multivariate-t GARCH/DCC, calibration.py:480-590 */
+  LETF_MARKET_JOINT_T = 2,  /* institutional_v1 multivariate-t GARCH/DCC, calibration.py:480-590 */
+  /* 3 is reserved (caller-supplied series, letf_run_strategies) */
+  LETF_MARKET_BOOTSTRAP = 4 /* legacy_hybrid two-pool block bootstrap blended with correlated Student-t noise,
+                               bootstrap.py:310-458 + engine.py:50-80 */
 };
 
 /* strategy types (cfg.STRATEGIES[*]['type'], config.py:348-437) */
@@ -145,6 +148,30 @@ typedef struct LetfFundingModel {     /* funding_model, calibration.py:601-609 *
   double base, beta_vix, beta_inv_curve, beta_liquidity, beta_credit, min_spread, max_spread;
 } LetfFundingModel;
 
+typedef struct LetfBootstrapPool {     /* one block pool of one regime, bootstrap.py:49-160 */
+  int32_t n_blocks;
+  int32_t pad;
+  const int32_t* start;       /* HOST [n_blocks] first history row of each block (copied by letf_create) */
+  const double* block_ret;    /* HOST [n_blocks] cumulative SPY return of the block: the selection key */
+} LetfBootstrapPool;
+
+typedef struct LetfBootstrap {         /* bootstrap_sampler + cfg.BOOTSTRAP_* (legacy_hybrid only) */
+  int32_t hist_len;           /* rows of the cleaned history */
+  int32_t block_size;         /* cfg.BOOTSTRAP_BLOCK_SIZE: rows per pool block (168) */
+  int32_t block_min, block_max;  /* cfg.BOOTSTRAP_BLOCK_MIN / MAX, bootstrap.py:302-308 */
+  double block_mean;          /* cfg.BOOTSTRAP_BLOCK_MEAN: geometric p = 1 / mean */
+  double momentum_bias[2];    /* cfg.BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME */
+  double sampler_weight;      /* sample_returns(bootstrap_weight=0.85), bootstrap.py:312 */
+  double engine_weight;       /* cfg.BOOTSTRAP_WEIGHT, engine.py:64, 77-79 */
+  double sampler_chol[2][3][3];  /* chol(corr_low_vol / corr_high_vol), bootstrap.py:404-417 */
+  double engine_chol[2][3][3];   /* chol(nearest_psd(corr_low / corr_high)), engine.py:60-63 */
+  const double* hist_spy;     /* HOST [hist_len] SPY_Ret, NaN -> 0 (bootstrap.py:131) */
+  const double* hist_qqq;     /* HOST [hist_len] QQQ_Ret, NaN -> 0 */
+  const double* hist_tlt;     /* HOST [hist_len] TLT_Ret, NaN -> 0 */
+  LetfBootstrapPool pool_a[2];   /* "economy" pool: SPY comes from these blocks */
+  LetfBootstrapPool pool_b[2];   /* "tech" pool (real-QQQ era): QQQ and TLT come from these blocks */
+} LetfBootstrap;
+
 typedef struct LetfParams {
   int32_t abi_version;         /* LETF_ABI_VERSION */
   int32_t market_mode;         /* LETF_MARKET_* */
@@ -193,6 +220,8 @@ typedef struct LetfParams {
   int32_t pad1;
 
   LetfStrategyParams strategies[LETF_MAX_STRATEGIES];
+
+  LetfBootstrap boot;            /* MARKET_BOOTSTRAP only */
 } LetfParams;
 
 /*
@@ -210,7 +239,7 @@ typedef struct LetfTape {
   int32_t pad;
   int32_t* start_offset;         /* [n]            random_start.py:57 */
   int32_t* spells;               /* [max_spells][n] engine.py:280/283 (already >= 1) */
-  double* x;                     /* [G][3][n] N(0,1) (JOINT_T, NORMAL) or t(df) (PARAM_T) */
+  double* x;                     /* [G][3][n] N(0,1) (JOINT_T, NORMAL) or t(df) (PARAM_T, BOOTSTRAP: engine.py:68) */
   double* chi2;                  /* [G][n]   chisquare(nu_regime)      calibration.py:565 */
   double* vix_n;                 /* [G][n]   N(0,1)                    engine.py:115 */
   double* irx_n;                 /* [G][n]   N(0,1)                    engine.py:122 */
@@ -220,6 +249,13 @@ typedef struct LetfTape {
   double* jump_t;                /* [T][n]   t(5)                      calibration.py:828 */
   double* sign;                  /* [T][n]   -1 / +1                   engine.py:509 */
   double* te_t;                  /* [6][T][n] t(te_df[a])              engine.py:185 */
+  /* MARKET_BOOTSTRAP only (NULL otherwise); block k of a trial, at most max_blocks = G / block_min + 2 */
+  int32_t max_blocks;
+  int32_t pad2;
+  int32_t* boot_len;             /* [max_blocks][n]    geometric(1 / block_mean)            bootstrap.py:304 */
+  double* boot_u;                /* [max_blocks][6][n] U[0,1): momentum A, block A, offset A, momentum B,
+                                    block B (uniform index or weighted choice), offset B      bootstrap.py:212-262, 348-374 */
+  double* boot_t;                /* [G][3][n] t(df) noise of sample_returns                  bootstrap.py:400 */
 } LetfTape;
 
 /* per-trial outputs, structure-of-arrays: [strategy][n_trials] */

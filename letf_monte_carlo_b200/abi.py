@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_ASSETS = 6
 N_REGIMES = 2
 MAX_STRATEGIES = 32
@@ -26,6 +26,7 @@ UNDERLYING_INDEX = {"SPY": 0, "QQQ": 1, "TLT": 2}
 OK, ERR_INVALID, ERR_CUDA, ERR_NONFINITE, ERR_NOMEM = 0, 1, 2, 3, 4
 # market modes
 MARKET_NORMAL, MARKET_PARAM_T, MARKET_JOINT_T = 0, 1, 2
+MARKET_BOOTSTRAP = 4      # legacy_hybrid block bootstrap (3 = caller-supplied series, internal)
 # precision / rng
 PREC_F64, PREC_F32 = 0, 1
 RNG_PHILOX, RNG_TAPE, RNG_PHILOX_RECORD = 0, 1, 2
@@ -83,6 +84,22 @@ class FundingModel(C.Structure):
                 ("min_spread", C.c_double), ("max_spread", C.c_double)]
 
 
+class BootstrapPool(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("pad", C.c_int32),
+                ("start", C.POINTER(C.c_int32)), ("block_ret", C.POINTER(C.c_double))]
+
+
+class Bootstrap(C.Structure):
+    _fields_ = [
+        ("hist_len", C.c_int32), ("block_size", C.c_int32), ("block_min", C.c_int32), ("block_max", C.c_int32),
+        ("block_mean", C.c_double), ("momentum_bias", C.c_double * 2),
+        ("sampler_weight", C.c_double), ("engine_weight", C.c_double),
+        ("sampler_chol", ((C.c_double * 3) * 3) * 2), ("engine_chol", ((C.c_double * 3) * 3) * 2),
+        ("hist_spy", C.POINTER(C.c_double)), ("hist_qqq", C.POINTER(C.c_double)), ("hist_tlt", C.POINTER(C.c_double)),
+        ("pool_a", BootstrapPool * 2), ("pool_b", BootstrapPool * 2),
+    ]
+
+
 class Params(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("market_mode", C.c_int32), ("sim_days", C.c_int32),
@@ -104,6 +121,7 @@ class Params(C.Structure):
         ("cash_rate", C.c_double * 2), ("base_spread_bps", C.c_double * 2),
         ("rebalance_cost", C.c_double), ("apply_costs", C.c_int32), ("pad1", C.c_int32),
         ("strategies", StrategyParams * MAX_STRATEGIES),
+        ("boot", Bootstrap),
     ]
 
 
@@ -115,11 +133,13 @@ class Tape(C.Structure):
         ("chi2", C.c_void_p), ("vix_n", C.c_void_p), ("irx_n", C.c_void_p),
         ("liq_n", C.c_void_p), ("cred_n", C.c_void_p), ("jump_u", C.c_void_p),
         ("jump_t", C.c_void_p), ("sign", C.c_void_p), ("te_t", C.c_void_p),
+        ("max_blocks", C.c_int32), ("pad2", C.c_int32),
+        ("boot_len", C.c_void_p), ("boot_u", C.c_void_p), ("boot_t", C.c_void_p),
     ]
 
 
 TAPE_FIELDS = ("start_offset", "spells", "x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n",
-               "jump_u", "jump_t", "sign", "te_t")
+               "jump_u", "jump_t", "sign", "te_t", "boot_len", "boot_u", "boot_t")
 
 
 class Outputs(C.Structure):

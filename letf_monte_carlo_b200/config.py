@@ -49,6 +49,11 @@ REGIME_NAMES = {0: "Low Vol", 1: "High Vol"}
 STUDENT_T_DF = 5                             # letf/config.py:239
 USE_BLOCK_BOOTSTRAP = True
 BOOTSTRAP_WEIGHT = 0.80
+BOOTSTRAP_BLOCK_MIN = 21                     # letf/config.py:221-224
+BOOTSTRAP_BLOCK_MAX = 168
+BOOTSTRAP_BLOCK_MEAN = 84
+BOOTSTRAP_BLOCK_SIZE = BOOTSTRAP_BLOCK_MAX
+BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME = {0: 0.54, 1: 0.505}   # letf/config.py:227-230
 SIM_ENGINE_MODE = "institutional_v1"         # letf/config.py:267
 
 USE_RANDOM_START = True                      # letf/config.py:308-345

@@ -46,8 +46,9 @@ class DeviceTape:
         s = abi.Tape()
         h = self.host
         s.n_tapes, s.gen_days, s.sim_days, s.max_spells = h.n_tapes, h.gen_days, h.sim_days, h.max_spells
+        s.max_blocks = h.max_blocks
         for k, t in self.t.items():
-            setattr(s, k, t.data_ptr())
+            setattr(s, k, t.data_ptr() if t.numel() else None)
         return s
 
     def to_host(self) -> HostTape:

@@ -118,6 +118,42 @@ def pack_strategy(sid: str, conf: Mapping, taxable_ids: Sequence[str]) -> abi.St
     return sp
 
 
+def _pack_bootstrap(p: abi.Params, keep: list, sampler, cfg) -> None:
+    """bootstrap_sampler + cfg.BOOTSTRAP_* -> LetfBootstrap (host tables; letf_create copies them)."""
+    from . import bootstrap as bs
+    pools = bs.as_pools(sampler)
+    keep.append(pools)
+    b = p.boot
+    b.hist_len = len(pools.hist_spy)
+    b.block_size = int(pools.block_size)
+    b.block_min = int(cfg.BOOTSTRAP_BLOCK_MIN); b.block_max = int(cfg.BOOTSTRAP_BLOCK_MAX)
+    b.block_mean = float(cfg.BOOTSTRAP_BLOCK_MEAN)
+    if not (1 <= b.block_min <= b.block_max <= b.block_size):
+        # bootstrap.py:350-352 slices block[start:start+len] with len <= block_size; a longer request would
+        # silently yield a short block in numpy and desynchronise the day counter
+        raise UnsupportedConfig("BOOTSTRAP_BLOCK_MIN <= BOOTSTRAP_BLOCK_MAX <= BOOTSTRAP_BLOCK_SIZE is required")
+    for r in range(2):
+        b.momentum_bias[r] = float(cfg.BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME.get(r, 0.52))
+        _set_mat(b.sampler_chol[r], np.linalg.cholesky(bs.SAMPLER_CORR[r]))
+        _set_mat(b.engine_chol[r], np.linalg.cholesky(nearest_psd_matrix(bs.ENGINE_CORR[r])))
+    b.sampler_weight = 0.85                                    # sample_returns' default (bootstrap.py:312)
+    b.engine_weight = float(cfg.BOOTSTRAP_WEIGHT)
+    dp = C.POINTER(C.c_double)
+    b.hist_spy = pools.hist_spy.ctypes.data_as(dp)
+    b.hist_qqq = pools.hist_qqq.ctypes.data_as(dp)
+    b.hist_tlt = pools.hist_tlt.ctypes.data_as(dp)
+    for name, table in (("pool_a", pools.pool_a), ("pool_b", pools.pool_b)):
+        for r in range(2):
+            start, ret = table[r]
+            if len(start) == 0:
+                # the reference would fall back to synthetic Student-t blocks (bootstrap.py:214-222)
+                raise UnsupportedConfig(f"bootstrap {name}[{r}] is empty: the synthetic-block fallback is not implemented")
+            q = getattr(b, name)[r]
+            q.n_blocks = len(start)
+            q.start = start.ctypes.data_as(C.POINTER(C.c_int32))
+            q.block_ret = ret.ctypes.data_as(dp)
+
+
 _NEEDS_SPY = {abi.STRATEGY_TYPES[k] for k in ("sma", "sma_band", "composite", "adaptive_vol", "convex_vol",
                                                  "meta_ensemble", "mom_vol_convergence", "conviction_compounder")}
 
@@ -178,7 +214,8 @@ def build_params(strategy_ids: Sequence[str], time_horizon: float, regime_model:
     elif institutional and joint is not None:
         p.market_mode = abi.MARKET_JOINT_T
     elif regime_model.get("bootstrap_sampler") is not None and getattr(cfg, "USE_BLOCK_BOOTSTRAP", False):
-        raise UnsupportedConfig("legacy_hybrid block bootstrap is out of scope for the GPU path (SURVEY.md 8f)")
+        p.market_mode = abi.MARKET_BOOTSTRAP                   # engine.py:50-80
+        _pack_bootstrap(p, keep, regime_model["bootstrap_sampler"], cfg)
     else:
         p.market_mode = abi.MARKET_PARAM_T
     p.moment_matching = 1 if (p.market_mode == abi.MARKET_JOINT_T and getattr(cfg, "USE_MOMENT_MATCHING", False)) else 0

@@ -160,3 +160,41 @@ EXTRA_BENCHMARKS = {
     "B_TMF": {"name": "TMF Buy Hold", "type": "benchmark", "asset": "TMF"},
     "B_TLT": {"name": "TLT Buy Hold", "type": "benchmark", "asset": "TLT"},
 }
+
+
+def synthetic_history(n_days: int = 12000, seed: int = 7, start: str = "1978-01-03", nan_every: int = 0):
+    """A deterministic stand-in for the historical frame the block bootstrap samples from
+    (columns as letf/simulation/bootstrap.py:77-96 reads them: SPY_Ret, QQQ_Ret, TLT_Ret, VIX, IRX on a
+    business-day index).  Two volatility states with persistent spells so that both regimes' pools and
+    both eras (before / after the real-QQQ cutoff 1999-03-10) are populated; optional NaN holes exercise
+    the nan_to_num / NaN-count rules of _create_regime_blocks."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    idx = pd.bdate_range(start=start, periods=n_days)
+    state = np.zeros(n_days, dtype=int)
+    t, cur = 0, 0
+    while t < n_days:
+        ln = int(rng.geometric(1 / (400 if cur == 0 else 120)))
+        state[t:t + ln] = cur
+        t += ln
+        cur ^= 1
+    vol = np.where(state == 0, 0.008, 0.022)
+    spy = 0.0004 - 0.0008 * state + vol * rng.standard_t(6, n_days) * 0.8
+    qqq = 1.2 * spy + 0.006 * rng.standard_normal(n_days)
+    tlt = -0.2 * spy + 0.005 * rng.standard_normal(n_days)
+    vix = np.where(state == 0, 15.0, 32.0) + 3.0 * rng.standard_normal(n_days)
+    irx = np.clip(np.where(state == 0, 3.5, 1.5) + 0.5 * rng.standard_normal(n_days), 0, 15)
+    if nan_every:
+        spy[::nan_every] = np.nan
+        vix[5::nan_every] = np.nan
+        qqq[3::nan_every] = np.nan
+    return pd.DataFrame({"SPY_Ret": spy, "QQQ_Ret": qqq, "TLT_Ret": tlt, "VIX": np.maximum(vix, 9.0), "IRX": irx},
+                        index=idx)
+
+
+def legacy_bootstrap_model(history=None, variant: str = "default") -> dict:
+    """fallback regime model + a bootstrap sampler over `history` (legacy_hybrid mode, engine.py:50-80)."""
+    from .bootstrap import create_bootstrap_sampler
+    m = fallback_regime_model(variant)
+    m["bootstrap_sampler"] = create_bootstrap_sampler(history if history is not None else synthetic_history())
+    return m

@@ -13,15 +13,19 @@ import numpy as np
 
 from . import abi
 
-F64_FIELDS = ("x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n", "jump_u", "jump_t", "sign", "te_t")
+F64_FIELDS = ("x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n", "jump_u", "jump_t", "sign", "te_t", "boot_u", "boot_t")
 
 
 class HostTape:
     """numpy-backed LetfTape."""
 
-    def __init__(self, n_tapes: int, gen_days: int, sim_days: int, max_spells: int):
+    def __init__(self, n_tapes: int, gen_days: int, sim_days: int, max_spells: int, max_blocks: int = 0):
         n, G, T, K = int(n_tapes), int(gen_days), int(sim_days), int(max_spells)
         self.n_tapes, self.gen_days, self.sim_days, self.max_spells = n, G, T, K
+        self.max_blocks = B = int(max_blocks)         # MARKET_BOOTSTRAP only
+        self.boot_len = np.ones((B, n), np.int32)
+        self.boot_u = np.zeros((B, 6, n))
+        self.boot_t = np.zeros((G if B else 0, 3, n))
         self.start_offset = np.zeros(n, np.int32)
         self.spells = np.full((K, n), max(G, 1), np.int32)
         self.x = np.zeros((G, 3, n))
@@ -41,9 +45,10 @@ class HostTape:
     def as_struct(self) -> abi.Tape:
         t = abi.Tape()
         t.n_tapes, t.gen_days, t.sim_days, t.max_spells = self.n_tapes, self.gen_days, self.sim_days, self.max_spells
+        t.max_blocks = self.max_blocks
         for k, a in self.arrays().items():
             assert a.flags["C_CONTIGUOUS"]
-            setattr(t, k, a.ctypes.data)
+            setattr(t, k, a.ctypes.data if a.size else None)
         return t
 
     def regime_full(self, params: abi.Params) -> np.ndarray:
@@ -86,14 +91,19 @@ def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
             spells.append(s.astype(np.int32))
             cover += np.maximum(s, 1)
             k += 1
-    tp = HostTape(n, G, T, max(len(spells), 1))
+    boot = params.market_mode == abi.MARKET_BOOTSTRAP
+    tp = HostTape(n, G, T, max(len(spells), 1), (G // max(int(params.boot.block_min), 1) + 2) if boot else 0)
     for i, s in enumerate(spells):
         tp.spells[i] = s
     if params.random_start and params.buffer_days > 0:
         b = int(params.buffer_days)
         tp.start_offset[:] = rng.integers(min(50, b // 4), b, size=n)
     reg = tp.regime_full(params)
-    if params.market_mode == abi.MARKET_PARAM_T:
+    if boot:       # bootstrap.py:302-308 block lengths, :212-262 selection uniforms, :400 blend noise
+        tp.boot_len[:] = rng.geometric(1.0 / params.boot.block_mean, size=tp.boot_len.shape)
+        tp.boot_u[:] = rng.random(tp.boot_u.shape)
+        tp.boot_t[:] = rng.standard_t(params.param_t_df, size=tp.boot_t.shape)
+    if params.market_mode in (abi.MARKET_PARAM_T, abi.MARKET_BOOTSTRAP):
         tp.x[:] = rng.standard_t(params.param_t_df, size=tp.x.shape)
     else:
         tp.x[:] = rng.standard_normal(tp.x.shape)

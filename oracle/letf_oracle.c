@@ -664,6 +664,142 @@ static void chol3(const double c[3][3], double L[3][3]) {
   L[2][2] = sqrt(c[2][2] - L[2][0] * L[2][0] - L[2][1] * L[2][1]);
 }
 
+/* ------------------------------------------------------------------------ */
+/* legacy_hybrid block bootstrap: BlockBootstrapReturns.sample_returns (bootstrap.py:310-458)
+ * followed by the second noise blend of generate_fat_tailed_returns (engine.py:50-80).
+ * Tape ledger per block k: boot_len[k] = rng.geometric(1 / BLOCK_MEAN) (bootstrap.py:304);
+ * boot_u[k][0..5] = momentum coin A (:226), block index A (:262), sub-section start A (:352),
+ * momentum coin B, block index B (uniform :262 or weighted rng.choice :259), sub-section start B (:370).
+ * rng.integers(0, m) on a tape uniform u is floor(u * m); rng.choice(m, p=w) is numpy's
+ * cdf.searchsorted(u, side='right').  Empty pools (the reference's synthetic-block fallback,
+ * bootstrap.py:214-222) are rejected by the parameter builder and not restated here. */
+static int boot_pick(const LetfBootstrapPool* pool, int have_last, double last_ret, double bias,
+                     double u_mom, double u_idx, int use_target, double target) {
+  /* returns the index (into the pool's own block list) of the chosen block */
+  const int nb = pool->n_blocks;
+  int* cand = (int*)malloc(sizeof(int) * (size_t)(nb > 0 ? nb : 1));
+  int nc = 0;
+  int all = 1;
+  if (have_last) {
+    const int desired = last_ret >= 0 ? 1 : -1;
+    int ns = 0;
+    for (int i = 0; i < nb; i++) {
+      const double r = pool->block_ret[i];
+      if ((r >= 0 && desired >= 0) || (r < 0 && desired < 0)) cand[ns++] = i;
+    }
+    if (ns > 0 && bias > 0 && u_mom < bias) { nc = ns; all = 0; }
+  }
+  if (all) { for (int i = 0; i < nb; i++) cand[i] = i; nc = nb; }
+  int pick;
+  if (use_target && nc > 5) {
+    /* Gaussian kernel weights around the economy block's SPY return (bootstrap.py:232-259) */
+    double mean = 0, var = 0;
+    for (int i = 0; i < nc; i++) mean += pool->block_ret[cand[i]];
+    mean /= nc;
+    for (int i = 0; i < nc; i++) { double d = pool->block_ret[cand[i]] - mean; var += d * d; }
+    double sigma = sqrt(var / nc);
+    if (sigma < 1e-8) sigma = 0.05;
+    double W = 0;
+    for (int i = 0; i < nc; i++) { double d = (pool->block_ret[cand[i]] - target) / sigma; W += exp(-0.5 * (d * d)); }
+    double cum = 0; int idx = 0;
+    for (int i = 0; i < nc; i++) {
+      double d = (pool->block_ret[cand[i]] - target) / sigma;
+      cum += exp(-0.5 * (d * d)) / W;
+      if (cum <= u_idx) idx = i + 1;
+    }
+    if (idx > nc - 1) idx = nc - 1;
+    pick = cand[idx];
+  } else {
+    int idx = (int)floor(u_idx * nc);
+    if (idx > nc - 1) idx = nc - 1;
+    pick = cand[idx];
+  }
+  free(cand);
+  return pick;
+}
+
+static int boot_generate(const LetfParams* p, const LetfTape* tp, int64_t ti, int64_t n, const int* regf, int G,
+                         double* spy, double* qqq, double* tlt) {
+  const LetfBootstrap* b = &p->boot;
+  if (!tp->boot_len || !tp->boot_u || !tp->boot_t) return LETF_ERR_INVALID;
+  int cur = 0, k = 0, have_last = 0;
+  double last_a = 0, last_b = 0;
+  while (cur < G) {
+    if (k >= tp->max_blocks) return LETF_ERR_INVALID;
+    const int remaining = G - cur;
+    int len = tp->boot_len[(int64_t)k * n + ti];
+    if (len < b->block_min) len = b->block_min;
+    if (len > b->block_max) len = b->block_max;
+    if (len > remaining) len = remaining;
+    int ones = 0;
+    for (int j = 0; j < len; j++) ones += regf[cur + j];
+    const int regime = 2 * ones > len ? 1 : 0;          /* int(np.median(block_regime_path)) */
+    const double bias = b->momentum_bias[regime];
+#define BU(s) tp->boot_u[((int64_t)k * 6 + (s)) * n + ti]
+    const LetfBootstrapPool* pa = &b->pool_a[regime];
+    const LetfBootstrapPool* pb = &b->pool_b[regime];
+    if (pa->n_blocks <= 0 || pb->n_blocks <= 0) return LETF_ERR_INVALID;
+    int ia = boot_pick(pa, have_last, last_a, bias, BU(0), BU(1), 0, 0.0);
+    int row_a = pa->start[ia];
+    if (len < b->block_size) row_a += (int)floor(BU(2) * (double)(b->block_size - len + 1));
+    double prod_a = 1.0;
+    for (int j = 0; j < len; j++) prod_a *= 1 + b->hist_spy[row_a + j];
+    const double spy_block_return = prod_a - 1;
+    int ib = boot_pick(pb, have_last, last_b, bias, BU(3), BU(4), 1, spy_block_return);
+    int row_b = pb->start[ib];
+    if (len < b->block_size) row_b += (int)floor(BU(5) * (double)(b->block_size - len + 1));
+#undef BU
+    double prod_b = 1.0;
+    for (int j = 0; j < len; j++) {
+      spy[cur + j] = b->hist_spy[row_a + j];
+      qqq[cur + j] = b->hist_qqq[row_b + j];
+      tlt[cur + j] = b->hist_tlt[row_b + j];
+      prod_b *= 1 + b->hist_qqq[row_b + j];
+    }
+    last_a = spy_block_return; last_b = prod_b - 1; have_last = 1;
+    cur += len; k++;
+  }
+  /* shared correlated Student-t noise, mean-preserving blend (bootstrap.py:386-449) */
+  if (b->sampler_weight < 1.0 && G > 0) {
+    const double nw = 1.0 - b->sampler_weight;
+    const double m0 = np_pairwise_sum(spy, G) / (double)G, m1 = np_pairwise_sum(qqq, G) / (double)G,
+                 m2 = np_pairwise_sum(tlt, G) / (double)G;
+    for (int t = 0; t < G; t++) {
+      const int rg = regf[t];
+      const double s0 = rg == 0 ? 0.007 : 0.022, s1 = s0 * 1.35, s2 = s0 * 0.5;
+      const double (*C)[3] = b->sampler_chol[rg];
+      const double z0 = tp->boot_t[((int64_t)t * 3 + 0) * n + ti], z1 = tp->boot_t[((int64_t)t * 3 + 1) * n + ti],
+                   z2 = tp->boot_t[((int64_t)t * 3 + 2) * n + ti];
+      const double c0 = C[0][0] * z0 + C[0][1] * z1 + C[0][2] * z2;
+      const double c1 = C[1][0] * z0 + C[1][1] * z1 + C[1][2] * z2;
+      const double c2 = C[2][0] * z0 + C[2][1] * z1 + C[2][2] * z2;
+      spy[t] = b->sampler_weight * spy[t] + nw * (c0 * s0 + m0);
+      qqq[t] = b->sampler_weight * qqq[t] + nw * (c1 * s1 + m1);
+      tlt[t] = b->sampler_weight * tlt[t] + nw * (c2 * s2 + m2);
+    }
+  }
+  /* second blend, engine.py:57-79 */
+  {
+    const double W = b->engine_weight;
+    const double noise_w = clipd(1.0 - W, 0.0, 1.0);
+    for (int t = 0; t < G; t++) {
+      const int rg = regf[t];
+      const double (*C)[3] = b->engine_chol[rg];
+      const double z0 = tp->x[((int64_t)t * 3 + 0) * n + ti], z1 = tp->x[((int64_t)t * 3 + 1) * n + ti],
+                   z2 = tp->x[((int64_t)t * 3 + 2) * n + ti];
+      const double x0 = C[0][0] * z0 + C[0][1] * z1 + C[0][2] * z2;
+      const double x1 = C[1][0] * z0 + C[1][1] * z1 + C[1][2] * z2;
+      const double x2 = C[2][0] * z0 + C[2][1] * z1 + C[2][2] * z2;
+      const double sd = p->regime_daily_std[rg], qsd = 1.35 * sd, tsd = 0.55 * sd;
+      const double n0 = noise_w * sd * 0.55 * x0, n1 = noise_w * qsd * 0.45 * x1, n2 = noise_w * tsd * 0.35 * x2;
+      spy[t] = W * spy[t] + (1.0 - W) * (spy[t] + n0);
+      qqq[t] = W * qqq[t] + (1.0 - W) * (qqq[t] + n1);
+      tlt[t] = W * tlt[t] + (1.0 - W) * (tlt[t] + n2);
+    }
+  }
+  return 0;
+}
+
 /* one trial.  Returns 0, or LETF_ERR_NONFINITE when the reference would raise. */
 static int oracle_trial(const LetfParams* p, const LetfTape* tp, int64_t k, int64_t col,
                         const LetfOutputs* out, LetfOracleSeries* dump, Journal* full_journal,
@@ -767,6 +903,9 @@ static int oracle_trial(const LetfParams* p, const LetfTape* tp, int64_t k, int6
         for (int t = 0; t < G; t++) outp[a][t] = outp[a][t] + sh;
       }
     }
+  } else if (p->market_mode == LETF_MARKET_BOOTSTRAP) {
+    int rc = boot_generate(p, tp, ti, n, regf, G, spy, qqq, tlt);
+    if (rc) { free(regf); free(gen); return rc; }
   } else if (p->market_mode == LETF_MARKET_PARAM_T) {
     /* engine.py:81-97 */
     for (int t = 0; t < G; t++) {

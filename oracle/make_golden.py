@@ -59,6 +59,11 @@ CASES = [
     dict(name="one_day", variant="default", years=1 / 252 + 1e-9, n_tapes=1, seed=114, cfg={}, strategies=ALL19),
     dict(name="inst_10y", variant="default", years=10, n_tapes=2, seed=115, cfg={}, strategies=ALL19 + EXTRAS),
     dict(name="inst_30y", variant="default", years=30, n_tapes=1, seed=116, cfg={}, strategies=ALL19),
+    dict(name="boot_1y", variant="boot", years=1, n_tapes=3, seed=119,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid"}, strategies=ALL19 + EXTRAS),
+    dict(name="boot_3y_nan_fixed_start", variant="boot_nan", years=3, n_tapes=2, seed=120,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MEAN": 40,
+              "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME": {0: 0.9, 1: 0.2}}, strategies=ALL19),
     dict(name="layers_c2_5y", variant="normal_c2", years=5, n_tapes=4, seed=117, cfg={},
          strategies=["S1", "S3", "B_UPRO"]),
     dict(name="voldrag_c1", variant="normal_c1", years=1, n_tapes=8, seed=118,
@@ -69,6 +74,8 @@ CASES = [
 def case_config(case):
     """our-config snapshot for a case (shared with the tests)."""
     over = dict(case["cfg"])
+    if "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME" in over:          # JSON round trip turns the regime keys into strings
+        over["BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"] = {int(k): float(v) for k, v in over["BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"].items()}
     if over.get("LETF_CONFIGS") == "pure_leverage":
         over["LETF_CONFIGS"] = synthetic.pure_leverage_assets()
         over["ASSETS"] = over["LETF_CONFIGS"]
@@ -83,6 +90,9 @@ def case_model(case):
     v = case["variant"]
     if v.startswith("normal_"):
         return synthetic.normal_regime_model(v.split("_", 1)[1])
+    if v.startswith("boot"):
+        hist = synthetic.synthetic_history(nan_every=97) if v == "boot_nan" else synthetic.synthetic_history()
+        return synthetic.legacy_bootstrap_model(hist)
     return synthetic.fallback_regime_model(v)
 
 
@@ -201,7 +211,8 @@ class TapeGenerator(np.random.Generator):
 class PatchedRng:
     """context manager: np.random.default_rng -> TapeGenerators bound to one tape column."""
 
-    def __init__(self, tape, col, sim_id, regime_full, ref_engine, param_t=False):
+    def __init__(self, tape, col, sim_id, regime_full, ref_engine, param_t=False, boot=None):
+        self.boot = boot
         self.tape, self.col, self.sim_id, self.reg = tape, col, sim_id, regime_full
         self.eng = ref_engine
         self.calls_50000 = 0
@@ -220,6 +231,8 @@ class PatchedRng:
             g = TapeGenerator("B", self.tape, self.col, self.reg)
             if self.param_t:
                 g = ParamTGenerator("B", self.tape, self.col, self.reg)
+            if self.boot is not None:
+                g = BootGenerator("B", self.tape, self.col, self.reg, self.boot)
             return g
         # NB: _stable_asset_seed collides for 'SSO' and 'QQQ' (both hash to 486): the reference's
         # two streams then share a seed; on a tape each asset has its own column, served in call order.
@@ -250,6 +263,57 @@ class ParamTGenerator(TapeGenerator):
         return v
 
 
+class BootGenerator(TapeGenerator):
+    """stream B of the legacy_hybrid bootstrap (bootstrap.py:310-458, engine.py:50-80): per block a geometric
+    length, up to two momentum coins, block indices / sub-section offsets; then the (n_days, 3) noise matrix of
+    sample_returns and one standard_t(size=3) per day in generate_fat_tailed_returns."""
+
+    def __init__(self, role, tape, col, regime_full, boot):
+        super().__init__(role, tape, col, regime_full)
+        self.boot = boot
+        self.k = -1
+        self.cur = 0
+
+    def geometric(self, p, size=None):
+        assert size is None and abs(p - 1.0 / self.boot.block_mean) < 1e-15
+        self.k += 1
+        v = int(self.tp.boot_len[self.k, self.c])
+        ln = min(int(np.clip(v, self.boot.block_min, self.boot.block_max)), self.tp.gen_days - self.cur)
+        self.cur += ln
+        off = ln < self.boot.block_size
+        self.slots = [1] + ([2] if off else []) + [4] + ([5] if off else [])
+        self.n_int = 0
+        return v
+
+    def _next_u(self):
+        u = float(self.tp.boot_u[self.k, self.slots[self.n_int], self.c])
+        self.n_int += 1
+        return u
+
+    def random(self, size=None, *a, **k):
+        assert size is None
+        return float(self.tp.boot_u[self.k, 0 if self.n_int == 0 else 3, self.c])
+
+    def integers(self, low, high=None, *a, **k):
+        u = self._next_u()
+        return int(low + min(int(np.floor(u * (high - low))), high - low - 1))
+
+    def choice(self, a, size=None, replace=True, p=None, **k):
+        assert size is None and p is not None and self.slots[self.n_int] == 4
+        u = self._next_u()
+        cdf = np.asarray(p, dtype=float).cumsum()
+        cdf /= cdf[-1]
+        return int(min(cdf.searchsorted(u, side="right"), a - 1))
+
+    def standard_t(self, df, size=None):
+        if isinstance(size, tuple):                  # bootstrap.py:400
+            assert size == (self.tp.gen_days, 3)
+            return self.tp.boot_t[:, :, self.c].copy()
+        v = self.tp.x[self.g_mvn, :, self.c].copy()  # engine.py:68
+        self.g_mvn += 1
+        return v
+
+
 def import_reference():
     sys.path.insert(0, REF)
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache_golden")
@@ -263,7 +327,9 @@ def apply_ref_cfg(ref_cfg, ns):
     """mirror our config snapshot into the reference's module globals (in-process)."""
     saved = {}
     for k in ("USE_RANDOM_START", "RANDOM_START_METHOD", "RANDOM_START_BUFFER_YEARS", "USE_MOMENT_MATCHING",
-              "USE_ANTITHETIC_VARIATES", "SIM_ENGINE_MODE", "STUDENT_T_DF"):
+              "USE_ANTITHETIC_VARIATES", "SIM_ENGINE_MODE", "STUDENT_T_DF", "USE_BLOCK_BOOTSTRAP", "BOOTSTRAP_WEIGHT",
+              "BOOTSTRAP_BLOCK_MIN", "BOOTSTRAP_BLOCK_MAX", "BOOTSTRAP_BLOCK_MEAN", "BOOTSTRAP_BLOCK_SIZE",
+              "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"):
         saved[k] = getattr(ref_cfg, k)
         setattr(ref_cfg, k, getattr(ns, k))
     saved["STRATEGIES"] = dict(ref_cfg.STRATEGIES)
@@ -290,13 +356,22 @@ def run_reference_full(case, ref_cfg, ref_engine):
            for s in sids}
     meta = {"start_offset": [], "regime_days": [], "jump_days": [], "repaired": []}
     ref_model = {k: v for k, v in model.items() if k != "synthetic_normal"}
+    boot = None
+    if params.market_mode == abi.MARKET_BOOTSTRAP:
+        # the reference's own sampler over the same frame (bootstrap.py:27-47; its pickle cache is bypassed)
+        import contextlib, io
+        from letf.simulation.bootstrap import BlockBootstrapReturns
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_model["bootstrap_sampler"] = BlockBootstrapReturns(model["bootstrap_sampler"].df,
+                                                                   block_size=ns.BOOTSTRAP_BLOCK_SIZE)
+        boot = params.boot
     try:
         for k in range(n_trials):
             col = k >> 1 if params.antithetic_pairs else k
             anti = bool(k & 1) if params.antithetic_pairs else False
             sim_id = 1000 + col
             with PatchedRng(tape, col, sim_id, reg_all[:, col], ref_engine,
-                            param_t=params.market_mode == abi.MARKET_PARAM_T):
+                            param_t=params.market_mode == abi.MARKET_PARAM_T, boot=boot):
                 res = ref_engine.simulate_single_path_fixed((sim_id, case["years"], ref_model, {}, sids, anti))
             for s in sids:
                 r = res[s]

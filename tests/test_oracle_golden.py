@@ -35,7 +35,7 @@ def test_golden_cover_every_strategy_and_generator():
         markets.add(params.market_mode)
         for k in range(params.n_strategies):
             seen_types.add(params.strategies[k].type)
-    assert markets == {0, 1, 2}
+    assert markets == {0, 1, 2, 4}
     assert seen_types == set(range(18))
 
 
