@@ -47,6 +47,10 @@ WORKLOADS = {
                     "1 2 5 10 20 30 40 y, 4.762M trials per horizon and GPU, per-cell wealth / CAGR / max-drawdown histograms + moments "
                     "reduced on device and allreduced",
                trials=4_762_000, years=None, lane_ops=400, mufu=12, horizons=[1, 2, 5, 10, 20, 30, 40]),
+    "boot": dict(desc="legacy_hybrid engine mode (SURVEY.md 8f rank 4): two-pool block bootstrap over a 12 000-row synthetic history "
+                      "blended twice with correlated Student-t noise (bootstrap.py:310-458, engine.py:50-80), VIX/IRX, random start; "
+                      "TQQQ / SPY / SSO buy&hold, 200k trials x 7560 days per GPU",
+                 trials=200_000, years=30, lane_ops=(6 * 110 + 2 * 36 + 40) * (7560 + 1260) / 7560 + 3 * 150, mufu=40),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "200k trials x 7560 days per GPU",
                     trials=200_000, years=30, lane_ops=2600, mufu=60),
@@ -76,6 +80,10 @@ def build_workload(name):
         model = synthetic.normal_regime_model("c2")
         params, keep = build_params(sids, 40, model, ns)
         return ns, model, sids, params, keep
+    elif name == "boot":
+        ns = synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid")
+        sids = ["S1", "S2", "S3"]
+        model = synthetic.legacy_bootstrap_model()
     elif name == "sweep19":
         ns = synthetic.config_namespace()
         sids = ["S%d" % i for i in range(1, 20)]

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "letf_kernels.cuh"
 
@@ -53,6 +54,8 @@ constexpr uint32_t kNeedRingP = (1u << LETF_ST_SMA) | (1u << LETF_ST_SMA_BAND) |
                                 (1u << LETF_ST_ADAPTIVE_VOL) | (1u << LETF_ST_CONVEX_VOL) |
                                 (1u << LETF_ST_META_ENSEMBLE) | (1u << LETF_ST_CONVICTION);
 constexpr uint32_t kNeedRingS = (1u << LETF_ST_MOM_VOL_CONV) | (1u << LETF_ST_CONVICTION);
+
+static inline size_t align256_(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct DevBuf {
   void* p = nullptr;
@@ -95,6 +98,13 @@ struct LetfEngine {
   std::vector<int32_t> host_dur[2];
   uint32_t type_mask = 0;
   bool any_taxable = false;
+  // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
+  void* boot_blob = nullptr;
+  DevBoot<double> boot64;
+  DevBoot<float> boot32;
+  std::vector<double> host_hist[3];
+  std::vector<int32_t> host_pstart[2][2];
+  std::vector<double> host_pret[2][2];
   DevBuf xscr, ringP, ringS, ringA;          // per-thread scratch of the fused kernel
   DevBuf stage_tape, stage_out, stage_log;   // device staging of the *_host entry points
   PinBuf pin_out;                            // pinned mirror of stage_out
@@ -159,7 +169,8 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   if (max_blocks < 1) return fail(LETF_ERR_CUDA, std::string("kernel ") + ke->name + " cannot be resident on this device");
   static thread_local KArgs<R, NS, NA> ka;
   memset(&ka, 0, sizeof(ka));
-  convert_params<R, NS, NA>(e->params, e->dev_dur, ka.p);
+  convert_params<R, NS, NA>(e->params, e->dev_dur, ka.p,
+                            sizeof(R) == 8 ? (const DevBoot<R>*)(const void*)&e->boot64 : (const DevBoot<R>*)(const void*)&e->boot32);
   // persistent grid: every resident thread owns ceil(n / nthreads) work items; shrink the grid so that
   // all waves are full (equal-length trials: a partial last wave costs a whole trial time).  A work item is
   // one trial, or `upt` interleaved trials in the straight-line fast path (letf_fast.cuh).
@@ -185,7 +196,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
 
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
-  if (ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching && G > 0) {
+  if (((ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching) || ke->market == LETF_MARKET_BOOTSTRAP) && G > 0) {
     size_t b = ((size_t)G * 4 + (size_t)((G + 3) & ~3)) * (size_t)nthreads * sizeof(R);   // day vectors + the IRX-normal column (letf_core.cuh AUXSCR)
     cudaError_t ce = e->xscr.reserve(b);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
@@ -219,6 +230,8 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
     int64_t last = first + n - 1;
     int64_t need = n > 0 ? (e->params.antithetic_pairs ? (last >> 1) : last) + 1 : 0;
     if (tape->n_tapes < need) return fail(LETF_ERR_INVALID, "tape has fewer columns than the trial range needs");
+    if (market == LETF_MARKET_BOOTSTRAP && (!tape->boot_len || !tape->boot_u || !tape->boot_t || tape->max_blocks < 1))
+      return fail(LETF_ERR_INVALID, "bootstrap tape arrays missing");
   }
   if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
@@ -298,6 +311,38 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
       e->params.duration_samples[r] = e->host_dur[r].data();
     } else e->params.duration_samples[r] = nullptr;
   }
+  memset(&e->boot64, 0, sizeof(e->boot64)); memset(&e->boot32, 0, sizeof(e->boot32));
+  if (params->market_mode == LETF_MARKET_BOOTSTRAP) {
+    // own copies of the caller's host tables, then one device blob: history [3][len], candidate rows, candidate returns
+    LetfBootstrap& b = e->params.boot;
+    const double* hsrc[3] = {params->boot.hist_spy, params->boot.hist_qqq, params->boot.hist_tlt};
+    for (int c = 0; c < 3; c++) e->host_hist[c].assign(hsrc[c], hsrc[c] + b.hist_len);
+    b.hist_spy = e->host_hist[0].data(); b.hist_qqq = e->host_hist[1].data(); b.hist_tlt = e->host_hist[2].data();
+    for (int q = 0; q < 2; q++) for (int r = 0; r < 2; r++) {
+      LetfBootstrapPool& pl = q ? b.pool_b[r] : b.pool_a[r];
+      e->host_pstart[q][r].assign(pl.start, pl.start + pl.n_blocks);
+      e->host_pret[q][r].assign(pl.block_ret, pl.block_ret + pl.n_blocks);
+      pl.start = e->host_pstart[q][r].data(); pl.block_ret = e->host_pret[q][r].data();
+    }
+    auto upload = [&](auto& tables, auto& meta) -> cudaError_t {
+      typedef typename std::remove_reference<decltype(tables.hist[0])>::type RR;
+      const size_t hb = align256_(tables.hist.size() * sizeof(RR)), sb = align256_(tables.cstart.size() * sizeof(int)),
+                   rb = tables.cret.size() * sizeof(RR);
+      cudaError_t ce2 = cudaMalloc(&e->boot_blob, hb + sb + rb + 256);
+      if (ce2 != cudaSuccess) return ce2;
+      char* base = (char*)e->boot_blob;
+      if ((ce2 = cudaMemcpy(base, tables.hist.data(), tables.hist.size() * sizeof(RR), cudaMemcpyHostToDevice)) != cudaSuccess) return ce2;
+      if ((ce2 = cudaMemcpy(base + hb, tables.cstart.data(), tables.cstart.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return ce2;
+      if ((ce2 = cudaMemcpy(base + hb + sb, tables.cret.data(), rb, cudaMemcpyHostToDevice)) != cudaSuccess) return ce2;
+      meta = tables.meta;
+      for (int c = 0; c < 3; c++) meta.hist[c] = (const RR*)base + (size_t)c * b.hist_len;
+      meta.cstart = (const int*)(base + hb); meta.cret = (const RR*)(base + hb + sb);
+      return cudaSuccess;
+    };
+    if (precision == LETF_PREC_F64) { BootTables<double> t; build_boot_tables<double>(e->params, t); ce = upload(t, e->boot64); }
+    else { BootTables<float> t; build_boot_tables<float>(e->params, t); ce = upload(t, e->boot32); }
+    if (ce != cudaSuccess) { letf_destroy(e); return fail_cuda(ce, "bootstrap tables upload"); }
+  }
   e->type_mask = strategy_type_mask(*params);
   for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
   ce = cudaEventCreate(&e->ev0);
@@ -311,6 +356,7 @@ void letf_destroy(LetfEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
+  if (e->boot_blob) cudaFree(e->boot_blob);
   e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release();
   e->stage_tape.release(); e->stage_out.release(); e->stage_log.release(); e->pin_out.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -370,13 +416,16 @@ int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
 // ---- host-buffer entry points ------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TapeLayout { size_t off[12]; size_t bytes[12]; size_t total; };
+constexpr int kTapeFields = 15;
+struct TapeLayout { size_t off[kTapeFields]; size_t bytes[kTapeFields]; size_t total; };
 static TapeLayout tape_layout(const LetfTape& t) {
   const size_t n = (size_t)t.n_tapes, G = (size_t)t.gen_days, T = (size_t)t.sim_days, K = (size_t)t.max_spells;
-  const size_t b[12] = {4 * n, 4 * K * n, 8 * G * 3 * n, 8 * G * n, 8 * G * n, 8 * G * n,
-                        8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * LETF_N_ASSETS * T * n};
+  const size_t B = t.boot_len ? (size_t)t.max_blocks : 0;
+  const size_t b[kTapeFields] = {4 * n, 4 * K * n, 8 * G * 3 * n, 8 * G * n, 8 * G * n, 8 * G * n,
+                                 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * LETF_N_ASSETS * T * n,
+                                 4 * B * n, 8 * B * 6 * n, B ? 8 * G * 3 * n : 0};
   TapeLayout L; size_t o = 0;
-  for (int i = 0; i < 12; i++) { L.off[i] = o; L.bytes[i] = b[i]; o += align256(b[i]); }
+  for (int i = 0; i < kTapeFields; i++) { L.off[i] = o; L.bytes[i] = b[i]; o += align256(b[i]); }
   L.total = o;
   return L;
 }
@@ -385,7 +434,8 @@ static void** tape_field(LetfTape& t, int i) {
     case 0: return (void**)&t.start_offset; case 1: return (void**)&t.spells; case 2: return (void**)&t.x;
     case 3: return (void**)&t.chi2; case 4: return (void**)&t.vix_n; case 5: return (void**)&t.irx_n;
     case 6: return (void**)&t.liq_n; case 7: return (void**)&t.cred_n; case 8: return (void**)&t.jump_u;
-    case 9: return (void**)&t.jump_t; case 10: return (void**)&t.sign; default: return (void**)&t.te_t;
+    case 9: return (void**)&t.jump_t; case 10: return (void**)&t.sign; case 11: return (void**)&t.te_t;
+    case 12: return (void**)&t.boot_len; case 13: return (void**)&t.boot_u; default: return (void**)&t.boot_t;
   }
 }
 
@@ -396,12 +446,12 @@ static int stage_tape(LetfEngine* e, const LetfTape* host, bool upload, LetfTape
   TapeLayout L = tape_layout(h);
   cudaError_t ce = e->stage_tape.reserve(L.total ? L.total : 256);
   if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "tape staging: " + std::string(cudaGetErrorString(ce))); }
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < kTapeFields; i++) {
     void* hp = *tape_field(h, i);
     char* dp = (char*)e->stage_tape.p + L.off[i];
-    *tape_field(*dev, i) = dp;
-    if (!hp) return fail(LETF_ERR_INVALID, "host tape has a null array");
+    *tape_field(*dev, i) = (i >= 12 && !hp) ? nullptr : dp;       // the bootstrap arrays are optional
     if (L.bytes[i] == 0) continue;
+    if (!hp) return fail(LETF_ERR_INVALID, "host tape has a null array");
     // record mode uploads too: entries the run does not consume keep the caller's values
     (void)upload;
     CK(cudaMemcpy(dp, hp, L.bytes[i], cudaMemcpyHostToDevice));
@@ -411,9 +461,9 @@ static int stage_tape(LetfEngine* e, const LetfTape* host, bool upload, LetfTape
 static int unstage_tape(LetfEngine* e, const LetfTape* host) {
   LetfTape h = *host;
   TapeLayout L = tape_layout(h);
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < kTapeFields; i++) {
     void* hp = *tape_field(h, i);
-    if (L.bytes[i]) CK(cudaMemcpy(hp, (char*)e->stage_tape.p + L.off[i], L.bytes[i], cudaMemcpyDeviceToHost));
+    if (L.bytes[i] && hp) CK(cudaMemcpy(hp, (char*)e->stage_tape.p + L.off[i], L.bytes[i], cudaMemcpyDeviceToHost));
   }
   return LETF_OK;
 }

@@ -387,6 +387,143 @@ struct Trial {
     }
   }
 
+  // ---- legacy_hybrid block bootstrap (bootstrap.py:310-458 + engine.py:50-80) --------------------
+  // one block draw from a (pool, regime): momentum continuation picks the same-sign candidates with probability
+  // `bias` (bootstrap.py:224-229); pool B is then weighted by a Gaussian kernel around the economy block's SPY
+  // return (:232-259, numpy's choice = cdf.searchsorted(u, 'right')), pool A is uniform (:262).  Returns the block's
+  // first history row.
+  LETF_HDN int boot_pick(int pool, int regime, bool have_last, R last_ret, R u_mom, R u_idx, bool use_target, R target) const {
+    const DevBoot<R>& b = p.boot;
+    int kind = 0;
+    if (have_last) {
+      const int want = last_ret >= (R)0 ? 1 : 2;
+      if (b.cnt[pool][regime][want] > 0 && b.bias[regime] > (R)0 && u_mom < b.bias[regime]) kind = want;
+    }
+    const int nc = b.cnt[pool][regime][kind];
+    const int* cs = b.cstart + b.off[pool][regime][kind];
+    const R* cr = b.cret + b.off[pool][regime][kind];
+    int idx = 0;
+    if (use_target && nc > 5) {
+      const R sigma = b.sigma[regime][kind];
+      R W = 0;
+      for (int i = 0; i < nc; i++) { const R d = M::div_(cr[i] - target, sigma); W += M::exp_((R)-0.5 * (d * d)); }
+      R cum = 0;
+      for (int i = 0; i < nc; i++) {
+        const R d = M::div_(cr[i] - target, sigma);
+        cum += M::div_(M::exp_((R)-0.5 * (d * d)), W);
+        if (cum <= u_idx) idx = i + 1;
+      }
+    } else {
+      idx = (int)M::floor_(u_idx * (R)nc);
+    }
+    if (idx > nc - 1) idx = nc - 1;
+    return cs[idx];
+  }
+
+  // pass 1: stitch the blocks into the per-thread scratch column and return the three column means
+  template <typename X4>
+  LETF_HDN void boot_stitch(X4* xs, R (&mean)[3]) {
+    const DevBoot<R>& b = p.boot;
+    const int G = p.T + p.buffer;
+    RegimeGen rgl; regime_init(rgl);
+    R sum[3] = {0, 0, 0}, cmp[3] = {0, 0, 0};
+    int cur = 0, kb = 0;
+    bool have_last = false;
+    R last_a = 0, last_b = 0;
+    while (cur < G) {
+      int len;
+      R u[6];
+      if (use_tape) {
+        if (kb >= ka.tape.max_blocks) { flags |= LETF_FLAG_SPELL_OVERFLOW; len = G; for (int s = 0; s < 6; s++) u[s] = 0; }
+        else {
+          len = ka.tape.boot_len[(int64_t)kb * nt + tcol];
+          for (int s = 0; s < 6; s++) u[s] = tp_get(ka.tape.boot_u, (int64_t)kb * 6 + s);
+        }
+      } else {
+        const U4 wa = rng_block(key, (uint32_t)kb, STREAM_BOOT_A), wb = rng_block(key, (uint32_t)kb, STREAM_BOOT_B);
+        const R q = M::div_(M::log_(M::u01(wa.x)), b.log1mp);         // geometric(1 / block_mean), bootstrap.py:304
+        len = q < (R)1e6 ? (int)q + 1 : 1000000;
+        u[0] = M::u01(wa.y); u[1] = M::u01(wa.z); u[2] = M::u01(wa.w);
+        u[3] = M::u01(wb.x); u[4] = M::u01(wb.y); u[5] = M::u01(wb.z);
+        if (rec && kb < ka.tape.max_blocks) {
+          ka.tape.boot_len[(int64_t)kb * nt + tcol] = len;
+          for (int s = 0; s < 6; s++) tp_put(ka.tape.boot_u, (int64_t)kb * 6 + s, u[s]);
+        }
+      }
+      len = len < b.block_min ? b.block_min : (len > b.block_max ? b.block_max : len);
+      if (len > G - cur) len = G - cur;
+      int ones = 0;
+      for (int j = 0; j < len; j++) ones += regime_next(rgl);
+      const int regime = 2 * ones > len ? 1 : 0;                      // int(np.median(block_regime_path)), bootstrap.py:340
+      const int span = b.block_size - len + 1;                        // sub-section starts (bootstrap.py:350-352)
+      int row_a = boot_pick(0, regime, have_last, last_a, u[0], u[1], false, (R)0);
+      if (len < b.block_size) { int o = (int)M::floor_(u[2] * (R)span); row_a += o > span - 1 ? span - 1 : o; }
+      const R* hs = b.hist[0] + row_a;
+      R prod_a = (R)1;
+      for (int j = 0; j < len; j++) prod_a *= (R)1 + hs[j];
+      const R spy_ret = prod_a - (R)1;
+      int row_b = boot_pick(1, regime, have_last, last_b, u[3], u[4], true, spy_ret);
+      if (len < b.block_size) { int o = (int)M::floor_(u[5] * (R)span); row_b += o > span - 1 ? span - 1 : o; }
+      const R* hq = b.hist[1] + row_b;
+      const R* ht = b.hist[2] + row_b;
+      R prod_b = (R)1;
+      for (int j = 0; j < len; j++) {
+        X4 v; v.x = hs[j]; v.y = hq[j]; v.z = ht[j]; v.w = (R)0;
+        xs[cur + j] = v;
+        prod_b *= (R)1 + v.y;
+        const R xv[3] = {v.x, v.y, v.z};
+        for (int a = 0; a < 3; a++) { R y = xv[a] - cmp[a], t = sum[a] + y; cmp[a] = (t - sum[a]) - y; sum[a] = t; }
+      }
+      last_a = spy_ret; last_b = prod_b - (R)1; have_last = true;
+      cur += len; kb++;
+    }
+    for (int a = 0; a < 3; a++) mean[a] = G > 0 ? sum[a] / (R)G : (R)0;
+  }
+
+  // pass 2, one generated day: both correlated Student-t blends on the stitched returns, and the day's VIX / IRX normals
+  LETF_HD void boot_day(int g, int reg, R b0, R b1, R b2, const R (&mean)[3], R x[3], R& vix_n, R& irx_n) {
+    const DevBoot<R>& b = p.boot;
+    R z1[3], z2[3];
+    if (use_tape) {
+      for (int c = 0; c < 3; c++) { z1[c] = tp_get(ka.tape.boot_t, (int64_t)g * 3 + c); z2[c] = tp_get(ka.tape.x, (int64_t)g * 3 + c); }
+      vix_n = tp_get(ka.tape.vix_n, g); irx_n = tp_get(ka.tape.irx_n, g);
+    } else {
+      for (int c = 0; c < 3; c++) {
+        const U4 w1 = rng_block(key, (uint32_t)g, STREAM_BN0 + c);
+        z1[c] = student_t_block<R>(w1, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_BN0 + c);
+        const U4 w2 = rng_block(key, (uint32_t)g, STREAM_PT0 + c);
+        z2[c] = student_t_block<R>(w2, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
+      }
+      const U4 w = rng_block(key, (uint32_t)g, STREAM_MKT1);
+      M::box_muller(w.x, w.y, vix_n, irx_n);
+      if (rec) {
+        for (int c = 0; c < 3; c++) { tp_put(ka.tape.boot_t, (int64_t)g * 3 + c, z1[c]); tp_put(ka.tape.x, (int64_t)g * 3 + c, z2[c]); }
+        tp_put(ka.tape.vix_n, g, vix_n); tp_put(ka.tape.irx_n, g, irx_n);
+      }
+    }
+    if (b.nw1 > (R)0) {                                               // bootstrap.py:386-449
+      const R* C = b.ch1[reg];
+      const R c0 = C[0] * z1[0] + C[1] * z1[1] + C[2] * z1[2];
+      const R c1 = C[3] * z1[0] + C[4] * z1[1] + C[5] * z1[2];
+      const R c2 = C[6] * z1[0] + C[7] * z1[1] + C[8] * z1[2];
+      const R s0 = reg == 0 ? (R)0.007 : (R)0.022, s1 = s0 * (R)1.35, s2 = s0 * (R)0.5;
+      b0 = b.w1 * b0 + b.nw1 * (c0 * s0 + mean[0]);
+      b1 = b.w1 * b1 + b.nw1 * (c1 * s1 + mean[1]);
+      b2 = b.w1 * b2 + b.nw1 * (c2 * s2 + mean[2]);
+    }
+    {                                                                 // engine.py:57-79
+      const R* C = b.ch2[reg];
+      const R x0 = C[0] * z2[0] + C[1] * z2[1] + C[2] * z2[2];
+      const R x1 = C[3] * z2[0] + C[4] * z2[1] + C[5] * z2[2];
+      const R x2 = C[6] * z2[0] + C[7] * z2[1] + C[8] * z2[2];
+      const R sd = p.reg_std[reg], qsd = (R)1.35 * sd, tsd = (R)0.55 * sd;
+      const R n0 = b.noise_w2 * sd * (R)0.55 * x0, n1 = b.noise_w2 * qsd * (R)0.45 * x1, n2 = b.noise_w2 * tsd * (R)0.35 * x2;
+      x[0] = b.w2 * b0 + b.omw2 * (b0 + n0);
+      x[1] = b.w2 * b1 + b.omw2 * (b1 + n1);
+      x[2] = b.w2 * b2 + b.omw2 * (b2 + n2);
+    }
+  }
+
   // ---- strategy bank ------------------------------------------------------------------------
   struct Signals {          // state "as of yesterday" (pandas .shift(1)) unless noted
     RollSum<R, EXACT> sma200, sma100, gain14, loss14, mom126, mean60;
@@ -470,13 +607,15 @@ struct Trial {
     const int Gp = (p.T + p.buffer + 3) & ~3;
     R* const is = (R*)ka.xscr + (int64_t)4 * (p.T + p.buffer) * ka.nthreads + (int64_t)lane * Gp;
     R shift[3] = {(R)0, (R)0, (R)0};
-    const bool two_pass = MARKET == LETF_MARKET_JOINT_T && p.mm;
+    const bool two_pass = (MARKET == LETF_MARKET_JOINT_T && p.mm) || MARKET == kMarketBoot;
     const int T = MARKET == kMarketSeries ? ka.series.sim_days : p.T;
     JointState js;
     js.prev_reg = 0;
     for (int a = 0; a < 3; a++) { js.h[a] = 0; js.pz[a] = 0; }
     for (int a = 0; a < 6; a++) js.q[a] = 0;
-    if (two_pass && G > 0) {
+    if (MARKET == kMarketBoot) {
+      if (G > 0) boot_stitch(xs, shift);            // shift[] holds the column MEANS of the stitched returns here
+    } else if (two_pass && G > 0) {
       RegimeGen rg; regime_init(rg);
       R sum[3] = {0, 0, 0}, cmp[3] = {0, 0, 0};
       X4 ib; ib.x = ib.y = ib.z = ib.w = (R)0;
@@ -542,7 +681,10 @@ struct Trial {
     for (int g = 0; g < so; g++) {
       int reg = regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
-      if (two_pass && AUXSCR) {
+      if (MARKET == kMarketBoot) {
+        const X4 v = xs[g];
+        boot_day(g, reg, v.x, v.y, v.z, shift, x, vn, in);
+      } else if (two_pass && AUXSCR) {
         const X4 v = xs[g];
         x[0] = v.x + shift[0]; vn = v.w;
       } else if (two_pass) {
@@ -587,6 +729,8 @@ struct Trial {
       if (MARKET == kMarketSeries) {
         vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
         x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
+      } else if (MARKET == kMarketBoot) {
+        boot_day(g, reg, vcur.x, vcur.y, vcur.z, shift, x, vn, in);
       } else if (two_pass) {
         if (AUXSCR) { vn = vcur.w; in = icur; }
         else market_day<false, true>(g, reg, js, x, vn, in);

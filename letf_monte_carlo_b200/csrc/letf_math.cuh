@@ -57,7 +57,9 @@ LETF_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 enum : uint32_t {
   STREAM_START = 1, STREAM_SPELL = 2, STREAM_MKT0 = 3, STREAM_MKT1 = 4, STREAM_STRESS = 5,
   STREAM_JUMP = 6, STREAM_MKT_PAIR = 7 /* iid-normal market: one block per two days */,
-  STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T */
+  STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T and the second noise blend of BOOTSTRAP */,
+  STREAM_BOOT_A = 24 /* counter = block index: length, momentum A, block A, offset A */,
+  STREAM_BOOT_B = 25 /* momentum B, block B, offset B */, STREAM_BN0 = 26 /* +component: sample_returns noise */
 };
 
 struct RngKey {
@@ -111,6 +113,8 @@ template <> struct Mth<double> {
   static LETF_HD double log_(double x) { return ::log(x); }
   static LETF_HD double neg2log_(double x) { return -2.0 * ::log(x); }
   static LETF_HD double tanh_(double x) { return ::tanh(x); }
+  static LETF_HD double exp_(double x) { return ::exp(x); }
+  static LETF_HD double floor_(double x) { return ::floor(x); }
   static LETF_HD double pow_(double x, double y) { return ::pow(x, y); }
   static LETF_HD double abs_(double x) { return ::fabs(x); }
   static LETF_HD double div_(double a, double b) { return a / b; }
@@ -157,6 +161,8 @@ template <> struct Mth<float> {
   static LETF_HD float pow_(float x, float y) { return ::powf(x, y); }
   static LETF_HD float div_(float a, float b) { return a / b; }
 #endif
+  static LETF_HD float exp_(float x) { return ::expf(x); }
+  static LETF_HD float floor_(float x) { return ::floorf(x); }
   static LETF_HD float abs_(float x) { return ::fabsf(x); }
   static LETF_HD float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
   // (a + 0.5) * 2^-32, never 0; may round to exactly 1 (log -> 0, harmless)

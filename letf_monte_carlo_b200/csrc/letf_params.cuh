@@ -3,6 +3,9 @@
 #pragma once
 #include "../../include/letf_b200.h"
 #include <string.h>
+#ifndef LETF_DEVICE_ONLY
+#include <vector>
+#endif
 #include "letf_math.cuh"
 
 namespace letf {
@@ -34,6 +37,23 @@ template <typename R> struct DevJoint {
 
 template <typename R> struct DevVix { R phi, drift /* (1-phi)*target */, noise_std, jump_thr, jump_scale, denom; };
 template <typename R> struct DevStress { R liq_mu, liq_phi, liq_sigma, cr_mu, cr_phi, cr_sigma, jbase, jscale; };
+
+// legacy_hybrid block bootstrap (bootstrap.py:310-458, engine.py:50-80).  The candidate lists a block draw can
+// select from - every block of a (pool, regime), or only those whose cumulative SPY return is >= 0 / < 0
+// (momentum continuation, bootstrap.py:224-229) - are flattened on the host into (first history row, return) pairs.
+constexpr int kMarketBoot = LETF_MARKET_BOOTSTRAP;
+template <typename R> struct DevBoot {
+  int block_size, block_min, block_max, hist_len;
+  R log1mp;                     // ln(1 - 1 / block_mean): inverse CDF of the geometric block length
+  R bias[2];
+  R w1, nw1, w2, omw2, noise_w2;   // sampler weight, 1 - it; engine weight W, 1 - W, clip(1 - W, 0, 1)
+  R ch1[2][9], ch2[2][9];       // Cholesky factors of the two noise blends, row-major
+  int off[2][2][3], cnt[2][2][3];  // [pool A/B][regime][all / non-negative / negative]
+  R sigma[2][3];                // pool B kernel bandwidth = std of the candidates' block returns (bootstrap.py:247-249)
+  const R* hist[3];             // cleaned SPY, QQQ, TLT history
+  const int* cstart;
+  const R* cret;
+};
 
 template <typename R> struct DevStrategy {
   int type, asset, asset2, taxable, port, pad;
@@ -71,13 +91,34 @@ template <typename R, int NS, int NA> struct DevParams {
   int n_act, pad_a;
   R cash_daily[2], spread_cost[2], rebalance_cost;
   DevStrategy<R> strat[NS];
+  DevBoot<R> boot;
 };
+
 
 #ifndef LETF_DEVICE_ONLY
 // ---- host: validate + convert -------------------------------------------------------------
+// flat bootstrap tables in precision R (uploaded once per engine; the emulation build keeps them on the host)
+template <typename R> struct BootTables {
+  std::vector<R> hist;          // [3][hist_len]
+  std::vector<int> cstart;
+  std::vector<R> cret;
+  DevBoot<R> meta;              // offsets / counts / bandwidths; pointers filled by the owner
+};
 inline const char* validate_params(const LetfParams& s) {
   if (s.abi_version != LETF_ABI_VERSION) return "abi_version mismatch";
-  if (s.market_mode < 0 || s.market_mode > 2) return "bad market_mode";
+  if (s.market_mode < 0 || (s.market_mode > 2 && s.market_mode != LETF_MARKET_BOOTSTRAP)) return "bad market_mode";
+  if (s.market_mode == LETF_MARKET_BOOTSTRAP) {
+    const LetfBootstrap& b = s.boot;
+    if (b.hist_len <= 0 || !b.hist_spy || !b.hist_qqq || !b.hist_tlt) return "bootstrap history missing";
+    if (!(b.block_min >= 1 && b.block_min <= b.block_max && b.block_max <= b.block_size)) return "bootstrap block lengths must satisfy 1 <= min <= max <= block_size";
+    if (!(b.block_mean > 1.0)) return "bootstrap block_mean must be > 1";
+    for (int q = 0; q < 2; q++) for (int r = 0; r < 2; r++) {
+      const LetfBootstrapPool& pl = q ? b.pool_b[r] : b.pool_a[r];
+      if (pl.n_blocks <= 0 || !pl.start || !pl.block_ret) return "bootstrap pools must be non-empty (the synthetic-block fallback is not implemented)";
+      for (int i = 0; i < pl.n_blocks; i++)
+        if (pl.start[i] < 0 || pl.start[i] + b.block_size > b.hist_len) return "bootstrap block outside the history";
+    }
+  }
   if (s.sim_days < 0 || s.buffer_days < 0) return "negative day count";
   if (s.n_strategies < 0 || s.n_strategies > LETF_MAX_STRATEGIES) return "bad n_strategies";
   if (s.random_start && s.buffer_days <= 0) return "random_start needs buffer_days > 0";
@@ -121,9 +162,64 @@ inline uint32_t strategy_type_mask(const LetfParams& s) {
   return m;
 }
 
+template <typename R>
+inline void build_boot_tables(const LetfParams& s, BootTables<R>& t) {
+  const LetfBootstrap& b = s.boot;
+  memset(&t.meta, 0, sizeof(t.meta));
+  t.hist.clear(); t.cstart.clear(); t.cret.clear();
+  if (s.market_mode != LETF_MARKET_BOOTSTRAP) return;
+  DevBoot<R>& m = t.meta;
+  m.block_size = b.block_size; m.block_min = b.block_min; m.block_max = b.block_max; m.hist_len = b.hist_len;
+  m.log1mp = (R)::log(1.0 - 1.0 / b.block_mean);
+  for (int r = 0; r < 2; r++) {
+    m.bias[r] = (R)b.momentum_bias[r];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+      m.ch1[r][i * 3 + j] = (R)b.sampler_chol[r][i][j];
+      m.ch2[r][i * 3 + j] = (R)b.engine_chol[r][i][j];
+    }
+  }
+  m.w1 = (R)b.sampler_weight; m.nw1 = (R)(1.0 - b.sampler_weight);
+  m.w2 = (R)b.engine_weight; m.omw2 = (R)(1.0 - b.engine_weight);
+  { double nw = 1.0 - b.engine_weight; nw = nw < 0 ? 0 : (nw > 1 ? 1 : nw); m.noise_w2 = (R)nw; }
+  t.hist.resize((size_t)3 * b.hist_len);
+  for (int i = 0; i < b.hist_len; i++) {
+    t.hist[i] = (R)b.hist_spy[i]; t.hist[(size_t)b.hist_len + i] = (R)b.hist_qqq[i];
+    t.hist[(size_t)2 * b.hist_len + i] = (R)b.hist_tlt[i];
+  }
+  for (int q = 0; q < 2; q++) for (int r = 0; r < 2; r++) {
+    const LetfBootstrapPool& pl = q ? b.pool_b[r] : b.pool_a[r];
+    for (int kind = 0; kind < 3; kind++) {
+      m.off[q][r][kind] = (int)t.cstart.size();
+      double mean = 0; int nc = 0;
+      for (int i = 0; i < pl.n_blocks; i++) {
+        const double v = pl.block_ret[i];
+        if (kind == 0 || (kind == 1 && v >= 0) || (kind == 2 && v < 0)) {
+          t.cstart.push_back(pl.start[i]); t.cret.push_back((R)v); mean += v; nc++;
+        }
+      }
+      m.cnt[q][r][kind] = nc;
+      if (q == 1) {
+        double var = 0, sg = 0.05;
+        if (nc > 0) {
+          mean /= nc;
+          for (int i = 0; i < pl.n_blocks; i++) {
+            const double v = pl.block_ret[i];
+            if (kind == 0 || (kind == 1 && v >= 0) || (kind == 2 && v < 0)) var += (v - mean) * (v - mean);
+          }
+          sg = ::sqrt(var / nc);
+          if (sg < 1e-8) sg = 0.05;
+        }
+        m.sigma[r][kind] = (R)sg;
+      }
+    }
+  }
+}
+
 template <typename R, int NS, int NA>
-inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS, NA>& d) {
+inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS, NA>& d,
+                           const DevBoot<R>* boot = nullptr) {
   memset(&d, 0, sizeof(d));
+  if (boot) d.boot = *boot;
   d.market_mode = s.market_mode; d.T = s.sim_days; d.buffer = s.buffer_days; d.random_start = s.random_start;
   d.min_offset = s.buffer_days / 4 < 50 ? s.buffer_days / 4 : 50;
   d.offset_range = s.buffer_days - d.min_offset;

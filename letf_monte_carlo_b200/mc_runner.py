@@ -121,6 +121,20 @@ def _engine_for(params, keep, precision, device):
         nd = int(params.n_duration[r])
         durs.append(bytes(C.string_at(params.duration_samples[r], 4 * nd)) if nd > 0 else b"")
         probe.duration_samples[r] = None                   # host pointers are not part of the identity
+    if params.market_mode == abi.MARKET_BOOTSTRAP:            # same for the bootstrap's host tables
+        import hashlib
+        h = hashlib.sha256()
+        b = params.boot
+        for ptr in (b.hist_spy, b.hist_qqq, b.hist_tlt):
+            h.update(C.string_at(ptr, 8 * b.hist_len))
+        for pools, probe_pools in ((b.pool_a, probe.boot.pool_a), (b.pool_b, probe.boot.pool_b)):
+            for r in range(2):
+                h.update(C.string_at(pools[r].start, 4 * pools[r].n_blocks))
+                h.update(C.string_at(pools[r].block_ret, 8 * pools[r].n_blocks))
+                probe_pools[r].start = None
+                probe_pools[r].block_ret = None
+        probe.boot.hist_spy = probe.boot.hist_qqq = probe.boot.hist_tlt = None
+        durs.append(h.digest())
     key = (bytes(probe), tuple(durs), str(precision), dev)
     eng = _ENGINES.get(key)
     if eng is None or eng._h is None:
@@ -137,10 +151,12 @@ def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correla
     exactly as in the reference (strategy.py:55 is its only reader and ignores it)."""
     from .engine import PathEngine
     cfg = _default_cfg if cfg is None else cfg
-    if historical_df is not None and getattr(cfg, "SIM_ENGINE_MODE", "") == "legacy_hybrid" \
-            and getattr(cfg, "USE_BLOCK_BOOTSTRAP", False):
-        from .params import UnsupportedConfig
-        raise UnsupportedConfig("legacy_hybrid block bootstrap is not implemented on the GPU path")
+    if historical_df is not None and getattr(cfg, "USE_BLOCK_BOOTSTRAP", False):
+        # mc_runner.py:79-84: the sampler rides in the (shallow-copied) regime_model; the generator dispatch
+        # (engine.py:45-52) only reaches it when the engine mode is not institutional_v1 with a joint model
+        from .bootstrap import create_bootstrap_sampler
+        regime_model = dict(regime_model)
+        regime_model["bootstrap_sampler"] = create_bootstrap_sampler(historical_df, cfg=cfg)
     strategy_ids = list(strategy_ids)
     n_total = int(cfg.NUM_SIMULATIONS)
     params, keep = build_params(strategy_ids, time_horizon, regime_model, cfg)

@@ -1262,10 +1262,19 @@ int letf_oracle_fill_tape(const LetfParams* p, uint64_t seed, LetfTape* tp) {
     }
     for (int gday = 0; gday < G; gday++) {
       for (int a = 0; a < 3; a++)
-        tp->x[((int64_t)gday * 3 + a) * n + c] = p->market_mode == LETF_MARKET_PARAM_T ? xo_t(&g, p->param_t_df) : xo_n(&g);
+        tp->x[((int64_t)gday * 3 + a) * n + c] = (p->market_mode == LETF_MARKET_PARAM_T || p->market_mode == LETF_MARKET_BOOTSTRAP)
+                                                     ? xo_t(&g, p->param_t_df) : xo_n(&g);
+      if (p->market_mode == LETF_MARKET_BOOTSTRAP && tp->boot_t)
+        for (int a = 0; a < 3; a++) tp->boot_t[((int64_t)gday * 3 + a) * n + c] = xo_t(&g, p->param_t_df);
       if (p->market_mode == LETF_MARKET_JOINT_T) tp->chi2[(int64_t)gday * n + c] = 2 * xo_gamma(&g, p->joint[regf[gday]].nu / 2);
       if (p->has_vix_dynamics) { tp->vix_n[(int64_t)gday * n + c] = xo_n(&g); tp->irx_n[(int64_t)gday * n + c] = xo_n(&g); }
     }
+    if (p->market_mode == LETF_MARKET_BOOTSTRAP && tp->boot_len && tp->boot_u)
+      for (int kb = 0; kb < tp->max_blocks; kb++) {
+        tp->boot_len[(int64_t)kb * n + c] = (int)ceil(log(1.0 - xo_u(&g)) / log(1.0 - 1.0 / p->boot.block_mean));
+        if (tp->boot_len[(int64_t)kb * n + c] < 1) tp->boot_len[(int64_t)kb * n + c] = 1;
+        for (int q = 0; q < 6; q++) tp->boot_u[((int64_t)kb * 6 + q) * n + c] = xo_u(&g);
+      }
     for (int i = 0; i < T; i++) {
       if (p->has_stress) {
         tp->liq_n[(int64_t)i * n + c] = xo_n(&g); tp->cred_n[(int64_t)i * n + c] = xo_n(&g);

@@ -108,7 +108,9 @@ def trade_list(params: abi.Params, tape: HostTape, trial: int, strategy: int, ca
 
 
 def fill_tape(params: abi.Params, n_tapes: int, seed: int, max_spells: int = 2048) -> HostTape:
-    tp = HostTape(n_tapes, params.sim_days + params.buffer_days, params.sim_days, max_spells)
+    G = params.sim_days + params.buffer_days
+    boot = params.market_mode == abi.MARKET_BOOTSTRAP
+    tp = HostTape(n_tapes, G, params.sim_days, max_spells, (G // max(params.boot.block_min, 1) + 2) if boot else 0)
     ts = tp.as_struct()
     lib().letf_oracle_fill_tape(C.byref(params), seed, C.byref(ts))
     return tp

@@ -21,7 +21,13 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
   constexpr int NA = kAssets;
   static KArgs<R, NS, NA> ka;
   const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
-  convert_params<R, NS, NA>(*sp, dd, ka.p);
+  static BootTables<R> boot;                       // host copies of the bootstrap tables (device blob in the product)
+  build_boot_tables<R>(*sp, boot);
+  if (sp->market_mode == LETF_MARKET_BOOTSTRAP) {
+    for (int c = 0; c < 3; c++) boot.meta.hist[c] = boot.hist.data() + (size_t)c * sp->boot.hist_len;
+    boot.meta.cstart = boot.cstart.data(); boot.meta.cret = boot.cret.data();
+  }
+  convert_params<R, NS, NA>(*sp, dd, ka.p, &boot.meta);
   if (tape) ka.tape = *tape; else memset(&ka.tape, 0, sizeof(ka.tape));
   ka.out = *out;
   ka.seed = seed; ka.first_trial = first; ka.n_trials = n;
@@ -50,9 +56,11 @@ extern "C" int letf_emu_run(const LetfParams* sp, int precision, const LetfTape*
   if (err) return -1;
 #define GO(R, MK) return run_t<R, MK>(sp, tape, out, seed, first, n, rng_mode, log_trial, log_strategy, log_cap, log_count, log_day, log_asset, log_action, log_shares, log_price)
   if (precision == LETF_PREC_F64) {
-    if (sp->market_mode == 0) GO(double, 0); else if (sp->market_mode == 1) GO(double, 1); else GO(double, 2);
+    if (sp->market_mode == 0) GO(double, 0); else if (sp->market_mode == 1) GO(double, 1);
+    else if (sp->market_mode == LETF_MARKET_BOOTSTRAP) GO(double, 4); else GO(double, 2);
   } else {
-    if (sp->market_mode == 0) GO(float, 0); else if (sp->market_mode == 1) GO(float, 1); else GO(float, 2);
+    if (sp->market_mode == 0) GO(float, 0); else if (sp->market_mode == 1) GO(float, 1);
+    else if (sp->market_mode == LETF_MARKET_BOOTSTRAP) GO(float, 4); else GO(float, 2);
   }
 #undef GO
 }

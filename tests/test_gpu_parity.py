@@ -56,7 +56,7 @@ def test_f64_tape_matches_oracle_all_outputs(name, engine_lib):
     np.testing.assert_allclose(h.journal_volume, o.journal_volume, rtol=1e-11, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1"])
+@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1", "boot_1y"])
 def test_f32_tape_close_to_reference(name, engine_lib):
     """fp32 throughput mode on the same tape: 2e-4 relative on terminal wealth over <= 5 years,
     1e-4 absolute on drawdown, < 2 % of (strategy, trial) cells with a different trade count."""
@@ -81,15 +81,19 @@ def test_constant_window_corner(engine_lib):
 
 
 @pytest.mark.parametrize("variant,years,precision", [("default", 2, "f64"), ("vix_te", 1, "f64"), ("no_joint", 1, "f64"),
-                                                     ("durations", 1, "f64"), ("normal_c2", 3, "f64")])
+                                                     ("durations", 1, "f64"), ("normal_c2", 3, "f64"),
+                                                     ("boot", 2, "f64")])
 def test_philox_record_replays_through_oracle(variant, years, precision, engine_lib):
     """the on-device Philox path records the variates it consumed; the oracle on that tape must agree"""
     sids = ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"]
-    doc = {"case": dict(variant=variant, years=years, n_tapes=40, seed=0, cfg={}, strategies=sids)}
+    doc = {"case": dict(variant=variant, years=years, n_tapes=40, seed=0,
+                        cfg={"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {}, strategies=sids)}
     ns, model, params, keep, _ = case_inputs(doc)
     n_t = 40
     n = n_t * (2 if params.antithetic_pairs else 1)
-    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    G = params.sim_days + params.buffer_days
+    rec = HostTape(n_t, G, params.sim_days, 512,
+                   (G // params.boot.block_min + 2) if params.market_mode == abi.MARKET_BOOTSTRAP else 0)
     with _engine(params, keep, precision) as eng:
         out = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec, journal=True)
         plain = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX, journal=True)

@@ -53,6 +53,46 @@ def test_build_params_dispatch_and_rejections():
     assert p.transition[0][0] == 1.0 and p.transition[0][1] == 0.0
 
 
+def test_bootstrap_pools_and_dispatch():
+    """bootstrap.py:49-160: stride-21 blocks of BOOTSTRAP_BLOCK_SIZE rows, regime = median VIX >= 25, pool B only in the
+    real-QQQ era, NaN -> 0 in the gathered history, blocks with > size // 4 missing SPY rows skipped; dispatch as
+    engine.py:45-52 (the sampler is only reached outside institutional_v1)."""
+    from letf_monte_carlo_b200.bootstrap import BlockBootstrapPools, create_bootstrap_sampler
+    hist = synthetic.synthetic_history(n_days=6000, seed=3, start="1990-01-02", nan_every=53)
+    pools = create_bootstrap_sampler(hist, cfg=synthetic.config_namespace())
+    assert isinstance(pools, BlockBootstrapPools) and pools.block_size == 168
+    cnt = pools.counts()
+    assert sum(cnt["A"]) == len(range(0, 6000 - 168 + 1, 21)) and 0 < sum(cnt["B"]) < sum(cnt["A"])
+    assert not np.isnan(pools.hist_spy).any() and not np.isnan(pools.hist_qqq).any()
+    spy = np.nan_to_num(hist["SPY_Ret"].values, nan=0.0)
+    for r in (0, 1):
+        start, ret = pools.pool_a[r]
+        assert (start % 21 == 0).all()
+        for s0, rr in list(zip(start, ret))[:5]:
+            assert rr == np.prod(1 + spy[s0:s0 + 168]) - 1
+            med = np.nanmedian(hist["VIX"].values[s0:s0 + 168])
+            assert (0 if med < 25 else 1) == r
+        sb, _ = pools.pool_b[r]
+        assert all(hist.index[s0] >= np.datetime64("1999-03-10") for s0 in sb)
+    model = synthetic.fallback_regime_model()
+    model["bootstrap_sampler"] = pools
+    p, keep = build_params(["S1"], 1, model, synthetic.config_namespace())                       # institutional wins
+    assert p.market_mode == abi.MARKET_JOINT_T
+    p, keep = build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid"))
+    assert p.market_mode == abi.MARKET_BOOTSTRAP and p.has_stress == 0 and p.has_funding == 0 and p.moment_matching == 0
+    assert p.boot.hist_len == 6000 and p.boot.block_min == 21 and p.boot.block_max == 168 and p.boot.block_mean == 84
+    assert p.boot.pool_a[0].n_blocks == cnt["A"][0] and p.boot.pool_b[1].n_blocks == cnt["B"][1]
+    assert p.boot.sampler_weight == 0.85 and p.boot.engine_weight == 0.80
+    p, _ = build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid", USE_BLOCK_BOOTSTRAP=False))
+    assert p.market_mode == abi.MARKET_PARAM_T
+    with pytest.raises(UnsupportedConfig):       # min <= max <= block size
+        build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid", BOOTSTRAP_BLOCK_MAX=200))
+    early = synthetic.synthetic_history(n_days=2000, seed=3, start="1980-01-02")                 # no real-QQQ rows: pool B empty
+    model["bootstrap_sampler"] = create_bootstrap_sampler(early)
+    with pytest.raises(UnsupportedConfig):
+        build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid"))
+
+
 def test_shard_range_partitions_trials():
     for n in (0, 1, 7, 200, 1001, 10_000_000):
         for ws in (1, 2, 3, 8):

@@ -46,7 +46,7 @@ def test_f64_constant_window_corner_matches_oracle():
     assert o.num_trades[9].min() > 0      # S10 (downside vol) traded
 
 
-@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1"])
+@pytest.mark.parametrize("name", ["inst_1y", "layers_c2_5y", "param_t_1y", "vix_te_1y", "voldrag_c1", "boot_1y"])
 def test_f32_kernel_body_close_to_reference(name):
     """throughput mode (fp32 shocks / returns / signals, fp64 wealth compounding) on the SAME tape:
     stated tolerance 2e-4 relative on terminal wealth over <= 5 years, 1e-4 absolute on drawdown."""
@@ -58,16 +58,24 @@ def test_f32_kernel_body_close_to_reference(name):
     assert np.mean(out.num_trades != nt) < 0.02
 
 
-@pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2)])
+def _blank_tape(params, n_tapes, max_spells):
+    G = params.sim_days + params.buffer_days
+    boot = params.market_mode == abi.MARKET_BOOTSTRAP
+    return HostTape(n_tapes, G, params.sim_days, max_spells, (G // max(params.boot.block_min, 1) + 2) if boot else 0)
+
+
+@pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2), ("boot", 1)])
 def test_philox_record_replays_through_oracle(variant, years):
     """RNG_PHILOX_RECORD writes every variate it consumes; feeding that tape to the oracle must give
     the same results -> the Philox path consumes draws exactly where the tape semantics say."""
-    case = dict(variant=variant, years=years, n_tapes=3, seed=0, cfg={},
+    case = dict(variant=variant, years=years, n_tapes=3, seed=0,
+                cfg={"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {},
                 strategies=ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"])
     doc = {"case": case}
     ns, model, params, keep, _ = case_inputs(doc)
+    assert (params.market_mode == abi.MARKET_BOOTSTRAP) == (variant == "boot")
     G = params.sim_days + params.buffer_days
-    rec = HostTape(3, G, params.sim_days, 256)
+    rec = _blank_tape(params, 3, 256)
     n = 6 if params.antithetic_pairs else 3
     e = emu.run(params, rec, precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX_RECORD, seed=1234, n=n)
     assert not (e.flags & abi.FLAG_SPELL_OVERFLOW).any()
@@ -226,3 +234,32 @@ def test_lean_fast_variant_config5_shape():
     np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-5)
     np.testing.assert_allclose(two.final_wealth, fast.final_wealth, rtol=1e-6)
     np.testing.assert_allclose(fast.max_dd, slow.max_dd, atol=2e-6)
+
+
+def test_bootstrap_block_draws_follow_the_reference_rules():
+    """Philox block draws of the legacy_hybrid bootstrap (bootstrap.py:302-308, 212-262): recorded block lengths are
+    geometric(1 / BLOCK_MEAN), the six selection variates uniform, both noise matrices t(STUDENT_T_DF); and the
+    stitched market is a pure function of (seed, trial): a second run reproduces it."""
+    doc = {"case": dict(variant="boot", years=2, n_tapes=1, seed=0, cfg={"SIM_ENGINE_MODE": "legacy_hybrid"},
+                        strategies=["S1", "S2", "B_QQQ", "B_TLT"])}
+    ns, model, params, keep, _ = case_inputs(doc)
+    n_t = 64
+    rec = _blank_tape(params, n_t, 512)
+    a = emu.run(params, rec, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX_RECORD, seed=11, n=2 * n_t)
+    b = emu.run(params, _blank_tape(params, 1, 1), precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=11, n=2 * n_t)
+    np.testing.assert_array_equal(a.final_wealth, b.final_wealth)
+    G = rec.gen_days
+    lens = rec.boot_len.astype(np.int64)
+    used = np.zeros_like(lens, dtype=bool)                 # blocks actually consumed: until the column covers G days
+    cover = np.zeros(n_t, np.int64)
+    for k in range(rec.max_blocks):
+        used[k] = cover < G
+        cover += np.clip(lens[k], params.boot.block_min, params.boot.block_max)
+    p = 1.0 / params.boot.block_mean
+    _ks(lens[used] - 1 + np.random.default_rng(0).random(used.sum()), lambda x: 1 - (1 - p) ** np.maximum(x, 0))  # jittered geometric
+    for s in range(6):
+        _ks(rec.boot_u[:, s, :][used], stats.uniform.cdf)
+    cons = np.arange(G)[:, None] < (rec.start_offset[None, :] + params.sim_days)
+    for c in range(3):
+        _ks(rec.boot_t[:, c, :][cons], stats.t(params.param_t_df).cdf)
+        _ks(rec.x[:, c, :][cons], stats.t(params.param_t_df).cdf)
