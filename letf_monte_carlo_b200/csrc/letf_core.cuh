@@ -392,7 +392,7 @@ struct Trial {
   // `bias` (bootstrap.py:224-229); pool B is then weighted by a Gaussian kernel around the economy block's SPY
   // return (:232-259, numpy's choice = cdf.searchsorted(u, 'right')), pool A is uniform (:262).  Returns the block's
   // first history row.
-  LETF_HDN int boot_pick(int pool, int regime, bool have_last, R last_ret, R u_mom, R u_idx, bool use_target, R target) const {
+  LETF_HD int boot_pick(int pool, int regime, bool have_last, R last_ret, R u_mom, R u_idx, bool use_target, R target) const {
     const DevBoot<R>& b = p.boot;
     int kind = 0;
     if (have_last) {
@@ -422,7 +422,7 @@ struct Trial {
 
   // pass 1: stitch the blocks into the per-thread scratch column and return the three column means
   template <typename X4>
-  LETF_HDN void boot_stitch(X4* xs, R (&mean)[3]) {
+  LETF_HD void boot_stitch(X4* xs, R (&mean)[3]) {
     const DevBoot<R>& b = p.boot;
     const int G = p.T + p.buffer;
     RegimeGen rgl; regime_init(rgl);
@@ -482,7 +482,7 @@ struct Trial {
 
   // pass 2, one generated day: both correlated Student-t blends on the stitched returns, and the day's VIX / IRX normals
   LETF_HD void boot_day(int g, int reg, R b0, R b1, R b2, const R (&mean)[3], R x[3], R& vix_n, R& irx_n) {
-    const DevBoot<R>& b = p.boot;
+    const auto& b = p.boot;
     R z1[3], z2[3];
     if (use_tape) {
       for (int c = 0; c < 3; c++) { z1[c] = tp_get(ka.tape.boot_t, (int64_t)g * 3 + c); z2[c] = tp_get(ka.tape.x, (int64_t)g * 3 + c); }
@@ -502,20 +502,23 @@ struct Trial {
       }
     }
     if (b.nw1 > (R)0) {                                               // bootstrap.py:386-449
-      const R* C = b.ch1[reg];
-      const R c0 = C[0] * z1[0] + C[1] * z1[1] + C[2] * z1[2];
-      const R c1 = C[3] * z1[0] + C[4] * z1[1] + C[5] * z1[2];
-      const R c2 = C[6] * z1[0] + C[7] * z1[1] + C[8] * z1[2];
+      // (indexed through the parameter block, not through a pointer into it: constant-bank loads, no generic LD)
+#define C(i) b.ch1[reg][i]
+      const R c0 = C(0) * z1[0] + C(1) * z1[1] + C(2) * z1[2];
+      const R c1 = C(3) * z1[0] + C(4) * z1[1] + C(5) * z1[2];
+      const R c2 = C(6) * z1[0] + C(7) * z1[1] + C(8) * z1[2];
+#undef C
       const R s0 = reg == 0 ? (R)0.007 : (R)0.022, s1 = s0 * (R)1.35, s2 = s0 * (R)0.5;
       b0 = b.w1 * b0 + b.nw1 * (c0 * s0 + mean[0]);
       b1 = b.w1 * b1 + b.nw1 * (c1 * s1 + mean[1]);
       b2 = b.w1 * b2 + b.nw1 * (c2 * s2 + mean[2]);
     }
     {                                                                 // engine.py:57-79
-      const R* C = b.ch2[reg];
-      const R x0 = C[0] * z2[0] + C[1] * z2[1] + C[2] * z2[2];
-      const R x1 = C[3] * z2[0] + C[4] * z2[1] + C[5] * z2[2];
-      const R x2 = C[6] * z2[0] + C[7] * z2[1] + C[8] * z2[2];
+#define C(i) b.ch2[reg][i]
+      const R x0 = C(0) * z2[0] + C(1) * z2[1] + C(2) * z2[2];
+      const R x1 = C(3) * z2[0] + C(4) * z2[1] + C(5) * z2[2];
+      const R x2 = C(6) * z2[0] + C(7) * z2[1] + C(8) * z2[2];
+#undef C
       const R sd = p.reg_std[reg], qsd = (R)1.35 * sd, tsd = (R)0.55 * sd;
       const R n0 = b.noise_w2 * sd * (R)0.55 * x0, n1 = b.noise_w2 * qsd * (R)0.45 * x1, n2 = b.noise_w2 * tsd * (R)0.35 * x2;
       x[0] = b.w2 * b0 + b.omw2 * (b0 + n0);

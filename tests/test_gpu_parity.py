@@ -465,3 +465,33 @@ def test_horizon_leverage_grid_config5(engine_lib):
         se = L * vol / np.sqrt(2520 * n)
         assert abs(g[(10.0, sid)] - want) < 5 * se + 2e-6, (sid, g[(10.0, sid)], want)
     grid.close()
+
+
+def test_bootstrap_lean_kernel_vs_generic_and_oracle(engine_lib):
+    """legacy_hybrid block bootstrap: bench.py's `boot` workload runs the lean buy&hold build.
+    Chain of evidence on the device: lean (Philox) == generic fp32 build recording the same counters (identical
+    block choices and regime days, fp32 reassociation only on wealth), and the oracle replaying that tape agrees."""
+    sids = ["S1", "S2", "S3"]
+    doc = {"case": dict(variant="boot", years=3, n_tapes=128, seed=0, cfg={"SIM_ENGINE_MODE": "legacy_hybrid"},
+                        strategies=sids)}
+    ns, model, params, keep, _ = case_inputs(doc)
+    assert params.market_mode == abi.MARKET_BOOTSTRAP
+    n_t = 128
+    n = 2 * n_t if params.antithetic_pairs else n_t
+    G = params.sim_days + params.buffer_days
+    rec = HostTape(n_t, G, params.sim_days, 512, G // params.boot.block_min + 2)
+    with _engine(params, keep, "f32") as eng:
+        lean = eng.run_host(n, seed=2718)
+        regs_lean = eng.launch_info()["regs_per_thread"]
+        gen = eng.run_host(n, seed=2718, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+        regs_gen = eng.launch_info()["regs_per_thread"]
+    assert regs_lean != regs_gen                     # two different instantiations really ran
+    o = orc.run(params, rec)
+    np.testing.assert_array_equal(lean.regime_days, gen.regime_days)
+    np.testing.assert_array_equal(gen.regime_days, o.regime_days)
+    np.testing.assert_array_equal(lean.start_offset, o.start_offset)
+    np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=5e-5)
+    np.testing.assert_allclose(gen.final_wealth, o.final_wealth, rtol=3e-4)
+    np.testing.assert_allclose(lean.max_dd, o.max_dd, atol=1e-4)
+    # antithetic twins are identical paths outside the joint-t generator (calibration.py:563-564 is its only reader)
+    np.testing.assert_array_equal(lean.final_wealth[:, 0::2], lean.final_wealth[:, 1::2])
