@@ -168,6 +168,7 @@ struct Trial {
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
+  static constexpr bool KEYREF = NA < kAssets; // calling convention of the non-inlined sampler retry loop (letf_math.cuh)
   static constexpr bool HAS_VOL = (TM & kVolTypes) != 0;
   static constexpr bool HAS_ACTIVE = (TM & ~((1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT))) != 0;
   static constexpr bool HAS_SMA200 = TM_HAS(LETF_ST_SMA) || TM_HAS(LETF_ST_SMA_BAND) || TM_HAS(LETF_ST_COMPOSITE) ||
@@ -276,7 +277,7 @@ struct Trial {
       if (WANT_X && MARKET == LETF_MARKET_PARAM_T) {
         for (int c = 0; c < 3; c++) {
           U4 b = rng_block(key, (uint32_t)g, STREAM_PT0 + c);
-          R t = student_t_block<R>(b, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
+          R t = student_t_block<R, KEYREF>(b, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
           if (c == 0) z0 = t; else if (c == 1) z1 = t; else z2 = t;
         }
       }
@@ -310,7 +311,7 @@ struct Trial {
       if (use_tape) u = tp_get(ka.tape.chi2, g);
       else {
         u = jp.nu_fast_k ? chi2_int_fast<R>(jp.nu_fast_k, cw0, cw1, nchi)
-                         : chi2_marsaglia_tsang<R>(jp.nu, nchi, cw0, key, (uint32_t)g, STREAM_MKT1);
+                         : chi2_marsaglia_tsang<R, KEYREF>(jp.nu, nchi, cw0, key, (uint32_t)g, STREAM_MKT1);
         if (rec) tp_put(ka.tape.chi2, g, u);
       }
       // GARCH / DCC recursions (calibration.py:532-548)
@@ -490,9 +491,9 @@ struct Trial {
     } else {
       for (int c = 0; c < 3; c++) {
         const U4 w1 = rng_block(key, (uint32_t)g, STREAM_BN0 + c);
-        z1[c] = student_t_block<R>(w1, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_BN0 + c);
+        z1[c] = student_t_block<R, KEYREF>(w1, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_BN0 + c);
         const U4 w2 = rng_block(key, (uint32_t)g, STREAM_PT0 + c);
-        z2[c] = student_t_block<R>(w2, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
+        z2[c] = student_t_block<R, KEYREF>(w2, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_PT0 + c);
       }
       const U4 w = rng_block(key, (uint32_t)g, STREAM_MKT1);
       M::box_muller(w.x, w.y, vix_n, irx_n);
@@ -569,11 +570,13 @@ struct Trial {
   // pandas recomputes a rolling-variance window from scratch when a removal collapses it
   // (letf_rolling.cuh): re-add the w-1 surviving observations, oldest first, from the return ring
   // (cursor = slot today's return will be written to).  Rare: the window just became constant.
-  LETF_HDN void revar(RollVar<R, EXACT>& rv, const R* ring, int cursor, int w, bool downside) const {
+  // (static: a non-inlined MEMBER would take `this`, and once `this` escapes every parameter read of the day loop
+  //  turns from a constant-bank load into a generic load through the saved reference)
+  static LETF_HDN void revar_(RollVar<R, EXACT>& rv, const R* ring, int64_t nthreads, int cursor, int w, bool downside) {
     rv.init();
     for (int j = w - 1; j >= 1; j--) {
       int c = cursor - j; if (c < 0) c += kRingA;
-      R v = ring[(int64_t)c * ka.nthreads];
+      R v = ring[(int64_t)c * nthreads];
       rv.add(downside ? (v < (R)0 ? v : (R)0) : v);
     }
   }
@@ -788,7 +791,7 @@ struct Trial {
             if (use_tape) t5 = tp_get(ka.tape.jump_t, i);
             else {
               U4 bj = rng_block(key, (uint32_t)g, STREAM_JUMP);
-              t5 = student_t_block<R>(bj, (R)5, 5, key, (uint32_t)g, STREAM_JUMP);
+              t5 = student_t_block<R, KEYREF>(bj, (R)5, 5, key, (uint32_t)g, STREAM_JUMP);
               if (rec) tp_put(ka.tape.jump_t, i, t5);
             }
             if (ju < jp) {
@@ -854,7 +857,7 @@ struct Trial {
               // builds with a compile-time asset mask also fix the tracking-error dof at cfg.ASSETS' defaults
               // (t(5) for the four LETFs, t(10) for SPY / QQQ; letf_api.cu checks it): no sampler dispatch
               if (AM != 0 && NA == kAssets && !EXACT) innov = a >= 4 ? student_t10<R>(b) : student_t5<R>(b);
-              else innov = student_t_block<R>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
+              else innov = student_t_block<R, KEYREF>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
               if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);
             }
             R ds = u < (R)0 ? ap.te_down : (R)0.98;
@@ -973,11 +976,11 @@ struct Trial {
           if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[roff(c)]; }
           if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[roff(c)]; }
         }
-        if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar(sg.v5, ring, sg.cA, 5, false); sg.v5.add(ra); }
-        if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar(sg.v10, ring, sg.cA, 10, false); sg.v10.add(ra); }
-        if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar(sg.v20, ring, sg.cA, 20, false); sg.v20.add(ra); }
-        if (HAS_V60) { if (i >= 60 && sg.v60.remove(r60)) revar(sg.v60, ring, sg.cA, 60, false); sg.v60.add(ra); }
-        if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar(sg.dv20, ring, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
+        if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar_(sg.v5, ring, nth, sg.cA, 5, false); sg.v5.add(ra); }
+        if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar_(sg.v10, ring, nth, sg.cA, 10, false); sg.v10.add(ra); }
+        if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar_(sg.v20, ring, nth, sg.cA, 20, false); sg.v20.add(ra); }
+        if (HAS_V60) { if (i >= 60 && sg.v60.remove(r60)) revar_(sg.v60, ring, nth, sg.cA, 60, false); sg.v60.add(ra); }
+        if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar_(sg.dv20, ring, nth, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
         if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
         if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
         ring[roff(sg.cA)] = ra;

@@ -256,8 +256,12 @@ LETF_HD R chi2_int_fast(int k, uint32_t wa, uint32_t wb, R nrm) {
 
 // Marsaglia-Tsang gamma(shape a >= 1) * 2 = chi2(2a).  First attempt uses (n0, u0) supplied by the
 // caller's block; retries pull blocks (stream, sub = 1, 2, ...).
+// Two calling conventions for the (rare, non-inlined) retry loop.  By value keeps the caller's Trial object out of
+// memory: with a reference to its `key` member the object escapes and, in the large typed / generic builds, every
+// parameter read of the day loop degrades from a constant-bank load to a generic load through the saved reference.
+// By reference costs the lean 128-register builds nothing extra (their key then lives on the stack).
 template <typename R>
-LETF_HDN R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+LETF_HD R chi2_mt_body(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
   R a = (R)0.5 * nu;
   R d = a - (R)(1.0 / 3.0);
@@ -279,6 +283,18 @@ LETF_HDN R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uin
     uw = b.z;
   }
   return (R)2 * d;  // unreachable in practice (acceptance > 95 % per attempt)
+}
+template <typename R>
+LETF_HDN R chi2_mt_byval(R nu, R n0, uint32_t u0w, const RngKey key, uint32_t day, uint32_t stream) {
+  return chi2_mt_body<R>(nu, n0, u0w, key, day, stream);
+}
+template <typename R>
+LETF_HDN R chi2_mt_byref(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+  return chi2_mt_body<R>(nu, n0, u0w, key, day, stream);
+}
+template <typename R, bool KEYREF = false>
+LETF_HD R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+  return KEYREF ? chi2_mt_byref<R>(nu, n0, u0w, key, day, stream) : chi2_mt_byval<R>(nu, n0, u0w, key, day, stream);
 }
 
 struct DfInfo {      // host-precomputed per distribution
@@ -332,7 +348,7 @@ LETF_HD R student_t10(const U4& b) {
 }
 
 // Student-t(df) from one Philox block: N0 / sqrt(chi2(df) / df).
-template <typename R>
+template <typename R, bool KEYREF = false>
 LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
   if (sizeof(R) == 4 && fast_k == 5) return student_t5<R>(b);
@@ -340,7 +356,7 @@ LETF_HD R student_t_block(const U4& b, R df, int fast_k, const RngKey& key, uint
   R n0, n1;
   M::box_muller(b.x, b.y, n0, n1);
   R c2 = fast_k ? chi2_int_fast<R>(fast_k, b.z, b.w, n1)
-                : chi2_marsaglia_tsang<R>(df, n1, b.z, key, day, stream);
+                : chi2_marsaglia_tsang<R, KEYREF>(df, n1, b.z, key, day, stream);
   if (sizeof(R) == 8) return n0 * M::sqrt_(M::div_(df, rmax(c2, (R)1e-30)));
   return n0 * (M::sqrt_(df) * M::rsqrt_(rmax(c2, (R)1e-30)));   // sqrt(df) is loop-invariant: one MUFU per variate
 }
