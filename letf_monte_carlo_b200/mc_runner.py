@@ -92,6 +92,15 @@ class MonteCarloRun(dict):
         for s, sid in enumerate(strategy_ids):
             self[sid] = StrategyResults(self, sid, s)
 
+    def taxable_summary(self, tax_fn=None, tax_config=None, cfg=None, **kw):
+        """Rows of the reference's taxable-brokerage table (reporting.py:399-560): <= 50 wealth-ranked trials per
+        strategy are replayed on the device for their Trade_List and taxed by `tax_fn` (tax_sampling.py)."""
+        from .tax_sampling import taxable_summary
+        cfg = _default_cfg if cfg is None else cfg
+        return taxable_summary(self, self.years, tax_fn=tax_fn, tax_config=tax_config,
+                               initial_capital=float(cfg.INITIAL_CAPITAL), names=cfg.STRATEGIES,
+                               taxable_ids=[s for s in TAXABLE_IDS if s in self], **kw)
+
     def metadata(self, i: int) -> dict:
         o = self.out
         fl = int(o.flags[i])

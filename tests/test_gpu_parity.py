@@ -495,3 +495,29 @@ def test_bootstrap_lean_kernel_vs_generic_and_oracle(engine_lib):
     np.testing.assert_allclose(lean.max_dd, o.max_dd, atol=1e-4)
     # antithetic twins are identical paths outside the joint-t generator (calibration.py:563-564 is its only reader)
     np.testing.assert_array_equal(lean.final_wealth[:, 0::2], lean.final_wealth[:, 1::2])
+
+
+def test_sampled_tax_path_replays_trade_lists_on_device(engine_lib):
+    """parallel_monte_carlo_fixed -> MonteCarloRun.taxable_summary.  Only the <= 50 wealth-ranked
+    trials per strategy are re-simulated for their Trade_List (reporting.py:457-467); each replayed list must carry
+    exactly the journal entries the bulk launch counted for that trial."""
+    from letf_monte_carlo_b200 import parallel_monte_carlo_fixed
+    ns = synthetic.config_namespace(NUM_SIMULATIONS=160, GPU_PRECISION="f64")
+    sids = ["S2", "S7", "S8", "S19"]
+    run = parallel_monte_carlo_fixed(sids, 1, synthetic.fallback_regime_model(), {}, cfg=ns, verbose=False, device=0)
+    bulk = run.engine.run_host(160, seed=run.seed, journal=True)
+    seen = []
+
+    def tax(trades, years, capital, strategy_id, tax_config):
+        seen.append((strategy_id, len(trades)))
+        return 0.2 * sum(t["dollar_amount"] for t in trades if t["action"] == "SELL") * 0.01
+    rows = run.taxable_summary(tax_fn=tax, tax_config={}, cfg=ns)
+    assert sorted(r["id"] for r in rows) == ["S19", "S7", "S8"]
+    for r in rows:
+        s = sids.index(r["id"])
+        assert len(r["sampled_trials"]) == 50
+        for i in r["sampled_trials"][::7]:
+            assert len(run[r["id"]].trade_list(i)) == bulk.journal_count[s, i]
+        assert r["pcts"]["p60"]["post_wealth"] <= r["pcts"]["p60"]["pre_wealth"] + 1e-9
+        assert 0.0 <= r["win"] <= 100.0
+    assert len(seen) <= 150 and all(n > 0 for _, n in seen)
