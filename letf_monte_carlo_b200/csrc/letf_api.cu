@@ -516,6 +516,23 @@ int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_t
   ce = e->pin_out.reserve(L.total ? L.total : 256);
   if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "pinned staging: " + std::string(cudaGetErrorString(ce))); }
   CK(cudaMemcpyAsync(e->pin_out.p, base, L.total, cudaMemcpyDeviceToHost, (cudaStream_t)0));
+  // while the kernel runs: fault in the caller's (typically freshly allocated, still unmapped) result pages, so the
+  // scatter below is a plain copy instead of a few thousand first-touch page faults on the critical path
+  {
+    auto touch = [&](void* dst, int field, size_t elem, int nrows) {
+      if (!dst || !L.bytes[field]) return;
+      for (int r = 0; r < nrows; r++) {
+        volatile char* q = (volatile char*)dst + (size_t)r * N * elem;
+        const size_t len = n * elem;
+        for (size_t o = 0; o < len; o += 4096) q[o] = 0;
+        if (len) q[len - 1] = 0;
+      }
+    };
+    touch(host_out->final_wealth, 0, 8, S); touch(host_out->max_dd, 1, 8, S); touch(host_out->num_trades, 2, 4, S);
+    touch(host_out->journal_count, 3, 4, S); touch(host_out->journal_volume, 4, 8, S);
+    touch(host_out->start_offset, 5, 4, 1); touch(host_out->flags, 6, 4, 1); touch(host_out->regime_days, 7, 4, 2);
+    touch(host_out->jump_days, 8, 4, 1);
+  }
   CK(cudaStreamSynchronize((cudaStream_t)0));
   const char* hb = (const char*)e->pin_out.p;
   auto rows = [&](void* dst, int field, size_t elem, int nrows) {
