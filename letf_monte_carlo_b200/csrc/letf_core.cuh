@@ -252,6 +252,11 @@ struct Trial {
   // Also returns the two "phase-2" normals of the day (VIX noise, IRX noise) when WANT_AUX.
   template <bool WANT_X, bool WANT_AUX>
   LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n) {
+    market_day<WANT_X, WANT_AUX>(g, reg, js, x, vix_n, irx_n, p.joint[reg]);
+  }
+  // jp: the joint-t constants of `reg` (pass 1 of the two-pass builds keeps them in registers between regime switches)
+  template <bool WANT_X, bool WANT_AUX>
+  LETF_HD void market_day(int g, int reg, JointState& js, R x[3], R& vix_n, R& irx_n, const DevJoint<R>& jp) {
     R z0 = 0, z1 = 0, z2 = 0, nchi = 0;
     uint32_t cw0 = 0, cw1 = 0;
     if (use_tape) {
@@ -305,7 +310,6 @@ struct Trial {
       x[1] = (R)1.15 * x[0] + (R)0.006 * xb;
       x[2] = (R)-0.12 * x[0] + (R)0.004 * xc;
     } else {
-      const DevJoint<R>& jp = p.joint[reg];
       // chi-square mixing variable (calibration.py:565)
       R u;
       if (use_tape) u = tp_get(ka.tape.chi2, g);
@@ -625,13 +629,20 @@ struct Trial {
       RegimeGen rg; regime_init(rg);
       R sum[3] = {0, 0, 0}, cmp[3] = {0, 0, 0};
       X4 ib; ib.x = ib.y = ib.z = ib.w = (R)0;
+      X4 vprev; vprev.x = vprev.y = vprev.z = vprev.w = (R)0;
+      DevJoint<R> jpc = p.joint[0];            // regime-indexed constants cached in registers, reloaded on a switch
+      int jreg = 0;
       for (int g = 0; g < G; g++) {
         int reg = regime_next(rg);
         R x[3], d0 = 0, d1 = 0;
-        if (AUXSCR) market_day<true, true>(g, reg, js, x, d0, d1);
-        else market_day<true, false>(g, reg, js, x, d0, d1);
+        if (!EXACT && reg != jreg) { jpc = p.joint[reg]; jreg = reg; }
+        if (EXACT) market_day<true, false>(g, reg, js, x, d0, d1);
+        else if (AUXSCR) market_day<true, true>(g, reg, js, x, d0, d1, jpc);
+        else market_day<true, false>(g, reg, js, x, d0, d1, jpc);
         X4 v; v.x = x[0]; v.y = x[1]; v.z = x[2]; v.w = d0;
-        xs[g] = v;
+        if (EXACT) xs[g] = v;
+        else if (g & 1) { xs[g - 1] = vprev; xs[g] = v; }      // fp32: two days = one full 32-byte sector per store pair
+        else vprev = v;
         if (AUXSCR) {
           ib.x = ib.y; ib.y = ib.z; ib.z = ib.w; ib.w = d1;
           if ((g & 3) == 3) *(X4*)(is + (g - 3)) = ib;
@@ -641,6 +652,7 @@ struct Trial {
           cmp[a] = (t - sum[a]) - y; sum[a] = t;
         }
       }
+      if (!EXACT && (G & 1)) xs[G - 1] = vprev;
       if (AUXSCR && (G & 3)) {          // the last G % 4 days: shift them to the front of a final, padded vector
         for (int r = G & 3; r < 4; r++) { ib.x = ib.y; ib.y = ib.z; ib.z = ib.w; ib.w = (R)0; }
         *(X4*)(is + (G & ~3)) = ib;
