@@ -64,6 +64,12 @@ CASES = [
     dict(name="boot_3y_nan_fixed_start", variant="boot_nan", years=3, n_tapes=2, seed=120,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MEAN": 40,
               "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME": {0: 0.9, 1: 0.2}}, strategies=ALL19),
+    dict(name="boot_fullblocks_1y", variant="boot", years=1, n_tapes=2, seed=121,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MIN": 168,
+              "BOOTSTRAP_BLOCK_MAX": 168, "USE_ANTITHETIC_VARIATES": False}, strategies=ALL19),
+    dict(name="boot_tinyblocks_halfyear", variant="boot_nan", years=0.5, n_tapes=2, seed=122,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "BOOTSTRAP_BLOCK_MIN": 1, "BOOTSTRAP_BLOCK_MAX": 5,
+              "BOOTSTRAP_BLOCK_MEAN": 2, "BOOTSTRAP_WEIGHT": 1.0}, strategies=ALL19 + EXTRAS),
     dict(name="layers_c2_5y", variant="normal_c2", years=5, n_tapes=4, seed=117, cfg={},
          strategies=["S1", "S3", "B_UPRO"]),
     dict(name="voldrag_c1", variant="normal_c1", years=1, n_tapes=8, seed=118,
