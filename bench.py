@@ -284,10 +284,13 @@ def run_b200(args):
     parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local, verbose=False)
     barrier()
     t0 = time.perf_counter()
+    call_ms = []
     for _ in range(e2e_steps):
+        tc = time.perf_counter()
         res = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local,
                                          verbose=False)
-        med = float(np.median(res[sids[0]].final_wealth))     # the step's result is read on the host
+        med = float(np.mean(res[sids[0]].final_wealth))       # the step's result is read on the host
+        call_ms.append(round(1e3 * (time.perf_counter() - tc), 3))
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_launches = e2e_steps
@@ -310,7 +313,7 @@ def run_b200(args):
             ncu_c = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json"))).get(args.workload, {})
         except Exception:
             pass
-        traffic = ncu_c.get("dram_bytes_per_launch") if n == wl["trials"] else None
+        traffic = ncu_c["dram_bytes_per_trial"] * n if "dram_bytes_per_trial" in ncu_c else None
         exe = ncu_c.get("executed_warp_instr_per_path_day")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
@@ -327,7 +330,7 @@ def run_b200(args):
             "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed: parameter dicts in, host result arrays out "
                            "(engine handle cached across calls; results staged through the library's pinned buffer)",
-                    "steps": e2e_steps, "median_final_wealth": med},
+                    "steps": e2e_steps, "mean_final_wealth": med, "rank0_call_ms": call_ms},
             "gpu_launches": launches + e2e_launches,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
                          "traffic": traffic, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
@@ -337,8 +340,11 @@ def run_b200(args):
                          "peak_def": f"{sm_count} SMs x 128 FP32/INT lanes x {pk['sm_max_mhz']:.0f} MHz ({pk['source']})",
                          "frac_at_observed_clock": (achieved / (sm_count * 128 * clocks["sm_mhz"] * 1e6 / 1e12)
                                                     if clocks and clocks.get("sm_mhz") else None),
-                         "hbm": {"achieved_gbs": out_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
-                                 "note": "outputs only; paths never round-trip HBM"}},
+                         "hbm": {"achieved_gbs": (traffic if traffic is not None else out_bytes) / (kern_ms * 1e-3) / 1e9,
+                                 "peak_gbs": pk["hbm_gbs"],
+                                 "note": ("DRAM bytes of the committed ncu capture scaled to this launch (two-pass scratch, history "
+                                          "rings, outputs) over the live kernel time" if traffic is not None else
+                                          "outputs only; per-day paths never round-trip HBM")}},
         }
         if ws == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
