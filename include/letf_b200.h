@@ -222,6 +222,11 @@ typedef struct LetfParams {
   LetfStrategyParams strategies[LETF_MAX_STRATEGIES];
 
   LetfBootstrap boot;            /* MARKET_BOOTSTRAP only */
+
+  double start_regime_prob1;     /* P(trial starts in regime 1): cfg.START_REGIME_PROBABILITIES for RANDOM_START_METHOD
+                                    'regime_only' (random_start.py:14-31), the share of valid anchor rows with VIX >= 25
+                                    for 'historical_anchor' (:60-129, the anchor row is uniform); 0 = regime 0 (default,
+                                    and always with 'offset') */
 } LetfParams;
 
 /*
@@ -256,6 +261,7 @@ typedef struct LetfTape {
   double* boot_u;                /* [max_blocks][6][n] U[0,1): momentum A, block A, offset A, momentum B,
                                     block B (uniform index or weighted choice), offset B      bootstrap.py:212-262, 348-374 */
   double* boot_t;                /* [G][3][n] t(df) noise of sample_returns                  bootstrap.py:400 */
+  int32_t* start_regime;         /* [n] 0 / 1, random_start.py:31 / :106 (NULL or zeros: regime 0) */
 } LetfTape;
 
 /* per-trial outputs, structure-of-arrays: [strategy][n_trials] */

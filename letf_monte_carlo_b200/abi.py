@@ -122,6 +122,7 @@ class Params(C.Structure):
         ("rebalance_cost", C.c_double), ("apply_costs", C.c_int32), ("pad1", C.c_int32),
         ("strategies", StrategyParams * MAX_STRATEGIES),
         ("boot", Bootstrap),
+        ("start_regime_prob1", C.c_double),
     ]
 
 
@@ -135,11 +136,12 @@ class Tape(C.Structure):
         ("jump_t", C.c_void_p), ("sign", C.c_void_p), ("te_t", C.c_void_p),
         ("max_blocks", C.c_int32), ("pad2", C.c_int32),
         ("boot_len", C.c_void_p), ("boot_u", C.c_void_p), ("boot_t", C.c_void_p),
+        ("start_regime", C.c_void_p),
     ]
 
 
 TAPE_FIELDS = ("start_offset", "spells", "x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n",
-               "jump_u", "jump_t", "sign", "te_t", "boot_len", "boot_u", "boot_t")
+               "jump_u", "jump_t", "sign", "te_t", "boot_len", "boot_u", "boot_t", "start_regime")
 
 
 class Outputs(C.Structure):

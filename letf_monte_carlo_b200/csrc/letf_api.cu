@@ -416,14 +416,14 @@ int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
 // ---- host-buffer entry points ------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-constexpr int kTapeFields = 15;
+constexpr int kTapeFields = 16;
 struct TapeLayout { size_t off[kTapeFields]; size_t bytes[kTapeFields]; size_t total; };
 static TapeLayout tape_layout(const LetfTape& t) {
   const size_t n = (size_t)t.n_tapes, G = (size_t)t.gen_days, T = (size_t)t.sim_days, K = (size_t)t.max_spells;
   const size_t B = t.boot_len ? (size_t)t.max_blocks : 0;
   const size_t b[kTapeFields] = {4 * n, 4 * K * n, 8 * G * 3 * n, 8 * G * n, 8 * G * n, 8 * G * n,
                                  8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * LETF_N_ASSETS * T * n,
-                                 4 * B * n, 8 * B * 6 * n, B ? 8 * G * 3 * n : 0};
+                                 4 * B * n, 8 * B * 6 * n, B ? 8 * G * 3 * n : 0, t.start_regime ? 4 * n : 0};
   TapeLayout L; size_t o = 0;
   for (int i = 0; i < kTapeFields; i++) { L.off[i] = o; L.bytes[i] = b[i]; o += align256(b[i]); }
   L.total = o;
@@ -435,7 +435,8 @@ static void** tape_field(LetfTape& t, int i) {
     case 3: return (void**)&t.chi2; case 4: return (void**)&t.vix_n; case 5: return (void**)&t.irx_n;
     case 6: return (void**)&t.liq_n; case 7: return (void**)&t.cred_n; case 8: return (void**)&t.jump_u;
     case 9: return (void**)&t.jump_t; case 10: return (void**)&t.sign; case 11: return (void**)&t.te_t;
-    case 12: return (void**)&t.boot_len; case 13: return (void**)&t.boot_u; default: return (void**)&t.boot_t;
+    case 12: return (void**)&t.boot_len; case 13: return (void**)&t.boot_u; case 14: return (void**)&t.boot_t;
+    default: return (void**)&t.start_regime;
   }
 }
 

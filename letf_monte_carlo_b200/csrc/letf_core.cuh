@@ -216,7 +216,8 @@ struct Trial {
 
   // ---- regime path ---------------------------------------------------------------------
   struct RegimeGen { int cur, left, ks; };
-  LETF_HD void regime_init(RegimeGen& g) const { g.cur = 0; g.left = 0; g.ks = 0; }
+  int start_reg = 0;      // random_start.py:31 / :106 ('regime_only', 'historical_anchor'); 0 otherwise
+  LETF_HD void regime_init(RegimeGen& g) const { g.cur = start_reg; g.left = 0; g.ks = 0; }
   LETF_HD int draw_spell(int ks, int cur) {
     const int G = p.T + p.buffer;
     int spell;
@@ -602,6 +603,15 @@ struct Trial {
         U4 b = rng_block(key, 0, STREAM_START);
         so = p.min_offset + (int)mulhi32(b.x, (uint32_t)p.offset_range);
         if (rec) ka.tape.start_offset[tcol] = so;
+      }
+    }
+
+    if (MARKET != kMarketSeries && MARKET != LETF_MARKET_NORMAL && p.start_p1 > (R)0) {
+      if (use_tape) start_reg = ka.tape.start_regime ? (ka.tape.start_regime[tcol] != 0) : 0;
+      else {
+        U4 b = rng_block(key, 0, STREAM_START);
+        start_reg = M::u01(b.y) < p.start_p1 ? 1 : 0;
+        if (rec && ka.tape.start_regime) ka.tape.start_regime[tcol] = start_reg;
       }
     }
 

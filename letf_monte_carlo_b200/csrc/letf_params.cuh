@@ -68,6 +68,7 @@ template <typename R, int NS, int NA> struct DevParams {
       fast_layers /* 0, or 1 + bitmask of the slots whose tracking error is t(10) (others t(5)): every slot active,
                      no tanh cap, no funding model, no TLT series -> straight-line day step (letf_fast.cuh) */, pad_f;
   R W0, sim_years;
+  R start_p1;                   // P(start in regime 1), LetfParams::start_regime_prob1
   int flip[2];
   R log_pstay[2];
   int n_dur[2];
@@ -122,6 +123,7 @@ inline const char* validate_params(const LetfParams& s) {
   if (s.sim_days < 0 || s.buffer_days < 0) return "negative day count";
   if (s.n_strategies < 0 || s.n_strategies > LETF_MAX_STRATEGIES) return "bad n_strategies";
   if (s.random_start && s.buffer_days <= 0) return "random_start needs buffer_days > 0";
+  if (!(s.start_regime_prob1 >= 0.0 && s.start_regime_prob1 <= 1.0)) return "start_regime_prob1 must be in [0, 1]";
   if (s.market_mode == LETF_MARKET_JOINT_T)
     for (int r = 0; r < 2; r++) if (!(s.joint[r].nu >= 2.0)) return "joint nu must be >= 2";
   int sig_asset = -1, nport = 0;
@@ -228,6 +230,7 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
   d.has_funding = s.has_funding && s.institutional; d.asset_mask = s.asset_mask; d.n_strat = s.n_strategies;
   d.apply_costs = s.apply_costs;
   d.W0 = (R)s.initial_capital; d.sim_years = (R)s.sim_years;
+  d.start_p1 = (R)s.start_regime_prob1;
   d.sig_asset = 0;
   for (int r = 0; r < 2; r++) {
     d.flip[r] = s.transition[r][1 - r] > 0 ? 1 : 0;

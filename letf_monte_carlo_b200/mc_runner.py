@@ -166,6 +166,10 @@ def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correla
         from .bootstrap import create_bootstrap_sampler
         regime_model = dict(regime_model)
         regime_model["bootstrap_sampler"] = create_bootstrap_sampler(historical_df, cfg=cfg)
+    if historical_df is not None and getattr(cfg, "USE_RANDOM_START", False) \
+            and getattr(cfg, "RANDOM_START_METHOD", "") == "historical_anchor":
+        regime_model = dict(regime_model)                      # mc_runner.py:120-124
+        regime_model["historical_df_for_anchors"] = historical_df
     strategy_ids = list(strategy_ids)
     n_total = int(cfg.NUM_SIMULATIONS)
     params, keep = build_params(strategy_ids, time_horizon, regime_model, cfg)

@@ -118,6 +118,28 @@ def pack_strategy(sid: str, conf: Mapping, taxable_ids: Sequence[str]) -> abi.St
     return sp
 
 
+def _start_regime_prob1(method: str, historical_df, cfg) -> float:
+    """P(start_regime == 1).  'regime_only': rng.choice over cfg.START_REGIME_PROBABILITIES (random_start.py:14-31).
+    'historical_anchor': the anchor row is uniform on [min_days, n - 252) and its regime is VIX >= 25
+    (random_start.py:91-99), i.e. Bernoulli with the share of such rows; without enough history the reference falls
+    back to 'regime_only' (:188-191), and with too little for a valid range to regime 0 (:78-86)."""
+    def regime_only():
+        pr = cfg.START_REGIME_PROBABILITIES
+        tot = float(sum(pr.values()))
+        return float(pr.get(1, 0.0)) / tot
+    if method == "regime_only":
+        return regime_only()
+    min_years = float(getattr(cfg, "MIN_HISTORY_FOR_ANCHOR", 2))
+    if historical_df is None or not len(historical_df) > 252 * min_years:
+        return regime_only()
+    lo, hi = int(min_years * 252), len(historical_df) - 252
+    if hi <= lo:
+        return 0.0
+    vix = np.asarray(historical_df["VIX"].values[lo:hi], dtype=float) if "VIX" in historical_df.columns \
+        else np.full(hi - lo, 20.0)
+    return float(np.mean(~(vix < 25)))            # regime = 0 if vix < 25 else 1 (NaN -> 1, as in the reference)
+
+
 def _pack_bootstrap(p: abi.Params, keep: list, sampler, cfg) -> None:
     """bootstrap_sampler + cfg.BOOTSTRAP_* -> LetfBootstrap (host tables; letf_create copies them)."""
     from . import bootstrap as bs
@@ -199,8 +221,11 @@ def build_params(strategy_ids: Sequence[str], time_horizon: float, regime_model:
         if method == "offset":
             p.buffer_days = int(cfg.RANDOM_START_BUFFER_YEARS * 252)
             p.random_start = 1 if p.buffer_days > 0 else 0
-        else:
-            raise UnsupportedConfig(f"RANDOM_START_METHOD={method!r}: only 'offset' (the default) is implemented")
+        elif method in ("regime_only", "historical_anchor"):
+            # both only decide the regime the path starts in (the initial VIX they also draw is never read once the
+            # VIX path is generated, engine.py:494-500); no buffer, no offset (random_start.py:169-199)
+            p.start_regime_prob1 = _start_regime_prob1(method, regime_model.get("historical_df_for_anchors"), cfg)
+        # any other value leaves the defaults in place, exactly as random_start.py:168-199 does
     p.antithetic_pairs = 1 if getattr(cfg, "USE_ANTITHETIC_VARIATES", False) else 0
 
     # ---- market generator dispatch (engine.py:45-97)

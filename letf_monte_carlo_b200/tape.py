@@ -27,6 +27,7 @@ class HostTape:
         self.boot_u = np.zeros((B, 6, n))
         self.boot_t = np.zeros((G if B else 0, 3, n))
         self.start_offset = np.zeros(n, np.int32)
+        self.start_regime = np.zeros(n, np.int32)
         self.spells = np.full((K, n), max(G, 1), np.int32)
         self.x = np.zeros((G, 3, n))
         self.chi2 = np.ones((G, n))
@@ -59,7 +60,7 @@ class HostTape:
             return reg
         flip = [params.transition[0][1] > 0, params.transition[1][0] > 0]
         for c in range(n):
-            cur, t, k = 0, 0, 0
+            cur, t, k = int(self.start_regime[c]), 0, 0
             while t < G:
                 sp = int(self.spells[k, c]) if k < self.max_spells else G
                 sp = max(sp, 1)
@@ -77,17 +78,26 @@ def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
     n, T = int(n_tapes), int(params.sim_days)
     G = T + int(params.buffer_days)
     normal_mode = params.market_mode == abi.MARKET_NORMAL
+    start_regime = (rng.random(n) < params.start_regime_prob1).astype(np.int32) if params.start_regime_prob1 > 0 \
+        else np.zeros(n, np.int32)
     # ---- dwell-time draws until every column covers G days
     spells, cover, k = [], np.zeros(n, np.int64), 0
     if not normal_mode:
         while cover.min() < G:
-            r = k % 2 if params.transition[0][1] > 0 and params.transition[1][0] > 0 else 0
-            if params.n_duration[r] > 0:
-                pool = np.ctypeslib.as_array(params.duration_samples[r], shape=(params.n_duration[r],))
-                s = rng.choice(pool, size=n)
-            else:
-                p_stay = float(np.clip(params.transition[r][r], 0.80, 0.995))
-                s = np.maximum(1, rng.geometric(1 - p_stay, size=n))
+            # regime of spell k per column (both regimes flip in every test model; otherwise the path stays put)
+            both = params.transition[0][1] > 0 and params.transition[1][0] > 0
+            rcol = (start_regime + k) % 2 if both else start_regime
+            s = np.zeros(n, np.int64)
+            for r in (0, 1):
+                m = rcol == r
+                if not m.any():
+                    continue
+                if params.n_duration[r] > 0:
+                    pool = np.ctypeslib.as_array(params.duration_samples[r], shape=(params.n_duration[r],))
+                    s[m] = rng.choice(pool, size=int(m.sum()))
+                else:
+                    p_stay = float(np.clip(params.transition[r][r], 0.80, 0.995))
+                    s[m] = np.maximum(1, rng.geometric(1 - p_stay, size=int(m.sum())))
             spells.append(s.astype(np.int32))
             cover += np.maximum(s, 1)
             k += 1
@@ -95,6 +105,7 @@ def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
     tp = HostTape(n, G, T, max(len(spells), 1), (G // max(int(params.boot.block_min), 1) + 2) if boot else 0)
     for i, s in enumerate(spells):
         tp.spells[i] = s
+    tp.start_regime[:] = start_regime
     if params.random_start and params.buffer_days > 0:
         b = int(params.buffer_days)
         tp.start_offset[:] = rng.integers(min(50, b // 4), b, size=n)

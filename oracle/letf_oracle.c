@@ -820,7 +820,7 @@ static int oracle_trial(const LetfParams* p, const LetfTape* tp, int64_t k, int6
 
   /* ---- regime path, engine.py:255-302 (2 regimes; next regime is the only off-diagonal state) */
   if (p->market_mode != LETF_MARKET_NORMAL) {
-    int cur = 0, t = 0, ks = 0;
+    int cur = (tp->start_regime && tp->start_regime[ti]) ? 1 : 0, t = 0, ks = 0;   /* random_start.py:31 / :106 */
     while (t < G) {
       int spell;
       if (ks >= tp->max_spells) { flags |= LETF_FLAG_SPELL_OVERFLOW; spell = G; }
@@ -1243,6 +1243,7 @@ int letf_oracle_fill_tape(const LetfParams* p, uint64_t seed, LetfTape* tp) {
     /* spells + regime path (needed to pick nu per day) */
     int* regf = (int*)calloc(G > 0 ? G : 1, sizeof(int));
     int cur = 0, t = 0, ks = 0;
+    if (tp->start_regime) { cur = (p->start_regime_prob1 > 0 && xo_u(&g) < p->start_regime_prob1) ? 1 : 0; tp->start_regime[c] = cur; }
     while (ks < tp->max_spells) {
       int spell;
       if (p->n_duration[cur] > 0) spell = p->duration_samples[cur][(int)(xo_u(&g) * p->n_duration[cur])];

@@ -59,6 +59,8 @@ CASES = [
     dict(name="one_day", variant="default", years=1 / 252 + 1e-9, n_tapes=1, seed=114, cfg={}, strategies=ALL19),
     dict(name="inst_10y", variant="default", years=10, n_tapes=2, seed=115, cfg={}, strategies=ALL19 + EXTRAS),
     dict(name="inst_30y", variant="default", years=30, n_tapes=1, seed=116, cfg={}, strategies=ALL19),
+    dict(name="regime_only_start_1y", variant="default", years=1, n_tapes=4, seed=123,
+         cfg={"RANDOM_START_METHOD": "regime_only", "START_REGIME_PROBABILITIES": {0: 0.4, 1: 0.6}}, strategies=ALL19),
     dict(name="boot_1y", variant="boot", years=1, n_tapes=3, seed=119,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid"}, strategies=ALL19 + EXTRAS),
     dict(name="boot_3y_nan_fixed_start", variant="boot_nan", years=3, n_tapes=2, seed=120,
@@ -80,6 +82,8 @@ CASES = [
 def case_config(case):
     """our-config snapshot for a case (shared with the tests)."""
     over = dict(case["cfg"])
+    if "START_REGIME_PROBABILITIES" in over:
+        over["START_REGIME_PROBABILITIES"] = {int(k): float(v) for k, v in over["START_REGIME_PROBABILITIES"].items()}
     if "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME" in over:          # JSON round trip turns the regime keys into strings
         over["BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"] = {int(k): float(v) for k, v in over["BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"].items()}
     if over.get("LETF_CONFIGS") == "pure_leverage":
@@ -157,6 +161,9 @@ class TapeGenerator(np.random.Generator):
         return self._spell()
 
     def choice(self, a, size=None, replace=True, p=None, **k):
+        if self.role == "S":                         # random_start.py:31 start regime ('regime_only')
+            assert list(a) == [0, 1] and size is None
+            return int(self.tp.start_regime[self.c])
         assert self.role == "A"
         if size is not None:                         # engine.py:509 jump signs
             assert list(a) == [-1.0, 1.0]
@@ -335,7 +342,7 @@ def apply_ref_cfg(ref_cfg, ns):
     for k in ("USE_RANDOM_START", "RANDOM_START_METHOD", "RANDOM_START_BUFFER_YEARS", "USE_MOMENT_MATCHING",
               "USE_ANTITHETIC_VARIATES", "SIM_ENGINE_MODE", "STUDENT_T_DF", "USE_BLOCK_BOOTSTRAP", "BOOTSTRAP_WEIGHT",
               "BOOTSTRAP_BLOCK_MIN", "BOOTSTRAP_BLOCK_MAX", "BOOTSTRAP_BLOCK_MEAN", "BOOTSTRAP_BLOCK_SIZE",
-              "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME"):
+              "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME", "START_REGIME_PROBABILITIES"):
         saved[k] = getattr(ref_cfg, k)
         setattr(ref_cfg, k, getattr(ns, k))
     saved["STRATEGIES"] = dict(ref_cfg.STRATEGIES)

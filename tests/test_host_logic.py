@@ -43,8 +43,18 @@ def test_build_params_dispatch_and_rejections():
     assert p.market_mode == abi.MARKET_PARAM_T and p.has_stress == 0 and p.has_funding == 0   # engine.py:81-97
     p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model("no_joint"), synthetic.config_namespace())
     assert p.market_mode == abi.MARKET_PARAM_T and p.has_stress == 1
-    with pytest.raises(UnsupportedConfig):
-        build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(RANDOM_START_METHOD="regime"))
+    # random_start.py:168-199: an unknown method leaves the defaults (no buffer, regime 0), it does not raise
+    p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(RANDOM_START_METHOD="regime"))
+    assert p.buffer_days == 0 and p.random_start == 0 and p.start_regime_prob1 == 0.0
+    p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(RANDOM_START_METHOD="regime_only"))
+    assert p.buffer_days == 0 and p.random_start == 0 and p.start_regime_prob1 == pytest.approx(0.2)     # config.py:318
+    # 'historical_anchor': uniform anchor row, regime = VIX >= 25 (random_start.py:91-99); falls back to regime_only
+    hist = synthetic.synthetic_history(n_days=3000, seed=5)
+    m = synthetic.fallback_regime_model(); m["historical_df_for_anchors"] = hist
+    p, _ = build_params(["S1"], 1, m, synthetic.config_namespace(RANDOM_START_METHOD="historical_anchor"))
+    assert p.start_regime_prob1 == pytest.approx(float(np.mean(hist["VIX"].values[504:3000 - 252] >= 25)))
+    p, _ = build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(RANDOM_START_METHOD="historical_anchor"))
+    assert p.start_regime_prob1 == pytest.approx(0.2)
     with pytest.raises(UnsupportedConfig):
         build_params(["S1"], 1, synthetic.fallback_regime_model(), synthetic.config_namespace(N_REGIMES=3))
     tm = np.array([[2.0, 0.0], [0.5, 0.5]])       # row normalisation of engine.py:264-272

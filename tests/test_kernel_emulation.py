@@ -64,20 +64,26 @@ def _blank_tape(params, n_tapes, max_spells):
     return HostTape(n_tapes, G, params.sim_days, max_spells, (G // max(params.boot.block_min, 1) + 2) if boot else 0)
 
 
-@pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2), ("boot", 1)])
+@pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2), ("boot", 1),
+                                           ("regime_only", 1)])
 def test_philox_record_replays_through_oracle(variant, years):
     """RNG_PHILOX_RECORD writes every variate it consumes; feeding that tape to the oracle must give
     the same results -> the Philox path consumes draws exactly where the tape semantics say."""
-    case = dict(variant=variant, years=years, n_tapes=3, seed=0,
-                cfg={"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {},
+    cfg_over = {"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {}
+    if variant == "regime_only":      # random_start.py:169-172: the start regime is drawn, no buffer / offset
+        variant, cfg_over = "default", {"RANDOM_START_METHOD": "regime_only", "START_REGIME_PROBABILITIES": {0: 0.5, 1: 0.5}}
+    case = dict(variant=variant, years=years, n_tapes=3, seed=0, cfg=cfg_over,
                 strategies=ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"])
     doc = {"case": case}
     ns, model, params, keep, _ = case_inputs(doc)
     assert (params.market_mode == abi.MARKET_BOOTSTRAP) == (variant == "boot")
     G = params.sim_days + params.buffer_days
-    rec = _blank_tape(params, 3, 256)
-    n = 6 if params.antithetic_pairs else 3
+    n_rec = 12 if params.start_regime_prob1 > 0 else 3
+    rec = _blank_tape(params, n_rec, 256)
+    n = 2 * n_rec if params.antithetic_pairs else n_rec
     e = emu.run(params, rec, precision=abi.PREC_F64, rng_mode=abi.RNG_PHILOX_RECORD, seed=1234, n=n)
+    if params.start_regime_prob1 > 0:
+        assert 0 < rec.start_regime.sum() < n_rec and params.buffer_days == 0
     assert not (e.flags & abi.FLAG_SPELL_OVERFLOW).any()
     o = orc.run(params, rec)
     np.testing.assert_allclose(e.final_wealth, o.final_wealth, rtol=1e-11)
