@@ -51,6 +51,9 @@ WORKLOADS = {
                       "blended twice with correlated Student-t noise (bootstrap.py:310-458, engine.py:50-80), VIX/IRX, random start; "
                       "TQQQ / SPY / SSO buy&hold, 200k trials x 7560 days per GPU",
                  trials=200_000, years=30, lane_ops=(6 * 110 + 2 * 36 + 40) * (7560 + 1260) / 7560 + 3 * 150, mufu=40),
+    "series": dict(desc="materialised-path mode (run_strategy_fixed seam, strategy.py:55): strategy rules S1 S2 S4 S5 on caller-supplied "
+                        "day-major fp64 TQQQ_Ret / SPY_Ret series + int32 regime path resident in HBM, 200k paths x 2520 days",
+                   trials=200_000, years=10, lane_ops=120, mufu=2, bytes_per_path_day=2 * 8 + 4),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "200k trials x 7560 days per GPU",
                     trials=200_000, years=30, lane_ops=2600, mufu=60),
@@ -448,6 +451,81 @@ def run_c5(args):
         dist.destroy_process_group()
 
 
+def run_series(args):
+    """The HBM-side mode: the strategy kernel streams materialised return series (letf_run_strategies).  Roofline bound
+    = HBM: algorithmic bytes = the series it must read once (2 x fp64 + the int32 regime per path-day)."""
+    import torch
+    from letf_monte_carlo_b200 import synthetic
+    from letf_monte_carlo_b200.engine import PathEngine
+    from letf_monte_carlo_b200.params import build_params
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("the series workload is a single-GPU measurement")
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    wl = WORKLOADS["series"]
+    n, T = int(args.trials or wl["trials"]), int(wl["years"] * 252)
+    ns = synthetic.config_namespace()
+    sids = ["S1", "S2", "S4", "S5"]
+    params, keep = build_params(sids, wl["years"], synthetic.fallback_regime_model(), ns)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(args.seed)
+    spy = (0.0003 + 0.01 * torch.randn((T, n), device=dev, dtype=torch.float64, generator=g))
+    tqqq = (3.3 * spy - 0.0003)
+    regime = (torch.rand((T, n), device=dev, generator=g) < 0.2).to(torch.int32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    eng = PathEngine(params, keep, precision=args.precision, device=0)
+    series = {"TQQQ": tqqq, "SPY": spy}
+
+    def step():
+        flush.zero_()
+        return eng.run_strategies(series, regime=regime)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    clk = ClockSampler(0); clk.start(); time.sleep(0.25)
+    kms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        kms.append(eng.launch_info()["last_kernel_ms"])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = clk.stop()
+    kern_ms = float(np.mean(kms))
+    info = eng.launch_info()
+    pk = peaks()
+    bytes_launch = n * T * wl["bytes_per_path_day"]
+    achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+    # end to end: host series in (pinned), results out
+    hs = {k: v.cpu().pin_memory() for k, v in series.items()}
+    hr = regime.cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = eng.run_strategies({k: v.to(dev, non_blocking=True) for k, v in hs.items()}, regime=hr.to(dev, non_blocking=True))
+    fw = out.to_host().final_wealth
+    e2e_s = time.perf_counter() - t0
+    line = {"metric": METRIC, "value": n * T * args.steps / wall, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"series: {wl['desc']}", "paths": n, "sim_days": T, "strategies": sids,
+                       "l2": f"256 MiB memset between steps; inputs ({bytes_launch / 1e9:.1f} GB) exceed L2",
+                       "kernel": {"grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"]}},
+            "clocks": clocks,
+            "e2e": {"value": n * T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bytes_launch, "d2h_bytes_per_step": n * len(sids) * 20,
+                    "api": "PathEngine.run_strategies with pinned host series", "mean_final_wealth": float(np.mean(fw[0]))},
+            "gpu_launches": args.steps + 1,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": None, "kernel": "letf_path_kernel<series>", "kernel_ms": kern_ms,
+                         "bytes_per_path_day": wl["bytes_per_path_day"], "units_per_launch": n * T,
+                         "peak_def": f"measured copy bandwidth ({pk['source']})"}}
+    eng.close()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,6 +543,8 @@ def main():
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
+    elif args.workload == "series":
+        run_series(args)
     else:
         run_b200(args)
 

@@ -730,6 +730,24 @@ struct Trial {
     X4 vnext; vnext.x = vnext.y = vnext.z = vnext.w = (R)0;
     R inext = (R)0;
     if (two_pass && T > 0) { vnext = xs[so]; if (AUXSCR) inext = is[so]; }
+    // materialised-path mode: the day's series values are requested kSeriesAhead days ahead (a warp reads 256 B per
+    // series and day; without the prefetch every day step is one exposed HBM round trip)
+    constexpr int kSeriesAhead = 4;
+    double sq_er[MARKET == kMarketSeries ? kSeriesAhead : 1][kAssets];
+    double sq_vix[MARKET == kMarketSeries ? kSeriesAhead : 1], sq_tlt[MARKET == kMarketSeries ? kSeriesAhead : 1];
+    int sq_reg[MARKET == kMarketSeries ? kSeriesAhead : 1];
+    auto series_fetch = [&](int slot, int day) {
+      const int64_t o = (int64_t)day * ka.series.n_paths + col;
+#pragma unroll
+      for (int a = 0; a < kAssets; a++) sq_er[slot][a] = ka.series.asset_ret[a] ? ka.series.asset_ret[a][o] : 0.0;
+      sq_vix[slot] = ka.series.vix ? ka.series.vix[o] : 15.0;
+      sq_tlt[slot] = ka.series.tlt_ret ? ka.series.tlt_ret[o] : 0.0;
+      sq_reg[slot] = ka.series.regime ? ka.series.regime[o] : 0;
+    };
+    if (MARKET == kMarketSeries) {
+#pragma unroll
+      for (int d = 0; d < kSeriesAhead; d++) if (d < T) series_fetch(d, d);
+    }
     for (int i = 0; i < T; i++) {
       const int g = so + i;
       const int64_t sn = ka.series.n_paths;
@@ -752,11 +770,25 @@ struct Trial {
           if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; pf_r5 = ring[roff(c)]; }
         }
       }
-      const int reg = MARKET == kMarketSeries ? (ka.series.regime ? ka.series.regime[(int64_t)i * sn + col] : 0) : regime_next(rg);
+      // series mode: take day i from the front of the prefetch queue, shift, request day i + kSeriesAhead
+      R s_er[kAssets];
+      int s_reg = 0;
+      if (MARKET == kMarketSeries) {
+#pragma unroll
+        for (int a = 0; a < kAssets; a++) s_er[a] = (R)sq_er[0][a];
+        vix = (R)sq_vix[0]; s_reg = sq_reg[0];
+      }
+      const int reg = MARKET == kMarketSeries ? s_reg : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
       if (MARKET == kMarketSeries) {
-        vix = ka.series.vix ? (R)ka.series.vix[(int64_t)i * sn + col] : (R)15;
-        x[2] = ka.series.tlt_ret ? (R)ka.series.tlt_ret[(int64_t)i * sn + col] : (R)0;
+        x[2] = (R)sq_tlt[0];
+#pragma unroll
+        for (int d = 0; d + 1 < kSeriesAhead; d++) {
+#pragma unroll
+          for (int a = 0; a < kAssets; a++) sq_er[d][a] = sq_er[d + 1][a];
+          sq_vix[d] = sq_vix[d + 1]; sq_tlt[d] = sq_tlt[d + 1]; sq_reg[d] = sq_reg[d + 1];
+        }
+        if (i + kSeriesAhead < T) series_fetch(kSeriesAhead - 1, i + kSeriesAhead);
       } else if (MARKET == kMarketBoot) {
         boot_day(g, reg, vcur.x, vcur.y, vcur.z, shift, x, vn, in);
       } else if (two_pass) {
@@ -853,7 +885,7 @@ struct Trial {
         R er;
         if (MARKET == kMarketSeries) {
           if (!ka.series.asset_ret[a]) continue;
-          er = (R)ka.series.asset_ret[a][(int64_t)i * sn + col];
+          er = s_er[a];
         } else {
           if (AM != 0 && NA == kAssets ? !((AM >> a) & 1) : !p.act_on[a]) continue;
           const DevAsset<R>& ap = p.act[a];
