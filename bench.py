@@ -54,6 +54,10 @@ WORKLOADS = {
     "series": dict(desc="materialised-path mode (run_strategy_fixed seam, strategy.py:55): strategy rules S1 S2 S4 S5 on caller-supplied "
                         "day-major fp64 TQQQ_Ret / SPY_Ret series + int32 regime path resident in HBM, 200k paths x 2520 days",
                    trials=200_000, years=10, lane_ops=120, mufu=2, bytes_per_path_day=2 * 8 + 4),
+    "series19": dict(desc="materialised-path mode with the reference's default 19-strategy list (typed-slot series build): "
+                          "caller-supplied day-major fp64 TQQQ / SSO / TMF / SPY return series + VIX + int32 regime path resident "
+                          "in HBM, 100k paths x 2520 days",
+                     trials=100_000, years=10, lane_ops=1500, mufu=40, bytes_per_path_day=5 * 8 + 4),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "200k trials x 7560 days per GPU",
                     trials=200_000, years=30, lane_ops=2600, mufu=60),
@@ -463,10 +467,11 @@ def run_series(args):
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    wl = WORKLOADS["series"]
+    wl = WORKLOADS[args.workload]
     n, T = int(args.trials or wl["trials"]), int(wl["years"] * 252)
     ns = synthetic.config_namespace()
-    sids = ["S1", "S2", "S4", "S5"]
+    full = args.workload == "series19"
+    sids = ["S%d" % i for i in range(1, 20)] if full else ["S1", "S2", "S4", "S5"]
     params, keep = build_params(sids, wl["years"], synthetic.fallback_regime_model(), ns)
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
@@ -477,10 +482,15 @@ def run_series(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     eng = PathEngine(params, keep, precision=args.precision, device=0)
     series = {"TQQQ": tqqq, "SPY": spy}
+    vix = None
+    if full:
+        series["SSO"] = 2.0 * spy - 0.0001
+        series["TMF"] = -0.6 * spy + 0.004 * torch.randn((T, n), device=dev, dtype=torch.float64, generator=g)
+        vix = 18.0 + 6.0 * torch.rand((T, n), device=dev, dtype=torch.float64, generator=g) + 14.0 * regime.to(torch.float64)
 
     def step():
         flush.zero_()
-        return eng.run_strategies(series, regime=regime)
+        return eng.run_strategies(series, regime=regime, vix=vix)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -503,13 +513,17 @@ def run_series(args):
     hr = regime.cpu().pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out = eng.run_strategies({k: v.to(dev, non_blocking=True) for k, v in hs.items()}, regime=hr.to(dev, non_blocking=True))
+    hv = vix.cpu().pin_memory() if vix is not None else None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = eng.run_strategies({k: v.to(dev, non_blocking=True) for k, v in hs.items()}, regime=hr.to(dev, non_blocking=True),
+                             vix=hv.to(dev, non_blocking=True) if hv is not None else None)
     fw = out.to_host().final_wealth
     e2e_s = time.perf_counter() - t0
     line = {"metric": METRIC, "value": n * T * args.steps / wall, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"series: {wl['desc']}", "paths": n, "sim_days": T, "strategies": sids,
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "paths": n, "sim_days": T, "strategies": sids,
                        "l2": f"256 MiB memset between steps; inputs ({bytes_launch / 1e9:.1f} GB) exceed L2",
                        "kernel": {"grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"]}},
             "clocks": clocks,
@@ -543,7 +557,7 @@ def main():
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
-    elif args.workload == "series":
+    elif args.workload in ("series", "series19"):
         run_series(args)
     else:
         run_b200(args)

@@ -235,7 +235,8 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
   }
   if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
-  const bool need_io = rng_mode != LETF_RNG_PHILOX || want_journal || lg.count != nullptr || market == kMarketSeries;
+  // (a caller-supplied frame needs no tape plumbing; only the journal does)
+  const bool need_io = (market != kMarketSeries && rng_mode != LETF_RNG_PHILOX) || want_journal || lg.count != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);

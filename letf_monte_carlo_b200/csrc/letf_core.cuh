@@ -732,7 +732,7 @@ struct Trial {
     if (two_pass && T > 0) { vnext = xs[so]; if (AUXSCR) inext = is[so]; }
     // materialised-path mode: the day's series values are requested kSeriesAhead days ahead (a warp reads 256 B per
     // series and day; without the prefetch every day step is one exposed HBM round trip)
-    constexpr int kSeriesAhead = 4;
+    constexpr int kSeriesAhead = LIST != 0 ? 2 : 4;      // (the typed 19-rule build has no registers for a deeper queue)
     double sq_er[MARKET == kMarketSeries ? kSeriesAhead : 1][kAssets];
     double sq_vix[MARKET == kMarketSeries ? kSeriesAhead : 1], sq_tlt[MARKET == kMarketSeries ? kSeriesAhead : 1];
     int sq_reg[MARKET == kMarketSeries ? kSeriesAhead : 1];

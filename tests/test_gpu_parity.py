@@ -521,3 +521,37 @@ def test_sampled_tax_path_replays_trade_lists_on_device(engine_lib):
         assert r["pcts"]["p60"]["post_wealth"] <= r["pcts"]["p60"]["pre_wealth"] + 1e-9
         assert 0.0 <= r["win"] <= 100.0
     assert len(seen) <= 150 and all(n > 0 for _, n in seen)
+
+
+def test_typed_series_kernel_vs_generic_and_oracle(engine_lib):
+    """materialised-path mode with the default 19-strategy list: the typed-slot fp32 series build (bench.py
+    `series19`) against the generic fp32 series build (journal on -> tape-capable kernel) and the fp64 oracle."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    T, n = 900, 96
+    ns = synthetic.config_namespace()
+    params, keep = build_params(ALL19, T / 252, synthetic.fallback_regime_model(), ns)
+    rets = {a: np.ascontiguousarray(rng.standard_t(5, (T, n)) * s + 0.0004) for a, s in
+            zip(abi.ASSET_NAMES, (0.028, 0.028, 0.019, 0.022, 0.0095, 0.012))}
+    vix = np.ascontiguousarray(14 + 12 * rng.random((T, n)))
+    regime = np.ascontiguousarray((rng.random((T, n)) < 0.2).astype(np.int32))
+    from oracle.oracle import HostOutputs
+    o = HostOutputs(params.n_strategies, n)
+    s = abi.Series()
+    s.n_paths, s.sim_days = n, T
+    for a, name in enumerate(abi.ASSET_NAMES):
+        s.asset_ret[a] = rets[name].ctypes.data
+    s.vix, s.regime = vix.ctypes.data, regime.ctypes.data
+    assert orc.lib().letf_oracle_run_strategies(C.byref(params), C.byref(s), C.byref(o.as_struct())) == 0
+    with _engine(params, keep, "f32") as eng:
+        typed = eng.run_strategies(rets, vix=vix, regime=regime).to_host()
+        regs_typed = eng.launch_info()["regs_per_thread"]
+        gen = eng.run_strategies(rets, vix=vix, regime=regime, journal=True).to_host()
+        regs_gen = eng.launch_info()["regs_per_thread"]
+    assert regs_typed != regs_gen                    # two different instantiations really ran
+    assert np.mean(typed.num_trades != gen.num_trades) < 0.01
+    assert np.mean(gen.num_trades != o.num_trades) < 0.02
+    same = typed.num_trades == o.num_trades          # a flipped trade decision moves the whole path: compare the rest
+    assert np.median(np.abs(typed.final_wealth / o.final_wealth - 1)[same]) < 1e-5
+    np.testing.assert_allclose(typed.final_wealth[same], o.final_wealth[same], rtol=5e-4)
+    np.testing.assert_allclose(typed.final_wealth[:3], o.final_wealth[:3], rtol=2e-5)      # buy & hold rows
