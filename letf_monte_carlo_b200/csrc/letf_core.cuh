@@ -1257,7 +1257,9 @@ struct Trial {
     const int64_t N = ka.out.n_trials;
 #pragma unroll(LIST != 0 || NS <= 8 ? NS : 1)
     for (int s = 0; s < NS; s++) {
-      if (s >= p.n_strat) break;
+      // (`continue`, not `break`: with a run-time trip count the unrolled loop gets a rolled remainder loop, whose
+      //  dynamic slot[s] forces the whole slot array - wealth, drawdown, trade counts - through local memory every day)
+      if (s >= p.n_strat) continue;
       const int ty = p.strat[s].type;
       double fw = T > 0 ? slot[s].W : 0.0;
       double md = T > 1 ? slot[s].dd.value() : 0.0;
