@@ -30,9 +30,10 @@ template <typename R, int NS, int NA> struct KArgs {
   int64_t first_trial, n_trials, tape_first;
   int rng_mode;
   int pad;
-  R* xscr;                  // [nthreads][G][4]   moment-matching scratch: one aligned 4-vector per generated day,
-                            // thread-major (each lane streams its own column; window days are offset by the
-                            // lane's random start, so a day-major layout cannot coalesce the second pass)
+  R* xscr;                  // [nthreads][G][4]   two-pass scratch (joint-t moment matching, block bootstrap): one aligned
+                            // 4-vector per generated day, thread-major (each lane streams its own column; window days
+                            // are offset by the lane's random start, so a day-major layout cannot coalesce the second
+                            // pass); behind it [nthreads][G rounded up to 4] scalars (Trial::run, AUXSCR)
   R* ringP;                 // [kRingP][nthreads]
   R* ringS;                 // [kRingS][nthreads]
   R* ringA;                 // [kRingA][nthreads]
