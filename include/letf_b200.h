@@ -339,6 +339,14 @@ int letf_trade_list_host(LetfEngine* e, uint64_t seed, int64_t trial, int strate
                          const LetfTape* host_tape, int cap, int32_t* day, int32_t* asset,
                          int32_t* action, double* shares, double* price, int32_t* count);
 
+/* Same for SEVERAL trials of one taxable strategy in ONE launch - the <= 50 wealth-ranked trials per strategy of
+ * reporting.py:457-467: trial trials[j] is re-simulated by its own thread with the journal log on (Philox draws).
+ * Host buffers day / asset / action / shares / price are [n][cap]; count[n] receives each trial's number of entries
+ * (an entry count above cap means that trial's list was truncated: call again with a larger cap). */
+int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, int n, int strategy, int cap,
+                          int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price,
+                          int32_t* count);
+
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info);
 
 /* Strategy rules on caller-supplied return series (materialised-path mode):

@@ -117,6 +117,7 @@ struct LetfEngine {
 namespace letf {
 
 struct LogArgs {
+  const int64_t* trial_ids = nullptr;       // device: batch replay (letf_trade_lists_host)
   int64_t trial = -1; int strategy = -1; int cap = 0;
   int32_t* count = nullptr; int32_t* day = nullptr; int32_t* asset = nullptr; int32_t* action = nullptr;
   double* shares = nullptr; double* price = nullptr;
@@ -190,6 +191,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   ka.out = *out;
   ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.tape_first = 0;
   ka.rng_mode = rng_mode; ka.nthreads = nthreads;
+  ka.trial_ids = lg.trial_ids;
   ka.log_trial = lg.trial; ka.log_strategy = lg.strategy; ka.log_cap = lg.cap;
   ka.log_count = lg.count; ka.log_day = lg.day; ka.log_asset = lg.asset; ka.log_action = lg.action;
   ka.log_shares = lg.shares; ka.log_price = lg.price;
@@ -606,6 +608,49 @@ int letf_trade_list_host(LetfEngine* e, uint64_t seed, int64_t trial, int strate
     CK(cudaMemcpy(action, lg.action, 4 * m, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(shares, lg.shares, 8 * m, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(price, lg.price, 8 * m, cudaMemcpyDeviceToHost));
+  }
+  return LETF_OK;
+}
+
+int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, int n, int strategy, int cap,
+                          int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count) {
+  if (!e || !count || (n > 0 && !trials)) return fail(LETF_ERR_INVALID, "null argument");
+  if (n < 0) return fail(LETF_ERR_INVALID, "negative trial count");
+  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  if (cap < 0 || (cap > 0 && (!day || !asset || !action || !shares || !price))) return fail(LETF_ERR_INVALID, "bad log buffers");
+  for (int j = 0; j < n; j++) { count[j] = 0; if (trials[j] < 0) return fail(LETF_ERR_INVALID, "negative trial id"); }
+  if (n == 0 || !e->params.strategies[strategy].taxable) return LETF_OK;     // engine.py:571: journal only for TAXABLE_IDS
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  const int S = e->params.n_strategies;
+  const size_t c = (size_t)(cap > 0 ? cap : 1), m = (size_t)n;
+  const size_t o_ids = 0, o_cnt = o_ids + align256(8 * m), o_day = o_cnt + align256(4 * m), o_asset = o_day + align256(4 * c * m),
+               o_act = o_asset + align256(4 * c * m), o_sh = o_act + align256(4 * c * m), o_pr = o_sh + align256(8 * c * m),
+               o_fw = o_pr + align256(8 * c * m), o_dd = o_fw + align256(8 * S * m), o_nt = o_dd + align256(8 * S * m),
+               o_fl = o_nt + align256(4 * S * m), total = o_fl + align256(4 * m);
+  cudaError_t ce = e->stage_log.reserve(total);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "log staging"); }
+  char* base = (char*)e->stage_log.p;
+  CK(cudaMemcpy(base + o_ids, trials, 8 * m, cudaMemcpyHostToDevice));
+  CK(cudaMemset(base + o_cnt, 0, 4 * m));
+  LogArgs lg;
+  lg.trial_ids = (const int64_t*)(base + o_ids); lg.trial = -1; lg.strategy = strategy; lg.cap = cap;
+  lg.count = (int32_t*)(base + o_cnt); lg.day = (int32_t*)(base + o_day); lg.asset = (int32_t*)(base + o_asset);
+  lg.action = (int32_t*)(base + o_act); lg.shares = (double*)(base + o_sh); lg.price = (double*)(base + o_pr);
+  LetfOutputs dout; memset(&dout, 0, sizeof(dout));
+  dout.n_trials = n;
+  dout.final_wealth = (double*)(base + o_fw); dout.max_dd = (double*)(base + o_dd);
+  dout.num_trades = (int32_t*)(base + o_nt); dout.flags = (uint32_t*)(base + o_fl);
+  int rc = launch_any(e, e->params.market_mode, (cudaStream_t)0, seed, 0, n, LETF_RNG_PHILOX, nullptr, &dout, nullptr, lg);
+  if (rc) return rc;
+  CK(cudaMemcpy(count, lg.count, 4 * m, cudaMemcpyDeviceToHost));
+  if (cap > 0) {
+    // rows are [n][cap]; copy whole rows (the unused tail of a row is whatever the staging held)
+    CK(cudaMemcpy(day, lg.day, 4 * c * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(asset, lg.asset, 4 * c * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(action, lg.action, 4 * c * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(shares, lg.shares, 8 * c * m, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(price, lg.price, 8 * c * m, cudaMemcpyDeviceToHost));
   }
   return LETF_OK;
 }

@@ -38,7 +38,9 @@ template <typename R, int NS, int NA> struct KArgs {
   R* ringS;                 // [kRingS][nthreads]
   R* ringA;                 // [kRingA][nthreads]
   int64_t nthreads;
-  // optional journal log of ONE trial / ONE strategy (Trade_List replay)
+  // optional journal log of ONE strategy (Trade_List replay): of the single trial log_trial, or - when trial_ids is
+  // set - of every launched trial (work item j simulates trial_ids[j] and logs into row j of the [n][log_cap] buffers)
+  const int64_t* trial_ids;
   int64_t log_trial; int log_strategy; int log_cap;
   int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
 };
@@ -560,13 +562,15 @@ struct Trial {
     double ch = target - j.pos[which];
     if (::fabs(ch) < 0.001) return;
     double sh = ch > 0 ? ch : ::fabs(ch);
-    if (TAPEIO && ka.log_count && ka.log_trial == k && ka.log_strategy == s) {
-      int n = *ka.log_count;
+    if (TAPEIO && ka.log_count && (ka.trial_ids || ka.log_trial == k) && ka.log_strategy == s) {
+      const int64_t row = ka.trial_ids ? col : 0;
+      int n = ka.log_count[row];
       if (n < ka.log_cap) {
-        ka.log_day[n] = day; ka.log_asset[n] = asset; ka.log_action[n] = ch > 0 ? 1 : -1;
-        ka.log_shares[n] = sh; ka.log_price[n] = (double)price;
+        const int64_t o = row * ka.log_cap + n;
+        ka.log_day[o] = day; ka.log_asset[o] = asset; ka.log_action[o] = ch > 0 ? 1 : -1;
+        ka.log_shares[o] = sh; ka.log_price[o] = (double)price;
       }
-      *ka.log_count = n + 1;
+      ka.log_count[row] = n + 1;
     }
     j.cnt++;
     j.vol += sh * (double)price;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
     }
   }
   for (int64_t j = lane; j < ka.n_trials; j += ka.nthreads) {
-    Trial<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM> t(ka, ka.first_trial + j, j, lane);
+    Trial<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM> t(ka, (TAPEIO && ka.trial_ids) ? ka.trial_ids[j] : ka.first_trial + j, j, lane);
     t.run();
   }
 }

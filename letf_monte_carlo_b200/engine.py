@@ -234,6 +234,30 @@ class PathEngine:
                  "price": float(price[i]), "dollar_amount": float(shares[i] * price[i])}
                 for i in range(cnt.value)]
 
+    def trade_lists(self, trials, strategy: int, *, seed: int = 0, cap: int = 2048) -> list[list[dict]]:
+        """`Trade_List`s of several trials of one taxable strategy in ONE launch (the <= 50 sampled trials of
+        reporting.py:457-467); a single-thread replay per trial would cost one launch each."""
+        ids = np.ascontiguousarray(np.asarray(list(trials), dtype=np.int64))
+        n = len(ids)
+        if n == 0:
+            return []
+        while True:
+            day, asset, action = (np.zeros((n, cap), np.int32) for _ in range(3))
+            shares, price = np.zeros((n, cap)), np.zeros((n, cap))
+            cnt = np.zeros(n, np.int32)
+            rc = self._lib.letf_trade_lists_host(self._h, seed, ids.ctypes.data, n, strategy, cap, day.ctypes.data,
+                                                 asset.ctypes.data, action.ctypes.data, shares.ctypes.data,
+                                                 price.ctypes.data, cnt.ctypes.data)
+            self._check(rc)
+            self.launches += 1
+            if cnt.max(initial=0) <= cap:
+                break
+            cap = int(cnt.max())
+        return [[{"day_index": int(day[j, i]), "asset": abi.ASSET_NAMES[asset[j, i]],
+                  "action": "BUY" if action[j, i] > 0 else "SELL", "shares": float(shares[j, i]),
+                  "price": float(price[j, i]), "dollar_amount": float(shares[j, i] * price[j, i])}
+                 for i in range(int(cnt[j]))] for j in range(n)]
+
     def launch_info(self) -> dict:
         li = abi.LaunchInfo()
         self._check(self._lib.letf_launch_info(self._h, C.byref(li)))

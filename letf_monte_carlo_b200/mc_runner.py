@@ -80,6 +80,10 @@ class StrategyResults(Sequence):
     def trade_list(self, i: int):
         return self.run.engine.trade_list(self.run.first_trial + i, self.s, seed=self.run.seed)
 
+    def trade_lists(self, idx):
+        """several trials in one launch (what the sampled-trial tax path asks for)"""
+        return self.run.engine.trade_lists([self.run.first_trial + int(i) for i in idx], self.s, seed=self.run.seed)
+
 
 class MonteCarloRun(dict):
     """The returned mapping {sid: StrategyResults}; also keeps the launch metadata."""

@@ -69,8 +69,8 @@ def interpolated_tax(results, sid: str, time_horizon, tax_fn: Callable, tax_conf
     n = len(wealth)
     idx = tax_sample_indices(wealth, max_tax_sims)
     taxes = []
-    for i in idx:
-        tl = _trade_list(results, i)
+    lists = results.trade_lists(idx) if hasattr(results, "trade_lists") else [_trade_list(results, i) for i in idx]
+    for i, tl in zip(idx, lists):
         taxes.append(float(tax_fn(tl, time_horizon, initial_capital, f"{sid}_bulk", tax_config)) if tl else 0.0)
     sw, st = wealth[idx], np.array(taxes)
     if n <= max_tax_sims:

@@ -516,8 +516,10 @@ def test_sampled_tax_path_replays_trade_lists_on_device(engine_lib):
     for r in rows:
         s = sids.index(r["id"])
         assert len(r["sampled_trials"]) == 50
-        for i in r["sampled_trials"][::7]:
-            assert len(run[r["id"]].trade_list(i)) == bulk.journal_count[s, i]
+        batch = run[r["id"]].trade_lists(r["sampled_trials"])          # one launch for the 50 trials
+        assert [len(b) for b in batch] == [int(bulk.journal_count[s, i]) for i in r["sampled_trials"]]
+        for i, b in list(zip(r["sampled_trials"], batch))[::7]:
+            assert run[r["id"]].trade_list(i) == b                     # identical to the single-trial replay
         assert r["pcts"]["p60"]["post_wealth"] <= r["pcts"]["p60"]["pre_wealth"] + 1e-9
         assert 0.0 <= r["win"] <= 100.0
     assert len(seen) <= 150 and all(n > 0 for _, n in seen)

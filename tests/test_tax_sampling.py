@@ -100,3 +100,15 @@ def test_array_backed_results_replay_only_the_sampled_trials(doc, results):
                              tax_config=doc["tax_config"], taxable_ids=[sid])
     assert not misses and sorted(asked) == sorted(rows_v[0]["sampled_trials"]) and len(asked) == 50
     assert rows_v[0]["pcts"] == rows_d[0]["pcts"] and rows_v[0]["win"] == rows_d[0]["win"]
+
+    class BatchView(View):                 # the device path: ONE call for all sampled trials (letf_trade_lists_host)
+        calls = []
+
+        def trade_lists(self, idx):
+            self.calls.append(list(idx))
+            return [results[sid][i]["Trade_List"] for i in idx]
+
+    bv = BatchView()
+    rows_b = taxable_summary({sid: bv, "S2": results["S2"]}, doc["case"]["years"], tax_fn=_lookup(doc, misses),
+                             tax_config=doc["tax_config"], taxable_ids=[sid])
+    assert len(bv.calls) == 1 and bv.calls[0] == rows_b[0]["sampled_trials"] and rows_b[0]["pcts"] == rows_d[0]["pcts"]
