@@ -30,6 +30,15 @@ class NonFiniteTrials(ValueError):
     out of the trial (engine.py:486-498)."""
 
 
+def _trade_dicts(day, asset, action, shares, price, n: int) -> list[dict]:
+    """rows of the reference's Trade_List (trade.py:83-91) from the replay buffers; .tolist() converts in C"""
+    names = abi.ASSET_NAMES
+    return [{"day_index": d, "asset": names[a], "action": "BUY" if t > 0 else "SELL", "shares": s, "price": p,
+             "dollar_amount": s * p}
+            for d, a, t, s, p in zip(day[:n].tolist(), asset[:n].tolist(), action[:n].tolist(), shares[:n].tolist(),
+                                     price[:n].tolist())]
+
+
 def default_device() -> int:
     return int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -229,10 +238,7 @@ class PathEngine:
         self.launches += 1
         if cnt.value > cap:
             return self.trade_list(trial, strategy, seed=seed, rng_mode=rng_mode, tape=tape, cap=cnt.value)
-        return [{"day_index": int(day[i]), "asset": abi.ASSET_NAMES[asset[i]],
-                 "action": "BUY" if action[i] > 0 else "SELL", "shares": float(shares[i]),
-                 "price": float(price[i]), "dollar_amount": float(shares[i] * price[i])}
-                for i in range(cnt.value)]
+        return _trade_dicts(day, asset, action, shares, price, cnt.value)
 
     def trade_lists(self, trials, strategy: int, *, seed: int = 0, cap: int = 2048) -> list[list[dict]]:
         """`Trade_List`s of several trials of one taxable strategy in ONE launch (the <= 50 sampled trials of
@@ -253,10 +259,7 @@ class PathEngine:
             if cnt.max(initial=0) <= cap:
                 break
             cap = int(cnt.max())
-        return [[{"day_index": int(day[j, i]), "asset": abi.ASSET_NAMES[asset[j, i]],
-                  "action": "BUY" if action[j, i] > 0 else "SELL", "shares": float(shares[j, i]),
-                  "price": float(price[j, i]), "dollar_amount": float(shares[j, i] * price[j, i])}
-                 for i in range(int(cnt[j]))] for j in range(n)]
+        return [_trade_dicts(day[j], asset[j], action[j], shares[j], price[j], int(cnt[j])) for j in range(n)]
 
     def launch_info(self) -> dict:
         li = abi.LaunchInfo()
