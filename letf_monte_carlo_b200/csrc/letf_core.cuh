@@ -497,6 +497,16 @@ struct Trial {
       for (int c = 0; c < 3; c++) { z1[c] = tp_get(ka.tape.boot_t, (int64_t)g * 3 + c); z2[c] = tp_get(ka.tape.x, (int64_t)g * 3 + c); }
       vix_n = tp_get(ka.tape.vix_n, g); irx_n = tp_get(ka.tape.irx_n, g);
     } else {
+      if (!EXACT && p.pt_fast_k == 5) {
+        // cfg.STUDENT_T_DF's default: the six variates straight-line, their Philox blocks three at a time with
+        // interleaved rounds (same counters and arithmetic as the general branch below)
+        const uint32_t s1[3] = {STREAM_BN0, STREAM_BN0 + 1, STREAM_BN0 + 2}, s2[3] = {STREAM_PT0, STREAM_PT0 + 1, STREAM_PT0 + 2};
+        U4 w1[3], w2[3];
+        rng_blocks<3>(key, (uint32_t)g, s1, w1);
+        rng_blocks<3>(key, (uint32_t)g, s2, w2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) { z1[c] = student_t5<R>(w1[c]); z2[c] = student_t5<R>(w2[c]); }
+      } else
       for (int c = 0; c < 3; c++) {
         const U4 w1 = rng_block(key, (uint32_t)g, STREAM_BN0 + c);
         z1[c] = student_t_block<R, KEYREF>(w1, p.pt_df, p.pt_fast_k, key, (uint32_t)g, STREAM_BN0 + c);
