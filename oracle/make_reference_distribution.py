@@ -25,6 +25,10 @@ SIDS = ["S1", "S2", "S3", "S4", "S5", "S6", "S7", "S19", "B_QQQ", "B_TLT"]
 from letf_monte_carlo_b200 import synthetic  # noqa: E402
 
 
+MODE = "inst"          # "inst": institutional_v1 defaults; "boot": legacy_hybrid block bootstrap over synthetic_history()
+_BOOT = {}
+
+
 def _init():
     sys.path.insert(0, REF)
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache_golden")
@@ -33,12 +37,20 @@ def _init():
     from letf import config as ref_cfg
     for k, v in synthetic.EXTRA_BENCHMARKS.items():
         ref_cfg.STRATEGIES[k] = dict(v)
+    if MODE == "boot":
+        import contextlib, io
+        from letf.simulation.bootstrap import BlockBootstrapReturns
+        ref_cfg.SIM_ENGINE_MODE = "legacy_hybrid"
+        with contextlib.redirect_stdout(io.StringIO()):      # the reference's own sampler (bootstrap.py:27-47)
+            _BOOT["sampler"] = BlockBootstrapReturns(synthetic.synthetic_history(), block_size=ref_cfg.BOOTSTRAP_BLOCK_SIZE)
 
 
 def _one(args):
     sim_id, years, anti = args
     from letf.simulation import engine as ref_engine
     model = synthetic.fallback_regime_model("default")
+    if MODE == "boot":
+        model["bootstrap_sampler"] = _BOOT["sampler"]
     res = ref_engine.simulate_single_path_fixed((sim_id, years, model, {}, SIDS, anti))
     row = []
     for s in SIDS:
@@ -56,10 +68,17 @@ def main():
     ap.add_argument("--pairs", type=int, default=1000)
     ap.add_argument("--years", type=float, default=2)
     ap.add_argument("--procs", type=int, default=os.cpu_count())
-    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "ref_distribution_2y.npz"))
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--mode", default="inst", choices=["inst", "boot"])
     a = ap.parse_args()
+    global MODE
+    MODE = a.mode
+    if a.out is None:
+        a.out = os.path.join(ROOT, "tests", "golden", "ref_distribution_2y.npz" if MODE == "inst" else "ref_distribution_boot_1y.npz")
     # mc_runner.py:145-153: (sim_id, False), (sim_id, True) for sim_id = 0, 2, 4, ...
     tasks = [(2 * k, a.years, anti) for k in range(a.pairs) for anti in (False, True)]
+    if MODE == "boot":     # outside the joint-t generator the antithetic flag is never read: twins would be identical paths
+        tasks = [(k, a.years, False) for k in range(2 * a.pairs)]
     t0 = time.time()
     with mp.get_context("fork").Pool(a.procs, initializer=_init) as pool:
         out = pool.map(_one, tasks, chunksize=4)
@@ -74,7 +93,9 @@ def main():
                         repaired=np.array([o[3] for o in out]),
                         versions=np.array([f"numpy {np.__version__}", f"pandas {pandas.__version__}", f"scipy {scipy.__version__}"]),
                         generator=np.array("oracle/make_reference_distribution.py: live reference, its own PCG64 streams, "
-                                           "fallback regime model, default cfg (institutional_v1, antithetic, moment matching, offset start)"))
+                                           + ("fallback regime model, default cfg (institutional_v1, antithetic, moment matching, offset start)"
+                                              if MODE == "inst" else
+                                              "legacy_hybrid block bootstrap (the reference's BlockBootstrapReturns over synthetic_history()), offset start")))
     print(f"{n} trials in {time.time() - t0:.0f}s -> {a.out}")
 
 

@@ -56,11 +56,24 @@ def assert_matches_reference(out, doc, rtol, dd_atol, exact_counts=True, journal
     np.testing.assert_array_equal(rep, np.array(meta["repaired"]))
 
 
-def reference_distribution():
+def reference_distribution(name="ref_distribution_2y.npz"):
     """terminal statistics of the LIVE reference run with its own NumPy streams
-    (oracle/make_reference_distribution.py -> tests/golden/ref_distribution_2y.npz)"""
-    d = np.load(os.path.join(GOLDEN_DIR, "ref_distribution_2y.npz"))
+    (oracle/make_reference_distribution.py -> tests/golden/ref_distribution_2y.npz, ref_distribution_boot_1y.npz)"""
+    d = np.load(os.path.join(GOLDEN_DIR, name))
     return {k: d[k] for k in d.files}
+
+
+def bootstrap_distribution_case():
+    """(reference arrays, strategy ids, params, keepalive) of the legacy_hybrid block-bootstrap distribution fixture:
+    the reference's own BlockBootstrapReturns over synthetic_history(), 8 000 independent trials, 1 year."""
+    from letf_monte_carlo_b200 import synthetic
+    from letf_monte_carlo_b200.params import build_params
+    ref = reference_distribution("ref_distribution_boot_1y.npz")
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, SIM_ENGINE_MODE="legacy_hybrid",
+                                    USE_ANTITHETIC_VARIATES=False)
+    params, keep = build_params(sids, float(ref["years"]), synthetic.legacy_bootstrap_model(), ns)
+    return ref, sids, params, keep
 
 
 def assert_same_distribution(ref, out, sids, p_min=1e-3):

@@ -557,3 +557,14 @@ def test_typed_series_kernel_vs_generic_and_oracle(engine_lib):
     assert np.median(np.abs(typed.final_wealth / o.final_wealth - 1)[same]) < 1e-5
     np.testing.assert_allclose(typed.final_wealth[same], o.final_wealth[same], rtol=5e-4)
     np.testing.assert_allclose(typed.final_wealth[:3], o.final_wealth[:3], rtol=2e-5)      # buy & hold rows
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_bootstrap_philox_distribution_matches_live_reference(precision, engine_lib):
+    """KS + summary-quantile agreement of the on-device block bootstrap with the LIVE reference's own sampler and NumPy
+    streams (tests/golden/ref_distribution_boot_1y.npz: 8 000 trials, legacy_hybrid, 1 year, 10 strategies)."""
+    from tests.common import assert_same_distribution, bootstrap_distribution_case
+    ref, sids, params, keep = bootstrap_distribution_case()
+    with _engine(params, keep, precision) as eng:
+        out = eng.run_host(40000, seed=1618)
+    assert_same_distribution(ref, out, sids)

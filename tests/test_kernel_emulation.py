@@ -212,6 +212,16 @@ def test_philox_distribution_matches_live_reference():
     assert_same_distribution(ref, out, sids)
 
 
+def test_bootstrap_philox_distribution_matches_live_reference():
+    """same for the legacy_hybrid block bootstrap: the reference side ran its own BlockBootstrapReturns with NumPy's
+    geometric / integers / choice(p=...) / standard_t streams (tests/golden/ref_distribution_boot_1y.npz)."""
+    from tests.common import assert_same_distribution, bootstrap_distribution_case
+    ref, sids, params, keep = bootstrap_distribution_case()
+    assert params.market_mode == abi.MARKET_BOOTSTRAP
+    out = emu.run(params, _blank_tape(params, 1, 1), precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=23, n=8000)
+    assert_same_distribution(ref, out, sids)
+
+
 @pytest.mark.parametrize("slot_list,sids", [(1, ["S1", "S2", "S4", "S5", "S6", "S19"]), (2, ALL19)])
 def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
     """one compile-time rule per slot + compile-time asset mask (the c4 and default-sweep builds) must
