@@ -37,6 +37,9 @@ def _init():
     from letf import config as ref_cfg
     for k, v in synthetic.EXTRA_BENCHMARKS.items():
         ref_cfg.STRATEGIES[k] = dict(v)
+    if MODE == "anchor":      # random_start.py:182-191: start regime from a uniformly drawn historical row
+        ref_cfg.RANDOM_START_METHOD = "historical_anchor"
+        _BOOT["anchors"] = synthetic.synthetic_history(n_days=3000, seed=5)
     if MODE == "boot":
         import contextlib, io
         from letf.simulation.bootstrap import BlockBootstrapReturns
@@ -51,6 +54,8 @@ def _one(args):
     model = synthetic.fallback_regime_model("default")
     if MODE == "boot":
         model["bootstrap_sampler"] = _BOOT["sampler"]
+    if MODE == "anchor":
+        model["historical_df_for_anchors"] = _BOOT["anchors"]
     res = ref_engine.simulate_single_path_fixed((sim_id, years, model, {}, SIDS, anti))
     row = []
     for s in SIDS:
@@ -69,12 +74,13 @@ def main():
     ap.add_argument("--years", type=float, default=2)
     ap.add_argument("--procs", type=int, default=os.cpu_count())
     ap.add_argument("--out", default=None)
-    ap.add_argument("--mode", default="inst", choices=["inst", "boot"])
+    ap.add_argument("--mode", default="inst", choices=["inst", "boot", "anchor"])
     a = ap.parse_args()
     global MODE
     MODE = a.mode
     if a.out is None:
-        a.out = os.path.join(ROOT, "tests", "golden", "ref_distribution_2y.npz" if MODE == "inst" else "ref_distribution_boot_1y.npz")
+        a.out = os.path.join(ROOT, "tests", "golden", {"inst": "ref_distribution_2y.npz", "boot": "ref_distribution_boot_1y.npz",
+                                                       "anchor": "ref_distribution_anchor_1y.npz"}[MODE])
     # mc_runner.py:145-153: (sim_id, False), (sim_id, True) for sim_id = 0, 2, 4, ...
     tasks = [(2 * k, a.years, anti) for k in range(a.pairs) for anti in (False, True)]
     if MODE == "boot":     # outside the joint-t generator the antithetic flag is never read: twins would be identical paths
@@ -95,6 +101,8 @@ def main():
                         generator=np.array("oracle/make_reference_distribution.py: live reference, its own PCG64 streams, "
                                            + ("fallback regime model, default cfg (institutional_v1, antithetic, moment matching, offset start)"
                                               if MODE == "inst" else
+                                              "institutional_v1 defaults with RANDOM_START_METHOD = 'historical_anchor' over "
+                                              "synthetic_history(n_days=3000, seed=5)" if MODE == "anchor" else
                                               "legacy_hybrid block bootstrap (the reference's BlockBootstrapReturns over synthetic_history()), offset start")))
     print(f"{n} trials in {time.time() - t0:.0f}s -> {a.out}")
 

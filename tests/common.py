@@ -76,6 +76,20 @@ def bootstrap_distribution_case():
     return ref, sids, params, keep
 
 
+def anchor_distribution_case():
+    """RANDOM_START_METHOD = 'historical_anchor' (random_start.py:182-191): the reference draws a uniform anchor row of the
+    history and starts in its regime; here that is a Bernoulli start regime with the share of high-VIX valid rows."""
+    from letf_monte_carlo_b200 import synthetic
+    from letf_monte_carlo_b200.params import build_params
+    ref = reference_distribution("ref_distribution_anchor_1y.npz")
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, RANDOM_START_METHOD="historical_anchor")
+    model = synthetic.fallback_regime_model("default")
+    model["historical_df_for_anchors"] = synthetic.synthetic_history(n_days=3000, seed=5)
+    params, keep = build_params(sids, float(ref["years"]), model, ns)
+    return ref, sids, params, keep
+
+
 def assert_same_distribution(ref, out, sids, p_min=1e-3):
     """two-sample KS on terminal wealth and max drawdown per strategy, summary quantiles of wealth (rank agreement),
     mean trade counts within 3 %, regime / jump / repair statistics within sampling error"""

@@ -568,3 +568,14 @@ def test_bootstrap_philox_distribution_matches_live_reference(precision, engine_
     with _engine(params, keep, precision) as eng:
         out = eng.run_host(40000, seed=1618)
     assert_same_distribution(ref, out, sids)
+
+
+def test_historical_anchor_start_matches_live_reference(engine_lib):
+    """RANDOM_START_METHOD = 'historical_anchor': Bernoulli start regime on the device against the reference's uniformly
+    drawn history row (tests/golden/ref_distribution_anchor_1y.npz, 4 000 live-reference trials)."""
+    from tests.common import anchor_distribution_case, assert_same_distribution
+    ref, sids, params, keep = anchor_distribution_case()
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run_host(40000, seed=577)
+    assert_same_distribution(ref, out, sids)
+    assert stats.ks_2samp(ref["high_vol_days"], out.regime_days[1]).pvalue > 1e-3

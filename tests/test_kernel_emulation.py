@@ -222,6 +222,20 @@ def test_bootstrap_philox_distribution_matches_live_reference():
     assert_same_distribution(ref, out, sids)
 
 
+def test_historical_anchor_start_matches_live_reference():
+    """'historical_anchor' start: Bernoulli start regime here, a uniformly drawn history row in the reference
+    (tests/golden/ref_distribution_anchor_1y.npz: 4 000 trials, institutional_v1, 1 year, no buffer)."""
+    from scipy import stats as st
+    from tests.common import anchor_distribution_case, assert_same_distribution
+    ref, sids, params, keep = anchor_distribution_case()
+    assert params.buffer_days == 0 and 0.05 < params.start_regime_prob1 < 0.95
+    out = emu.run(params, HostTape(1, params.sim_days, params.sim_days, 1), precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX,
+                  seed=29, n=8000)
+    assert_same_distribution(ref, out, sids)
+    # the start regime drives the regime-day counts of a 1-year window directly: compare their whole distribution
+    assert st.ks_2samp(ref["high_vol_days"], out.regime_days[1]).pvalue > 1e-3
+
+
 @pytest.mark.parametrize("slot_list,sids", [(1, ["S1", "S2", "S4", "S5", "S6", "S19"]), (2, ALL19)])
 def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
     """one compile-time rule per slot + compile-time asset mask (the c4 and default-sweep builds) must
