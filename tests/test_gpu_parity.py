@@ -579,3 +579,27 @@ def test_historical_anchor_start_matches_live_reference(engine_lib):
         out = eng.run_host(40000, seed=577)
     assert_same_distribution(ref, out, sids)
     assert stats.ks_2samp(ref["high_vol_days"], out.regime_days[1]).pvalue > 1e-3
+
+
+def test_public_api_bootstrap_via_historical_df(engine_lib):
+    """mc_runner.py:79-84: parallel_monte_carlo_fixed(..., historical_df) builds the sampler itself; in legacy_hybrid mode
+    that selects the block-bootstrap generator.  Same results as handing the sampler over in regime_model; the engine
+    handle is reused across calls with the same tables (content-keyed cache)."""
+    from letf_monte_carlo_b200 import parallel_monte_carlo_fixed
+    from letf_monte_carlo_b200.bootstrap import create_bootstrap_sampler
+    hist = synthetic.synthetic_history(n_days=8000, seed=9)
+    ns = synthetic.config_namespace(NUM_SIMULATIONS=300, SIM_ENGINE_MODE="legacy_hybrid")
+    sids = ["S1", "S2", "S4", "S9"]
+    a = parallel_monte_carlo_fixed(sids, 2, synthetic.fallback_regime_model(), {}, hist, cfg=ns, verbose=False, device=0)
+    assert a.engine.params.market_mode == abi.MARKET_BOOTSTRAP and a.engine.params.boot.hist_len == 8000
+    model = synthetic.fallback_regime_model()
+    model["bootstrap_sampler"] = create_bootstrap_sampler(hist, cfg=ns)
+    b = parallel_monte_carlo_fixed(sids, 2, model, {}, cfg=ns, verbose=False, device=0)
+    assert b.engine is a.engine
+    for sid in sids:
+        np.testing.assert_array_equal(a[sid].final_wealth, b[sid].final_wealth)
+        assert np.isfinite(a[sid].final_wealth).all() and (a[sid].final_wealth > 0).all()
+    assert a["S4"].num_trades.sum() > 0
+    inst = parallel_monte_carlo_fixed(sids, 2, synthetic.fallback_regime_model(), {}, hist,
+                                      cfg=synthetic.config_namespace(NUM_SIMULATIONS=300), verbose=False, device=0)
+    assert inst.engine.params.market_mode == abi.MARKET_JOINT_T      # institutional_v1 + joint model wins (engine.py:45)
