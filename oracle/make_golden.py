@@ -66,6 +66,8 @@ CASES = [
     dict(name="boot_3y_nan_fixed_start", variant="boot_nan", years=3, n_tapes=2, seed=120,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MEAN": 40,
               "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME": {0: 0.9, 1: 0.2}}, strategies=ALL19),
+    dict(name="boot_10y", variant="boot", years=10, n_tapes=1, seed=124,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid"}, strategies=ALL19 + EXTRAS),
     dict(name="boot_fullblocks_1y", variant="boot", years=1, n_tapes=2, seed=121,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MIN": 168,
               "BOOTSTRAP_BLOCK_MAX": 168, "USE_ANTITHETIC_VARIATES": False}, strategies=ALL19),
