@@ -168,6 +168,7 @@ typedef struct LetfBootstrap {         /* bootstrap_sampler + cfg.BOOTSTRAP_* (l
   const double* hist_spy;     /* HOST [hist_len] SPY_Ret, NaN -> 0 (bootstrap.py:131) */
   const double* hist_qqq;     /* HOST [hist_len] QQQ_Ret, NaN -> 0 */
   const double* hist_tlt;     /* HOST [hist_len] TLT_Ret, NaN -> 0 */
+  /* a pool may be EMPTY (n_blocks 0): its blocks are then synthetic Student-t returns, bootstrap.py:214-222, 273-300 */
   LetfBootstrapPool pool_a[2];   /* "economy" pool: SPY comes from these blocks */
   LetfBootstrapPool pool_b[2];   /* "tech" pool (real-QQQ era): QQQ and TLT come from these blocks */
 } LetfBootstrap;
@@ -256,12 +257,15 @@ typedef struct LetfTape {
   double* te_t;                  /* [6][T][n] t(te_df[a])              engine.py:185 */
   /* MARKET_BOOTSTRAP only (NULL otherwise); block k of a trial, at most max_blocks = G / block_min + 2 */
   int32_t max_blocks;
-  int32_t pad2;
+  int32_t boot_block_size;       /* rows per synthetic block in boot_syn (= LetfBootstrap.block_size), 0 without boot_syn */
   int32_t* boot_len;             /* [max_blocks][n]    geometric(1 / block_mean)            bootstrap.py:304 */
   double* boot_u;                /* [max_blocks][6][n] U[0,1): momentum A, block A, offset A, momentum B,
                                     block B (uniform index or weighted choice), offset B      bootstrap.py:212-262, 348-374 */
   double* boot_t;                /* [G][3][n] t(df) noise of sample_returns                  bootstrap.py:400 */
   int32_t* start_regime;         /* [n] 0 / 1, random_start.py:31 / :106 (NULL or zeros: regime 0) */
+  double* boot_syn;              /* [max_blocks][2][boot_block_size][n] t(df) of the synthetic blocks that stand in for an
+                                    empty pool (pool A / B of the block's regime), bootstrap.py:295; NULL when every
+                                    pool has blocks */
 } LetfTape;
 
 /* per-trial outputs, structure-of-arrays: [strategy][n_trials] */

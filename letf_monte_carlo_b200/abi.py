@@ -134,14 +134,14 @@ class Tape(C.Structure):
         ("chi2", C.c_void_p), ("vix_n", C.c_void_p), ("irx_n", C.c_void_p),
         ("liq_n", C.c_void_p), ("cred_n", C.c_void_p), ("jump_u", C.c_void_p),
         ("jump_t", C.c_void_p), ("sign", C.c_void_p), ("te_t", C.c_void_p),
-        ("max_blocks", C.c_int32), ("pad2", C.c_int32),
+        ("max_blocks", C.c_int32), ("boot_block_size", C.c_int32),
         ("boot_len", C.c_void_p), ("boot_u", C.c_void_p), ("boot_t", C.c_void_p),
-        ("start_regime", C.c_void_p),
+        ("start_regime", C.c_void_p), ("boot_syn", C.c_void_p),
     ]
 
 
 TAPE_FIELDS = ("start_offset", "spells", "x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n",
-               "jump_u", "jump_t", "sign", "te_t", "boot_len", "boot_u", "boot_t", "start_regime")
+               "jump_u", "jump_t", "sign", "te_t", "boot_len", "boot_u", "boot_t", "start_regime", "boot_syn")
 
 
 class Outputs(C.Structure):

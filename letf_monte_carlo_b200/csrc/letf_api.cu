@@ -234,6 +234,12 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
     if (tape->n_tapes < need) return fail(LETF_ERR_INVALID, "tape has fewer columns than the trial range needs");
     if (market == LETF_MARKET_BOOTSTRAP && (!tape->boot_len || !tape->boot_u || !tape->boot_t || tape->max_blocks < 1))
       return fail(LETF_ERR_INVALID, "bootstrap tape arrays missing");
+    if (market == LETF_MARKET_BOOTSTRAP) {
+      const LetfBootstrap& bb = e->params.boot;
+      const bool empty = !bb.pool_a[0].n_blocks || !bb.pool_a[1].n_blocks || !bb.pool_b[0].n_blocks || !bb.pool_b[1].n_blocks;
+      if (empty && (!tape->boot_syn || tape->boot_block_size != bb.block_size))
+        return fail(LETF_ERR_INVALID, "a bootstrap pool is empty: the tape needs boot_syn with boot_block_size == block_size");
+    }
   }
   if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
@@ -419,14 +425,15 @@ int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
 // ---- host-buffer entry points ------------------------------------------------------------------
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-constexpr int kTapeFields = 16;
+constexpr int kTapeFields = 17;
 struct TapeLayout { size_t off[kTapeFields]; size_t bytes[kTapeFields]; size_t total; };
 static TapeLayout tape_layout(const LetfTape& t) {
   const size_t n = (size_t)t.n_tapes, G = (size_t)t.gen_days, T = (size_t)t.sim_days, K = (size_t)t.max_spells;
   const size_t B = t.boot_len ? (size_t)t.max_blocks : 0;
   const size_t b[kTapeFields] = {4 * n, 4 * K * n, 8 * G * 3 * n, 8 * G * n, 8 * G * n, 8 * G * n,
                                  8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * T * n, 8 * LETF_N_ASSETS * T * n,
-                                 4 * B * n, 8 * B * 6 * n, B ? 8 * G * 3 * n : 0, t.start_regime ? 4 * n : 0};
+                                 4 * B * n, 8 * B * 6 * n, B ? 8 * G * 3 * n : 0, t.start_regime ? 4 * n : 0,
+                                 (t.boot_syn && B) ? 8 * B * 2 * (size_t)t.boot_block_size * n : 0};
   TapeLayout L; size_t o = 0;
   for (int i = 0; i < kTapeFields; i++) { L.off[i] = o; L.bytes[i] = b[i]; o += align256(b[i]); }
   L.total = o;
@@ -439,7 +446,7 @@ static void** tape_field(LetfTape& t, int i) {
     case 6: return (void**)&t.liq_n; case 7: return (void**)&t.cred_n; case 8: return (void**)&t.jump_u;
     case 9: return (void**)&t.jump_t; case 10: return (void**)&t.sign; case 11: return (void**)&t.te_t;
     case 12: return (void**)&t.boot_len; case 13: return (void**)&t.boot_u; case 14: return (void**)&t.boot_t;
-    default: return (void**)&t.start_regime;
+    case 15: return (void**)&t.start_regime; default: return (void**)&t.boot_syn;
   }
 }
 

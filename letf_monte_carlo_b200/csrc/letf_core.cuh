@@ -465,23 +465,48 @@ struct Trial {
       for (int j = 0; j < len; j++) ones += regime_next(rgl);
       const int regime = 2 * ones > len ? 1 : 0;                      // int(np.median(block_regime_path)), bootstrap.py:340
       const int span = b.block_size - len + 1;                        // sub-section starts (bootstrap.py:350-352)
-      int row_a = boot_pick(0, regime, have_last, last_a, u[0], u[1], false, (R)0);
+      // an empty pool is served by a synthetic block (bootstrap.py:214-222, 273-300): Student-t draws times a regime
+      // volatility for SPY, QQQ = 1.25 SPY, TLT = -0.25 SPY; no momentum coin, no block index, same sub-section rule
+      const bool syn_a = b.cnt[0][regime][0] == 0, syn_b = b.cnt[1][regime][0] == 0;
+      const R syn_std = regime == 0 ? (R)0.011 : (R)0.035;
+      auto syn = [&](int q, int row) -> R {                           // row of block kb's synthetic block for pool q
+        R t;
+        const int64_t slot = ((int64_t)kb * 2 + q) * ka.tape.boot_block_size + row;
+        if (use_tape) t = ka.tape.boot_syn ? tp_get(ka.tape.boot_syn, slot) : (R)0;
+        else {
+          const uint32_t ctr = (uint32_t)kb * (uint32_t)b.block_size + (uint32_t)row;
+          const U4 w = rng_block(key, ctr, STREAM_BOOT_SYN + q);
+          t = student_t_block<R, KEYREF>(w, p.pt_df, p.pt_fast_k, key, ctr, STREAM_BOOT_SYN + q);
+          if (rec && ka.tape.boot_syn && kb < ka.tape.max_blocks) tp_put(ka.tape.boot_syn, slot, t);
+        }
+        return t * syn_std;
+      };
+      int row_a = syn_a ? 0 : boot_pick(0, regime, have_last, last_a, u[0], u[1], false, (R)0);
       if (len < b.block_size) { int o = (int)M::floor_(u[2] * (R)span); row_a += o > span - 1 ? span - 1 : o; }
-      const R* hs = b.hist[0] + row_a;
+      const R* hs = b.hist[0] + (syn_a ? 0 : row_a);
       R prod_a = (R)1;
-      for (int j = 0; j < len; j++) prod_a *= (R)1 + hs[j];
+      if (!syn_a) { for (int j = 0; j < len; j++) prod_a *= (R)1 + hs[j]; }          // (the common case stays a plain gather loop)
+      else { for (int j = 0; j < len; j++) prod_a *= (R)1 + syn(0, row_a + j); }
       const R spy_ret = prod_a - (R)1;
-      int row_b = boot_pick(1, regime, have_last, last_b, u[3], u[4], true, spy_ret);
+      int row_b = syn_b ? 0 : boot_pick(1, regime, have_last, last_b, u[3], u[4], true, spy_ret);
       if (len < b.block_size) { int o = (int)M::floor_(u[5] * (R)span); row_b += o > span - 1 ? span - 1 : o; }
-      const R* hq = b.hist[1] + row_b;
-      const R* ht = b.hist[2] + row_b;
+      const R* hq = b.hist[1] + (syn_b ? 0 : row_b);
+      const R* ht = b.hist[2] + (syn_b ? 0 : row_b);
       R prod_b = (R)1;
-      for (int j = 0; j < len; j++) {
-        X4 v; v.x = hs[j]; v.y = hq[j]; v.z = ht[j]; v.w = (R)0;
+      auto put = [&](int j, R vx, R vy, R vz) {
+        X4 v; v.x = vx; v.y = vy; v.z = vz; v.w = (R)0;
         xs[cur + j] = v;
-        prod_b *= (R)1 + v.y;
-        const R xv[3] = {v.x, v.y, v.z};
+        prod_b *= (R)1 + vy;
+        const R xv[3] = {vx, vy, vz};
         for (int a = 0; a < 3; a++) { R y = xv[a] - cmp[a], t = sum[a] + y; cmp[a] = (t - sum[a]) - y; sum[a] = t; }
+      };
+      if (!syn_a && !syn_b) { for (int j = 0; j < len; j++) put(j, hs[j], hq[j], ht[j]); }
+      else {
+        for (int j = 0; j < len; j++) {
+          const R vx = syn_a ? syn(0, row_a + j) : hs[j];
+          if (syn_b) { const R sb = syn(1, row_b + j); put(j, vx, sb * (R)1.25, -sb * (R)0.25); }
+          else put(j, vx, hq[j], ht[j]);
+        }
       }
       last_a = spy_ret; last_b = prod_b - (R)1; have_last = true;
       cur += len; kb++;

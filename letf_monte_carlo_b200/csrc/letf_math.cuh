@@ -59,7 +59,8 @@ enum : uint32_t {
   STREAM_JUMP = 6, STREAM_MKT_PAIR = 7 /* iid-normal market: one block per two days */,
   STREAM_TE0 = 8 /* +asset */, STREAM_PT0 = 16 /* +component, PARAM_T and the second noise blend of BOOTSTRAP */,
   STREAM_BOOT_A = 24 /* counter = block index: length, momentum A, block A, offset A */,
-  STREAM_BOOT_B = 25 /* momentum B, block B, offset B */, STREAM_BN0 = 26 /* +component: sample_returns noise */
+  STREAM_BOOT_B = 25 /* momentum B, block B, offset B */, STREAM_BN0 = 26 /* +component: sample_returns noise */,
+  STREAM_BOOT_SYN = 30 /* +pool: synthetic blocks of an empty pool, counter = block index * block_size + row */
 };
 
 struct RngKey {

@@ -115,7 +115,7 @@ inline const char* validate_params(const LetfParams& s) {
     if (!(b.block_mean > 1.0)) return "bootstrap block_mean must be > 1";
     for (int q = 0; q < 2; q++) for (int r = 0; r < 2; r++) {
       const LetfBootstrapPool& pl = q ? b.pool_b[r] : b.pool_a[r];
-      if (pl.n_blocks <= 0 || !pl.start || !pl.block_ret) return "bootstrap pools must be non-empty (the synthetic-block fallback is not implemented)";
+      if (pl.n_blocks < 0 || (pl.n_blocks > 0 && (!pl.start || !pl.block_ret))) return "bootstrap pool table missing";
       for (int i = 0; i < pl.n_blocks; i++)
         if (pl.start[i] < 0 || pl.start[i] + b.block_size > b.hist_len) return "bootstrap block outside the history";
     }

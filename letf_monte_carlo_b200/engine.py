@@ -56,6 +56,7 @@ class DeviceTape:
         h = self.host
         s.n_tapes, s.gen_days, s.sim_days, s.max_spells = h.n_tapes, h.gen_days, h.sim_days, h.max_spells
         s.max_blocks = h.max_blocks
+        s.boot_block_size = h.boot_block_size
         for k, t in self.t.items():
             setattr(s, k, t.data_ptr() if t.numel() else None)
         return s

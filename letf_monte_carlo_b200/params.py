@@ -167,13 +167,11 @@ def _pack_bootstrap(p: abi.Params, keep: list, sampler, cfg) -> None:
     for name, table in (("pool_a", pools.pool_a), ("pool_b", pools.pool_b)):
         for r in range(2):
             start, ret = table[r]
-            if len(start) == 0:
-                # the reference would fall back to synthetic Student-t blocks (bootstrap.py:214-222)
-                raise UnsupportedConfig(f"bootstrap {name}[{r}] is empty: the synthetic-block fallback is not implemented")
             q = getattr(b, name)[r]
-            q.n_blocks = len(start)
-            q.start = start.ctypes.data_as(C.POINTER(C.c_int32))
-            q.block_ret = ret.ctypes.data_as(dp)
+            q.n_blocks = len(start)      # 0: this (pool, regime) is served by synthetic Student-t blocks (bootstrap.py:214-222)
+            if len(start):
+                q.start = start.ctypes.data_as(C.POINTER(C.c_int32))
+                q.block_ret = ret.ctypes.data_as(dp)
 
 
 _NEEDS_SPY = {abi.STRATEGY_TYPES[k] for k in ("sma", "sma_band", "composite", "adaptive_vol", "convex_vol",

@@ -13,19 +13,23 @@ import numpy as np
 
 from . import abi
 
-F64_FIELDS = ("x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n", "jump_u", "jump_t", "sign", "te_t", "boot_u", "boot_t")
+F64_FIELDS = ("x", "chi2", "vix_n", "irx_n", "liq_n", "cred_n", "jump_u", "jump_t", "sign", "te_t", "boot_u", "boot_t",
+              "boot_syn")
 
 
 class HostTape:
     """numpy-backed LetfTape."""
 
-    def __init__(self, n_tapes: int, gen_days: int, sim_days: int, max_spells: int, max_blocks: int = 0):
+    def __init__(self, n_tapes: int, gen_days: int, sim_days: int, max_spells: int, max_blocks: int = 0,
+                 syn_block_size: int = 0):
         n, G, T, K = int(n_tapes), int(gen_days), int(sim_days), int(max_spells)
         self.n_tapes, self.gen_days, self.sim_days, self.max_spells = n, G, T, K
         self.max_blocks = B = int(max_blocks)         # MARKET_BOOTSTRAP only
         self.boot_len = np.ones((B, n), np.int32)
         self.boot_u = np.zeros((B, 6, n))
         self.boot_t = np.zeros((G if B else 0, 3, n))
+        self.boot_block_size = int(syn_block_size) if B else 0   # > 0: some pool is empty -> synthetic-block variates
+        self.boot_syn = np.zeros((B if self.boot_block_size else 0, 2, self.boot_block_size, n))
         self.start_offset = np.zeros(n, np.int32)
         self.start_regime = np.zeros(n, np.int32)
         self.spells = np.full((K, n), max(G, 1), np.int32)
@@ -47,6 +51,7 @@ class HostTape:
         t = abi.Tape()
         t.n_tapes, t.gen_days, t.sim_days, t.max_spells = self.n_tapes, self.gen_days, self.sim_days, self.max_spells
         t.max_blocks = self.max_blocks
+        t.boot_block_size = self.boot_block_size
         for k, a in self.arrays().items():
             assert a.flags["C_CONTIGUOUS"]
             setattr(t, k, a.ctypes.data if a.size else None)
@@ -70,6 +75,17 @@ class HostTape:
                 if flip[cur]:
                     cur = 1 - cur
         return reg
+
+
+def boot_tape_shape(params: abi.Params):
+    """(max_blocks, synthetic block size) of a tape for these parameters: (0, 0) outside MARKET_BOOTSTRAP; the
+    synthetic-block array only exists when some pool is empty (bootstrap.py:214-222)."""
+    if params.market_mode != abi.MARKET_BOOTSTRAP:
+        return 0, 0
+    b = params.boot
+    G = int(params.sim_days + params.buffer_days)
+    empty = any(pl[r].n_blocks == 0 for pl in (b.pool_a, b.pool_b) for r in range(2))
+    return G // max(int(b.block_min), 1) + 2, (int(b.block_size) if empty else 0)
 
 
 def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
@@ -102,7 +118,7 @@ def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
             cover += np.maximum(s, 1)
             k += 1
     boot = params.market_mode == abi.MARKET_BOOTSTRAP
-    tp = HostTape(n, G, T, max(len(spells), 1), (G // max(int(params.boot.block_min), 1) + 2) if boot else 0)
+    tp = HostTape(n, G, T, max(len(spells), 1), *boot_tape_shape(params))
     for i, s in enumerate(spells):
         tp.spells[i] = s
     tp.start_regime[:] = start_regime
@@ -114,6 +130,8 @@ def make_tape(params: abi.Params, n_tapes: int, seed: int) -> HostTape:
         tp.boot_len[:] = rng.geometric(1.0 / params.boot.block_mean, size=tp.boot_len.shape)
         tp.boot_u[:] = rng.random(tp.boot_u.shape)
         tp.boot_t[:] = rng.standard_t(params.param_t_df, size=tp.boot_t.shape)
+        if tp.boot_syn.size:
+            tp.boot_syn[:] = rng.standard_t(params.param_t_df, size=tp.boot_syn.shape)
     if params.market_mode in (abi.MARKET_PARAM_T, abi.MARKET_BOOTSTRAP):
         tp.x[:] = rng.standard_t(params.param_t_df, size=tp.x.shape)
     else:

@@ -738,24 +738,28 @@ static int boot_generate(const LetfParams* p, const LetfTape* tp, int64_t ti, in
 #define BU(s) tp->boot_u[((int64_t)k * 6 + (s)) * n + ti]
     const LetfBootstrapPool* pa = &b->pool_a[regime];
     const LetfBootstrapPool* pb = &b->pool_b[regime];
-    if (pa->n_blocks <= 0 || pb->n_blocks <= 0) return LETF_ERR_INVALID;
-    int ia = boot_pick(pa, have_last, last_a, bias, BU(0), BU(1), 0, 0.0);
-    int row_a = pa->start[ia];
+    /* an empty pool is served by a synthetic block (bootstrap.py:214-222, 273-300): block_size Student-t draws times a
+     * regime volatility for SPY, QQQ = 1.25 SPY, TLT = -0.25 SPY; no momentum coin, no block index, same sub-section rule */
+    const int syn_a = pa->n_blocks <= 0, syn_b = pb->n_blocks <= 0;
+    if ((syn_a || syn_b) && (!tp->boot_syn || tp->boot_block_size != b->block_size)) return LETF_ERR_INVALID;
+    const double syn_std = regime == 0 ? 0.011 : 0.035;
+#define SYN(q, j) (tp->boot_syn[(((int64_t)k * 2 + (q)) * tp->boot_block_size + (j)) * n + ti] * syn_std)
+    int row_a = syn_a ? 0 : pa->start[boot_pick(pa, have_last, last_a, bias, BU(0), BU(1), 0, 0.0)];
     if (len < b->block_size) row_a += (int)floor(BU(2) * (double)(b->block_size - len + 1));
     double prod_a = 1.0;
-    for (int j = 0; j < len; j++) prod_a *= 1 + b->hist_spy[row_a + j];
+    for (int j = 0; j < len; j++) prod_a *= 1 + (syn_a ? SYN(0, row_a + j) : b->hist_spy[row_a + j]);
     const double spy_block_return = prod_a - 1;
-    int ib = boot_pick(pb, have_last, last_b, bias, BU(3), BU(4), 1, spy_block_return);
-    int row_b = pb->start[ib];
+    int row_b = syn_b ? 0 : pb->start[boot_pick(pb, have_last, last_b, bias, BU(3), BU(4), 1, spy_block_return)];
     if (len < b->block_size) row_b += (int)floor(BU(5) * (double)(b->block_size - len + 1));
 #undef BU
     double prod_b = 1.0;
     for (int j = 0; j < len; j++) {
-      spy[cur + j] = b->hist_spy[row_a + j];
-      qqq[cur + j] = b->hist_qqq[row_b + j];
-      tlt[cur + j] = b->hist_tlt[row_b + j];
-      prod_b *= 1 + b->hist_qqq[row_b + j];
+      spy[cur + j] = syn_a ? SYN(0, row_a + j) : b->hist_spy[row_a + j];
+      qqq[cur + j] = syn_b ? SYN(1, row_b + j) * 1.25 : b->hist_qqq[row_b + j];
+      tlt[cur + j] = syn_b ? -SYN(1, row_b + j) * 0.25 : b->hist_tlt[row_b + j];
+      prod_b *= 1 + qqq[cur + j];
     }
+#undef SYN
     last_a = spy_block_return; last_b = prod_b - 1; have_last = 1;
     cur += len; k++;
   }
@@ -1275,6 +1279,9 @@ int letf_oracle_fill_tape(const LetfParams* p, uint64_t seed, LetfTape* tp) {
         tp->boot_len[(int64_t)kb * n + c] = (int)ceil(log(1.0 - xo_u(&g)) / log(1.0 - 1.0 / p->boot.block_mean));
         if (tp->boot_len[(int64_t)kb * n + c] < 1) tp->boot_len[(int64_t)kb * n + c] = 1;
         for (int q = 0; q < 6; q++) tp->boot_u[((int64_t)kb * 6 + q) * n + c] = xo_u(&g);
+        if (tp->boot_syn)
+          for (int q = 0; q < 2 * tp->boot_block_size; q++)
+            tp->boot_syn[((int64_t)kb * 2 * tp->boot_block_size + q) * n + c] = xo_t(&g, p->param_t_df);
       }
     for (int i = 0; i < T; i++) {
       if (p->has_stress) {

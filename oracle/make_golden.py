@@ -66,6 +66,10 @@ CASES = [
     dict(name="boot_3y_nan_fixed_start", variant="boot_nan", years=3, n_tapes=2, seed=120,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MEAN": 40,
               "BOOTSTRAP_MOMENTUM_BIAS_BY_REGIME": {0: 0.9, 1: 0.2}}, strategies=ALL19),
+    dict(name="boot_empty_tech_pool_1y", variant="boot_early", years=1, n_tapes=3, seed=125,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid"}, strategies=ALL19 + EXTRAS),
+    dict(name="boot_no_highvol_blocks_1y", variant="boot_calm", years=1, n_tapes=3, seed=126,
+         cfg={"SIM_ENGINE_MODE": "legacy_hybrid", "USE_RANDOM_START": False, "BOOTSTRAP_BLOCK_MEAN": 30}, strategies=ALL19),
     dict(name="boot_10y", variant="boot", years=10, n_tapes=1, seed=124,
          cfg={"SIM_ENGINE_MODE": "legacy_hybrid"}, strategies=ALL19 + EXTRAS),
     dict(name="boot_fullblocks_1y", variant="boot", years=1, n_tapes=2, seed=121,
@@ -103,7 +107,15 @@ def case_model(case):
     if v.startswith("normal_"):
         return synthetic.normal_regime_model(v.split("_", 1)[1])
     if v.startswith("boot"):
-        hist = synthetic.synthetic_history(nan_every=97) if v == "boot_nan" else synthetic.synthetic_history()
+        if v == "boot_nan":
+            hist = synthetic.synthetic_history(nan_every=97)
+        elif v == "boot_early":        # ends before the real-QQQ cutoff: pool B is empty in both regimes
+            hist = synthetic.synthetic_history(n_days=4000, seed=8, start="1980-01-02")
+        elif v == "boot_calm":         # VIX never reaches 25: no high-vol blocks in either pool
+            hist = synthetic.synthetic_history(n_days=9000, seed=10, start="1992-01-02")
+            hist["VIX"] = hist["VIX"].clip(upper=22.0)
+        else:
+            hist = synthetic.synthetic_history()
         return synthetic.legacy_bootstrap_model(hist)
     return synthetic.fallback_regime_model(v)
 
@@ -280,41 +292,50 @@ class ParamTGenerator(TapeGenerator):
 
 class BootGenerator(TapeGenerator):
     """stream B of the legacy_hybrid bootstrap (bootstrap.py:310-458, engine.py:50-80): per block a geometric
-    length, up to two momentum coins, block indices / sub-section offsets; then the (n_days, 3) noise matrix of
-    sample_returns and one standard_t(size=3) per day in generate_fat_tailed_returns."""
+    length, up to two momentum coins, block indices / sub-section offsets (or, for an empty pool, the Student-t and
+    normal draws of a synthetic block, bootstrap.py:295-298); then the (n_days, 3) noise matrix of sample_returns and
+    one standard_t(size=3) per day in generate_fat_tailed_returns."""
 
     def __init__(self, role, tape, col, regime_full, boot):
         super().__init__(role, tape, col, regime_full)
         self.boot = boot
         self.k = -1
         self.cur = 0
+        self.in_sampler = True
 
     def geometric(self, p, size=None):
         assert size is None and abs(p - 1.0 / self.boot.block_mean) < 1e-15
         self.k += 1
         v = int(self.tp.boot_len[self.k, self.c])
         ln = min(int(np.clip(v, self.boot.block_min, self.boot.block_max)), self.tp.gen_days - self.cur)
+        regime = int(np.median(self.regime_full[self.cur:self.cur + ln]))
         self.cur += ln
         off = ln < self.boot.block_size
-        self.slots = [1] + ([2] if off else []) + [4] + ([5] if off else [])
-        self.n_int = 0
+        # the calls this block will make, in order: ('syn', pool) = synthetic block of an empty pool, ('u', slot) = one
+        # integer / choice draw served from boot_u[k][slot]
+        self.expect = []
+        for q, pools, idx_slot, off_slot in ((0, self.boot.pool_a, 1, 2), (1, self.boot.pool_b, 4, 5)):
+            self.expect.append(("u", idx_slot) if pools[regime].n_blocks > 0 else ("syn", q))
+            if off:
+                self.expect.append(("u", off_slot))
+        self.pending_normals = 0
         return v
 
     def _next_u(self):
-        u = float(self.tp.boot_u[self.k, self.slots[self.n_int], self.c])
-        self.n_int += 1
-        return u
+        kind, slot = self.expect.pop(0)
+        assert kind == "u", (kind, slot)
+        return float(self.tp.boot_u[self.k, slot, self.c])
 
     def random(self, size=None, *a, **k):
-        assert size is None
-        return float(self.tp.boot_u[self.k, 0 if self.n_int == 0 else 3, self.c])
+        assert size is None and self.expect and self.expect[0] in (("u", 1), ("u", 4))   # momentum coin before a block index
+        return float(self.tp.boot_u[self.k, 0 if self.expect[0][1] == 1 else 3, self.c])
 
     def integers(self, low, high=None, *a, **k):
         u = self._next_u()
         return int(low + min(int(np.floor(u * (high - low))), high - low - 1))
 
     def choice(self, a, size=None, replace=True, p=None, **k):
-        assert size is None and p is not None and self.slots[self.n_int] == 4
+        assert size is None and p is not None and self.expect[0] == ("u", 4)
         u = self._next_u()
         cdf = np.asarray(p, dtype=float).cumsum()
         cdf /= cdf[-1]
@@ -323,10 +344,23 @@ class BootGenerator(TapeGenerator):
     def standard_t(self, df, size=None):
         if isinstance(size, tuple):                  # bootstrap.py:400
             assert size == (self.tp.gen_days, 3)
+            self.in_sampler = False
             return self.tp.boot_t[:, :, self.c].copy()
+        if self.in_sampler:                          # bootstrap.py:295 synthetic block of an empty pool
+            kind, q = self.expect.pop(0)
+            assert kind == "syn" and size == self.boot.block_size
+            self.pending_normals = 2
+            return self.tp.boot_syn[self.k, q, :, self.c].copy()
         v = self.tp.x[self.g_mvn, :, self.c].copy()  # engine.py:68
         self.g_mvn += 1
         return v
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        if self.in_sampler:                          # bootstrap.py:297-298: VIX / IRX columns of a synthetic block, never read
+            assert self.pending_normals > 0 and size == self.boot.block_size
+            self.pending_normals -= 1
+            return np.zeros(size)
+        return super().normal(loc, scale, size)
 
 
 def import_reference():

@@ -108,9 +108,9 @@ def trade_list(params: abi.Params, tape: HostTape, trial: int, strategy: int, ca
 
 
 def fill_tape(params: abi.Params, n_tapes: int, seed: int, max_spells: int = 2048) -> HostTape:
+    from letf_monte_carlo_b200.tape import boot_tape_shape
     G = params.sim_days + params.buffer_days
-    boot = params.market_mode == abi.MARKET_BOOTSTRAP
-    tp = HostTape(n_tapes, G, params.sim_days, max_spells, (G // max(params.boot.block_min, 1) + 2) if boot else 0)
+    tp = HostTape(n_tapes, G, params.sim_days, max_spells, *boot_tape_shape(params))
     ts = tp.as_struct()
     lib().letf_oracle_fill_tape(C.byref(params), seed, C.byref(ts))
     return tp

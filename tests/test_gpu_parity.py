@@ -82,18 +82,18 @@ def test_constant_window_corner(engine_lib):
 
 @pytest.mark.parametrize("variant,years,precision", [("default", 2, "f64"), ("vix_te", 1, "f64"), ("no_joint", 1, "f64"),
                                                      ("durations", 1, "f64"), ("normal_c2", 3, "f64"),
-                                                     ("boot", 2, "f64")])
+                                                     ("boot", 2, "f64"), ("boot_early", 1, "f64")])
 def test_philox_record_replays_through_oracle(variant, years, precision, engine_lib):
     """the on-device Philox path records the variates it consumed; the oracle on that tape must agree"""
     sids = ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"]
     doc = {"case": dict(variant=variant, years=years, n_tapes=40, seed=0,
-                        cfg={"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {}, strategies=sids)}
+                        cfg={"SIM_ENGINE_MODE": "legacy_hybrid"} if variant.startswith("boot") else {}, strategies=sids)}
     ns, model, params, keep, _ = case_inputs(doc)
     n_t = 40
     n = n_t * (2 if params.antithetic_pairs else 1)
     G = params.sim_days + params.buffer_days
-    rec = HostTape(n_t, G, params.sim_days, 512,
-                   (G // params.boot.block_min + 2) if params.market_mode == abi.MARKET_BOOTSTRAP else 0)
+    from letf_monte_carlo_b200.tape import boot_tape_shape
+    rec = HostTape(n_t, G, params.sim_days, 512, *boot_tape_shape(params))
     with _engine(params, keep, precision) as eng:
         out = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec, journal=True)
         plain = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX, journal=True)
@@ -479,7 +479,8 @@ def test_bootstrap_lean_kernel_vs_generic_and_oracle(engine_lib):
     n_t = 128
     n = 2 * n_t if params.antithetic_pairs else n_t
     G = params.sim_days + params.buffer_days
-    rec = HostTape(n_t, G, params.sim_days, 512, G // params.boot.block_min + 2)
+    from letf_monte_carlo_b200.tape import boot_tape_shape
+    rec = HostTape(n_t, G, params.sim_days, 512, *boot_tape_shape(params))
     with _engine(params, keep, "f32") as eng:
         lean = eng.run_host(n, seed=2718)
         regs_lean = eng.launch_info()["regs_per_thread"]

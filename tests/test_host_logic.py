@@ -99,8 +99,11 @@ def test_bootstrap_pools_and_dispatch():
         build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid", BOOTSTRAP_BLOCK_MAX=200))
     early = synthetic.synthetic_history(n_days=2000, seed=3, start="1980-01-02")                 # no real-QQQ rows: pool B empty
     model["bootstrap_sampler"] = create_bootstrap_sampler(early)
-    with pytest.raises(UnsupportedConfig):
-        build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid"))
+    p, keep = build_params(["S1"], 1, model, synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid"))
+    assert p.boot.pool_b[0].n_blocks == 0 and p.boot.pool_b[1].n_blocks == 0 and p.boot.pool_a[0].n_blocks > 0
+    from letf_monte_carlo_b200.tape import boot_tape_shape, make_tape
+    assert boot_tape_shape(p) == ((252 + 1260) // 21 + 2, 168)          # synthetic-block variates ride on the tape
+    assert make_tape(p, 2, 1).boot_syn.shape == (74, 2, 168, 2)
 
 
 def test_shard_range_partitions_trials():

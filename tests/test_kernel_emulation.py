@@ -59,24 +59,26 @@ def test_f32_kernel_body_close_to_reference(name):
 
 
 def _blank_tape(params, n_tapes, max_spells):
+    from letf_monte_carlo_b200.tape import boot_tape_shape
     G = params.sim_days + params.buffer_days
-    boot = params.market_mode == abi.MARKET_BOOTSTRAP
-    return HostTape(n_tapes, G, params.sim_days, max_spells, (G // max(params.boot.block_min, 1) + 2) if boot else 0)
+    return HostTape(n_tapes, G, params.sim_days, max_spells, *boot_tape_shape(params))
 
 
 @pytest.mark.parametrize("variant,years", [("default", 1), ("vix_te", 1), ("no_joint", 1), ("normal_c2", 2), ("boot", 1),
-                                           ("regime_only", 1)])
+                                           ("regime_only", 1), ("boot_early", 1), ("boot_calm", 1)])
 def test_philox_record_replays_through_oracle(variant, years):
     """RNG_PHILOX_RECORD writes every variate it consumes; feeding that tape to the oracle must give
     the same results -> the Philox path consumes draws exactly where the tape semantics say."""
-    cfg_over = {"SIM_ENGINE_MODE": "legacy_hybrid"} if variant == "boot" else {}
+    cfg_over = {"SIM_ENGINE_MODE": "legacy_hybrid"} if variant.startswith("boot") else {}
     if variant == "regime_only":      # random_start.py:169-172: the start regime is drawn, no buffer / offset
         variant, cfg_over = "default", {"RANDOM_START_METHOD": "regime_only", "START_REGIME_PROBABILITIES": {0: 0.5, 1: 0.5}}
     case = dict(variant=variant, years=years, n_tapes=3, seed=0, cfg=cfg_over,
                 strategies=ALL19 if variant != "normal_c2" else ["S1", "S3", "B_UPRO", "S4", "S6", "S19"])
     doc = {"case": case}
     ns, model, params, keep, _ = case_inputs(doc)
-    assert (params.market_mode == abi.MARKET_BOOTSTRAP) == (variant == "boot")
+    assert (params.market_mode == abi.MARKET_BOOTSTRAP) == variant.startswith("boot")
+    if variant in ("boot_early", "boot_calm"):       # some pool is empty: synthetic Student-t blocks (bootstrap.py:214-222)
+        assert min(pl[r].n_blocks for pl in (params.boot.pool_a, params.boot.pool_b) for r in range(2)) == 0
     G = params.sim_days + params.buffer_days
     n_rec = 12 if params.start_regime_prob1 > 0 else 3
     rec = _blank_tape(params, n_rec, 256)
