@@ -54,6 +54,9 @@ for w, n in TRIALS.items():
                  "source": f"profiles/r1_{w}_{tag}_ncu_full_summary.csv ({n} trials)"}
     print(w, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % consts[w]["executed_warp_instr_per_path_day"],
           "issue %.1f%%" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0), "DRAM GB %.2f" % (dram / 1e9))
-json.dump(consts, open(os.path.join(prof, "ncu_constants.json"), "w"), indent=1)
+cpath = os.path.join(prof, "ncu_constants.json")
+merged = json.load(open(cpath)) if os.path.exists(cpath) else {}
+merged.update(consts)             # workloads not in this pass keep their constants
+json.dump(merged, open(cpath, "w"), indent=1)
 for r in rows:
     print(r)
