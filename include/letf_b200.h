@@ -351,6 +351,11 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
                           int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price,
                           int32_t* count);
 
+/* Daily equity curve of ONE trial / ONE strategy - the Series run_strategy_fixed returns (strategy.py:55-1277; its last
+ * element is Final_Wealth, engine.py:578): the trial is re-simulated with the curve log on.  curve: host double[T]. */
+int letf_equity_curve_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode,
+                           const LetfTape* host_tape, double* curve);
+
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info);
 
 /* Strategy rules on caller-supplied return series (materialised-path mode):
@@ -367,6 +372,14 @@ typedef struct LetfSeries {
 } LetfSeries;
 int letf_run_strategies(LetfEngine* e, void* stream, const LetfSeries* series,
                         const LetfOutputs* out);
+
+/* run_strategy_fixed(df, sid, regime_path, corr, apply_costs, trade_journal) on ONE caller-supplied frame: `host_series`
+ * holds HOST pointers to [T] columns (n_paths must be 1).  Returns the equity curve (host double[T]), the trade count and,
+ * for a taxable id, the journal entries (buffers of capacity cap as in letf_trade_list_host; may be NULL with cap 0). */
+int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* host_series, int strategy, double* curve,
+                                 int32_t* num_trades, int cap, int32_t* day, int32_t* asset, int32_t* action,
+                                 double* shares, double* price, int32_t* count);
+
 
 /* helper for non-Python callers: utils.py:42-53 on a 3x3 matrix */
 int letf_nearest_psd3(const double in[9], double out[9]);

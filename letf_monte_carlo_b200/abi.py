@@ -182,7 +182,7 @@ class Series(C.Structure):
 ENGINE_SYMBOLS = (
     "letf_create", "letf_destroy", "letf_last_error", "letf_abi_version", "letf_run",
     "letf_run_host", "letf_summary_reset", "letf_reduce", "letf_trade_list_host", "letf_trade_lists_host",
-    "letf_launch_info",
+    "letf_equity_curve_host", "letf_run_strategy_curve_host", "letf_launch_info",
     "letf_run_strategies", "letf_nearest_psd3",
 )
 
@@ -228,6 +228,11 @@ def load_engine_library(path: str | None = None):
     lib.letf_trade_list_host.restype = i32
     lib.letf_trade_lists_host.argtypes = [vp, u64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.letf_trade_lists_host.restype = i32
+    lib.letf_equity_curve_host.argtypes = [vp, u64, i64, i32, i32, C.POINTER(Tape), vp]
+    lib.letf_equity_curve_host.restype = i32
+    lib.letf_run_strategy_curve_host.argtypes = [vp, C.POINTER(Series), i32, vp, C.POINTER(C.c_int32), i32, vp, vp, vp, vp, vp,
+                                                 C.POINTER(C.c_int32)]
+    lib.letf_run_strategy_curve_host.restype = i32
     lib.letf_launch_info.argtypes = [vp, C.POINTER(LaunchInfo)]
     lib.letf_launch_info.restype = i32
     lib.letf_run_strategies.argtypes = [vp, vp, C.POINTER(Series), C.POINTER(Outputs)]

@@ -121,6 +121,7 @@ struct LogArgs {
   int64_t trial = -1; int strategy = -1; int cap = 0;
   int32_t* count = nullptr; int32_t* day = nullptr; int32_t* asset = nullptr; int32_t* action = nullptr;
   double* shares = nullptr; double* price = nullptr;
+  double* curve = nullptr;                  // device [T]: equity curve of (trial, strategy)
 };
 
 static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask,
@@ -194,7 +195,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   ka.trial_ids = lg.trial_ids;
   ka.log_trial = lg.trial; ka.log_strategy = lg.strategy; ka.log_cap = lg.cap;
   ka.log_count = lg.count; ka.log_day = lg.day; ka.log_asset = lg.asset; ka.log_action = lg.action;
-  ka.log_shares = lg.shares; ka.log_price = lg.price;
+  ka.log_shares = lg.shares; ka.log_price = lg.price; ka.log_curve = lg.curve;
 
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
@@ -244,7 +245,8 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
   if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
   // (a caller-supplied frame needs no tape plumbing; only the journal does)
-  const bool need_io = (market != kMarketSeries && rng_mode != LETF_RNG_PHILOX) || want_journal || lg.count != nullptr;
+  const bool need_io = (market != kMarketSeries && rng_mode != LETF_RNG_PHILOX) || want_journal || lg.count != nullptr ||
+                       lg.curve != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);
@@ -660,6 +662,105 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
     CK(cudaMemcpy(price, lg.price, 8 * c * m, cudaMemcpyDeviceToHost));
   }
   return LETF_OK;
+}
+
+// one path replayed with the journal log and / or the equity-curve log on; `series` (device pointers) selects the
+// caller-supplied-frame mode.  Shared by letf_equity_curve_host and letf_run_strategy_curve_host.
+static int replay_one(LetfEngine* e, int market, uint64_t seed, int64_t trial, int strategy, int rng_mode, const LetfTape* dtape,
+                      const LetfSeries* dseries, int T, double* curve, int32_t* num_trades, int cap, int32_t* day, int32_t* asset,
+                      int32_t* action, double* shares, double* price, int32_t* count) {
+  const int S = e->params.n_strategies;
+  const size_t c = (size_t)(cap > 0 ? cap : 1), t = (size_t)(T > 0 ? T : 1);
+  const size_t o_cnt = 0, o_day = 256, o_asset = o_day + align256(4 * c), o_act = o_asset + align256(4 * c),
+               o_sh = o_act + align256(4 * c), o_pr = o_sh + align256(8 * c), o_cv = o_pr + align256(8 * c),
+               o_out = o_cv + align256(8 * t), total = o_out + align256(8 * S) * 2 + align256(4 * S) + 256;
+  cudaError_t ce = e->stage_log.reserve(total);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "log staging"); }
+  char* base = (char*)e->stage_log.p;
+  CK(cudaMemset(base, 0, 256));
+  CK(cudaMemset(base + o_cv, 0, 8 * t));
+  LogArgs lg;
+  lg.trial = trial; lg.strategy = strategy; lg.cap = cap;
+  const bool want_log = count != nullptr && e->params.strategies[strategy].taxable;
+  if (want_log) {
+    lg.count = (int32_t*)(base + o_cnt); lg.day = (int32_t*)(base + o_day); lg.asset = (int32_t*)(base + o_asset);
+    lg.action = (int32_t*)(base + o_act); lg.shares = (double*)(base + o_sh); lg.price = (double*)(base + o_pr);
+  }
+  if (curve) lg.curve = (double*)(base + o_cv);
+  LetfOutputs dout; memset(&dout, 0, sizeof(dout));
+  dout.n_trials = 1;
+  dout.final_wealth = (double*)(base + o_out); dout.max_dd = (double*)(base + o_out + align256(8 * S));
+  dout.num_trades = (int32_t*)(base + o_out + 2 * align256(8 * S));
+  dout.flags = (uint32_t*)(base + o_out + 2 * align256(8 * S) + align256(4 * S));
+  int rc = launch_any(e, market, (cudaStream_t)0, seed, trial, 1, rng_mode, dtape, &dout, dseries, lg);
+  if (rc) return rc;
+  if (curve && T > 0) CK(cudaMemcpy(curve, base + o_cv, 8 * (size_t)T, cudaMemcpyDeviceToHost));
+  if (num_trades) CK(cudaMemcpy(num_trades, dout.num_trades + strategy, 4, cudaMemcpyDeviceToHost));
+  if (count) *count = 0;
+  if (want_log) {
+    int32_t nlog = 0;
+    CK(cudaMemcpy(&nlog, lg.count, 4, cudaMemcpyDeviceToHost));
+    *count = nlog;
+    const size_t m = (size_t)(nlog < cap ? nlog : cap);
+    if (m) {
+      CK(cudaMemcpy(day, lg.day, 4 * m, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(asset, lg.asset, 4 * m, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(action, lg.action, 4 * m, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(shares, lg.shares, 8 * m, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(price, lg.price, 8 * m, cudaMemcpyDeviceToHost));
+    }
+  }
+  return LETF_OK;
+}
+
+int letf_equity_curve_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode, const LetfTape* host_tape,
+                           double* curve) {
+  if (!e || !curve) return fail(LETF_ERR_INVALID, "null argument");
+  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  if (rng_mode == LETF_RNG_PHILOX_RECORD) return fail(LETF_ERR_INVALID, "equity curve replay does not record");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  LetfTape dtape; const LetfTape* tp = nullptr;
+  if (rng_mode == LETF_RNG_TAPE) {
+    if (!host_tape) return fail(LETF_ERR_INVALID, "rng_mode needs a tape");
+    int rc = stage_tape(e, host_tape, true, &dtape);
+    if (rc) return rc;
+    tp = &dtape;
+  }
+  return replay_one(e, e->params.market_mode, seed, trial, strategy, rng_mode, tp, nullptr, e->params.sim_days, curve, nullptr, 0,
+                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* hs, int strategy, double* curve, int32_t* num_trades, int cap,
+                                 int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count) {
+  if (!e || !hs || !curve) return fail(LETF_ERR_INVALID, "null argument");
+  if (hs->n_paths != 1 || hs->sim_days < 0) return fail(LETF_ERR_INVALID, "host frame: n_paths must be 1");
+  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  if (!hs->asset_ret[4]) return fail(LETF_ERR_INVALID, "series needs SPY_Ret (signals read SPY_Price)");
+  if (cap < 0 || (cap > 0 && (!day || !asset || !action || !shares || !price || !count))) return fail(LETF_ERR_INVALID, "bad log buffers");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  // upload the frame's columns into the tape staging buffer (unused in this mode)
+  const size_t T = (size_t)hs->sim_days, col8 = align256(8 * (T ? T : 1)), col4 = align256(4 * (T ? T : 1));
+  cudaError_t ce = e->stage_tape.reserve(col8 * (LETF_N_ASSETS + 2) + col4);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "series staging"); }
+  char* base = (char*)e->stage_tape.p;
+  LetfSeries ds; memset(&ds, 0, sizeof(ds));
+  ds.n_paths = 1; ds.sim_days = hs->sim_days;
+  size_t o = 0;
+  auto up = [&](const void* src, size_t bytes, size_t stride) -> const void* {
+    if (!src) return nullptr;
+    void* dst = base + o; o += stride;
+    if (bytes) cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return dst;
+  };
+  for (int a = 0; a < LETF_N_ASSETS; a++) ds.asset_ret[a] = (const double*)up(hs->asset_ret[a], 8 * T, col8);
+  ds.tlt_ret = (const double*)up(hs->tlt_ret, 8 * T, col8);
+  ds.vix = (const double*)up(hs->vix, 8 * T, col8);
+  ds.regime = (const int32_t*)up(hs->regime, 4 * T, col4);
+  CK(cudaGetLastError());
+  return replay_one(e, kMarketSeries, 0, 0, strategy, LETF_RNG_PHILOX, nullptr, &ds, hs->sim_days, curve, num_trades, cap, day, asset,
+                    action, shares, price, count);
 }
 
 int letf_nearest_psd3(const double in[9], double out[9]) {

@@ -43,6 +43,7 @@ template <typename R, int NS, int NA> struct KArgs {
   const int64_t* trial_ids;
   int64_t log_trial; int log_strategy; int log_cap;
   int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
+  double* log_curve;        // [T] daily equity of (log_trial, log_strategy): the Series run_strategy_fixed returns
 };
 
 LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -1277,6 +1278,18 @@ struct Trial {
 #pragma unroll(NS <= 8 ? NS : 1)
           for (int s = 0; s < NS; s++) slot_body(s, std::integral_constant<int, -1>{}, std::integral_constant<int, -1>{});
         }
+      }
+      if (TAPEIO && ka.log_curve && !ka.trial_ids && ka.log_trial == k && ka.log_strategy >= 0 && ka.log_strategy < p.n_strat) {
+        // equity curve of one strategy (tape-capable builds only: their slot loop is rolled, slot[] lives in local memory)
+        const int s = ka.log_strategy, ty = p.strat[s].type;
+        double w = slot[s].W;
+        if (ty == LETF_ST_BENCHMARK_TLT) w = (double)p.W0 * cp_tlt;
+        else if (ty == LETF_ST_BENCHMARK) {
+          w = (double)p.W0;
+#pragma unroll
+          for (int a = 0; a < NA; a++) if (p.act_id[a] == p.strat[s].asset) w = (double)p.W0 * cp[a];
+        }
+        ka.log_curve[i] = w;
       }
     }
 

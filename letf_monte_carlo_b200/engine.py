@@ -262,6 +262,48 @@ class PathEngine:
             cap = int(cnt.max())
         return [_trade_dicts(day[j], asset[j], action[j], shares[j], price[j], int(cnt[j])) for j in range(n)]
 
+    def equity_curve(self, trial: int, strategy: int, *, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
+                     tape: HostTape | None = None) -> np.ndarray:
+        """daily equity of one trial / one strategy (the Series `run_strategy_fixed` returns), by replaying the trial"""
+        curve = np.zeros(max(int(self.params.sim_days), 1))
+        ts = tape.as_struct() if tape is not None else None
+        rc = self._lib.letf_equity_curve_host(self._h, seed, trial, strategy, rng_mode,
+                                              C.byref(ts) if ts is not None else None, curve.ctypes.data)
+        self._check(rc)
+        self.launches += 1
+        return curve[:int(self.params.sim_days)]
+
+    def run_strategy_curve(self, frame: dict, strategy: int, *, tlt_ret=None, vix=None, regime=None, cap: int = 4096):
+        """`run_strategy_fixed` on ONE caller-supplied frame (strategy.py:55): frame = {asset name: [T] returns}.
+        -> (equity curve [T], num_trades, Trade_List rows for a taxable id)"""
+        cols = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in frame.items()}
+        T = len(next(iter(cols.values())))
+        s = abi.Series()
+        s.n_paths, s.sim_days = 1, T
+        for name, a in cols.items():
+            assert a.shape == (T,)
+            s.asset_ret[abi.ASSET_INDEX[name]] = a.ctypes.data
+        tl = None if tlt_ret is None else np.ascontiguousarray(np.asarray(tlt_ret, dtype=np.float64))
+        vx = None if vix is None else np.ascontiguousarray(np.asarray(vix, dtype=np.float64))
+        rg = None if regime is None else np.ascontiguousarray(np.asarray(regime, dtype=np.int32))
+        s.tlt_ret = tl.ctypes.data if tl is not None else None
+        s.vix = vx.ctypes.data if vx is not None else None
+        s.regime = rg.ctypes.data if rg is not None else None
+        curve = np.zeros(max(T, 1))
+        nt, cnt = C.c_int32(0), C.c_int32(0)
+        while True:
+            day, asset, action = (np.zeros(cap, np.int32) for _ in range(3))
+            shares, price = np.zeros(cap), np.zeros(cap)
+            rc = self._lib.letf_run_strategy_curve_host(self._h, C.byref(s), strategy, curve.ctypes.data, C.byref(nt), cap,
+                                                        day.ctypes.data, asset.ctypes.data, action.ctypes.data,
+                                                        shares.ctypes.data, price.ctypes.data, C.byref(cnt))
+            self._check(rc)
+            self.launches += 1
+            if cnt.value <= cap:
+                break
+            cap = cnt.value
+        return curve[:T], int(nt.value), _trade_dicts(day, asset, action, shares, price, cnt.value)
+
     def launch_info(self) -> dict:
         li = abi.LaunchInfo()
         self._check(self._lib.letf_launch_info(self._h, C.byref(li)))

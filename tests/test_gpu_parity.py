@@ -604,3 +604,52 @@ def test_public_api_bootstrap_via_historical_df(engine_lib):
     inst = parallel_monte_carlo_fixed(sids, 2, synthetic.fallback_regime_model(), {}, hist,
                                       cfg=synthetic.config_namespace(NUM_SIMULATIONS=300), verbose=False, device=0)
     assert inst.engine.params.market_mode == abi.MARKET_JOINT_T      # institutional_v1 + joint model wins (engine.py:45)
+
+
+def test_run_strategy_fixed_dropin_matches_live_reference(engine_lib):
+    """letf_monte_carlo_b200.run_strategy_fixed against the LIVE reference's run_strategy_fixed (strategy.py:55) on one
+    seeded frame (tests/golden/run_strategy_fixed_700d.npz): daily equity curve, trade count, journal entries."""
+    import os
+    from letf_monte_carlo_b200 import TradeJournal, run_strategy_fixed
+    from letf_monte_carlo_b200.trade import TAXABLE_IDS
+    from oracle.make_strategy_golden import strategy_frame
+    from tests.common import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "run_strategy_fixed_700d.npz"))
+    df, regime = strategy_frame(int(g["T"]), int(g["seed"]))
+    for sid in [str(x) for x in g["sids"]]:
+        j = TradeJournal() if sid in TAXABLE_IDS else None
+        ec, nt = run_strategy_fixed(df, sid, regime, {}, apply_costs=True, trade_journal=j, device=0)
+        ref = g[f"{sid}_curve"]
+        assert len(ec) == len(ref) and list(ec.index) == list(df.index)
+        np.testing.assert_allclose(ec.values, ref, rtol=1e-11, err_msg=sid)
+        assert nt == int(g[f"{sid}_trades"]), sid
+        if j is not None:
+            tl = j.get_full_trades()
+            assert len(tl) == int(g[f"{sid}_journal_n"]), sid
+            np.testing.assert_array_equal([t["day_index"] for t in tl], g[f"{sid}_journal_days"])
+            assert abs(sum(t["dollar_amount"] for t in tl) - float(g[f"{sid}_journal_volume"])) <= 1e-9 * max(1.0, float(g[f"{sid}_journal_volume"]))
+
+
+def test_simulate_single_path_fixed_dropin_and_equity_curve(engine_lib):
+    """the single-trial seam (engine.py:423) returns the bulk launch's numbers for that trial, with the reference's keys;
+    the replayed equity curve ends at Final_Wealth and reproduces Max_DD (engine.py:578-586)."""
+    from letf_monte_carlo_b200 import parallel_monte_carlo_fixed, simulate_single_path_fixed
+    from letf_monte_carlo_b200.mc_runner import _engine_for
+    ns = synthetic.config_namespace(NUM_SIMULATIONS=64, GPU_PRECISION="f64")
+    sids = ["S1", "S2", "S4", "S8", "S19"]
+    model = synthetic.fallback_regime_model()
+    bulk = parallel_monte_carlo_fixed(sids, 1, model, {}, cfg=ns, verbose=False, device=0)
+    for sim_id, anti in ((6, False), (6, True), (20, True)):
+        one = simulate_single_path_fixed((sim_id, 1, model, {}, sids, anti), cfg=ns, device=0)
+        k = sim_id | (1 if anti else 0)
+        for sid in sids:
+            r = one[sid]
+            assert r["Final_Wealth"] == bulk[sid][k]["Final_Wealth"] and r["Num_Trades"] == bulk[sid][k]["Num_Trades"]
+            assert r["Max_DD"] == bulk[sid][k]["Max_DD"] and r["Metadata"]["regime_counts"] == bulk[sid][k]["Metadata"]["regime_counts"]
+            assert ("Trade_List" in r) == (sid in ("S8", "S19"))
+    eng = bulk.engine
+    for s, sid in enumerate(sids):
+        ec = eng.equity_curve(7, s, seed=bulk.seed)
+        assert len(ec) == 252 and ec[-1] == pytest.approx(bulk[sid][7]["Final_Wealth"], rel=1e-13)
+        rm = np.maximum.accumulate(ec)
+        assert abs(((ec - rm) / np.where(rm > 0, rm, 1.0)).min()) == pytest.approx(bulk[sid][7]["Max_DD"], abs=1e-12)
