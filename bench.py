@@ -97,6 +97,10 @@ def build_workload(name):
         model = synthetic.fallback_regime_model("default")
     else:
         raise KeyError(name)
+    nu = os.environ.get("LETF_BENCH_JOINT_NU")        # e.g. "5.3,4.2": calibrated models have non-integer dof (calibration.py:399)
+    if nu and model.get("joint_return_model"):
+        for r, v in enumerate(nu.split(",")):
+            model["joint_return_model"]["regimes"][r]["nu"] = float(v)
     params, keep = build_params(sids, WORKLOADS[name]["years"], model, ns)
     return ns, model, sids, params, keep
 

@@ -261,8 +261,39 @@ LETF_HD R chi2_int_fast(int k, uint32_t wa, uint32_t wb, R nrm) {
 // memory: with a reference to its `key` member the object escapes and, in the large typed / generic builds, every
 // parameter read of the day loop degrades from a constant-bank load to a generic load through the saved reference.
 // By reference costs the lean 128-register builds nothing extra (their key then lives on the stack).
+// one Marsaglia-Tsang attempt: squeeze test, then the log test
 template <typename R>
-LETF_HD R chi2_mt_body(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
+LETF_HD bool mt_accept(R d, R c, R x, uint32_t uw, R& out) {
+  typedef Mth<R> M;
+  R v = (R)1 + c * x;
+  if (v > (R)0) {
+    v = v * v * v;
+    R u = M::u01(uw);
+    R x2 = x * x;
+    if (u < (R)1 - (R)0.0331 * x2 * x2 || M::log_(u) < (R)0.5 * x2 + d * ((R)1 - v + M::log_(v))) { out = (R)2 * d * v; return true; }
+  }
+  return false;
+}
+// the retries (acceptance > 95 % per attempt, so ~4 % of the calls get here): blocks (stream, sub = 1, 2, ...)
+template <typename R>
+LETF_HD R chi2_mt_retry_body(R d, R c, const RngKey& key, uint32_t day, uint32_t stream) {
+  typedef Mth<R> M;
+  for (uint32_t sub = 1; sub < 64; sub++) {
+    U4 b = rng_block(key, day, stream, sub);
+    R x, dump, out;
+    M::box_muller(b.x, b.y, x, dump);
+    if (mt_accept<R>(d, c, x, b.z, out)) return out;
+  }
+  return (R)2 * d;  // unreachable in practice
+}
+template <typename R>
+LETF_HDN R chi2_mt_retry_byval(R d, R c, const RngKey key, uint32_t day, uint32_t stream) {
+  return chi2_mt_retry_body<R>(d, c, key, day, stream);
+}
+// the lean 128-register builds keep the whole sampler out of line, first attempt included (one loop, as compact as it gets:
+// inlining the first attempt, or even restructuring this function, costs them hundreds of bytes of spills)
+template <typename R>
+LETF_HDN R chi2_mt_full_byref(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
   typedef Mth<R> M;
   R a = (R)0.5 * nu;
   R d = a - (R)(1.0 / 3.0);
@@ -285,17 +316,17 @@ LETF_HD R chi2_mt_body(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day
   }
   return (R)2 * d;  // unreachable in practice (acceptance > 95 % per attempt)
 }
-template <typename R>
-LETF_HDN R chi2_mt_byval(R nu, R n0, uint32_t u0w, const RngKey key, uint32_t day, uint32_t stream) {
-  return chi2_mt_body<R>(nu, n0, u0w, key, day, stream);
-}
-template <typename R>
-LETF_HDN R chi2_mt_byref(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
-  return chi2_mt_body<R>(nu, n0, u0w, key, day, stream);
-}
+// the 6-asset builds run the first attempt inline (calibrated joint models have non-integer dof, calibration.py:399: this
+// runs every generated day) and only a rejection pays for the call
 template <typename R, bool KEYREF = false>
 LETF_HD R chi2_marsaglia_tsang(R nu, R n0, uint32_t u0w, const RngKey& key, uint32_t day, uint32_t stream) {
-  return KEYREF ? chi2_mt_byref<R>(nu, n0, u0w, key, day, stream) : chi2_mt_byval<R>(nu, n0, u0w, key, day, stream);
+  typedef Mth<R> M;
+  if (KEYREF) return chi2_mt_full_byref<R>(nu, n0, u0w, key, day, stream);
+  const R d = (R)0.5 * nu - (R)(1.0 / 3.0);
+  const R c = M::rsqrt_((R)9 * d);
+  R out;
+  if (mt_accept<R>(d, c, n0, u0w, out)) return out;
+  return chi2_mt_retry_byval<R>(d, c, key, day, stream);
 }
 
 struct DfInfo {      // host-precomputed per distribution
