@@ -75,11 +75,11 @@ def build_workload(name):
     elif name == "c3":
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
         sids = ["S2", "B_QQQ", "B_TLT"]
-        model = synthetic.fallback_regime_model("default")
+        model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     elif name == "c4":
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
         sids = ["S1", "S2", "S4", "S5", "S6", "S19"]
-        model = synthetic.fallback_regime_model("default")
+        model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     elif name == "c5":
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
                                         USE_ANTITHETIC_VARIATES=False)
@@ -94,7 +94,7 @@ def build_workload(name):
     elif name == "sweep19":
         ns = synthetic.config_namespace()
         sids = ["S%d" % i for i in range(1, 20)]
-        model = synthetic.fallback_regime_model("default")
+        model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     else:
         raise KeyError(name)
     nu = os.environ.get("LETF_BENCH_JOINT_NU")        # e.g. "5.3,4.2": calibrated models have non-integer dof (calibration.py:399)

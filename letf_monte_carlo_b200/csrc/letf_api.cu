@@ -133,9 +133,10 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (need_io && !k->tapeio) continue;
     if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
     if (k->am) {        // compile-time asset mask: same series, default tracking-error dof (config.py:62-135)
-      bool ok = k->am == e->params.asset_mask;
-      for (int a = 0; ok && a < kAssets; a++)
-        if ((k->am >> a) & 1) ok = df_fast_k(e->params.assets[a].te_df) == (a >= 4 ? 10 : 5);
+      bool ok = (k->am & 0x3F) == e->params.asset_mask;
+      if (!(k->am & 0x40))          // bit 6: tracking-error dof read at run time (calibrated tracking_residual_model)
+        for (int a = 0; ok && a < kAssets; a++)
+          if ((k->am >> a) & 1) ok = df_fast_k(e->params.assets[a].te_df) == (a >= 4 ? 10 : 5);
       if (!ok) continue;
     }
     if (k->list) {      // typed slots: the strategy list must be exactly the one compiled in
@@ -154,8 +155,9 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (!best) { best = k; continue; }
     // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
     // typed-slot builds first, then fewer slots / series / rules, no tape plumbing
-    int a = (k->list ? 0 : 100000) + k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio;
-    int b = (best->list ? 0 : 100000) + best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio;
+    int a = (k->list ? 0 : 100000) + k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio + ((k->am & 0x40) ? 1 : 0);
+    int b = (best->list ? 0 : 100000) + best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio +
+            ((best->am & 0x40) ? 1 : 0);
     if (a < b) best = k;
   }
   return best;

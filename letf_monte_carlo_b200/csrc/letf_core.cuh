@@ -951,7 +951,8 @@ struct Trial {
               U4 b = rng_block(key, (uint32_t)g, STREAM_TE0 + aid);
               // builds with a compile-time asset mask also fix the tracking-error dof at cfg.ASSETS' defaults
               // (t(5) for the four LETFs, t(10) for SPY / QQQ; letf_api.cu checks it): no sampler dispatch
-              if (AM != 0 && NA == kAssets && !EXACT) innov = a >= 4 ? student_t10<R>(b) : student_t5<R>(b);
+              // (bit 6 of AM = "tracking-error dof at run time": the typed builds for calibrated residual models)
+              if (AM != 0 && !(AM & 0x40) && NA == kAssets && !EXACT) innov = a >= 4 ? student_t10<R>(b) : student_t5<R>(b);
               else innov = student_t_block<R, KEYREF>(b, ap.te_df, ap.te_fast_k, key, (uint32_t)g, STREAM_TE0 + aid);
               if (rec) tp_put(ka.tape.te_t, (int64_t)aid * T + i, innov);
             }

@@ -380,13 +380,15 @@ def test_philox_distribution_matches_live_reference(precision, engine_lib):
     assert_same_distribution(ref, out, sids)
 
 
+@pytest.mark.parametrize("variant", ["default", "vix_te"], ids=["default_te", "calibrated_te"])
 @pytest.mark.parametrize("sids", [["S1", "S2", "S4", "S5", "S6", "S19"], ALL19], ids=["c4_list", "sweep19_list"])
-def test_typed_slot_kernels_vs_generic_and_oracle(sids, engine_lib):
+def test_typed_slot_kernels_vs_generic_and_oracle(sids, variant, engine_lib):
     """The typed-slot builds (one compile-time rule per slot; BASELINE config 4 and the reference's default
     19-strategy sweep) against the generic fp32 build recording the same Philox counters, and the oracle
-    replaying that tape."""
+    replaying that tape.  `vix_te`: an explicit tracking_residual_model (non-integer dof, tanh cap) - served by the
+    typed builds that read the tracking-error dof at run time, not by the generic 32-slot build."""
     ns = synthetic.config_namespace()
-    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model(variant), ns)
     n_t = 128
     rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
     with _engine(params, keep, "f32") as eng:
@@ -403,7 +405,7 @@ def test_typed_slot_kernels_vs_generic_and_oracle(sids, engine_lib):
     rel = np.abs(typed.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
     assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97, (np.median(rel), np.mean(rel < 1e-2))
     assert np.mean(typed.num_trades != o.num_trades) < 0.03
-    assert regs_typed > 0
+    assert regs_typed > 0 and regs_typed != 227        # 227 = the generic f32_joint_t_all build: a typed build ran
 
 
 def test_edge_sizes_and_offsets(engine_lib):
