@@ -12,7 +12,11 @@ from oracle.oracle import HostOutputs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
-LIB = os.path.join(_BUILD, "libletf_emu.so")
+# LETF_EMU_SANITIZE=1 builds the emulation with AddressSanitizer + UBSan (run pytest under
+# LD_PRELOAD=$(gcc -print-file-name=libasan.so)): out-of-bounds indexing of the kernel source's scratch / ring / history /
+# tape accesses then aborts the test run - the CPU stand-in for compute-sanitizer
+_SAN = os.environ.get("LETF_EMU_SANITIZE") == "1"
+LIB = os.path.join(_BUILD, "libletf_emu_asan.so" if _SAN else "libletf_emu.so")
 _lib = None
 
 
@@ -23,7 +27,8 @@ def build(force=False):
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     deps.append(os.path.join(_HERE, "..", "..", "include", "letf_b200.h"))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", LIB, src],
+        san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if _SAN else []
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] + san + ["-o", LIB, src],
                        check=True)
     return LIB
 
