@@ -133,4 +133,42 @@ extern "C" int letf_emu_run_typed(const LetfParams* sp, int list, const LetfOutp
   return -4;
 }
 
+// materialised-path mode (run_strategy_fixed seam): caller-supplied series, optional journal + equity-curve log of one
+// (path, strategy), optional batch replay ids.  typed = 1 runs the typed 19-rule fp32 series build.
+template <typename R, int NS, bool TAPEIO, uint32_t TM, int LIST>
+static int run_series_t(const LetfParams* sp, const LetfSeries* series, const LetfOutputs* out, int64_t log_trial, int log_strategy,
+                        int log_cap, int32_t* log_count, int32_t* log_day, int32_t* log_asset, int32_t* log_action,
+                        double* log_shares, double* log_price, double* log_curve) {
+  constexpr int NA = kAssets;
+  static KArgs<R, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  const int32_t* dd[2] = {nullptr, nullptr};
+  convert_params<R, NS, NA>(*sp, dd, ka.p);
+  ka.series = *series; ka.p.T = series->sim_days; ka.p.buffer = 0; ka.p.random_start = 0;
+  ka.out = *out; ka.n_trials = series->n_paths; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
+  std::vector<R> rp(kRingP), rs(kRingS), ra(kRingA);
+  ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
+  ka.log_trial = log_trial; ka.log_strategy = log_strategy; ka.log_cap = log_cap;
+  ka.log_count = log_count; ka.log_day = log_day; ka.log_asset = log_asset; ka.log_action = log_action;
+  ka.log_shares = log_shares; ka.log_price = log_price; ka.log_curve = log_curve;
+  for (int64_t j = 0; j < series->n_paths; j++) {
+    Trial<R, NS, NA, 3, TAPEIO, TM, LIST, 0> t(ka, j, j, 0);
+    t.run();
+  }
+  return 0;
+}
+extern "C" int letf_emu_run_series(const LetfParams* sp, int precision, int typed, const LetfSeries* series, const LetfOutputs* out,
+                                   int64_t log_trial, int log_strategy, int log_cap, int32_t* log_count, int32_t* log_day,
+                                   int32_t* log_asset, int32_t* log_action, double* log_shares, double* log_price, double* log_curve) {
+  if (validate_params(*sp)) return -1;
+#define GO(R, NS, IO, TMASK, LST) return run_series_t<R, NS, IO, TMASK, LST>(sp, series, out, log_trial, log_strategy, log_cap, log_count, log_day, log_asset, log_action, log_shares, log_price, log_curve)
+  if (typed) {
+    if (precision != LETF_PREC_F32 || sp->n_strategies != slot_list_count(2)) return -2;
+    GO(float, 32, false, slot_list_mask(2), 2);
+  }
+  if (precision == LETF_PREC_F64) GO(double, LETF_MAX_STRATEGIES, true, 0xFFFFFFFFu, 0);
+  GO(float, LETF_MAX_STRATEGIES, true, 0xFFFFFFFFu, 0);
+#undef GO
+}
+
 extern "C" const char* letf_emu_validate(const LetfParams* sp) { return validate_params(*sp); }

@@ -47,6 +47,9 @@ def lib():
         L.letf_emu_run_lean.restype = C.c_int
         L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_typed.restype = C.c_int
+        L.letf_emu_run_series.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, C.POINTER(abi.Series), C.POINTER(abi.Outputs),
+                                          C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.letf_emu_run_series.restype = C.c_int
         L.letf_emu_validate.argtypes = [C.POINTER(abi.Params)]
         L.letf_emu_validate.restype = C.c_char_p
         _lib = L
@@ -70,6 +73,38 @@ def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, fir
         raise RuntimeError(f"emu rc={rc}: {lib().letf_emu_validate(C.byref(params))}")
     if log is not None:
         out.log = bufs
+    return out
+
+
+def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, precision=abi.PREC_F64, typed=False, log=None,
+               curve=False):
+    """materialised-path mode on host series: asset_ret = {asset name: [T][n] array}; log = (path, strategy, cap) switches
+    the journal log on, curve=True also returns that (path, strategy)'s daily equity (out.curve)"""
+    cols = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in asset_ret.items()}
+    first = next(iter(cols.values()))
+    T, n = first.shape
+    s = abi.Series()
+    s.n_paths, s.sim_days = n, T
+    for name, a in cols.items():
+        s.asset_ret[abi.ASSET_INDEX[name]] = a.ctypes.data
+    keep = [np.ascontiguousarray(np.asarray(x, dtype=dt)) if x is not None else None
+            for x, dt in ((tlt_ret, np.float64), (vix, np.float64), (regime, np.int32))]
+    s.tlt_ret, s.vix, s.regime = (k.ctypes.data if k is not None else None for k in keep)
+    out = HostOutputs(params.n_strategies, n)
+    args = [-1, -1, 0] + [None] * 7
+    if log is not None:
+        path, strat, cap = log
+        bufs = {"count": np.zeros(1, np.int32), "day": np.zeros(cap, np.int32), "asset": np.zeros(cap, np.int32),
+                "action": np.zeros(cap, np.int32), "shares": np.zeros(cap), "price": np.zeros(cap)}
+        cv = np.zeros(max(T, 1)) if curve else None
+        args = [path, strat, cap] + [bufs[k].ctypes.data for k in ("count", "day", "asset", "action", "shares", "price")] + \
+               [cv.ctypes.data if cv is not None else None]
+    rc = lib().letf_emu_run_series(C.byref(params), precision, 1 if typed else 0, C.byref(s), C.byref(out.as_struct()), *args)
+    if rc != 0:
+        raise RuntimeError(f"emu series rc={rc}")
+    if log is not None:
+        out.log = bufs
+        out.curve = cv[:T] if cv is not None else None
     return out
 
 

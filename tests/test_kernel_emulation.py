@@ -295,3 +295,65 @@ def test_bootstrap_block_draws_follow_the_reference_rules():
     for c in range(3):
         _ks(rec.boot_t[:, c, :][cons], stats.t(params.param_t_df).cdf)
         _ks(rec.x[:, c, :][cons], stats.t(params.param_t_df).cdf)
+
+
+def _reference_frame():
+    import os
+    from oracle.make_strategy_golden import strategy_frame
+    from tests.common import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "run_strategy_fixed_700d.npz"))
+    df, regime = strategy_frame(int(g["T"]), int(g["seed"]))
+    return g, df, regime
+
+
+def test_series_mode_equity_curves_match_live_reference():
+    """materialised-path mode of the kernel source (run_strategy_fixed seam) on the frame the LIVE reference's
+    run_strategy_fixed was run on (tests/golden/run_strategy_fixed_700d.npz): daily equity curve to 1e-11 at every day,
+    identical trade counts, journal entry counts and journal days, for 13 rules."""
+    from letf_monte_carlo_b200.trade import TAXABLE_IDS
+    g, df, regime = _reference_frame()
+    T = len(df)
+    frame = {a: df[f"{a}_Ret"].to_numpy().reshape(T, 1) for a in abi.ASSET_NAMES}
+    ns = synthetic.config_namespace()
+    for sid in [str(x) for x in g["sids"]]:
+        params, keep = build_params([sid], T / 252.0, synthetic.fallback_regime_model(), ns)
+        out = emu.run_series(params, frame, tlt_ret=df["TLT_Ret"].to_numpy().reshape(T, 1), vix=df["VIX"].to_numpy().reshape(T, 1),
+                             regime=regime.reshape(T, 1), log=(0, 0, 4096), curve=True)
+        np.testing.assert_allclose(out.curve, g[f"{sid}_curve"], rtol=1e-11, err_msg=sid)
+        assert out.num_trades[0, 0] == int(g[f"{sid}_trades"]), sid
+        assert out.final_wealth[0, 0] == out.curve[-1]
+        if sid in TAXABLE_IDS:
+            n = int(out.log["count"][0])
+            assert n == int(g[f"{sid}_journal_n"]), sid
+            np.testing.assert_array_equal(out.log["day"][:n], g[f"{sid}_journal_days"])
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 61, 203])
+def test_series_mode_short_frames_and_typed_build(T):
+    """edge lengths of the series prefetch queue (T below / around its depth and the window lengths), generic fp64 and
+    fp32 builds and the typed 19-rule fp32 build against the oracle's run_strategy on the same frame"""
+    import ctypes as C
+    rng = np.random.default_rng(100 + T)
+    n = 5
+    ns = synthetic.config_namespace()
+    params, keep = build_params(ALL19, max(T, 1) / 252.0, synthetic.fallback_regime_model(), ns)
+    rets = {a: np.ascontiguousarray(rng.standard_t(5, (T, n)) * s) for a, s in
+            zip(abi.ASSET_NAMES, (0.03, 0.03, 0.02, 0.025, 0.01, 0.013))}
+    vix = np.ascontiguousarray(15 + 10 * rng.random((T, n)))
+    regime = np.ascontiguousarray((rng.random((T, n)) < 0.3).astype(np.int32))
+    tlt = np.ascontiguousarray(rng.normal(0, 0.008, (T, n)))
+    o = orc.HostOutputs(params.n_strategies, n)
+    s = abi.Series()
+    s.n_paths, s.sim_days = n, T
+    for a, name in enumerate(abi.ASSET_NAMES):
+        s.asset_ret[a] = rets[name].ctypes.data
+    s.tlt_ret, s.vix, s.regime = tlt.ctypes.data, vix.ctypes.data, regime.ctypes.data
+    assert orc.lib().letf_oracle_run_strategies(C.byref(params), C.byref(s), C.byref(o.as_struct())) == 0
+    e64 = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, precision=abi.PREC_F64)
+    np.testing.assert_allclose(e64.final_wealth, o.final_wealth, rtol=1e-12)
+    np.testing.assert_array_equal(e64.num_trades, o.num_trades)
+    e32 = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, precision=abi.PREC_F32)
+    typed = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, precision=abi.PREC_F32, typed=True)
+    np.testing.assert_allclose(e32.final_wealth, o.final_wealth, rtol=5e-4)
+    np.testing.assert_allclose(typed.final_wealth, e32.final_wealth, rtol=1e-4)
+    assert np.mean(typed.num_trades != e32.num_trades) < 0.02
