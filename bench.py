@@ -335,7 +335,7 @@ def run_b200(args):
                                                           f"summary allreduce (NCCL) per step",
                        "rng": "on-device Philox4x32-10 keyed by (seed, sim_id, day, stream)",
                        "l2": "256 MiB memset between steps (inside the timed region); the path kernel reads no HBM inputs",
-                       "kernel": {"grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"],
+                       "kernel": {"name": info["kernel"], "grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"],
                                   "scratch_bytes": info["scratch_bytes"]}},
             "clocks": clocks,
             "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -550,7 +550,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--trials", type=int, default=0, help="trials per GPU (default: the workload's)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--seed", type=int, default=20240229)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LETF_ABI_VERSION 2
+#define LETF_ABI_VERSION 3
 
 #define LETF_N_ASSETS 6
 #define LETF_N_UNDERLYINGS 3
@@ -303,10 +303,13 @@ typedef struct LetfEngine LetfEngine;   /* opaque */
 typedef struct LetfLaunchInfo {
   int32_t grid, block;
   int32_t regs_per_thread;
-  int32_t kernel_launches;       /* kernels launched by the last letf_run / letf_run_host */
+  int32_t kernel_launches;       /* path kernels launched by the last letf_run / letf_run_host / replay call */
   int64_t scratch_bytes;
   float last_kernel_ms;          /* CUDA-event time of the fused kernel in the last call */
   int32_t sm_count;
+  int32_t aux_launches;          /* reduction / reset kernels launched by the last letf_reduce / letf_summary_reset */
+  int32_t pad;
+  char kernel[48];               /* instantiation name of the last path kernel (e.g. "f32_joint_t_pair_c3") */
 } LetfLaunchInfo;
 
 /* lifecycle ---------------------------------------------------------------- */

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 N_ASSETS = 6
 N_REGIMES = 2
 MAX_STRATEGIES = 32
@@ -168,6 +168,7 @@ class LaunchInfo(C.Structure):
         ("grid", C.c_int32), ("block", C.c_int32), ("regs_per_thread", C.c_int32),
         ("kernel_launches", C.c_int32), ("scratch_bytes", C.c_int64),
         ("last_kernel_ms", C.c_float), ("sm_count", C.c_int32),
+        ("aux_launches", C.c_int32), ("pad", C.c_int32), ("kernel", C.c_char * 48),
     ]
 
 

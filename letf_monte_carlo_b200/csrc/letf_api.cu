@@ -98,6 +98,8 @@ struct LetfEngine {
   std::vector<int32_t> host_dur[2];
   uint32_t type_mask = 0;
   bool any_taxable = false;
+  std::string pin_kernel;                    // tuning aids, read from the environment when the engine is created:
+  bool no_jpair = false;                     // LETF_KERNEL=<instantiation>, LETF_NO_JPAIR=1
   // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
   void* boot_blob = nullptr;
   DevBoot<double> boot64;
@@ -127,11 +129,14 @@ struct LogArgs {
 static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask,
                                        int n_assets) {
   const KernelEntry* best = nullptr;
+  const char* pin = e->pin_kernel.c_str();      // LETF_KERNEL, read once per engine (letf_create)
   for (int i = 0; i < kernel_count(); i++) {
     const KernelEntry* k = kernel_at(i);
     if (k->precision != e->precision || k->market != market) continue;
     if (need_io && !k->tapeio) continue;
     if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
+    // antithetic-pair kernels serve exactly one shape (letf_jfast.cuh); LETF_NO_JPAIR=1 keeps the generic lean build (A/B runs)
+    if (k->fj && (k->fj != fast_joint_shape(e->params, k->na) || e->no_jpair)) continue;
     if (k->am) {        // compile-time asset mask: same series, default tracking-error dof (config.py:62-135)
       bool ok = (k->am & 0x3F) == e->params.asset_mask;
       if (!(k->am & 0x40))          // bit 6: tracking-error dof read at run time (calibrated tracking_residual_model)
@@ -150,14 +155,14 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
       if (!same) continue;
     }
     // tuning aid: LETF_KERNEL=<instantiation name> pins an eligible build
-    const char* pin = getenv("LETF_KERNEL");
     if (pin && *pin && !strcmp(pin, k->name)) return k;
     if (!best) { best = k; continue; }
     // prefer the leanest build: fewer strategy slots, fewer rule types, no tape plumbing
     // typed-slot builds first, then fewer slots / series / rules, no tape plumbing
-    int a = (k->list ? 0 : 100000) + k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio + ((k->am & 0x40) ? 1 : 0);
+    int a = (k->list ? 0 : 100000) + k->ns * 64 + k->na * 16 + __builtin_popcount(k->tm) * 2 + k->tapeio + ((k->am & 0x40) ? 1 : 0) -
+            (k->fj ? 1 : 0);
     int b = (best->list ? 0 : 100000) + best->ns * 64 + best->na * 16 + __builtin_popcount(best->tm) * 2 + best->tapeio +
-            ((best->am & 0x40) ? 1 : 0);
+            ((best->am & 0x40) ? 1 : 0) - (best->fj ? 1 : 0);
     if (a < b) best = k;
   }
   return best;
@@ -180,7 +185,8 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   // one trial, or `upt` interleaved trials in the straight-line fast path (letf_fast.cuh).
   const int kBlock = ke->block;
   const int upt = (ke->upt > 1 && fast_pattern_compiled<NA>(ka.p.fast_layers) && rng_mode == LETF_RNG_PHILOX && !series) ? ke->upt : 1;
-  const int64_t items = (n + upt - 1) / upt;
+  // pair kernels: one work item per antithetic pair the trial range touches
+  const int64_t items = ke->fj ? ((first + n - 1) >> 1) - (first >> 1) + 1 : (n + upt - 1) / upt;
   const int64_t resident = (int64_t)e->sm_count * max_blocks * kBlock;
   const int64_t waves = (items + resident - 1) / resident;
   const int64_t per_wave = (items + waves - 1) / waves;
@@ -203,6 +209,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   size_t scratch = 0;
   if (((ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching) || ke->market == LETF_MARKET_BOOTSTRAP) && G > 0) {
     size_t b = ((size_t)G * 4 + (size_t)((G + 3) & ~3)) * (size_t)nthreads * sizeof(R);   // day vectors + the IRX-normal column (letf_core.cuh AUXSCR)
+    if (ke->fj) b = (size_t)G * sizeof(JF8) * (size_t)nthreads;                            // one 32-byte record per day and pair (letf_jfast.cuh)
     cudaError_t ce = e->xscr.reserve(b);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
     ka.xscr = (R*)e->xscr.p; scratch += b;
@@ -217,6 +224,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   e->timed = true;
   e->info.grid = (int)grid; e->info.block = kBlock; e->info.regs_per_thread = fa.numRegs;
   e->info.kernel_launches = 1; e->info.scratch_bytes = (int64_t)scratch; e->info.sm_count = e->sm_count;
+  snprintf(e->info.kernel, sizeof(e->info.kernel), "%s", ke->name);
   return LETF_OK;
 }
 
@@ -244,7 +252,7 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
         return fail(LETF_ERR_INVALID, "a bootstrap pool is empty: the tape needs boot_syn with boot_block_size == block_size");
     }
   }
-  if (n == 0) { e->info.kernel_launches = 0; return LETF_OK; }
+  if (n == 0) { e->info.kernel_launches = 0; e->info.kernel[0] = 0; return LETF_OK; }
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
   // (a caller-supplied frame needs no tape plumbing; only the journal does)
   const bool need_io = (market != kMarketSeries && rng_mode != LETF_RNG_PHILOX) || want_journal || lg.count != nullptr ||
@@ -357,6 +365,8 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
     if (ce != cudaSuccess) { letf_destroy(e); return fail_cuda(ce, "bootstrap tables upload"); }
   }
   e->type_mask = strategy_type_mask(*params);
+  { const char* v = getenv("LETF_KERNEL"); e->pin_kernel = v ? v : ""; }
+  { const char* v = getenv("LETF_NO_JPAIR"); e->no_jpair = v && *v && *v != '0'; }
   for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
   ce = cudaEventCreate(&e->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);
@@ -396,9 +406,10 @@ int letf_run_strategies(LetfEngine* e, void* stream, const LetfSeries* series, c
 
 int letf_summary_reset(LetfEngine* e, void* stream, const LetfSummary* sm) {
   if (!e || !sm || !sm->hist || !sm->moments || !sm->extrema || !sm->counters) return fail(LETF_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   CK(launch_summary_reset(*sm, e->params.n_strategies, (cudaStream_t)stream));
-  e->info.kernel_launches = 1;
+  e->info.aux_launches = 1;
   return LETF_OK;
 }
 
@@ -407,15 +418,17 @@ int letf_reduce(LetfEngine* e, void* stream, const LetfOutputs* out, int64_t n_t
   if (n_trials < 0 || n_trials > out->n_trials) return fail(LETF_ERR_INVALID, "bad n_trials");
   for (int q = 0; q < LETF_N_METRICS; q++) if (!(sm->hist_hi[q] > sm->hist_lo[q])) return fail(LETF_ERR_INVALID, "histogram range must have hi > lo");
   if (sm->bench_strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "bench_strategy out of range");
+  std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   CK(launch_reduce(*out, *sm, n_trials, e->params.n_strategies, e->params.initial_capital, e->params.sim_years,
                    e->sm_count, (cudaStream_t)stream));
-  e->info.kernel_launches = n_trials > 0 ? 1 : 0;
+  e->info.aux_launches = n_trials > 0 ? 1 : 0;
   return LETF_OK;
 }
 
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
   if (!e || !info) return fail(LETF_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
   if (e->timed) {
     CK(cudaEventSynchronize(e->ev1));
     float ms = 0.f;
@@ -750,17 +763,18 @@ int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* hs, int strate
   LetfSeries ds; memset(&ds, 0, sizeof(ds));
   ds.n_paths = 1; ds.sim_days = hs->sim_days;
   size_t o = 0;
+  cudaError_t up_err = cudaSuccess;
   auto up = [&](const void* src, size_t bytes, size_t stride) -> const void* {
     if (!src) return nullptr;
     void* dst = base + o; o += stride;
-    if (bytes) cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (bytes) { cudaError_t ce2 = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); if (ce2 != cudaSuccess && up_err == cudaSuccess) up_err = ce2; }
     return dst;
   };
   for (int a = 0; a < LETF_N_ASSETS; a++) ds.asset_ret[a] = (const double*)up(hs->asset_ret[a], 8 * T, col8);
   ds.tlt_ret = (const double*)up(hs->tlt_ret, 8 * T, col8);
   ds.vix = (const double*)up(hs->vix, 8 * T, col8);
   ds.regime = (const int32_t*)up(hs->regime, 4 * T, col4);
-  CK(cudaGetLastError());
+  CK(up_err);
   return replay_one(e, kMarketSeries, 0, 0, strategy, LETF_RNG_PHILOX, nullptr, &ds, hs->sim_days, curve, num_trades, cap, day, asset,
                     action, shares, price, count);
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include "letf_core.cuh"
 #include "letf_fast.cuh"
+#include "letf_jfast.cuh"
 
 namespace letf {
 
@@ -38,6 +39,15 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
   }
 }
 
+// one antithetic pair per thread (letf_jfast.cuh): work item j = pair (first_trial >> 1) + j; a twin outside
+// [first_trial, first_trial + n_trials) is computed and not stored
+template <int NS, int NA, int NACT, int K10, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB) letf_jpair_kernel(const __grid_constant__ KArgs<float, NS, NA> ka) {
+  const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p0 = ka.first_trial >> 1, p1 = (ka.first_trial + ka.n_trials - 1) >> 1;
+  for (int64_t pj = p0 + lane; pj <= p1; pj += ka.nthreads) JointPair<NS, NA, NACT, K10>::run(ka, pj, lane);
+}
+
 // type-erased launcher table -----------------------------------------------------------------
 struct KernelEntry {
   int precision;      // LETF_PREC_*
@@ -50,6 +60,7 @@ struct KernelEntry {
   int am;             // compile-time asset mask, 0 = run time
   int block;          // threads per block
   int upt;            // trials per thread when DevParams::fast_layers applies (letf_fast.cuh), else 1
+  int fj;             // DevParams::fast_joint code this entry serves (antithetic-pair kernel, letf_jfast.cuh), 0 = any shape
   const char* name;
   cudaError_t (*launch)(const void* kargs, int grid, cudaStream_t st);
   cudaError_t (*attrs)(cudaFuncAttributes* a, int* max_blocks_per_sm);
@@ -79,9 +90,35 @@ struct KernelImpl {
     Reg_##ID() {                                                                                         \
       typedef letf::KernelImpl<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB> K;                    \
       letf::KernelEntry e = {PREC, NS, NA, MARKET, TAPEIO ? 1 : 0, TM, LIST, AM, BLK,                    \
-                             letf::fast_upt<R, NA, MARKET, TAPEIO>(), #ID, &K::launch,                   \
+                             letf::fast_upt<R, NA, MARKET, TAPEIO>(), 0, #ID, &K::launch,                \
                              &K::attrs,                                                                  \
                              sizeof(letf::KArgs<R, NS, NA>)};                                                \
+      letf::register_kernel(e);                                                                          \
+    }                                                                                                    \
+  } reg_##ID;                                                                                            \
+  }
+
+template <int NS, int NA, int NACT, int K10, int BLK, int MINB>
+struct JPairImpl {
+  static cudaError_t launch(const void* kargs, int grid, cudaStream_t st) {
+    letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<float, NS, NA>*)kargs);
+    return cudaGetLastError();
+  }
+  static cudaError_t attrs(cudaFuncAttributes* a, int* mb) {
+    cudaError_t e = cudaFuncGetAttributes(a, letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB>);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB>, BLK, 0);
+  }
+};
+
+#define LETF_INSTANTIATE_JPAIR(ID, NS, NA, NACT, K10, BLK, MINB)                                         \
+  namespace {                                                                                            \
+  struct Reg_##ID {                                                                                      \
+    Reg_##ID() {                                                                                         \
+      typedef letf::JPairImpl<NS, NA, NACT, K10, BLK, MINB> K;                                           \
+      letf::KernelEntry e = {LETF_PREC_F32, NS, NA, LETF_MARKET_JOINT_T, 0, letf::TM_BENCH, 0, 0, BLK, 2, \
+                             letf::fast_joint_code(NACT, K10), #ID, &K::launch, &K::attrs,               \
+                             sizeof(letf::KArgs<float, NS, NA>)};                                        \
       letf::register_kernel(e);                                                                          \
     }                                                                                                    \
   } reg_##ID;                                                                                            \

@@ -21,6 +21,7 @@ template <typename R> struct DevAsset {
   R bl_252;          // max(leverage - 1, 0) / 252      (fp32 fast path of utils.py:169-216)
   R beta_eff;        // beta if it applies, else exactly 1
   R w_spy, w_qqq;    // beta_eff on the series' own underlying, 0 on the other (FAST loop: u = w_spy*spy + w_qqq*qqq)
+  R w_tlt;           // same for TLT-based series (TMF); the pair kernel of letf_jfast.cuh adds w_tlt*tlt
   R carry_const;     // iid-normal market: expense/252 + borrow at the constant rate (loop invariant)
   R te_scale;        // te_base * sqrt(1 - rho^2)
   int und, beta_applies, te_fast_k, pad;
@@ -36,6 +37,13 @@ template <typename R> struct DevJoint {
 };
 
 template <typename R> struct DevVix { R phi, drift /* (1-phi)*target */, noise_std, jump_thr, jump_scale, denom; };
+// the per-regime constants the window loop of letf_jfast.cuh reads every day, packed for 128-bit constant loads
+template <typename R> struct alignas(16) DevFJ {
+  R vphi, vnoise, vdrift, vjthr;          // VIX recursion (engine.py:100-115)
+  R vjscale, vinvden, rmult, jbase;       // 1 / max(daily_std, 1e-4); tracking-error regime multiplier (engine.py:179)
+  R liq_mu, liq_phi, liq_sigma, jscale;   // latent stress (calibration.py:787-830)
+  R cr_mu, cr_phi, cr_sigma, pad;
+};
 template <typename R> struct DevStress { R liq_mu, liq_phi, liq_sigma, cr_mu, cr_phi, cr_sigma, jbase, jscale; };
 
 // legacy_hybrid block bootstrap (bootstrap.py:310-458, engine.py:50-80).  The candidate lists a block draw can
@@ -66,7 +74,10 @@ template <typename R, int NS, int NA> struct DevParams {
       has_vix, has_stress, has_funding, asset_mask, n_strat, apply_costs, sig_asset,
       bench_mask /* assets tracked for a buy&hold strategy */, bench_tlt, need_tlt,
       fast_layers /* 0, or 1 + bitmask of the slots whose tracking error is t(10) (others t(5)): every slot active,
-                     no tanh cap, no funding model, no TLT series -> straight-line day step (letf_fast.cuh) */, pad_f;
+                     no tanh cap, no funding model, no TLT series -> straight-line day step (letf_fast.cuh) */,
+      fast_joint /* 0, or (n_act << 8) | mask of the t(10) slots: institutional joint-t market with moment matching,
+                    antithetic pairs, stress + funding models, integer joint dof, every active series buy&hold with
+                    default tracking-error dof and no tanh cap -> one antithetic pair per thread (letf_jfast.cuh) */;
   R W0, sim_years;
   R start_p1;                   // P(start in regime 1), LetfParams::start_regime_prob1
   int flip[2];
@@ -83,6 +94,7 @@ template <typename R, int NS, int NA> struct DevParams {
   DevVix<R> vix[2];
   R vix_base[2], irx_base[2];
   DevStress<R> stress[2];
+  DevFJ<R> fj[2];
   R f_base, f_vix, f_inv, f_liq, f_cr, f_min, f_max;
   DevAsset<R> assets[kAssets];
   // the ETF series this launch computes: NA == 6 -> slot j is asset j (act_on = mask bit);
@@ -217,6 +229,29 @@ inline void build_boot_tables(const LetfParams& s, BootTables<R>& t) {
   }
 }
 
+// shape code of the antithetic-pair kernel (letf_jfast.cuh), 0 = not admitted; computed from the public parameter block so
+// that kernel selection (letf_api.cu) and the device parameter block agree
+inline int fast_joint_shape(const LetfParams& s, int na) {
+  if (na >= kAssets || s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs) return 0;
+  if (!s.institutional || !s.has_stress || !s.has_funding || s.sim_days < 2) return 0;
+  for (int r = 0; r < 2; r++) if (!df_fast_k(s.joint[r].nu)) return 0;
+  for (int k = 0; k < s.n_strategies; k++)
+    if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) return 0;
+  int nact = 0, k10 = 0;
+  for (int a = 0; a < kAssets; a++) {
+    if (!((s.asset_mask >> a) & 1)) continue;
+    const int fk = df_fast_k(s.assets[a].te_df);
+    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) return 0;
+    bool bench = false;
+    for (int k = 0; k < s.n_strategies; k++) if (s.strategies[k].type == LETF_ST_BENCHMARK && s.strategies[k].asset == a) bench = true;
+    if (!bench) return 0;
+    if (fk == 10) k10 |= 1 << nact;
+    nact++;
+  }
+  if (nact < 1 || nact > na) return 0;
+  return (nact << 8) | k10;
+}
+
 template <typename R, int NS, int NA>
 inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2], DevParams<R, NS, NA>& d,
                            const DevBoot<R>* boot = nullptr) {
@@ -269,6 +304,12 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     u.cr_mu = (R)t.credit_mu; u.cr_phi = (R)t.credit_phi; u.cr_sigma = (R)t.credit_sigma;
     u.jbase = (R)t.jump_base_prob; u.jscale = (R)t.jump_scale;
     d.cash_daily[r] = (R)(s.cash_rate[r] / 252); d.spread_cost[r] = (R)(s.base_spread_bps[r] / 10000);
+    DevFJ<R>& f = d.fj[r];
+    f.vphi = d.vix[r].phi; f.vnoise = d.vix[r].noise_std; f.vdrift = d.vix[r].drift; f.vjthr = d.vix[r].jump_thr;
+    f.vjscale = d.vix[r].jump_scale; f.vinvden = (R)(1.0 / (s.regime_daily_std[r] > 1e-4 ? s.regime_daily_std[r] : 1e-4));
+    f.rmult = r == 0 ? (R)1 : (R)1.15; f.jbase = u.jbase;
+    f.liq_mu = u.liq_mu; f.liq_phi = u.liq_phi; f.liq_sigma = u.liq_sigma; f.jscale = u.jscale;
+    f.cr_mu = u.cr_mu; f.cr_phi = u.cr_phi; f.cr_sigma = u.cr_sigma; f.pad = (R)0;
   }
   for (int a = 0; a < 3; a++) d.mm_theo[a] = (R)((s.joint[0].mu[a] + s.joint[1].mu[a]) / 2.0);
   d.pt_df = (R)s.param_t_df; d.pt_fast_k = df_fast_k(s.param_t_df);
@@ -291,6 +332,7 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
     y.beta_eff = x.beta_applies ? (R)x.beta : (R)1;
     y.w_spy = x.underlying == 0 ? y.beta_eff : (R)0;
     y.w_qqq = x.underlying == 1 ? y.beta_eff : (R)0;
+    y.w_tlt = x.underlying == 2 ? y.beta_eff : (R)0;
     {
       double rate = s.const_rf + x.borrow_spread; if (!(rate > 0.0)) rate = 0.0;
       y.carry_const = (R)(x.expense_ratio / 252 + (x.leverage > 1.0 ? (x.leverage - 1.0) * rate / 252 : 0.0));
@@ -329,6 +371,7 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
   }
   if (d.n_act != NA) d.fast_layers = 0;
   if (d.fast_layers) for (int j = 0; j < NA; j++) if (d.act[j].te_fast_k == 10) d.fast_layers += 1 << j;
+  d.fast_joint = fast_joint_shape(s, NA);
 }
 #endif  // LETF_DEVICE_ONLY
 

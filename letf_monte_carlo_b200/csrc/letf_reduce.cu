@@ -137,11 +137,11 @@ cudaError_t launch_reduce(const LetfOutputs& out, const LetfSummary& sm, int64_t
   int gx = (int)(want < per ? want : per);
   dim3 grid(gx, n_strat);
   const int smem = LETF_N_METRICS * LETF_HIST_BINS * (int)sizeof(unsigned int);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in is a per-DEVICE attribute of the function and cheap to set: set it on every launch (a process-wide flag
+  // left a second device driven from the same process without it)
+  {
     cudaError_t e = cudaFuncSetAttribute(letf_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   letf_reduce_kernel<<<grid, kRBlock, smem, st>>>(ra);
   return cudaGetLastError();

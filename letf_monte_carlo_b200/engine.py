@@ -307,4 +307,6 @@ class PathEngine:
     def launch_info(self) -> dict:
         li = abi.LaunchInfo()
         self._check(self._lib.letf_launch_info(self._h, C.byref(li)))
-        return {k: getattr(li, k) for k, _ in abi.LaunchInfo._fields_}
+        d = {k: getattr(li, k) for k, _ in abi.LaunchInfo._fields_ if k != "pad"}
+        d["kernel"] = d["kernel"].decode()
+        return d

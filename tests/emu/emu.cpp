@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../letf_monte_carlo_b200/csrc/letf_core.cuh"
 #include "../../letf_monte_carlo_b200/csrc/letf_fast.cuh"
+#include "../../letf_monte_carlo_b200/csrc/letf_jfast.cuh"
 
 using namespace letf;
 
@@ -101,6 +102,46 @@ extern "C" int letf_emu_run_lean(const LetfParams* sp, const LetfOutputs* out, u
     Trial<float, NS, NA, LETF_MARKET_NORMAL, false, TMB> t(ka, first + j, j, 0);
     t.run();
   }
+  return 0;
+}
+
+// the lean institutional buy&hold build: the antithetic-pair kernel body (letf_jfast.cuh) when the shape is admitted and
+// compiled in, else (or with force_generic) the lean build's general loop; Philox only
+template <int NACT, int K10>
+static void run_jpairs(const KArgs<float, 4, 3>& ka, int64_t first, int64_t n) {
+  for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<4, 3, NACT, K10>::run(ka, pj, 0);
+}
+extern "C" int letf_emu_run_jpair(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n,
+                                  int* used_pair, int force_generic) {
+  if (validate_params(*sp) || sp->market_mode != LETF_MARKET_JOINT_T) return -1;
+  constexpr int NS = 4, NA = 3;
+  constexpr uint32_t TMB = (1u << LETF_ST_BENCHMARK) | (1u << LETF_ST_BENCHMARK_TLT);
+  if (sp->n_strategies > NS || __builtin_popcount((unsigned)sp->asset_mask & 0x3Fu) > NA) return -2;
+  static KArgs<float, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
+  convert_params<float, NS, NA>(*sp, dd, ka.p);
+  ka.out = *out; ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.rng_mode = LETF_RNG_PHILOX; ka.nthreads = 1;
+  ka.log_trial = -1;
+  const int G = sp->sim_days + sp->buffer_days;
+  float* xscr = (float*)aligned_alloc(32, ((size_t)(G > 0 ? G : 1) * 8 + 8) * sizeof(float));
+  ka.xscr = xscr;
+  const int code = ka.p.fast_joint;
+  const bool compiled = code == fast_joint_code(2, 3) || code == fast_joint_code(3, 4) || code == fast_joint_code(1, 0) ||
+                        code == fast_joint_code(1, 1);
+  if (used_pair) *used_pair = (compiled && !force_generic) ? code : 0;
+  if (compiled && !force_generic && n > 0) {
+    if (code == fast_joint_code(2, 3)) run_jpairs<2, 3>(ka, first, n);
+    else if (code == fast_joint_code(3, 4)) run_jpairs<3, 4>(ka, first, n);
+    else if (code == fast_joint_code(1, 0)) run_jpairs<1, 0>(ka, first, n);
+    else run_jpairs<1, 1>(ka, first, n);
+  } else {
+    for (int64_t j = 0; j < n; j++) {
+      Trial<float, NS, NA, LETF_MARKET_JOINT_T, false, TMB> t(ka, first + j, j, 0);
+      t.run();
+    }
+  }
+  free(xscr);
   return 0;
 }
 

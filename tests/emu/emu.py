@@ -45,6 +45,9 @@ def lib():
         L.letf_emu_run_lean.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64,
                                         C.POINTER(C.c_int), C.c_int, C.c_int]
         L.letf_emu_run_lean.restype = C.c_int
+        L.letf_emu_run_jpair.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64,
+                                         C.POINTER(C.c_int), C.c_int]
+        L.letf_emu_run_jpair.restype = C.c_int
         L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_typed.restype = C.c_int
         L.letf_emu_run_series.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, C.POINTER(abi.Series), C.POINTER(abi.Outputs),
@@ -119,6 +122,18 @@ def run_lean(params, n, seed=0, first=0, two_per_thread=False, force_generic=Fal
     if rc != 0:
         raise RuntimeError(f"emu lean rc={rc}")
     return out, int(fast.value)
+
+
+def run_jpair(params, n, seed=0, first=0, force_generic=False):
+    """lean institutional buy&hold build (NA = 3 compacted slots, joint-t market); returns (outputs, pair-kernel shape code).
+    default: the antithetic-pair body (letf_jfast.cuh) when the shape is admitted; force_generic: Trial::run"""
+    out = HostOutputs(params.n_strategies, n)
+    used = C.c_int(0)
+    rc = lib().letf_emu_run_jpair(C.byref(params), C.byref(out.as_struct()), seed, first, n, C.byref(used),
+                                  1 if force_generic else 0)
+    if rc != 0:
+        raise RuntimeError(f"emu jpair rc={rc}")
+    return out, int(used.value)
 
 
 def run_typed(params, slot_list, n, seed=0, first=0):

@@ -366,6 +366,49 @@ def test_lean_fast_kernel_vs_generic_and_oracle(engine_lib):
     assert (lean.flags == 0).all() and (o.flags == 0).all()
 
 
+@pytest.mark.parametrize("sids,years", [(["S2", "B_QQQ", "B_TLT"], 2), (["S1", "S2", "S3"], 1), (["S2", "B_QQQ", "B_TLT"], 30)],
+                         ids=["c3_2y", "letf3_1y", "c3_30y"])
+def test_joint_pair_kernel_vs_generic_and_oracle(sids, years, engine_lib, monkeypatch):
+    """bench.py's c3 workload (BASELINE configs[2]) runs the antithetic-pair kernel (letf_jfast.cuh): one thread carries both
+    twins of a pair and draws their shared Philox blocks once.  Chain of evidence on the device: pair kernel (Philox) ==
+    the lean build's general loop on the same counters == the generic fp32 build recording those counters, and the
+    fp64 oracle replaying the recorded tape agrees with all of them - at 30 years too (the benchmarked horizon)."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, years, synthetic.fallback_regime_model("default"), ns)
+    n_t = 96 if years < 30 else 24
+    n = 2 * n_t
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 1024)
+    with _engine(params, keep, "f32") as eng:
+        pair = eng.run_host(n, seed=4242)
+        assert eng.launch_info()["kernel"].startswith("f32_joint_t_pair")
+        part = eng.run_host(9, seed=4242, first_trial=3)           # starts on an odd twin, ends on an even one
+        gen = eng.run_host(n, seed=4242, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+        assert not eng.launch_info()["kernel"].startswith("f32_joint_t_pair")
+    monkeypatch.setenv("LETF_NO_JPAIR", "1")
+    with _engine(params, keep, "f32") as eng:
+        lean = eng.run_host(n, seed=4242)
+        assert eng.launch_info()["kernel"] == "f32_joint_t_bench"
+    o = orc.run(params, rec)
+    tol = 5e-5 if years < 30 else 5e-4          # fp32 reassociation between builds, compounded over the horizon
+    for other in (lean, gen):
+        np.testing.assert_allclose(pair.final_wealth, other.final_wealth, rtol=tol)
+        np.testing.assert_allclose(pair.max_dd, other.max_dd, atol=2e-5)
+        np.testing.assert_array_equal(pair.regime_days, other.regime_days)
+        np.testing.assert_array_equal(pair.start_offset, other.start_offset)
+        np.testing.assert_array_equal(pair.jump_days, other.jump_days)
+        np.testing.assert_array_equal(pair.flags, other.flags)
+    np.testing.assert_array_equal(part.final_wealth, pair.final_wealth[:, 3:12])
+    # fp32 device arithmetic vs the fp64 oracle on identical shocks: stated fp32 tolerance (2e-4 over <= 5 years, 2e-3 at 30 years)
+    np.testing.assert_allclose(pair.final_wealth, o.final_wealth, rtol=2e-4 if years < 30 else 2e-3)
+    np.testing.assert_allclose(pair.max_dd, o.max_dd, atol=1e-4 if years < 30 else 5e-4)
+    np.testing.assert_array_equal(pair.regime_days, o.regime_days)
+    np.testing.assert_array_equal(pair.jump_days, o.jump_days)
+    np.testing.assert_array_equal(pair.start_offset, o.start_offset)
+    np.testing.assert_array_equal((pair.flags & abi.FLAG_REPAIRED) != 0, (o.flags & abi.FLAG_REPAIRED) != 0)
+    print("joint_pair", sids, years, "max rel vs oracle", float(np.max(np.abs(pair.final_wealth / o.final_wealth - 1))),
+          "vs lean", float(np.max(np.abs(pair.final_wealth / lean.final_wealth - 1))))
+
+
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 def test_philox_distribution_matches_live_reference(precision, engine_lib):
     """KS + summary-quantile agreement of on-device Philox runs with the LIVE reference's own NumPy streams

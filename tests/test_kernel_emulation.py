@@ -200,6 +200,56 @@ def test_lean_fast_variant_matches_generic_build():
     np.testing.assert_allclose(lean2.final_wealth, gen2.final_wealth, rtol=2e-5)
 
 
+@pytest.mark.parametrize("sids,code", [(["S2", "B_QQQ", "B_TLT"], 0x203), (["S1", "S2", "S3"], 0x304), (["S1"], 0x100), (["S2", "B_TLT"], 0x101)])
+def test_joint_pair_variant_matches_generic_build(sids, code):
+    """One antithetic pair per thread (letf_jfast.cuh, what bench.py's c3 workload runs): the twins share every Philox block
+    and variate, as the reference's identically seeded twins do (mc_runner.py:145-153), against the lean build's general
+    loop and the tape-capable generic build on the same counters: same draws, fp32 reassociation only."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    pair, used = emu.run_jpair(params, 48, seed=11)
+    assert used == code
+    slow, _ = emu.run_jpair(params, 48, seed=11, force_generic=True)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    gen = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=11, n=48)
+    for ref in (slow, gen):
+        np.testing.assert_allclose(pair.final_wealth, ref.final_wealth, rtol=2e-5)
+        np.testing.assert_allclose(pair.max_dd, ref.max_dd, atol=5e-6)
+        np.testing.assert_array_equal(pair.flags, ref.flags)
+        np.testing.assert_array_equal(pair.start_offset, ref.start_offset)
+        np.testing.assert_array_equal(pair.regime_days, ref.regime_days)
+        np.testing.assert_array_equal(pair.jump_days, ref.jump_days)
+    assert pair.jump_days.sum() > 0 and (pair.regime_days[1] > 0).any()
+    # twins share the start offset and the regime path, and differ
+    np.testing.assert_array_equal(pair.start_offset[0::2], pair.start_offset[1::2])
+    assert not np.allclose(pair.final_wealth[:, 0::2], pair.final_wealth[:, 1::2])
+    # a trial range that starts on an odd twin and ends on an even one
+    part, _ = emu.run_jpair(params, 9, seed=11, first=3)
+    np.testing.assert_array_equal(part.final_wealth, pair.final_wealth[:, 3:12])
+    np.testing.assert_array_equal(part.jump_days, pair.jump_days[3:12])
+
+
+def test_joint_pair_variant_not_admitted_shapes_fall_back():
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_ANTITHETIC_VARIATES=False)
+    params, keep = build_params(["S2", "B_QQQ", "B_TLT"], 1, synthetic.fallback_regime_model("default"), ns)
+    out, used = emu.run_jpair(params, 4, seed=1)
+    assert used == 0 and np.isfinite(out.final_wealth).all()
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(["S1", "S2"], 1, synthetic.fallback_regime_model("vix_te"), ns)   # TQQQ: calibrated dof 4 + tanh cap
+    out, used = emu.run_jpair(params, 4, seed=1)
+    assert used == 0 and np.isfinite(out.final_wealth).all()
+    # explicit VIX dynamics and empirical dwell-time samples are run-time parameters of the pair kernel
+    for variant in ("vix_te", "durations", "jumpy"):
+        params, keep = build_params(["S2", "B_QQQ", "B_TLT"], 1, synthetic.fallback_regime_model(variant), ns)
+        pair, used = emu.run_jpair(params, 16, seed=2)
+        slow, _ = emu.run_jpair(params, 16, seed=2, force_generic=True)
+        assert used == 0x203
+        np.testing.assert_allclose(pair.final_wealth, slow.final_wealth, rtol=2e-5)
+        np.testing.assert_array_equal(pair.regime_days, slow.regime_days)
+        np.testing.assert_array_equal(pair.jump_days, slow.jump_days)
+        np.testing.assert_array_equal(pair.flags, slow.flags)
+
+
 def test_philox_distribution_matches_live_reference():
     """north star: 'On-device Philox draws must match the reference's distributions by KS test and
     summary-quantile agreement' - the reference side is the LIVE reference with its own PCG64 streams
