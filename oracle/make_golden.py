@@ -80,6 +80,8 @@ CASES = [
               "BOOTSTRAP_BLOCK_MEAN": 2, "BOOTSTRAP_WEIGHT": 1.0}, strategies=ALL19 + EXTRAS),
     dict(name="layers_c2_5y", variant="normal_c2", years=5, n_tapes=4, seed=117, cfg={},
          strategies=["S1", "S3", "B_UPRO"]),
+    dict(name="layers_c2_30y", variant="normal_c2", years=30, n_tapes=2, seed=123, cfg={},
+         strategies=["S1", "S3", "B_UPRO"]),
     dict(name="voldrag_c1", variant="normal_c1", years=1, n_tapes=8, seed=118,
          cfg={"LETF_CONFIGS": "pure_leverage"}, strategies=["B_UPRO", "S3", "S2"]),
 ]

@@ -69,6 +69,23 @@ def test_f32_tape_close_to_reference(name, engine_lib):
     assert np.mean(out.num_trades != expected_arrays(doc)[2]) < 0.02
 
 
+@pytest.mark.parametrize("name", ["inst_10y", "inst_30y", "boot_10y", "layers_c2_30y"])
+def test_f32_tape_close_to_reference_at_benchmark_horizons(name, engine_lib):
+    """fp32 throughput mode at the horizons bench.py runs (10 and 30 years = 7 560 days), same pre-drawn tape as the
+    live-reference golden.  Stated fp32 tolerance at 30 years: terminal wealth 5e-4 relative (measured <= 7e-5), max
+    drawdown 5e-5 absolute, trade counts within 1 in < 2 % of (strategy, trial) cells, integer path state identical."""
+    doc = load_case(name)
+    ns, model, params, keep, tape = case_inputs(doc)
+    n = tape.n_tapes * (2 if params.antithetic_pairs else 1)
+    with _engine(params, keep, "f32") as eng:
+        out = eng.run_host(n, rng_mode=abi.RNG_TAPE, tape=tape, journal=True)
+    assert_matches_reference(out, doc, rtol=5e-4, dd_atol=5e-5, exact_counts=False)
+    fw, dd, nt, jc, jv = expected_arrays(doc)
+    assert np.mean(out.num_trades != nt) < 0.02 and np.abs(out.num_trades - nt).max() <= 2
+    print("f32 tape", name, "max rel", float(np.max(np.abs(out.final_wealth / fw - 1))), "dd", float(np.max(np.abs(out.max_dd - dd))),
+          "trade-cell mismatch", float(np.mean(out.num_trades != nt)))
+
+
 def test_constant_window_corner(engine_lib):
     from tests.test_kernel_emulation import drifty_case
     params, keep, tape = drifty_case(years=3, n=64, seed=11)
@@ -342,14 +359,16 @@ def test_full_size_properties_config2(engine_lib):
         assert abs(lg.mean() - g) < 5 * se + 2e-6, (a, lg.mean(), g, se)
 
 
-def test_lean_fast_kernel_vs_generic_and_oracle(engine_lib):
+@pytest.mark.parametrize("years", [5, 30])
+def test_lean_fast_kernel_vs_generic_and_oracle(years, engine_lib):
     """bench.py's c2 workload runs the lean buy&hold build with the loop-unswitched FAST day step.
     Chain of evidence on the device: FAST (Philox) == generic fp32 build recording the same counters
-    (fp32 reassociation only), and the oracle replaying that recorded tape agrees with both."""
+    (fp32 reassociation only), and the oracle replaying that recorded tape agrees with both - at 5 years and at the
+    benchmarked 30-year horizon (stated fp32 tolerance there: 1e-3 relative, measured value printed)."""
     sids = ["S1", "B_UPRO", "S3"]
-    doc = {"case": dict(variant="normal_c2", years=5, n_tapes=256, seed=0, cfg={}, strategies=sids)}
+    n = 256 if years == 5 else 64
+    doc = {"case": dict(variant="normal_c2", years=years, n_tapes=n, seed=0, cfg={}, strategies=sids)}
     ns, model, params, keep, _ = case_inputs(doc)
-    n = 256
     rec = HostTape(n, params.sim_days, params.sim_days, 1)
     with _engine(params, keep, "f32") as eng:
         lean = eng.run_host(n, seed=31337)
@@ -358,12 +377,15 @@ def test_lean_fast_kernel_vs_generic_and_oracle(engine_lib):
         regs_gen = eng.launch_info()["regs_per_thread"]
     assert regs_lean < regs_gen                      # two different instantiations really ran
     o = orc.run(params, rec)
-    np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=5e-5)
-    np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=5e-6)
-    np.testing.assert_allclose(gen.final_wealth, o.final_wealth, rtol=2e-4)
-    np.testing.assert_allclose(lean.final_wealth, o.final_wealth, rtol=2e-4)
+    k = 1 if years == 5 else 5
+    np.testing.assert_allclose(lean.final_wealth, gen.final_wealth, rtol=5e-5 * k)
+    np.testing.assert_allclose(lean.max_dd, gen.max_dd, atol=5e-6 * k)
+    np.testing.assert_allclose(gen.final_wealth, o.final_wealth, rtol=2e-4 * k)
+    np.testing.assert_allclose(lean.final_wealth, o.final_wealth, rtol=2e-4 * k)
     np.testing.assert_allclose(lean.max_dd, o.max_dd, atol=1e-4)
     assert (lean.flags == 0).all() and (o.flags == 0).all()
+    print("c2 FAST", years, "y: max rel vs oracle", float(np.max(np.abs(lean.final_wealth / o.final_wealth - 1))),
+          "vs generic", float(np.max(np.abs(lean.final_wealth / gen.final_wealth - 1))))
 
 
 @pytest.mark.parametrize("sids,years", [(["S2", "B_QQQ", "B_TLT"], 2), (["S1", "S2", "S3"], 1), (["S2", "B_QQQ", "B_TLT"], 30)],
