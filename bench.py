@@ -35,6 +35,11 @@ UNIT = "path-days/s"
 # algorithmic lane-instructions per path-day (Philox4x32-10, inverse-CDF / Box-Muller
 # normals, gamma-based chi2 / Student-t, compounding + drawdown per tracked equity); restated in DESIGN.md
 WORKLOADS = {
+    "c1": dict(desc="BASELINE configs[0]: TQQQ-like 3x daily-reset single-asset GBM (validation.py:33-57: zero drift, sigma 15 %/yr, "
+                    "no frictions), buy&hold, 10k trials x 252 days (literal size: launch-bound)",
+               trials=10_000, years=1, lane_ops=46, mufu=2),
+    "c1x": dict(desc="BASELINE configs[0] at throughput size (SURVEY.md 8d): the same 3x GBM shape, 1e8 trials x 252 days",
+                trials=100_000_000, years=1, lane_ops=46, mufu=2),
     "c2": dict(desc="BASELINE configs[1]: TQQQ/UPRO/SSO, expense ratio + borrow cost + AR(1) Student-t tracking error, "
                     "correlated normal SPY/QQQ shocks, buy&hold, 100k trials x 7560 days",
                trials=100_000, years=30, lane_ops=470, mufu=14),
@@ -67,7 +72,13 @@ WORKLOADS = {
 def build_workload(name):
     from letf_monte_carlo_b200 import synthetic
     from letf_monte_carlo_b200.params import build_params
-    if name == "c2":
+    if name in ("c1", "c1x"):
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                        USE_ANTITHETIC_VARIATES=False, LETF_CONFIGS=synthetic.pure_leverage_assets())
+        ns.ASSETS = ns.LETF_CONFIGS
+        sids = ["B_UPRO"]
+        model = synthetic.normal_regime_model("c1")
+    elif name == "c2":
         ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
                                         USE_ANTITHETIC_VARIATES=False)
         sids = ["S1", "B_UPRO", "S3"]
@@ -180,6 +191,32 @@ def cpu_port_rate(params, budget_s, threads, seed=1):
     return done * T / dt, done, dt
 
 
+def numpy_reference_leg(workload, years, cores):
+    """The reference's own NumPy path (unmodified package under baseline/_ref), timed on this box's host cores with the
+    reference's default worker count (cpu_count - 2, config.py:151) and with every core; SURVEY.md 8(d)."""
+    from baseline import numpy_reference as nr
+    if not nr.available():
+        return {"unavailable": "baseline/_ref/letf not present"}
+    if workload in ("c1", "c1x"):
+        d = nr.numpy_rate("c1", 1, 0, 1)
+        if "unavailable" in d:
+            return d
+        return {"value": d["value"], "unit": UNIT, "cores": 1, "kind": "reference", "entry": d["entry"],
+                "sample": f"{d['trials']} trials x 252 days in {d['seconds']:.2f} s (vectorised NumPy, one core)"}
+    trials = int(os.environ.get("LETF_BENCH_NUMPY_TRIALS", "0")) or 2 * cores
+    runs = {}
+    for label, w in (("workers_default", max(1, cores - 2)), ("workers_all", cores)):
+        d = nr.numpy_rate(workload, years, trials, w)
+        if "unavailable" in d:
+            return d
+        runs[label] = {"workers": w, "value": d["value"], "seconds": d["seconds"], "trials": d["trials"]}
+    best = max(runs.values(), key=lambda r: r["value"])
+    return {"value": best["value"], "unit": UNIT, "cores": cores, "kind": "reference", "runs": runs, "entry": d["entry"],
+            "strategies": d.get("strategies"),
+            "sample": f"{trials} trials x {int(years * 252)} days through the unmodified reference (baseline/_ref), full "
+                      f"institutional_v1 engine with all six ETF layers (it cannot switch them off), one warm-up call excluded"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -215,7 +252,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from letf_monte_carlo_b200 import abi
-    from letf_monte_carlo_b200.distributed import allreduce_summary
+    from letf_monte_carlo_b200.distributed import exchange_summary
     from letf_monte_carlo_b200.engine import PathEngine
     from letf_monte_carlo_b200.mc_runner import parallel_monte_carlo_fixed
 
@@ -261,7 +298,7 @@ def run_b200(args):
         eng.reset_summary(sm)
         eng.reduce(out, sm)
         if ws > 1:
-            allreduce_summary(sm.hist, sm.moments, sm.extrema, sm.counters)
+            exchange_summary(sm, engine=eng)
 
     for _ in range(args.warmup):
         step()
@@ -281,30 +318,59 @@ def run_b200(args):
     barrier()
     launches = eng.launches - launches0
     total_ms = t_start.elapsed_time(t_end)
+    # exchange-step correctness (every rank): after the allreduce each strategy's histogram holds ws * n trials minus the
+    # ones the reduction rejected as non-finite, and the valid counters agree with it
+    hist_n = sm.hist.sum(dim=2).cpu().numpy()
+    cnt = sm.counters.cpu().numpy()
+    assert (hist_n == cnt[:, :1]).all(), "histogram totals disagree with the valid-trial counters"
+    assert (cnt[:, 0] <= ws * n).all() and (cnt[:, 0] >= ws * n - cnt[:, 3]).all() and cnt[:, 0].min() > 0.99 * ws * n, \
+        f"summary exchange lost trials: valid {cnt[:, 0]} of {ws * n}"
+    summary_check = {"valid": int(cnt[:, 0].min()), "expected": ws * n}
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     clocks = clk.stop() if rank == 0 else None
     info = eng.launch_info()
 
-    # ---- end to end through the public API: host in, host out, engine created per call
+    # ---- end to end through the public API (the call a user makes): parameter dicts in from the host, the run's summary
+    # table out on the host.  summary_only=True: the per-trial arrays stay on the device, the reduction kernel and the
+    # cross-rank exchange run inside the call, and only the packed summary (histograms, moments, counters) is copied back.
+    # The per-trial route (host result arrays, what the reference returns) is timed beside it.
     h2d = ctypes.sizeof(abi.Params)
     S = len(sids)
-    d2h = n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
     ns.NUM_SIMULATIONS = n * ws
     ns.GPU_SEED = args.seed
     e2e_steps = max(1, min(args.steps, 5))
-    parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local, verbose=False)
+    kw = dict(cfg=ns, precision=args.precision, device=local, verbose=False)
+    res = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, summary_only=True, **kw)
+    res.table()
+    d2h = res.d2h_bytes
     barrier()
     t0 = time.perf_counter()
     call_ms = []
     for _ in range(e2e_steps):
         tc = time.perf_counter()
-        res = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, cfg=ns, precision=args.precision, device=local,
-                                         verbose=False)
-        med = float(np.mean(res[sids[0]].final_wealth))       # the step's result is read on the host
+        res = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, summary_only=True, **kw)
+        rows = res.table()                                           # the step's result is read on the host
+        med = float(rows[0]["median"])
         call_ms.append(round(1e3 * (time.perf_counter() - tc), 3))
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_launches = e2e_steps
+    e2e_launches = 2 * e2e_steps + (e2e_steps if ws > 1 else 0)
+    # per-trial route: every trial's results copied to host arrays (bounded: at most 2e7 trials per rank)
+    pt = None
+    if n <= 20_000_000:
+        d2h_pt = n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
+        parallel_monte_carlo_fixed(sids, wl["years"], model, {}, **kw)
+        barrier()
+        t1 = time.perf_counter()
+        pt_steps = max(1, min(args.steps, 2))
+        for _ in range(pt_steps):
+            r2 = parallel_monte_carlo_fixed(sids, wl["years"], model, {}, **kw)
+            mean_w = float(np.mean(r2[sids[0]].final_wealth))
+        barrier()
+        pt = {"value": ws * n * T * pt_steps / (time.perf_counter() - t1), "unit": UNIT, "d2h_bytes_per_step": d2h_pt,
+              "steps": pt_steps, "mean_final_wealth": mean_w,
+              "api": "parallel_monte_carlo_fixed(...): host result arrays out (library's pinned staging buffer)"}
+        e2e_launches += pt_steps
 
     t = torch.tensor([total_ms, kern_ms, e2e_s], dtype=torch.float64, device=dev)
     if ws > 1:
@@ -318,7 +384,7 @@ def run_b200(args):
         sm_count = info["sm_count"]
         peak_lane = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e12               # T lane-ops/s at max clock
         achieved = n * T * wl["lane_ops"] / (kern_ms * 1e-3) / 1e12
-        out_bytes = d2h
+        out_bytes = n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
         ncu_c = {}
         try:
             ncu_c = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json"))).get(args.workload, {})
@@ -339,10 +405,12 @@ def run_b200(args):
                                   "scratch_bytes": info["scratch_bytes"]}},
             "clocks": clocks,
             "e2e": {"value": ws * n * T * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed: parameter dicts in, host result arrays out "
-                           "(engine handle cached across calls; results staged through the library's pinned buffer)",
-                    "steps": e2e_steps, "mean_final_wealth": med, "rank0_call_ms": call_ms},
+                    "api": "letf_monte_carlo_b200.parallel_monte_carlo_fixed(..., summary_only=True).table(): parameter dicts in, "
+                           "summary table out on the host (reduction + cross-rank exchange inside the call; engine handle "
+                           "cached across calls)",
+                    "steps": e2e_steps, "median_final_wealth_top_row": med, "rank0_call_ms": call_ms, "per_trial_route": pt},
             "gpu_launches": launches + e2e_launches,
+            "summary_check": summary_check,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
                          "traffic": traffic, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
                          "issue_slot_frac_executed": (n * T * exe / (kern_ms * 1e-3) / 1e12 / peak_lane) if exe else None,
@@ -363,6 +431,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{nt} trials x {T} days of the same workload in {dt:.1f} s, oracle/letf_oracle.c "
                                               f"incl. its own CPU random draws, {threads} threads"}
+            line["cpu_baseline_numpy"] = numpy_reference_leg(args.workload, wl["years"], threads)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

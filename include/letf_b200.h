@@ -335,6 +335,15 @@ int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_t
  * into `summary` (so several launches / trial ranges can be folded); letf_summary_reset zeroes the
  * bins, moments and counters and sets the extrema to +/-inf. */
 int letf_summary_reset(LetfEngine* e, void* stream, const LetfSummary* summary);
+
+/* The exchange step of a multi-GPU run (reporting.py:358-376 consumes the result).  A summary can live in ONE
+ * packed device buffer of 8-byte words, [hist S*3*LETF_HIST_BINS | counters S*4 | moments S*3*2 | extrema S*3*2]
+ * (letf_summary_words(S) words; the LetfSummary pointers then point into it), so that the ranks exchange it with a single
+ * all-gather.  letf_summary_combine folds `world` gathered packed summaries (device, [world][words]) into `dst_packed`
+ * (device, words): bins / counters / moments summed, extrema min / max.  One kernel, no host round trip. */
+int64_t letf_summary_words(int n_strategies);
+int letf_summary_combine(LetfEngine* e, void* stream, const void* gathered, int world, int n_strategies,
+                         void* dst_packed);
 int letf_reduce(LetfEngine* e, void* stream, const LetfOutputs* out, int64_t n_trials,
                 const LetfSummary* summary);
 
@@ -372,6 +381,7 @@ typedef struct LetfSeries {
   const double* tlt_ret;
   const double* vix;
   const int32_t* regime;
+  const double* cash_ret;                 /* Cash_Ret column (strategy.py:138 ...); NULL: the regime's cash rate / 252 (engine.py:544) */
 } LetfSeries;
 int letf_run_strategies(LetfEngine* e, void* stream, const LetfSeries* series,
                         const LetfOutputs* out);

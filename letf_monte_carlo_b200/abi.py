@@ -176,7 +176,7 @@ class Series(C.Structure):
     _fields_ = [
         ("n_paths", C.c_int64), ("sim_days", C.c_int32), ("pad", C.c_int32),
         ("asset_ret", C.c_void_p * N_ASSETS), ("tlt_ret", C.c_void_p), ("vix", C.c_void_p),
-        ("regime", C.c_void_p),
+        ("regime", C.c_void_p), ("cash_ret", C.c_void_p),
     ]
 
 
@@ -184,7 +184,7 @@ ENGINE_SYMBOLS = (
     "letf_create", "letf_destroy", "letf_last_error", "letf_abi_version", "letf_run",
     "letf_run_host", "letf_summary_reset", "letf_reduce", "letf_trade_list_host", "letf_trade_lists_host",
     "letf_equity_curve_host", "letf_run_strategy_curve_host", "letf_launch_info",
-    "letf_run_strategies", "letf_nearest_psd3",
+    "letf_run_strategies", "letf_nearest_psd3", "letf_summary_words", "letf_summary_combine",
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -240,6 +240,10 @@ def load_engine_library(path: str | None = None):
     lib.letf_run_strategies.restype = i32
     lib.letf_nearest_psd3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.letf_nearest_psd3.restype = i32
+    lib.letf_summary_words.argtypes = [i32]
+    lib.letf_summary_words.restype = i64
+    lib.letf_summary_combine.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.letf_summary_combine.restype = i32
     if lib.letf_abi_version() != ABI_VERSION:
         raise EngineLibraryMissing(f"{p}: ABI version {lib.letf_abi_version()} != {ABI_VERSION}; rebuild")
     if path is None:

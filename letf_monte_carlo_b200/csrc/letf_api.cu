@@ -34,6 +34,7 @@ const KernelEntry* kernel_at(int i) { return &registry()[i]; }
 cudaError_t launch_reduce(const LetfOutputs& out, const LetfSummary& sm, int64_t n, int n_strat, double w0,
                           double years, int sm_count, cudaStream_t st);
 cudaError_t launch_summary_reset(const LetfSummary& sm, int n_strat, cudaStream_t st);
+cudaError_t launch_summary_combine(const void* gathered, int world, int n_strat, void* dst, cudaStream_t st);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -426,6 +427,21 @@ int letf_reduce(LetfEngine* e, void* stream, const LetfOutputs* out, int64_t n_t
   return LETF_OK;
 }
 
+int64_t letf_summary_words(int n_strategies) {
+  const int64_t S = n_strategies > 0 ? n_strategies : 1;
+  return S * (LETF_N_METRICS * LETF_HIST_BINS + 4 + 2 * LETF_N_METRICS * 2);
+}
+
+int letf_summary_combine(LetfEngine* e, void* stream, const void* gathered, int world, int n_strategies, void* dst_packed) {
+  if (!e || !gathered || !dst_packed) return fail(LETF_ERR_INVALID, "null argument");
+  if (world < 1 || n_strategies < 1) return fail(LETF_ERR_INVALID, "bad world size / strategy count");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  CK(launch_summary_combine(gathered, world, n_strategies, dst_packed, (cudaStream_t)stream));
+  e->info.aux_launches = 1;
+  return LETF_OK;
+}
+
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info) {
   if (!e || !info) return fail(LETF_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(e->mu);
@@ -757,7 +773,7 @@ int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* hs, int strate
   CK(cudaSetDevice(e->device));
   // upload the frame's columns into the tape staging buffer (unused in this mode)
   const size_t T = (size_t)hs->sim_days, col8 = align256(8 * (T ? T : 1)), col4 = align256(4 * (T ? T : 1));
-  cudaError_t ce = e->stage_tape.reserve(col8 * (LETF_N_ASSETS + 2) + col4);
+  cudaError_t ce = e->stage_tape.reserve(col8 * (LETF_N_ASSETS + 3) + col4);
   if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "series staging"); }
   char* base = (char*)e->stage_tape.p;
   LetfSeries ds; memset(&ds, 0, sizeof(ds));
@@ -774,6 +790,7 @@ int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* hs, int strate
   ds.tlt_ret = (const double*)up(hs->tlt_ret, 8 * T, col8);
   ds.vix = (const double*)up(hs->vix, 8 * T, col8);
   ds.regime = (const int32_t*)up(hs->regime, 4 * T, col4);
+  ds.cash_ret = (const double*)up(hs->cash_ret, 8 * T, col8);
   CK(up_err);
   return replay_one(e, kMarketSeries, 0, 0, strategy, LETF_RNG_PHILOX, nullptr, &ds, hs->sim_days, curve, num_trades, cap, day, asset,
                     action, shares, price, count);

@@ -777,6 +777,7 @@ struct Trial {
     double sq_er[MARKET == kMarketSeries ? kSeriesAhead : 1][kAssets];
     double sq_vix[MARKET == kMarketSeries ? kSeriesAhead : 1], sq_tlt[MARKET == kMarketSeries ? kSeriesAhead : 1];
     int sq_reg[MARKET == kMarketSeries ? kSeriesAhead : 1];
+    R sq_cash[MARKET == kMarketSeries ? kSeriesAhead : 1];          // the frame's Cash_Ret column, when it has one
     auto series_fetch = [&](int slot, int day) {
       const int64_t o = (int64_t)day * ka.series.n_paths + col;
 #pragma unroll
@@ -784,6 +785,7 @@ struct Trial {
       sq_vix[slot] = ka.series.vix ? ka.series.vix[o] : 15.0;
       sq_tlt[slot] = ka.series.tlt_ret ? ka.series.tlt_ret[o] : 0.0;
       sq_reg[slot] = ka.series.regime ? ka.series.regime[o] : 0;
+      sq_cash[slot] = ka.series.cash_ret ? (R)ka.series.cash_ret[o] : (R)0;
     };
     if (MARKET == kMarketSeries) {
 #pragma unroll
@@ -814,10 +816,11 @@ struct Trial {
       // series mode: take day i from the front of the prefetch queue, shift, request day i + kSeriesAhead
       R s_er[kAssets];
       int s_reg = 0;
+      R s_cash = (R)0;
       if (MARKET == kMarketSeries) {
 #pragma unroll
         for (int a = 0; a < kAssets; a++) s_er[a] = (R)sq_er[0][a];
-        vix = (R)sq_vix[0]; s_reg = sq_reg[0];
+        vix = (R)sq_vix[0]; s_reg = sq_reg[0]; s_cash = sq_cash[0];
       }
       const int reg = MARKET == kMarketSeries ? s_reg : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
@@ -827,7 +830,7 @@ struct Trial {
         for (int d = 0; d + 1 < kSeriesAhead; d++) {
 #pragma unroll
           for (int a = 0; a < kAssets; a++) sq_er[d][a] = sq_er[d + 1][a];
-          sq_vix[d] = sq_vix[d + 1]; sq_tlt[d] = sq_tlt[d + 1]; sq_reg[d] = sq_reg[d + 1];
+          sq_vix[d] = sq_vix[d + 1]; sq_tlt[d] = sq_tlt[d + 1]; sq_reg[d] = sq_reg[d + 1]; sq_cash[d] = sq_cash[d + 1];
         }
         if (i + kSeriesAhead < T) series_fetch(kSeriesAhead - 1, i + kSeriesAhead);
       } else if (MARKET == kMarketBoot) {
@@ -1000,7 +1003,7 @@ struct Trial {
           } else ddT.step_ret(tlt);
         }
       }
-      const R cash = p.cash_daily[reg];
+      const R cash = (MARKET == kMarketSeries && ka.series.cash_ret) ? s_cash : p.cash_daily[reg];
       const R Pspy = NA == kAssets ? (R)(cp[NA == kAssets ? 4 : 0] * 100.0) : (R)100;
 
       // ---- signals as of yesterday, then roll the windows forward with today's values

@@ -13,8 +13,10 @@
 
 namespace letf {
 
-// K10: bitmask of the slots whose tracking-error innovations are t(10) (the others are t(5))
-template <int NS, int NA, int U, int K10 = 0>
+// K10: bitmask of the slots whose tracking-error innovations are t(10) (the others are t(5)); NACT: active (compacted)
+// slots; TE = false: every active series has tracking_error_base == 0 (the frictionless vol-drag shape of
+// validation.py:33-57, BASELINE config 1) - no tracking-error block is drawn at all
+template <int NS, int NA, int U, int K10 = 0, int NACT = NA, bool TE = true>
 struct FastLayers {
   typedef float R;
   typedef Mth<float> M;
@@ -31,26 +33,28 @@ struct FastLayers {
       key[u].k0 = (uint32_t)ka.seed; key[u].k1 = (uint32_t)(ka.seed >> 32);
       key[u].t0 = (uint32_t)sim_id; key[u].t1 = (uint32_t)((uint64_t)sim_id >> 32);
     }
-    R te_prev[U][NA], bias[U][NA], q[U][NA], qmin[U][NA], chk[U];
-    double cp[U][NA];
+    R te_prev[U][NACT], bias[U][NACT], q[U][NACT], qmin[U][NACT], chk[U];
+    double cp[U][NACT];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       chk[u] = 0.0f;
 #pragma unroll
-      for (int a = 0; a < NA; a++) { te_prev[u][a] = 0.0f; bias[u][a] = 0.0f; q[u][a] = INFINITY; qmin[u][a] = 1.0f; cp[u][a] = 1.0; }
+      for (int a = 0; a < NACT; a++) { te_prev[u][a] = 0.0f; bias[u][a] = 0.0f; q[u][a] = INFINITY; qmin[u][a] = 1.0f; cp[u][a] = 1.0; }
     }
     const R vix = p.const_vix;
     const R vrmult = clipx(M::sqrt_(vix * 0.05f), 0.5f, 1.5f) * 1.0f;      // regime 0 (engine.py:178-181)
-    uint32_t streams[NA];
+    uint32_t streams[NACT];
 #pragma unroll
-    for (int a = 0; a < NA; a++) streams[a] = STREAM_TE0 + (uint32_t)p.act_id[a];
+    for (int a = 0; a < NACT; a++) streams[a] = STREAM_TE0 + (uint32_t)p.act_id[a];
     const R alpha = (R)(2.0 / 127.0);
 
     // one simulated day of all U trials; (wa, wb) = the two market words of the day
     auto day = [&](const int i, const uint32_t (&wa)[U], const uint32_t (&wb)[U]) {
-      U4 blk[U][NA];
+      U4 blk[U][NACT];
+      if (TE) {
 #pragma unroll
-      for (int u = 0; u < U; u++) rng_blocks<NA>(key[u], (uint32_t)i, streams, blk[u]);
+        for (int u = 0; u < U; u++) rng_blocks<NACT>(key[u], (uint32_t)i, streams, blk[u]);
+      }
       const R vrlive = i >= 1 ? vrmult : 0.0f;          // no tracking error on day 0 (engine.py:184)
       R spy[U], qqq[U];
 #pragma unroll
@@ -62,19 +66,24 @@ struct FastLayers {
         chk[u] = fmaf(spy[u], 0.0f, chk[u]); chk[u] = fmaf(qqq[u], 0.0f, chk[u]);
       }
 #pragma unroll
-      for (int a = 0; a < NA; a++) {
+      for (int a = 0; a < NACT; a++) {
         const DevAsset<R>& ap = p.act[a];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const R un = fmaf(ap.w_spy, spy[u], ap.w_qqq * qqq[u]);
           const R lev = ap.lev * un - ap.carry_const;
-          const R innov = ((K10 >> a) & 1) ? student_t10<R>(blk[u][a]) : student_t5<R>(blk[u][a]);
-          const R ds = un < 0.0f ? ap.te_down : 0.98f;
-          const R mm = (1.0f + 0.3f * fabsf(un)) * ds;
-          const R te_raw = ap.te_rho * te_prev[u][a] + (innov * vrlive) * (ap.te_scale * mm);
-          te_prev[u][a] = te_raw;
-          bias[u][a] = alpha * te_raw + (1.0f - alpha) * bias[u][a];
-          const R er = clipfast(lev + (te_raw - bias[u][a]), -0.999f, 10.0f);
+          R er;
+          if (TE) {
+            const R innov = ((K10 >> a) & 1) ? student_t10<R>(blk[u][a]) : student_t5<R>(blk[u][a]);
+            const R ds = un < 0.0f ? ap.te_down : 0.98f;
+            const R mm = (1.0f + 0.3f * fabsf(un)) * ds;
+            const R te_raw = ap.te_rho * te_prev[u][a] + (innov * vrlive) * (ap.te_scale * mm);
+            te_prev[u][a] = te_raw;
+            bias[u][a] = alpha * te_raw + (1.0f - alpha) * bias[u][a];
+            er = clipfast(lev + (te_raw - bias[u][a]), -0.999f, 10.0f);
+          } else {
+            er = clipfast(lev, -0.999f, 10.0f);       // te_scale == 0: the AR(1) residual and its EMA bias are identically 0
+          }
           cp[u][a] = ::fma(cp[u][a], (double)er, cp[u][a]);
           q[u][a] = fminf(1.0f, fmaf(q[u][a], er, q[u][a]));
           qmin[u][a] = fminf(qmin[u][a], q[u][a]);
@@ -111,13 +120,13 @@ struct FastLayers {
       if (T > 0 && (!isfinite_(vix) || vix <= 0.0f)) flags |= LETF_FLAG_BAD_VIX;
       if (chk[u] != 0.0f) flags |= LETF_FLAG_NONFINITE_RET;
 #pragma unroll
-      for (int a = 0; a < NA; a++) if (T > 0 && !(cp[u][a] > 0.0 && isfinite_(cp[u][a]))) bad = true;
+      for (int a = 0; a < NACT; a++) if (T > 0 && !(cp[u][a] > 0.0 && isfinite_(cp[u][a]))) bad = true;
       if (T == 0 || bad || !(vix >= 5.0f) || !(vix <= 120.0f)) flags |= LETF_FLAG_REPAIRED;
       for (int s = 0; s < NS; s++) {
         if (s >= p.n_strat) break;
         double c = 1.0; R qm = 1.0f;
 #pragma unroll
-        for (int a = 0; a < NA; a++) if (p.act_id[a] == p.strat[s].asset) { c = cp[u][a]; qm = qmin[u][a]; }
+        for (int a = 0; a < NACT; a++) if (p.act_id[a] == p.strat[s].asset) { c = cp[u][a]; qm = qmin[u][a]; }
         ka.out.final_wealth[(int64_t)s * N + col[u]] = T > 0 ? (double)p.W0 * c : 0.0;
         ka.out.max_dd[(int64_t)s * N + col[u]] = T > 1 ? (double)(1.0f - qm) : 0.0;
         ka.out.num_trades[(int64_t)s * N + col[u]] = 0;
@@ -132,15 +141,22 @@ struct FastLayers {
   }
 };
 
-// DevParams::fast_layers codes with a compiled-in straight-line loop: all t(5) (BASELINE config 2) and
-// "last slot t(10)" (config 5: UPRO / SSO / SPY).  Any other admitted pattern runs the general loop.
-template <int NA> LETF_HD constexpr bool fast_pattern_compiled(int code) { return code == 1 || code == 1 + (1 << (NA - 1)); }
+// DevParams::fast_layers = (1 + mask of the t(10) slots) | n_act << 8 | (no tracking error) << 12.  Shapes with a
+// compiled-in straight-line loop: all NA slots t(5) (BASELINE config 2), "last slot t(10)" (config 5: UPRO / SSO / SPY),
+// and one frictionless series (config 1).  Any other admitted shape runs the general loop.
+LETF_HD constexpr int fast_layers_code(int nact, int k10, bool no_te) { return (1 + k10) | (nact << 8) | ((no_te ? 1 : 0) << 12); }
+template <int NA> LETF_HD constexpr bool fast_pattern_compiled(int code) {
+  return code == fast_layers_code(NA, 0, false) || code == fast_layers_code(NA, 1 << (NA - 1), false) ||
+         code == fast_layers_code(1, 0, true) || code == fast_layers_code(1, 1, true);
+}
 
 template <int NS, int NA, int U>
 LETF_HD void fast_layers_run(const KArgs<float, NS, NA>& ka, const int64_t (&trial)[U], const int64_t (&col)[U],
                              const bool (&live)[U]) {
-  if (ka.p.fast_layers == 1) FastLayers<NS, NA, U, 0>::run(ka, trial, col, live);
-  else FastLayers<NS, NA, U, 1 << (NA - 1)>::run(ka, trial, col, live);
+  const int code = ka.p.fast_layers;
+  if (code == fast_layers_code(NA, 0, false)) FastLayers<NS, NA, U, 0>::run(ka, trial, col, live);
+  else if (code == fast_layers_code(NA, 1 << (NA - 1), false)) FastLayers<NS, NA, U, 1 << (NA - 1)>::run(ka, trial, col, live);
+  else FastLayers<NS, NA, U, 0, 1, false>::run(ka, trial, col, live);
 }
 
 }  // namespace letf

@@ -355,12 +355,13 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
   }
   d.need_tlt = d.bench_tlt;
   for (int a = 0; a < kAssets; a++) if (((s.asset_mask >> a) & 1) && s.assets[a].underlying == 2) d.need_tlt = 1;
-  d.fast_layers = (NA < kAssets) && !d.need_tlt && !d.has_funding && s.market_mode == LETF_MARKET_NORMAL;
+  bool fast = (NA < kAssets) && !d.need_tlt && !d.has_funding && s.market_mode == LETF_MARKET_NORMAL &&
+              !(s.random_start && s.buffer_days > 0);      // the straight-line loop keys its draws by the simulated day
   d.n_act = 0;
   for (int a = 0; a < kAssets; a++) {
     const bool on = (s.asset_mask >> a) & 1;
     if (on && ((d.assets[a].te_fast_k != 5 && d.assets[a].te_fast_k != 10) || d.assets[a].te_clip > (R)0 ||
-               !((d.bench_mask >> a) & 1))) d.fast_layers = 0;
+               !((d.bench_mask >> a) & 1))) fast = false;
     if (NA == kAssets) {
       d.act[a] = d.assets[a]; d.act_id[a] = a; d.act_on[a] = on; d.act_bench[a] = (d.bench_mask >> a) & 1;
       d.n_act = kAssets;
@@ -369,8 +370,12 @@ inline void convert_params(const LetfParams& s, const int32_t* const dev_dur[2],
       d.act[j] = d.assets[a]; d.act_id[j] = a; d.act_on[j] = 1; d.act_bench[j] = (d.bench_mask >> a) & 1;
     }
   }
-  if (d.n_act != NA) d.fast_layers = 0;
-  if (d.fast_layers) for (int j = 0; j < NA; j++) if (d.act[j].te_fast_k == 10) d.fast_layers += 1 << j;
+  d.fast_layers = 0;
+  if (fast && d.n_act >= 1) {
+    int k10 = 0; bool no_te = true;
+    for (int j = 0; j < d.n_act; j++) { if (d.act[j].te_fast_k == 10) k10 |= 1 << j; if (d.act[j].te_scale != (R)0) no_te = false; }
+    d.fast_layers = (1 + k10) | (d.n_act << 8) | ((no_te ? 1 : 0) << 12);      // letf_fast.cuh fast_layers_code
+  }
   d.fast_joint = fast_joint_shape(s, NA);
 }
 #endif  // LETF_DEVICE_ONLY

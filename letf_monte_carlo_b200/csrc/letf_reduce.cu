@@ -166,3 +166,36 @@ cudaError_t launch_summary_reset(const LetfSummary& sm, int n_strat, cudaStream_
   return cudaGetLastError();
 }
 }  // namespace letf
+
+// ---- exchange step: fold `world` packed summaries (one per rank, gathered over NCCL) into one --------------------------
+namespace letf {
+__global__ void letf_summary_combine_kernel(const unsigned long long* __restrict__ g, int world, int64_t words, int64_t n_int,
+                                            int64_t n_mom, unsigned long long* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= words) return;
+  if (i < n_int) {                         // histogram bins and counters: integer sums
+    unsigned long long a = 0;
+    for (int r = 0; r < world; r++) a += g[(int64_t)r * words + i];
+    dst[i] = a;
+  } else if (i < n_int + n_mom) {          // sum x, sum x^2 (rank order is fixed: the result is the same on every rank)
+    double a = 0.0;
+    for (int r = 0; r < world; r++) a += __longlong_as_double((long long)g[(int64_t)r * words + i]);
+    dst[i] = (unsigned long long)__double_as_longlong(a);
+  } else {                                 // extrema [.., 2]: even word = min, odd word = max
+    const bool is_max = ((i - n_int - n_mom) & 1) != 0;
+    double a = is_max ? -INFINITY : INFINITY;
+    for (int r = 0; r < world; r++) {
+      const double v = __longlong_as_double((long long)g[(int64_t)r * words + i]);
+      a = is_max ? fmax(a, v) : fmin(a, v);
+    }
+    dst[i] = (unsigned long long)__double_as_longlong(a);
+  }
+}
+cudaError_t launch_summary_combine(const void* gathered, int world, int n_strat, void* dst, cudaStream_t st) {
+  const int64_t n_int = (int64_t)n_strat * (LETF_N_METRICS * LETF_HIST_BINS + 4), n_mom = (int64_t)n_strat * LETF_N_METRICS * 2;
+  const int64_t words = n_int + 2 * n_mom;
+  letf_summary_combine_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>((const unsigned long long*)gathered, world, words,
+                                                                                n_int, n_mom, (unsigned long long*)dst);
+  return cudaGetLastError();
+}
+}  // namespace letf

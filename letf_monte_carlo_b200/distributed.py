@@ -51,3 +51,33 @@ def allreduce_summary(hist, moments, extrema, counters, group=None):
     dist.all_reduce(packed, op=dist.ReduceOp.MAX, group=group)
     packed[..., 0].neg_()
     extrema.copy_(packed)
+
+
+def exchange_summary(summary, engine=None, group=None):
+    """The exchange step on a packed `DeviceSummary`: ONE all-gather of the packed buffer (NCCL over NVLink) and one
+    combine kernel (`letf_summary_combine`: integer sums for bins / counters, fp64 sums for the moments, min / max for the
+    extrema) - instead of three all-reduces plus packing kernels.  CPU tensors (the gloo tests of the host logic) are
+    combined with torch ops."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return summary
+    ws = dist.get_world_size(group)
+    buf = summary.buf
+    gathered = torch.empty((ws, buf.numel()), dtype=buf.dtype, device=buf.device)
+    if buf.is_cuda:
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+        if engine is None:
+            raise RuntimeError("exchange_summary on device tensors needs the PathEngine (letf_summary_combine)")
+        engine.combine_summaries(gathered, ws, summary)
+        return summary
+    dist.all_gather(list(gathered.unbind(0)), buf, group=group)
+    nh, nc = summary.hist.numel(), summary.counters.numel()
+    nm = summary.moments.numel()
+    buf[:nh + nc] = gathered[:, :nh + nc].sum(0)
+    f = gathered[:, nh + nc:].view(torch.float64)
+    buf[nh + nc:nh + nc + nm] = f[:, :nm].sum(0).view(torch.int64)
+    ex = f[:, nm:].view(ws, -1, 2)
+    out = torch.stack([ex[:, :, 0].amin(0), ex[:, :, 1].amax(0)], dim=1).reshape(-1)
+    buf[nh + nc + nm:] = out.view(torch.int64)
+    return summary

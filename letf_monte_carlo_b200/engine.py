@@ -68,18 +68,24 @@ class DeviceTape:
 
 
 class DeviceSummary:
-    """Histogram / moment buffers of `letf_reduce` (sum/min/max-reducible across GPUs)."""
+    """Histogram / moment buffers of `letf_reduce` (sum/min/max-reducible across GPUs).
+
+    One packed buffer of 8-byte words, [hist S*3*4096 | counters S*4 | moments S*3*2 | extrema S*3*2]
+    (include/letf_b200.h `letf_summary_words`); `hist`, `counters`, `moments`, `extrema` are views into it, so the
+    ranks of a multi-GPU run exchange the whole summary with one all-gather (distributed.exchange_summary)."""
 
     def __init__(self, n_strategies: int, device, lo=(-20.0, -1.0, 0.0), hi=(10.0, 2.0, 1.0), bench_strategy=-1):
         import torch
         S = max(int(n_strategies), 1)
         self.n_strategies = int(n_strategies)
-        self.hist = torch.zeros((S, abi.N_METRICS, abi.HIST_BINS), dtype=torch.int64, device=device)
-        self.moments = torch.zeros((S, abi.N_METRICS, 2), dtype=torch.float64, device=device)
-        self.extrema = torch.zeros((S, abi.N_METRICS, 2), dtype=torch.float64, device=device)
+        nh, nc, nm = S * abi.N_METRICS * abi.HIST_BINS, S * 4, S * abi.N_METRICS * 2
+        self.buf = torch.zeros(nh + nc + 2 * nm, dtype=torch.int64, device=device)
+        self.hist = self.buf[:nh].view(S, abi.N_METRICS, abi.HIST_BINS)
+        self.counters = self.buf[nh:nh + nc].view(S, 4)
+        self.moments = self.buf[nh + nc:nh + nc + nm].view(torch.float64).view(S, abi.N_METRICS, 2)
+        self.extrema = self.buf[nh + nc + nm:].view(torch.float64).view(S, abi.N_METRICS, 2)
         self.extrema[:, :, 0] = float("inf")
         self.extrema[:, :, 1] = float("-inf")
-        self.counters = torch.zeros((S, 4), dtype=torch.int64, device=device)
         self.lo, self.hi = tuple(map(float, lo)), tuple(map(float, hi))
         self.bench_strategy = int(bench_strategy)
 
@@ -121,6 +127,15 @@ class PathEngine:
         if rc == abi.ERR_NONFINITE:
             raise NonFiniteTrials(msg)
         raise EngineError(rc, msg)
+
+    @staticmethod
+    def raise_if_nonfinite(flags):
+        """the device-buffer route's counterpart of letf_run_host's check: the reference raises ValueError out of a trial
+        with non-finite returns or VIX <= 0 (engine.py:486-498)"""
+        bad = int(np.count_nonzero(np.asarray(flags) & (abi.FLAG_NONFINITE_RET | abi.FLAG_BAD_VIX)))
+        if bad:
+            raise NonFiniteTrials(f"{bad} of {len(flags)} trials generated non-finite returns or VIX <= 0 "
+                                  f"(reference raises ValueError, engine.py:486-498)")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -177,7 +192,7 @@ class PathEngine:
         self._check(rc)
         return out
 
-    def run_strategies(self, asset_ret: dict, *, tlt_ret=None, vix=None, regime=None, journal: bool = False,
+    def run_strategies(self, asset_ret: dict, *, tlt_ret=None, vix=None, regime=None, cash_ret=None, journal: bool = False,
                        stream=None) -> DeviceOutputs:
         """Strategy rules on caller-supplied series (`run_strategy_fixed` seam, strategy.py:55).
         asset_ret: {asset name: [T][n] array-like}; all arrays day-major."""
@@ -199,6 +214,8 @@ class PathEngine:
             assert tuple(t.shape) == (T, n)
             s.asset_ret[abi.ASSET_INDEX[name]] = t.data_ptr()
         tl, vx, rg = up(tlt_ret, torch.float64), up(vix, torch.float64), up(regime, torch.int32)
+        cr = up(cash_ret, torch.float64)
+        s.cash_ret = cr.data_ptr() if cr is not None else None
         s.tlt_ret = tl.data_ptr() if tl is not None else None
         s.vix = vx.data_ptr() if vx is not None else None
         s.regime = rg.data_ptr() if rg is not None else None
@@ -219,6 +236,14 @@ class PathEngine:
         self._check(rc)
         self.launches += 1 if n > 0 else 0
         return summary
+
+    def combine_summaries(self, gathered, world: int, summary: DeviceSummary, stream=None):
+        """fold `world` gathered packed summaries ([world][words] int64 device tensor) into `summary` (one kernel)"""
+        assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == world * summary.buf.numel()
+        rc = self._lib.letf_summary_combine(self._h, self._stream(stream), gathered.data_ptr(), int(world),
+                                            max(self.n_strategies, 1), summary.buf.data_ptr())
+        self._check(rc)
+        self.launches += 1
 
     def reset_summary(self, summary: DeviceSummary, stream=None):
         self._check(self._lib.letf_summary_reset(self._h, self._stream(stream), C.byref(summary.as_struct())))
@@ -273,7 +298,7 @@ class PathEngine:
         self.launches += 1
         return curve[:int(self.params.sim_days)]
 
-    def run_strategy_curve(self, frame: dict, strategy: int, *, tlt_ret=None, vix=None, regime=None, cap: int = 4096):
+    def run_strategy_curve(self, frame: dict, strategy: int, *, tlt_ret=None, vix=None, regime=None, cash_ret=None, cap: int = 4096):
         """`run_strategy_fixed` on ONE caller-supplied frame (strategy.py:55): frame = {asset name: [T] returns}.
         -> (equity curve [T], num_trades, Trade_List rows for a taxable id)"""
         cols = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in frame.items()}
@@ -286,6 +311,13 @@ class PathEngine:
         tl = None if tlt_ret is None else np.ascontiguousarray(np.asarray(tlt_ret, dtype=np.float64))
         vx = None if vix is None else np.ascontiguousarray(np.asarray(vix, dtype=np.float64))
         rg = None if regime is None else np.ascontiguousarray(np.asarray(regime, dtype=np.int32))
+        cr = None if cash_ret is None else np.ascontiguousarray(np.asarray(cash_ret, dtype=np.float64))
+        s.cash_ret = cr.ctypes.data if cr is not None else None
+        for name, a in (("tlt_ret", tl), ("vix", vx), ("regime", rg), ("cash_ret", cr)):
+            if a is not None and a.shape != (T,):
+                raise ValueError(f"{name} has shape {a.shape}, the frame has {T} rows (the library reads T elements of every column)")
+        if rg is not None and rg.size and (rg.min() < 0 or rg.max() > 1):
+            raise ValueError("regime path values must be 0 or 1 (they index the per-regime cash rate and spread cost)")
         s.tlt_ret = tl.ctypes.data if tl is not None else None
         s.vix = vx.ctypes.data if vx is not None else None
         s.regime = rg.ctypes.data if rg is not None else None

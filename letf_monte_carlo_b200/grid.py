@@ -11,7 +11,7 @@ from typing import Mapping, Sequence
 import numpy as np
 
 from . import abi
-from .distributed import allreduce_summary, shard_range, world
+from .distributed import exchange_summary, shard_range, world
 from .params import build_params
 from .summary import PERCENTILES, histogram_quantile
 
@@ -56,7 +56,7 @@ class HorizonGrid:
             eng.reset_summary(sm)
             eng.reduce(out, sm, n_trials=n)
             if reduce_across_ranks and ws > 1:
-                allreduce_summary(sm.hist, sm.moments, sm.extrema, sm.counters)
+                exchange_summary(sm, engine=eng)
         return self
 
     def table(self, initial_capital: float = 10000.0) -> list[dict]:

@@ -27,14 +27,32 @@ from .trade import TAXABLE_IDS
 
 
 class TrialResult(Mapping):
-    """One trial of one strategy; behaves like the reference's result dict (engine.py:592-603)."""
+    """One trial of one strategy; behaves like the reference's result dict (engine.py:592-603).
+
+    A strategy whose equity ended non-finite is reported the way the reference reports a strategy that raised inside
+    `run_strategy_fixed` (engine.py:606-617): a zero-wealth record carrying an 'Error' key, so that downstream
+    `r['Final_Wealth']` / `r.get('Max_DD', 0)` keep working and the failure stays visible.  (The reference's 300 s
+    per-trial timeout and its `None`-skip, mc_runner.py:169,197-208, have no counterpart: a launch either completes
+    or raises.)"""
     _KEYS = ("Final_Wealth", "Num_Trades", "Trades_Per_Year", "Max_DD", "Metadata", "Trade_List")
 
     def __init__(self, parent: "StrategyResults", i: int):
         self._p, self._i = parent, i
 
+    def _failed(self):
+        return not np.isfinite(self._p.final_wealth[self._i])
+
     def __getitem__(self, k):
         p, i = self._p, self._i
+        if self._failed():
+            if k == "Error":
+                return "non-finite strategy equity"
+            if k in ("Final_Wealth", "Max_DD", "Trades_Per_Year"):
+                return 0.0
+            if k == "Num_Trades":
+                return 0
+            if k == "Trade_List" and p.sid in p.run.taxable_ids:
+                return []
         if k == "Final_Wealth":
             return float(p.final_wealth[i])
         if k == "Max_DD":
@@ -50,7 +68,8 @@ class TrialResult(Mapping):
         raise KeyError(k)
 
     def __iter__(self):
-        return (k for k in self._KEYS if k != "Trade_List" or self._p.sid in self._p.run.taxable_ids)
+        keys = [k for k in self._KEYS if k != "Trade_List" or self._p.sid in self._p.run.taxable_ids]
+        return iter(keys + (["Error"] if self._failed() else []))
 
     def __len__(self):
         return sum(1 for _ in self)
@@ -61,9 +80,19 @@ class StrategyResults(Sequence):
 
     def __init__(self, run: "MonteCarloRun", sid: str, s: int):
         self.run, self.sid, self.s = run, sid, s
-        self.final_wealth = run.out.final_wealth[s]
-        self.max_dd = run.out.max_dd[s]
-        self.num_trades = run.out.num_trades[s]
+
+    # host views; the device -> host copy of the per-trial arrays happens on first access (MonteCarloRun.out)
+    @property
+    def final_wealth(self):
+        return self.run.out.final_wealth[self.s]
+
+    @property
+    def max_dd(self):
+        return self.run.out.max_dd[self.s]
+
+    @property
+    def num_trades(self):
+        return self.run.out.num_trades[self.s]
 
     def __len__(self):
         return self.run.n_local
@@ -86,15 +115,37 @@ class StrategyResults(Sequence):
 
 
 class MonteCarloRun(dict):
-    """The returned mapping {sid: StrategyResults}; also keeps the launch metadata."""
+    """The returned mapping {sid: StrategyResults}; also keeps the launch metadata.
 
-    def __init__(self, engine, out, strategy_ids, years, seed, first_trial, n_local, n_total, taxable_ids):
+    `out` is either the host arrays `letf_run_host` filled, or - `device_out` given - fetched from the device on first
+    access: a caller that only wants `summary()` never pays the per-trial device -> host copy."""
+
+    def __init__(self, engine, out, strategy_ids, years, seed, first_trial, n_local, n_total, taxable_ids, device_out=None):
         super().__init__()
-        self.engine, self.out, self.years, self.seed = engine, out, float(years), seed
+        self.engine, self._out, self.device_out = engine, out, device_out
+        self.years, self.seed = float(years), seed
         self.first_trial, self.n_local, self.n_total = first_trial, n_local, n_total
         self.taxable_ids = set(taxable_ids)
+        self.strategy_ids = list(strategy_ids)
+        self._summary = None
         for s, sid in enumerate(strategy_ids):
             self[sid] = StrategyResults(self, sid, s)
+
+    @property
+    def out(self):
+        if self._out is None:
+            self._out = self.device_out.to_host()
+            self.engine.raise_if_nonfinite(self._out.flags)
+        return self._out
+
+    def summary(self, benchmark_id: str = "S2"):
+        """`MonteCarloSummary` of this run: reduced on the device (letf_reduce) and exchanged across the ranks."""
+        if self._summary is None:
+            if self.device_out is None:
+                raise RuntimeError("summary() needs the device-resident route: parallel_monte_carlo_fixed(..., summary_only=True) "
+                                   "or device_results=True")
+            self._summary = MonteCarloSummary(self, benchmark_id)
+        return self._summary
 
     def taxable_summary(self, tax_fn=None, tax_config=None, cfg=None, **kw):
         """Rows of the reference's taxable-brokerage table (reporting.py:399-560): <= 50 wealth-ranked trials per
@@ -115,6 +166,66 @@ class MonteCarloRun(dict):
                 "start_offset": int(o.start_offset[i]),
                 "sim_id": int((self.first_trial + i) & ~1) if self.engine.params.antithetic_pairs else int(self.first_trial + i),
                 "engine": "letf_monte_carlo_b200"}
+
+
+class MonteCarloSummary:
+    """Summary statistics of a run, reduced on the device: per (strategy, metric) 4096-bin histograms, moments, extrema and
+    counters (`letf_reduce`), exchanged across the ranks with one all-gather + one combine kernel.  Only these buffers
+    (~0.1 MB per strategy) ever leave the device; `table()` reads the reference's report columns off them
+    (reporting.py:353-388): histogram percentiles (bin-width accuracy) or, with exact=True, np.percentile-exact values of
+    the union of all ranks' trials by histogram-guided selection on the device-resident per-trial arrays."""
+
+    def __init__(self, run: MonteCarloRun, benchmark_id: str = "S2"):
+        from .distributed import exchange_summary
+        eng, dev = run.engine, run.device_out
+        self.run = run
+        bench = run.strategy_ids.index(benchmark_id) if benchmark_id in run.strategy_ids else -1
+        self.sm = eng.new_summary(bench_strategy=bench)
+        eng.reduce(dev, self.sm, n_trials=run.n_local)
+        exchange_summary(self.sm, engine=eng)
+        self._host = None
+
+    def _fetch(self):
+        if self._host is None:
+            b = self.sm.buf.cpu()                                       # the one device -> host copy of this route
+            nh, nc = self.sm.hist.numel(), self.sm.counters.numel()
+            nm = self.sm.moments.numel()
+            S = max(self.sm.n_strategies, 1)
+            f = b[nh + nc:].view(__import__("torch").float64).numpy()
+            self._host = {"hist": b[:nh].numpy().reshape(S, abi.N_METRICS, abi.HIST_BINS), "counters": b[nh:nh + nc].numpy().reshape(S, 4),
+                          "moments": f[:nm].reshape(S, abi.N_METRICS, 2), "extrema": f[nm:].reshape(S, abi.N_METRICS, 2)}
+            valid = self._host["counters"][:, 0]
+            if (valid < self.run.n_total).any():
+                bad = int(self.run.n_total - valid.min())
+                from .engine import NonFiniteTrials
+                raise NonFiniteTrials(f"{bad} of {self.run.n_total} trials generated non-finite returns or VIX <= 0 "
+                                      f"(reference raises ValueError, engine.py:486-498)")
+        return self._host
+
+    @property
+    def d2h_bytes(self):
+        return int(self.sm.buf.numel() * 8)
+
+    def table(self, initial_capital: float = 10000.0, exact: bool = False) -> list[dict]:
+        from .summary import PERCENTILES, global_percentiles, summary_from_histograms
+        h = self._fetch()
+        rows = summary_from_histograms(h["hist"], self.sm.lo, self.sm.hi, h["counters"], initial_capital)
+        years = self.run.years
+        for s, (sid, row) in enumerate(zip(self.run.strategy_ids, rows)):
+            row["id"] = sid
+            row["median"] = row["p50"]
+            if exact:
+                qs = list(PERCENTILES)
+                for q, v in zip(qs, global_percentiles(self.run.device_out.final_wealth[s], qs)):
+                    row[f"p{q}"] = v
+                row["median"] = row["p50"]
+                row["dd_median"] = global_percentiles(self.run.device_out.max_dd[s], [50])[0]
+            row["cagr"] = (row["median"] / initial_capital) ** (1 / years) - 1
+            row["dd"] = row["dd_median"]
+            row["trades"] = row["total_trades"] / max(row["valid"], 1) / years
+            row["mean_log10_growth"] = float(h["moments"][s, 0, 0]) / max(row["valid"], 1)
+        rows.sort(key=lambda r: r["median"], reverse=True)
+        return rows
 
 
 _ENGINES: dict = {}      # (parameter bytes, precision, device) -> PathEngine; the handle owns device scratch worth reusing
@@ -152,16 +263,22 @@ def _engine_for(params, keep, precision, device):
     eng = _ENGINES.get(key)
     if eng is None or eng._h is None:
         while len(_ENGINES) >= _ENGINE_CACHE_MAX:
-            _ENGINES.pop(next(iter(_ENGINES))).close()
+            # drop the cache entry only: earlier MonteCarloRun objects may still hold the engine for their lazy Trade_List /
+            # summary calls; the handle is destroyed when the last reference goes (PathEngine.__del__)
+            _ENGINES.pop(next(iter(_ENGINES)))
         eng = _ENGINES[key] = PathEngine(params, keep, precision=precision, device=dev)
     return eng
 
 
 def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correlation_matrices,
                                historical_df=None, *, cfg=None, precision=None, seed=None, device=None,
-                               verbose=True):
+                               verbose=True, summary_only=False, device_results=False):
     """Reference signature: letf/mc_runner.py:24-25.  `correlation_matrices` is accepted and unused,
-    exactly as in the reference (strategy.py:55 is its only reader and ignores it)."""
+    exactly as in the reference (strategy.py:55 is its only reader and ignores it).
+
+    summary_only=True returns a `MonteCarloSummary` (device-side reduction + cross-rank exchange; no per-trial array
+    leaves the device).  device_results=True returns the usual mapping with the per-trial arrays left on the device and
+    copied to the host lazily, on first access."""
     from .engine import PathEngine
     cfg = _default_cfg if cfg is None else cfg
     if historical_df is not None and getattr(cfg, "USE_BLOCK_BOOTSTRAP", False):
@@ -185,6 +302,10 @@ def parallel_monte_carlo_fixed(strategy_ids, time_horizon, regime_model, correla
         print(f"\n{'=' * 80}\nMONTE CARLO: {n_total:,} sims x {time_horizon}Y  "
               f"[B200 path engine, {precision}, {ws} GPU(s)]\n{'=' * 80}")
     eng = _engine_for(params, keep, precision, device if device is not None else getattr(cfg, "GPU_DEVICE", None))
+    if summary_only or device_results:
+        dev = eng.run(hi - lo, first_trial=lo, seed=seed)
+        run = MonteCarloRun(eng, None, strategy_ids, time_horizon, seed, lo, hi - lo, n_total, TAXABLE_IDS, device_out=dev)
+        return run.summary() if summary_only else run
     # raises NonFiniteTrials like the reference's ValueError (the C-ABI stages through its own pinned buffer)
     out = eng.run_host(hi - lo, first_trial=lo, seed=seed)
     return MonteCarloRun(eng, out, strategy_ids, time_horizon, seed, lo, hi - lo, n_total, TAXABLE_IDS)

@@ -25,8 +25,11 @@ def run_strategy_fixed(df, strategy_id, regime_path, correlation_matrices=None, 
     accepted and unused, as in the reference)."""
     import pandas as pd
     from .mc_runner import _engine_for
+    from .utils import regime_path_for_frame
     cfg = _default_cfg if cfg is None else cfg
     T = len(df)
+    # strategy.py:64-78: a missing regime path, or one whose length does not match the frame, is inferred from the frame
+    regime_path = regime_path_for_frame(df, regime_path)
     model = {"regime_params": {}, "transition_matrix": np.eye(2), "joint_return_model": None}
     taxable = TAXABLE_IDS if trade_journal is not None else ()
     params, keep = build_params([strategy_id], max(T, 1) / 252.0, model, cfg, taxable_ids=taxable, apply_costs=bool(apply_costs))
@@ -38,7 +41,8 @@ def run_strategy_fixed(df, strategy_id, regime_path, correlation_matrices=None, 
         frame, 0,
         tlt_ret=df["TLT_Ret"].fillna(0).to_numpy() if "TLT_Ret" in df.columns else None,
         vix=df["VIX"].to_numpy() if "VIX" in df.columns else None,
-        regime=np.asarray(regime_path, dtype=np.int32) if regime_path is not None else None)
+        cash_ret=df["Cash_Ret"].to_numpy() if "Cash_Ret" in df.columns else None,      # the reference reads the column (strategy.py:138)
+        regime=np.asarray(regime_path, dtype=np.int32))
     if trade_journal is not None:
         for t in trades:
             trade_journal.trades.append(Trade(t["day_index"], t["asset"], t["action"], t["shares"], t["price"], t["dollar_amount"]))

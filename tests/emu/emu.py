@@ -79,8 +79,8 @@ def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, fir
     return out
 
 
-def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, precision=abi.PREC_F64, typed=False, log=None,
-               curve=False):
+def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, cash_ret=None, precision=abi.PREC_F64, typed=False,
+               log=None, curve=False):
     """materialised-path mode on host series: asset_ret = {asset name: [T][n] array}; log = (path, strategy, cap) switches
     the journal log on, curve=True also returns that (path, strategy)'s daily equity (out.curve)"""
     cols = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in asset_ret.items()}
@@ -91,8 +91,8 @@ def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, precis
     for name, a in cols.items():
         s.asset_ret[abi.ASSET_INDEX[name]] = a.ctypes.data
     keep = [np.ascontiguousarray(np.asarray(x, dtype=dt)) if x is not None else None
-            for x, dt in ((tlt_ret, np.float64), (vix, np.float64), (regime, np.int32))]
-    s.tlt_ret, s.vix, s.regime = (k.ctypes.data if k is not None else None for k in keep)
+            for x, dt in ((tlt_ret, np.float64), (vix, np.float64), (regime, np.int32), (cash_ret, np.float64))]
+    s.tlt_ret, s.vix, s.regime, s.cash_ret = (k.ctypes.data if k is not None else None for k in keep)
     out = HostOutputs(params.n_strategies, n)
     args = [-1, -1, 0] + [None] * 7
     if log is not None:

@@ -720,3 +720,74 @@ def test_simulate_single_path_fixed_dropin_and_equity_curve(engine_lib):
         assert len(ec) == 252 and ec[-1] == pytest.approx(bulk[sid][7]["Final_Wealth"], rel=1e-13)
         rm = np.maximum.accumulate(ec)
         assert abs(((ec - rm) / np.where(rm > 0, rm, 1.0)).min()) == pytest.approx(bulk[sid][7]["Max_DD"], abs=1e-12)
+
+
+def test_summary_only_route_matches_per_trial_route(engine_lib):
+    """parallel_monte_carlo_fixed(..., summary_only=True): reduction on the device, only the packed summary leaves it.  Its
+    table must agree with the reference's definitions (reporting.py:353-388) evaluated on the per-trial arrays of the same
+    run: histogram percentiles to bin width, exact=True percentiles bit for bit; device_results=True copies lazily."""
+    from letf_monte_carlo_b200 import parallel_monte_carlo_fixed
+    from letf_monte_carlo_b200.summary import summary_table
+    ns = synthetic.config_namespace(NUM_SIMULATIONS=6000, GPU_SEED=7)
+    sids = ["S1", "S2", "S4", "S19"]
+    model = synthetic.fallback_regime_model("default")
+    full = parallel_monte_carlo_fixed(sids, 2, model, {}, cfg=ns, verbose=False)
+    ref = {r["id"]: r for r in summary_table(full, 2)}
+    sm = parallel_monte_carlo_fixed(sids, 2, model, {}, cfg=ns, verbose=False, summary_only=True)
+    assert sm.d2h_bytes < 1 << 20
+    approx = {r["id"]: r for r in sm.table()}
+    exact = {r["id"]: r for r in sm.table(exact=True)}
+    for sid in sids:
+        for k in ("p10", "p25", "p40", "p60", "p75", "p90", "median"):
+            assert exact[sid][k] == ref[sid][k], (sid, k)
+            assert abs(np.log10(approx[sid][k] / ref[sid][k])) < 2 * 30 / 4096, (sid, k)
+        assert exact[sid]["dd"] == ref[sid]["dd"] and exact[sid]["cagr"] == ref[sid]["cagr"]
+        assert abs(approx[sid]["win"] - ref[sid]["win"]) < 1e-9 and abs(approx[sid]["trades"] - ref[sid]["trades"]) < 1e-9
+        assert approx[sid]["valid"] == 6000
+    lazy = parallel_monte_carlo_fixed(sids, 2, model, {}, cfg=ns, verbose=False, device_results=True)
+    assert lazy._out is None
+    np.testing.assert_array_equal(lazy["S4"].final_wealth, full["S4"].final_wealth)
+    assert lazy["S19"][5]["Num_Trades"] == full["S19"][5]["Num_Trades"]
+
+
+def test_reduce_on_a_second_engine_after_the_first(engine_lib):
+    """the reduction's shared-memory opt-in is set per launch (it is a per-device attribute): two engines in one process,
+    each with its own summary, both reduce"""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(["S1", "S2"], 1, synthetic.fallback_regime_model("default"), ns)
+    for _ in range(2):
+        with _engine(params, keep, "f32") as eng:
+            out = eng.run(512, seed=3)
+            sm = eng.new_summary(bench_strategy=1)
+            eng.reduce(out, sm)
+            assert int(sm.counters[0, 0]) == 512 and int(sm.hist[0, 0].sum()) == 512
+            info = eng.launch_info()
+            assert info["kernel_launches"] == 1 and info["aux_launches"] == 1 and info["kernel"]
+
+
+def test_run_strategy_fixed_infers_the_regime_path_like_the_reference(engine_lib):
+    """run_strategy_fixed(df, sid, None, ...) and a regime path of the wrong length: the reference infers the path from VIX /
+    realised volatility / term spread (strategy.py:64-78) - cash rate and spread cost follow it.  Equity curves against the
+    live reference (tests/golden/infer_regime_900d.npz)."""
+    import os
+    from letf_monte_carlo_b200 import run_strategy_fixed
+    from oracle.make_regime_inference_golden import frame
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infer_regime_900d.npz"))
+    df = frame()
+    df["VIX"] = df["VIX"].ffill()
+    for sid in ("S4", "S8", "S16"):
+        curve, nt = run_strategy_fixed(df, sid, None, {}, apply_costs=True)
+        np.testing.assert_allclose(curve.to_numpy(), g[f"{sid}_curve"], rtol=1e-11)
+        assert nt == int(g[f"{sid}_trades"])
+        curve2, _ = run_strategy_fixed(df, sid, np.zeros(17, dtype=int), {}, apply_costs=True)
+        np.testing.assert_allclose(curve2.to_numpy(), g[f"{sid}_curve_mismatch"], rtol=1e-11)
+    # the engine-level seam refuses columns whose length is not the frame's (it would read past them)
+    from letf_monte_carlo_b200.params import build_params as bp
+    params, keep = bp(["S4"], len(df) / 252.0, {"regime_params": {}, "transition_matrix": np.eye(2), "joint_return_model": None},
+                      synthetic.config_namespace())
+    with _engine(params, keep, "f64") as eng:
+        with pytest.raises(ValueError):
+            eng.run_strategy_curve({"SPY": df["SPY_Ret"].to_numpy(), "TQQQ": df["TQQQ_Ret"].to_numpy()}, 0, regime=np.zeros(17, np.int32))
+        with pytest.raises(ValueError):
+            eng.run_strategy_curve({"SPY": df["SPY_Ret"].to_numpy(), "TQQQ": df["TQQQ_Ret"].to_numpy()}, 0,
+                                   regime=np.full(len(df), 2, np.int32))

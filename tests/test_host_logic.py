@@ -186,6 +186,77 @@ def _gloo_worker(rank, ws, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_worker2(rank, ws, port, q):
+    """the packed-summary exchange (one all-gather + combine) and the exact cross-rank percentiles, CPU tensors over gloo"""
+    import torch
+    import torch.distributed as dist
+    from letf_monte_carlo_b200.distributed import exchange_summary, shard_range as sr
+    from letf_monte_carlo_b200.engine import DeviceSummary
+    from letf_monte_carlo_b200.summary import global_order_statistics, global_percentiles, summary_table
+    from letf_monte_carlo_b200.mc_runner import MonteCarloRun
+    from letf_monte_carlo_b200.outputs import HostOutputs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    n = 20001
+    lo, hi = sr(n, rank, ws)
+    rng = np.random.default_rng(3)
+    w = 1e4 * np.exp(rng.normal(0.5, 1.0, (2, n)))              # "final wealth" of two strategies, identical on every rank
+    w[1, ::7] = w[1, 3]                                           # ties
+    dd = rng.uniform(0, 1, (2, n)); tr = rng.integers(0, 50, (2, n))
+    sm = DeviceSummary(2, "cpu", bench_strategy=0)
+    mine = slice(lo, hi)
+    for s in range(2):
+        x = np.log10(w[s, mine] / 1e4)
+        sm.hist[s, 0] = torch.from_numpy(np.histogram(x, bins=4096, range=(sm.lo[0], sm.hi[0]))[0])
+        sm.moments[s, 0, 0] = x.sum(); sm.moments[s, 0, 1] = (x ** 2).sum()
+        sm.extrema[s, 0, 0] = x.min(); sm.extrema[s, 0, 1] = x.max()
+        sm.counters[s, 0] = hi - lo; sm.counters[s, 2] = int(tr[s, mine].sum())
+    exchange_summary(sm)
+    ok = True
+    for s in range(2):
+        x = np.log10(w[s] / 1e4)
+        ok &= np.array_equal(sm.hist[s, 0].numpy(), np.histogram(x, bins=4096, range=(sm.lo[0], sm.hi[0]))[0])
+        ok &= abs(float(sm.moments[s, 0, 0]) - x.sum()) < 1e-8 and float(sm.extrema[s, 0, 0]) == x.min()
+        ok &= float(sm.extrema[s, 0, 1]) == x.max() and int(sm.counters[s, 0]) == n and int(sm.counters[s, 2]) == int(tr[s].sum())
+        ok &= float(sm.extrema[s, 1, 0]) == float("inf") and float(sm.extrema[s, 1, 1]) == float("-inf")      # untouched metric
+    # exact percentiles of the union, each rank holding only its shard; tiny `cap` forces the histogram refinement rounds
+    qs = [10, 25, 40, 50, 60, 75, 90]
+    for s in range(2):
+        got = global_percentiles(torch.from_numpy(w[s, mine].copy()), qs)
+        ok &= got == [float(v) for v in np.percentile(w[s], qs)]
+        ks = [0, 1, n // 3, n - 1]
+        ok &= global_order_statistics(torch.from_numpy(w[s, mine].copy()), ks, cap=64) == [float(np.sort(w[s])[k]) for k in ks]
+    # summary_table on a sharded run = the reference's table on the whole run (reporting.py:353-388)
+    out = HostOutputs(2, hi - lo)
+    out.final_wealth[...] = w[:, mine]; out.max_dd[...] = dd[:, mine]; out.num_trades[...] = tr[:, mine]
+    run = MonteCarloRun(None, out, ["S2", "S4"], 10, 0, lo, hi - lo, n, [])
+    whole = HostOutputs(2, n)
+    whole.final_wealth[...] = w; whole.max_dd[...] = dd; whole.num_trades[...] = tr
+    ref_rows = {r["id"]: r for r in summary_table(MonteCarloRun(None, whole, ["S2", "S4"], 10, 0, 0, n, n, []), 10)}
+    for r in summary_table(run, 10):
+        e = ref_rows[r["id"]]
+        for k in ("p10", "p25", "p40", "p60", "p75", "p90", "median", "cagr", "dd"):
+            ok &= r[k] == e[k]
+        ok &= abs(r["win"] - e["win"]) < 1e-9 and abs(r["trades"] - e["trades"]) < 1e-9
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_packed_summary_exchange_and_exact_percentiles_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
 def test_summary_allreduce_world_size_2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -221,3 +292,25 @@ def test_summary_table_matches_reference_definitions():
     h, _ = np.histogram(x, bins=4096, range=(-20, 10))
     for q in (10, 50, 90):
         assert abs(histogram_quantile(h, -20, 10, q) - np.percentile(x, q)) < 2 * 30 / 4096
+
+
+def test_regime_inference_matches_live_reference():
+    """run_strategy_fixed without a (matching) regime path infers one from the frame (strategy.py:64-78, utils.py:55-127);
+    golden from the live reference (oracle/make_regime_inference_golden.py)"""
+    from letf_monte_carlo_b200.utils import compute_high_vol_probability, infer_regime_from_vix, regime_path_for_frame
+    from oracle.make_regime_inference_golden import frame
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infer_regime_900d.npz"))
+    df = frame()
+    rv = (df["SPY_Ret"].rolling(20, min_periods=5).std().bfill().fillna(0) * np.sqrt(252)).to_numpy()
+    ts = (df["TNX"] - df["IRX"]).to_numpy()
+    np.testing.assert_allclose(compute_high_vol_probability(df["VIX"].to_numpy(), realized_vol=rv, term_spread=ts), g["p_high"],
+                               rtol=1e-13)
+    np.testing.assert_allclose(compute_high_vol_probability(df["VIX"].to_numpy()), g["p_high_vix_only"], rtol=1e-13)
+    np.testing.assert_array_equal(infer_regime_from_vix(df["VIX"].to_numpy(), realized_vol=rv, term_spread=ts), g["regime"])
+    np.testing.assert_array_equal(infer_regime_from_vix(df["VIX"].to_numpy(), realized_vol=rv), g["regime_no_ts"])
+    assert 0 < g["regime"].sum() < len(df)
+    np.testing.assert_array_equal(regime_path_for_frame(df, None), g["regime"])
+    np.testing.assert_array_equal(regime_path_for_frame(df, np.zeros(17, dtype=int)), g["regime"])      # length mismatch
+    own = np.arange(len(df)) % 2
+    np.testing.assert_array_equal(regime_path_for_frame(df, own), own)
+    np.testing.assert_array_equal(regime_path_for_frame(df.drop(columns=["VIX"]), None), np.zeros(len(df), dtype=int))

@@ -315,13 +315,35 @@ def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
     np.testing.assert_array_equal(typed.regime_days, gen.regime_days)
 
 
+def test_lean_fast_variant_config1_shape():
+    """BASELINE config 1 (validation.py:33-57): one frictionless 3x series - the straight-line loop draws no
+    tracking-error block at all; against the lean build's general loop and the generic build on the same counters"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=False,
+                                    USE_ANTITHETIC_VARIATES=False, LETF_CONFIGS=synthetic.pure_leverage_assets())
+    ns.ASSETS = ns.LETF_CONFIGS
+    params, keep = build_params(["B_UPRO"], 1, synthetic.normal_regime_model("c1"), ns)
+    fast, code = emu.run_lean(params, 33, seed=3)
+    assert code == 1 | (1 << 8) | (1 << 12)
+    two, _ = emu.run_lean(params, 33, seed=3, two_per_thread=True)
+    slow, _ = emu.run_lean(params, 33, seed=3, force_generic=True)
+    dummy = HostTape(1, params.sim_days, params.sim_days, 1)
+    gen = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=3, n=33)
+    for other in (two, slow, gen):
+        np.testing.assert_allclose(fast.final_wealth, other.final_wealth, rtol=2e-6)
+        np.testing.assert_allclose(fast.max_dd, other.max_dd, atol=1e-6)
+    # frictionless: terminal wealth is exactly the compounded 3x underlying, so log growth has mean -L^2 sigma^2 / 2 per year
+    big, _ = emu.run_lean(params, 4000, seed=9, two_per_thread=True)
+    ann = np.median(big.final_wealth[0] / params.initial_capital - 1.0)
+    assert abs(ann - (-0.10125)) < 0.015
+
+
 def test_lean_fast_variant_config5_shape():
     """BASELINE config 5 cell: L = 3 / 2 / 1 on one SPY-like underlying (UPRO, SSO, SPY rows of cfg.ASSETS;
     SPY's tracking error is t(10)) -> the "last slot t(10)" straight-line loop against the general loop"""
     sids = ["B_UPRO", "S3", "S2"]
     params, keep = _c2_params(sids, years=2)
     fast, code = emu.run_lean(params, 33, seed=3)
-    assert code == 1 + 4                       # slots UPRO, SSO, SPY: third one is t(10)
+    assert code == (1 + 4) | (3 << 8)          # slots UPRO, SSO, SPY: third one is t(10)
     two, _ = emu.run_lean(params, 33, seed=3, two_per_thread=True)
     slow, _ = emu.run_lean(params, 33, seed=3, force_generic=True)
     np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-5)
@@ -387,6 +409,29 @@ def test_series_mode_equity_curves_match_live_reference():
             n = int(out.log["count"][0])
             assert n == int(g[f"{sid}_journal_n"]), sid
             np.testing.assert_array_equal(out.log["day"][:n], g[f"{sid}_journal_days"])
+
+
+def test_series_mode_with_inferred_regime_path_matches_live_reference():
+    """run_strategy_fixed(df, sid, None, ...): the regime path is inferred from the frame (strategy.py:64-78); kernel source in
+    series mode fed with `regime_path_for_frame` against the live reference's curves (tests/golden/infer_regime_900d.npz)"""
+    import os
+    from letf_monte_carlo_b200.utils import regime_path_for_frame
+    from oracle.make_regime_inference_golden import frame as mk
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infer_regime_900d.npz"))
+    df = mk()
+    df["VIX"] = df["VIX"].ffill()
+    T = len(df)
+    frame = {a: df[f"{a}_Ret"].to_numpy().reshape(T, 1) for a in abi.ASSET_NAMES}
+    ns = synthetic.config_namespace()
+    for sid in ("S4", "S8", "S16"):
+        params, keep = build_params([sid], T / 252.0, synthetic.fallback_regime_model(), ns)
+        for given, key in ((None, f"{sid}_curve"), (np.zeros(17, dtype=int), f"{sid}_curve_mismatch")):
+            reg = regime_path_for_frame(df, given).astype(np.int32)
+            out = emu.run_series(params, frame, tlt_ret=df["TLT_Ret"].to_numpy().reshape(T, 1), vix=df["VIX"].to_numpy().reshape(T, 1),
+                                 regime=reg.reshape(T, 1), cash_ret=df["Cash_Ret"].to_numpy().reshape(T, 1), log=(0, 0, 4096),
+                                 curve=True)
+            np.testing.assert_allclose(out.curve, g[key], rtol=1e-11, err_msg=sid)
+        assert out.num_trades[0, 0] == int(g[f"{sid}_trades"]), sid
 
 
 @pytest.mark.parametrize("T", [1, 2, 3, 5, 61, 203])
