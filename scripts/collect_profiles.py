@@ -1,14 +1,20 @@
 """Copy one measurement pass (gpurun_out/<dir>) into profiles/ under a version tag and print a summary table.
 
-usage: python scripts/collect_profiles.py gpurun_out/final2 v14
-Writes profiles/r1_<workload>_<tag>_bench.json, ..._ncu_full_summary.csv, ..._sass_mix.txt, the launch list and the
+usage: python scripts/collect_profiles.py gpurun_out/final2 v14 [round prefix, default r1] [workload=trials ...]
+(round 2: python scripts/collect_profiles.py gpurun_out/r2a v1 r2 c3=113664; the bench default is c3 from round 2 on)
+Writes profiles/<round>_<workload>_<tag>_bench.json, ..._ncu_full_summary.csv, ..._sass_mix.txt, the launch list and the
 reference-arm line, and refreshes profiles/ncu_constants.json from the captures it finds."""
 import json, os, shutil, subprocess, sys
 
 src, tag = sys.argv[1], sys.argv[2]
+RND = sys.argv[3] if len(sys.argv) > 3 else "r1"
+DEFAULT_W = "c2" if RND == "r1" else "c3"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 prof = os.path.join(root, "profiles")
 TRIALS = {"c2": 100000, "c3": 75776, "c4": 50560, "boot": 50560, "sweep19": 37888}
+for kv in sys.argv[4:]:
+    k, v = kv.split("=")
+    TRIALS[k] = int(v)
 
 
 def last_json(path):
@@ -19,7 +25,7 @@ rows = []
 for f in sorted(os.listdir(src)):
     if f.startswith("bench_") and f.endswith(".json"):
         w = f[6:-5]
-        name = {"default": f"r1_c2_{tag}_bench.json", "reference": f"r1_c2_{tag}_reference_arm.json"}.get(w, f"r1_{w}_{tag}_bench.json")
+        name = {"default": f"{RND}_{DEFAULT_W}_{tag}_bench.json", "reference": f"{RND}_{DEFAULT_W}_{tag}_reference_arm.json"}.get(w, f"{RND}_{w}_{tag}_bench.json")
         shutil.copy(os.path.join(src, f), os.path.join(prof, name))
         try:
             d = last_json(os.path.join(src, f))
@@ -27,8 +33,9 @@ for f in sorted(os.listdir(src)):
             rows.append((w, d["value"], d["ms_per_step"], (d.get("e2e") or {}).get("value"), r.get("frac"), r.get("achieved"), r.get("unit")))
         except Exception as e:
             rows.append((w, "ERR", str(e)))
-if os.path.exists(os.path.join(src, "launches_c2.csv")):
-    shutil.copy(os.path.join(src, "launches_c2.csv"), os.path.join(prof, f"r1_c2_{tag}_launches.csv"))
+for lw in ("c2", "c3"):
+    if os.path.exists(os.path.join(src, f"launches_{lw}.csv")):
+        shutil.copy(os.path.join(src, f"launches_{lw}.csv"), os.path.join(prof, f"{RND}_{lw}_{tag}_launches.csv"))
 consts = {"_comment": "constants read from the committed ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per "
                       "launch / trials of that launch; smsp__inst_executed.sum x 32 / path-days of that launch); bench.py scales them "
                       "to its launch and copies them into the JSON line"}
@@ -37,11 +44,11 @@ for w, n in TRIALS.items():
     if not os.path.exists(rep):
         continue
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_metrics.py"), rep], capture_output=True, text=True).stdout
-    with open(os.path.join(prof, f"r1_{w}_{tag}_ncu_full_summary.csv"), "w") as fh:
+    with open(os.path.join(prof, f"{RND}_{w}_{tag}_ncu_full_summary.csv"), "w") as fh:
         fh.write("metric,unit,value\n" + out)
     mix = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_sass_mix.py"), rep, str(n * 7560), "--blocks"],
                          capture_output=True, text=True).stdout
-    with open(os.path.join(prof, f"r1_{w}_{tag}_sass_mix.txt"), "w") as fh:
+    with open(os.path.join(prof, f"{RND}_{w}_{tag}_sass_mix.txt"), "w") as fh:
         fh.write(mix)
     m = {}
     for line in out.splitlines():
@@ -51,7 +58,7 @@ for w, n in TRIALS.items():
     dram = m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
     inst = m.get("smsp__inst_executed.sum", 0.0)
     consts[w] = {"dram_bytes_per_trial": dram / n, "executed_warp_instr_per_path_day": inst * 32 / (n * 7560),
-                 "source": f"profiles/r1_{w}_{tag}_ncu_full_summary.csv ({n} trials)"}
+                 "source": f"profiles/{RND}_{w}_{tag}_ncu_full_summary.csv ({n} trials)"}
     print(w, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % consts[w]["executed_warp_instr_per_path_day"],
           "issue %.1f%%" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0), "DRAM GB %.2f" % (dram / 1e9))
 cpath = os.path.join(prof, "ncu_constants.json")
