@@ -2,9 +2,9 @@
 // antithetic-pair kernels of the lean institutional buy&hold shapes (letf_jfast.cuh)
 #include "letf_kernels.cuh"
 // BASELINE config 3: SPY + QQQ (+ TLT benchmark), both tracking errors t(10)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3, 4, 3, 2, 3, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3, 4, 3, 2, 3, false, 128, 3)
 // S1 S2 S3 and the like: two LETFs t(5) + SPY t(10)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3a, 4, 3, 3, 4, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3a, 4, 3, 3, 4, false, 128, 3)
 // one series
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t5, 4, 3, 1, 0, 128, 3)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t10, 4, 3, 1, 1, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t5, 4, 3, 1, 0, false, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t10, 4, 3, 1, 1, false, 128, 3)

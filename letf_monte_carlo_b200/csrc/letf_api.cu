@@ -100,7 +100,9 @@ struct LetfEngine {
   uint32_t type_mask = 0;
   bool any_taxable = false;
   std::string pin_kernel;                    // tuning aids, read from the environment when the engine is created:
-  bool no_jpair = false;                     // LETF_KERNEL=<instantiation>, LETF_NO_JPAIR=1
+  bool no_jpair = false;                     // LETF_KERNEL=<instantiation>, LETF_NO_JPAIR=1, LETF_NO_SPLIT=1
+  bool no_split = false;
+  DevBuf rec;                                // per-day records of the split strategy pipeline
   // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
   void* boot_blob = nullptr;
   DevBoot<double> boot64;
@@ -127,6 +129,51 @@ struct LogArgs {
   double* curve = nullptr;                  // device [T]: equity curve of (trial, strategy)
 };
 
+// typed slots: the strategy list must be exactly the one compiled in
+static bool list_matches(const KernelEntry* k, const LetfEngine* e) {
+  const int n_strat = e->params.n_strategies;
+  bool same = slot_list_count(k->list) == n_strat;
+  for (int s = 0; same && s < n_strat; s++) {
+    same = slot_list_type(k->list, s) == e->params.strategies[s].type;
+    const int as = slot_list_asset(k->list, s);
+    if (same && as >= 0) same = e->params.strategies[s].asset == as;
+    if (same && e->params.strategies[s].type == LETF_ST_COMPOSITE) same = e->params.strategies[s].asset2 == 4;
+  }
+  return same;
+}
+
+// Split strategy pipeline: the market + ETF layers of one antithetic pair per thread (letf_jfast.cuh, EMIT build) write
+// per-day records, a typed rule kernel (Trial::run in record mode, one trial per thread) consumes them.  Admitted: fp32,
+// Philox draws, no journal / tape plumbing, the institutional shape the pair kernel serves (joint-t + moment matching +
+// antithetic pairs + stress + funding, integer joint dof, default tracking-error dof, no tanh cap), SPY simulated and QQQ
+// not (the SPY price is the last record field), and a strategy list with a compiled-in typed rule kernel.
+struct SplitPlan { const KernelEntry* prod = nullptr; const KernelEntry* cons = nullptr; int nact = 0; };
+static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
+  const LetfParams& s = e->params;
+  if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split || (first & 1)) return false;
+  if (s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs || !s.institutional ||
+      !s.has_stress || !s.has_funding || s.sim_days < 2) return false;
+  for (int r = 0; r < 2; r++) if (!df_fast_k(s.joint[r].nu)) return false;
+  const int mask = s.asset_mask & 0x3F;
+  if (!((mask >> 4) & 1) || ((mask >> 5) & 1)) return false;
+  int nact = 0, k10 = 0;
+  for (int a = 0; a < kAssets; a++) {
+    if (!((mask >> a) & 1)) continue;
+    const int fk = df_fast_k(s.assets[a].te_df);
+    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) return false;
+    if (fk == 10) k10 |= 1 << nact;
+    nact++;
+  }
+  for (int i = 0; i < kernel_count(); i++) {
+    const KernelEntry* k = kernel_at(i);
+    if (k->precision != LETF_PREC_F32) continue;
+    if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact) plan->prod = k;
+    if (k->market == kMarketFSeries && k->list && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e)) plan->cons = k;
+  }
+  plan->nact = nact;
+  return plan->prod && plan->cons;
+}
+
 static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool need_io, int n_strat, uint32_t tmask,
                                        int n_assets) {
   const KernelEntry* best = nullptr;
@@ -137,7 +184,7 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
     if (need_io && !k->tapeio) continue;
     if (k->ns < n_strat || (tmask & ~k->tm) || k->na < n_assets) continue;
     // antithetic-pair kernels serve exactly one shape (letf_jfast.cuh); LETF_NO_JPAIR=1 keeps the generic lean build (A/B runs)
-    if (k->fj && (k->fj != fast_joint_shape(e->params, k->na) || e->no_jpair)) continue;
+    if (k->fj && (k->fj != fast_joint_shape(e->params, k->na) || e->no_jpair)) continue;      // (producers carry kSplitProducer: never equal)
     if (k->am) {        // compile-time asset mask: same series, default tracking-error dof (config.py:62-135)
       bool ok = (k->am & 0x3F) == e->params.asset_mask;
       if (!(k->am & 0x40))          // bit 6: tracking-error dof read at run time (calibrated tracking_residual_model)
@@ -145,16 +192,7 @@ static const KernelEntry* select_kernel(const LetfEngine* e, int market, bool ne
           if ((k->am >> a) & 1) ok = df_fast_k(e->params.assets[a].te_df) == (a >= 4 ? 10 : 5);
       if (!ok) continue;
     }
-    if (k->list) {      // typed slots: the strategy list must be exactly the one compiled in
-      bool same = slot_list_count(k->list) == n_strat;
-      for (int s = 0; same && s < n_strat; s++) {
-        same = slot_list_type(k->list, s) == e->params.strategies[s].type;
-        const int as = slot_list_asset(k->list, s);
-        if (same && as >= 0) same = e->params.strategies[s].asset == as;
-        if (same && e->params.strategies[s].type == LETF_ST_COMPOSITE) same = e->params.strategies[s].asset2 == 4;
-      }
-      if (!same) continue;
-    }
+    if (k->list && !list_matches(k, e)) continue;
     // tuning aid: LETF_KERNEL=<instantiation name> pins an eligible build
     if (pin && *pin && !strcmp(pin, k->name)) return k;
     if (!best) { best = k; continue; }
@@ -229,6 +267,101 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   return LETF_OK;
 }
 
+// full-wave persistent grid for `items` equal-length work items
+static int64_t full_wave_grid(int64_t items, int sm_count, int max_blocks, int block) {
+  const int64_t resident = (int64_t)sm_count * max_blocks * block;
+  const int64_t waves = (items + resident - 1) / resident;
+  const int64_t per_wave = (items + waves - 1) / waves;
+  int64_t grid = (per_wave + block - 1) / block;
+  return grid < 1 ? 1 : grid;
+}
+static LetfOutputs out_columns(const LetfOutputs& o, int64_t off) {
+  LetfOutputs r = o;             // [S][N] arrays: column j of every row is (pointer + j), the pitch N = n_trials stays
+  r.final_wealth += off; r.max_dd += off; r.num_trades += off;
+  if (r.journal_count) r.journal_count += off;
+  if (r.journal_volume) r.journal_volume += off;
+  if (r.start_offset) r.start_offset += off;
+  if (r.flags) r.flags += off;
+  if (r.regime_days) r.regime_days += off;
+  if (r.jump_days) r.jump_days += off;
+  return r;
+}
+
+template <int NSC>
+static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, uint64_t seed, int64_t first, int64_t n,
+                        const LetfOutputs* out) {
+  constexpr int NSP = 32, NAP = 4;                     // producer instantiations (inst_f32_split_producers.cu)
+  const KernelEntry *kp = plan.prod, *kc = plan.cons;
+  cudaFuncAttributes fap, fac;
+  int mbp = 0, mbc = 0;
+  CK(kp->attrs(&fap, &mbp));
+  CK(kc->attrs(&fac, &mbc));
+  if (mbp < 1 || mbc < 1) return fail(LETF_ERR_CUDA, "split pipeline kernels cannot be resident on this device");
+  static thread_local KArgs<float, NSP, NAP> ka_p;
+  static thread_local KArgs<float, NSC, kAssets> ka_c;
+  memset(&ka_p, 0, sizeof(ka_p)); memset(&ka_c, 0, sizeof(ka_c));
+  convert_params<float, NSP, NAP>(e->params, e->dev_dur, ka_p.p, (const DevBoot<float>*)(const void*)&e->boot32);
+  convert_params<float, NSC, kAssets>(e->params, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
+  const int T = e->params.sim_days, G = T + e->params.buffer_days, NF = plan.nact + 2;
+  // chunk of trials: whole producer waves (two trials per thread), as many as fit in half of the free device memory
+  const int64_t wave_trials = 2 * (int64_t)e->sm_count * mbp * kp->block;
+  const double per_trial = (double)T * NF * 4 + (double)G * sizeof(JF8) / 2;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const double budget = 0.5 * ((double)free_b + (double)e->rec.cap + (double)e->xscr.cap);
+  int64_t waves_fit = (int64_t)(budget / (per_trial * (double)wave_trials));
+  if (waves_fit < 1) return fail(LETF_ERR_NOMEM, "split pipeline: one wave of per-day records does not fit in device memory");
+  if (waves_fit > 4) waves_fit = 4;
+  int64_t cap = wave_trials * waves_fit;
+  if (cap > ((n + 1) & ~(int64_t)1)) cap = (n + 1) & ~(int64_t)1;
+  {
+    cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "split pipeline records: " + std::string(cudaGetErrorString(ce))); }
+  }
+  ka_p.seed = ka_c.seed = seed; ka_p.rng_mode = ka_c.rng_mode = LETF_RNG_PHILOX;
+  ka_p.rec = ka_c.rec = (float*)e->rec.p; ka_p.rec_ncol = ka_c.rec_ncol = cap;
+  ka_p.log_trial = ka_c.log_trial = -1;
+  ka_c.p.T = T; ka_c.p.buffer = 0; ka_c.p.random_start = 0;
+  ka_c.series.sim_days = T;
+  size_t scratch = (size_t)cap * T * NF * 4;
+  int launches = 0;
+  int64_t grid_c_last = 0, grid_p_last = 0;
+  CK(cudaEventRecord(e->ev0, st));
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+    const int64_t nc = n - c0 < cap ? n - c0 : cap;
+    const LetfOutputs oc = out_columns(*out, c0);
+    // producer: one work item per antithetic pair
+    const int64_t pairs = (nc + 1) / 2;
+    const int64_t grid_p = full_wave_grid(pairs, e->sm_count, mbp, kp->block);
+    ka_p.out = oc; ka_p.first_trial = first + c0; ka_p.n_trials = nc; ka_p.nthreads = grid_p * kp->block;
+    {
+      const size_t b = (size_t)G * sizeof(JF8) * (size_t)ka_p.nthreads;
+      cudaError_t ce = e->xscr.reserve(b);
+      if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
+      ka_p.xscr = (float*)e->xscr.p;
+      if (c0 == 0) scratch += b;
+    }
+    CK(kp->launch(&ka_p, (int)grid_p, st));
+    // rule kernel: one trial per thread, columns [0, nc) of the record buffer
+    const int64_t grid_c = full_wave_grid(nc, e->sm_count, mbc, kc->block);
+    const int64_t nth = grid_c * kc->block;
+    if ((int64_t)kRingP * nth >= ((int64_t)1 << 32)) return fail(LETF_ERR_INVALID, "grid too large for 32-bit ring offsets");
+    ka_c.out = oc; ka_c.first_trial = first + c0; ka_c.n_trials = nc; ka_c.nthreads = nth; ka_c.series.n_paths = nc;
+    if (kc->tm & kNeedRingP) { size_t b = (size_t)kRingP * nth * 4; CK(e->ringP.reserve(b)); ka_c.ringP = (float*)e->ringP.p; if (c0 == 0) scratch += b; }
+    if (kc->tm & kNeedRingS) { size_t b = (size_t)kRingS * nth * 4; CK(e->ringS.reserve(b)); ka_c.ringS = (float*)e->ringS.p; if (c0 == 0) scratch += b; }
+    if (kc->tm & kVolTypes) { size_t b = (size_t)kRingA * nth * 4; CK(e->ringA.reserve(b)); ka_c.ringA = (float*)e->ringA.p; if (c0 == 0) scratch += b; }
+    CK(kc->launch(&ka_c, (int)grid_c, st));
+    launches += 2; grid_c_last = grid_c; grid_p_last = grid_p;
+  }
+  CK(cudaEventRecord(e->ev1, st));
+  e->timed = true;
+  e->info.grid = (int)grid_p_last; e->info.block = kp->block; e->info.regs_per_thread = fap.numRegs;
+  e->info.kernel_launches = launches; e->info.scratch_bytes = (int64_t)scratch; e->info.sm_count = e->sm_count;
+  snprintf(e->info.kernel, sizeof(e->info.kernel), "%s+%s", kp->name + 4, kc->name + 4);
+  (void)grid_c_last;
+  return LETF_OK;
+}
+
 static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed, int64_t first, int64_t n,
                       int rng_mode, const LetfTape* tape, const LetfOutputs* out, const LetfSeries* series,
                       const LogArgs& lg) {
@@ -260,6 +393,14 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
                        lg.curve != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
+  if (market == e->params.market_mode && !series && !(e->pin_kernel.size())) {
+    SplitPlan plan;
+    if (find_split(e, rng_mode, need_io, first, &plan)) {
+      CK(cudaSetDevice(e->device));
+      if (plan.cons->ns == 8) return launch_split<8>(e, plan, st, seed, first, n, out);
+      if (plan.cons->ns == 32) return launch_split<32>(e, plan, st, seed, first, n, out);
+    }
+  }
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);
   if (!ke) return fail(LETF_ERR_INVALID, "no kernel instantiation for this (precision, market, strategies) combination");
   CK(cudaSetDevice(e->device));
@@ -368,6 +509,7 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
   e->type_mask = strategy_type_mask(*params);
   { const char* v = getenv("LETF_KERNEL"); e->pin_kernel = v ? v : ""; }
   { const char* v = getenv("LETF_NO_JPAIR"); e->no_jpair = v && *v && *v != '0'; }
+  { const char* v = getenv("LETF_NO_SPLIT"); e->no_split = v && *v && *v != '0'; }
   for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
   ce = cudaEventCreate(&e->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);
@@ -381,7 +523,7 @@ void letf_destroy(LetfEngine* e) {
   cudaSetDevice(e->device);
   for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
   if (e->boot_blob) cudaFree(e->boot_blob);
-  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release();
+  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release(); e->rec.release();
   e->stage_tape.release(); e->stage_out.release(); e->stage_log.release(); e->pin_out.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);

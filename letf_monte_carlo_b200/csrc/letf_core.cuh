@@ -44,6 +44,10 @@ template <typename R, int NS, int NA> struct KArgs {
   int64_t log_trial; int log_strategy; int log_cap;
   int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
   double* log_curve;        // [T] daily equity of (log_trial, log_strategy): the Series run_strategy_fixed returns
+  // split strategy pipeline (letf_jfast.cuh EMIT producer -> Trial::run with MARKET == kMarketFSeries): per-day records,
+  // rec[(field * T + day) * rec_ncol + column], fields = the active layer returns, VIX (regime in the sign bit), SPY price
+  float* rec;
+  int64_t rec_ncol;
 };
 
 LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
@@ -127,6 +131,7 @@ template <typename R> LETF_HD R pick6(const R (&v)[LETF_N_ASSETS], int a) {
 
 #define TM_HAS(t) ((TM >> (t)) & 1u)
 constexpr int kMarketSeries = 3;
+constexpr int kMarketFSeries = 5;     // fp32 day-major records written by the pair producer (letf_jfast.cuh EMIT): split strategy pipeline
 constexpr uint32_t kVolTypes = (1u << LETF_ST_VOL_TARGETING) | (1u << LETF_ST_ADAPTIVE_VOL) | (1u << LETF_ST_DOWNSIDE_VOL) |
                                (1u << LETF_ST_CONVEX_VOL) | (1u << LETF_ST_VOL_VELOCITY) | (1u << LETF_ST_VOL_MOM) |
                                (1u << LETF_ST_SKEW_CONVEX) | (1u << LETF_ST_META_ENSEMBLE) | (1u << LETF_ST_REGIME_ASYMMETRIC) |
@@ -171,6 +176,10 @@ struct Trial {
   // LIST: typed slot list (0 = dynamic); AM: compile-time asset mask (0 = p.act_on at run time)
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
+  static constexpr bool FSER = MARKET == kMarketFSeries;
+  static constexpr bool SERIES = MARKET == kMarketSeries || FSER;
+  static constexpr int NF = FSER ? __builtin_popcount((unsigned)AM & 0x3Fu) + 2 : 1;      // record fields: active returns, VIX, SPY price
+  static_assert(!FSER || (AM != 0 && LIST != 0 && !TAPEIO && !EXACT), "record mode: typed fp32 builds only");
   static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
   static constexpr bool KEYREF = NA < kAssets; // calling convention of the non-inlined sampler retry loop (letf_math.cuh)
   static constexpr bool HAS_VOL = (TM & kVolTypes) != 0;
@@ -638,7 +647,7 @@ struct Trial {
 
     // ---- start offset (random_start.py:33-57)
     int so = 0;
-    if (MARKET != kMarketSeries && p.random_start) {
+    if (!SERIES && p.random_start) {
       if (use_tape) so = ka.tape.start_offset[tcol];
       else {
         U4 b = rng_block(key, 0, STREAM_START);
@@ -647,7 +656,7 @@ struct Trial {
       }
     }
 
-    if (MARKET != kMarketSeries && MARKET != LETF_MARKET_NORMAL && p.start_p1 > (R)0) {
+    if (!SERIES && MARKET != LETF_MARKET_NORMAL && p.start_p1 > (R)0) {
       if (use_tape) start_reg = ka.tape.start_regime ? (ka.tape.start_regime[tcol] != 0) : 0;
       else {
         U4 b = rng_block(key, 0, STREAM_START);
@@ -669,7 +678,7 @@ struct Trial {
     R* const is = (R*)ka.xscr + (int64_t)4 * (p.T + p.buffer) * ka.nthreads + (int64_t)lane * Gp;
     R shift[3] = {(R)0, (R)0, (R)0};
     const bool two_pass = (MARKET == LETF_MARKET_JOINT_T && p.mm) || MARKET == kMarketBoot;
-    const int T = MARKET == kMarketSeries ? ka.series.sim_days : p.T;
+    const int T = SERIES ? ka.series.sim_days : p.T;
     JointState js;
     js.prev_reg = 0;
     for (int a = 0; a < 3; a++) { js.h[a] = 0; js.pz[a] = 0; }
@@ -716,7 +725,7 @@ struct Trial {
     R vix = p.const_vix;
     // stress / tracking-error / price state
     R liq = 0, cred = 0;
-    static_assert(NA == kAssets || (!HAS_ACTIVE && MARKET != kMarketSeries), "compacted asset slots are for buy&hold-only builds");
+    static_assert(NA == kAssets || (!HAS_ACTIVE && !SERIES), "compacted asset slots are for buy&hold-only builds");
     R te_prev[NA], bias[NA];
     double cp[NA];                   // cumulative growth of each ETF series (price / 100), always fp64
     Drawdown<R> ddA[NA], ddT;        // buy&hold statistics live on the asset, not on a strategy slot
@@ -791,6 +800,18 @@ struct Trial {
 #pragma unroll
       for (int d = 0; d < kSeriesAhead; d++) if (d < T) series_fetch(d, d);
     }
+    // record mode: the day's NF fields (coalesced: one column per thread, every thread on the same day)
+    R fq[FSER ? kSeriesAhead : 1][NF];
+    auto rec_fetch = [&](int slot, int day) {
+      const float* r = ka.rec + (int64_t)day * ka.rec_ncol + col;
+      const int64_t fstride = (int64_t)T * ka.rec_ncol;
+#pragma unroll
+      for (int f = 0; f < NF; f++) fq[slot][f] = (R)r[(int64_t)f * fstride];
+    };
+    if (FSER) {
+#pragma unroll
+      for (int d = 0; d < kSeriesAhead; d++) if (d < T) rec_fetch(d, d);
+    }
     for (int i = 0; i < T; i++) {
       const int g = so + i;
       const int64_t sn = ka.series.n_paths;
@@ -822,9 +843,25 @@ struct Trial {
         for (int a = 0; a < kAssets; a++) s_er[a] = (R)sq_er[0][a];
         vix = (R)sq_vix[0]; s_reg = sq_reg[0]; s_cash = sq_cash[0];
       }
-      const int reg = MARKET == kMarketSeries ? s_reg : regime_next(rg);
+      R rec_pspy = (R)100;
+      if (FSER) {
+        int f = 0;
+#pragma unroll
+        for (int a = 0; a < kAssets; a++) s_er[a] = ((AM >> a) & 1) ? fq[0][f++] : (R)0;
+        const R v = fq[0][NF - 2];
+        vix = M::abs_(v); s_reg = v < (R)0 ? 1 : 0;              // VIX >= 10: the sign bit carries the regime
+        rec_pspy = fq[0][NF - 1];
+#pragma unroll
+        for (int d = 0; d + 1 < kSeriesAhead; d++) {
+#pragma unroll
+          for (int q = 0; q < NF; q++) fq[d][q] = fq[d + 1][q];
+        }
+        if (i + kSeriesAhead < T) rec_fetch(kSeriesAhead - 1, i + kSeriesAhead);
+      }
+      const int reg = SERIES ? s_reg : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
-      if (MARKET == kMarketSeries) {
+      if (FSER) {
+      } else if (MARKET == kMarketSeries) {
         x[2] = (R)sq_tlt[0];
 #pragma unroll
         for (int d = 0; d + 1 < kSeriesAhead; d++) {
@@ -843,7 +880,7 @@ struct Trial {
         market_day<true, true>(g, reg, js, x, vn, in);
       }
       R rf = p.const_rf;
-      if (MARKET != LETF_MARKET_NORMAL && MARKET != kMarketSeries) {
+      if (MARKET != LETF_MARKET_NORMAL && !SERIES) {
         vix = vix_step(g, reg, vix, x[0], vn);
         R irx = clipx(p.irx_base[reg] + ((R)0 + (R)0.5 * in), (R)0, (R)15);   // engine.py:117-123
         rf = EXACT ? clipx(irx, (R)0, (R)20) / (R)100 : clipx(irx, (R)0, (R)20) * (R)0.01;                                // engine.py:516
@@ -861,7 +898,7 @@ struct Trial {
       }
 
       // ---- latent stress + jump overlay (calibration.py:787-830, engine.py:502-512)
-      if (MARKET != kMarketSeries && MARKET != LETF_MARKET_NORMAL && p.has_stress) {   // params.py: no stress model with the iid-normal shapes
+      if (!SERIES && MARKET != LETF_MARKET_NORMAL && p.has_stress) {   // params.py: no stress model with the iid-normal shapes
         const DevStress<R>& sp = p.stress[reg];
         R jump = 0, sign = 1;
         if (i == 0) {
@@ -905,7 +942,7 @@ struct Trial {
 
       // ---- financing spread shared by all assets (engine.py:328-342, calibration.py:833-857)
       R spread_common = 0;
-      if (MARKET != kMarketSeries && p.has_funding) {
+      if (!SERIES && p.has_funding) {
         R irx_level = rf * (R)100;
         R term = p.has_stress ? (R)1.25 - (R)1.1 * clipx(cred, (R)0, (R)3) : (vix > (R)30 ? (R)-0.25 : (R)1.10);
         R tnx = irx_level + term;
@@ -927,8 +964,8 @@ struct Trial {
       for (int a = 0; a < NA; a++) {             // a = slot; aid = asset id (identical when NA == 6)
         const int aid = NA == kAssets ? a : p.act_id[a];
         R er;
-        if (MARKET == kMarketSeries) {
-          if (!ka.series.asset_ret[a]) continue;
+        if (SERIES) {
+          if (FSER ? !((AM >> a) & 1) : !ka.series.asset_ret[a]) continue;
           er = s_er[a];
         } else {
           if (AM != 0 && NA == kAssets ? !((AM >> a) & 1) : !p.act_on[a]) continue;
@@ -977,6 +1014,7 @@ struct Trial {
           er = EXACT ? clipr(lev + te, (R)-0.999, (R)10) : clipfast(lev + te, (R)-0.999, (R)10);
         }
         if (NA == kAssets) ret[a] = er;
+        if (FSER) continue;                     // prices and buy&hold statistics belong to the producer
         if (EXACT) {
           cp[a] = i == 0 ? (1.0 + (double)er) : cp[a] * (1.0 + (double)er);
           double pr = cp[a] * 100.0;
@@ -995,8 +1033,8 @@ struct Trial {
         if (EXACT) {
           cp_tlt = i == 0 ? (1.0 + (double)tlt) : cp_tlt * (1.0 + (double)tlt);
           if (!isfinite_(tlt) || !(cp_tlt > 0.0)) bad = true;
-        } else if (p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
-        if (p.bench_tlt) {
+        } else if (!FSER && p.bench_tlt) cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt);
+        if (!FSER && p.bench_tlt) {
           if (EXACT) {
             if (i == 0) ddT.init((double)p.W0 * cp_tlt);
             else ddT.step((double)p.W0 * cp_tlt, (R)1 + tlt);
@@ -1004,7 +1042,7 @@ struct Trial {
         }
       }
       const R cash = (MARKET == kMarketSeries && ka.series.cash_ret) ? s_cash : p.cash_daily[reg];
-      const R Pspy = NA == kAssets ? (R)(cp[NA == kAssets ? 4 : 0] * 100.0) : (R)100;
+      const R Pspy = FSER ? rec_pspy : (NA == kAssets ? (R)(cp[NA == kAssets ? 4 : 0] * 100.0) : (R)100);
 
       // ---- signals as of yesterday, then roll the windows forward with today's values
       R s_sma200 = nan_<R>(), s_sma200f = nan_<R>(), s_sma100 = nan_<R>(), s_rsi = nan_<R>(), s_mom = nan_<R>();
@@ -1305,7 +1343,7 @@ struct Trial {
       // fp32 mode defers the per-day validity checks: non-finite values and exhausted products are sticky
       if (chk != (R)0) flags |= LETF_FLAG_NONFINITE_RET;
       for (int a = 0; a < NA; a++) {
-        bool on = MARKET == kMarketSeries ? ka.series.asset_ret[a] != nullptr : p.act_on[a] != 0;
+        bool on = FSER ? false : (MARKET == kMarketSeries ? ka.series.asset_ret[a] != nullptr : p.act_on[a] != 0);
         if (on && T > 0 && !(cp[a] > 0.0 && isfinite_(cp[a]))) bad = true;
       }
       if (p.bench_tlt && T > 0 && !(cp_tlt > 0.0 && isfinite_(cp_tlt))) bad = true;
@@ -1318,6 +1356,7 @@ struct Trial {
       //  dynamic slot[s] forces the whole slot array - wealth, drawdown, trade counts - through local memory every day)
       if (s >= p.n_strat) continue;
       const int ty = p.strat[s].type;
+      if (FSER && (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT)) continue;       // written by the producer
       double fw = T > 0 ? slot[s].W : 0.0;
       double md = T > 1 ? slot[s].dd.value() : 0.0;
       if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) {
@@ -1336,6 +1375,7 @@ struct Trial {
       if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = JOURNAL ? sj[s].cnt : 0;
       if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = JOURNAL ? sj[s].vol : 0.0;
     }
+    if (FSER) return;                          // path metadata and validity flags are the producer's
     if (ka.out.start_offset) ka.out.start_offset[col] = so;
     if (ka.out.flags) ka.out.flags[col] = flags;
     if (ka.out.regime_days) { ka.out.regime_days[col] = T - reg_days1; ka.out.regime_days[N + col] = reg_days1; }   // NORMAL: reg_days1 stays 0

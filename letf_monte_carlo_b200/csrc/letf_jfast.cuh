@@ -86,8 +86,14 @@ static LETF_HDN float jf_jump_t5(uint32_t k0, uint32_t k1, uint32_t t0, uint32_t
 }
 
 // NACT: active ETF series (compacted slots 0 .. NACT-1); K10: bitmask of the slots whose tracking-error innovations are
-// t(10) (the others t(5))
-template <int NS, int NA, int NACT, int K10>
+// t(10) (the others t(5)).
+// EMIT: producer half of the split strategy pipeline (letf_api.cu launch_split).  Besides the buy&hold statistics the
+// thread writes, per simulated day and twin, the record the rule kernel consumes - the NACT layer returns, the VIX with
+// the regime in its sign bit, and the SPY price (last active slot) - day-major and field-major,
+// rec[(field * T + day) * ncol + column], so that both its own float2 stores (twins are adjacent columns) and the rule
+// kernel's loads (one thread per column, all on the same day) are coalesced.  Only benchmark-type strategy slots are
+// written by the producer; the rule kernel (Trial::run, MARKET == kMarketFSeries) writes the others.
+template <int NS, int NA, int NACT, int K10, bool EMIT = false>
 struct JointPair {
   typedef float R;
   typedef Mth<float> M;
@@ -255,6 +261,7 @@ struct JointPair {
     const float ema = (float)(2.0 / 127.0);
     const bool want_tlt = p.bench_tlt != 0;
 
+    const int64_t ecol = (pj - (ka.first_trial >> 1)) * 2;      // EMIT: this pair's first column (the chunk starts on an even trial)
     JF8 vnext;
     vnext.a0 = vnext.a1 = vnext.a2 = vnext.a3 = vnext.b0 = vnext.b1 = vnext.b2 = vnext.b3 = 0.0f;
     if (T > 0) vnext = jf_load(xs + so);
@@ -313,6 +320,7 @@ struct JointPair {
         const float jprob = clipx(fmaf(0.008f, vamp, jp_sh), 0.0f, 0.01f);
         hit[t] = i >= 1 && ju < jprob;
       }
+      float e_ret[2][NACT];                      // EMIT: the day's layer returns of both twins
       float sjv[2] = {0.0f, 0.0f};
       if (hit[0] || hit[1]) {
         const float jump = jf_jump_t5(key.k0, key.k1, key.t0, key.t1, (uint32_t)g) * c.jscale;
@@ -344,12 +352,23 @@ struct JointPair {
           cp[t][a] = ::fma(cp[t][a], (double)er, cp[t][a]);
           ddq[t][a] = fminf(1.0f, fmaf(ddq[t][a], er, ddq[t][a]));
           ddm[t][a] = fminf(ddm[t][a], ddq[t][a]);
+          if (EMIT) e_ret[t][a] = er;
         }
         if (want_tlt) {
           cp_tlt[t] = ::fma(cp_tlt[t], (double)tlt, cp_tlt[t]);
           tq[t] = fminf(1.0f, fmaf(tq[t], tlt, tq[t]));
           tm[t] = fminf(tm[t], tq[t]);
         }
+      }
+      if (EMIT) {
+        struct alignas(8) F2 { float a, b; };
+        const int64_t ncol = ka.rec_ncol;
+        F2* const base = (F2*)(ka.rec + (int64_t)i * ncol + ecol);
+        const int64_t fstride = (int64_t)T * ncol / 2;          // fields are T * ncol floats apart (ncol is even)
+#pragma unroll
+        for (int a = 0; a < NACT; a++) { F2 v; v.a = e_ret[0][a]; v.b = e_ret[1][a]; base[(int64_t)a * fstride] = v; }
+        { F2 v; v.a = u2f_(f2u_(vix[0]) | ((uint32_t)reg << 31)); v.b = u2f_(f2u_(vix[1]) | ((uint32_t)reg << 31)); base[(int64_t)NACT * fstride] = v; }
+        { F2 v; v.a = (float)(cp[0][NACT - 1] * 100.0); v.b = (float)(cp[1][NACT - 1] * 100.0); base[(int64_t)(NACT + 1) * fstride] = v; }
       }
     }
 
@@ -370,6 +389,7 @@ struct JointPair {
       if (T == 0 || bad || !(vmin[t] >= 5.0f) || !(vmax[t] <= 120.0f)) flags |= LETF_FLAG_REPAIRED;
       for (int s = 0; s < NS; s++) {
         if (s >= p.n_strat) break;
+        if (EMIT && p.strat[s].type != LETF_ST_BENCHMARK && p.strat[s].type != LETF_ST_BENCHMARK_TLT) continue;
         double c = 1.0; float qm = tm[t];
         if (p.strat[s].type == LETF_ST_BENCHMARK_TLT) c = cp_tlt[t];
         else {

@@ -41,11 +41,11 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
 
 // one antithetic pair per thread (letf_jfast.cuh): work item j = pair (first_trial >> 1) + j; a twin outside
 // [first_trial, first_trial + n_trials) is computed and not stored
-template <int NS, int NA, int NACT, int K10, int BLK, int MINB>
+template <int NS, int NA, int NACT, int K10, bool EMIT, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) letf_jpair_kernel(const __grid_constant__ KArgs<float, NS, NA> ka) {
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p0 = ka.first_trial >> 1, p1 = (ka.first_trial + ka.n_trials - 1) >> 1;
-  for (int64_t pj = p0 + lane; pj <= p1; pj += ka.nthreads) JointPair<NS, NA, NACT, K10>::run(ka, pj, lane);
+  for (int64_t pj = p0 + lane; pj <= p1; pj += ka.nthreads) JointPair<NS, NA, NACT, K10, EMIT>::run(ka, pj, lane);
 }
 
 // type-erased launcher table -----------------------------------------------------------------
@@ -98,26 +98,28 @@ struct KernelImpl {
   } reg_##ID;                                                                                            \
   }
 
-template <int NS, int NA, int NACT, int K10, int BLK, int MINB>
+template <int NS, int NA, int NACT, int K10, bool EMIT, int BLK, int MINB>
 struct JPairImpl {
   static cudaError_t launch(const void* kargs, int grid, cudaStream_t st) {
-    letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<float, NS, NA>*)kargs);
+    letf_jpair_kernel<NS, NA, NACT, K10, EMIT, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<float, NS, NA>*)kargs);
     return cudaGetLastError();
   }
   static cudaError_t attrs(cudaFuncAttributes* a, int* mb) {
-    cudaError_t e = cudaFuncGetAttributes(a, letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB>);
+    cudaError_t e = cudaFuncGetAttributes(a, letf_jpair_kernel<NS, NA, NACT, K10, EMIT, BLK, MINB>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_jpair_kernel<NS, NA, NACT, K10, BLK, MINB>, BLK, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_jpair_kernel<NS, NA, NACT, K10, EMIT, BLK, MINB>, BLK, 0);
   }
 };
+constexpr int kSplitProducer = 0x10000;      // KernelEntry::fj flag: EMIT build (producer of the split strategy pipeline)
 
-#define LETF_INSTANTIATE_JPAIR(ID, NS, NA, NACT, K10, BLK, MINB)                                         \
+#define LETF_INSTANTIATE_JPAIR(ID, NS, NA, NACT, K10, EMIT, BLK, MINB)                                   \
   namespace {                                                                                            \
   struct Reg_##ID {                                                                                      \
     Reg_##ID() {                                                                                         \
-      typedef letf::JPairImpl<NS, NA, NACT, K10, BLK, MINB> K;                                           \
+      typedef letf::JPairImpl<NS, NA, NACT, K10, EMIT, BLK, MINB> K;                                     \
       letf::KernelEntry e = {LETF_PREC_F32, NS, NA, LETF_MARKET_JOINT_T, 0, letf::TM_BENCH, 0, 0, BLK, 2, \
-                             letf::fast_joint_code(NACT, K10), #ID, &K::launch, &K::attrs,               \
+                             letf::fast_joint_code(NACT, K10) | (EMIT ? letf::kSplitProducer : 0), #ID,  \
+                             &K::launch, &K::attrs,                                                      \
                              sizeof(letf::KArgs<float, NS, NA>)};                                        \
       letf::register_kernel(e);                                                                          \
     }                                                                                                    \

@@ -174,6 +174,43 @@ extern "C" int letf_emu_run_typed(const LetfParams* sp, int list, const LetfOutp
   return -4;
 }
 
+// split strategy pipeline (letf_api.cu launch_split): the pair producer writes per-day records, the typed rule kernel body
+// (Trial::run in record mode) consumes them; Philox only, fp32
+template <int NS, int LIST, int AM, int NACT, int K10>
+static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
+  if (sp->n_strategies != slot_list_count(LIST) || sp->asset_mask != AM || sp->market_mode != LETF_MARKET_JOINT_T || (first & 1)) return -2;
+  for (int s = 0; s < sp->n_strategies; s++) if (sp->strategies[s].type != slot_list_type(LIST, s)) return -3;
+  static KArgs<float, 32, 4> kp;
+  static KArgs<float, NS, kAssets> kc;
+  memset(&kp, 0, sizeof(kp)); memset(&kc, 0, sizeof(kc));
+  const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
+  convert_params<float, 32, 4>(*sp, dd, kp.p);
+  convert_params<float, NS, kAssets>(*sp, dd, kc.p);
+  const int T = sp->sim_days, G = T + sp->buffer_days, NF = NACT + 2;
+  const int64_t cap = (n + 1) & ~(int64_t)1;
+  std::vector<float> rec((size_t)cap * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
+  float* xscr = (float*)aligned_alloc(32, ((size_t)(G > 0 ? G : 1) * 8 + 8) * sizeof(float));
+  kp.out = *out; kp.seed = seed; kp.first_trial = first; kp.n_trials = n; kp.rng_mode = LETF_RNG_PHILOX; kp.nthreads = 1;
+  kp.xscr = xscr; kp.rec = rec.data(); kp.rec_ncol = cap; kp.log_trial = -1;
+  for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<32, 4, NACT, K10, true>::run(kp, pj, 0);
+  kc.out = *out; kc.seed = seed; kc.first_trial = first; kc.n_trials = n; kc.rng_mode = LETF_RNG_PHILOX; kc.nthreads = 1;
+  kc.rec = rec.data(); kc.rec_ncol = cap; kc.log_trial = -1;
+  kc.p.T = T; kc.p.buffer = 0; kc.p.random_start = 0; kc.series.sim_days = T; kc.series.n_paths = n;
+  kc.ringP = rp.data(); kc.ringS = rs.data(); kc.ringA = ra.data();
+  for (int64_t j = 0; j < n; j++) {
+    Trial<float, NS, kAssets, kMarketFSeries, false, slot_list_mask(LIST), LIST, AM> t(kc, first + j, j, 0);
+    t.run();
+  }
+  free(xscr);
+  return 0;
+}
+extern "C" int letf_emu_run_split(const LetfParams* sp, int list, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
+  if (validate_params(*sp)) return -1;
+  if (list == 1) return run_split<8, 1, 25, 3, 4>(sp, out, seed, first, n);
+  if (list == 2) return run_split<32, 2, 29, 4, 8>(sp, out, seed, first, n);
+  return -4;
+}
+
 // materialised-path mode (run_strategy_fixed seam): caller-supplied series, optional journal + equity-curve log of one
 // (path, strategy), optional batch replay ids.  typed = 1 runs the typed 19-rule fp32 series build.
 template <typename R, int NS, bool TAPEIO, uint32_t TM, int LIST>

@@ -50,6 +50,8 @@ def lib():
         L.letf_emu_run_jpair.restype = C.c_int
         L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_typed.restype = C.c_int
+        L.letf_emu_run_split.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
+        L.letf_emu_run_split.restype = C.c_int
         L.letf_emu_run_series.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, C.POINTER(abi.Series), C.POINTER(abi.Outputs),
                                           C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.letf_emu_run_series.restype = C.c_int
@@ -134,6 +136,15 @@ def run_jpair(params, n, seed=0, first=0, force_generic=False):
     if rc != 0:
         raise RuntimeError(f"emu jpair rc={rc}")
     return out, int(used.value)
+
+
+def run_split(params, slot_list, n, seed=0, first=0):
+    """split strategy pipeline (pair producer -> per-day records -> typed rule kernel body), slot lists as run_typed"""
+    out = HostOutputs(params.n_strategies, n)
+    rc = lib().letf_emu_run_split(C.byref(params), slot_list, C.byref(out.as_struct()), seed, first, n)
+    if rc != 0:
+        raise RuntimeError(f"emu split rc={rc}")
+    return out
 
 
 def run_typed(params, slot_list, n, seed=0, first=0):

@@ -474,6 +474,43 @@ def test_typed_slot_kernels_vs_generic_and_oracle(sids, variant, engine_lib):
     assert regs_typed > 0 and regs_typed != 227        # 227 = the generic f32_joint_t_all build: a typed build ran
 
 
+@pytest.mark.parametrize("sids", [["S1", "S2", "S4", "S5", "S6", "S19"], ALL19], ids=["c4_list", "sweep19_list"])
+def test_split_pipeline_vs_fused_generic_and_oracle(sids, engine_lib, monkeypatch):
+    """The split strategy pipeline (pair producer -> per-day records in HBM -> typed rule kernel) is what runs for the c4 and
+    default-sweep shapes.  On the device: split == fused typed build (LETF_NO_SPLIT=1) on the same Philox counters to fp32
+    reassociation, identical path metadata; and the fp64 oracle replaying the tape the generic build recorded agrees."""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    n_t = 160
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    with _engine(params, keep, "f32") as eng:
+        split = eng.run_host(2 * n_t, seed=99)
+        info = eng.launch_info()
+        assert "prod" in info["kernel"] and "rules" in info["kernel"] and info["kernel_launches"] == 2
+        odd = eng.run_host(7, seed=99)                                        # odd count: last twin computed, not stored
+        off = eng.run_host(10, seed=99, first_trial=4)
+        gen = eng.run_host(2 * n_t, seed=99, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+    monkeypatch.setenv("LETF_NO_SPLIT", "1")
+    with _engine(params, keep, "f32") as eng:
+        fused = eng.run_host(2 * n_t, seed=99)
+        assert "prod" not in eng.launch_info()["kernel"]
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=2e-3)
+    assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 5e-6
+    assert np.mean(split.num_trades != fused.num_trades) < 0.01
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+    np.testing.assert_array_equal(odd.final_wealth, split.final_wealth[:, :7])
+    np.testing.assert_array_equal(off.final_wealth, split.final_wealth[:, 4:14])
+    np.testing.assert_array_equal(off.num_trades, split.num_trades[:, 4:14])
+    rel = np.abs(split.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
+    assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97, (np.median(rel), np.mean(rel < 1e-2))
+    assert np.mean(split.num_trades != o.num_trades) < 0.03
+    np.testing.assert_array_equal(split.regime_days, o.regime_days)
+    np.testing.assert_array_equal(split.start_offset, o.start_offset)
+    np.testing.assert_array_equal(split.jump_days, o.jump_days)
+
+
 def test_edge_sizes_and_offsets(engine_lib):
     """empty launch, single trial, odd trial counts and odd first_trial with antithetic pairing, the tail of the
     two-trials-per-thread fast path"""

@@ -315,6 +315,27 @@ def test_typed_slot_builds_match_dynamic_dispatch(slot_list, sids):
     np.testing.assert_array_equal(typed.regime_days, gen.regime_days)
 
 
+@pytest.mark.parametrize("slot_list,sids", [(1, ["S1", "S2", "S4", "S5", "S6", "S19"]), (2, ALL19)])
+def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
+    """The split strategy pipeline (what the c4 / default-sweep shapes run): the antithetic-pair producer writes per-day
+    records (layer returns, VIX + regime, SPY price), the typed rule kernel body consumes them.  Same Philox counters as
+    the fused typed build: market state identical, wealth to fp32 reassociation, trade decisions almost everywhere equal."""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
+    split = emu.run_split(params, slot_list, 48, seed=5)
+    fused = emu.run_typed(params, slot_list, 48, seed=5)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
+    assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 2e-6
+    np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
+    assert np.mean(split.num_trades != fused.num_trades) < 0.01
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+    # an odd number of trials (the last pair's second twin is computed and not stored)
+    part = emu.run_split(params, slot_list, 7, seed=5)
+    np.testing.assert_array_equal(part.final_wealth, split.final_wealth[:, :7])
+    np.testing.assert_array_equal(part.num_trades, split.num_trades[:, :7])
+
+
 def test_lean_fast_variant_config1_shape():
     """BASELINE config 1 (validation.py:33-57): one frictionless 3x series - the straight-line loop draws no
     tracking-error block at all; against the lean build's general loop and the generic build on the same counters"""
