@@ -591,6 +591,19 @@ struct Trial {
     int cP, cS, cA;         // ring cursors = day index modulo ring depth
   };
 
+  // fp32 throughput mode: plain sliding sums instead of pandas' compensated online kernels.  Returns have |mean| << std, so
+  // the variance / skew from raw power sums is well conditioned; the sums are refreshed from the window's history every
+  // kRefresh days (uniform: every thread is on the same day), which bounds the add/subtract drift.
+  struct FastSig {
+    R a1[4], a2[4];         // sum r, sum r^2 over the last 5 / 10 / 20 / 60 returns of the signal asset
+    R a3;                   // sum r^3 over the last 60
+    R d1, d2;               // sum min(r, 0) and its square over the last 20 (downside vol)
+    R p200, p100;           // SPY price sums
+    R g14, l14;             // RSI: gains / losses over the last 14 price differences
+    R m126;                 // SPY return sum (momentum)
+  };
+  static constexpr int kRefresh = 128;
+
   struct Slot {
     double W;               // equity (always fp64: 7 560 multiplicative steps)
     Drawdown<R> dd;
@@ -754,6 +767,9 @@ struct Trial {
     sg.v5.init(); sg.v10.init(); sg.v20.init(); sg.v60.init(); sg.dv20.init(); sg.sk60.init();
     for (int i = 0; i < 6; i++) sg.volhist[i] = nan_<R>();
     sg.P_prev = nan_<R>(); sg.vix_prev = nan_<R>(); sg.cP = sg.cS = sg.cA = 0;
+    FastSig fs;
+    for (int q = 0; q < 4; q++) { fs.a1[q] = 0; fs.a2[q] = 0; }
+    fs.a3 = fs.d1 = fs.d2 = fs.p200 = fs.p100 = fs.g14 = fs.l14 = fs.m126 = (R)0;
 
     // ---- burn-in: generated days before the window (only the VIX recursion consumes them)
     for (int g = 0; g < so; g++) {
@@ -812,18 +828,44 @@ struct Trial {
 #pragma unroll
       for (int d = 0; d < kSeriesAhead; d++) if (d < T) rec_fetch(d, d);
     }
-    for (int i = 0; i < T; i++) {
+    // one simulated day.  steady_c = true_type: i >= kSteady, every rolling window is full (fp32 builds: the per-window
+    // observation counts, their reciprocals and the warm-up predicates are compile-time constants in that copy of the body)
+    constexpr int kSteady = 256;
+    auto day_step = [&](const int i, auto steady_c) {
+      constexpr bool STEADY = decltype(steady_c)::value;
       const int g = so + i;
       const int64_t sn = ka.series.n_paths;
       const X4 vcur = vnext;
       const R icur = inext;
       if (two_pass && i + 1 < T) { vnext = xs[g + 1]; if (AUXSCR) inext = is[g + 1]; }
-      R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0;
-      if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
+      R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0, pf_p14 = 0, pf_p15 = 0;
+      if (FSER) {
+        // record mode: the values a window retires are the records of earlier days - coalesced loads at constant offsets
+        // from today's row, no ring, no cursor arithmetic
+        const float* r0 = ka.rec + (int64_t)i * ka.rec_ncol + col;
+        const int64_t nc = ka.rec_ncol, fstride = (int64_t)T * ka.rec_ncol;
+        const float* rp = r0 + (NF - 1) * fstride;        // SPY price
+        const float* rs_ = r0 + (NF - 3) * fstride;       // SPY return (last return field)
+        if (HAS_SMA200 && (STEADY || i >= 200)) pf_p200 = rp[-200 * nc];
+        if (HAS_SMA100 && (STEADY || i >= 100)) pf_p100 = rp[-100 * nc];
+        if (HAS_RSI && (STEADY || i >= 15)) { pf_p14 = rp[-14 * nc]; pf_p15 = rp[-15 * nc]; }
+        if (NEED_RINGS && (STEADY || i >= 126)) pf_s126 = rs_[-126 * nc];
+        if (NEED_RINGA) {
+          if ((STEADY || i >= 60) && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) pf_r60 = r0[-60 * nc];
+          if ((STEADY || i >= 20) && (HAS_V20 || HAS_DV20)) pf_r20 = r0[-20 * nc];
+          if ((STEADY || i >= 10) && HAS_V10) pf_r10 = r0[-10 * nc];
+          if ((STEADY || i >= 5) && HAS_V5) pf_r5 = r0[-5 * nc];
+        }
+      } else if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
         if (NEED_RINGP) {
           const R* ring = ka.ringP + lane;
           if (HAS_SMA200 && i >= 200) pf_p200 = ring[roff(sg.cP)];
           if (HAS_SMA100 && i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; pf_p100 = ring[roff(c)]; }
+          if (HAS_RSI && i >= 15) {
+            int c1 = sg.cP - 14; if (c1 < 0) c1 += kRingP;
+            int c2 = sg.cP - 15; if (c2 < 0) c2 += kRingP;
+            pf_p14 = ring[roff(c1)]; pf_p15 = ring[roff(c2)];
+          }
         }
         if (NEED_RINGS && i >= 126) pf_s126 = (ka.ringS + lane)[roff(sg.cS)];
         if (NEED_RINGA) {
@@ -1050,79 +1092,209 @@ struct Trial {
       R s_dv20 = nan_<R>(), s_dv20f = nan_<R>(), s_sk = nan_<R>(), s_mean60 = nan_<R>(), s_vm = nan_<R>(), s_v20_today = nan_<R>();
       const R P_prev = sg.P_prev, vix_prev = sg.vix_prev;
       const R ra = LIST != 0 ? ret[0] : pick6(ret, p.sig_asset);
-      if (i >= 1) {
-        if (HAS_SMA200) { s_sma200 = sg.sma200.mean(1); s_sma200f = sg.sma200.mean(200); }
-        if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
-        if (HAS_RSI) {
-          R gm = sg.gain14.mean(14), lm = sg.loss14.mean(14);
-          R rs = M::div_(gm, lm);
-          s_rsi = (R)100 - M::div_((R)100, (R)1 + rs);
-        }
-        if (HAS_MOM) s_mom = sg.mom126.sum(1);
-        if (HAS_V5) s_v5 = sg.v5.stdev(1) * V;
-        if (HAS_V10) s_v10 = sg.v10.stdev(1) * V;
-        if (HAS_V20) { s_v20 = sg.v20.stdev(1) * V; s_v20f = sg.v20.stdev(20) * V; }
-        if (HAS_V60) s_v60 = sg.v60.stdev(1) * V;
-        if (HAS_DV20) { s_dv20 = sg.dv20.stdev(1) * V; s_dv20f = sg.dv20.stdev(20) * V; }
-        if (HAS_SKEW) s_sk = sg.sk60.skew(1);
-        if (HAS_MEAN60) s_mean60 = sg.mean60.mean(1) * (R)252;
-      }
-      if (HAS_VOLMOM) {
-        // vol_slow.pct_change(5): shifted 20-day vol today vs five rows earlier
-        for (int q = 5; q >= 1; q--) sg.volhist[q] = sg.volhist[q - 1];
-        sg.volhist[0] = s_v20;
-        s_vm = M::div_(sg.volhist[0], sg.volhist[5]) - (R)1;
-      }
-      // roll forward (pandas: removals first, then the new observation)
-      if (NEED_RINGP) {
-        R* ring = ka.ringP + lane;
-        if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(EXACT ? ring[roff(sg.cP)] : pf_p200); sg.sma200.add(Pspy); }
-        if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(EXACT ? ring[roff(c)] : pf_p100); } sg.sma100.add(Pspy); }
-        if (HAS_RSI) {
-          if (i >= 14) {
-            R dg = 0, dl = -(R)0;
-            if (i >= 15) {
-              int c1 = sg.cP - 14; if (c1 < 0) c1 += kRingP;
-              int c2 = sg.cP - 15; if (c2 < 0) c2 += kRingP;
-              R dlt = ring[roff(c1)] - ring[roff(c2)];
-              dg = dlt > (R)0 ? dlt : (R)0;
-              dl = -(dlt < (R)0 ? dlt : (R)0);
-            }
-            sg.gain14.remove(dg); sg.loss14.remove(dl);
+      if (EXACT) {
+        if (i >= 1) {
+          if (HAS_SMA200) { s_sma200 = sg.sma200.mean(1); s_sma200f = sg.sma200.mean(200); }
+          if (HAS_SMA100) s_sma100 = sg.sma100.mean(1);
+          if (HAS_RSI) {
+            R gm = sg.gain14.mean(14), lm = sg.loss14.mean(14);
+            R rs = M::div_(gm, lm);
+            s_rsi = (R)100 - M::div_((R)100, (R)1 + rs);
           }
-          R dlt = i == 0 ? nan_<R>() : Pspy - P_prev;
-          sg.gain14.add(dlt > (R)0 ? dlt : (R)0);
-          sg.loss14.add(-(dlt < (R)0 ? dlt : (R)0));
+          if (HAS_MOM) s_mom = sg.mom126.sum(1);
+          if (HAS_V5) s_v5 = sg.v5.stdev(1) * V;
+          if (HAS_V10) s_v10 = sg.v10.stdev(1) * V;
+          if (HAS_V20) { s_v20 = sg.v20.stdev(1) * V; s_v20f = sg.v20.stdev(20) * V; }
+          if (HAS_V60) s_v60 = sg.v60.stdev(1) * V;
+          if (HAS_DV20) { s_dv20 = sg.dv20.stdev(1) * V; s_dv20f = sg.dv20.stdev(20) * V; }
+          if (HAS_SKEW) s_sk = sg.sk60.skew(1);
+          if (HAS_MEAN60) s_mean60 = sg.mean60.mean(1) * (R)252;
         }
-        ring[roff(sg.cP)] = Pspy;
-        sg.cP = sg.cP + 1 == kRingP ? 0 : sg.cP + 1;
-      }
-      if (NEED_RINGS) {
-        R* ring = ka.ringS + lane;
-        if (i >= 126) sg.mom126.remove(EXACT ? ring[roff(sg.cS)] : pf_s126);
-        sg.mom126.add(ret[4]);
-        ring[roff(sg.cS)] = ret[4];
-        sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
-      }
-      if (NEED_RINGA) {
-        R* ring = ka.ringA + lane;
-        R r60 = pf_r60, r20 = pf_r20, r10 = pf_r10, r5 = pf_r5;
-        if (EXACT) {
-          if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[roff(sg.cA)];
-          if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[roff(c)]; }
-          if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[roff(c)]; }
-          if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[roff(c)]; }
+        if (HAS_VOLMOM) {
+          // vol_slow.pct_change(5): shifted 20-day vol today vs five rows earlier
+          for (int q = 5; q >= 1; q--) sg.volhist[q] = sg.volhist[q - 1];
+          sg.volhist[0] = s_v20;
+          s_vm = M::div_(sg.volhist[0], sg.volhist[5]) - (R)1;
         }
-        if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar_(sg.v5, ring, nth, sg.cA, 5, false); sg.v5.add(ra); }
-        if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar_(sg.v10, ring, nth, sg.cA, 10, false); sg.v10.add(ra); }
-        if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar_(sg.v20, ring, nth, sg.cA, 20, false); sg.v20.add(ra); }
-        if (HAS_V60) { if (i >= 60 && sg.v60.remove(r60)) revar_(sg.v60, ring, nth, sg.cA, 60, false); sg.v60.add(ra); }
-        if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar_(sg.dv20, ring, nth, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
-        if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
-        if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
-        ring[roff(sg.cA)] = ra;
-        sg.cA = sg.cA + 1 == kRingA ? 0 : sg.cA + 1;
-        if (TM_HAS(LETF_ST_VOL_TARGETING)) s_v20_today = sg.v20.stdev(20) * V;   // strategy.py:255 (unshifted)
+        // roll forward (pandas: removals first, then the new observation)
+        if (NEED_RINGP) {
+          R* ring = ka.ringP + lane;
+          if (HAS_SMA200) { if (i >= 200) sg.sma200.remove(EXACT ? ring[roff(sg.cP)] : pf_p200); sg.sma200.add(Pspy); }
+          if (HAS_SMA100) { if (i >= 100) { int c = sg.cP - 100; if (c < 0) c += kRingP; sg.sma100.remove(EXACT ? ring[roff(c)] : pf_p100); } sg.sma100.add(Pspy); }
+          if (HAS_RSI) {
+            if (i >= 14) {
+              R dg = 0, dl = -(R)0;
+              if (i >= 15) {
+                int c1 = sg.cP - 14; if (c1 < 0) c1 += kRingP;
+                int c2 = sg.cP - 15; if (c2 < 0) c2 += kRingP;
+                R dlt = ring[roff(c1)] - ring[roff(c2)];
+                dg = dlt > (R)0 ? dlt : (R)0;
+                dl = -(dlt < (R)0 ? dlt : (R)0);
+              }
+              sg.gain14.remove(dg); sg.loss14.remove(dl);
+            }
+            R dlt = i == 0 ? nan_<R>() : Pspy - P_prev;
+            sg.gain14.add(dlt > (R)0 ? dlt : (R)0);
+            sg.loss14.add(-(dlt < (R)0 ? dlt : (R)0));
+          }
+          ring[roff(sg.cP)] = Pspy;
+          sg.cP = sg.cP + 1 == kRingP ? 0 : sg.cP + 1;
+        }
+        if (NEED_RINGS) {
+          R* ring = ka.ringS + lane;
+          if (i >= 126) sg.mom126.remove(EXACT ? ring[roff(sg.cS)] : pf_s126);
+          sg.mom126.add(ret[4]);
+          ring[roff(sg.cS)] = ret[4];
+          sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
+        }
+        if (NEED_RINGA) {
+          R* ring = ka.ringA + lane;
+          R r60 = pf_r60, r20 = pf_r20, r10 = pf_r10, r5 = pf_r5;
+          if (EXACT) {
+            if (i >= 60 && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) r60 = ring[roff(sg.cA)];
+            if (i >= 20 && (HAS_V20 || HAS_DV20)) { int c = sg.cA - 20; if (c < 0) c += kRingA; r20 = ring[roff(c)]; }
+            if (i >= 10 && HAS_V10) { int c = sg.cA - 10; if (c < 0) c += kRingA; r10 = ring[roff(c)]; }
+            if (i >= 5 && HAS_V5) { int c = sg.cA - 5; if (c < 0) c += kRingA; r5 = ring[roff(c)]; }
+          }
+          if (HAS_V5) { if (i >= 5 && sg.v5.remove(r5)) revar_(sg.v5, ring, nth, sg.cA, 5, false); sg.v5.add(ra); }
+          if (HAS_V10) { if (i >= 10 && sg.v10.remove(r10)) revar_(sg.v10, ring, nth, sg.cA, 10, false); sg.v10.add(ra); }
+          if (HAS_V20) { if (i >= 20 && sg.v20.remove(r20)) revar_(sg.v20, ring, nth, sg.cA, 20, false); sg.v20.add(ra); }
+          if (HAS_V60) { if (i >= 60 && sg.v60.remove(r60)) revar_(sg.v60, ring, nth, sg.cA, 60, false); sg.v60.add(ra); }
+          if (HAS_DV20) { if (i >= 20 && sg.dv20.remove(r20 < (R)0 ? r20 : (R)0)) revar_(sg.dv20, ring, nth, sg.cA, 20, true); sg.dv20.add(ra < (R)0 ? ra : (R)0); }
+          if (HAS_SKEW) { if (i >= 60) sg.sk60.remove(r60); sg.sk60.add(ra); }
+          if (HAS_MEAN60) { if (i >= 60) sg.mean60.remove(r60); sg.mean60.add(ra); }
+          ring[roff(sg.cA)] = ra;
+          sg.cA = sg.cA + 1 == kRingA ? 0 : sg.cA + 1;
+          if (TM_HAS(LETF_ST_VOL_TARGETING)) s_v20_today = sg.v20.stdev(20) * V;   // strategy.py:255 (unshifted)
+        }
+      } else {
+        // ---- fp32: sliding power sums (FastSig).  n(w) = min(i, w) observations are in the state "as of yesterday"
+        R ri = (R)0, rim1 = (R)0;
+        if (!STEADY) { ri = i > 0 ? M::div_((R)1, (R)i) : (R)0; rim1 = i > 1 ? M::div_((R)1, (R)(i - 1)) : (R)0; }
+        auto inv = [&](int w) -> R { return (STEADY || i >= w) ? (R)(1.0 / w) : ri; };
+        auto invm1 = [&](int w) -> R { return (STEADY || i >= w) ? (R)(1.0 / (w - 1)) : rim1; };
+        auto sdev = [&](R s1, R s2, int w) -> R {      // rolling(w).std() * sqrt(252) from the window's power sums
+          const R var = rmax(M::fma_(-s1 * inv(w), s1, s2), (R)0) * invm1(w);
+          return M::sqrt_(var) * V;
+        };
+        if (STEADY || i >= 1) {
+          if (HAS_SMA200) { s_sma200 = fs.p200 * inv(200); if (STEADY || i >= 200) s_sma200f = s_sma200; }
+          if (HAS_SMA100) s_sma100 = fs.p100 * inv(100);
+          if (HAS_RSI && (STEADY || i >= 14)) s_rsi = (R)100 - M::div_((R)100, (R)1 + M::div_(fs.g14, fs.l14));
+          if (HAS_MOM) s_mom = fs.m126;
+          if (HAS_MEAN60) s_mean60 = fs.a1[3] * inv(60) * (R)252;
+        }
+        if (STEADY || i >= 2) {
+          if (HAS_V5) s_v5 = sdev(fs.a1[0], fs.a2[0], 5);
+          if (HAS_V10) s_v10 = sdev(fs.a1[1], fs.a2[1], 10);
+          if (HAS_V20) { s_v20 = sdev(fs.a1[2], fs.a2[2], 20); if (STEADY || i >= 20) s_v20f = s_v20; }
+          if (HAS_V60) s_v60 = sdev(fs.a1[3], fs.a2[3], 60);
+          if (HAS_DV20) { s_dv20 = sdev(fs.d1, fs.d2, 20); if (STEADY || i >= 20) s_dv20f = s_dv20; }
+        }
+        if (HAS_SKEW && (STEADY || i >= 3)) {
+          // bias-corrected sample skewness (pandas rolling.skew) of the last n = min(i, 60) returns
+          const R n = (STEADY || i >= 60) ? (R)60 : (R)i, in_ = inv(60);
+          const R k = (STEADY || i >= 60) ? (R)1.0258258469409323                      // sqrt(n (n-1)) / (n-2) at n = 60
+                                          : M::div_(M::sqrt_(n * (n - (R)1)), n - (R)2);
+          const R m = fs.a1[3] * in_;
+          const R M2 = M::fma_(-fs.a1[3], m, fs.a2[3]);                                // sum (r - m)^2
+          const R M3 = M::fma_((R)2 * m * m, fs.a1[3], M::fma_((R)-3 * m, fs.a2[3], fs.a3));   // sum (r - m)^3
+          const R B = M2 * in_;
+          const R rb = M::rsqrt_(rmax(B, (R)1e-30));
+          s_sk = B <= (R)1e-14 ? nan_<R>() : k * (M3 * in_) * (rb * rb * rb);
+        }
+        if (HAS_VOLMOM) {
+          for (int q = 5; q >= 1; q--) sg.volhist[q] = sg.volhist[q - 1];
+          sg.volhist[0] = s_v20;
+          s_vm = M::div_(sg.volhist[0], sg.volhist[5]) - (R)1;
+        }
+        // roll forward: subtract the value each window retires (0 while the window is still filling), add today's
+        if (NEED_RINGP) {
+          if (HAS_SMA200) fs.p200 += Pspy - pf_p200;
+          if (HAS_SMA100) fs.p100 += Pspy - pf_p100;
+          if (HAS_RSI) {
+            const R dold = pf_p14 - pf_p15;                       // price difference of day i - 14 (0 before day 15)
+            const R dnew = (STEADY || i >= 1) ? Pspy - P_prev : (R)0;
+            fs.g14 += rmax(dnew, (R)0) - rmax(dold, (R)0);
+            fs.l14 += rmax(-dnew, (R)0) - rmax(-dold, (R)0);
+          }
+          if (!FSER) {
+            R* ring = ka.ringP + lane;
+            ring[roff(sg.cP)] = Pspy;
+            sg.cP = sg.cP + 1 == kRingP ? 0 : sg.cP + 1;
+          }
+        }
+        if (NEED_RINGS) {
+          fs.m126 += ret[4] - pf_s126;
+          if (!FSER) {
+            R* ring = ka.ringS + lane;
+            ring[roff(sg.cS)] = ret[4];
+            sg.cS = sg.cS + 1 == kRingS ? 0 : sg.cS + 1;
+          }
+        }
+        if (NEED_RINGA) {
+          const R olds[4] = {pf_r5, pf_r10, pf_r20, pf_r60};
+          const bool need[4] = {HAS_V5, HAS_V10, HAS_V20, HAS_V60 || HAS_SKEW || HAS_MEAN60};
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (need[q]) {
+            fs.a1[q] += ra - olds[q];
+            fs.a2[q] = M::fma_(-olds[q], olds[q], M::fma_(ra, ra, fs.a2[q]));
+          }
+          if (HAS_SKEW) fs.a3 = M::fma_(-pf_r60 * pf_r60, pf_r60, M::fma_(ra * ra, ra, fs.a3));
+          if (HAS_DV20) {
+            const R dn = rmin(ra, (R)0), dol = rmin(pf_r20, (R)0);
+            fs.d1 += dn - dol;
+            fs.d2 = M::fma_(-dol, dol, M::fma_(dn, dn, fs.d2));
+          }
+          if (!FSER) {
+            R* ring = ka.ringA + lane;
+            ring[roff(sg.cA)] = ra;
+            sg.cA = sg.cA + 1 == kRingA ? 0 : sg.cA + 1;
+          }
+          if (TM_HAS(LETF_ST_VOL_TARGETING) && (STEADY || i >= 19)) {                  // strategy.py:255 (unshifted): n = min(i + 1, 20)
+            const R var = rmax(M::fma_(-fs.a1[2] * (R)(1.0 / 20), fs.a1[2], fs.a2[2]), (R)0) * (R)(1.0 / 19);
+            s_v20_today = M::sqrt_(var) * V;
+          }
+        }
+        // drift control: every kRefresh days rebuild the sums from the windows' history (today's value included)
+        if (STEADY && (i & (kRefresh - 1)) == kRefresh - 1) {
+          auto hist = [&](int which, int back) -> R {          // value `back` days ago (0 = today) of series 0: signal return, 1: SPY return, 2: SPY price
+            if (FSER) {
+              const int f = which == 0 ? 0 : (which == 1 ? NF - 3 : NF - 1);
+              return (R)ka.rec[((int64_t)f * T + (i - back)) * ka.rec_ncol + col];
+            }
+            const int depth = which == 0 ? kRingA : (which == 1 ? kRingS : kRingP);
+            int c = (which == 0 ? sg.cA : (which == 1 ? sg.cS : sg.cP)) - 1 - back;    // cursors already point at tomorrow's slot
+            if (c < 0) c += depth;
+            const R* ring = which == 0 ? ka.ringA : (which == 1 ? ka.ringS : ka.ringP);
+            return (ring + lane)[roff(c)];
+          };
+          if (NEED_RINGA) {
+            R t1 = 0, t2 = 0, t3 = 0, e1 = 0, e2 = 0;
+            for (int b = 0; b < 60; b++) {
+              const R v = hist(0, b);
+              t1 += v; t2 = M::fma_(v, v, t2); t3 = M::fma_(v * v, v, t3);
+              if (b < 20) { const R dn = rmin(v, (R)0); e1 += dn; e2 = M::fma_(dn, dn, e2); }
+              if (b == 4) { fs.a1[0] = t1; fs.a2[0] = t2; }
+              if (b == 9) { fs.a1[1] = t1; fs.a2[1] = t2; }
+              if (b == 19) { fs.a1[2] = t1; fs.a2[2] = t2; fs.d1 = e1; fs.d2 = e2; }
+            }
+            fs.a1[3] = t1; fs.a2[3] = t2; fs.a3 = t3;
+          }
+          if (NEED_RINGS) { R t = 0; for (int b = 0; b < 126; b++) t += hist(1, b); fs.m126 = t; }
+          if (NEED_RINGP) {
+            R t = 0, gq = 0, lq = 0, newer = 0;
+            for (int b = 0; b < 200; b++) {
+              const R v = hist(2, b);
+              if (HAS_RSI && b >= 1 && b <= 14) { const R d = newer - v; gq += rmax(d, (R)0); lq += rmax(-d, (R)0); }
+              newer = v;
+              t += v;
+              if (b == 99) fs.p100 = t;
+            }
+            fs.p200 = t;
+            if (HAS_RSI) { fs.g14 = gq; fs.l14 = lq; }
+          }
+        }
       }
       sg.P_prev = Pspy; sg.vix_prev = vix;
 
@@ -1146,9 +1318,16 @@ struct Trial {
           bool buy = P_prev >= thr, sell = P_prev < thr;
           int pos_prev = (int)sl.aux, pos = pos_prev == 0 ? (buy ? 1 : 0) : (sell ? 0 : 1);
           r_strat = pos == 1 ? r_asset : cash;
-          if (pos != pos_prev) {
-            sl.trades++;
-            if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * lev_asset * M::abs_(r_asset) + (R)0;
+          if (EXACT) {
+            if (pos != pos_prev) {
+              sl.trades++;
+              if (p.apply_costs) r_strat -= p.spread_cost[reg] + p.rebalance_cost * lev_asset * M::abs_(r_asset) + (R)0;
+            }
+          } else {
+            const bool sw = pos != pos_prev;
+            sl.trades += sw ? 1 : 0;
+            const R tc = p.spread_cost[reg] + p.rebalance_cost * lev_asset * M::abs_(r_asset);
+            if (p.apply_costs) r_strat -= sw ? tc : (R)0;
           }
           sl.aux = (R)pos;
         }
@@ -1296,22 +1475,38 @@ struct Trial {
             } break;
             default: break;
           }
-          if (skip) { sl.dd.step(sl.W, (R)1); return; }
-          R prev_alloc = sl.aux;
-          R turnover = M::abs_(alloc - prev_alloc), cost = 0;
-          if (turnover > thresh) {
-            sl.trades++;
-            if (JOURNAL && st.taxable) jlog(sj[s], 0, s, i, st.asset, alloc, sl.W, (R)(cp[st.asset] * 100.0));
-            cost = turnover * (R)0.0003;
-            sl.aux = alloc;
+          if (EXACT || JOURNAL) {
+            if (skip) { sl.dd.step(sl.W, (R)1); return; }
+            R prev_alloc = sl.aux;
+            R turnover = M::abs_(alloc - prev_alloc), cost = 0;
+            if (turnover > thresh) {
+              sl.trades++;
+              if (JOURNAL && st.taxable) jlog(sj[s], 0, s, i, st.asset, alloc, sl.W, (R)(cp[st.asset] * 100.0));
+              cost = turnover * (R)0.0003;
+              sl.aux = alloc;
+            } else {
+              if (sticky) alloc = prev_alloc; else sl.aux = alloc;
+            }
+            r_strat = cashleg ? (alloc * r_asset) + (((R)1 - alloc) * cash) : r_asset * alloc;
+            if (p.apply_costs) r_strat -= cost;
           } else {
-            if (sticky) alloc = prev_alloc; else sl.aux = alloc;
+            // same decisions without divergent branches (fp32 throughput builds keep no journal)
+            const R prev_alloc = sl.aux;
+            if (skip) alloc = prev_alloc;                      // strategy.py: the day is skipped, allocation state unchanged
+            const R turnover = M::abs_(alloc - prev_alloc);
+            const bool traded = turnover > thresh;
+            sl.trades += traded ? 1 : 0;
+            const R cost = traded ? turnover * (R)0.0003 : (R)0;
+            if (sticky) alloc = traded ? alloc : prev_alloc;
+            sl.aux = alloc;
+            r_strat = cashleg ? (alloc * r_asset) + (((R)1 - alloc) * cash) : r_asset * alloc;
+            if (p.apply_costs) r_strat -= cost;
+            if (skip) r_strat = (R)0;
           }
-          r_strat = cashleg ? (alloc * r_asset) + (((R)1 - alloc) * cash) : r_asset * alloc;
-          if (p.apply_costs) r_strat -= cost;
         }
         growth = (R)1 + r_strat;
-        sl.W = sl.W * (1.0 + (double)r_strat);
+        if (EXACT) sl.W = sl.W * (1.0 + (double)r_strat);
+        else sl.W = ::fma(sl.W, (double)r_strat, sl.W);
         sl.dd.step(sl.W, growth);
       };
       if (HAS_ACTIVE && i >= 1) {         // active strategies leave equity[0] = W0
@@ -1333,6 +1528,13 @@ struct Trial {
         }
         ka.log_curve[i] = w;
       }
+    };
+    if (EXACT) {
+      for (int i = 0; i < T; i++) day_step(i, std::false_type{});
+    } else {
+      const int warm = T < kSteady ? T : kSteady;
+      for (int i = 0; i < warm; i++) day_step(i, std::false_type{});
+      for (int i = warm; i < T; i++) day_step(i, std::true_type{});
     }
 
     // ---- per-trial outputs (engine.py:578-603)

@@ -1,6 +1,6 @@
 """Executed-instruction mix of one kernel from an ncu report's SASS source page.
 
-usage: python scripts/ncu_sass_mix.py report.ncu-rep [path_days] [--blocks]
+usage: python scripts/ncu_sass_mix.py report.ncu-rep [path_days] [--blocks] [--kernel=REGEX]
 Prints warp-level executed instructions by opcode class (and per basic block with --blocks),
 divided by `path_days / 32` when given, i.e. instructions per path-day per lane.
 """
@@ -8,7 +8,9 @@ import csv, io, subprocess, sys, collections, re
 
 rep = sys.argv[1]
 pd = float(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else None
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+ksel = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--kernel=")]
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + ksel[0]] if ksel else []),
+                     capture_output=True, text=True).stdout
 lines = txt.splitlines()
 hdr_i = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[hdr_i:]))))

@@ -66,7 +66,7 @@ def test_f32_kernel_body_close_to_reference_at_30_years(name):
     out = emu.run(params, tape, precision=abi.PREC_F32, rng_mode=abi.RNG_TAPE)
     assert_matches_reference(out, doc, rtol=5e-4, dd_atol=5e-5, exact_counts=False)
     nt = __import__("tests.common", fromlist=["x"]).expected_arrays(doc)[2]
-    assert np.mean(out.num_trades != nt) < 0.02 and np.abs(out.num_trades - nt).max() <= 2
+    assert np.sum(out.num_trades != nt) <= 3 and np.abs(out.num_trades - nt).max() <= 2
 
 
 def _blank_tape(params, n_tapes, max_spells):
