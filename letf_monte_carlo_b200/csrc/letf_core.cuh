@@ -129,6 +129,18 @@ template <typename R> LETF_HD R pick6(const R (&v)[LETF_N_ASSETS], int a) {
   return r;
 }
 
+// ---- record staging of the rule kernels (Trial::run, MARKET == kMarketFSeries) -----------------------------------------------
+constexpr int kStage = 4;                                     // days in flight
+template <int NF> LETF_HD constexpr int kRecValues() { return NF + 9; }      // fields + the 9 retired-value lags
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float* letf_stage_smem() { extern __shared__ float letf_stage_buf[]; return letf_stage_buf; }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
+
 #define TM_HAS(t) ((TM >> (t)) & 1u)
 constexpr int kMarketSeries = 3;
 constexpr int kMarketFSeries = 5;     // fp32 day-major records written by the pair producer (letf_jfast.cuh EMIT): split strategy pipeline
@@ -816,18 +828,47 @@ struct Trial {
 #pragma unroll
       for (int d = 0; d < kSeriesAhead; d++) if (d < T) series_fetch(d, d);
     }
-    // record mode: the day's NF fields (coalesced: one column per thread, every thread on the same day)
-    R fq[FSER ? kSeriesAhead : 1][NF];
-    auto rec_fetch = [&](int slot, int day) {
-      const float* r = ka.rec + (int64_t)day * ka.rec_ncol + col;
-      const int64_t fstride = (int64_t)T * ka.rec_ncol;
-#pragma unroll
-      for (int f = 0; f < NF; f++) fq[slot][f] = (R)r[(int64_t)f * fstride];
+    // record mode: everything a day reads from the producer's records - its NF fields and the values its rolling windows
+    // retire (the same fields 5 ... 200 days back) - is staged through shared memory by asynchronous copies kStage - 1 days
+    // ahead of its use (cp.async, one 4-byte element per thread and value: every thread owns its own slots, so no
+    // barrier is needed and the copies cost neither registers nor scoreboard stalls).  Loads are coalesced: one column
+    // per thread, every thread of a warp on the same day.  Slot v of day d: smem[((d % kStage) * kNV + v) * blockDim + tid].
+    constexpr int kNV = kRecValues<NF>();
+    const int64_t rnc = ka.rec_ncol, rfs = (int64_t)T * ka.rec_ncol;
+    // the record element behind value v of day `day` (nullptr: no such value yet, the window is still filling)
+    auto rec_src = [&](int v, int day) -> const float* {
+      const float* r0 = ka.rec + (int64_t)day * rnc + col;
+      if (v < NF) return r0 + (int64_t)v * rfs;
+      const int lag = v == NF ? 5 : v == NF + 1 ? 10 : v == NF + 2 ? 20 : v == NF + 3 ? 60 : v == NF + 4 ? 126 :
+                      v == NF + 5 ? 100 : v == NF + 6 ? 200 : v == NF + 7 ? 14 : 15;
+      const int f = v <= NF + 3 ? 0 : (v == NF + 4 ? NF - 3 : NF - 1);      // signal return | SPY return | SPY price
+      return day >= lag ? r0 + (int64_t)f * rfs - (int64_t)lag * rnc : nullptr;
     };
+    const bool rec_used[kNV > NF ? kNV - NF : 1] = {HAS_V5, HAS_V10, HAS_V20 || HAS_DV20, HAS_V60 || HAS_SKEW || HAS_MEAN60, NEED_RINGS,
+                                                    HAS_SMA100, HAS_SMA200, HAS_RSI, HAS_RSI};
+#if defined(__CUDA_ARCH__)
+    float* const stage = FSER ? letf_stage_smem() + threadIdx.x : nullptr;
+    const int sblk = blockDim.x;
+    auto stage_issue = [&](int day) {
+      if (day < T) {
+        float* dst = stage + (day % kStage) * kNV * sblk;
+#pragma unroll
+        for (int v = 0; v < kNV; v++) {
+          if (v >= NF && !rec_used[v - NF]) continue;
+          const float* src = rec_src(v, day);
+          if (src) cp_async4(dst + v * sblk, src);
+        }
+      }
+      cp_async_commit();
+    };
+    auto stage_value = [&](int v, int day) -> R { return (R)stage[((day % kStage) * kNV + v) * sblk]; };
     if (FSER) {
 #pragma unroll
-      for (int d = 0; d < kSeriesAhead; d++) if (d < T) rec_fetch(d, d);
+      for (int d = 0; d < kStage - 1; d++) stage_issue(d);
     }
+#else
+    auto stage_value = [&](int v, int day) -> R { const float* src = rec_src(v, day); return src ? (R)*src : (R)0; };
+#endif
     // one simulated day.  steady_c = true_type: i >= kSteady, every rolling window is full (fp32 builds: the per-window
     // observation counts, their reciprocals and the warm-up predicates are compile-time constants in that copy of the body)
     constexpr int kSteady = 256;
@@ -840,22 +881,19 @@ struct Trial {
       if (two_pass && i + 1 < T) { vnext = xs[g + 1]; if (AUXSCR) inext = is[g + 1]; }
       R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0, pf_p14 = 0, pf_p15 = 0;
       if (FSER) {
-        // record mode: the values a window retires are the records of earlier days - coalesced loads at constant offsets
-        // from today's row, no ring, no cursor arithmetic
-        const float* r0 = ka.rec + (int64_t)i * ka.rec_ncol + col;
-        const int64_t nc = ka.rec_ncol, fstride = (int64_t)T * ka.rec_ncol;
-        const float* rp = r0 + (NF - 1) * fstride;        // SPY price
-        const float* rs_ = r0 + (NF - 3) * fstride;       // SPY return (last return field)
-        if (HAS_SMA200 && (STEADY || i >= 200)) pf_p200 = rp[-200 * nc];
-        if (HAS_SMA100 && (STEADY || i >= 100)) pf_p100 = rp[-100 * nc];
-        if (HAS_RSI && (STEADY || i >= 15)) { pf_p14 = rp[-14 * nc]; pf_p15 = rp[-15 * nc]; }
-        if (NEED_RINGS && (STEADY || i >= 126)) pf_s126 = rs_[-126 * nc];
-        if (NEED_RINGA) {
-          if ((STEADY || i >= 60) && (HAS_V60 || HAS_SKEW || HAS_MEAN60)) pf_r60 = r0[-60 * nc];
-          if ((STEADY || i >= 20) && (HAS_V20 || HAS_DV20)) pf_r20 = r0[-20 * nc];
-          if ((STEADY || i >= 10) && HAS_V10) pf_r10 = r0[-10 * nc];
-          if ((STEADY || i >= 5) && HAS_V5) pf_r5 = r0[-5 * nc];
-        }
+#if defined(__CUDA_ARCH__)
+        stage_issue(i + kStage - 1);
+        cp_async_wait<kStage - 1>();                    // day i's copies have landed (all but the newest kStage - 1 groups)
+#endif
+        // the values each window retires today (0 while the window is still filling)
+        if (HAS_V5 && (STEADY || i >= 5)) pf_r5 = stage_value(NF, i);
+        if (HAS_V10 && (STEADY || i >= 10)) pf_r10 = stage_value(NF + 1, i);
+        if ((HAS_V20 || HAS_DV20) && (STEADY || i >= 20)) pf_r20 = stage_value(NF + 2, i);
+        if ((HAS_V60 || HAS_SKEW || HAS_MEAN60) && (STEADY || i >= 60)) pf_r60 = stage_value(NF + 3, i);
+        if (NEED_RINGS && (STEADY || i >= 126)) pf_s126 = stage_value(NF + 4, i);
+        if (HAS_SMA100 && (STEADY || i >= 100)) pf_p100 = stage_value(NF + 5, i);
+        if (HAS_SMA200 && (STEADY || i >= 200)) pf_p200 = stage_value(NF + 6, i);
+        if (HAS_RSI && (STEADY || i >= 15)) { pf_p14 = stage_value(NF + 7, i); pf_p15 = stage_value(NF + 8, i); }
       } else if (!EXACT) {       // (the fp64 parity build keeps the loads at their use sites)
         if (NEED_RINGP) {
           const R* ring = ka.ringP + lane;
@@ -889,16 +927,10 @@ struct Trial {
       if (FSER) {
         int f = 0;
 #pragma unroll
-        for (int a = 0; a < kAssets; a++) s_er[a] = ((AM >> a) & 1) ? fq[0][f++] : (R)0;
-        const R v = fq[0][NF - 2];
+        for (int a = 0; a < kAssets; a++) s_er[a] = ((AM >> a) & 1) ? stage_value(f++, i) : (R)0;
+        const R v = stage_value(NF - 2, i);
         vix = M::abs_(v); s_reg = v < (R)0 ? 1 : 0;              // VIX >= 10: the sign bit carries the regime
-        rec_pspy = fq[0][NF - 1];
-#pragma unroll
-        for (int d = 0; d + 1 < kSeriesAhead; d++) {
-#pragma unroll
-          for (int q = 0; q < NF; q++) fq[d][q] = fq[d + 1][q];
-        }
-        if (i + kSeriesAhead < T) rec_fetch(kSeriesAhead - 1, i + kSeriesAhead);
+        rec_pspy = stage_value(NF - 1, i);
       }
       const int reg = SERIES ? s_reg : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
@@ -1577,6 +1609,9 @@ struct Trial {
       if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = JOURNAL ? sj[s].cnt : 0;
       if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = JOURNAL ? sj[s].vol : 0.0;
     }
+#if defined(__CUDA_ARCH__)
+    if (FSER) cp_async_wait<0>();              // nothing of this trial's staging may still be in flight when the next one starts
+#endif
     if (FSER) return;                          // path metadata and validity flags are the producer's
     if (ka.out.start_offset) ka.out.start_offset[col] = so;
     if (ka.out.flags) ka.out.flags[col] = flags;

@@ -73,14 +73,22 @@ const KernelEntry* kernel_at(int i);
 
 template <typename R, int NS, int NA, int MARKET, bool TAPEIO, uint32_t TM, int LIST, int AM, int BLK, int MINB>
 struct KernelImpl {
+  // record mode stages kStage days x kRecValues values per thread through dynamic shared memory (letf_core.cuh)
+  static constexpr size_t kSmem = MARKET == kMarketFSeries
+      ? (size_t)kStage * kRecValues<__builtin_popcount((unsigned)AM & 0x3Fu) + 2>() * BLK * sizeof(float) : 0;
   static cudaError_t launch(const void* kargs, int grid, cudaStream_t st) {
-    letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB><<<grid, BLK, 0, st>>>(*(const KArgs<R, NS, NA>*)kargs);
+    if (kSmem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+      if (e != cudaSuccess) return e;
+    }
+    letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB><<<grid, BLK, kSmem, st>>>(*(const KArgs<R, NS, NA>*)kargs);
     return cudaGetLastError();
   }
   static cudaError_t attrs(cudaFuncAttributes* a, int* mb) {
     cudaError_t e = cudaFuncGetAttributes(a, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>, BLK, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(mb, letf_path_kernel<R, NS, NA, MARKET, TAPEIO, TM, LIST, AM, BLK, MINB>, BLK, kSmem);
   }
 };
 

@@ -17,3 +17,4 @@ PY
 for w in sweep19 c4; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"letf_path_kernel|letf_jpair_kernel" -s 6 -c 2 -f -o $F/prof_${w} python bench.py --workload $w --trials 113664 --steps 1 --warmup 3 --no-cpu > $F/ncu_${w}.log 2>&1; echo "ncu $w rc $?"
 done
+./scripts/pipe_peaks $F/pipe_peaks.json > $F/pipe_peaks.txt 2>&1; echo "pipe rc $?"; cat $F/pipe_peaks.txt
