@@ -167,8 +167,11 @@ static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t 
   for (int i = 0; i < kernel_count(); i++) {
     const KernelEntry* k = kernel_at(i);
     if (k->precision != LETF_PREC_F32) continue;
-    if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact) plan->prod = k;
-    if (k->market == kMarketFSeries && k->list && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e)) plan->cons = k;
+    // (first registered candidate wins unless LETF_KERNEL names another one)
+    if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact &&
+        (!plan->prod || e->pin_kernel == k->name)) plan->prod = k;
+    if (k->market == kMarketFSeries && k->list && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e) &&
+        (!plan->cons || e->pin_kernel == k->name)) plan->cons = k;
   }
   plan->nact = nact;
   return plan->prod && plan->cons;
@@ -393,9 +396,12 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
                        lg.curve != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
-  if (market == e->params.market_mode && !series && !(e->pin_kernel.size())) {
+  if (market == e->params.market_mode && !series) {
     SplitPlan plan;
-    if (find_split(e, rng_mode, need_io, first, &plan)) {
+    // LETF_KERNEL=<a fused instantiation> pins the fused path; naming a producer / rule kernel picks among the split ones
+    const bool pin_fused = e->pin_kernel.size() && e->pin_kernel.find("_prod_") == std::string::npos &&
+                           e->pin_kernel.find("_rules_") == std::string::npos;
+    if (!pin_fused && find_split(e, rng_mode, need_io, first, &plan)) {
       CK(cudaSetDevice(e->device));
       if (plan.cons->ns == 8) return launch_split<8>(e, plan, st, seed, first, n, out);
       if (plan.cons->ns == 32) return launch_split<32>(e, plan, st, seed, first, n, out);
