@@ -2,10 +2,11 @@
 // antithetic-pair kernels of the lean institutional buy&hold shapes (letf_jfast.cuh)
 #include "letf_kernels.cuh"
 // BASELINE config 3: SPY + QQQ (+ TLT benchmark), both tracking errors t(10)
-// (capped at 128 registers, no spills: four resident blocks per SM = 4 warps per scheduler, +12.7 % over the 142-register
-//  three-block build, which stays selectable for A/B runs: LETF_KERNEL=f32_joint_t_pair_c3_r168)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3, 4, 3, 2, 3, false, 128, 4)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3_r168, 4, 3, 2, 3, false, 128, 3)
+// (142 registers, three resident blocks per SM.  Capped at 128 registers / four blocks it also compiles without spills, but
+//  measures 5 % slower at the literal 1M-trial size, 164.0 vs 156.4 ms on the same box - A/B: LETF_KERNEL=f32_joint_t_pair_c3_r128;
+//  at trial counts that quantise badly into three-block waves the capped build wins, see profiles/README.md)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3, 4, 3, 2, 3, false, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3_r128, 4, 3, 2, 3, false, 128, 4)
 // S1 S2 S3 and the like: two LETFs t(5) + SPY t(10)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3a, 4, 3, 3, 4, false, 128, 3)
 // one series

@@ -3,10 +3,9 @@
 // buy&hold statistics, and the per-day records the rule kernels consume
 #include "letf_kernels.cuh"
 // BASELINE config 4: TQQQ / TMF t(5), SPY t(10)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4, 32, 4, 3, 4, true, 128, 4)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4, 32, 4, 3, 4, true, 128, 3)
 // the reference's default sweep: TQQQ / SSO / TMF t(5), SPY t(10)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19, 32, 4, 4, 8, true, 128, 3)
-// A/B variants (LETF_KERNEL=<name>): the c4 producer runs best capped at 128 registers (4 blocks per SM, +2.6 %), the four-series
-// producer of the default sweep at 150 registers / 3 blocks (-6 % when capped)
-LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_r168, 32, 4, 3, 4, true, 128, 3)
+// A/B variants capped at 128 registers / four blocks per SM (LETF_KERNEL=<name>)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_r128, 32, 4, 3, 4, true, 128, 4)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19_r128, 32, 4, 4, 8, true, 128, 4)
