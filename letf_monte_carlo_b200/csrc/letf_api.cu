@@ -103,6 +103,7 @@ struct LetfEngine {
   bool no_jpair = false;                     // LETF_KERNEL=<instantiation>, LETF_NO_JPAIR=1, LETF_NO_SPLIT=1
   bool no_split = false;
   DevBuf rec;                                // per-day records of the split strategy pipeline
+  DevBuf spell;                              // regime spells of the pair kernels
   // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
   void* boot_blob = nullptr;
   DevBoot<double> boot64;
@@ -251,7 +252,13 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   size_t scratch = 0;
   if (((ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching) || ke->market == LETF_MARKET_BOOTSTRAP) && G > 0) {
     size_t b = ((size_t)G * 4 + (size_t)((G + 3) & ~3)) * (size_t)nthreads * sizeof(R);   // day vectors + the IRX-normal column (letf_core.cuh AUXSCR)
-    if (ke->fj) b = (size_t)G * sizeof(JF8) * (size_t)nthreads;                            // one 32-byte record per day and pair (letf_jfast.cuh)
+    if (ke->fj) {
+      b = (size_t)G * sizeof(JF8) * (size_t)nthreads;                                      // one 32-byte record per day and pair (letf_jfast.cuh)
+      const size_t sb = (size_t)(G + 1) * 4 * (size_t)nthreads;                            // + the pair's regime spells
+      cudaError_t ce2 = e->spell.reserve(sb);
+      if (ce2 != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "regime spell scratch: " + std::string(cudaGetErrorString(ce2))); }
+      ka.spell_scr = (uint32_t*)e->spell.p; scratch += sb;
+    }
     cudaError_t ce = e->xscr.reserve(b);
     if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
     ka.xscr = (R*)e->xscr.p; scratch += b;
@@ -342,7 +349,11 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
       cudaError_t ce = e->xscr.reserve(b);
       if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "moment-matching scratch: " + std::string(cudaGetErrorString(ce))); }
       ka_p.xscr = (float*)e->xscr.p;
-      if (c0 == 0) scratch += b;
+      const size_t sb = (size_t)(G + 1) * 4 * (size_t)ka_p.nthreads;
+      ce = e->spell.reserve(sb);
+      if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "regime spell scratch: " + std::string(cudaGetErrorString(ce))); }
+      ka_p.spell_scr = (uint32_t*)e->spell.p;
+      if (c0 == 0) scratch += b + sb;
     }
     CK(kp->launch(&ka_p, (int)grid_p, st));
     // rule kernel: one trial per thread, columns [0, nc) of the record buffer
@@ -529,7 +540,7 @@ void letf_destroy(LetfEngine* e) {
   cudaSetDevice(e->device);
   for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
   if (e->boot_blob) cudaFree(e->boot_blob);
-  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release(); e->rec.release();
+  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release(); e->rec.release(); e->spell.release();
   e->stage_tape.release(); e->stage_out.release(); e->stage_log.release(); e->pin_out.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);

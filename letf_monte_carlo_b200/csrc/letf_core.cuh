@@ -48,6 +48,7 @@ template <typename R, int NS, int NA> struct KArgs {
   // rec[(field * T + day) * rec_ncol + column], fields = the active layer returns, VIX (regime in the sign bit), SPY price
   float* rec;
   int64_t rec_ncol;
+  uint32_t* spell_scr;      // [nthreads][G + 1]: regime spells of the pair kernels (letf_jfast.cuh), (end day << 1) | regime
 };
 
 LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {

@@ -117,16 +117,30 @@ struct JointPair {
 
     JF8* const xs = (JF8*)ka.xscr + lane * (int64_t)G;
 
+    // ---- regime path (engine.py:255-302), once per pair, before anything else: the dwell-time draws are a Philox block each
+    // and happen on ~2 % of the days of a lane, i.e. on ~half of the days of a WARP - inside the day loop the whole warp
+    // would step through the draw on each of those days.  Here every lane walks its own ~G/50 spells in a compact loop and
+    // leaves (last day of the spell + 1) << 1 | regime in its scratch row; the day loop only compares against the next entry.
+    uint32_t* const sw = ka.spell_scr + lane * (int64_t)(G + 1);
+    {
+      int day = 0;
+      uint32_t ks = 0;
+      while (day < G) {
+        if (ks > 0 && p.flip[cur]) cur ^= 1;
+        day += jf_spell(key.k0, key.k1, key.t0, key.t1, ks, p.log_pstay[cur], p.n_dur[cur], p.dur[cur], G);
+        sw[ks++] = ((uint32_t)(day < G ? day : G) << 1) | (uint32_t)cur;
+      }
+    }
+
     // ---- pass 1: raw joint returns of both twins -> scratch, column means (calibration.py:508-588)
     float shift[2][3];
     {
-      int left = 0;
-      uint32_t ks = 0;
-      float h[2][3], q[2][6], pz[2][3], sum[2][3], cmp[2][3];
+      uint32_t ks = 0, nsw = 0;                 // nsw: first day of the next spell
+      float h[2][3], q[2][6], pz[2][3], sum[2][3], cmp[2][3], part[2][3];
 #pragma unroll
       for (int t = 0; t < 2; t++) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) { h[t][a] = 0.0f; pz[t][a] = 0.0f; sum[t][a] = 0.0f; cmp[t][a] = 0.0f; }
+        for (int a = 0; a < 3; a++) { h[t][a] = 0.0f; pz[t][a] = 0.0f; sum[t][a] = 0.0f; cmp[t][a] = 0.0f; part[t][a] = 0.0f; }
 #pragma unroll
         for (int a = 0; a < 6; a++) q[t][a] = 0.0f;
       }
@@ -135,14 +149,9 @@ struct JointPair {
       float alpha = 0, beta = 0, dcc_a = 0, dcc_b = 0, sqrt_nu = 0, kodd = 0, irx_base = 0;
       int kk = 0, jreg = -1;
       const uint32_t mstreams[2] = {STREAM_MKT0, STREAM_MKT1};
+      int reg = 0;
       for (int g = 0; g < G; g++) {
-        if (left == 0) {
-          if (ks > 0 && p.flip[cur]) cur ^= 1;
-          left = jf_spell(key.k0, key.k1, key.t0, key.t1, ks, p.log_pstay[cur], p.n_dur[cur], p.dur[cur], G);
-          ks++;
-        }
-        left--;
-        const int reg = cur;
+        if ((uint32_t)g == nsw) { const uint32_t e = sw[ks++]; reg = (int)(e & 1u); nsw = e >> 1; }
         U4 w[2];
         rng_blocks<2>(key, (uint32_t)g, mstreams, w);
         float z0, z1, z2, nchi, vn, in;
@@ -215,13 +224,21 @@ struct JointPair {
             const float zs = t ? -zz[a] : zz[a];                  // antithetic twin: negated normal vector (calibration.py:563)
             x[a] = clipr(mu[a] + zs * scale, -0.95f, 4.0f);
             pz[t][a] = (x[a] - mu[a]) * ih[a];
-            const float y = x[a] - cmp[t][a], s = sum[t][a] + y;   // Kahan, as Trial::run
-            cmp[t][a] = (s - sum[t][a]) - y; sum[t][a] = s;
+            part[t][a] += x[a];                                    // eight-day partial sums, Kahan across them (below)
           }
           if (t == 0) { rec.a0 = x[0]; rec.a1 = x[1]; rec.a2 = x[2]; }
           else { rec.b0 = x[0]; rec.b1 = x[1]; rec.b2 = x[2]; }
         }
         jf_store(xs + g, rec);
+        if ((g & 7) == 7 || g == G - 1) {
+#pragma unroll
+          for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              const float y = part[t][a] - cmp[t][a], s = sum[t][a] + y;
+              cmp[t][a] = (s - sum[t][a]) - y; sum[t][a] = s; part[t][a] = 0.0f;
+            }
+        }
       }
 #pragma unroll
       for (int t = 0; t < 2; t++)

@@ -126,6 +126,8 @@ extern "C" int letf_emu_run_jpair(const LetfParams* sp, const LetfOutputs* out, 
   const int G = sp->sim_days + sp->buffer_days;
   float* xscr = (float*)aligned_alloc(32, ((size_t)(G > 0 ? G : 1) * 8 + 8) * sizeof(float));
   ka.xscr = xscr;
+  std::vector<uint32_t> spells((size_t)G + 2);
+  ka.spell_scr = spells.data();
   const int code = ka.p.fast_joint;
   const bool compiled = code == fast_joint_code(2, 3) || code == fast_joint_code(3, 4) || code == fast_joint_code(1, 0) ||
                         code == fast_joint_code(1, 1);
@@ -191,7 +193,8 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   std::vector<float> rec((size_t)cap * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
   float* xscr = (float*)aligned_alloc(32, ((size_t)(G > 0 ? G : 1) * 8 + 8) * sizeof(float));
   kp.out = *out; kp.seed = seed; kp.first_trial = first; kp.n_trials = n; kp.rng_mode = LETF_RNG_PHILOX; kp.nthreads = 1;
-  kp.xscr = xscr; kp.rec = rec.data(); kp.rec_ncol = cap; kp.log_trial = -1;
+  std::vector<uint32_t> spells((size_t)G + 2);
+  kp.xscr = xscr; kp.rec = rec.data(); kp.rec_ncol = cap; kp.log_trial = -1; kp.spell_scr = spells.data();
   for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<32, 4, NACT, K10, true>::run(kp, pj, 0);
   kc.out = *out; kc.seed = seed; kc.first_trial = first; kc.n_trials = n; kc.rng_mode = LETF_RNG_PHILOX; kc.nthreads = 1;
   kc.rec = rec.data(); kc.rec_ncol = cap; kc.log_trial = -1;
