@@ -368,6 +368,13 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
 int letf_equity_curve_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode,
                            const LetfTape* host_tape, double* curve);
 
+/* The generated underlying returns (SPY, QQQ, TLT; before the jump overlay) of ONE trial's simulated window - what
+ * simulate_joint_returns_t(n_days, regime_path, joint_model, rng, antithetic) returns (calibration.py:480-590), moment
+ * matching included: the trial is re-simulated (same seed or same tape) with the market log on.
+ * returns: host double[sim_days][3].  With buffer_days == 0 the window is the whole generated path. */
+int letf_market_returns_host(LetfEngine* e, uint64_t seed, int64_t trial, int rng_mode,
+                             const LetfTape* host_tape, double* returns);
+
 int letf_launch_info(LetfEngine* e, LetfLaunchInfo* info);
 
 /* Strategy rules on caller-supplied return series (materialised-path mode):

@@ -128,6 +128,7 @@ struct LogArgs {
   int32_t* count = nullptr; int32_t* day = nullptr; int32_t* asset = nullptr; int32_t* action = nullptr;
   double* shares = nullptr; double* price = nullptr;
   double* curve = nullptr;                  // device [T]: equity curve of (trial, strategy)
+  double* market = nullptr;                 // device [T][3]: generated SPY / QQQ / TLT returns of `trial`
 };
 
 // typed slots: the strategy list must be exactly the one compiled in
@@ -246,7 +247,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   ka.trial_ids = lg.trial_ids;
   ka.log_trial = lg.trial; ka.log_strategy = lg.strategy; ka.log_cap = lg.cap;
   ka.log_count = lg.count; ka.log_day = lg.day; ka.log_asset = lg.asset; ka.log_action = lg.action;
-  ka.log_shares = lg.shares; ka.log_price = lg.price; ka.log_curve = lg.curve;
+  ka.log_shares = lg.shares; ka.log_price = lg.price; ka.log_curve = lg.curve; ka.log_market = lg.market;
 
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
@@ -404,7 +405,7 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
   const bool want_journal = e->any_taxable && (out->journal_count || out->journal_volume);
   // (a caller-supplied frame needs no tape plumbing; only the journal does)
   const bool need_io = (market != kMarketSeries && rng_mode != LETF_RNG_PHILOX) || want_journal || lg.count != nullptr ||
-                       lg.curve != nullptr;
+                       lg.curve != nullptr || lg.market != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
   if (market == e->params.market_mode && !series) {
@@ -919,6 +920,41 @@ int letf_equity_curve_host(LetfEngine* e, uint64_t seed, int64_t trial, int stra
   }
   return replay_one(e, e->params.market_mode, seed, trial, strategy, rng_mode, tp, nullptr, e->params.sim_days, curve, nullptr, 0,
                     nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int letf_market_returns_host(LetfEngine* e, uint64_t seed, int64_t trial, int rng_mode, const LetfTape* host_tape,
+                             double* returns) {
+  if (!e || !returns) return fail(LETF_ERR_INVALID, "null argument");
+  if (trial < 0) return fail(LETF_ERR_INVALID, "negative trial id");
+  if (rng_mode == LETF_RNG_PHILOX_RECORD) return fail(LETF_ERR_INVALID, "market replay does not record");
+  if (e->params.n_strategies < 1) return fail(LETF_ERR_INVALID, "engine has no strategy slot");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  LetfTape dtape; const LetfTape* tp = nullptr;
+  if (rng_mode == LETF_RNG_TAPE) {
+    if (!host_tape) return fail(LETF_ERR_INVALID, "rng_mode needs a tape");
+    int rc = stage_tape(e, host_tape, true, &dtape);
+    if (rc) return rc;
+    tp = &dtape;
+  }
+  const int S = e->params.n_strategies, T = e->params.sim_days;
+  const size_t t3 = (size_t)(T > 0 ? T : 1) * 3;
+  const size_t o_mk = 0, o_out = align256(8 * t3), total = o_out + align256(8 * S) * 2 + align256(4 * S) + 256;
+  cudaError_t ce = e->stage_log.reserve(total);
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "log staging"); }
+  char* base = (char*)e->stage_log.p;
+  CK(cudaMemset(base + o_mk, 0, 8 * t3));
+  LogArgs lg;
+  lg.trial = trial; lg.strategy = -1; lg.market = (double*)(base + o_mk);
+  LetfOutputs dout; memset(&dout, 0, sizeof(dout));
+  dout.n_trials = 1;
+  dout.final_wealth = (double*)(base + o_out); dout.max_dd = (double*)(base + o_out + align256(8 * S));
+  dout.num_trades = (int32_t*)(base + o_out + 2 * align256(8 * S));
+  dout.flags = (uint32_t*)(base + o_out + 2 * align256(8 * S) + align256(4 * S));
+  int rc = launch_any(e, e->params.market_mode, (cudaStream_t)0, seed, trial, 1, rng_mode, tp, &dout, nullptr, lg);
+  if (rc) return rc;
+  if (T > 0) CK(cudaMemcpy(returns, base + o_mk, 8 * (size_t)T * 3, cudaMemcpyDeviceToHost));
+  return LETF_OK;
 }
 
 int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* hs, int strategy, double* curve, int32_t* num_trades, int cap,

@@ -44,6 +44,7 @@ template <typename R, int NS, int NA> struct KArgs {
   int64_t log_trial; int log_strategy; int log_cap;
   int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
   double* log_curve;        // [T] daily equity of (log_trial, log_strategy): the Series run_strategy_fixed returns
+  double* log_market;       // [T][3] SPY / QQQ / TLT returns of log_trial's window (the simulate_joint_returns_t seam)
   // split strategy pipeline (letf_jfast.cuh EMIT producer -> Trial::run with MARKET == kMarketFSeries): per-day records,
   // rec[(field * T + day) * rec_ncol + column], fields = the active layer returns, VIX (regime in the sign bit), SPY price
   float* rec;
@@ -180,7 +181,7 @@ template <> struct Drawdown<float> {
     q = fminf(1.0f, fmaf(q, ret, q));
     qmin = fminf(qmin, q);
   }
-  LETF_HD double value() const { return (double)(1.0f - qmin); }
+  LETF_HD double value() const { return 1.0 - (double)qmin; }   // in fp64: drawdowns within 1e-7 of 100 % (30-year 3x paths) keep their digits
 };
 
 // ------------------------------------------------------------------------------------------
@@ -961,6 +962,10 @@ struct Trial {
         rf = EXACT ? clipx(irx, (R)0, (R)20) / (R)100 : clipx(irx, (R)0, (R)20) * (R)0.01;                                // engine.py:516
       }
       R spy = x[0], qqq = x[1], tlt = x[2];
+      if (TAPEIO && ka.log_market && !ka.trial_ids && ka.log_trial == k) {
+        // the generated underlying returns, before the jump overlay (what calibration.py:480-590 returns)
+        for (int a = 0; a < 3; a++) ka.log_market[(int64_t)i * 3 + a] = (double)x[a];
+      }
       if (EXACT) {
         if (!isfinite_(spy) || !isfinite_(qqq) || !isfinite_(tlt)) flags |= LETF_FLAG_NONFINITE_RET;
       } else {

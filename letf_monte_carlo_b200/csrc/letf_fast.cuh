@@ -128,7 +128,7 @@ struct FastLayers {
 #pragma unroll
         for (int a = 0; a < NACT; a++) if (p.act_id[a] == p.strat[s].asset) { c = cp[u][a]; qm = qmin[u][a]; }
         ka.out.final_wealth[(int64_t)s * N + col[u]] = T > 0 ? (double)p.W0 * c : 0.0;
-        ka.out.max_dd[(int64_t)s * N + col[u]] = T > 1 ? (double)(1.0f - qm) : 0.0;
+        ka.out.max_dd[(int64_t)s * N + col[u]] = T > 1 ? 1.0 - (double)qm : 0.0;
         ka.out.num_trades[(int64_t)s * N + col[u]] = 0;
         if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col[u]] = 0;
         if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col[u]] = 0.0;

@@ -298,6 +298,17 @@ class PathEngine:
         self.launches += 1
         return curve[:int(self.params.sim_days)]
 
+    def market_returns(self, trial: int, *, seed: int = 0, rng_mode: int = abi.RNG_PHILOX, tape: HostTape | None = None) -> np.ndarray:
+        """[sim_days][3] generated SPY / QQQ / TLT returns of one trial's window (before the jump overlay), by replaying it"""
+        T = int(self.params.sim_days)
+        ret = np.zeros((max(T, 1), 3))
+        ts = tape.as_struct() if tape is not None else None
+        rc = self._lib.letf_market_returns_host(self._h, seed, trial, rng_mode, C.byref(ts) if ts is not None else None,
+                                                ret.ctypes.data)
+        self._check(rc)
+        self.launches += 1
+        return ret[:T]
+
     def run_strategy_curve(self, frame: dict, strategy: int, *, tlt_ret=None, vix=None, regime=None, cash_ret=None, cap: int = 4096):
         """`run_strategy_fixed` on ONE caller-supplied frame (strategy.py:55): frame = {asset name: [T] returns}.
         -> (equity curve [T], num_trades, Trade_List rows for a taxable id)"""

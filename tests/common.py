@@ -90,7 +90,7 @@ def anchor_distribution_case():
     return ref, sids, params, keep
 
 
-def assert_same_distribution(ref, out, sids, p_min=1e-3):
+def assert_same_distribution(ref, out, sids, p_min=1e-3, rank_tol=4.0):
     """two-sample KS on terminal wealth and max drawdown per strategy, summary quantiles of wealth (rank agreement),
     mean trade counts within 3 %, regime / jump / repair statistics within sampling error"""
     from scipy import stats
@@ -103,7 +103,7 @@ def assert_same_distribution(ref, out, sids, p_min=1e-3):
             # (its own sampling error at n = 2 400 is ~ 1 point; wealth spans decades, so compare ranks)
             qa = np.percentile(a, q)
             rank = 100.0 * np.mean(b <= qa)
-            assert abs(rank - q) < 4.0, (s, q, qa, rank)
+            assert abs(rank - q) < rank_tol, (s, q, qa, rank)
         ta, tb = ref["num_trades"][k].mean(), out.num_trades[k].mean()
         assert abs(tb - ta) <= 0.03 * max(ta, 1.0), (s, ta, tb)
     n_ref = len(ref["high_vol_days"])

@@ -48,6 +48,35 @@ static int run_t(const LetfParams* sp, const LetfTape* tape, const LetfOutputs* 
   return 0;
 }
 
+// the simulate_joint_returns_t seam: generated SPY / QQQ / TLT returns of one trial's window (kernel source, market log on)
+template <typename R, int MARKET>
+static int market_t(const LetfParams* sp, const LetfTape* tape, uint64_t seed, int64_t trial, int rng_mode, double* returns) {
+  constexpr int NS = LETF_MAX_STRATEGIES;
+  constexpr int NA = kAssets;
+  static KArgs<R, NS, NA> ka;
+  memset(&ka, 0, sizeof(ka));
+  const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
+  convert_params<R, NS, NA>(*sp, dd, ka.p);
+  if (tape) ka.tape = *tape;
+  const int S = sp->n_strategies > 0 ? sp->n_strategies : 1;
+  std::vector<double> fw(S), md(S); std::vector<int32_t> nt(S);
+  ka.out.n_trials = 1; ka.out.final_wealth = fw.data(); ka.out.max_dd = md.data(); ka.out.num_trades = nt.data();
+  ka.seed = seed; ka.first_trial = trial; ka.n_trials = 1; ka.rng_mode = rng_mode;
+  const int G = sp->sim_days + sp->buffer_days;
+  std::vector<R> xscr((size_t)(G > 0 ? G : 1) * 5 + 8), rp(kRingP), rs(kRingS), ra(kRingA);
+  ka.xscr = xscr.data(); ka.ringP = rp.data(); ka.ringS = rs.data(); ka.ringA = ra.data();
+  ka.nthreads = 1; ka.log_trial = trial; ka.log_strategy = -1; ka.log_market = returns;
+  Trial<R, NS, NA, MARKET, true, 0xFFFFFFFFu> t(ka, trial, 0, 0);
+  t.run();
+  return 0;
+}
+extern "C" int letf_emu_market(const LetfParams* sp, int precision, const LetfTape* tape, uint64_t seed, int64_t trial, int rng_mode,
+                               double* returns) {
+  if (validate_params(*sp) || sp->market_mode != LETF_MARKET_JOINT_T) return -1;
+  if (precision == LETF_PREC_F64) return market_t<double, 2>(sp, tape, seed, trial, rng_mode, returns);
+  return market_t<float, 2>(sp, tape, seed, trial, rng_mode, returns);
+}
+
 extern "C" int letf_emu_run(const LetfParams* sp, int precision, const LetfTape* tape, const LetfOutputs* out,
                             uint64_t seed, int64_t first, int64_t n, int rng_mode,
                             int64_t log_trial, int log_strategy, int log_cap, int32_t* log_count,

@@ -50,6 +50,8 @@ def lib():
         L.letf_emu_run_jpair.restype = C.c_int
         L.letf_emu_run_typed.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_typed.restype = C.c_int
+        L.letf_emu_market.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Tape), C.c_uint64, C.c_int64, C.c_int, C.c_void_p]
+        L.letf_emu_market.restype = C.c_int
         L.letf_emu_run_split.argtypes = [C.POINTER(abi.Params), C.c_int, C.POINTER(abi.Outputs), C.c_uint64, C.c_int64, C.c_int64]
         L.letf_emu_run_split.restype = C.c_int
         L.letf_emu_run_series.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int, C.POINTER(abi.Series), C.POINTER(abi.Outputs),
@@ -136,6 +138,16 @@ def run_jpair(params, n, seed=0, first=0, force_generic=False):
     if rc != 0:
         raise RuntimeError(f"emu jpair rc={rc}")
     return out, int(used.value)
+
+
+def market_returns(params, tape, trial, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0):
+    """[sim_days][3] generated SPY / QQQ / TLT returns of one trial (the simulate_joint_returns_t seam)"""
+    ret = np.zeros((max(int(params.sim_days), 1), 3))
+    ts = tape.as_struct()
+    rc = lib().letf_emu_market(C.byref(params), precision, C.byref(ts), seed, trial, rng_mode, ret.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"emu market rc={rc}")
+    return ret[:int(params.sim_days)]
 
 
 def run_split(params, slot_list, n, seed=0, first=0):

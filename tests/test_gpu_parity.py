@@ -446,6 +446,22 @@ def test_philox_distribution_matches_live_reference(precision, engine_lib):
     assert_same_distribution(ref, out, sids)
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_philox_distribution_matches_live_reference_at_10_years(precision, engine_lib):
+    """tests/golden/ref_distribution_10y.npz: 2 000 trials x 10 years x {S1 S2 S3 S4 S5 S6 S7 S19 QQQ TLT} of the unmodified
+    reference with its own NumPy streams (oracle/make_reference_distribution.py --pairs 1000 --years 10).  On-device Philox
+    runs, fp32 (the split strategy pipeline) and fp64: KS p > 0.01 per strategy on wealth and drawdown, the reference's
+    P10 ... P90 within +- 3 rank points, mean trade counts within 3 %."""
+    from tests.common import assert_same_distribution, reference_distribution
+    ref = reference_distribution("ref_distribution_10y.npz")
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, float(ref["years"]), synthetic.fallback_regime_model("default"), ns)
+    with _engine(params, keep, precision) as eng:
+        out = eng.run_host(40000, seed=314)
+    assert_same_distribution(ref, out, sids, p_min=0.01, rank_tol=3.0)
+
+
 @pytest.mark.parametrize("variant", ["default", "vix_te"], ids=["default_te", "calibrated_te"])
 @pytest.mark.parametrize("sids", [["S1", "S2", "S4", "S5", "S6", "S19"], ALL19], ids=["c4_list", "sweep19_list"])
 def test_typed_slot_kernels_vs_generic_and_oracle(sids, variant, engine_lib):
@@ -829,3 +845,26 @@ def test_run_strategy_fixed_infers_the_regime_path_like_the_reference(engine_lib
         with pytest.raises(ValueError):
             eng.run_strategy_curve({"SPY": df["SPY_Ret"].to_numpy(), "TQQQ": df["TQQQ_Ret"].to_numpy()}, 0,
                                    regime=np.full(len(df), 2, np.int32))
+
+
+@pytest.mark.parametrize("anti", [False, True])
+def test_simulate_joint_returns_t_dropin_matches_live_reference(anti, engine_lib):
+    """the last inner seam (calibration.py:480-590): per-day SPY / QQQ / TLT returns of one path along a caller-supplied regime
+    path, variates injected through `rng`; fp64 device kernel vs the live reference on the same variates, <= 1e-12"""
+    import os
+    from letf_monte_carlo_b200 import simulate_joint_returns_t
+    from oracle.make_joint_returns_golden import inputs
+    from tests.test_kernel_emulation import _PresetRng
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "joint_returns_400d.npz"))
+    regime, x, chi2, joint = inputs()
+    for mm in (True, False):
+        ns = synthetic.config_namespace(USE_MOMENT_MATCHING=mm)
+        out = simulate_joint_returns_t(len(regime), regime, joint, _PresetRng(x, chi2), antithetic=anti, cfg=ns)
+        assert list(out) == ["SPY_Ret", "QQQ_Ret", "TLT_Ret"]
+        got = np.stack([out[a] for a in out], axis=1)
+        np.testing.assert_allclose(got, g[f"ret_mm{int(mm)}_anti{int(anti)}"], rtol=1e-12, atol=1e-15)
+    # with a real generator: finite, right length, reproducible for a seeded stream
+    a = simulate_joint_returns_t(300, regime[:300], joint, np.random.default_rng(5), cfg=synthetic.config_namespace())
+    b = simulate_joint_returns_t(300, regime[:300], joint, np.random.default_rng(5), cfg=synthetic.config_namespace())
+    assert all(len(v) == 300 and np.isfinite(v).all() for v in a.values())
+    np.testing.assert_array_equal(a["QQQ_Ret"], b["QQQ_Ret"])

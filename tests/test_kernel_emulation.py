@@ -275,6 +275,20 @@ def test_philox_distribution_matches_live_reference():
     assert_same_distribution(ref, out, sids)
 
 
+def test_philox_distribution_matches_live_reference_at_10_years():
+    """the longer fixture (tests/golden/ref_distribution_10y.npz: 2 000 trials x 10 years x 10 strategies of the unmodified
+    reference with its own NumPy streams): two-sample KS p > 0.01 on terminal wealth and max drawdown per strategy, the
+    reference's P10 ... P90 within +- 3 rank points of ours, trade counts within 3 %"""
+    from tests.common import assert_same_distribution, reference_distribution
+    ref = reference_distribution("ref_distribution_10y.npz")
+    sids = [str(s) for s in ref["strategies"]]
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, float(ref["years"]), synthetic.fallback_regime_model("default"), ns)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    out = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=11, n=6000)
+    assert_same_distribution(ref, out, sids, p_min=0.01, rank_tol=3.0)
+
+
 def test_bootstrap_philox_distribution_matches_live_reference():
     """same for the legacy_hybrid block bootstrap: the reference side ran its own BlockBootstrapReturns with NumPy's
     geometric / integers / choice(p=...) / standard_t streams (tests/golden/ref_distribution_boot_1y.npz)."""
@@ -430,6 +444,41 @@ def test_series_mode_equity_curves_match_live_reference():
             n = int(out.log["count"][0])
             assert n == int(g[f"{sid}_journal_n"]), sid
             np.testing.assert_array_equal(out.log["day"][:n], g[f"{sid}_journal_days"])
+
+
+class _PresetRng:
+    """stands in for the numpy Generator handed to simulate_joint_returns_t: returns pre-drawn variates"""
+
+    def __init__(self, x, chi2):
+        self.x, self.chi2 = x, chi2
+
+    def standard_normal(self, size=None):
+        assert tuple(size) == self.x.shape
+        return self.x
+
+    def chisquare(self, df):
+        assert len(df) == len(self.chi2)
+        return self.chi2
+
+
+@pytest.mark.parametrize("mm", [True, False])
+@pytest.mark.parametrize("anti", [False, True])
+def test_joint_returns_seam_matches_live_reference(mm, anti):
+    """simulate_joint_returns_t(n_days, regime_path, joint_model, rng, antithetic) (calibration.py:480-590) along a caller's
+    regime path: the kernel source fed with the drop-in's parameter block and tape, against the LIVE reference on the same
+    variates (tests/golden/joint_returns_400d.npz): every daily return of the three series to 1e-12, clips included"""
+    import os
+    from letf_monte_carlo_b200.calibration import joint_case
+    from oracle.make_joint_returns_golden import inputs
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "joint_returns_400d.npz"))
+    regime, x, chi2, joint = inputs()
+    np.testing.assert_array_equal(x, g["x"])
+    ns = synthetic.config_namespace(USE_MOMENT_MATCHING=mm)
+    params, keep, tape, trial = joint_case(len(regime), regime, joint, _PresetRng(x, chi2), anti, ns)
+    ret = emu.market_returns(params, tape, trial)
+    want = g[f"ret_mm{int(mm)}_anti{int(anti)}"]
+    np.testing.assert_allclose(ret, want, rtol=1e-12, atol=1e-15)
+    assert np.abs(want).max() > 0.9          # the clip at -0.95 is exercised
 
 
 def test_series_mode_with_inferred_regime_path_matches_live_reference():
