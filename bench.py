@@ -116,6 +116,10 @@ def build_workload(name):
     return ns, model, sids, params, keep
 
 
+def out_bytes_fn(n, S):
+    return n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -384,7 +388,7 @@ def run_b200(args):
         sm_count = info["sm_count"]
         peak_lane = sm_count * 128 * pk["sm_max_mhz"] * 1e6 / 1e12               # T lane-ops/s at max clock
         achieved = n * T * wl["lane_ops"] / (kern_ms * 1e-3) / 1e12
-        out_bytes = n * (S * (8 + 8 + 4) + 4 + 4 + 8 + 4)
+        out_bytes = out_bytes_fn(n, S)
         ncu_c = {}
         try:
             ncu_c = json.load(open(os.path.join(ROOT, "profiles", "ncu_constants.json"))).get(args.workload, {})
@@ -392,6 +396,18 @@ def run_b200(args):
             pass
         traffic = ncu_c["dram_bytes_per_trial"] * n if "dram_bytes_per_trial" in ncu_c else None
         exe = ncu_c.get("executed_warp_instr_per_path_day")
+        # algorithmic HBM bytes of the launch: per-trial outputs, plus - for the two-pass (moment matching) kernels - one
+        # 32-byte record per generated day and antithetic pair written by pass 1 and read back by pass 2
+        G = T + int(params.buffer_days)
+        alg_bytes = out_bytes_fn(n, S)
+        if info["kernel"].startswith("f32_joint_t_pair") or "prod" in info["kernel"]:
+            alg_bytes += n * G * 32
+        pipes = None
+        try:
+            pp = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks.json")))
+            pipes = {k: v["lane_ops_per_clk_per_sm"] for k, v in pp.items() if isinstance(v, dict)}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -412,7 +428,8 @@ def run_b200(args):
             "gpu_launches": launches + e2e_launches,
             "summary_check": summary_check,
             "roofline": {"bound": "alu", "achieved": achieved, "peak": peak_lane, "unit": "T lane-ops/s", "frac": achieved / peak_lane,
-                         "traffic": traffic, "kernel": "letf_path_kernel", "kernel_ms": kern_ms,
+                         "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": info["kernel"], "kernel_ms": kern_ms,
+                         "pipe_peaks_lane_ops_per_clk_per_sm": pipes,
                          "issue_slot_frac_executed": (n * T * exe / (kern_ms * 1e-3) / 1e12 / peak_lane) if exe else None,
                          "ncu": ncu_c.get("source"),
                          "lane_ops_per_path_day": wl["lane_ops"], "units_per_launch": n * T,

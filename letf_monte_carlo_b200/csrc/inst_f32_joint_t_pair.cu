@@ -7,6 +7,8 @@
 //  at trial counts that quantise badly into three-block waves the capped build wins, see profiles/README.md)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3, 4, 3, 2, 3, false, 128, 3)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3_r128, 4, 3, 2, 3, false, 128, 4)
+// 64-thread blocks, seven per SM: 14 warps instead of 12 at the same register budget (146 cap)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_c3_b64, 4, 3, 2, 3, false, 64, 7)
 // S1 S2 S3 and the like: two LETFs t(5) + SPY t(10)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3a, 4, 3, 3, 4, false, 128, 3)
 // one series

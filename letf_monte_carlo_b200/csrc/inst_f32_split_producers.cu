@@ -9,3 +9,4 @@ LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19, 32, 4, 4, 8, true, 128, 3)
 // A/B variants capped at 128 registers / four blocks per SM (LETF_KERNEL=<name>)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_r128, 32, 4, 3, 4, true, 128, 4)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19_r128, 32, 4, 4, 8, true, 128, 4)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_b64, 32, 4, 3, 4, true, 64, 7)

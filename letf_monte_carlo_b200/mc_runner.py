@@ -128,8 +128,23 @@ class MonteCarloRun(dict):
         self.taxable_ids = set(taxable_ids)
         self.strategy_ids = list(strategy_ids)
         self._summary = None
+        # the mapping stores slot indices and builds the (cheap) StrategyResults views on access: a stored view would point
+        # back at the run - a reference cycle, so a dropped run (and its device buffers) would wait for the cyclic collector
+        # and every call would have to cudaMalloc fresh result buffers
         for s, sid in enumerate(strategy_ids):
-            self[sid] = StrategyResults(self, sid, s)
+            dict.__setitem__(self, sid, s)
+
+    def __getitem__(self, sid):
+        return StrategyResults(self, sid, dict.__getitem__(self, sid))
+
+    def get(self, sid, default=None):
+        return self[sid] if sid in self else default
+
+    def values(self):
+        return [self[k] for k in self]
+
+    def items(self):
+        return [(k, self[k]) for k in self]
 
     @property
     def out(self):
@@ -177,28 +192,30 @@ class MonteCarloSummary:
 
     def __init__(self, run: MonteCarloRun, benchmark_id: str = "S2"):
         from .distributed import exchange_summary
-        eng, dev = run.engine, run.device_out
-        self.run = run
-        bench = run.strategy_ids.index(benchmark_id) if benchmark_id in run.strategy_ids else -1
+        eng = run.engine
+        # (no reference back to the run: see MonteCarloRun.__init__)
+        self.device_out, self.strategy_ids, self.years, self.n_total = run.device_out, list(run.strategy_ids), run.years, run.n_total
+        bench = self.strategy_ids.index(benchmark_id) if benchmark_id in self.strategy_ids else -1
         self.sm = eng.new_summary(bench_strategy=bench)
-        eng.reduce(dev, self.sm, n_trials=run.n_local)
+        eng.reduce(self.device_out, self.sm, n_trials=run.n_local)
         exchange_summary(self.sm, engine=eng)
         self._host = None
 
     def _fetch(self):
         if self._host is None:
+            import torch
             b = self.sm.buf.cpu()                                       # the one device -> host copy of this route
             nh, nc = self.sm.hist.numel(), self.sm.counters.numel()
             nm = self.sm.moments.numel()
             S = max(self.sm.n_strategies, 1)
-            f = b[nh + nc:].view(__import__("torch").float64).numpy()
+            f = b[nh + nc:].view(torch.float64).numpy()
             self._host = {"hist": b[:nh].numpy().reshape(S, abi.N_METRICS, abi.HIST_BINS), "counters": b[nh:nh + nc].numpy().reshape(S, 4),
                           "moments": f[:nm].reshape(S, abi.N_METRICS, 2), "extrema": f[nm:].reshape(S, abi.N_METRICS, 2)}
             valid = self._host["counters"][:, 0]
-            if (valid < self.run.n_total).any():
-                bad = int(self.run.n_total - valid.min())
+            if (valid < self.n_total).any():
+                bad = int(self.n_total - valid.min())
                 from .engine import NonFiniteTrials
-                raise NonFiniteTrials(f"{bad} of {self.run.n_total} trials generated non-finite returns or VIX <= 0 "
+                raise NonFiniteTrials(f"{bad} of {self.n_total} trials generated non-finite returns or VIX <= 0 "
                                       f"(reference raises ValueError, engine.py:486-498)")
         return self._host
 
@@ -210,16 +227,16 @@ class MonteCarloSummary:
         from .summary import PERCENTILES, global_percentiles, summary_from_histograms
         h = self._fetch()
         rows = summary_from_histograms(h["hist"], self.sm.lo, self.sm.hi, h["counters"], initial_capital)
-        years = self.run.years
-        for s, (sid, row) in enumerate(zip(self.run.strategy_ids, rows)):
+        years = self.years
+        for s, (sid, row) in enumerate(zip(self.strategy_ids, rows)):
             row["id"] = sid
             row["median"] = row["p50"]
             if exact:
                 qs = list(PERCENTILES)
-                for q, v in zip(qs, global_percentiles(self.run.device_out.final_wealth[s], qs)):
+                for q, v in zip(qs, global_percentiles(self.device_out.final_wealth[s], qs)):
                     row[f"p{q}"] = v
                 row["median"] = row["p50"]
-                row["dd_median"] = global_percentiles(self.run.device_out.max_dd[s], [50])[0]
+                row["dd_median"] = global_percentiles(self.device_out.max_dd[s], [50])[0]
             row["cagr"] = (row["median"] / initial_capital) ** (1 / years) - 1
             row["dd"] = row["dd_median"]
             row["trades"] = row["total_trades"] / max(row["valid"], 1) / years
