@@ -14,3 +14,6 @@ LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3a, 4, 3, 3, 4, false, 128, 3)
 // one series
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t5, 4, 3, 1, 0, false, 128, 3)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_1t10, 4, 3, 1, 1, false, 128, 3)
+// calibrated tracking_residual_model (per-series dof, tanh cap), two / three series
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_2tedf, 4, 3, 2, 0x80, false, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_pair_3tedf, 4, 3, 3, 0x80, false, 128, 3)

@@ -10,3 +10,6 @@ LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19, 32, 4, 4, 8, true, 128, 3)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_r128, 32, 4, 3, 4, true, 128, 4)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19_r128, 32, 4, 4, 8, true, 128, 4)
 LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_b64, 32, 4, 3, 4, true, 64, 7)
+// calibrated tracking_residual_model (per-series dof, tanh cap): the tracking-error sampler dispatches at run time
+LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_c4_tedf, 32, 4, 3, 0x80, true, 128, 3)
+LETF_INSTANTIATE_JPAIR(f32_joint_t_prod_sweep19_tedf, 32, 4, 4, 0x80, true, 128, 3)

@@ -147,7 +147,7 @@ static bool list_matches(const KernelEntry* k, const LetfEngine* e) {
 // Split strategy pipeline: the market + ETF layers of one antithetic pair per thread (letf_jfast.cuh, EMIT build) write
 // per-day records, a typed rule kernel (Trial::run in record mode, one trial per thread) consumes them.  Admitted: fp32,
 // Philox draws, no journal / tape plumbing, the institutional shape the pair kernel serves (joint-t + moment matching +
-// antithetic pairs + stress + funding, integer joint dof, default tracking-error dof, no tanh cap), SPY simulated and QQQ
+// antithetic pairs + stress + funding), SPY simulated and QQQ
 // not (the SPY price is the last record field), and a strategy list with a compiled-in typed rule kernel.
 struct SplitPlan { const KernelEntry* prod = nullptr; const KernelEntry* cons = nullptr; int nact = 0; };
 static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
@@ -155,17 +155,18 @@ static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t 
   if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split || (first & 1)) return false;
   if (s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs || !s.institutional ||
       !s.has_stress || !s.has_funding || s.sim_days < 2) return false;
-  for (int r = 0; r < 2; r++) if (!df_fast_k(s.joint[r].nu)) return false;
   const int mask = s.asset_mask & 0x3F;
   if (!((mask >> 4) & 1) || ((mask >> 5) & 1)) return false;
   int nact = 0, k10 = 0;
+  bool tedf = false;
   for (int a = 0; a < kAssets; a++) {
     if (!((mask >> a) & 1)) continue;
     const int fk = df_fast_k(s.assets[a].te_df);
-    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) return false;
+    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) tedf = true;      // calibrated tracking_residual_model: run-time sampler build
     if (fk == 10) k10 |= 1 << nact;
     nact++;
   }
+  if (tedf) k10 = 0x80;
   for (int i = 0; i < kernel_count(); i++) {
     const KernelEntry* k = kernel_at(i);
     if (k->precision != LETF_PREC_F32) continue;

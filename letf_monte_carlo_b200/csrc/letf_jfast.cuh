@@ -98,6 +98,8 @@ struct JointPair {
   typedef float R;
   typedef Mth<float> M;
   static_assert(NACT >= 1 && NACT <= NA, "active slots");
+  // K10 bit 7: tracking-error dof and tanh cap read at run time (calibrated tracking_residual_model, engine.py:185, :198-203)
+  static constexpr bool TEDF = (K10 & 0x80) != 0;
 
   // pj: global pair index (trials 2 pj and 2 pj + 1); lane: this thread's scratch column
   static LETF_HD void run(const KArgs<R, NS, NA>& ka, const int64_t pj, const int64_t lane) {
@@ -146,7 +148,7 @@ struct JointPair {
       }
       // per-regime constants held in registers between regime switches
       float mu[3] = {0, 0, 0}, c0[3] = {0, 0, 0}, c1[6] = {0, 0, 0, 0, 0, 0};
-      float alpha = 0, beta = 0, dcc_a = 0, dcc_b = 0, sqrt_nu = 0, kodd = 0, irx_base = 0;
+      float alpha = 0, beta = 0, dcc_a = 0, dcc_b = 0, sqrt_nu = 0, kodd = 0, irx_base = 0, nu = 0;
       int kk = 0, jreg = -1;
       const uint32_t mstreams[2] = {STREAM_MKT0, STREAM_MKT1};
       int reg = 0;
@@ -167,7 +169,7 @@ struct JointPair {
 #pragma unroll
           for (int a = 0; a < 6; a++) c1[a] = jp.c1[a];
           alpha = jp.alpha; beta = jp.beta; dcc_a = jp.dcc_a; dcc_b = jp.dcc_b; sqrt_nu = jp.sqrt_nu;
-          kk = jp.nu_fast_k; kodd = (kk & 1) ? 1.0f : 0.0f;
+          kk = jp.nu_fast_k; kodd = (kk & 1) ? 1.0f : 0.0f; nu = jp.nu;
           irx_base = p.irx_base[reg];
 #pragma unroll
           for (int t = 0; t < 2; t++) {
@@ -190,10 +192,13 @@ struct JointPair {
             q[t][5] = fmaf(dcc_b, q[t][5], fmaf(dcc_a, pz[t][2] * pz[t][2], c1[5]));
           }
         }
-        // chi-square mixing variable (calibration.py:565): nu = 4 / 5 straight-line, other integer dof through the general form
+        // chi-square mixing variable (calibration.py:565): nu = 4 / 5 straight-line, other integer dof through the general
+        // product form, non-integer dof (calibrated joint models, calibration.py:399) by Marsaglia-Tsang - first attempt inline,
+        // the ~3 % rejections out of line with their own Philox blocks, exactly as Trial::market_day draws them
         float u;
         if (kk == 4 || kk == 5) u = fmaf(nchi * kodd, nchi, M::neg2log_(M::u01(w[1].z) * M::u01(w[1].w)));
-        else u = chi2_int_fast<R>(kk, w[1].z, w[1].w, nchi);
+        else if (kk != 0) u = chi2_int_fast<R>(kk, w[1].z, w[1].w, nchi);
+        else u = chi2_marsaglia_tsang<R, false>(nu, nchi, w[1].z, key, (uint32_t)g, STREAM_MKT1);
         const float scale = sqrt_nu * M::rsqrt_(fmaxf(u, 1e-12f));
         // risk-free rate of the day (engine.py:117-123, :516), regime in the sign bit
         const float rf = fminf(fmaxf(fmaf(0.5f, in, irx_base), 0.0f), 15.0f) * 0.01f;
@@ -318,7 +323,10 @@ struct JointPair {
       // tracking-error innovations (engine.py:185): shared by the twins
       float innov[NACT];
 #pragma unroll
-      for (int a = 0; a < NACT; a++) innov[a] = ((K10 >> a) & 1) ? student_t10<R>(w[1 + a]) : student_t5<R>(w[1 + a]);
+      for (int a = 0; a < NACT; a++) {
+        if (TEDF) innov[a] = student_t_block<R, false>(w[1 + a], p.act[a].te_df, p.act[a].te_fast_k, key, (uint32_t)g, streams[1 + a]);
+        else innov[a] = ((K10 >> a) & 1) ? student_t10<R>(w[1 + a]) : student_t5<R>(w[1 + a]);
+      }
 
       float x0[2], x1[2], x2[2];
       x0[0] = v.a0 + shift[0][0]; x1[0] = v.a1 + shift[0][1]; x2[0] = v.a2 + shift[0][2];
@@ -365,7 +373,9 @@ struct JointPair {
           const float te_raw = fmaf(ap.te_rho, te_prev[t][a], (innov[a] * vrlive) * (ap.te_scale * mm));
           te_prev[t][a] = te_raw;
           bias[t][a] = fmaf(ema, te_raw, (1.0f - ema) * bias[t][a]);
-          const float er = clipfast(lev + (te_raw - bias[t][a]), -0.999f, 10.0f);
+          float te = te_raw - bias[t][a];
+          if (TEDF && ap.te_clip > 0.0f) te = ap.te_clip * M::tanh_(M::div_(te, ap.te_clip));
+          const float er = clipfast(lev + te, -0.999f, 10.0f);
           cp[t][a] = ::fma(cp[t][a], (double)er, cp[t][a]);
           ddq[t][a] = fminf(1.0f, fmaf(ddq[t][a], er, ddq[t][a]));
           ddm[t][a] = fminf(ddm[t][a], ddq[t][a]);

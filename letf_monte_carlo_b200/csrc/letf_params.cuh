@@ -76,8 +76,8 @@ template <typename R, int NS, int NA> struct DevParams {
       fast_layers /* 0, or 1 + bitmask of the slots whose tracking error is t(10) (others t(5)): every slot active,
                      no tanh cap, no funding model, no TLT series -> straight-line day step (letf_fast.cuh) */,
       fast_joint /* 0, or (n_act << 8) | mask of the t(10) slots: institutional joint-t market with moment matching,
-                    antithetic pairs, stress + funding models, integer joint dof, every active series buy&hold with
-                    default tracking-error dof and no tanh cap -> one antithetic pair per thread (letf_jfast.cuh) */;
+                    antithetic pairs, stress + funding models, every active series buy&hold -> one
+                    antithetic pair per thread (letf_jfast.cuh); mask 0x80 = tracking-error dof / tanh cap read at run time */;
   R W0, sim_years;
   R start_p1;                   // P(start in regime 1), LetfParams::start_regime_prob1
   int flip[2];
@@ -234,20 +234,21 @@ inline void build_boot_tables(const LetfParams& s, BootTables<R>& t) {
 inline int fast_joint_shape(const LetfParams& s, int na) {
   if (na >= kAssets || s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs) return 0;
   if (!s.institutional || !s.has_stress || !s.has_funding || s.sim_days < 2) return 0;
-  for (int r = 0; r < 2; r++) if (!df_fast_k(s.joint[r].nu)) return 0;
   for (int k = 0; k < s.n_strategies; k++)
     if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) return 0;
   int nact = 0, k10 = 0;
+  bool tedf = false;        // some series has a non-default tracking-error dof or a tanh cap: run-time sampler build (code 0x80)
   for (int a = 0; a < kAssets; a++) {
     if (!((s.asset_mask >> a) & 1)) continue;
     const int fk = df_fast_k(s.assets[a].te_df);
-    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) return 0;
+    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) tedf = true;
     bool bench = false;
     for (int k = 0; k < s.n_strategies; k++) if (s.strategies[k].type == LETF_ST_BENCHMARK && s.strategies[k].asset == a) bench = true;
     if (!bench) return 0;
     if (fk == 10) k10 |= 1 << nact;
     nact++;
   }
+  if (tedf) k10 = 0x80;
   if (nact < 1 || nact > na) return 0;
   return (nact << 8) | k10;
 }

@@ -159,12 +159,14 @@ extern "C" int letf_emu_run_jpair(const LetfParams* sp, const LetfOutputs* out, 
   ka.spell_scr = spells.data();
   const int code = ka.p.fast_joint;
   const bool compiled = code == fast_joint_code(2, 3) || code == fast_joint_code(3, 4) || code == fast_joint_code(1, 0) ||
-                        code == fast_joint_code(1, 1);
+                        code == fast_joint_code(1, 1) || code == fast_joint_code(2, 0x80) || code == fast_joint_code(3, 0x80);
   if (used_pair) *used_pair = (compiled && !force_generic) ? code : 0;
   if (compiled && !force_generic && n > 0) {
     if (code == fast_joint_code(2, 3)) run_jpairs<2, 3>(ka, first, n);
     else if (code == fast_joint_code(3, 4)) run_jpairs<3, 4>(ka, first, n);
     else if (code == fast_joint_code(1, 0)) run_jpairs<1, 0>(ka, first, n);
+    else if (code == fast_joint_code(2, 0x80)) run_jpairs<2, 0x80>(ka, first, n);
+    else if (code == fast_joint_code(3, 0x80)) run_jpairs<3, 0x80>(ka, first, n);
     else run_jpairs<1, 1>(ka, first, n);
   } else {
     for (int64_t j = 0; j < n; j++) {
@@ -238,8 +240,11 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
 }
 extern "C" int letf_emu_run_split(const LetfParams* sp, int list, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
   if (validate_params(*sp)) return -1;
-  if (list == 1) return run_split<8, 1, 25, 3, 4>(sp, out, seed, first, n);
-  if (list == 2) return run_split<32, 2, 29, 4, 8>(sp, out, seed, first, n);
+  bool tedf = false;
+  for (int a = 0; a < kAssets; a++)
+    if (((sp->asset_mask >> a) & 1) && ((df_fast_k(sp->assets[a].te_df) != 5 && df_fast_k(sp->assets[a].te_df) != 10) || sp->assets[a].te_clip > 0.0)) tedf = true;
+  if (list == 1) return tedf ? run_split<8, 1, 25, 3, 0x80>(sp, out, seed, first, n) : run_split<8, 1, 25, 3, 4>(sp, out, seed, first, n);
+  if (list == 2) return tedf ? run_split<32, 2, 29, 4, 0x80>(sp, out, seed, first, n) : run_split<32, 2, 29, 4, 8>(sp, out, seed, first, n);
   return -4;
 }
 

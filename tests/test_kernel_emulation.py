@@ -246,12 +246,21 @@ def test_joint_pair_variant_not_admitted_shapes_fall_back():
     out, used = emu.run_jpair(params, 4, seed=1)
     assert used == 0 and np.isfinite(out.final_wealth).all()
     ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
-    params, keep = build_params(["S1", "S2"], 1, synthetic.fallback_regime_model("vix_te"), ns)   # TQQQ: calibrated dof 4 + tanh cap
-    out, used = emu.run_jpair(params, 4, seed=1)
-    assert used == 0 and np.isfinite(out.final_wealth).all()
-    # explicit VIX dynamics and empirical dwell-time samples are run-time parameters of the pair kernel
-    for variant in ("vix_te", "durations", "jumpy"):
-        params, keep = build_params(["S2", "B_QQQ", "B_TLT"], 1, synthetic.fallback_regime_model(variant), ns)
+    # a calibrated tracking_residual_model (TQQQ: dof 4 + tanh cap) runs the pair body with the run-time sampler (code 0x80)
+    params, keep = build_params(["S1", "S2"], 1, synthetic.fallback_regime_model("vix_te"), ns)
+    pair, used = emu.run_jpair(params, 16, seed=1)
+    slow, _ = emu.run_jpair(params, 16, seed=1, force_generic=True)
+    assert used == 0x280
+    np.testing.assert_allclose(pair.final_wealth, slow.final_wealth, rtol=2e-5)
+    np.testing.assert_array_equal(pair.jump_days, slow.jump_days)
+    # explicit VIX dynamics, empirical dwell-time samples and non-integer joint dof (calibrated models, calibration.py:399:
+    # Marsaglia-Tsang chi-square with out-of-line retries) are run-time parameters of the pair kernel
+    for variant in ("vix_te", "durations", "jumpy", "calibrated_nu"):
+        model = synthetic.fallback_regime_model("default" if variant == "calibrated_nu" else variant)
+        if variant == "calibrated_nu":
+            model["joint_return_model"]["regimes"][0]["nu"] = 5.3
+            model["joint_return_model"]["regimes"][1]["nu"] = 4.2
+        params, keep = build_params(["S2", "B_QQQ", "B_TLT"], 1, model, ns)
         pair, used = emu.run_jpair(params, 16, seed=2)
         slow, _ = emu.run_jpair(params, 16, seed=2, force_generic=True)
         assert used == 0x203
@@ -338,6 +347,13 @@ def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
     params, keep = build_params(sids, 2, synthetic.fallback_regime_model("default"), ns)
     split = emu.run_split(params, slot_list, 48, seed=5)
     fused = emu.run_typed(params, slot_list, 48, seed=5)
+    # calibrated tracking_residual_model (non-integer dof, tanh cap): the producer with the run-time sampler
+    pv, keepv = build_params(sids, 1, synthetic.fallback_regime_model("vix_te"), ns)
+    dummy = HostTape(1, pv.sim_days + pv.buffer_days, pv.sim_days, 1)
+    sv = emu.run_split(pv, slot_list, 16, seed=6)
+    fv = emu.run(pv, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=6, n=16)      # generic build: run-time dispatch
+    np.testing.assert_allclose(sv.final_wealth, fv.final_wealth, rtol=1e-3)
+    assert np.mean(sv.num_trades != fv.num_trades) < 0.02
     np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
     assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 2e-6
     np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
