@@ -9,12 +9,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, "/root/reference")
-from letf import calibration as ref_cal  # noqa: E402
-from letf import config as ref_cfg  # noqa: E402
 from letf_monte_carlo_b200 import synthetic  # noqa: E402
 from letf_monte_carlo_b200.tape import HostTape  # noqa: E402
-from oracle.make_golden import TapeGenerator  # noqa: E402
+# (the reference is imported only when this script runs as the generator: tests import `inputs` on boxes without it)
 
 
 def inputs(n_days=400, seed=21):
@@ -30,6 +27,10 @@ def inputs(n_days=400, seed=21):
 
 
 if __name__ == "__main__":
+    sys.path.insert(0, "/root/reference")
+    from letf import calibration as ref_cal
+    from letf import config as ref_cfg
+    from oracle.make_golden import TapeGenerator
     regime, x, chi2, joint = inputs()
     n = len(regime)
     tape = HostTape(1, n, n, 1)

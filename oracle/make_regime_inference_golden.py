@@ -8,9 +8,7 @@ import numpy as np
 import pandas as pd
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, "/root/reference")
-from letf import strategy as ref_strategy  # noqa: E402
-from letf.utils import compute_high_vol_probability, infer_regime_from_vix  # noqa: E402
+# (the reference is imported only when this script runs as the generator: tests import `frame` on boxes without it)
 
 
 def frame(T=900, seed=11):
@@ -30,6 +28,9 @@ def frame(T=900, seed=11):
 
 
 if __name__ == "__main__":
+    sys.path.insert(0, "/root/reference")
+    from letf import strategy as ref_strategy
+    from letf.utils import compute_high_vol_probability, infer_regime_from_vix
     df = frame()
     rv = df["SPY_Ret"].rolling(20, min_periods=5).std().bfill().fillna(0) * np.sqrt(252)
     ts = (df["TNX"] - df["IRX"]).values

@@ -39,28 +39,43 @@ for lw in ("c2", "c3"):
 consts = {"_comment": "constants read from the committed ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum per "
                       "launch / trials of that launch; smsp__inst_executed.sum x 32 / path-days of that launch); bench.py scales them "
                       "to its launch and copies them into the JSON line"}
+KERNEL_RE = {0: "letf_jpair_kernel|letf_path_kernel", 1: "letf_path_kernel"}
 for w, n in TRIALS.items():
     rep = os.path.join(src, f"prof_{w}.ncu-rep")
     if not os.path.exists(rep):
         continue
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_metrics.py"), rep], capture_output=True, text=True).stdout
-    with open(os.path.join(prof, f"{RND}_{w}_{tag}_ncu_full_summary.csv"), "w") as fh:
-        fh.write("metric,unit,value\n" + out)
-    mix = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_sass_mix.py"), rep, str(n * 7560), "--blocks"],
-                         capture_output=True, text=True).stdout
-    with open(os.path.join(prof, f"{RND}_{w}_{tag}_sass_mix.txt"), "w") as fh:
-        fh.write(mix)
-    m = {}
-    for line in out.splitlines():
-        k, u, v = line.split(",")[:3]
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
-        m[k] = float(v) * scale
-    dram = m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
-    inst = m.get("smsp__inst_executed.sum", 0.0)
+    # a report of the split strategy pipeline holds two kernels: the pair producer and the rule kernel
+    parts = []
+    for ki in (0, 1):
+        out = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_metrics.py"), rep, str(ki)], capture_output=True, text=True).stdout
+        if out.strip():
+            parts.append(out)
+    split = len(parts) == 2
+    dram = inst = ms = 0.0
+    for ki, out in enumerate(parts):
+        sfx = ("_producer" if ki == 0 else "_rules") if split else ""
+        with open(os.path.join(prof, f"{RND}_{w}{sfx}_{tag}_ncu_full_summary.csv"), "w") as fh:
+            fh.write("metric,unit,value\n" + out)
+        kre = ("letf_jpair_kernel" if ki == 0 else "letf_path_kernel") if split else None
+        mix = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_sass_mix.py"), rep, str(n * 7560), "--blocks"] +
+                             ([f"--kernel={kre}"] if kre else []), capture_output=True, text=True).stdout
+        with open(os.path.join(prof, f"{RND}_{w}{sfx}_{tag}_sass_mix.txt"), "w") as fh:
+            fh.write(mix)
+        m = {}
+        for line in out.splitlines():
+            k, u, v = line.split(",")[:3]
+            if k == "kernel":
+                continue
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+            m[k] = float(v) * scale
+        dram += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
+        inst += m.get("smsp__inst_executed.sum", 0.0)
+        ms += m.get("gpu__time_duration.sum", 0)
+        print(w, sfx, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % (m.get("smsp__inst_executed.sum", 0) * 32 / (n * 7560)),
+              "issue %.1f%%" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0),
+              "DRAM GB %.2f" % ((m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)) / 1e9))
     consts[w] = {"dram_bytes_per_trial": dram / n, "executed_warp_instr_per_path_day": inst * 32 / (n * 7560),
-                 "source": f"profiles/{RND}_{w}_{tag}_ncu_full_summary.csv ({n} trials)"}
-    print(w, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % consts[w]["executed_warp_instr_per_path_day"],
-          "issue %.1f%%" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0), "DRAM GB %.2f" % (dram / 1e9))
+                 "source": f"profiles/{RND}_{w}" + ("_{producer,rules}" if split else "") + f"_{tag}_ncu_full_summary.csv ({n} trials)"}
 cpath = os.path.join(prof, "ncu_constants.json")
 merged = json.load(open(cpath)) if os.path.exists(cpath) else {}
 merged.update(consts)             # workloads not in this pass keep their constants
