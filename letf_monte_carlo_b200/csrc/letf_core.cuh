@@ -851,22 +851,40 @@ struct Trial {
 #if defined(__CUDA_ARCH__)
     float* const stage = FSER ? letf_stage_smem() + threadIdx.x : nullptr;
     const int sblk = blockDim.x;
-    auto stage_issue = [&](int day) {
+    // the copies of one day all read at (loop-invariant, warp-uniform) element offsets from that day's row of field 0:
+    // one running pointer per thread, advanced by a row per day, instead of a 64-bit index product per value
+    const float* issue_row = FSER ? ka.rec + col : nullptr;          // row of the next day to be issued
+    int issue_slot = 0;                                              // its stage slot (day % kStage, kept incrementally)
+    auto rec_off = [&](int v) -> int64_t {
+      if (v < NF) return (int64_t)v * rfs;
+      const int lag = v == NF ? 5 : v == NF + 1 ? 10 : v == NF + 2 ? 20 : v == NF + 3 ? 60 : v == NF + 4 ? 126 :
+                      v == NF + 5 ? 100 : v == NF + 6 ? 200 : v == NF + 7 ? 14 : 15;
+      const int f = v <= NF + 3 ? 0 : (v == NF + 4 ? NF - 3 : NF - 1);
+      return (int64_t)f * rfs - (int64_t)lag * rnc;
+    };
+    auto rec_lag = [](int v) -> int {
+      return v < NF ? 0 : (v == NF ? 5 : v == NF + 1 ? 10 : v == NF + 2 ? 20 : v == NF + 3 ? 60 : v == NF + 4 ? 126 :
+                           v == NF + 5 ? 100 : v == NF + 6 ? 200 : v == NF + 7 ? 14 : 15);
+    };
+    // all_valid: the caller knows that every window is full on that day (steady-state copy of the day body)
+    auto stage_issue = [&](int day, bool all_valid) {
       if (day < T) {
-        float* dst = stage + (day % kStage) * kNV * sblk;
+        float* dst = stage + issue_slot * kNV * sblk;
 #pragma unroll
         for (int v = 0; v < kNV; v++) {
           if (v >= NF && !rec_used[v - NF]) continue;
-          const float* src = rec_src(v, day);
-          if (src) cp_async4(dst + v * sblk, src);
+          if (all_valid || day >= rec_lag(v)) cp_async4(dst + v * sblk, issue_row + rec_off(v));
         }
+        issue_row += rnc;
+        issue_slot = issue_slot + 1 == kStage ? 0 : issue_slot + 1;
       }
       cp_async_commit();
     };
-    auto stage_value = [&](int v, int day) -> R { return (R)stage[((day % kStage) * kNV + v) * sblk]; };
+    int read_slot = 0;                                               // stage slot of the day being consumed
+    auto stage_value = [&](int v, int) -> R { return (R)stage[(read_slot * kNV + v) * sblk]; };
     if (FSER) {
 #pragma unroll
-      for (int d = 0; d < kStage - 1; d++) stage_issue(d);
+      for (int d = 0; d < kStage - 1; d++) stage_issue(d, false);
     }
 #else
     auto stage_value = [&](int v, int day) -> R { const float* src = rec_src(v, day); return src ? (R)*src : (R)0; };
@@ -884,7 +902,7 @@ struct Trial {
       R pf_p200 = 0, pf_p100 = 0, pf_s126 = 0, pf_r60 = 0, pf_r20 = 0, pf_r10 = 0, pf_r5 = 0, pf_p14 = 0, pf_p15 = 0;
       if (FSER) {
 #if defined(__CUDA_ARCH__)
-        stage_issue(i + kStage - 1);
+        stage_issue(i + kStage - 1, STEADY);
         cp_async_wait<kStage - 1>();                    // day i's copies have landed (all but the newest kStage - 1 groups)
 #endif
         // the values each window retires today (0 while the window is still filling)
@@ -933,6 +951,9 @@ struct Trial {
         const R v = stage_value(NF - 2, i);
         vix = M::abs_(v); s_reg = v < (R)0 ? 1 : 0;              // VIX >= 10: the sign bit carries the regime
         rec_pspy = stage_value(NF - 1, i);
+#if defined(__CUDA_ARCH__)
+        read_slot = read_slot + 1 == kStage ? 0 : read_slot + 1;
+#endif
       }
       const int reg = SERIES ? s_reg : regime_next(rg);
       R x[3] = {0, 0, 0}, vn = 0, in = 0;
