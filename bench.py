@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py - LETF path-days/sec on N B200s (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c1x|c2|c3|c4|c5|sweep19|boot|series|series19]
 
-A "step" is one pass of the hot path over one batch: the fused path kernel over this rank's trials
-(Philox draws generated on the device), the summary reduction kernel, and - for N > 1 - the NCCL
-allreduce of the summary buffers.  N = 1 workload: BASELINE.json configs[1] ("c2": TQQQ/UPRO/SSO with
-expense ratio + borrow cost + tracking error, 100k trials x 7,560 days).  N > 1: the same number of
-trials PER GPU (weak scaling), trial ids globally unique.
+A "step" is one pass of the hot path over one batch: the path kernel(s) over this rank's trials (Philox draws generated on
+the device), the summary reduction kernel, and - for N > 1 - the exchange of the packed summary (one NCCL all-gather + one
+combine kernel).  N = 1 workload: BASELINE.json configs[2], the largest single-GPU configuration ("c3": regime-switching
+multivariate-t GARCH/DCC QQQ/SPY/TLT market with VIX / IRX, stress + jumps, antithetic pairs, moment matching, random
+start; 1M trials x 7,560 days).  N > 1: the same number of trials PER GPU (weak scaling), trial ids globally unique.
 
-`--impl reference` times the CPU restatement of the reference algorithm (oracle/letf_oracle.c, every
-variate drawn by a conventional CPU generator) with all host threads, on a bounded sample of the same
-workload.  (The reference itself is pure Python and is not importable on the GPU box.)
+The line carries `roofline` (ALU-issue roofline of SURVEY.md 8d, measured DRAM traffic vs algorithmic bytes, measured pipe
+peaks), `e2e` (the same metric through the public API: parameter dicts in, summary table out on the host),
+`cpu_baseline` (the C port of the reference algorithm on the box's host cores) and `cpu_baseline_numpy` (the UNMODIFIED
+reference package, copied to the git-ignored baseline/_ref, through its own parallel_monte_carlo_fixed).
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/letf_oracle.c, every variate drawn by a
+conventional CPU generator) with all host threads, on a bounded sample of the same workload - the conservative
+denominator: the reference's own NumPy path is three orders of magnitude slower.
 """
 from __future__ import annotations
 
