@@ -868,3 +868,34 @@ def test_simulate_joint_returns_t_dropin_matches_live_reference(anti, engine_lib
     b = simulate_joint_returns_t(300, regime[:300], joint, np.random.default_rng(5), cfg=synthetic.config_namespace())
     assert all(len(v) == 300 and np.isfinite(v).all() for v in a.values())
     np.testing.assert_array_equal(a["QQQ_Ret"], b["QQQ_Ret"])
+
+
+@pytest.mark.parametrize("days,random_start", [(2, True), (5, False), (61, True), (257, False), (300, True)])
+def test_pair_and_split_paths_at_edge_horizons(days, random_start, engine_lib, monkeypatch):
+    """horizons around the staging depth of the rule kernel (3 days ahead), the rolling-window lengths and the steady-state
+    switch of its day body (256), with and without the random-start buffer: the split pipeline and the pair kernel against
+    the fused / general builds on the same Philox counters"""
+    model = synthetic.fallback_regime_model("default")
+    years = days / 252.0 + 1e-9
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=random_start)
+    p3, k3 = build_params(["S2", "B_QQQ", "B_TLT"], years, model, ns)
+    p19, k19 = build_params(ALL19, years, model, synthetic.config_namespace(USE_RANDOM_START=random_start))
+    assert p3.sim_days == days
+    with _engine(p3, k3, "f32") as eng:
+        pair = eng.run_host(300, seed=3)
+        assert eng.launch_info()["kernel"].startswith("f32_joint_t_pair")
+    with _engine(p19, k19, "f32") as eng:
+        split = eng.run_host(300, seed=4)
+        assert "rules" in eng.launch_info()["kernel"]
+    monkeypatch.setenv("LETF_NO_JPAIR", "1")
+    monkeypatch.setenv("LETF_NO_SPLIT", "1")
+    with _engine(p3, k3, "f32") as eng:
+        lean = eng.run_host(300, seed=3)
+    with _engine(p19, k19, "f32") as eng:
+        fused = eng.run_host(300, seed=4)
+    np.testing.assert_allclose(pair.final_wealth, lean.final_wealth, rtol=5e-5)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=2e-3)
+    for a, b in ((pair, lean), (split, fused)):
+        for k in ("flags", "start_offset", "regime_days", "jump_days"):
+            np.testing.assert_array_equal(getattr(a, k), getattr(b, k))
+    assert np.mean(split.num_trades != fused.num_trades) < 0.01

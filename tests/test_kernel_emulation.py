@@ -366,6 +366,31 @@ def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
     np.testing.assert_array_equal(part.num_trades, split.num_trades[:, :7])
 
 
+@pytest.mark.parametrize("days,random_start", [(2, True), (5, False), (61, True), (257, False), (300, True)])
+def test_pair_and_split_paths_at_edge_horizons(days, random_start):
+    """horizons around the staging depth (3 days ahead), the window lengths and the steady-state switch of the day body
+    (256), with and without the random-start buffer: pair kernel and split pipeline against the general loops"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_RANDOM_START=random_start)
+    model = synthetic.fallback_regime_model("default")
+    years = days / 252.0 + 1e-9
+    params, keep = build_params(["S2", "B_QQQ", "B_TLT"], years, model, ns)
+    assert params.sim_days == days
+    pair, used = emu.run_jpair(params, 10, seed=3)
+    slow, _ = emu.run_jpair(params, 10, seed=3, force_generic=True)
+    assert used == 0x203
+    np.testing.assert_allclose(pair.final_wealth, slow.final_wealth, rtol=2e-5)
+    np.testing.assert_allclose(pair.max_dd, slow.max_dd, atol=5e-6)
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(pair, k), getattr(slow, k))
+    p19, keep19 = build_params(ALL19, years, model, synthetic.config_namespace(USE_RANDOM_START=random_start))
+    split = emu.run_split(p19, 2, 10, seed=4)
+    fused = emu.run_typed(p19, 2, 10, seed=4)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
+    np.testing.assert_array_equal(split.regime_days, fused.regime_days)
+    np.testing.assert_array_equal(split.flags, fused.flags)
+    assert np.mean(split.num_trades != fused.num_trades) < 0.02
+
+
 def test_lean_fast_variant_config1_shape():
     """BASELINE config 1 (validation.py:33-57): one frictionless 3x series - the straight-line loop draws no
     tracking-error block at all; against the lean build's general loop and the generic build on the same counters"""
