@@ -6,10 +6,10 @@ ranks (`MAX_TAX_SIMS`), push each sampled trial's `Trade_List` through the tax e
 wealth, and report percentiles of both distributions, tax drag and the post-tax win rate against S2.
 
 On the GPU path only the sampled trials ever have a trade list: it is replayed on the device for exactly those
-trials (`letf_trade_list_host`, one re-simulation each), everything else stays as arrays.  The tax engine itself
-(lot selection, wash sales, yearly netting: letf/tax/*, ~2 700 lines of host bookkeeping on <= 50 trials per
-strategy) is NOT restated here - it is injected as `tax_fn`, by default the reference's own function when the
-`letf` package is importable next to this one.
+trials (`letf_trade_lists_host`, one launch per strategy), everything else stays as arrays.  The tax engine (lot
+selection, wash sales, yearly netting, marginal brackets: host bookkeeping on <= 50 trade lists per strategy) is
+`tax_engine.process_trades`, a restatement of the reference's `process_trades_with_wired_engine` pinned to it
+(tests/test_tax_engine.py); any other engine can be injected as `tax_fn`.
 """
 from __future__ import annotations
 
@@ -24,19 +24,13 @@ PCTS = (("p10", 10), ("p25", 25), ("p40", 40), ("p60", 60), ("p75", 75), ("p90",
 
 
 def default_tax_fn() -> Callable:
-    """The reference's tax entry point (letf/integration.py:26), if its package is importable."""
-    try:
-        from letf.integration import process_trades_with_wired_engine
-        from letf.tax.engine import TaxpayerElections
-    except Exception as e:  # pragma: no cover - depends on the environment
-        raise RuntimeError("no tax engine: pass tax_fn=..., or make the reference's `letf` package importable "
-                           "(its tax engine is host code outside the GPU path)") from e
+    """The in-tree host tax engine (tax_engine.py: wash sales, lot selection, yearly netting, marginal brackets - the
+    reference's `process_trades_with_wired_engine`, letf/integration.py:26, restated and pinned to it) with the reference's
+    default elections (FIFO lots, short-term-first loss ordering)."""
+    from .tax_engine import process_trades
 
     def fn(trades, time_horizon_years, initial_capital, strategy_id, tax_config):
-        r = process_trades_with_wired_engine(trades=trades, time_horizon_years=time_horizon_years,
-                                             elections=TaxpayerElections(), initial_capital=initial_capital,
-                                             debug=False, strategy_id=strategy_id, tax_config=tax_config)
-        return r["total_tax"]
+        return process_trades(trades, time_horizon_years, initial_capital, tax_config=tax_config)["total_tax"]
     return fn
 
 
