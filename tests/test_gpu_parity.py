@@ -899,3 +899,35 @@ def test_pair_and_split_paths_at_edge_horizons(days, random_start, engine_lib, m
         for k in ("flags", "start_offset", "regime_days", "jump_days"):
             np.testing.assert_array_equal(getattr(a, k), getattr(b, k))
     assert np.mean(split.num_trades != fused.num_trades) < 0.01
+
+
+@pytest.mark.parametrize("sids,kname", [(["S2", "B_QQQ", "B_TLT"], "f32_joint_t_pair_c3"), (["S1", "S2"], "f32_joint_t_pair_2tedf"),
+                                        (ALL19, "prod_sweep19_tedf")], ids=["calibrated_nu", "calibrated_te_pair", "calibrated_te_split"])
+def test_pair_kernels_with_calibrated_models(sids, kname, engine_lib, monkeypatch):
+    """calibrated models (what letf.run() feeds the path): non-integer joint dof (calibration.py:399; Marsaglia-Tsang chi-square
+    with out-of-line retries in the pair kernel) and a tracking_residual_model with non-integer dof and a tanh cap (run-time
+    sampler builds): specialised kernels against the general builds on the same Philox counters, and against the oracle"""
+    model = synthetic.fallback_regime_model("vix_te" if "tedf" in kname else "default")
+    model["joint_return_model"]["regimes"][0]["nu"] = 5.3
+    model["joint_return_model"]["regimes"][1]["nu"] = 4.2
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, 1, model, ns)
+    n_t = 64
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    with _engine(params, keep, "f32") as eng:
+        fast = eng.run_host(2 * n_t, seed=123)
+        assert kname in eng.launch_info()["kernel"], eng.launch_info()["kernel"]
+        eng.run_host(2 * n_t, seed=123, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+    monkeypatch.setenv("LETF_NO_JPAIR", "1")
+    monkeypatch.setenv("LETF_NO_SPLIT", "1")
+    with _engine(params, keep, "f32") as eng:
+        slow = eng.run_host(2 * n_t, seed=123)
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-3)
+    assert np.median(np.abs(fast.final_wealth / slow.final_wealth - 1)) < 5e-6
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(fast, k), getattr(slow, k))
+    rel = np.abs(fast.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
+    assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
+    np.testing.assert_array_equal(fast.regime_days, o.regime_days)
+    np.testing.assert_array_equal(fast.jump_days, o.jump_days)
