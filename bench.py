@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - LETF path-days/sec on N B200s (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c1x|c2|c3|c4|c5|sweep19|boot|series|series19]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c1x|c2|c3|c4|c5|sweep19|sub5|boot|series|series19]
 
 A "step" is one pass of the hot path over one batch: the path kernel(s) over this rank's trials (Philox draws generated on
 the device), the summary reduction kernel, and - for N > 1 - the exchange of the packed summary (one NCCL all-gather + one
@@ -68,6 +68,9 @@ WORKLOADS = {
                           "caller-supplied day-major fp64 TQQQ / SSO / TMF / SPY return series + VIX + int32 regime path resident "
                           "in HBM, 100k paths x 2520 days",
                      trials=100_000, years=10, lane_ops=1500, mufu=40, bytes_per_path_day=5 * 8 + 4),
+    "sub5": dict(desc="a strategy list with no typed build (generic split pipeline: uncompacted pair producer -> six-field records -> "
+                      "dynamic-slot rule kernel): S1 S4 S7 S10 S15 on the institutional market, 227 328 trials x 7560 days per GPU",
+                 trials=227_328, years=30, lane_ops=520 * (7560 + 1260) / 7560 + 2 * 150 + 5 * 90 + 200, mufu=40),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "227 328 trials x 7560 days per GPU (whole waves of both kernels of the split pipeline: 2 x 56 832 "
                          "antithetic pairs, 6 x 37 888 rule-kernel trials; at 200 000 trials both run 88 % full)",
@@ -108,6 +111,10 @@ def build_workload(name):
         ns = synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid")
         sids = ["S1", "S2", "S3"]
         model = synthetic.legacy_bootstrap_model()
+    elif name == "sub5":
+        ns = synthetic.config_namespace()
+        sids = ["S1", "S4", "S7", "S10", "S15"]
+        model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     elif name == "sweep19":
         ns = synthetic.config_namespace()
         sids = ["S%d" % i for i in range(1, 20)]

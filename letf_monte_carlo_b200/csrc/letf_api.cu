@@ -18,6 +18,7 @@
 #include <string>
 #include <type_traits>
 #include <vector>
+#include <chrono>
 #include "letf_kernels.cuh"
 
 namespace letf {
@@ -102,7 +103,11 @@ struct LetfEngine {
   std::string pin_kernel;                    // tuning aids, read from the environment when the engine is created:
   bool no_jpair = false;                     // LETF_KERNEL=<instantiation>, LETF_NO_JPAIR=1, LETF_NO_SPLIT=1
   bool no_split = false;
+  bool no_generic_split = false;             // LETF_NO_GENERIC_SPLIT=1: untyped strategy lists keep the fused builds (A/B runs)
+  bool trace_host = false;
+  bool no_routed_split = false;              // LETF_NO_ROUTED_SPLIT=1: subsets of the default sweep skip the routed 19-rule kernel
   DevBuf rec;                                // per-day records of the split strategy pipeline
+  int64_t split_key = 0; int split_waves = 0; // its chunk size in producer waves, remembered per shape (launch_split)
   DevBuf spell;                              // regime spells of the pair kernels
   // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
   void* boot_blob = nullptr;
@@ -145,16 +150,27 @@ static bool list_matches(const KernelEntry* k, const LetfEngine* e) {
 }
 
 // Split strategy pipeline: the market + ETF layers of one antithetic pair per thread (letf_jfast.cuh, EMIT build) write
-// per-day records, a typed rule kernel (Trial::run in record mode, one trial per thread) consumes them.  Admitted: fp32,
+// per-day records, a rule kernel (Trial::run in record mode, one trial per thread) consumes them.  Admitted: fp32,
 // Philox draws, no journal / tape plumbing, the institutional shape the pair kernel serves (joint-t + moment matching +
-// antithetic pairs + stress + funding), SPY simulated and QQQ
-// not (the SPY price is the last record field), and a strategy list with a compiled-in typed rule kernel.
-struct SplitPlan { const KernelEntry* prod = nullptr; const KernelEntry* cons = nullptr; int nact = 0; };
-static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
+// antithetic pairs + stress + funding).  Two tiers:
+//  * typed: a strategy list with a compiled-in typed rule kernel, SPY simulated and QQQ not (compacted producer slots, the
+//    SPY price is the last record field);
+//  * generic: any strategy list - the uncompacted producer writes a field for each of the six series (zeros outside the
+//    asset mask), the dynamic-slot rule kernel reads them; no rule kernel launch when every strategy is buy&hold.
+struct SplitPlan {
+  const KernelEntry* prod = nullptr; const KernelEntry* cons = nullptr; int nact = 0; bool rules = true;
+  // routed: the requested strategies sit in slots of a larger typed list (slot_of[k] = slot of requested strategy k)
+  bool routed = false; int slot_of[LETF_MAX_STRATEGIES]; int n_slots = 0; int mask = 0;
+};
+static bool split_shape_ok(const LetfEngine* e, int rng_mode, bool need_io, int64_t first) {
   const LetfParams& s = e->params;
   if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split || (first & 1)) return false;
-  if (s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs || !s.institutional ||
-      !s.has_stress || !s.has_funding || s.sim_days < 2) return false;
+  return s.market_mode == LETF_MARKET_JOINT_T && s.moment_matching && s.antithetic_pairs && s.institutional &&
+         s.has_stress && s.has_funding && s.sim_days >= 2;
+}
+static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
+  const LetfParams& s = e->params;
+  if (!split_shape_ok(e, rng_mode, need_io, first)) return false;
   const int mask = s.asset_mask & 0x3F;
   if (!((mask >> 4) & 1) || ((mask >> 5) & 1)) return false;
   int nact = 0, k10 = 0;
@@ -171,12 +187,77 @@ static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t 
     const KernelEntry* k = kernel_at(i);
     if (k->precision != LETF_PREC_F32) continue;
     // (first registered candidate wins unless LETF_KERNEL names another one)
-    if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact &&
+    if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact && k->na < kAssets &&
         (!plan->prod || e->pin_kernel == k->name)) plan->prod = k;
-    if (k->market == kMarketFSeries && k->list && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e) &&
+    if (k->market == kMarketFSeries && k->list && k->list != 3 && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e) &&
         (!plan->cons || e->pin_kernel == k->name)) plan->cons = k;
   }
   plan->nact = nact;
+  return plan->prod && plan->cons;
+}
+// any subset of a typed list (today: the default 19-strategy sweep, slot list 3): every rule of the request goes to the slot
+// that compiles its type, buy&hold strategies to the list's buy&hold slots or to the free slots behind it (they cost the
+// rule kernel nothing: the producer writes them), every other slot is switched off; the producer simulates the list's series
+static bool find_routed_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
+  const LetfParams& s = e->params;
+  if (!split_shape_ok(e, rng_mode, need_io, first) || e->no_generic_split || e->no_routed_split) return false;
+  *plan = SplitPlan();
+  for (int i = 0; i < kernel_count(); i++) {
+    const KernelEntry* k = kernel_at(i);
+    if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || k->list != 3) continue;
+    const int mask = k->am & 0x3F, nl = slot_list_count(k->list);
+    if ((s.asset_mask & 0x3F) & ~mask) continue;
+    bool rules = false;
+    bool ok = route_request(s, k->list, k->ns, plan->slot_of, &rules);
+    for (int a = 0; ok && a < kAssets; a++) if (((mask >> a) & 1) && !(s.assets[a].leverage != 0.0)) ok = false;   // (series outside the request need a layer description)
+    if (!ok) continue;
+    plan->cons = k; plan->mask = mask; plan->rules = rules; plan->routed = true;
+    plan->n_slots = nl;
+    for (int q = 0; q < s.n_strategies; q++) if (plan->slot_of[q] + 1 > plan->n_slots) plan->n_slots = plan->slot_of[q] + 1;
+    break;
+  }
+  if (!plan->cons) return false;
+  int nact = 0, k10 = 0;
+  bool tedf = false;
+  for (int a = 0; a < kAssets; a++) {
+    if (!((plan->mask >> a) & 1)) continue;
+    const int fk = df_fast_k(s.assets[a].te_df);
+    if ((fk != 5 && fk != 10) || s.assets[a].te_clip > 0.0) tedf = true;
+    if (fk == 10) k10 |= 1 << nact;
+    nact++;
+  }
+  if (tedf) k10 = 0x80;
+  for (int i = 0; i < kernel_count(); i++) {
+    const KernelEntry* k = kernel_at(i);
+    if (k->precision == LETF_PREC_F32 && k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= plan->n_slots &&
+        k->na >= nact && k->na < kAssets && (!plan->prod || e->pin_kernel == k->name)) plan->prod = k;
+  }
+  plan->nact = nact;
+  return plan->prod != nullptr;
+}
+static bool find_generic_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
+  const LetfParams& s = e->params;
+  if (!split_shape_ok(e, rng_mode, need_io, first) || e->no_generic_split) return false;
+  const int mask = s.asset_mask & 0x3F;
+  // default tracking-error dof (config.py:62-135: t(5) for the leveraged series, t(10) for SPY / QQQ) or the run-time sampler build
+  bool tedf = false;
+  for (int a = 0; a < kAssets; a++) {
+    if (!((mask >> a) & 1)) continue;
+    if (df_fast_k(s.assets[a].te_df) != (a >= 4 ? 10 : 5) || s.assets[a].te_clip > 0.0) tedf = true;
+  }
+  const int code = kSplitProducer | fast_joint_code(kAssets, tedf ? 0x80 : 0x30);
+  *plan = SplitPlan();
+  for (int i = 0; i < kernel_count(); i++) {
+    const KernelEntry* k = kernel_at(i);
+    if (k->precision != LETF_PREC_F32) continue;
+    if (k->fj == code && k->na == kAssets && k->ns >= s.n_strategies && !plan->prod) plan->prod = k;
+    if (k->market == kMarketFSeries && !k->list && (k->am & 0x3F) == 0x3F && k->ns >= s.n_strategies &&
+        !(e->type_mask & ~k->tm) && !plan->cons) plan->cons = k;
+  }
+  plan->nact = kAssets;
+  plan->rules = false;
+  for (int k = 0; k < s.n_strategies; k++)
+    if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) plan->rules = true;
   return plan->prod && plan->cons;
 }
 
@@ -299,37 +380,72 @@ static LetfOutputs out_columns(const LetfOutputs& o, int64_t off) {
   return r;
 }
 
-template <int NSC>
+template <int NSC, int NAP>
 static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, uint64_t seed, int64_t first, int64_t n,
                         const LetfOutputs* out) {
-  constexpr int NSP = 32, NAP = 4;                     // producer instantiations (inst_f32_split_producers.cu)
+  constexpr int NSP = 32;                              // producer instantiations (inst_f32_split_producers.cu: NAP = 4 compacted
+                                                       // slots; inst_f32_split_generic_prod*.cu: NAP = 6, slot = asset)
   const KernelEntry *kp = plan.prod, *kc = plan.cons;
+  const bool trace = e->trace_host;           // LETF_TRACE_HOST=1: host time of each step of this function on stderr (tuning aid)
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[split %s %.3f ms] ", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
   cudaFuncAttributes fap, fac;
   int mbp = 0, mbc = 0;
   CK(kp->attrs(&fap, &mbp));
   CK(kc->attrs(&fac, &mbc));
   if (mbp < 1 || mbc < 1) return fail(LETF_ERR_CUDA, "split pipeline kernels cannot be resident on this device");
+  lap("attrs");
   static thread_local KArgs<float, NSP, NAP> ka_p;
   static thread_local KArgs<float, NSC, kAssets> ka_c;
   memset(&ka_p, 0, sizeof(ka_p)); memset(&ka_c, 0, sizeof(ka_c));
-  convert_params<float, NSP, NAP>(e->params, e->dev_dur, ka_p.p, (const DevBoot<float>*)(const void*)&e->boot32);
-  convert_params<float, NSC, kAssets>(e->params, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
-  const int T = e->params.sim_days, G = T + e->params.buffer_days, NF = plan.nact + 2;
-  // chunk of trials: whole producer waves (two trials per thread), as many as fit in half of the free device memory
-  const int64_t wave_trials = 2 * (int64_t)e->sm_count * mbp * kp->block;
-  const double per_trial = (double)T * NF * 4 + (double)G * sizeof(JF8) / 2;
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  const double budget = 0.5 * ((double)free_b + (double)e->rec.cap + (double)e->xscr.cap);
-  int64_t waves_fit = (int64_t)(budget / (per_trial * (double)wave_trials));
-  if (waves_fit < 1) return fail(LETF_ERR_NOMEM, "split pipeline: one wave of per-day records does not fit in device memory");
-  if (waves_fit > 4) waves_fit = 4;
-  int64_t cap = wave_trials * waves_fit;
-  if (cap > ((n + 1) & ~(int64_t)1)) cap = (n + 1) & ~(int64_t)1;
-  {
-    cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
-    if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "split pipeline records: " + std::string(cudaGetErrorString(ce))); }
+  if (plan.routed) {
+    static thread_local LetfParams rp;
+    rp = routed_params(e->params, plan.cons->list, plan.slot_of, plan.n_slots, plan.mask);
+    convert_params<float, NSP, NAP>(rp, e->dev_dur, ka_p.p, (const DevBoot<float>*)(const void*)&e->boot32);
+    convert_params<float, NSC, kAssets>(rp, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
+    route_slots(ka_p.p, e->params, plan.slot_of, plan.n_slots); route_slots(ka_c.p, e->params, plan.slot_of, plan.n_slots);
+  } else {
+    convert_params<float, NSP, NAP>(e->params, e->dev_dur, ka_p.p, (const DevBoot<float>*)(const void*)&e->boot32);
+    convert_params<float, NSC, kAssets>(e->params, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
   }
+  lap("params");
+  const int T = e->params.sim_days, G = T + e->params.buffer_days, NF = plan.rules ? plan.nact + 2 : 0;   // (no records without a rule kernel)
+  // chunk of trials: whole producer waves (two trials per thread), up to four, as many as fit in 60 % of the free device
+  // memory beside the producer's per-wave scratch.  The free-memory query is made once per (horizon, fields, wave) shape and
+  // remembered: cudaMemGetInfo costs 0.2 - 70 ms of host time with tens of GB allocated (measured), on every call's critical path
+  const int64_t wave_trials = 2 * (int64_t)e->sm_count * mbp * kp->block;
+  const double per_trial = (double)T * NF * 4;
+  const int64_t shape_key = ((int64_t)T << 32) ^ ((int64_t)NF << 24) ^ wave_trials;
+  int64_t waves_fit = e->split_waves;
+  if (e->split_key != shape_key || waves_fit < 1) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double wave_scratch = ((double)G * sizeof(JF8) + (double)(G + 1) * 4) * (double)(wave_trials / 2);
+    const double held = (double)e->xscr.cap + (double)e->spell.cap;
+    const double budget = 0.6 * ((double)free_b + (double)e->rec.cap - (wave_scratch > held ? wave_scratch - held : 0.0));
+    waves_fit = per_trial > 0 ? (int64_t)(budget / (per_trial * (double)wave_trials)) : 4;
+    if (waves_fit < 1) return fail(LETF_ERR_NOMEM, "split pipeline: one wave of per-day records does not fit in device memory");
+    if (waves_fit > 4) waves_fit = 4;
+    e->split_key = shape_key; e->split_waves = (int)waves_fit;
+  }
+  int64_t cap = 0;
+  for (;;) {
+    cap = wave_trials * waves_fit;
+    if (cap > ((n + 1) & ~(int64_t)1)) cap = (n + 1) & ~(int64_t)1;
+    cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
+    if (ce == cudaSuccess) break;
+    cudaGetLastError();
+    // (the remembered chunk size no longer fits, e.g. the caller allocated in between: smaller chunks, asked again next call)
+    e->split_key = 0;
+    if (waves_fit <= 1) return fail(LETF_ERR_NOMEM, "split pipeline records: " + std::string(cudaGetErrorString(ce)));
+    waves_fit /= 2;
+  }
+  lap("reserve");
   ka_p.seed = ka_c.seed = seed; ka_p.rng_mode = ka_c.rng_mode = LETF_RNG_PHILOX;
   ka_p.rec = ka_c.rec = (float*)e->rec.p; ka_p.rec_ncol = ka_c.rec_ncol = cap;
   ka_p.log_trial = ka_c.log_trial = -1;
@@ -357,7 +473,11 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
       ka_p.spell_scr = (uint32_t*)e->spell.p;
       if (c0 == 0) scratch += b + sb;
     }
+    lap("scratch");
     CK(kp->launch(&ka_p, (int)grid_p, st));
+    lap("producer");
+    launches++; grid_p_last = grid_p;
+    if (!plan.rules) continue;                 // buy&hold-only list: the producer wrote every output
     // rule kernel: one trial per thread, columns [0, nc) of the record buffer
     const int64_t grid_c = full_wave_grid(nc, e->sm_count, mbc, kc->block);
     const int64_t nth = grid_c * kc->block;
@@ -367,13 +487,16 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
     if (kc->tm & kNeedRingS) { size_t b = (size_t)kRingS * nth * 4; CK(e->ringS.reserve(b)); ka_c.ringS = (float*)e->ringS.p; if (c0 == 0) scratch += b; }
     if (kc->tm & kVolTypes) { size_t b = (size_t)kRingA * nth * 4; CK(e->ringA.reserve(b)); ka_c.ringA = (float*)e->ringA.p; if (c0 == 0) scratch += b; }
     CK(kc->launch(&ka_c, (int)grid_c, st));
-    launches += 2; grid_c_last = grid_c; grid_p_last = grid_p;
+    lap("rules");
+    launches++; grid_c_last = grid_c;
   }
+  if (trace) fprintf(stderr, "\n");
   CK(cudaEventRecord(e->ev1, st));
   e->timed = true;
   e->info.grid = (int)grid_p_last; e->info.block = kp->block; e->info.regs_per_thread = fap.numRegs;
   e->info.kernel_launches = launches; e->info.scratch_bytes = (int64_t)scratch; e->info.sm_count = e->sm_count;
-  snprintf(e->info.kernel, sizeof(e->info.kernel), "%s+%s", kp->name + 4, kc->name + 4);
+  if (plan.rules) snprintf(e->info.kernel, sizeof(e->info.kernel), "%s+%s", kp->name + 4, kc->name + 4);
+  else snprintf(e->info.kernel, sizeof(e->info.kernel), "%s", kp->name + 4);
   (void)grid_c_last;
   return LETF_OK;
 }
@@ -409,18 +532,31 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
                        lg.curve != nullptr || lg.market != nullptr;
   // a caller-supplied frame carries all six series; otherwise only the masked ones are simulated
   const int n_assets = market == kMarketSeries ? kAssets : __builtin_popcount((unsigned)e->params.asset_mask & 0x3Fu);
-  if (market == e->params.market_mode && !series) {
+  // LETF_KERNEL=<a fused instantiation> pins the fused path; naming a producer / rule kernel picks among the split ones
+  const bool pin_fused = e->pin_kernel.size() && e->pin_kernel.find("_prod_") == std::string::npos &&
+                         e->pin_kernel.find("_rules_") == std::string::npos;
+  const bool may_split = market == e->params.market_mode && !series && !pin_fused;
+  if (may_split) {
     SplitPlan plan;
-    // LETF_KERNEL=<a fused instantiation> pins the fused path; naming a producer / rule kernel picks among the split ones
-    const bool pin_fused = e->pin_kernel.size() && e->pin_kernel.find("_prod_") == std::string::npos &&
-                           e->pin_kernel.find("_rules_") == std::string::npos;
-    if (!pin_fused && find_split(e, rng_mode, need_io, first, &plan)) {
+    if (find_split(e, rng_mode, need_io, first, &plan)) {
       CK(cudaSetDevice(e->device));
-      if (plan.cons->ns == 8) return launch_split<8>(e, plan, st, seed, first, n, out);
-      if (plan.cons->ns == 32) return launch_split<32>(e, plan, st, seed, first, n, out);
+      if (plan.cons->ns == 8) return launch_split<8, 4>(e, plan, st, seed, first, n, out);
+      if (plan.cons->ns == 32) return launch_split<32, 4>(e, plan, st, seed, first, n, out);
     }
   }
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);
+  // no typed pipeline and no antithetic-pair kernel for this list: the generic split pipeline before the fused builds
+  if (may_split && !(ke && ke->fj)) {
+    SplitPlan plan;
+    if (find_routed_split(e, rng_mode, need_io, first, &plan)) {
+      CK(cudaSetDevice(e->device));
+      return launch_split<32, 4>(e, plan, st, seed, first, n, out);
+    }
+    if (find_generic_split(e, rng_mode, need_io, first, &plan)) {
+      CK(cudaSetDevice(e->device));
+      return launch_split<32, kAssets>(e, plan, st, seed, first, n, out);
+    }
+  }
   if (!ke) return fail(LETF_ERR_INVALID, "no kernel instantiation for this (precision, market, strategies) combination");
   CK(cudaSetDevice(e->device));
 #define GO(R, NS, NA) return launch_typed<R, NS, NA>(e, ke, st, seed, first, n, rng_mode, tape, out, series, lg)
@@ -529,6 +665,9 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
   { const char* v = getenv("LETF_KERNEL"); e->pin_kernel = v ? v : ""; }
   { const char* v = getenv("LETF_NO_JPAIR"); e->no_jpair = v && *v && *v != '0'; }
   { const char* v = getenv("LETF_NO_SPLIT"); e->no_split = v && *v && *v != '0'; }
+  { const char* v = getenv("LETF_NO_GENERIC_SPLIT"); e->no_generic_split = v && *v && *v != '0'; }
+  { const char* v = getenv("LETF_NO_ROUTED_SPLIT"); e->no_routed_split = v && *v && *v != '0'; }
+  { const char* v = getenv("LETF_TRACE_HOST"); e->trace_host = v && *v && *v != '0'; }
   for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
   ce = cudaEventCreate(&e->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);

@@ -65,6 +65,8 @@ LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 // exists once and no per-day type dispatch is left.  list 0 = dynamic dispatch on p.strat[s].type.
 //   1: BASELINE config 4 sweep        S1 S2 S4 S5 S6 S19
 //   2: the reference's default sweep  S1 ... S19 in cfg.STRATEGIES order (letf/config.py:348-437)
+//   3: list 2 with routed slots: any subset of the default sweep - a slot can be switched off and writes the output row
+//      DevStrategy::route names (record mode only; letf_api.cu find_routed_split)
 // -2 marks an empty slot.
 LETF_HD constexpr int slot_list_type(int list, int s) {
   if (list == 1) {
@@ -77,7 +79,7 @@ LETF_HD constexpr int slot_list_type(int list, int s) {
       default: return -2;
     }
   }
-  if (list == 2) {
+  if (list == 2 || list == 3) {
     switch (s) {
       case 0: case 1: case 2: return LETF_ST_BENCHMARK;
       case 3: return LETF_ST_SMA;
@@ -120,6 +122,62 @@ LETF_HD constexpr uint32_t slot_list_mask(int list) {
 template <int LIST, typename F, int... S>
 LETF_HD void for_typed_slots(F& f, std::integer_sequence<int, S...>) {
   (f(S, std::integral_constant<int, slot_list_type(LIST, S)>{}, std::integral_constant<int, slot_list_asset(LIST, S)>{}), ...);
+}
+
+// ---- routed typed lists (host side): any subset of a typed list runs that list's rule kernel with the other slots switched off.
+// Every rule of the request goes to the slot that compiles its type, buy&hold strategies to the list's buy&hold slots or to
+// the free slots behind it (they cost the rule kernel nothing: the producer writes them).  slot_of[q] = slot of requested
+// strategy q; false = some strategy has no slot (a rule type twice, a rule on another asset, more strategies than slots).
+inline bool route_request(const LetfParams& s, int list, int ns, int* slot_of, bool* has_rules) {
+  const int nl = slot_list_count(list);
+  bool used[LETF_MAX_STRATEGIES] = {false};
+  *has_rules = false;
+  for (int q = 0; q < s.n_strategies; q++) {
+    const LetfStrategyParams& st = s.strategies[q];
+    const bool hold = st.type == LETF_ST_BENCHMARK || st.type == LETF_ST_BENCHMARK_TLT;
+    int slot = -1;
+    for (int j = 0; j < ns && j < LETF_MAX_STRATEGIES && slot < 0; j++) {
+      if (used[j]) continue;
+      const int ty = j < nl ? slot_list_type(list, j) : -2;
+      if (hold) { if (ty == LETF_ST_BENCHMARK || ty == -2) slot = j; continue; }
+      if (ty != st.type) continue;
+      const int as = slot_list_asset(list, j);
+      if (as >= 0 && st.asset != as) continue;
+      if (st.type == LETF_ST_COMPOSITE && st.asset2 != 4) continue;
+      slot = j;
+    }
+    if (slot < 0) return false;
+    used[slot] = true; slot_of[q] = slot;
+    if (!hold) *has_rules = true;
+  }
+  return true;
+}
+// the parameter block of a routed launch: the typed list's slots with the requested strategies in theirs (the others are
+// placeholders of the slot's type, switched off by route_slots), the list's series as the asset mask
+inline LetfParams routed_params(const LetfParams& s, int list, const int* slot_of, int n_slots, int mask) {
+  LetfParams r = s;
+  r.n_strategies = n_slots; r.asset_mask = mask;
+  const int nl = slot_list_count(list);
+  for (int j = 0; j < n_slots; j++) {
+    LetfStrategyParams& st = r.strategies[j];
+    memset(&st, 0, sizeof(st));
+    const int ty = j < nl ? slot_list_type(list, j) : -2;
+    st.type = ty >= 0 ? ty : LETF_ST_BENCHMARK;
+    const int as = j < nl ? slot_list_asset(list, j) : -1;
+    st.asset = as >= 0 ? as : 0; st.asset2 = 4;
+  }
+  for (int q = 0; q < s.n_strategies; q++) r.strategies[slot_of[q]] = s.strategies[q];
+  return r;
+}
+template <typename P>
+inline void route_slots(P& p, const LetfParams& s, const int* slot_of, int n_slots) {
+  for (int j = 0; j < n_slots; j++) p.strat[j].route = -1;
+  for (int q = 0; q < s.n_strategies; q++) p.strat[slot_of[q]].route = q + 1;
+}
+inline int routed_slot_count(const LetfParams& s, int list, const int* slot_of) {
+  int n = slot_list_count(list);
+  for (int q = 0; q < s.n_strategies; q++) if (slot_of[q] + 1 > n) n = slot_of[q] + 1;
+  return n;
 }
 
 // v[a] for a run-time asset index without forcing the array into local memory: a select chain
@@ -191,9 +249,11 @@ struct Trial {
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool FSER = MARKET == kMarketFSeries;
+  static constexpr bool ROUTED = LIST == 3;     // slots can be switched off / write another output row (DevStrategy::route)
   static constexpr bool SERIES = MARKET == kMarketSeries || FSER;
   static constexpr int NF = FSER ? __builtin_popcount((unsigned)AM & 0x3Fu) + 2 : 1;      // record fields: active returns, VIX, SPY price
-  static_assert(!FSER || (AM != 0 && LIST != 0 && !TAPEIO && !EXACT), "record mode: typed fp32 builds only");
+  static constexpr int kFSpy = __builtin_popcount((unsigned)AM & 0x0Fu);                 // record field of the SPY return (asset 4)
+  static_assert(!FSER || (AM != 0 && ((AM >> 4) & 1) && (LIST == 0 || (AM & 1)) && !TAPEIO && !EXACT), "record mode: fp32 builds with a compile-time asset mask that holds SPY (typed lists: signal asset TQQQ = field 0)");
   static constexpr bool JOURNAL = TAPEIO;   // journal counters only in the parity/tape build
   static constexpr bool KEYREF = NA < kAssets; // calling convention of the non-inlined sampler retry loop (letf_math.cuh)
   static constexpr bool HAS_VOL = (TM & kVolTypes) != 0;
@@ -836,6 +896,10 @@ struct Trial {
     // barrier is needed and the copies cost neither registers nor scoreboard stalls).  Loads are coalesced: one column
     // per thread, every thread of a warp on the same day.  Slot v of day d: smem[((d % kStage) * kNV + v) * blockDim + tid].
     constexpr int kNV = kRecValues<NF>();
+    // record field of the signal asset's return: the first one in the typed builds, else counted off the asset mask
+    int fsig = 0;
+    if (FSER && LIST == 0)
+      for (int a = 0; a < kAssets; a++) if (a < p.sig_asset && ((AM >> a) & 1)) fsig++;
     const int64_t rnc = ka.rec_ncol, rfs = (int64_t)T * ka.rec_ncol;
     // the record element behind value v of day `day` (nullptr: no such value yet, the window is still filling)
     auto rec_src = [&](int v, int day) -> const float* {
@@ -843,7 +907,7 @@ struct Trial {
       if (v < NF) return r0 + (int64_t)v * rfs;
       const int lag = v == NF ? 5 : v == NF + 1 ? 10 : v == NF + 2 ? 20 : v == NF + 3 ? 60 : v == NF + 4 ? 126 :
                       v == NF + 5 ? 100 : v == NF + 6 ? 200 : v == NF + 7 ? 14 : 15;
-      const int f = v <= NF + 3 ? 0 : (v == NF + 4 ? NF - 3 : NF - 1);      // signal return | SPY return | SPY price
+      const int f = v <= NF + 3 ? fsig : (v == NF + 4 ? kFSpy : NF - 1);      // signal return | SPY return | SPY price
       return day >= lag ? r0 + (int64_t)f * rfs - (int64_t)lag * rnc : nullptr;
     };
     const bool rec_used[kNV > NF ? kNV - NF : 1] = {HAS_V5, HAS_V10, HAS_V20 || HAS_DV20, HAS_V60 || HAS_SKEW || HAS_MEAN60, NEED_RINGS,
@@ -859,7 +923,7 @@ struct Trial {
       if (v < NF) return (int64_t)v * rfs;
       const int lag = v == NF ? 5 : v == NF + 1 ? 10 : v == NF + 2 ? 20 : v == NF + 3 ? 60 : v == NF + 4 ? 126 :
                       v == NF + 5 ? 100 : v == NF + 6 ? 200 : v == NF + 7 ? 14 : 15;
-      const int f = v <= NF + 3 ? 0 : (v == NF + 4 ? NF - 3 : NF - 1);
+      const int f = v <= NF + 3 ? fsig : (v == NF + 4 ? kFSpy : NF - 1);
       return (int64_t)f * rfs - (int64_t)lag * rnc;
     };
     auto rec_lag = [](int v) -> int {
@@ -1319,7 +1383,7 @@ struct Trial {
         if (STEADY && (i & (kRefresh - 1)) == kRefresh - 1) {
           auto hist = [&](int which, int back) -> R {          // value `back` days ago (0 = today) of series 0: signal return, 1: SPY return, 2: SPY price
             if (FSER) {
-              const int f = which == 0 ? 0 : (which == 1 ? NF - 3 : NF - 1);
+              const int f = which == 0 ? fsig : (which == 1 ? kFSpy : NF - 1);
               return (R)ka.rec[((int64_t)f * T + (i - back)) * ka.rec_ncol + col];
             }
             const int depth = which == 0 ? kRingA : (which == 1 ? kRingS : kRingP);
@@ -1365,6 +1429,7 @@ struct Trial {
         if (TYC == -2 || TYC == LETF_ST_BENCHMARK || TYC == LETF_ST_BENCHMARK_TLT) return;
         if (TYC < 0 && s >= p.n_strat) return;
         const DevStrategy<R>& st = p.strat[s];
+        if (ROUTED && st.route < 0) return;
         Slot& sl = slot[s];
         const int ty = TYC >= 0 ? TYC : st.type;
         const R r_asset = ASC >= 0 ? ret[ASC >= 0 ? ASC : 0] : pick6(ret, st.asset);     // return of the traded asset
@@ -1618,6 +1683,8 @@ struct Trial {
       if (s >= p.n_strat) continue;
       const int ty = p.strat[s].type;
       if (FSER && (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT)) continue;       // written by the producer
+      if (ROUTED && p.strat[s].route < 0) continue;
+      const int64_t row = ROUTED && p.strat[s].route > 0 ? p.strat[s].route - 1 : s;
       double fw = T > 0 ? slot[s].W : 0.0;
       double md = T > 1 ? slot[s].dd.value() : 0.0;
       if (ty == LETF_ST_BENCHMARK || ty == LETF_ST_BENCHMARK_TLT) {
@@ -1630,11 +1697,11 @@ struct Trial {
         fw = T > 0 ? (double)p.W0 * c : 0.0;
         md = T > 1 ? d.value() : 0.0;
       }
-      ka.out.final_wealth[(int64_t)s * N + col] = fw;
-      ka.out.max_dd[(int64_t)s * N + col] = md;
-      ka.out.num_trades[(int64_t)s * N + col] = slot[s].trades;
-      if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = JOURNAL ? sj[s].cnt : 0;
-      if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = JOURNAL ? sj[s].vol : 0.0;
+      ka.out.final_wealth[row * N + col] = fw;
+      ka.out.max_dd[row * N + col] = md;
+      ka.out.num_trades[row * N + col] = slot[s].trades;
+      if (ka.out.journal_count) ka.out.journal_count[row * N + col] = JOURNAL ? sj[s].cnt : 0;
+      if (ka.out.journal_volume) ka.out.journal_volume[row * N + col] = JOURNAL ? sj[s].vol : 0.0;
     }
 #if defined(__CUDA_ARCH__)
     if (FSER) cp_async_wait<0>();              // nothing of this trial's staging may still be in flight when the next one starts

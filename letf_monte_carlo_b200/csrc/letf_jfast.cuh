@@ -98,6 +98,11 @@ struct JointPair {
   typedef float R;
   typedef Mth<float> M;
   static_assert(NACT >= 1 && NACT <= NA, "active slots");
+  static_assert(NA < kAssets || NACT == kAssets, "uncompacted build: slot j is asset j");
+  // uncompacted build (NA == 6, the producer of the generic split pipeline): slot j is asset j, series outside the asset mask
+  // are skipped at run time (their record fields are written as zeros); SPY sits in slot 4, otherwise in the last active slot
+  static constexpr bool ALLSLOTS = NA == kAssets;
+  static constexpr int kSpySlot = ALLSLOTS ? 4 : NACT - 1;
   // K10 bit 7: tracking-error dof and tanh cap read at run time (calibrated tracking_residual_model, engine.py:185, :198-203)
   static constexpr bool TEDF = (K10 & 0x80) != 0;
 
@@ -282,6 +287,7 @@ struct JointPair {
     for (int a = 0; a < NACT; a++) streams[1 + a] = STREAM_TE0 + (uint32_t)p.act_id[a];
     const float ema = (float)(2.0 / 127.0);
     const bool want_tlt = p.bench_tlt != 0;
+    const uint32_t amask = ALLSLOTS ? (uint32_t)p.asset_mask : ~0u;      // (compacted builds: every slot is live)
 
     const int64_t ecol = (pj - (ka.first_trial >> 1)) * 2;      // EMIT: this pair's first column (the chunk starts on an even trial)
     JF8 vnext;
@@ -324,6 +330,7 @@ struct JointPair {
       float innov[NACT];
 #pragma unroll
       for (int a = 0; a < NACT; a++) {
+        if (ALLSLOTS && !((amask >> a) & 1)) { innov[a] = 0.0f; continue; }
         if (TEDF) innov[a] = student_t_block<R, false>(w[1 + a], p.act[a].te_df, p.act[a].te_fast_k, key, (uint32_t)g, streams[1 + a]);
         else innov[a] = ((K10 >> a) & 1) ? student_t10<R>(w[1 + a]) : student_t5<R>(w[1 + a]);
       }
@@ -365,6 +372,7 @@ struct JointPair {
         const float vrlive = i >= 1 ? vmult * c.rmult : 0.0f;      // no tracking error on day 0 (engine.py:184)
 #pragma unroll
         for (int a = 0; a < NACT; a++) {
+          if (ALLSLOTS && !((amask >> a) & 1)) { if (EMIT) e_ret[t][a] = 0.0f; continue; }
           const DevAsset<R>& ap = p.act[a];
           const float un = fmaf(ap.w_spy, spy, fmaf(ap.w_qqq, qqq, ap.w_tlt * tlt));
           const float lev = ap.lev * un - fmaf(ap.bl_252, carry, ap.er_daily);
@@ -387,7 +395,7 @@ struct JointPair {
           tm[t] = fminf(tm[t], tq[t]);
         }
       }
-      if (EMIT) {
+      if (EMIT && ka.rec) {
         struct alignas(8) F2 { float a, b; };
         const int64_t ncol = ka.rec_ncol;
         F2* const base = (F2*)(ka.rec + (int64_t)i * ncol + ecol);
@@ -395,7 +403,7 @@ struct JointPair {
 #pragma unroll
         for (int a = 0; a < NACT; a++) { F2 v; v.a = e_ret[0][a]; v.b = e_ret[1][a]; base[(int64_t)a * fstride] = v; }
         { F2 v; v.a = u2f_(f2u_(vix[0]) | ((uint32_t)reg << 31)); v.b = u2f_(f2u_(vix[1]) | ((uint32_t)reg << 31)); base[(int64_t)NACT * fstride] = v; }
-        { F2 v; v.a = (float)(cp[0][NACT - 1] * 100.0); v.b = (float)(cp[1][NACT - 1] * 100.0); base[(int64_t)(NACT + 1) * fstride] = v; }
+        { F2 v; v.a = (float)(cp[0][kSpySlot] * 100.0); v.b = (float)(cp[1][kSpySlot] * 100.0); base[(int64_t)(NACT + 1) * fstride] = v; }
       }
     }
 
@@ -411,12 +419,14 @@ struct JointPair {
       if (!isfinite_(shift[t][0]) || !isfinite_(shift[t][1]) || !isfinite_(shift[t][2])) flags |= LETF_FLAG_NONFINITE_RET;
       if (T > 0 && (!(vmin[t] > 0.0f) || !isfinite_(vmax[t]))) flags |= LETF_FLAG_BAD_VIX;
 #pragma unroll
-      for (int a = 0; a < NACT; a++) if (T > 0 && !(cp[t][a] > 0.0 && isfinite_(cp[t][a]))) bad = true;
+      for (int a = 0; a < NACT; a++) if (T > 0 && ((amask >> a) & 1) && !(cp[t][a] > 0.0 && isfinite_(cp[t][a]))) bad = true;
       if (want_tlt && T > 0 && !(cp_tlt[t] > 0.0 && isfinite_(cp_tlt[t]))) bad = true;
       if (T == 0 || bad || !(vmin[t] >= 5.0f) || !(vmax[t] <= 120.0f)) flags |= LETF_FLAG_REPAIRED;
       for (int s = 0; s < NS; s++) {
         if (s >= p.n_strat) break;
         if (EMIT && p.strat[s].type != LETF_ST_BENCHMARK && p.strat[s].type != LETF_ST_BENCHMARK_TLT) continue;
+        if (EMIT && p.strat[s].route < 0) continue;                       // routed rule-kernel builds (DevStrategy::route)
+        const int64_t row = EMIT && p.strat[s].route > 0 ? p.strat[s].route - 1 : s;
         double c = 1.0; float qm = tm[t];
         if (p.strat[s].type == LETF_ST_BENCHMARK_TLT) c = cp_tlt[t];
         else {
@@ -424,11 +434,11 @@ struct JointPair {
 #pragma unroll
           for (int a = 0; a < NACT; a++) if (p.act_id[a] == p.strat[s].asset) { c = cp[t][a]; qm = ddm[t][a]; }
         }
-        ka.out.final_wealth[(int64_t)s * N + col] = T > 0 ? (double)p.W0 * c : 0.0;
-        ka.out.max_dd[(int64_t)s * N + col] = T > 1 ? 1.0 - (double)qm : 0.0;
-        ka.out.num_trades[(int64_t)s * N + col] = 0;
-        if (ka.out.journal_count) ka.out.journal_count[(int64_t)s * N + col] = 0;
-        if (ka.out.journal_volume) ka.out.journal_volume[(int64_t)s * N + col] = 0.0;
+        ka.out.final_wealth[row * N + col] = T > 0 ? (double)p.W0 * c : 0.0;
+        ka.out.max_dd[row * N + col] = T > 1 ? 1.0 - (double)qm : 0.0;
+        ka.out.num_trades[row * N + col] = 0;
+        if (ka.out.journal_count) ka.out.journal_count[row * N + col] = 0;
+        if (ka.out.journal_volume) ka.out.journal_volume[row * N + col] = 0.0;
       }
       if (ka.out.start_offset) ka.out.start_offset[col] = so;
       if (ka.out.flags) ka.out.flags[col] = flags;

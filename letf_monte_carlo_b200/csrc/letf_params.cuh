@@ -64,7 +64,8 @@ template <typename R> struct DevBoot {
 };
 
 template <typename R> struct DevStrategy {
-  int type, asset, asset2, taxable, port, pad;
+  int type, asset, asset2, taxable, port;
+  int route;      // output row of this slot: 0 = its own index, k > 0 = row k - 1, < 0 = slot switched off (routed typed builds, letf_api.cu)
   R w[kAssets];
   R p[LETF_STRAT_NPARAM];
 };

@@ -1,5 +1,5 @@
 """Where the end-to-end time of parallel_monte_carlo_fixed(..., summary_only=True).table() goes (tuning aid, GPU box).
-usage: python scripts/e2e_breakdown.py [c2|c3]"""
+usage: python scripts/e2e_breakdown.py [workload] [trials]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,11 +9,15 @@ from letf_monte_carlo_b200.params import build_params
 
 w = sys.argv[1] if len(sys.argv) > 1 else "c3"
 ns, model, sids, params, keep = bench.build_workload(w)
-n = bench.WORKLOADS[w]["trials"]; years = bench.WORKLOADS[w]["years"]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else bench.WORKLOADS[w]["trials"]; years = bench.WORKLOADS[w]["years"]
 ns.NUM_SIMULATIONS = n
 call = lambda: mc_runner.parallel_monte_carlo_fixed(sids, years, model, {}, cfg=ns, verbose=False, summary_only=True).table()
 for _ in range(3):
     call()
+each = []
+for _ in range(8):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); call(); torch.cuda.synchronize(); each.append((time.perf_counter() - t0) * 1e3)
+print("calls (ms):", " ".join(f"{x:.1f}" for x in each))
 def t(f, k=5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(k): r = f()

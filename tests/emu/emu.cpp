@@ -209,16 +209,32 @@ extern "C" int letf_emu_run_typed(const LetfParams* sp, int list, const LetfOutp
 
 // split strategy pipeline (letf_api.cu launch_split): the pair producer writes per-day records, the typed rule kernel body
 // (Trial::run in record mode) consumes them; Philox only, fp32
-template <int NS, int LIST, int AM, int NACT, int K10>
+template <int NS, int LIST, int AM, int NACT, int K10, int NAP = 4>
 static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
-  if (sp->n_strategies != slot_list_count(LIST) || sp->asset_mask != AM || sp->market_mode != LETF_MARKET_JOINT_T || (first & 1)) return -2;
-  for (int s = 0; s < sp->n_strategies; s++) if (sp->strategies[s].type != slot_list_type(LIST, s)) return -3;
-  static KArgs<float, 32, 4> kp;
+  if (sp->market_mode != LETF_MARKET_JOINT_T || (first & 1)) return -2;
+  // routed list (letf_api.cu find_routed_split): the request is a subset of the typed list
+  static LetfParams routed;
+  int slot_of[LETF_MAX_STRATEGIES], n_slots = 0;
+  const LetfParams* req = sp;
+  if (LIST == 3) {
+    bool rules = false;
+    if ((sp->asset_mask & 0x3F) & ~AM) return -2;
+    if (!route_request(*sp, LIST, NS, slot_of, &rules)) return -3;
+    n_slots = routed_slot_count(*sp, LIST, slot_of);
+    routed = routed_params(*sp, LIST, slot_of, n_slots, AM);
+    sp = &routed;
+  } else if (LIST != 0) {
+    if (sp->n_strategies != slot_list_count(LIST) || sp->asset_mask != AM) return -2;
+    for (int s = 0; s < sp->n_strategies; s++) if (sp->strategies[s].type != slot_list_type(LIST, s)) return -3;
+  }
+  constexpr uint32_t TMC = LIST != 0 ? slot_list_mask(LIST) : ((1u << LETF_ST__COUNT) - 1u);   // letf_kernels.cuh TM_ALL
+  static KArgs<float, 32, NAP> kp;
   static KArgs<float, NS, kAssets> kc;
   memset(&kp, 0, sizeof(kp)); memset(&kc, 0, sizeof(kc));
   const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
-  convert_params<float, 32, 4>(*sp, dd, kp.p);
+  convert_params<float, 32, NAP>(*sp, dd, kp.p);
   convert_params<float, NS, kAssets>(*sp, dd, kc.p);
+  if (LIST == 3) { route_slots(kp.p, *req, slot_of, n_slots); route_slots(kc.p, *req, slot_of, n_slots); }
   const int T = sp->sim_days, G = T + sp->buffer_days, NF = NACT + 2;
   const int64_t cap = (n + 1) & ~(int64_t)1;
   std::vector<float> rec((size_t)cap * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
@@ -226,13 +242,13 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   kp.out = *out; kp.seed = seed; kp.first_trial = first; kp.n_trials = n; kp.rng_mode = LETF_RNG_PHILOX; kp.nthreads = 1;
   std::vector<uint32_t> spells((size_t)G + 2);
   kp.xscr = xscr; kp.rec = rec.data(); kp.rec_ncol = cap; kp.log_trial = -1; kp.spell_scr = spells.data();
-  for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<32, 4, NACT, K10, true>::run(kp, pj, 0);
+  for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<32, NAP, NACT, K10, true>::run(kp, pj, 0);
   kc.out = *out; kc.seed = seed; kc.first_trial = first; kc.n_trials = n; kc.rng_mode = LETF_RNG_PHILOX; kc.nthreads = 1;
   kc.rec = rec.data(); kc.rec_ncol = cap; kc.log_trial = -1;
   kc.p.T = T; kc.p.buffer = 0; kc.p.random_start = 0; kc.series.sim_days = T; kc.series.n_paths = n;
   kc.ringP = rp.data(); kc.ringS = rs.data(); kc.ringA = ra.data();
   for (int64_t j = 0; j < n; j++) {
-    Trial<float, NS, kAssets, kMarketFSeries, false, slot_list_mask(LIST), LIST, AM> t(kc, first + j, j, 0);
+    Trial<float, NS, kAssets, kMarketFSeries, false, TMC, LIST, AM> t(kc, first + j, j, 0);
     t.run();
   }
   free(xscr);
@@ -245,6 +261,17 @@ extern "C" int letf_emu_run_split(const LetfParams* sp, int list, const LetfOutp
     if (((sp->asset_mask >> a) & 1) && ((df_fast_k(sp->assets[a].te_df) != 5 && df_fast_k(sp->assets[a].te_df) != 10) || sp->assets[a].te_clip > 0.0)) tedf = true;
   if (list == 1) return tedf ? run_split<8, 1, 25, 3, 0x80>(sp, out, seed, first, n) : run_split<8, 1, 25, 3, 4>(sp, out, seed, first, n);
   if (list == 2) return tedf ? run_split<32, 2, 29, 4, 0x80>(sp, out, seed, first, n) : run_split<32, 2, 29, 4, 8>(sp, out, seed, first, n);
+  if (list == 3) {      // routed: a subset of the default sweep on the 19-rule kernel with the other slots switched off
+    tedf = false;
+    for (int a = 0; a < kAssets; a++)
+      if (((29 >> a) & 1) && ((df_fast_k(sp->assets[a].te_df) != 5 && df_fast_k(sp->assets[a].te_df) != 10) || sp->assets[a].te_clip > 0.0)) tedf = true;
+    return tedf ? run_split<32, 3, 29, 4, 0x80>(sp, out, seed, first, n) : run_split<32, 3, 29, 4, 8>(sp, out, seed, first, n);
+  }
+  if (list == 0) {      // generic pipeline: uncompacted producer (default dof pattern or run-time sampler), dynamic-slot rule kernel
+    for (int a = 0; a < kAssets; a++)
+      if (((sp->asset_mask >> a) & 1) && df_fast_k(sp->assets[a].te_df) != (a >= 4 ? 10 : 5)) tedf = true;
+    return tedf ? run_split<32, 0, 0x3F, 6, 0x80, 6>(sp, out, seed, first, n) : run_split<32, 0, 0x3F, 6, 0x30, 6>(sp, out, seed, first, n);
+  }
   return -4;
 }
 

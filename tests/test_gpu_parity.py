@@ -931,3 +931,54 @@ def test_pair_kernels_with_calibrated_models(sids, kname, engine_lib, monkeypatc
     assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
     np.testing.assert_array_equal(fast.regime_days, o.regime_days)
     np.testing.assert_array_equal(fast.jump_days, o.jump_days)
+
+
+@pytest.mark.parametrize("sids,model,kname", [
+    (["S1", "S4", "S7", "S10", "S15"], "default", "prod_sweep19+rules_sub19"),
+    (["S19", "S2", "S8", "S6"], "default", "prod_sweep19+rules_sub19"),
+    (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], "default", "prod_sweep19+rules_sub19"),
+    (["S5", "S9", "S17"], "vix_te", "prod_sweep19_tedf+rules_sub19"),
+    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], "default", "prod_all+rules_all"),
+    (["S1", "S3", "S2", "B_UPRO", "B_TMF"], "default", "prod_all"),
+    (["S4", "S6", "S12", "S18", "B_QQQ"], "vix_te", "prod_all_tedf+rules_all"),
+], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "six_series", "buy_hold_five_series",
+        "generic_calibrated_te"])
+def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_lib, monkeypatch):
+    """strategy lists without a typed build.  A subset of the default sweep runs the 19-rule kernel with the other slots
+    switched off and its outputs routed (slot list 3); anything else the generic split pipeline (uncompacted pair producer ->
+    six-field records -> dynamic-slot rule kernel; producer alone for a buy&hold-only list).  Both against the fused generic
+    build on the same Philox counters and against the oracle on the recorded tape."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model(model), ns)
+    n_t = 160
+    rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+    with _engine(params, keep, "f32") as eng:
+        fast = eng.run_host(2 * n_t, seed=77)
+        info = eng.launch_info()
+        assert info["kernel"].endswith(kname), info["kernel"]
+        eng.run_host(2 * n_t, seed=77, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+        odd = eng.run_host(2 * n_t - 3, seed=77)
+    monkeypatch.setenv("LETF_NO_GENERIC_SPLIT", "1")
+    with _engine(params, keep, "f32") as eng:
+        slow = eng.run_host(2 * n_t, seed=77)
+        assert "prod_" not in eng.launch_info()["kernel"]
+    if "sub19" in kname:        # the generic pipeline serves the same request when the routed one is switched off
+        monkeypatch.delenv("LETF_NO_GENERIC_SPLIT")
+        monkeypatch.setenv("LETF_NO_ROUTED_SPLIT", "1")
+        with _engine(params, keep, "f32") as eng:
+            gen = eng.run_host(2 * n_t, seed=77)
+            assert "rules_all" in eng.launch_info()["kernel"]
+        np.testing.assert_allclose(fast.final_wealth, gen.final_wealth, rtol=2e-3)
+        np.testing.assert_array_equal(fast.flags, gen.flags)
+    o = orc.run(params, rec)
+    np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-3)
+    assert np.median(np.abs(fast.final_wealth / slow.final_wealth - 1)) < 5e-6
+    np.testing.assert_allclose(fast.max_dd, slow.max_dd, atol=1e-4)
+    assert np.mean(fast.num_trades != slow.num_trades) < 0.02
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(fast, k), getattr(slow, k))
+    np.testing.assert_array_equal(odd.final_wealth, fast.final_wealth[:, :2 * n_t - 3])
+    rel = np.abs(fast.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
+    assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
+    np.testing.assert_array_equal(fast.regime_days, o.regime_days)
+    np.testing.assert_array_equal(fast.jump_days, o.jump_days)

@@ -366,6 +366,58 @@ def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
     np.testing.assert_array_equal(part.num_trades, split.num_trades[:, :7])
 
 
+@pytest.mark.parametrize("sids,extra,model,years", [
+    (["S1", "S4", "S7", "S10", "S15"], False, "default", 2),              # a subset of the rules, no typed list for it
+    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], True, "default", 2),     # all six series incl. QQQ
+    (["S1", "S3", "S2", "B_UPRO", "B_TMF"], True, "default", 1),          # buy&hold only, more series than the pair kernels carry
+    (["S4", "S6", "S12", "S18"], False, "vix_te", 1),                      # calibrated tracking-error model: run-time sampler
+])
+def test_generic_split_pipeline_matches_fused_generic_build(sids, extra, model, years):
+    """Strategy lists without a typed build run the generic split pipeline: the uncompacted pair producer (slot = asset,
+    series outside the mask skipped and written as zeros) -> six-field records -> the dynamic-slot rule kernel body.
+    Same Philox counters as the fused generic build: market state identical, wealth to fp32 reassociation."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS) if extra else synthetic.config_namespace()
+    params, keep = build_params(sids, years, synthetic.fallback_regime_model(model), ns)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    split = emu.run_split(params, 0, 24, seed=8)
+    fused = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=8, n=24)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
+    assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 5e-6
+    np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
+    assert np.mean(split.num_trades != fused.num_trades) < 0.02
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+    part = emu.run_split(params, 0, 5, seed=8)
+    np.testing.assert_array_equal(part.final_wealth, split.final_wealth[:, :5])
+
+
+@pytest.mark.parametrize("sids,extra,model", [
+    (["S1", "S4", "S7", "S10", "S15"], False, "default"),
+    (["S19", "S2", "S8", "S6"], False, "default"),                               # out of list order; S8 reads SPY
+    (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], True, "default"),             # more buy&hold strategies than the list's three slots
+    (["S5", "S9", "S17"], False, "vix_te"),
+])
+def test_routed_split_pipeline_matches_fused_generic_build(sids, extra, model):
+    """Any subset of the default sweep runs the 19-rule kernel with the other slots switched off and the outputs routed to
+    the request's rows (slot list 3); the producer simulates the list's four series.  Against the fused generic build on
+    the same Philox counters."""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS) if extra else synthetic.config_namespace()
+    params, keep = build_params(sids, 2, synthetic.fallback_regime_model(model), ns)
+    dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
+    split = emu.run_split(params, 3, 24, seed=8)
+    fused = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=8, n=24)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
+    assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 5e-6
+    np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
+    assert np.mean(split.num_trades != fused.num_trades) < 0.02
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+    # a request the list cannot hold: the same rule type twice / a rule on a series outside the list
+    two_sma, _ = build_params(["S4", "S4"], 1, synthetic.fallback_regime_model("default"), ns)
+    with pytest.raises(RuntimeError):
+        emu.run_split(two_sma, 3, 2, seed=1)
+
+
 @pytest.mark.parametrize("days,random_start", [(2, True), (5, False), (61, True), (257, False), (300, True)])
 def test_pair_and_split_paths_at_edge_horizons(days, random_start):
     """horizons around the staging depth (3 days ahead), the window lengths and the steady-state switch of the day body
