@@ -630,13 +630,14 @@ def run_series(args):
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "paths": n, "sim_days": T, "strategies": sids,
                        "l2": f"256 MiB memset between steps; inputs ({bytes_launch / 1e9:.1f} GB) exceed L2",
-                       "kernel": {"grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"]}},
+                       "kernel": {"name": info["kernel"], "grid": info["grid"], "block": info["block"], "regs": info["regs_per_thread"],
+                                  "launches_per_step": int(info["kernel_launches"])}},
             "clocks": clocks,
             "e2e": {"value": n * T / e2e_s, "unit": UNIT, "h2d_bytes_per_step": bytes_launch, "d2h_bytes_per_step": n * len(sids) * 20,
                     "api": "PathEngine.run_strategies with pinned host series", "mean_final_wealth": float(np.mean(fw[0]))},
-            "gpu_launches": args.steps + 1,
+            "gpu_launches": (args.steps + 1) * max(1, int(info["kernel_launches"])),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": None, "kernel": "letf_path_kernel<series>", "kernel_ms": kern_ms,
+                         "traffic": None, "kernel": info["kernel"] or "letf_path_kernel<series>", "kernel_ms": kern_ms,
                          "bytes_per_path_day": wl["bytes_per_path_day"], "units_per_launch": n * T,
                          "peak_def": f"measured copy bandwidth ({pk['source']})"}}
     eng.close()

@@ -20,6 +20,7 @@
 #include <vector>
 #include <chrono>
 #include "letf_kernels.cuh"
+#include "letf_series_prep.cuh"
 
 namespace letf {
 
@@ -36,6 +37,7 @@ cudaError_t launch_reduce(const LetfOutputs& out, const LetfSummary& sm, int64_t
                           double years, int sm_count, cudaStream_t st);
 cudaError_t launch_summary_reset(const LetfSummary& sm, int n_strat, cudaStream_t st);
 cudaError_t launch_summary_combine(const void* gathered, int world, int n_strat, void* dst, cudaStream_t st);
+cudaError_t launch_series_records(const SeriesPrepArgs& a, cudaStream_t st);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -108,6 +110,7 @@ struct LetfEngine {
   bool no_routed_split = false;              // LETF_NO_ROUTED_SPLIT=1: subsets of the default sweep skip the routed 19-rule kernel
   DevBuf rec;                                // per-day records of the split strategy pipeline
   int64_t split_key = 0; int split_waves = 0; // its chunk size in producer waves, remembered per shape (launch_split)
+  int64_t series_key = 0, series_cap = 0;    // same for the materialised-path mode (launch_series_split), in paths
   DevBuf spell;                              // regime spells of the pair kernels
   // legacy_hybrid bootstrap tables on the device, in the engine's precision (letf_params.cuh build_boot_tables)
   void* boot_blob = nullptr;
@@ -501,6 +504,112 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
   return LETF_OK;
 }
 
+// Materialised-path mode through the split pipeline (letf_series_prep.cuh): a bandwidth-bound record pass over the caller's
+// series (it also writes the buy&hold strategies, flags and regime day counts), then the rule kernel the strategy list would
+// get on simulated paths - typed, routed or generic.  Not taken: fp64, journal / curve / trade-list plumbing, a frame with its
+// own Cash_Ret column (the rule kernels read the regime's cash rate), LETF_NO_SPLIT=1.
+static bool find_series_split(const LetfEngine* e, const LetfSeries* series, bool need_io, SplitPlan* plan) {
+  const LetfParams& s = e->params;
+  *plan = SplitPlan();
+  if (e->precision != LETF_PREC_F32 || need_io || e->no_split || series->cash_ret || series->sim_days < 1) return false;
+  const int mask = s.asset_mask & 0x3F;
+  bool rules = false;
+  for (int k = 0; k < s.n_strategies; k++)
+    if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) rules = true;
+  // 1: exactly a typed list; 2: a subset of the default sweep (routed); 3: dynamic slots
+  for (int tier = 1; tier <= 3 && !plan->cons; tier++) {
+    for (int i = 0; i < kernel_count() && !plan->cons; i++) {
+      const KernelEntry* k = kernel_at(i);
+      if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || k->ns < s.n_strategies) continue;
+      if (tier == 1 && k->list && k->list != 3 && (k->am & 0x3F) == mask && list_matches(k, e)) { plan->cons = k; plan->mask = mask; }
+      if (tier == 2 && k->list == 3 && !(mask & ~(k->am & 0x3F)) && !e->no_routed_split) {
+        bool r2 = false;
+        if (!route_request(s, k->list, k->ns, plan->slot_of, &r2)) continue;
+        plan->cons = k; plan->mask = k->am & 0x3F; plan->routed = true;
+        plan->n_slots = routed_slot_count(s, k->list, plan->slot_of);
+      }
+      if (tier == 3 && !k->list && (k->am & 0x3F) == 0x3F && !(e->type_mask & ~k->tm) && !e->no_generic_split) { plan->cons = k; plan->mask = 0x3F; }
+    }
+  }
+  plan->rules = rules;
+  plan->nact = __builtin_popcount((unsigned)plan->mask);
+  return plan->cons != nullptr;
+}
+
+template <int NSC>
+static int launch_series_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, const LetfSeries* series, const LetfOutputs* out) {
+  const KernelEntry* kc = plan.cons;
+  cudaFuncAttributes fac;
+  int mbc = 0;
+  CK(kc->attrs(&fac, &mbc));
+  if (mbc < 1) return fail(LETF_ERR_CUDA, "rule kernel cannot be resident on this device");
+  static thread_local KArgs<float, NSC, kAssets> ka_c;
+  static thread_local SeriesPrepArgs pa;
+  memset(&ka_c, 0, sizeof(ka_c)); memset(&pa, 0, sizeof(pa));
+  if (plan.routed) {
+    static thread_local LetfParams rp;
+    rp = routed_params(e->params, kc->list, plan.slot_of, plan.n_slots, plan.mask);
+    convert_params<float, NSC, kAssets>(rp, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
+    route_slots(ka_c.p, e->params, plan.slot_of, plan.n_slots);
+  } else {
+    convert_params<float, NSC, kAssets>(e->params, e->dev_dur, ka_c.p, (const DevBoot<float>*)(const void*)&e->boot32);
+  }
+  const int T = series->sim_days, NF = plan.rules ? plan.nact + 2 : 0;
+  const int64_t n = series->n_paths;
+  // chunk of paths: as many as fit in 60 % of the free device memory (decided once per shape, see launch_split)
+  const int64_t shape_key = ((int64_t)T << 32) ^ ((int64_t)NF << 24) ^ 1;
+  int64_t cap = e->series_cap;
+  if (e->series_key != shape_key || cap < 1) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double per_path = (double)T * NF * 4;
+    cap = per_path > 0 ? (int64_t)(0.6 * ((double)free_b + (double)e->rec.cap) / per_path) & ~(int64_t)127 : n;
+    if (cap < 128) return fail(LETF_ERR_NOMEM, "materialised-path mode: the per-day records of 128 paths do not fit in device memory");
+    e->series_key = shape_key; e->series_cap = cap;
+  }
+  if (cap > n) cap = n;
+  {
+    cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
+    if (ce != cudaSuccess) { cudaGetLastError(); e->series_key = 0; return fail(LETF_ERR_NOMEM, "materialised-path records: " + std::string(cudaGetErrorString(ce))); }
+  }
+  pa.series = *series; pa.rec = NF ? (float*)e->rec.p : nullptr; pa.rec_ncol = cap; pa.T = T;
+  pa.field_mask = plan.mask; pa.asset_mask = ka_c.p.asset_mask; pa.bench_mask = ka_c.p.bench_mask; pa.bench_tlt = ka_c.p.bench_tlt;
+  pa.n_strat = ka_c.p.n_strat; pa.W0 = (double)ka_c.p.W0;
+  for (int q = 0; q < ka_c.p.n_strat && q < LETF_MAX_STRATEGIES; q++) {
+    pa.type[q] = ka_c.p.strat[q].type; pa.asset[q] = ka_c.p.strat[q].asset; pa.route[q] = ka_c.p.strat[q].route;
+  }
+  ka_c.rng_mode = LETF_RNG_PHILOX; ka_c.rec = (float*)e->rec.p; ka_c.rec_ncol = cap; ka_c.log_trial = -1;
+  ka_c.p.T = T; ka_c.p.buffer = 0; ka_c.p.random_start = 0; ka_c.series.sim_days = T;
+  size_t scratch = (size_t)cap * T * NF * 4;
+  int launches = 0;
+  int64_t grid_last = 0;
+  CK(cudaEventRecord(e->ev0, st));
+  for (int64_t c0 = 0; c0 < n; c0 += cap) {
+    const int64_t nc = n - c0 < cap ? n - c0 : cap;
+    const LetfOutputs oc = out_columns(*out, c0);
+    pa.out = oc; pa.col0 = c0; pa.n = nc;
+    CK(launch_series_records(pa, st));
+    launches++;
+    if (!plan.rules) continue;
+    const int64_t grid_c = full_wave_grid(nc, e->sm_count, mbc, kc->block);
+    const int64_t nth = grid_c * kc->block;
+    if ((int64_t)kRingP * nth >= ((int64_t)1 << 32)) return fail(LETF_ERR_INVALID, "grid too large for 32-bit ring offsets");
+    ka_c.out = oc; ka_c.first_trial = c0; ka_c.n_trials = nc; ka_c.nthreads = nth; ka_c.series.n_paths = nc;
+    if (kc->tm & kNeedRingP) { size_t b = (size_t)kRingP * nth * 4; CK(e->ringP.reserve(b)); ka_c.ringP = (float*)e->ringP.p; if (c0 == 0) scratch += b; }
+    if (kc->tm & kNeedRingS) { size_t b = (size_t)kRingS * nth * 4; CK(e->ringS.reserve(b)); ka_c.ringS = (float*)e->ringS.p; if (c0 == 0) scratch += b; }
+    if (kc->tm & kVolTypes) { size_t b = (size_t)kRingA * nth * 4; CK(e->ringA.reserve(b)); ka_c.ringA = (float*)e->ringA.p; if (c0 == 0) scratch += b; }
+    CK(kc->launch(&ka_c, (int)grid_c, st));
+    launches++; grid_last = grid_c;
+  }
+  CK(cudaEventRecord(e->ev1, st));
+  e->timed = true;
+  e->info.grid = (int)grid_last; e->info.block = kc->block; e->info.regs_per_thread = fac.numRegs;
+  e->info.kernel_launches = launches; e->info.scratch_bytes = (int64_t)scratch; e->info.sm_count = e->sm_count;
+  if (plan.rules) snprintf(e->info.kernel, sizeof(e->info.kernel), "series_records+%s", kc->name + 4);
+  else snprintf(e->info.kernel, sizeof(e->info.kernel), "series_records");
+  return LETF_OK;
+}
+
 static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed, int64_t first, int64_t n,
                       int rng_mode, const LetfTape* tape, const LetfOutputs* out, const LetfSeries* series,
                       const LogArgs& lg) {
@@ -542,6 +651,14 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
       CK(cudaSetDevice(e->device));
       if (plan.cons->ns == 8) return launch_split<8, 4>(e, plan, st, seed, first, n, out);
       if (plan.cons->ns == 32) return launch_split<32, 4>(e, plan, st, seed, first, n, out);
+    }
+  }
+  if (market == kMarketSeries && series && !(e->pin_kernel.size() && e->pin_kernel.find("_rules_") == std::string::npos)) {
+    SplitPlan plan;
+    if (find_series_split(e, series, need_io, &plan)) {
+      CK(cudaSetDevice(e->device));
+      if (plan.cons->ns == 8) return launch_series_split<8>(e, plan, st, series, out);
+      if (plan.cons->ns == 32) return launch_series_split<32>(e, plan, st, series, out);
     }
   }
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);

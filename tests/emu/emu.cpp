@@ -10,6 +10,7 @@
 #include "../../letf_monte_carlo_b200/csrc/letf_core.cuh"
 #include "../../letf_monte_carlo_b200/csrc/letf_fast.cuh"
 #include "../../letf_monte_carlo_b200/csrc/letf_jfast.cuh"
+#include "../../letf_monte_carlo_b200/csrc/letf_series_prep.cuh"
 
 using namespace letf;
 
@@ -311,6 +312,58 @@ extern "C" int letf_emu_run_series(const LetfParams* sp, int precision, int type
   if (precision == LETF_PREC_F64) GO(double, LETF_MAX_STRATEGIES, true, 0xFFFFFFFFu, 0);
   GO(float, LETF_MAX_STRATEGIES, true, 0xFFFFFFFFu, 0);
 #undef GO
+}
+
+// materialised-path mode through the split pipeline (letf_api.cu launch_series_split): record pass over the series, then the
+// rule kernel body in record mode.  list: 1 / 2 typed, 3 routed, 0 dynamic slots
+template <int NS, int LIST, int AM>
+static int run_series_split(const LetfParams* sp, const LetfSeries* series, const LetfOutputs* out) {
+  static LetfParams routed;
+  int slot_of[LETF_MAX_STRATEGIES], n_slots = 0;
+  const LetfParams* req = sp;
+  if (LIST == 3) {
+    bool rules = false;
+    if ((sp->asset_mask & 0x3F) & ~AM) return -2;
+    if (!route_request(*sp, LIST, NS, slot_of, &rules)) return -3;
+    n_slots = routed_slot_count(*sp, LIST, slot_of);
+    routed = routed_params(*sp, LIST, slot_of, n_slots, AM);
+    sp = &routed;
+  } else if (LIST != 0) {
+    if (sp->n_strategies != slot_list_count(LIST) || sp->asset_mask != AM) return -2;
+    for (int s = 0; s < sp->n_strategies; s++) if (sp->strategies[s].type != slot_list_type(LIST, s)) return -3;
+  }
+  constexpr uint32_t TMC = LIST != 0 ? slot_list_mask(LIST) : ((1u << LETF_ST__COUNT) - 1u);
+  static KArgs<float, NS, kAssets> kc;
+  static SeriesPrepArgs pa;
+  memset(&kc, 0, sizeof(kc)); memset(&pa, 0, sizeof(pa));
+  const int32_t* dd[2] = {nullptr, nullptr};
+  convert_params<float, NS, kAssets>(*sp, dd, kc.p);
+  if (LIST == 3) route_slots(kc.p, *req, slot_of, n_slots);
+  const int T = series->sim_days, NF = __builtin_popcount((unsigned)AM & 0x3Fu) + 2;
+  const int64_t n = series->n_paths;
+  std::vector<float> rec((size_t)n * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
+  pa.series = *series; pa.out = *out; pa.rec = rec.data(); pa.rec_ncol = n; pa.col0 = 0; pa.n = n; pa.T = T;
+  pa.field_mask = AM & 0x3F; pa.asset_mask = kc.p.asset_mask; pa.bench_mask = kc.p.bench_mask; pa.bench_tlt = kc.p.bench_tlt;
+  pa.n_strat = kc.p.n_strat; pa.W0 = (double)kc.p.W0;
+  for (int q = 0; q < kc.p.n_strat; q++) { pa.type[q] = kc.p.strat[q].type; pa.asset[q] = kc.p.strat[q].asset; pa.route[q] = kc.p.strat[q].route; }
+  for (int64_t j = 0; j < n; j++) series_prep_path(pa, j);
+  kc.out = *out; kc.n_trials = n; kc.rng_mode = LETF_RNG_PHILOX; kc.nthreads = 1; kc.rec = rec.data(); kc.rec_ncol = n; kc.log_trial = -1;
+  kc.p.T = T; kc.p.buffer = 0; kc.p.random_start = 0; kc.series.sim_days = T; kc.series.n_paths = n;
+  kc.ringP = rp.data(); kc.ringS = rs.data(); kc.ringA = ra.data();
+  for (int64_t j = 0; j < n; j++) {
+    Trial<float, NS, kAssets, kMarketFSeries, false, TMC, LIST, AM> t(kc, j, j, 0);
+    t.run();
+  }
+  return 0;
+}
+extern "C" int letf_emu_run_series_split(const LetfParams* sp, int list, const LetfSeries* series, const LetfOutputs* out) {
+  if (validate_params(*sp)) return -1;
+  if (series->cash_ret || series->sim_days < 1) return -5;
+  if (list == 1) return run_series_split<8, 1, 25>(sp, series, out);
+  if (list == 2) return run_series_split<32, 2, 29>(sp, series, out);
+  if (list == 3) return run_series_split<32, 3, 29>(sp, series, out);
+  if (list == 0) return run_series_split<32, 0, 0x3F>(sp, series, out);
+  return -4;
 }
 
 extern "C" const char* letf_emu_validate(const LetfParams* sp) { return validate_params(*sp); }

@@ -84,7 +84,7 @@ def run(params, tape, precision=abi.PREC_F64, rng_mode=abi.RNG_TAPE, seed=0, fir
 
 
 def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, cash_ret=None, precision=abi.PREC_F64, typed=False,
-               log=None, curve=False):
+               log=None, curve=False, split_list=None):
     """materialised-path mode on host series: asset_ret = {asset name: [T][n] array}; log = (path, strategy, cap) switches
     the journal log on, curve=True also returns that (path, strategy)'s daily equity (out.curve)"""
     cols = {k: np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for k, v in asset_ret.items()}
@@ -98,6 +98,11 @@ def run_series(params, asset_ret, *, tlt_ret=None, vix=None, regime=None, cash_r
             for x, dt in ((tlt_ret, np.float64), (vix, np.float64), (regime, np.int32), (cash_ret, np.float64))]
     s.tlt_ret, s.vix, s.regime, s.cash_ret = (k.ctypes.data if k is not None else None for k in keep)
     out = HostOutputs(params.n_strategies, n)
+    if split_list is not None:      # record pass + rule kernel body (letf_api.cu launch_series_split): 1 / 2 typed, 3 routed, 0 dynamic
+        rc = lib().letf_emu_run_series_split(C.byref(params), split_list, C.byref(s), C.byref(out.as_struct()))
+        if rc != 0:
+            raise RuntimeError(f"emu series split rc={rc}")
+        return out
     args = [-1, -1, 0] + [None] * 7
     if log is not None:
         path, strat, cap = log

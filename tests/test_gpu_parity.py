@@ -982,3 +982,56 @@ def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_l
     assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
     np.testing.assert_array_equal(fast.regime_days, o.regime_days)
     np.testing.assert_array_equal(fast.jump_days, o.jump_days)
+
+
+@pytest.mark.parametrize("sids,kname", [(ALL19, "series_records+rules_sweep19"),
+                                        (["S19", "S2", "S8", "S6", "B_TLT"], "series_records+rules_sub19"),
+                                        (["S4", "S9", "B_QQQ", "B_UPRO", "S2"], "series_records+rules_all"),
+                                        (["S1", "S2", "S3"], "series_records")],
+                         ids=["typed", "routed", "dynamic", "buy_hold_only"])
+def test_series_mode_through_the_record_pass(sids, kname, engine_lib, monkeypatch):
+    """materialised-path mode (run_strategy_fixed seam) through the split pipeline: the bandwidth-bound record pass over the
+    caller's fp64 series + the rule kernel of the strategy list, against the fused series builds (LETF_NO_SPLIT=1) and the
+    fp64 oracle on the same frame; buy&hold rows, flags and regime counts are bit-identical between the two routes"""
+    import ctypes as C
+    rng = np.random.default_rng(17)
+    T, n = 900, 333                      # (not a multiple of the block size)
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    params, keep = build_params(sids, T / 252, synthetic.fallback_regime_model(), ns)
+    rets = {a: np.ascontiguousarray(rng.standard_t(5, (T, n)) * s + 0.0004) for a, s in
+            zip(abi.ASSET_NAMES, (0.028, 0.028, 0.019, 0.022, 0.0095, 0.012))}
+    vix = np.ascontiguousarray(14 + 12 * rng.random((T, n)))
+    vix[100, 5] = 140.0
+    regime = np.ascontiguousarray((rng.random((T, n)) < 0.2).astype(np.int32))
+    tlt = np.ascontiguousarray(rng.normal(0, 0.008, (T, n)))
+    from oracle.oracle import HostOutputs
+    o = HostOutputs(params.n_strategies, n)
+    s = abi.Series()
+    s.n_paths, s.sim_days = n, T
+    for a, name in enumerate(abi.ASSET_NAMES):
+        s.asset_ret[a] = rets[name].ctypes.data
+    s.tlt_ret, s.vix, s.regime = tlt.ctypes.data, vix.ctypes.data, regime.ctypes.data
+    assert orc.lib().letf_oracle_run_strategies(C.byref(params), C.byref(s), C.byref(o.as_struct())) == 0
+    with _engine(params, keep, "f32") as eng:
+        split = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime).to_host()
+        assert eng.launch_info()["kernel"] == kname, eng.launch_info()["kernel"]
+        # a frame with its own Cash_Ret column keeps the fused build (the rule kernels read the regime's cash rate)
+        eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=np.full((T, n), 1e-4))
+        assert "series_records" not in eng.launch_info()["kernel"]
+    monkeypatch.setenv("LETF_NO_SPLIT", "1")
+    with _engine(params, keep, "f32") as eng:
+        fused = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime).to_host()
+        assert "series_records" not in eng.launch_info()["kernel"]
+    hold = [k for k, sid in enumerate(sids) if ns.STRATEGIES[sid]["type"].startswith("benchmark")]
+    np.testing.assert_array_equal(split.final_wealth[hold], fused.final_wealth[hold])
+    np.testing.assert_array_equal(split.max_dd[hold], fused.max_dd[hold])
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+    assert split.flags[5] & abi.FLAG_REPAIRED
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=5e-4)
+    assert np.mean(split.num_trades != fused.num_trades) < 0.02
+    same = split.num_trades == o.num_trades
+    assert np.mean(same) > 0.97
+    assert np.median(np.abs(split.final_wealth / o.final_wealth - 1)[same]) < 1e-5
+    rel = np.abs(split.final_wealth / o.final_wealth - 1)[same]      # (same trade count, a decision a day apart: a handful of cells)
+    assert np.mean(rel < 5e-4) > 0.995 and rel.max() < 3e-2

@@ -626,3 +626,34 @@ def test_series_mode_short_frames_and_typed_build(T):
     np.testing.assert_allclose(e32.final_wealth, o.final_wealth, rtol=5e-4)
     np.testing.assert_allclose(typed.final_wealth, e32.final_wealth, rtol=1e-4)
     assert np.mean(typed.num_trades != e32.num_trades) < 0.02
+
+
+@pytest.mark.parametrize("T", [1, 2, 5, 61, 203, 700])
+def test_series_mode_through_the_record_pass(T):
+    """materialised-path mode through the split pipeline (letf_series_prep.cuh: record pass over the caller's series, then the
+    rule kernel body in record mode) - typed, routed and dynamic-slot rule kernels against the fused series builds on the same
+    frame: buy&hold rows, flags and regime counts bit for bit (same arithmetic), rule rows to fp32 reassociation"""
+    rng = np.random.default_rng(300 + T)
+    n = 6
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+    rets = {a: np.ascontiguousarray(rng.standard_t(5, (T, n)) * s) for a, s in
+            zip(abi.ASSET_NAMES, (0.03, 0.03, 0.02, 0.025, 0.01, 0.013))}
+    vix = np.ascontiguousarray(15 + 10 * rng.random((T, n)))
+    vix[T // 2, 0] = 130.0                                  # out of the validated band on one path -> LETF_FLAG_REPAIRED
+    regime = np.ascontiguousarray((rng.random((T, n)) < 0.3).astype(np.int32))
+    tlt = np.ascontiguousarray(rng.normal(0, 0.008, (T, n)))
+    years = max(T, 1) / 252.0
+    cases = [(ALL19, 2), (["S19", "S2", "S8", "S6", "B_TLT"], 3), (["S4", "S9", "B_QQQ", "B_UPRO", "S2"], 0)]
+    for sids, lst in cases:
+        params, keep = build_params(sids, years, synthetic.fallback_regime_model(), ns)
+        fused = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, precision=abi.PREC_F32, typed=(lst == 2))
+        split = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, split_list=lst)
+        hold = [k for k, sid in enumerate(sids) if ns.STRATEGIES[sid]["type"].startswith("benchmark")]
+        np.testing.assert_array_equal(split.final_wealth[hold], fused.final_wealth[hold])
+        np.testing.assert_array_equal(split.max_dd[hold], fused.max_dd[hold])
+        for k in ("flags", "start_offset", "regime_days", "jump_days"):
+            np.testing.assert_array_equal(getattr(split, k), getattr(fused, k))
+        assert split.flags[0] & abi.FLAG_REPAIRED
+        np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=2e-4)
+        np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
+        assert np.mean(split.num_trades != fused.num_trades) < 0.03
