@@ -254,8 +254,10 @@ static bool find_generic_split(const LetfEngine* e, int rng_mode, bool need_io, 
     const KernelEntry* k = kernel_at(i);
     if (k->precision != LETF_PREC_F32) continue;
     if (k->fj == code && k->na == kAssets && k->ns >= s.n_strategies && !plan->prod) plan->prod = k;
+    // (the build with the fewest slots that holds the list: eight slots unroll into registers, thirty-two live in local memory)
     if (k->market == kMarketFSeries && !k->list && (k->am & 0x3F) == 0x3F && k->ns >= s.n_strategies &&
-        !(e->type_mask & ~k->tm) && !plan->cons) plan->cons = k;
+        !(e->type_mask & ~k->tm) && (!plan->cons || k->ns < plan->cons->ns || e->pin_kernel == k->name) &&
+        !(plan->cons && e->pin_kernel == plan->cons->name)) plan->cons = k;
   }
   plan->nact = kAssets;
   plan->rules = false;
@@ -517,6 +519,7 @@ static bool find_series_split(const LetfEngine* e, const LetfSeries* series, boo
   for (int k = 0; k < s.n_strategies; k++)
     if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) rules = true;
   // 1: exactly a typed list; 2: a subset of the default sweep (routed); 3: dynamic slots
+  const KernelEntry* best3 = nullptr;
   for (int tier = 1; tier <= 3 && !plan->cons; tier++) {
     for (int i = 0; i < kernel_count() && !plan->cons; i++) {
       const KernelEntry* k = kernel_at(i);
@@ -528,9 +531,11 @@ static bool find_series_split(const LetfEngine* e, const LetfSeries* series, boo
         plan->cons = k; plan->mask = k->am & 0x3F; plan->routed = true;
         plan->n_slots = routed_slot_count(s, k->list, plan->slot_of);
       }
-      if (tier == 3 && !k->list && (k->am & 0x3F) == 0x3F && !(e->type_mask & ~k->tm) && !e->no_generic_split) { plan->cons = k; plan->mask = 0x3F; }
+      if (tier == 3 && !k->list && (k->am & 0x3F) == 0x3F && !(e->type_mask & ~k->tm) && !e->no_generic_split &&
+          (!best3 || k->ns < best3->ns)) best3 = k;
     }
   }
+  if (!plan->cons && best3) { plan->cons = best3; plan->mask = 0x3F; }
   plan->rules = rules;
   plan->nact = __builtin_popcount((unsigned)plan->mask);
   return plan->cons != nullptr;
@@ -671,6 +676,7 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
     }
     if (find_generic_split(e, rng_mode, need_io, first, &plan)) {
       CK(cudaSetDevice(e->device));
+      if (plan.cons->ns == 8) return launch_split<8, kAssets>(e, plan, st, seed, first, n, out);
       return launch_split<32, kAssets>(e, plan, st, seed, first, n, out);
     }
   }

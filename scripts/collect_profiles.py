@@ -11,7 +11,8 @@ RND = sys.argv[3] if len(sys.argv) > 3 else "r1"
 DEFAULT_W = "c2" if RND == "r1" else "c3"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 prof = os.path.join(root, "profiles")
-TRIALS = {"c2": 100000, "c3": 75776, "c4": 50560, "boot": 50560, "sweep19": 37888}
+TRIALS = {"c2": 100000, "c3": 75776, "c4": 50560, "boot": 50560, "sweep19": 37888, "series19": 100000}
+DAYS = {"series19": 2520, "series": 2520}        # simulated days per trial (default 7560)
 for kv in sys.argv[4:]:
     k, v = kv.split("=")
     TRIALS[k] = int(v)
@@ -53,11 +54,13 @@ for w, n in TRIALS.items():
     split = len(parts) == 2
     dram = inst = ms = 0.0
     for ki, out in enumerate(parts):
-        sfx = ("_producer" if ki == 0 else "_rules") if split else ""
+        first = "_records" if w.startswith("series") else "_producer"
+        sfx = (first if ki == 0 else "_rules") if split else ""
+        days = DAYS.get(w, 7560)
         with open(os.path.join(prof, f"{RND}_{w}{sfx}_{tag}_ncu_full_summary.csv"), "w") as fh:
             fh.write("metric,unit,value\n" + out)
-        kre = ("letf_jpair_kernel" if ki == 0 else "letf_path_kernel") if split else None
-        mix = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_sass_mix.py"), rep, str(n * 7560), "--blocks"] +
+        kre = (("letf_series_records_kernel" if w.startswith("series") else "letf_jpair_kernel") if ki == 0 else "letf_path_kernel") if split else None
+        mix = subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_sass_mix.py"), rep, str(n * days), "--blocks"] +
                              ([f"--kernel={kre}"] if kre else []), capture_output=True, text=True).stdout
         with open(os.path.join(prof, f"{RND}_{w}{sfx}_{tag}_sass_mix.txt"), "w") as fh:
             fh.write(mix)
@@ -71,11 +74,11 @@ for w, n in TRIALS.items():
         dram += m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)
         inst += m.get("smsp__inst_executed.sum", 0.0)
         ms += m.get("gpu__time_duration.sum", 0)
-        print(w, sfx, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % (m.get("smsp__inst_executed.sum", 0) * 32 / (n * 7560)),
+        print(w, sfx, "ms %.2f" % (m.get("gpu__time_duration.sum", 0)), "instr/path-day %.1f" % (m.get("smsp__inst_executed.sum", 0) * 32 / (n * days)),
               "issue %.1f%%" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0),
               "DRAM GB %.2f" % ((m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)) / 1e9))
-    consts[w] = {"dram_bytes_per_trial": dram / n, "executed_warp_instr_per_path_day": inst * 32 / (n * 7560),
-                 "source": f"profiles/{RND}_{w}" + ("_{producer,rules}" if split else "") + f"_{tag}_ncu_full_summary.csv ({n} trials)"}
+    consts[w] = {"dram_bytes_per_trial": dram / n, "executed_warp_instr_per_path_day": inst * 32 / (n * DAYS.get(w, 7560)),
+                 "source": f"profiles/{RND}_{w}" + ("_{producer|records,rules}" if split else "") + f"_{tag}_ncu_full_summary.csv ({n} trials)"}
 cpath = os.path.join(prof, "ncu_constants.json")
 merged = json.load(open(cpath)) if os.path.exists(cpath) else {}
 merged.update(consts)             # workloads not in this pass keep their constants

@@ -271,6 +271,8 @@ extern "C" int letf_emu_run_split(const LetfParams* sp, int list, const LetfOutp
   if (list == 0) {      // generic pipeline: uncompacted producer (default dof pattern or run-time sampler), dynamic-slot rule kernel
     for (int a = 0; a < kAssets; a++)
       if (((sp->asset_mask >> a) & 1) && df_fast_k(sp->assets[a].te_df) != (a >= 4 ? 10 : 5)) tedf = true;
+    if (sp->n_strategies <= 8)      // (the eight-slot build: slot loop unrolled, state in registers)
+      return tedf ? run_split<8, 0, 0x3F, 6, 0x80, 6>(sp, out, seed, first, n) : run_split<8, 0, 0x3F, 6, 0x30, 6>(sp, out, seed, first, n);
     return tedf ? run_split<32, 0, 0x3F, 6, 0x80, 6>(sp, out, seed, first, n) : run_split<32, 0, 0x3F, 6, 0x30, 6>(sp, out, seed, first, n);
   }
   return -4;
@@ -362,7 +364,7 @@ extern "C" int letf_emu_run_series_split(const LetfParams* sp, int list, const L
   if (list == 1) return run_series_split<8, 1, 25>(sp, series, out);
   if (list == 2) return run_series_split<32, 2, 29>(sp, series, out);
   if (list == 3) return run_series_split<32, 3, 29>(sp, series, out);
-  if (list == 0) return run_series_split<32, 0, 0x3F>(sp, series, out);
+  if (list == 0) return sp->n_strategies <= 8 ? run_series_split<8, 0, 0x3F>(sp, series, out) : run_series_split<32, 0, 0x3F>(sp, series, out);
   return -4;
 }
 

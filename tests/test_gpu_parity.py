@@ -938,11 +938,12 @@ def test_pair_kernels_with_calibrated_models(sids, kname, engine_lib, monkeypatc
     (["S19", "S2", "S8", "S6"], "default", "prod_sweep19+rules_sub19"),
     (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], "default", "prod_sweep19+rules_sub19"),
     (["S5", "S9", "S17"], "vix_te", "prod_sweep19_tedf+rules_sub19"),
-    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], "default", "prod_all+rules_all"),
+    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], "default", "prod_all+rules_all8"),
+    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13", "S4", "S5", "S7"], "default", "prod_all+rules_all"),
     (["S1", "S3", "S2", "B_UPRO", "B_TMF"], "default", "prod_all"),
-    (["S4", "S6", "S12", "S18", "B_QQQ"], "vix_te", "prod_all_tedf+rules_all"),
-], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "six_series", "buy_hold_five_series",
-        "generic_calibrated_te"])
+    (["S4", "S6", "S12", "S18", "B_QQQ"], "vix_te", "prod_all_tedf+rules_all8"),
+], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "six_series", "six_series_ten_slots",
+        "buy_hold_five_series", "generic_calibrated_te"])
 def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_lib, monkeypatch):
     """strategy lists without a typed build.  A subset of the default sweep runs the 19-rule kernel with the other slots
     switched off and its outputs routed (slot list 3); anything else the generic split pipeline (uncompacted pair producer ->
@@ -967,7 +968,7 @@ def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_l
         monkeypatch.setenv("LETF_NO_ROUTED_SPLIT", "1")
         with _engine(params, keep, "f32") as eng:
             gen = eng.run_host(2 * n_t, seed=77)
-            assert "rules_all" in eng.launch_info()["kernel"]
+            assert "rules_all8" in eng.launch_info()["kernel"]
         np.testing.assert_allclose(fast.final_wealth, gen.final_wealth, rtol=2e-3)
         np.testing.assert_array_equal(fast.flags, gen.flags)
     o = orc.run(params, rec)
@@ -986,9 +987,10 @@ def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_l
 
 @pytest.mark.parametrize("sids,kname", [(ALL19, "series_records+rules_sweep19"),
                                         (["S19", "S2", "S8", "S6", "B_TLT"], "series_records+rules_sub19"),
-                                        (["S4", "S9", "B_QQQ", "B_UPRO", "S2"], "series_records+rules_all"),
+                                        (["S4", "S9", "B_QQQ", "B_UPRO", "S2"], "series_records+rules_all8"),
+                                        (["S4", "S9", "B_QQQ", "B_UPRO", "S2", "S5", "S7", "S11", "S12"], "series_records+rules_all"),
                                         (["S1", "S2", "S3"], "series_records")],
-                         ids=["typed", "routed", "dynamic", "buy_hold_only"])
+                         ids=["typed", "routed", "dynamic", "dynamic_nine_slots", "buy_hold_only"])
 def test_series_mode_through_the_record_pass(sids, kname, engine_lib, monkeypatch):
     """materialised-path mode (run_strategy_fixed seam) through the split pipeline: the bandwidth-bound record pass over the
     caller's fp64 series + the rule kernel of the strategy list, against the fused series builds (LETF_NO_SPLIT=1) and the

@@ -369,6 +369,7 @@ def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
 @pytest.mark.parametrize("sids,extra,model,years", [
     (["S1", "S4", "S7", "S10", "S15"], False, "default", 2),              # a subset of the rules, no typed list for it
     (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], True, "default", 2),     # all six series incl. QQQ
+    (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13", "S4", "S5", "S7"], True, "default", 1),      # more than eight: 32-slot build
     (["S1", "S3", "S2", "B_UPRO", "B_TMF"], True, "default", 1),          # buy&hold only, more series than the pair kernels carry
     (["S4", "S6", "S12", "S18"], False, "vix_te", 1),                      # calibrated tracking-error model: run-time sampler
 ])
