@@ -417,6 +417,9 @@ def run_b200(args):
         alg_bytes = out_bytes_fn(n, S)
         if info["kernel"].startswith("f32_joint_t_pair") or "prod" in info["kernel"]:
             alg_bytes += n * G * 32
+        if "+rules_" in info["kernel"]:      # split pipeline: the per-day records are written once and read once (4 B per field)
+            nf = 5 if "rules_c4" in info["kernel"] else (8 if "rules_all" in info["kernel"] else 6)
+            alg_bytes += n * T * nf * 4 * 2
         pipes = None
         try:
             pp = json.load(open(os.path.join(ROOT, "profiles", "pipe_peaks.json")))

@@ -309,10 +309,19 @@ typedef struct LetfLaunchInfo {
   int32_t sm_count;
   int32_t aux_launches;          /* reduction / reset kernels launched by the last letf_reduce / letf_summary_reset */
   int32_t pad;
-  char kernel[48];               /* instantiation name of the last path kernel (e.g. "f32_joint_t_pair_c3") */
+  char kernel[48];               /* instantiation name of the last path kernel (e.g. "f32_joint_t_pair_c3"; a split pipeline
+                                    reports "<producer>+<rule kernel>", e.g. "joint_t_prod_sweep19+rules_sub19") */
 } LetfLaunchInfo;
 
-/* lifecycle ---------------------------------------------------------------- */
+/* lifecycle ----------------------------------------------------------------
+ * Tuning aids, read from the environment ONCE per engine by letf_create (they change which instantiation runs, never a result
+ * beyond fp32 reassociation; the tests use them for A/B comparisons on the same Philox counters):
+ *   LETF_KERNEL=<instantiation name>   pin an eligible build (LetfLaunchInfo::kernel reports what ran)
+ *   LETF_NO_JPAIR=1                    no antithetic-pair kernels: the fused lean builds
+ *   LETF_NO_SPLIT=1                    no split strategy pipeline at all (simulated paths and materialised-path mode)
+ *   LETF_NO_ROUTED_SPLIT=1             subsets of the default sweep skip the routed 19-rule kernel (generic pipeline instead)
+ *   LETF_NO_GENERIC_SPLIT=1            untyped strategy lists keep the fused generic builds
+ *   LETF_TRACE_HOST=1                  host time of each step of the split launch on stderr */
 int letf_create(const LetfParams* params, int device, int precision, LetfEngine** out);
 void letf_destroy(LetfEngine* e);
 const char* letf_last_error(void);

@@ -141,7 +141,7 @@ def test_partition_invariance_and_kernel_variants(engine_lib):
         b0 = e1.run_host(1000, seed=7, first_trial=0)
         b1 = e1.run_host(2000, seed=7, first_trial=1000)
         c = e2.run_host(n, seed=7)
-        assert e1.launch_info()["regs_per_thread"] < e2.launch_info()["regs_per_thread"]
+        assert e1.launch_info()["kernel"] != e2.launch_info()["kernel"]      # (pair kernel vs routed split pipeline)
     np.testing.assert_array_equal(a.final_wealth[:, :1000], b0.final_wealth)
     np.testing.assert_array_equal(a.final_wealth[:, 1000:], b1.final_wealth)
     np.testing.assert_array_equal(a.max_dd[:, 1000:], b1.max_dd)
