@@ -317,7 +317,7 @@ typedef struct LetfLaunchInfo {
  * Tuning aids, read from the environment ONCE per engine by letf_create (they change which instantiation runs, never a result
  * beyond fp32 reassociation; the tests use them for A/B comparisons on the same Philox counters):
  *   LETF_KERNEL=<instantiation name>   pin an eligible build (LetfLaunchInfo::kernel reports what ran)
- *   LETF_NO_JPAIR=1                    no antithetic-pair kernels: the fused lean builds
+ *   LETF_NO_JPAIR=1                    buy&hold shapes keep the fused lean builds (also switches the routed / generic pipelines off)
  *   LETF_NO_SPLIT=1                    no split strategy pipeline at all (simulated paths and materialised-path mode)
  *   LETF_NO_ROUTED_SPLIT=1             subsets of the default sweep skip the routed 19-rule kernel (generic pipeline instead)
  *   LETF_NO_GENERIC_SPLIT=1            untyped strategy lists keep the fused generic builds

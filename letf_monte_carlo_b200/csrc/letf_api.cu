@@ -167,7 +167,7 @@ struct SplitPlan {
 };
 static bool split_shape_ok(const LetfEngine* e, int rng_mode, bool need_io, int64_t first) {
   const LetfParams& s = e->params;
-  if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split || (first & 1)) return false;
+  if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split) return false;
   return s.market_mode == LETF_MARKET_JOINT_T && s.moment_matching && s.antithetic_pairs && s.institutional &&
          s.has_stress && s.has_funding && s.sim_days >= 2;
 }
@@ -442,7 +442,7 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
   for (;;) {
     cap = wave_trials * waves_fit;
     if (cap > ((n + 1) & ~(int64_t)1)) cap = (n + 1) & ~(int64_t)1;
-    cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
+    cudaError_t ce = e->rec.reserve((size_t)(cap + 2) * T * NF * 4);
     if (ce == cudaSuccess) break;
     cudaGetLastError();
     // (the remembered chunk size no longer fits, e.g. the caller allocated in between: smaller chunks, asked again next call)
@@ -452,11 +452,15 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
   }
   lap("reserve");
   ka_p.seed = ka_c.seed = seed; ka_p.rng_mode = ka_c.rng_mode = LETF_RNG_PHILOX;
-  ka_p.rec = ka_c.rec = (float*)e->rec.p; ka_p.rec_ncol = ka_c.rec_ncol = cap;
+  // record columns are pair-aligned: column 0 is the even twin of the chunk's first pair.  A launch that starts on an odd trial
+  // (its first pair half outside the range) reads from column 1 on - the rule kernel simply gets the base shifted by one
+  // element; two spare columns hold the half pairs at both ends
+  const int odd = (int)(first & 1);
+  ka_p.rec = (float*)e->rec.p; ka_c.rec = (float*)e->rec.p + odd; ka_p.rec_ncol = ka_c.rec_ncol = cap + 2;
   ka_p.log_trial = ka_c.log_trial = -1;
   ka_c.p.T = T; ka_c.p.buffer = 0; ka_c.p.random_start = 0;
   ka_c.series.sim_days = T;
-  size_t scratch = (size_t)cap * T * NF * 4;
+  size_t scratch = (size_t)(cap + 2) * T * NF * 4;
   int launches = 0;
   int64_t grid_c_last = 0, grid_p_last = 0;
   CK(cudaEventRecord(e->ev0, st));
@@ -464,7 +468,7 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
     const int64_t nc = n - c0 < cap ? n - c0 : cap;
     const LetfOutputs oc = out_columns(*out, c0);
     // producer: one work item per antithetic pair
-    const int64_t pairs = (nc + 1) / 2;
+    const int64_t pairs = ((first + c0 + nc - 1) >> 1) - ((first + c0) >> 1) + 1;
     const int64_t grid_p = full_wave_grid(pairs, e->sm_count, mbp, kp->block);
     ka_p.out = oc; ka_p.first_trial = first + c0; ka_p.n_trials = nc; ka_p.nthreads = grid_p * kp->block;
     {
@@ -668,7 +672,7 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
   }
   const KernelEntry* ke = select_kernel(e, market, need_io, e->params.n_strategies, e->type_mask, n_assets);
   // no typed pipeline and no antithetic-pair kernel for this list: the generic split pipeline before the fused builds
-  if (may_split && !(ke && ke->fj)) {
+  if (may_split && !(ke && ke->fj) && !e->no_jpair) {
     SplitPlan plan;
     if (find_routed_split(e, rng_mode, need_io, first, &plan)) {
       CK(cudaSetDevice(e->device));

@@ -212,7 +212,7 @@ extern "C" int letf_emu_run_typed(const LetfParams* sp, int list, const LetfOutp
 // (Trial::run in record mode) consumes them; Philox only, fp32
 template <int NS, int LIST, int AM, int NACT, int K10, int NAP = 4>
 static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed, int64_t first, int64_t n) {
-  if (sp->market_mode != LETF_MARKET_JOINT_T || (first & 1)) return -2;
+  if (sp->market_mode != LETF_MARKET_JOINT_T) return -2;
   // routed list (letf_api.cu find_routed_split): the request is a subset of the typed list
   static LetfParams routed;
   int slot_of[LETF_MAX_STRATEGIES], n_slots = 0;
@@ -237,7 +237,8 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   convert_params<float, NS, kAssets>(*sp, dd, kc.p);
   if (LIST == 3) { route_slots(kp.p, *req, slot_of, n_slots); route_slots(kc.p, *req, slot_of, n_slots); }
   const int T = sp->sim_days, G = T + sp->buffer_days, NF = NACT + 2;
-  const int64_t cap = (n + 1) & ~(int64_t)1;
+  const int64_t cap = ((n + 1) & ~(int64_t)1) + 2;        // pair-aligned columns + the half pairs at both ends (letf_api.cu launch_split)
+  const int odd = (int)(first & 1);
   std::vector<float> rec((size_t)cap * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
   float* xscr = (float*)aligned_alloc(32, ((size_t)(G > 0 ? G : 1) * 8 + 8) * sizeof(float));
   kp.out = *out; kp.seed = seed; kp.first_trial = first; kp.n_trials = n; kp.rng_mode = LETF_RNG_PHILOX; kp.nthreads = 1;
@@ -245,7 +246,7 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   kp.xscr = xscr; kp.rec = rec.data(); kp.rec_ncol = cap; kp.log_trial = -1; kp.spell_scr = spells.data();
   for (int64_t pj = first >> 1; pj <= (first + n - 1) >> 1; pj++) JointPair<32, NAP, NACT, K10, true>::run(kp, pj, 0);
   kc.out = *out; kc.seed = seed; kc.first_trial = first; kc.n_trials = n; kc.rng_mode = LETF_RNG_PHILOX; kc.nthreads = 1;
-  kc.rec = rec.data(); kc.rec_ncol = cap; kc.log_trial = -1;
+  kc.rec = rec.data() + odd; kc.rec_ncol = cap; kc.log_trial = -1;
   kc.p.T = T; kc.p.buffer = 0; kc.p.random_start = 0; kc.series.sim_days = T; kc.series.n_paths = n;
   kc.ringP = rp.data(); kc.ringS = rs.data(); kc.ringA = ra.data();
   for (int64_t j = 0; j < n; j++) {

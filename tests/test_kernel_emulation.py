@@ -364,6 +364,11 @@ def test_split_pipeline_matches_fused_typed_build(slot_list, sids):
     part = emu.run_split(params, slot_list, 7, seed=5)
     np.testing.assert_array_equal(part.final_wealth, split.final_wealth[:, :7])
     np.testing.assert_array_equal(part.num_trades, split.num_trades[:, :7])
+    # a launch that starts on an odd trial: the first pair's even twin is computed, its records written, nothing of it stored
+    off = emu.run_split(params, slot_list, 6, seed=5, first=3)
+    np.testing.assert_array_equal(off.final_wealth, split.final_wealth[:, 3:9])
+    np.testing.assert_array_equal(off.num_trades, split.num_trades[:, 3:9])
+    np.testing.assert_array_equal(off.flags, split.flags[3:9])
 
 
 @pytest.mark.parametrize("sids,extra,model,years", [
