@@ -168,7 +168,7 @@ struct SplitPlan {
 static bool split_shape_ok(const LetfEngine* e, int rng_mode, bool need_io, int64_t first) {
   const LetfParams& s = e->params;
   if (e->precision != LETF_PREC_F32 || need_io || rng_mode != LETF_RNG_PHILOX || e->no_split) return false;
-  return s.market_mode == LETF_MARKET_JOINT_T && s.moment_matching && s.antithetic_pairs && s.institutional &&
+  return s.market_mode == LETF_MARKET_JOINT_T && s.antithetic_pairs && s.institutional &&
          s.has_stress && s.has_funding && s.sim_days >= 2;
 }
 static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
@@ -338,7 +338,8 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
 
   const int G = e->params.sim_days + e->params.buffer_days;
   size_t scratch = 0;
-  if (((ke->market == LETF_MARKET_JOINT_T && e->params.moment_matching) || ke->market == LETF_MARKET_BOOTSTRAP) && G > 0) {
+  // (the pair kernels are two-pass with or without moment matching: pass 2 reads pass 1's day records either way)
+  if (((ke->market == LETF_MARKET_JOINT_T && (e->params.moment_matching || ke->fj)) || ke->market == LETF_MARKET_BOOTSTRAP) && G > 0) {
     size_t b = ((size_t)G * 4 + (size_t)((G + 3) & ~3)) * (size_t)nthreads * sizeof(R);   // day vectors + the IRX-normal column (letf_core.cuh AUXSCR)
     if (ke->fj) {
       b = (size_t)G * sizeof(JF8) * (size_t)nthreads;                                      // one 32-byte record per day and pair (letf_jfast.cuh)

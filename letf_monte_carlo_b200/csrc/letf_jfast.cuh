@@ -253,7 +253,7 @@ struct JointPair {
 #pragma unroll
       for (int t = 0; t < 2; t++)
 #pragma unroll
-        for (int a = 0; a < 3; a++) shift[t][a] = (p.mm_theo[a] - sum[t][a] / (R)G) * 0.1f;
+        for (int a = 0; a < 3; a++) shift[t][a] = p.mm ? (p.mm_theo[a] - sum[t][a] / (R)G) * 0.1f : 0.0f;      // (moment matching off: the raw draws, calibration.py:579)
     }
 
     // ---- VIX burn-in: generated days before the window (engine.py:100-115)

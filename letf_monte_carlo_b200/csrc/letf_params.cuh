@@ -233,7 +233,7 @@ inline void build_boot_tables(const LetfParams& s, BootTables<R>& t) {
 // shape code of the antithetic-pair kernel (letf_jfast.cuh), 0 = not admitted; computed from the public parameter block so
 // that kernel selection (letf_api.cu) and the device parameter block agree
 inline int fast_joint_shape(const LetfParams& s, int na) {
-  if (na >= kAssets || s.market_mode != LETF_MARKET_JOINT_T || !s.moment_matching || !s.antithetic_pairs) return 0;
+  if (na >= kAssets || s.market_mode != LETF_MARKET_JOINT_T || !s.antithetic_pairs) return 0;      // (moment matching off: same kernel, zero shift)
   if (!s.institutional || !s.has_stress || !s.has_funding || s.sim_days < 2) return 0;
   for (int k = 0; k < s.n_strategies; k++)
     if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) return 0;

@@ -48,6 +48,9 @@ LETF_HD void series_prep_path(const SeriesPrepArgs& a, const int64_t j) {
 #pragma unroll
   for (int k = 0; k < kAssets; k++) nf += (a.field_mask >> k) & 1;
   const int64_t fstride = (int64_t)T * a.rec_ncol;
+  // four days of loads in flight per thread (126 registers, 4 blocks per SM).  Measured on 100k paths x 2 520 days, 17.1 GB of
+  // DRAM traffic: 3.68 ms; eight days (142 registers, 3 blocks per SM) 7.70 ms; two days under a 6-blocks-per-SM register cap
+  // (one balanced wave, 108 B of spills) 4.17 ms
   constexpr int kAhead = 4;
   for (int i0 = 0; i0 < T; i0 += kAhead) {
     double er[kAhead][kAssets], vx[kAhead], tl[kAhead];

@@ -1037,3 +1037,32 @@ def test_series_mode_through_the_record_pass(sids, kname, engine_lib, monkeypatc
     assert np.median(np.abs(split.final_wealth / o.final_wealth - 1)[same]) < 1e-5
     rel = np.abs(split.final_wealth / o.final_wealth - 1)[same]      # (same trade count, a decision a day apart: a handful of cells)
     assert np.mean(rel < 5e-4) > 0.995 and rel.max() < 3e-2
+
+
+def test_pair_kernel_and_split_pipeline_without_moment_matching(engine_lib, monkeypatch):
+    """USE_MOMENT_MATCHING = False: the specialised paths still serve the shape (two passes, zero shift); against the fused
+    one-pass builds on the same Philox counters and the oracle on the recorded tape"""
+    model = synthetic.fallback_regime_model("default")
+    for sids, kname in ((["S2", "B_QQQ", "B_TLT"], "f32_joint_t_pair_c3"), (ALL19, "prod_sweep19+rules_sweep19")):
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_MOMENT_MATCHING=False)
+        params, keep = build_params(sids, 2, model, ns)
+        n_t = 64
+        rec = HostTape(n_t, params.sim_days + params.buffer_days, params.sim_days, 512)
+        with _engine(params, keep, "f32") as eng:
+            fast = eng.run_host(2 * n_t, seed=31)
+            assert eng.launch_info()["kernel"].endswith(kname), eng.launch_info()["kernel"]
+            eng.run_host(2 * n_t, seed=31, rng_mode=abi.RNG_PHILOX_RECORD, tape=rec)
+        monkeypatch.setenv("LETF_NO_JPAIR", "1")
+        monkeypatch.setenv("LETF_NO_SPLIT", "1")
+        with _engine(params, keep, "f32") as eng:
+            slow = eng.run_host(2 * n_t, seed=31)
+        monkeypatch.delenv("LETF_NO_JPAIR")
+        monkeypatch.delenv("LETF_NO_SPLIT")
+        o = orc.run(params, rec)
+        np.testing.assert_allclose(fast.final_wealth, slow.final_wealth, rtol=2e-3)
+        assert np.median(np.abs(fast.final_wealth / slow.final_wealth - 1)) < 5e-6
+        for k in ("flags", "start_offset", "regime_days", "jump_days"):
+            np.testing.assert_array_equal(getattr(fast, k), getattr(slow, k))
+        rel = np.abs(fast.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
+        assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
+        np.testing.assert_array_equal(fast.regime_days, o.regime_days)

@@ -663,3 +663,29 @@ def test_series_mode_through_the_record_pass(T):
         np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=2e-4)
         np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
         assert np.mean(split.num_trades != fused.num_trades) < 0.03
+
+
+def test_pair_kernel_and_split_pipeline_without_moment_matching():
+    """USE_MOMENT_MATCHING = False (calibration.py:579): the pair kernel and the split pipeline keep their two passes and shift
+    by zero - same Philox counters as the general one-pass loops"""
+    ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS, USE_MOMENT_MATCHING=False)
+    model = synthetic.fallback_regime_model("default")
+    params, keep = build_params(["S2", "B_QQQ", "B_TLT"], 1, model, ns)
+    assert not params.moment_matching
+    pair, used = emu.run_jpair(params, 12, seed=3)
+    slow, _ = emu.run_jpair(params, 12, seed=3, force_generic=True)
+    assert used == 0x203
+    np.testing.assert_allclose(pair.final_wealth, slow.final_wealth, rtol=2e-5)
+    np.testing.assert_allclose(pair.max_dd, slow.max_dd, atol=5e-6)
+    for k in ("flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(pair, k), getattr(slow, k))
+    p19, keep19 = build_params(ALL19, 1, model, synthetic.config_namespace(USE_MOMENT_MATCHING=False))
+    split = emu.run_split(p19, 2, 12, seed=4)
+    fused = emu.run_typed(p19, 2, 12, seed=4)
+    np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
+    np.testing.assert_array_equal(split.regime_days, fused.regime_days)
+    np.testing.assert_array_equal(split.flags, fused.flags)
+    # and it is NOT the moment-matched result
+    pmm, _ = build_params(["S2", "B_QQQ", "B_TLT"], 1, model, synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS))
+    mm, _ = emu.run_jpair(pmm, 12, seed=3)
+    assert np.abs(mm.final_wealth / pair.final_wealth - 1).max() > 1e-4
