@@ -938,11 +938,13 @@ def test_pair_kernels_with_calibrated_models(sids, kname, engine_lib, monkeypatc
     (["S19", "S2", "S8", "S6"], "default", "prod_sweep19+rules_sub19"),
     (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], "default", "prod_sweep19+rules_sub19"),
     (["S5", "S9", "S17"], "vix_te", "prod_sweep19_tedf+rules_sub19"),
+    (["S1", "S3", "S2", "B_TMF"], "default", "prod_sweep19"),
     (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], "default", "prod_all+rules_all8"),
     (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13", "S4", "S5", "S7"], "default", "prod_all+rules_all"),
     (["S1", "S3", "S2", "B_UPRO", "B_TMF"], "default", "prod_all"),
     (["S4", "S6", "S12", "S18", "B_QQQ"], "vix_te", "prod_all_tedf+rules_all8"),
-], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "six_series", "six_series_ten_slots",
+], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "routed_buy_hold_only", "six_series",
+        "six_series_ten_slots",
         "buy_hold_five_series", "generic_calibrated_te"])
 def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_lib, monkeypatch):
     """strategy lists without a typed build.  A subset of the default sweep runs the 19-rule kernel with the other slots
