@@ -109,6 +109,7 @@ struct LetfEngine {
   bool trace_host = false;
   bool no_routed_split = false;              // LETF_NO_ROUTED_SPLIT=1: subsets of the default sweep skip the routed 19-rule kernel
   DevBuf rec;                                // per-day records of the split strategy pipeline
+  DevBuf rec_cash;                           // + the frame's Cash_Ret column in the materialised-path mode
   int64_t split_key = 0; int split_waves = 0; // its chunk size in producer waves, remembered per shape (launch_split)
   int64_t series_key = 0, series_cap = 0;    // same for the materialised-path mode (launch_series_split), in paths
   DevBuf spell;                              // regime spells of the pair kernels
@@ -518,7 +519,7 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
 static bool find_series_split(const LetfEngine* e, const LetfSeries* series, bool need_io, SplitPlan* plan) {
   const LetfParams& s = e->params;
   *plan = SplitPlan();
-  if (e->precision != LETF_PREC_F32 || need_io || e->no_split || series->cash_ret || series->sim_days < 1) return false;
+  if (e->precision != LETF_PREC_F32 || need_io || e->no_split || series->sim_days < 1) return false;
   const int mask = s.asset_mask & 0x3F;
   bool rules = false;
   for (int k = 0; k < s.n_strategies; k++)
@@ -529,7 +530,8 @@ static bool find_series_split(const LetfEngine* e, const LetfSeries* series, boo
     for (int i = 0; i < kernel_count() && !plan->cons; i++) {
       const KernelEntry* k = kernel_at(i);
       if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || k->ns < s.n_strategies) continue;
-      if (tier == 1 && k->list && k->list != 3 && (k->am & 0x3F) == mask && list_matches(k, e)) { plan->cons = k; plan->mask = mask; }
+      // (a frame with its own Cash_Ret column: the typed kernels do not read one - the routed kernel takes the whole list)
+      if (tier == 1 && !series->cash_ret && k->list && k->list != 3 && (k->am & 0x3F) == mask && list_matches(k, e)) { plan->cons = k; plan->mask = mask; }
       if (tier == 2 && k->list == 3 && !(mask & ~(k->am & 0x3F)) && !e->no_routed_split) {
         bool r2 = false;
         if (!route_request(s, k->list, k->ns, plan->slot_of, &r2)) continue;
@@ -583,6 +585,11 @@ static int launch_series_split(LetfEngine* e, const SplitPlan& plan, cudaStream_
     if (ce != cudaSuccess) { cudaGetLastError(); e->series_key = 0; return fail(LETF_ERR_NOMEM, "materialised-path records: " + std::string(cudaGetErrorString(ce))); }
   }
   pa.series = *series; pa.rec = NF ? (float*)e->rec.p : nullptr; pa.rec_ncol = cap; pa.T = T;
+  if (series->cash_ret && plan.rules) {      // the frame's own Cash_Ret column (strategy.py:138 reads it per day)
+    cudaError_t ce = e->rec_cash.reserve((size_t)cap * T * 4);
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "materialised-path cash column: " + std::string(cudaGetErrorString(ce))); }
+    pa.rec_cash = (float*)e->rec_cash.p; ka_c.rec_cash = pa.rec_cash;
+  }
   pa.field_mask = plan.mask; pa.asset_mask = ka_c.p.asset_mask; pa.bench_mask = ka_c.p.bench_mask; pa.bench_tlt = ka_c.p.bench_tlt;
   pa.n_strat = ka_c.p.n_strat; pa.W0 = (double)ka_c.p.W0;
   for (int q = 0; q < ka_c.p.n_strat && q < LETF_MAX_STRATEGIES; q++) {
@@ -809,7 +816,7 @@ void letf_destroy(LetfEngine* e) {
   cudaSetDevice(e->device);
   for (int r = 0; r < 2; r++) if (e->dev_dur[r]) cudaFree(e->dev_dur[r]);
   if (e->boot_blob) cudaFree(e->boot_blob);
-  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release(); e->rec.release(); e->spell.release();
+  e->xscr.release(); e->ringP.release(); e->ringS.release(); e->ringA.release(); e->rec.release(); e->rec_cash.release(); e->spell.release();
   e->stage_tape.release(); e->stage_out.release(); e->stage_log.release(); e->pin_out.release();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);

@@ -49,6 +49,8 @@ template <typename R, int NS, int NA> struct KArgs {
   // rec[(field * T + day) * rec_ncol + column], fields = the active layer returns, VIX (regime in the sign bit), SPY price
   float* rec;
   int64_t rec_ncol;
+  const float* rec_cash;    // record mode on a caller-supplied frame with its own Cash_Ret column: [day][rec_ncol] (letf_series_prep.cuh);
+                            // nullptr = the regime's cash rate (engine.py:544), which is what the simulated frames carry
   uint32_t* spell_scr;      // [nthreads][G + 1]: regime spells of the pair kernels (letf_jfast.cuh), (end day << 1) | regime
 };
 
@@ -250,6 +252,9 @@ struct Trial {
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool FSER = MARKET == kMarketFSeries;
   static constexpr bool ROUTED = LIST == 3;     // slots can be switched off / write another output row (DevStrategy::route)
+  // record mode on a frame with its own Cash_Ret column (KArgs::rec_cash): the routed and dynamic-slot rule kernels only - the
+  // typed kernels of the benchmarked sweeps stay as they are (the test + select cost c4 1.4 %, measured)
+  static constexpr bool CASHCOL = MARKET == kMarketFSeries && (LIST == 0 || LIST == 3);
   static constexpr bool SERIES = MARKET == kMarketSeries || FSER;
   static constexpr int NF = FSER ? __builtin_popcount((unsigned)AM & 0x3Fu) + 2 : 1;      // record fields: active returns, VIX, SPY price
   static constexpr int kFSpy = __builtin_popcount((unsigned)AM & 0x0Fu);                 // record field of the SPY return (asset 4)
@@ -912,6 +917,7 @@ struct Trial {
     };
     const bool rec_used[kNV > NF ? kNV - NF : 1] = {HAS_V5, HAS_V10, HAS_V20 || HAS_DV20, HAS_V60 || HAS_SKEW || HAS_MEAN60, NEED_RINGS,
                                                     HAS_SMA100, HAS_SMA200, HAS_RSI, HAS_RSI};
+    R rec_cash_next = (CASHCOL && ka.rec_cash && T > 0) ? (R)ka.rec_cash[col] : (R)0;
 #if defined(__CUDA_ARCH__)
     float* const stage = FSER ? letf_stage_smem() + threadIdx.x : nullptr;
     const int sblk = blockDim.x;
@@ -1206,7 +1212,11 @@ struct Trial {
           } else ddT.step_ret(tlt);
         }
       }
-      const R cash = (MARKET == kMarketSeries && ka.series.cash_ret) ? s_cash : p.cash_daily[reg];
+      R cash = (MARKET == kMarketSeries && ka.series.cash_ret) ? s_cash : p.cash_daily[reg];
+      if (CASHCOL && ka.rec_cash) {       // requested a day ahead (one plain load per day: the column is not worth a staging slot)
+        cash = rec_cash_next;
+        if (i + 1 < T) rec_cash_next = (R)ka.rec_cash[(int64_t)(i + 1) * ka.rec_ncol + col];
+      }
       const R Pspy = FSER ? rec_pspy : (NA == kAssets ? (R)(cp[NA == kAssets ? 4 : 0] * 100.0) : (R)100);
 
       // ---- signals as of yesterday, then roll the windows forward with today's values

@@ -20,6 +20,7 @@ struct SeriesPrepArgs {
   LetfSeries series;          // device pointers, pitch series.n_paths
   LetfOutputs out;            // view of the chunk's columns (pitch out.n_trials)
   float* rec;                 // records of this chunk, rec_ncol columns
+  float* rec_cash;            // [day][rec_ncol] fp32 copy of the frame's Cash_Ret column, nullptr when the frame has none
   int64_t rec_ncol;
   int64_t col0, n;            // the chunk: paths [col0, col0 + n)
   int T;
@@ -53,7 +54,7 @@ LETF_HD void series_prep_path(const SeriesPrepArgs& a, const int64_t j) {
   // (one balanced wave, 108 B of spills) 4.17 ms
   constexpr int kAhead = 4;
   for (int i0 = 0; i0 < T; i0 += kAhead) {
-    double er[kAhead][kAssets], vx[kAhead], tl[kAhead];
+    double er[kAhead][kAssets], vx[kAhead], tl[kAhead], ch[kAhead];
     int rg[kAhead];
 #pragma unroll
     for (int d = 0; d < kAhead; d++) {
@@ -63,6 +64,7 @@ LETF_HD void series_prep_path(const SeriesPrepArgs& a, const int64_t j) {
       vx[d] = s.vix ? s.vix[o] : 15.0;
       tl[d] = s.tlt_ret ? s.tlt_ret[o] : 0.0;
       rg[d] = s.regime ? s.regime[o] : 0;
+      ch[d] = (s.cash_ret && a.rec_cash) ? s.cash_ret[o] : 0.0;
     }
 #pragma unroll
     for (int d = 0; d < kAhead; d++) {
@@ -86,6 +88,7 @@ LETF_HD void series_prep_path(const SeriesPrepArgs& a, const int64_t j) {
         if (row && ((a.field_mask >> k) & 1)) { row[(int64_t)f * fstride] = s.asset_ret[k] ? r : 0.0f; f++; }
       }
       if (a.bench_tlt) { cp_tlt = ::fma(cp_tlt, (double)tlt, cp_tlt); ddT.step_ret(tlt); }
+      if (a.rec_cash) a.rec_cash[(int64_t)i * a.rec_ncol + j] = (float)ch[d];
       if (row) {
         row[(int64_t)nf * fstride] = u2f_(f2u_(vix) | ((uint32_t)(reg != 0) << 31));
         row[(int64_t)(nf + 1) * fstride] = (float)(cp[4] * 100.0);

@@ -346,6 +346,8 @@ static int run_series_split(const LetfParams* sp, const LetfSeries* series, cons
   const int64_t n = series->n_paths;
   std::vector<float> rec((size_t)n * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
   pa.series = *series; pa.out = *out; pa.rec = rec.data(); pa.rec_ncol = n; pa.col0 = 0; pa.n = n; pa.T = T;
+  std::vector<float> cash(series->cash_ret ? (size_t)n * T : 0);
+  if (series->cash_ret) { pa.rec_cash = cash.data(); kc.rec_cash = cash.data(); }
   pa.field_mask = AM & 0x3F; pa.asset_mask = kc.p.asset_mask; pa.bench_mask = kc.p.bench_mask; pa.bench_tlt = kc.p.bench_tlt;
   pa.n_strat = kc.p.n_strat; pa.W0 = (double)kc.p.W0;
   for (int q = 0; q < kc.p.n_strat; q++) { pa.type[q] = kc.p.strat[q].type; pa.asset[q] = kc.p.strat[q].asset; pa.route[q] = kc.p.strat[q].route; }
@@ -361,7 +363,8 @@ static int run_series_split(const LetfParams* sp, const LetfSeries* series, cons
 }
 extern "C" int letf_emu_run_series_split(const LetfParams* sp, int list, const LetfSeries* series, const LetfOutputs* out) {
   if (validate_params(*sp)) return -1;
-  if (series->cash_ret || series->sim_days < 1) return -5;
+  if (series->sim_days < 1) return -5;
+  if ((list == 1 || list == 2) && series->cash_ret) list = 3;      // the typed rule kernels read no cash column (letf_api.cu find_series_split)
   if (list == 1) return run_series_split<8, 1, 25>(sp, series, out);
   if (list == 2) return run_series_split<32, 2, 29>(sp, series, out);
   if (list == 3) return run_series_split<32, 3, 29>(sp, series, out);

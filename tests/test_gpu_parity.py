@@ -1019,13 +1019,17 @@ def test_series_mode_through_the_record_pass(sids, kname, engine_lib, monkeypatc
     with _engine(params, keep, "f32") as eng:
         split = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime).to_host()
         assert eng.launch_info()["kernel"] == kname, eng.launch_info()["kernel"]
-        # a frame with its own Cash_Ret column keeps the fused build (the rule kernels read the regime's cash rate)
-        eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=np.full((T, n), 1e-4))
-        assert "series_records" not in eng.launch_info()["kernel"]
+        # a frame with its own Cash_Ret column (what the reference's frames carry, strategy.py:138): copied beside the records
+        cash = np.ascontiguousarray(2e-4 + 1e-4 * rng.random((T, n)))
+        split_c = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash).to_host()
+        assert eng.launch_info()["kernel"] == kname.replace("rules_sweep19", "rules_sub19")     # (the typed kernels read no cash column)
     monkeypatch.setenv("LETF_NO_SPLIT", "1")
     with _engine(params, keep, "f32") as eng:
         fused = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime).to_host()
         assert "series_records" not in eng.launch_info()["kernel"]
+        fused_c = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash).to_host()
+    np.testing.assert_allclose(split_c.final_wealth, fused_c.final_wealth, rtol=5e-4)
+    assert np.mean(split_c.num_trades != fused_c.num_trades) < 0.02
     hold = [k for k, sid in enumerate(sids) if ns.STRATEGIES[sid]["type"].startswith("benchmark")]
     np.testing.assert_array_equal(split.final_wealth[hold], fused.final_wealth[hold])
     np.testing.assert_array_equal(split.max_dd[hold], fused.max_dd[hold])

@@ -663,6 +663,13 @@ def test_series_mode_through_the_record_pass(T):
         np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=2e-4)
         np.testing.assert_allclose(split.max_dd, fused.max_dd, atol=5e-5)
         assert np.mean(split.num_trades != fused.num_trades) < 0.03
+        # a frame with its own Cash_Ret column (what the reference's frames carry, strategy.py:138): copied beside the records
+        cash = np.ascontiguousarray(2e-4 + 1e-4 * rng.random((T, n)))
+        fc = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash, precision=abi.PREC_F32, typed=(lst == 2))
+        sc = emu.run_series(params, rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash, split_list=lst)
+        np.testing.assert_allclose(sc.final_wealth, fc.final_wealth, rtol=2e-4)
+        if T > 5 and lst != 0:
+            assert np.abs(sc.final_wealth / split.final_wealth - 1).max() > 1e-7        # the column is really read
 
 
 def test_pair_kernel_and_split_pipeline_without_moment_matching():
