@@ -321,7 +321,8 @@ typedef struct LetfLaunchInfo {
  *   LETF_NO_SPLIT=1                    no split strategy pipeline at all (simulated paths and materialised-path mode)
  *   LETF_NO_ROUTED_SPLIT=1             subsets of the default sweep skip the routed 19-rule kernel (generic pipeline instead)
  *   LETF_NO_GENERIC_SPLIT=1            untyped strategy lists keep the fused generic builds
- *   LETF_TRACE_HOST=1                  host time of each step of the split launch on stderr */
+ *   LETF_TRACE_HOST=1                  host time of each step of the split launch on stderr
+ *   LETF_SPLIT_WAVES=<1..4>, LETF_SERIES_CHUNK=<paths>   smaller chunks of the split launches (the tests cross chunk seams with them) */
 int letf_create(const LetfParams* params, int device, int precision, LetfEngine** out);
 void letf_destroy(LetfEngine* e);
 const char* letf_last_error(void);

@@ -107,6 +107,8 @@ struct LetfEngine {
   bool no_split = false;
   bool no_generic_split = false;             // LETF_NO_GENERIC_SPLIT=1: untyped strategy lists keep the fused builds (A/B runs)
   bool trace_host = false;
+  int force_split_waves = 0;                 // LETF_SPLIT_WAVES=<1..4>: producer waves per chunk of the split launch (tests: chunk seams)
+  int64_t force_series_chunk = 0;            // LETF_SERIES_CHUNK=<paths>: paths per chunk of the materialised-path mode
   bool no_routed_split = false;              // LETF_NO_ROUTED_SPLIT=1: subsets of the default sweep skip the routed 19-rule kernel
   DevBuf rec;                                // per-day records of the split strategy pipeline
   DevBuf rec_cash;                           // + the frame's Cash_Ret column in the materialised-path mode
@@ -440,6 +442,7 @@ static int launch_split(LetfEngine* e, const SplitPlan& plan, cudaStream_t st, u
     if (waves_fit > 4) waves_fit = 4;
     e->split_key = shape_key; e->split_waves = (int)waves_fit;
   }
+  if (e->force_split_waves >= 1 && e->force_split_waves < waves_fit) waves_fit = e->force_split_waves;
   int64_t cap = 0;
   for (;;) {
     cap = wave_trials * waves_fit;
@@ -579,6 +582,7 @@ static int launch_series_split(LetfEngine* e, const SplitPlan& plan, cudaStream_
     if (cap < 128) return fail(LETF_ERR_NOMEM, "materialised-path mode: the per-day records of 128 paths do not fit in device memory");
     e->series_key = shape_key; e->series_cap = cap;
   }
+  if (e->force_series_chunk >= 128 && e->force_series_chunk < cap) cap = e->force_series_chunk & ~(int64_t)127;
   if (cap > n) cap = n;
   {
     cudaError_t ce = e->rec.reserve((size_t)cap * T * NF * 4);
@@ -803,6 +807,8 @@ int letf_create(const LetfParams* params, int device, int precision, LetfEngine*
   { const char* v = getenv("LETF_NO_GENERIC_SPLIT"); e->no_generic_split = v && *v && *v != '0'; }
   { const char* v = getenv("LETF_NO_ROUTED_SPLIT"); e->no_routed_split = v && *v && *v != '0'; }
   { const char* v = getenv("LETF_TRACE_HOST"); e->trace_host = v && *v && *v != '0'; }
+  { const char* v = getenv("LETF_SPLIT_WAVES"); e->force_split_waves = v ? atoi(v) : 0; }
+  { const char* v = getenv("LETF_SERIES_CHUNK"); e->force_series_chunk = v ? atoll(v) : 0; }
   for (int k = 0; k < params->n_strategies; k++) if (params->strategies[k].taxable) e->any_taxable = true;
   ce = cudaEventCreate(&e->ev0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);

@@ -1072,3 +1072,40 @@ def test_pair_kernel_and_split_pipeline_without_moment_matching(engine_lib, monk
         rel = np.abs(fast.final_wealth - o.final_wealth) / np.abs(o.final_wealth)
         assert np.median(rel) < 1e-4 and np.mean(rel < 1e-2) > 0.97
         np.testing.assert_array_equal(fast.regime_days, o.regime_days)
+
+
+def test_split_launches_are_chunk_invariant(engine_lib, monkeypatch):
+    """the split pipelines process trials in chunks of whole producer waves (memory-bounded); results must not depend on
+    where the seams fall - one wave per chunk / 256 paths per chunk against the default chunking, bit for bit"""
+    ns = synthetic.config_namespace()
+    params, keep = build_params(ALL19, 30 / 252.0 + 1e-9, synthetic.fallback_regime_model("default"), ns)
+    n = 250_001                                   # > 2 producer waves of 113 664 trials, odd
+    with _engine(params, keep, "f32") as eng:
+        whole = eng.run_host(n, seed=9)
+        assert eng.launch_info()["kernel_launches"] == 2
+    monkeypatch.setenv("LETF_SPLIT_WAVES", "1")
+    with _engine(params, keep, "f32") as eng:
+        parts = eng.run_host(n, seed=9)
+        assert eng.launch_info()["kernel_launches"] >= 6
+    for k in ("final_wealth", "max_dd", "num_trades", "flags", "start_offset", "regime_days", "jump_days"):
+        np.testing.assert_array_equal(getattr(parts, k), getattr(whole, k))
+    # materialised-path mode: 256 paths per chunk
+    rng = np.random.default_rng(3)
+    T, m = 120, 1000
+    p2, k2 = build_params(["S19", "S2", "S8", "S6", "B_TLT"], T / 252, synthetic.fallback_regime_model(),
+                          synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS))
+    rets = {a: np.ascontiguousarray(rng.standard_t(5, (T, m)) * s) for a, s in zip(abi.ASSET_NAMES, (0.028, 0.028, 0.019, 0.022, 0.0095, 0.012))}
+    vix = np.ascontiguousarray(14 + 12 * rng.random((T, m)))
+    regime = np.ascontiguousarray((rng.random((T, m)) < 0.2).astype(np.int32))
+    tlt = np.ascontiguousarray(rng.normal(0, 0.008, (T, m)))
+    cash = np.ascontiguousarray(2e-4 + 1e-4 * rng.random((T, m)))
+    monkeypatch.delenv("LETF_SPLIT_WAVES")
+    with _engine(p2, k2, "f32") as eng:
+        a = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash).to_host()
+        assert eng.launch_info()["kernel_launches"] == 2
+    monkeypatch.setenv("LETF_SERIES_CHUNK", "256")
+    with _engine(p2, k2, "f32") as eng:
+        b = eng.run_strategies(rets, tlt_ret=tlt, vix=vix, regime=regime, cash_ret=cash).to_host()
+        assert eng.launch_info()["kernel_launches"] == 8
+    for k in ("final_wealth", "max_dd", "num_trades", "flags", "regime_days"):
+        np.testing.assert_array_equal(getattr(b, k), getattr(a, k))
