@@ -107,8 +107,14 @@ struct JointPair {
   static constexpr bool TEDF = (K10 & 0x80) != 0;
 
   // pj: global pair index (trials 2 pj and 2 pj + 1); lane: this thread's scratch column
-  static LETF_HD void run(const KArgs<R, NS, NA>& ka, const int64_t pj, const int64_t lane) {
+  // fjs / jts: the two regimes' per-day constants and joint-model constants staged in shared memory by the kernel
+  // (letf_kernels.cuh).  A lane indexes them with ITS regime: from the constant bank that is a divergent LDC, replayed per
+  // distinct address; from shared memory one LDS.  nullptr (host emulation): read them from the parameter block.
+  static LETF_HD void run(const KArgs<R, NS, NA>& ka, const int64_t pj, const int64_t lane,
+                          const DevFJ<R>* fjs = nullptr, const DevJoint<R>* jts = nullptr) {
     const DevParams<R, NS, NA>& p = ka.p;
+    if (!fjs) fjs = p.fj;
+    if (!jts) jts = p.joint;
     const int T = p.T, G = p.T + p.buffer;
     RngKey key;
     key.k0 = (uint32_t)ka.seed; key.k1 = (uint32_t)(ka.seed >> 32);
@@ -168,7 +174,7 @@ struct JointPair {
         if (reg != jreg) {
           // regime switch (or day 0): reload the constants; GARCH / DCC state resets on day 0 and otherwise blends
           // 10 % toward the new regime's long-run values (calibration.py:532-541)
-          const DevJoint<R>& jp = p.joint[reg];
+          const DevJoint<R>& jp = jts[reg];
 #pragma unroll
           for (int a = 0; a < 3; a++) { mu[a] = jp.mu[a]; c0[a] = jp.c0[a]; }
 #pragma unroll
@@ -265,9 +271,9 @@ struct JointPair {
 #pragma unroll
         for (int d = 0; d < 4; d++) v[d] = jf_load(xs + g + d);
 #pragma unroll
-        for (int d = 0; d < 4; d++) vix_day(p, g + d, v[d], shift, vix);
+        for (int d = 0; d < 4; d++) vix_day(p, fjs, g + d, v[d], shift, vix);
       }
-      for (; g < so; g++) vix_day(p, g, jf_load(xs + g), shift, vix);
+      for (; g < so; g++) vix_day(p, fjs, g, jf_load(xs + g), shift, vix);
     }
 
     // ---- pass 2: the simulated window
@@ -299,7 +305,7 @@ struct JointPair {
       if (i + 1 < T) vnext = jf_load(xs + g + 1);
       const int reg = (int)(f2u_(v.b3) >> 31);
       const float rf = fabsf(v.b3);
-      const DevFJ<R>& c = p.fj[reg];
+      const DevFJ<R>& c = fjs[reg];
       reg_days1 += reg;
 
       // the day's Philox blocks, rounds interleaved: stress + one per tracking-error series
@@ -450,9 +456,9 @@ struct JointPair {
   static LETF_HD float vn_of(const JF8& v) { return v.a3; }
 
   // one burn-in day: only the VIX recursion consumes it
-  static LETF_HD void vix_day(const DevParams<R, NS, NA>& p, int g, const JF8& v, const float (&shift)[2][3], float (&vix)[2]) {
+  static LETF_HD void vix_day(const DevParams<R, NS, NA>& p, const DevFJ<R>* fjs, int g, const JF8& v, const float (&shift)[2][3], float (&vix)[2]) {
     const int reg = (int)(f2u_(v.b3) >> 31);
-    const DevFJ<R>& c = p.fj[reg];
+    const DevFJ<R>& c = fjs[reg];
     const float nz = fmaf(c.vnoise, v.a3, c.vdrift);
     const float xr[2] = {v.a0 + shift[0][0], v.b0 + shift[1][0]};
 #pragma unroll

@@ -43,9 +43,15 @@ __global__ void __launch_bounds__(BLK, MINB) letf_path_kernel(const __grid_const
 // [first_trial, first_trial + n_trials) is computed and not stored
 template <int NS, int NA, int NACT, int K10, bool EMIT, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) letf_jpair_kernel(const __grid_constant__ KArgs<float, NS, NA> ka) {
+  // both regimes' constants in shared memory: every lane reads them with its own regime index (letf_jfast.cuh)
+  __shared__ DevFJ<float> s_fj[2];
+  __shared__ DevJoint<float> s_jt[2];
+  for (int i = threadIdx.x; i < (int)(sizeof(s_fj) / 4); i += BLK) ((uint32_t*)s_fj)[i] = ((const uint32_t*)ka.p.fj)[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(s_jt) / 4); i += BLK) ((uint32_t*)s_jt)[i] = ((const uint32_t*)ka.p.joint)[i];
+  __syncthreads();
   const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p0 = ka.first_trial >> 1, p1 = (ka.first_trial + ka.n_trials - 1) >> 1;
-  for (int64_t pj = p0 + lane; pj <= p1; pj += ka.nthreads) JointPair<NS, NA, NACT, K10, EMIT>::run(ka, pj, lane);
+  for (int64_t pj = p0 + lane; pj <= p1; pj += ka.nthreads) JointPair<NS, NA, NACT, K10, EMIT>::run(ka, pj, lane, s_fj, s_jt);
 }
 
 // type-erased launcher table -----------------------------------------------------------------
