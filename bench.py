@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - LETF path-days/sec on N B200s (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c1x|c2|c3|c4|c5|sweep19|sub5|boot|series|series19]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c1x|c2|c3|c4|c5|sweep19|sub5|sma2|boot|series|series19]
 
 A "step" is one pass of the hot path over one batch: the path kernel(s) over this rank's trials (Philox draws generated on
 the device), the summary reduction kernel, and - for N > 1 - the exchange of the packed summary (one NCCL all-gather + one
@@ -71,6 +71,9 @@ WORKLOADS = {
     "sub5": dict(desc="a strategy list with no typed build (generic split pipeline: uncompacted pair producer -> six-field records -> "
                       "dynamic-slot rule kernel): S1 S4 S7 S10 S15 on the institutional market, 227 328 trials x 7560 days per GPU",
                  trials=227_328, years=30, lane_ops=520 * (7560 + 1260) / 7560 + 2 * 150 + 5 * 90 + 200, mufu=40),
+    "sma2": dict(desc="SMA switch against buy&hold (S4 on TQQQ, S2 = SPY): a subset of the config-4 list -> its routed six-slot rule "
+                      "kernel; 227 328 trials x 7560 days per GPU",
+                 trials=227_328, years=30, lane_ops=520 * (7560 + 1260) / 7560 + 2 * 150 + 90 + 60, mufu=30),
     "sweep19": dict(desc="the reference's default sweep: all 19 strategies S1..S19 on the institutional market (config.py:348-437), "
                          "227 328 trials x 7560 days per GPU (whole waves of both kernels of the split pipeline: 2 x 56 832 "
                          "antithetic pairs, 6 x 37 888 rule-kernel trials; at 200 000 trials both run 88 % full)",
@@ -111,6 +114,10 @@ def build_workload(name):
         ns = synthetic.config_namespace(SIM_ENGINE_MODE="legacy_hybrid")
         sids = ["S1", "S2", "S3"]
         model = synthetic.legacy_bootstrap_model()
+    elif name == "sma2":
+        ns = synthetic.config_namespace()
+        sids = ["S4", "S2"]
+        model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     elif name == "sub5":
         ns = synthetic.config_namespace()
         sids = ["S1", "S4", "S7", "S10", "S15"]
@@ -418,7 +425,7 @@ def run_b200(args):
         if info["kernel"].startswith("f32_joint_t_pair") or "prod" in info["kernel"]:
             alg_bytes += n * G * 32
         if "+rules_" in info["kernel"]:      # split pipeline: the per-day records are written once and read once (4 B per field)
-            nf = 5 if "rules_c4" in info["kernel"] else (8 if "rules_all" in info["kernel"] else 6)
+            nf = 5 if ("rules_c4" in info["kernel"] or "rules_sub6" in info["kernel"]) else (8 if "rules_all" in info["kernel"] else 6)
             alg_bytes += n * T * nf * 4 * 2
         pipes = None
         try:

@@ -195,7 +195,7 @@ static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t 
     // (first registered candidate wins unless LETF_KERNEL names another one)
     if (k->fj == (kSplitProducer | fast_joint_code(nact, k10)) && k->ns >= s.n_strategies && k->na >= nact && k->na < kAssets &&
         (!plan->prod || e->pin_kernel == k->name)) plan->prod = k;
-    if (k->market == kMarketFSeries && k->list && k->list != 3 && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e) &&
+    if (k->market == kMarketFSeries && k->list && !slot_list_routed(k->list) && (k->am & 0x3F) == mask && k->ns >= s.n_strategies && list_matches(k, e) &&
         (!plan->cons || e->pin_kernel == k->name)) plan->cons = k;
   }
   plan->nact = nact;
@@ -208,19 +208,22 @@ static bool find_routed_split(const LetfEngine* e, int rng_mode, bool need_io, i
   const LetfParams& s = e->params;
   if (!split_shape_ok(e, rng_mode, need_io, first) || e->no_generic_split || e->no_routed_split) return false;
   *plan = SplitPlan();
+  // (several routed lists can hold a request: the one with the fewest slots is the cheapest rule kernel)
   for (int i = 0; i < kernel_count(); i++) {
     const KernelEntry* k = kernel_at(i);
-    if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || k->list != 3) continue;
+    if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || !slot_list_routed(k->list)) continue;
+    if (plan->cons && slot_list_count(k->list) >= slot_list_count(plan->cons->list)) continue;
     const int mask = k->am & 0x3F, nl = slot_list_count(k->list);
     if ((s.asset_mask & 0x3F) & ~mask) continue;
     bool rules = false;
-    bool ok = route_request(s, k->list, k->ns, plan->slot_of, &rules);
+    int slot_of[LETF_MAX_STRATEGIES];
+    bool ok = route_request(s, k->list, k->ns, slot_of, &rules);
     for (int a = 0; ok && a < kAssets; a++) if (((mask >> a) & 1) && !(s.assets[a].leverage != 0.0)) ok = false;   // (series outside the request need a layer description)
     if (!ok) continue;
     plan->cons = k; plan->mask = mask; plan->rules = rules; plan->routed = true;
+    for (int q = 0; q < s.n_strategies; q++) plan->slot_of[q] = slot_of[q];
     plan->n_slots = nl;
     for (int q = 0; q < s.n_strategies; q++) if (plan->slot_of[q] + 1 > plan->n_slots) plan->n_slots = plan->slot_of[q] + 1;
-    break;
   }
   if (!plan->cons) return false;
   int nact = 0, k10 = 0;
@@ -528,18 +531,26 @@ static bool find_series_split(const LetfEngine* e, const LetfSeries* series, boo
   for (int k = 0; k < s.n_strategies; k++)
     if (s.strategies[k].type != LETF_ST_BENCHMARK && s.strategies[k].type != LETF_ST_BENCHMARK_TLT) rules = true;
   // 1: exactly a typed list; 2: a subset of the default sweep (routed); 3: dynamic slots
-  const KernelEntry* best3 = nullptr;
+  const KernelEntry *best2 = nullptr, *best3 = nullptr;
   for (int tier = 1; tier <= 3 && !plan->cons; tier++) {
+    if (tier == 3 && best2) {        // the cheapest routed list that holds the request
+      bool r2 = false;
+      route_request(s, best2->list, best2->ns, plan->slot_of, &r2);
+      plan->cons = best2; plan->mask = best2->am & 0x3F; plan->routed = true;
+      plan->n_slots = routed_slot_count(s, best2->list, plan->slot_of);
+      break;
+    }
     for (int i = 0; i < kernel_count() && !plan->cons; i++) {
       const KernelEntry* k = kernel_at(i);
       if (k->precision != LETF_PREC_F32 || k->market != kMarketFSeries || k->ns < s.n_strategies) continue;
       // (a frame with its own Cash_Ret column: the typed kernels do not read one - the routed kernel takes the whole list)
-      if (tier == 1 && !series->cash_ret && k->list && k->list != 3 && (k->am & 0x3F) == mask && list_matches(k, e)) { plan->cons = k; plan->mask = mask; }
-      if (tier == 2 && k->list == 3 && !(mask & ~(k->am & 0x3F)) && !e->no_routed_split) {
+      if (tier == 1 && !series->cash_ret && k->list && !slot_list_routed(k->list) && (k->am & 0x3F) == mask && list_matches(k, e)) { plan->cons = k; plan->mask = mask; }
+      if (tier == 2 && slot_list_routed(k->list) && !(mask & ~(k->am & 0x3F)) && !e->no_routed_split &&
+          (!best2 || slot_list_count(k->list) < slot_list_count(best2->list))) {
         bool r2 = false;
-        if (!route_request(s, k->list, k->ns, plan->slot_of, &r2)) continue;
-        plan->cons = k; plan->mask = k->am & 0x3F; plan->routed = true;
-        plan->n_slots = routed_slot_count(s, k->list, plan->slot_of);
+        int slot_of[LETF_MAX_STRATEGIES];
+        if (!route_request(s, k->list, k->ns, slot_of, &r2)) continue;
+        best2 = k;
       }
       if (tier == 3 && !k->list && (k->am & 0x3F) == 0x3F && !(e->type_mask & ~k->tm) && !e->no_generic_split &&
           (!best3 || k->ns < best3->ns)) best3 = k;
@@ -688,6 +699,7 @@ static int launch_any(LetfEngine* e, int market, cudaStream_t st, uint64_t seed,
     SplitPlan plan;
     if (find_routed_split(e, rng_mode, need_io, first, &plan)) {
       CK(cudaSetDevice(e->device));
+      if (plan.cons->ns == 8) return launch_split<8, 4>(e, plan, st, seed, first, n, out);
       return launch_split<32, 4>(e, plan, st, seed, first, n, out);
     }
     if (find_generic_split(e, rng_mode, need_io, first, &plan)) {

@@ -69,9 +69,11 @@ LETF_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 //   2: the reference's default sweep  S1 ... S19 in cfg.STRATEGIES order (letf/config.py:348-437)
 //   3: list 2 with routed slots: any subset of the default sweep - a slot can be switched off and writes the output row
 //      DevStrategy::route names (record mode only; letf_api.cu find_routed_split)
+//   4: list 1 with routed slots (subsets of the config-4 list: the cheaper six-slot kernel)
 // -2 marks an empty slot.
+LETF_HD constexpr bool slot_list_routed(int list) { return list == 3 || list == 4; }
 LETF_HD constexpr int slot_list_type(int list, int s) {
-  if (list == 1) {
+  if (list == 1 || list == 4) {
     switch (s) {
       case 0: case 1: return LETF_ST_BENCHMARK;
       case 2: return LETF_ST_SMA;
@@ -251,10 +253,10 @@ struct Trial {
   typedef Mth<R> M;
   static constexpr bool EXACT = sizeof(R) == 8;
   static constexpr bool FSER = MARKET == kMarketFSeries;
-  static constexpr bool ROUTED = LIST == 3;     // slots can be switched off / write another output row (DevStrategy::route)
+  static constexpr bool ROUTED = slot_list_routed(LIST);     // slots can be switched off / write another output row (DevStrategy::route)
   // record mode on a frame with its own Cash_Ret column (KArgs::rec_cash): the routed and dynamic-slot rule kernels only - the
   // typed kernels of the benchmarked sweeps stay as they are (the test + select cost c4 1.4 %, measured)
-  static constexpr bool CASHCOL = MARKET == kMarketFSeries && (LIST == 0 || LIST == 3);
+  static constexpr bool CASHCOL = MARKET == kMarketFSeries && (LIST == 0 || slot_list_routed(LIST));
   static constexpr bool SERIES = MARKET == kMarketSeries || FSER;
   static constexpr int NF = FSER ? __builtin_popcount((unsigned)AM & 0x3Fu) + 2 : 1;      // record fields: active returns, VIX, SPY price
   static constexpr int kFSpy = __builtin_popcount((unsigned)AM & 0x0Fu);                 // record field of the SPY return (asset 4)

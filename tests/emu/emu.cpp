@@ -217,7 +217,7 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   static LetfParams routed;
   int slot_of[LETF_MAX_STRATEGIES], n_slots = 0;
   const LetfParams* req = sp;
-  if (LIST == 3) {
+  if (slot_list_routed(LIST)) {
     bool rules = false;
     if ((sp->asset_mask & 0x3F) & ~AM) return -2;
     if (!route_request(*sp, LIST, NS, slot_of, &rules)) return -3;
@@ -235,7 +235,7 @@ static int run_split(const LetfParams* sp, const LetfOutputs* out, uint64_t seed
   const int32_t* dd[2] = {sp->duration_samples[0], sp->duration_samples[1]};
   convert_params<float, 32, NAP>(*sp, dd, kp.p);
   convert_params<float, NS, kAssets>(*sp, dd, kc.p);
-  if (LIST == 3) { route_slots(kp.p, *req, slot_of, n_slots); route_slots(kc.p, *req, slot_of, n_slots); }
+  if (slot_list_routed(LIST)) { route_slots(kp.p, *req, slot_of, n_slots); route_slots(kc.p, *req, slot_of, n_slots); }
   const int T = sp->sim_days, G = T + sp->buffer_days, NF = NACT + 2;
   const int64_t cap = ((n + 1) & ~(int64_t)1) + 2;        // pair-aligned columns + the half pairs at both ends (letf_api.cu launch_split)
   const int odd = (int)(first & 1);
@@ -263,6 +263,12 @@ extern "C" int letf_emu_run_split(const LetfParams* sp, int list, const LetfOutp
     if (((sp->asset_mask >> a) & 1) && ((df_fast_k(sp->assets[a].te_df) != 5 && df_fast_k(sp->assets[a].te_df) != 10) || sp->assets[a].te_clip > 0.0)) tedf = true;
   if (list == 1) return tedf ? run_split<8, 1, 25, 3, 0x80>(sp, out, seed, first, n) : run_split<8, 1, 25, 3, 4>(sp, out, seed, first, n);
   if (list == 2) return tedf ? run_split<32, 2, 29, 4, 0x80>(sp, out, seed, first, n) : run_split<32, 2, 29, 4, 8>(sp, out, seed, first, n);
+  if (list == 4) {      // routed: a subset of the config-4 list on its six-slot kernel
+    tedf = false;
+    for (int a = 0; a < kAssets; a++)
+      if (((25 >> a) & 1) && ((df_fast_k(sp->assets[a].te_df) != 5 && df_fast_k(sp->assets[a].te_df) != 10) || sp->assets[a].te_clip > 0.0)) tedf = true;
+    return tedf ? run_split<8, 4, 25, 3, 0x80>(sp, out, seed, first, n) : run_split<8, 4, 25, 3, 4>(sp, out, seed, first, n);
+  }
   if (list == 3) {      // routed: a subset of the default sweep on the 19-rule kernel with the other slots switched off
     tedf = false;
     for (int a = 0; a < kAssets; a++)
@@ -324,7 +330,7 @@ static int run_series_split(const LetfParams* sp, const LetfSeries* series, cons
   static LetfParams routed;
   int slot_of[LETF_MAX_STRATEGIES], n_slots = 0;
   const LetfParams* req = sp;
-  if (LIST == 3) {
+  if (slot_list_routed(LIST)) {
     bool rules = false;
     if ((sp->asset_mask & 0x3F) & ~AM) return -2;
     if (!route_request(*sp, LIST, NS, slot_of, &rules)) return -3;
@@ -341,7 +347,7 @@ static int run_series_split(const LetfParams* sp, const LetfSeries* series, cons
   memset(&kc, 0, sizeof(kc)); memset(&pa, 0, sizeof(pa));
   const int32_t* dd[2] = {nullptr, nullptr};
   convert_params<float, NS, kAssets>(*sp, dd, kc.p);
-  if (LIST == 3) route_slots(kc.p, *req, slot_of, n_slots);
+  if (slot_list_routed(LIST)) route_slots(kc.p, *req, slot_of, n_slots);
   const int T = series->sim_days, NF = __builtin_popcount((unsigned)AM & 0x3Fu) + 2;
   const int64_t n = series->n_paths;
   std::vector<float> rec((size_t)n * T * NF + 8), rp(kRingP), rs(kRingS), ra(kRingA);
@@ -368,6 +374,7 @@ extern "C" int letf_emu_run_series_split(const LetfParams* sp, int list, const L
   if (list == 1) return run_series_split<8, 1, 25>(sp, series, out);
   if (list == 2) return run_series_split<32, 2, 29>(sp, series, out);
   if (list == 3) return run_series_split<32, 3, 29>(sp, series, out);
+  if (list == 4) return run_series_split<8, 4, 25>(sp, series, out);
   if (list == 0) return sp->n_strategies <= 8 ? run_series_split<8, 0, 0x3F>(sp, series, out) : run_series_split<32, 0, 0x3F>(sp, series, out);
   return -4;
 }

@@ -939,11 +939,15 @@ def test_pair_kernels_with_calibrated_models(sids, kname, engine_lib, monkeypatc
     (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], "default", "prod_sweep19+rules_sub19"),
     (["S5", "S9", "S17"], "vix_te", "prod_sweep19_tedf+rules_sub19"),
     (["S1", "S3", "S2", "B_TMF"], "default", "prod_sweep19"),
+    (["S4", "S2"], "default", "prod_c4+rules_sub6"),
+    (["S19", "S5", "B_TMF", "S1", "S2", "B_TLT"], "default", "prod_c4+rules_sub6"),
+    (["S6", "S4"], "vix_te", "prod_c4_tedf+rules_sub6"),
     (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13"], "default", "prod_all+rules_all8"),
     (["S2", "S3", "B_QQQ", "B_UPRO", "B_TLT", "S9", "S13", "S4", "S5", "S7"], "default", "prod_all+rules_all"),
     (["S1", "S3", "S2", "B_UPRO", "B_TMF"], "default", "prod_all"),
     (["S4", "S6", "S12", "S18", "B_QQQ"], "vix_te", "prod_all_tedf+rules_all8"),
-], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "routed_buy_hold_only", "six_series",
+], ids=["routed_subset", "routed_out_of_order", "routed_extra_buy_hold", "routed_calibrated_te", "routed_buy_hold_only", "routed6_sma_vs_hold",
+        "routed6_out_of_order", "routed6_calibrated_te", "six_series",
         "six_series_ten_slots",
         "buy_hold_five_series", "generic_calibrated_te"])
 def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_lib, monkeypatch):
@@ -965,7 +969,7 @@ def test_generic_split_pipeline_vs_fused_and_oracle(sids, model, kname, engine_l
     with _engine(params, keep, "f32") as eng:
         slow = eng.run_host(2 * n_t, seed=77)
         assert "prod_" not in eng.launch_info()["kernel"]
-    if "sub19" in kname:        # the generic pipeline serves the same request when the routed one is switched off
+    if "rules_sub" in kname:    # the generic pipeline serves the same request when the routed one is switched off
         monkeypatch.delenv("LETF_NO_GENERIC_SPLIT")
         monkeypatch.setenv("LETF_NO_ROUTED_SPLIT", "1")
         with _engine(params, keep, "f32") as eng:

@@ -397,20 +397,23 @@ def test_generic_split_pipeline_matches_fused_generic_build(sids, extra, model, 
     np.testing.assert_array_equal(part.final_wealth, split.final_wealth[:, :5])
 
 
-@pytest.mark.parametrize("sids,extra,model", [
-    (["S1", "S4", "S7", "S10", "S15"], False, "default"),
-    (["S19", "S2", "S8", "S6"], False, "default"),                               # out of list order; S8 reads SPY
-    (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], True, "default"),             # more buy&hold strategies than the list's three slots
-    (["S5", "S9", "S17"], False, "vix_te"),
+@pytest.mark.parametrize("sids,extra,model,lst", [
+    (["S1", "S4", "S7", "S10", "S15"], False, "default", 3),
+    (["S19", "S2", "S8", "S6"], False, "default", 3),                               # out of list order; S8 reads SPY
+    (["S3", "S1", "S2", "B_TMF", "B_TLT", "S12"], True, "default", 3),             # more buy&hold strategies than the list's three slots
+    (["S5", "S9", "S17"], False, "vix_te", 3),
+    (["S4", "S2"], False, "default", 4),                                            # subsets of the config-4 list: its six-slot kernel
+    (["S19", "S5", "B_TMF", "S1", "S2", "B_TLT"], True, "default", 4),
+    (["S6", "S4"], False, "vix_te", 4),
 ])
-def test_routed_split_pipeline_matches_fused_generic_build(sids, extra, model):
+def test_routed_split_pipeline_matches_fused_generic_build(sids, extra, model, lst):
     """Any subset of the default sweep runs the 19-rule kernel with the other slots switched off and the outputs routed to
     the request's rows (slot list 3); the producer simulates the list's four series.  Against the fused generic build on
     the same Philox counters."""
     ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS) if extra else synthetic.config_namespace()
     params, keep = build_params(sids, 2, synthetic.fallback_regime_model(model), ns)
     dummy = HostTape(1, params.sim_days + params.buffer_days, params.sim_days, 1)
-    split = emu.run_split(params, 3, 24, seed=8)
+    split = emu.run_split(params, lst, 24, seed=8)
     fused = emu.run(params, dummy, precision=abi.PREC_F32, rng_mode=abi.RNG_PHILOX, seed=8, n=24)
     np.testing.assert_allclose(split.final_wealth, fused.final_wealth, rtol=1e-3)
     assert np.median(np.abs(split.final_wealth / fused.final_wealth - 1)) < 5e-6
