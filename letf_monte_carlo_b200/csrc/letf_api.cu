@@ -157,12 +157,15 @@ static bool list_matches(const KernelEntry* k, const LetfEngine* e) {
 
 // Split strategy pipeline: the market + ETF layers of one antithetic pair per thread (letf_jfast.cuh, EMIT build) write
 // per-day records, a rule kernel (Trial::run in record mode, one trial per thread) consumes them.  Admitted: fp32,
-// Philox draws, no journal / tape plumbing, the institutional shape the pair kernel serves (joint-t + moment matching +
-// antithetic pairs + stress + funding).  Two tiers:
-//  * typed: a strategy list with a compiled-in typed rule kernel, SPY simulated and QQQ not (compacted producer slots, the
-//    SPY price is the last record field);
-//  * generic: any strategy list - the uncompacted producer writes a field for each of the six series (zeros outside the
-//    asset mask), the dynamic-slot rule kernel reads them; no rule kernel launch when every strategy is buy&hold.
+// Philox draws, no journal / tape plumbing, the institutional shape the pair kernel serves (joint-t with or without moment
+// matching, antithetic pairs, stress + funding models).  Three tiers, tried in this order:
+//  * typed (find_split): the list is exactly a compiled one, SPY simulated and QQQ not (compacted producer slots, the SPY
+//    price is the last record field);
+//  * routed (find_routed_split): the list is a subset of a compiled one - its rule kernel in the routed build, the other
+//    slots switched off, output rows routed; the producer simulates the compiled list's series;
+//  * generic (find_generic_split): any other list - the uncompacted producer writes a field for each of the six series
+//    (zeros outside the asset mask), a dynamic-slot rule kernel reads them.
+// No rule kernel is launched when every strategy is buy&hold (the producer writes those rows).
 struct SplitPlan {
   const KernelEntry* prod = nullptr; const KernelEntry* cons = nullptr; int nact = 0; bool rules = true;
   // routed: the requested strategies sit in slots of a larger typed list (slot_of[k] = slot of requested strategy k)
@@ -201,7 +204,7 @@ static bool find_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t 
   plan->nact = nact;
   return plan->prod && plan->cons;
 }
-// any subset of a typed list (today: the default 19-strategy sweep, slot list 3): every rule of the request goes to the slot
+// any subset of a typed list (slot lists 3 and 4: the default 19-strategy sweep and the config-4 six): every rule of the request goes to the slot
 // that compiles its type, buy&hold strategies to the list's buy&hold slots or to the free slots behind it (they cost the
 // rule kernel nothing: the producer writes them), every other slot is switched off; the producer simulates the list's series
 static bool find_routed_split(const LetfEngine* e, int rng_mode, bool need_io, int64_t first, SplitPlan* plan) {
