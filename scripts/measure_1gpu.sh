@@ -8,7 +8,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > $F/smoke.log 2>&1; echo "sm
 python bench.py > $F/bench_default.json 2> $F/bench_default.err; echo "default rc $?"
 python bench.py --impl reference > $F/bench_reference.json 2> $F/bench_reference.err; echo "ref rc $?"
 for w in c1 c1x c2; do python bench.py --workload $w --steps 5 --warmup 3 > $F/bench_${w}.json 2> $F/bench_${w}.err; echo "$w rc $?"; done
-for w in c4 sweep19 sub5 boot; do python bench.py --workload $w --steps 3 --warmup 3 --no-cpu > $F/bench_${w}.json 2> $F/bench_${w}.err; echo "$w rc $?"; done
+for w in c4 sweep19 sub5 sma2 boot; do python bench.py --workload $w --steps 3 --warmup 3 --no-cpu > $F/bench_${w}.json 2> $F/bench_${w}.err; echo "$w rc $?"; done
 python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu > $F/bench_c5.json 2> $F/bench_c5.err; echo "c5 rc $?"
 for w in series series19; do python bench.py --workload $w --steps 3 --warmup 3 > $F/bench_${w}.json 2> $F/bench_${w}.err; echo "$w rc $?"; done
 LETF_NO_ROUTED_SPLIT=1 python bench.py --workload sub5 --steps 3 --warmup 3 --no-cpu > $F/bench_sub5generic.json 2> $F/bench_sub5generic.err; echo "sub5 generic pipeline rc $?"
