@@ -19,6 +19,7 @@
 #include <type_traits>
 #include <vector>
 #include <chrono>
+#include <thread>
 #include "letf_kernels.cuh"
 #include "letf_series_prep.cuh"
 
@@ -1035,9 +1036,30 @@ int letf_run_host(LetfEngine* e, uint64_t seed, int64_t first_trial, int64_t n_t
   }
   CK(cudaStreamSynchronize((cudaStream_t)0));
   const char* hb = (const char*)e->pin_out.p;
+  // pinned -> the caller's (pageable) arrays.  One thread copies ~10 GB/s; a 1M-trial result block is 80 MB, so large rows
+  // are split over a few host threads (the copy is the only part of a per-trial call that cannot overlap the kernel)
+  auto big_copy = [](char* dst, const char* src, size_t bytes) {
+    const size_t kMin = (size_t)4 << 20;
+    unsigned nt = bytes >= 2 * kMin ? (unsigned)(bytes / kMin) : 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned cap = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+    if (nt > cap) nt = cap;
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t part = ((bytes / nt) + 63) & ~(size_t)63;
+    for (unsigned t = 1; t < nt; t++) {
+      const size_t o = (size_t)t * part;
+      if (o >= bytes) break;
+      const size_t len = o + part < bytes ? part : bytes - o;
+      th.emplace_back([=] { memcpy(dst + o, src + o, len); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto& x : th) x.join();
+  };
   auto rows = [&](void* dst, int field, size_t elem, int nrows) {
     if (!dst || !L.bytes[field]) return;
-    for (int r = 0; r < nrows; r++) memcpy((char*)dst + (size_t)r * N * elem, hb + L.off[field] + (size_t)r * n * elem, n * elem);
+    if (N == n) { big_copy((char*)dst, hb + L.off[field], (size_t)nrows * n * elem); return; }     // same pitch: one block
+    for (int r = 0; r < nrows; r++) big_copy((char*)dst + (size_t)r * N * elem, hb + L.off[field] + (size_t)r * n * elem, n * elem);
   };
   rows(host_out->final_wealth, 0, 8, S); rows(host_out->max_dd, 1, 8, S); rows(host_out->num_trades, 2, 4, S);
   rows(host_out->journal_count, 3, 4, S); rows(host_out->journal_volume, 4, 8, S);
