@@ -96,7 +96,9 @@ def build_workload(name):
         sids = ["S1", "B_UPRO", "S3"]
         model = synthetic.normal_regime_model("c2")
     elif name == "c3":
-        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS)
+        # LETF_BENCH_NO_MM=1: moment matching off (SURVEY.md 8d asks for both; same pair kernel, zero shift)
+        ns = synthetic.config_namespace(EXTRA_STRATEGIES=synthetic.EXTRA_BENCHMARKS,
+                                        USE_MOMENT_MATCHING=os.environ.get("LETF_BENCH_NO_MM", "0") in ("", "0"))
         sids = ["S2", "B_QQQ", "B_TLT"]
         model = synthetic.fallback_regime_model(os.environ.get("LETF_BENCH_MODEL", "default"))
     elif name == "c4":
