@@ -26,7 +26,9 @@ every election, lot method, filing status and state (tests/golden/tax/engine_cas
 """
 from __future__ import annotations
 
+from bisect import bisect_left, bisect_right
 from collections import defaultdict
+from itertools import accumulate
 from typing import Mapping, Sequence
 
 import numpy as np
@@ -185,29 +187,38 @@ def wash_sale_adjustments(trades: Sequence[Mapping]):
     for asset, rows in by_asset.items():
         rows = sorted(rows, key=lambda r: r[0])                         # stable: same-day trades keep their order
         buys = [r for r in rows if r[1] == "BUY"]
+        bdays = [b[0] for b in buys]                                    # ascending (rows are sorted by day)
+        # FIFO cost of a sale over ALL buys of the asset (the reference never depletes them between sales): running sums
+        # over the buys that hold shares, in the order the reference's loop visits them.  A strategy that trades daily for
+        # 30 years has thousands of buys per asset; walking them per sale is quadratic (seconds per trade list).
+        live = [(bd, bsh, bpx) for bd, _, bsh, bpx in buys if bsh > EPS_SHARES]
+        cum_sh = list(accumulate(b[1] for b in live))
+        cum_cost = list(accumulate(b[1] * b[2] for b in live))
         used = set()
         for day, action, shares, price in rows:
             if action != "SELL":
                 continue
-            # FIFO cost of this sale over ALL buys of the asset (the reference never depletes them between sales)
-            left, cost, first_day = shares, 0, None
-            for bd, _, bsh, bpx in buys:
-                if left <= EPS_SHARES:
-                    break
-                if bsh <= EPS_SHARES:
-                    continue
-                take = min(left, bsh)
-                cost += take * bpx
-                left -= take
-                first_day = bd if first_day is None else min(first_day, bd)
+            cost, first_day = 0, None
+            if shares > EPS_SHARES and live:
+                first_day = live[0][0]
+                m = bisect_left(cum_sh, shares)                         # first buy that covers what is left
+                if m >= len(live):
+                    cost = cum_cost[-1]
+                else:
+                    prev_sh = cum_sh[m - 1] if m else 0.0
+                    cost = cum_cost[m - 1] if m else 0
+                    left = shares - prev_sh
+                    if left > EPS_SHARES:
+                        cost += min(left, live[m][1]) * live[m][2]
             loss = -(shares * price - cost)
             if loss <= 0:
                 continue
-            cand = [(abs(bd - day), i) for i, (bd, _, _, _) in enumerate(buys)
-                    if abs(bd - day) <= 30 and bd != day and i not in used]
+            # replacement buy: the nearest one within 30 days (not the same day, not used yet); ties: the earlier buy
+            lo, hi = bisect_left(bdays, day - 30), bisect_right(bdays, day + 30)
+            cand = [(abs(bdays[i] - day), i) for i in range(lo, hi) if bdays[i] != day and i not in used]
             if not cand:
                 continue
-            _, i = min(cand, key=lambda c: c[0])                         # nearest replacement; ties: the earlier buy
+            _, i = min(cand, key=lambda c: c[0])
             rday, _, rsh, _ = buys[i]
             disallowed = loss if rsh >= shares else loss * (rsh / shares)
             basis[(asset, rday)] += disallowed
@@ -252,6 +263,8 @@ def realised_by_year(trades: Sequence[Mapping], lot_method="fifo") -> dict:
     for t in trades:
         if t["action"] == "BUY":
             buy_days[t["asset"]].append(t["day_index"])
+    for d in buy_days.values():
+        d.sort()
     years = defaultdict(lambda: {"st_gains": 0, "st_losses": 0, "lt_gains": 0, "lt_losses": 0, "wash_sale_disallowed": 0})
     book = defaultdict(list)
     for t in trades:
@@ -265,7 +278,9 @@ def realised_by_year(trades: Sequence[Mapping], lot_method="fifo") -> dict:
         elif t["action"] == "SELL":
             need = t.get("shares", t["dollar_amount"] / t["price"])
             px, lots = t["price"], book[asset]
-            rebought = any(d != day and abs(d - day) <= 30 for d in buy_days[asset])
+            # any buy of the asset within 30 days that is not on the sale's own day (bisection on the sorted buy days)
+            bd = buy_days[asset]
+            rebought = (bisect_right(bd, day + 30) - bisect_left(bd, day - 30)) > (bisect_right(bd, day) - bisect_left(bd, day))
             for i in lots_to_sell(lots, need, lot_method, day, px):
                 if need <= EPS_SHARES:
                     break

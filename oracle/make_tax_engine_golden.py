@@ -60,6 +60,11 @@ def cases():
         years = [2, 3, 5, 10][k % 4]
         cs.append({"seed": 1000 + k, "years": years, "n_assets": 1 + k % 4, "n_trades": [12, 40, 90, 400][(k // 4) % 4],
                    "loss": LOSS[k % 4], "lots": LOTS[k % 8], "config": CONFIGS[k % len(CONFIGS)], "capital": [10000.0, 250000.0][k % 2]})
+    # the benchmarked horizon: 30 years of near-daily trading (what S7 ... S19 journal), thousands of buys per asset - the
+    # shapes on which a per-sale walk over all buys is quadratic (the in-tree engine bisects running sums instead)
+    for k in range(4):
+        cs.append({"seed": 2000 + k, "years": 30, "n_assets": 1 + k % 2, "n_trades": [3000, 5000, 6000, 4000][k],
+                   "loss": LOSS[k % 4], "lots": ["fifo", "fifo", "hifo", "lifo"][k], "config": CONFIGS[k % len(CONFIGS)], "capital": 10000.0})
     return cs
 
 

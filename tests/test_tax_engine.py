@@ -41,7 +41,8 @@ def test_ltcg_stacking_known_answer():
 def test_stress_set_matches_live_reference():
     from oracle.make_tax_engine_golden import trade_list
     doc = json.load(open(os.path.join(GOLD, "engine_cases.json")))
-    assert len(doc["cases"]) == 48
+    assert len(doc["cases"]) == 52          # 48 short journals + 4 at the benchmarked horizon (30 years, 3 000 - 6 000 trades)
+    assert sum(d["case"]["years"] == 30 and d["total_tax"] > 0 for d in doc["cases"]) == 4
     seen = set()
     for d in doc["cases"]:
         c = d["case"]
