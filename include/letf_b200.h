@@ -414,6 +414,18 @@ int letf_run_strategy_curve_host(LetfEngine* e, const LetfSeries* host_series, i
 /* helper for non-Python callers: utils.py:42-53 on a 3x3 matrix */
 int letf_nearest_psd3(const double in[9], double out[9]);
 
+/* Host-only (no GPU work): realised gains / losses per tax year of ONE trade list - wash-sale basis adjustments, lot
+ * selection and the short / long-term split - i.e. the per-trade bookkeeping of process_trades_with_wired_engine
+ * (letf/integration.py:113-226 over letf/tax/wash_sale.py:149-397, letf/tax/lot_selection.py).  The <= 50 trade lists per
+ * taxable strategy that create_summary_statistics taxes (letf/reporting.py:457-487) hold thousands of trades each at long
+ * horizons; the yearly netting / bracket arithmetic on top of this table stays in Python (tax_engine.py).
+ *   day / asset / action / shares / price: the journal in its own order, n entries (action 1 = BUY, 0 = SELL, others ignored;
+ *   asset = small non-negative ids); lot_method: 0 fifo, 1 lifo, 2 hifo, 3 lofo, 4 ltfo, 5 stfo, 6 mintax, 7 specific
+ *   (tax/engine.py:45-52); out: [n_years][5] = st_gains, st_losses, lt_gains, lt_losses, wash_sale_disallowed per year
+ *   (day / 252). */
+int letf_tax_realised_by_year(const int32_t* day, const int32_t* asset, const int32_t* action, const double* shares,
+                              const double* price, int64_t n, int lot_method, int n_years, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,8 +256,49 @@ def lots_to_sell(lots, shares_needed, method, sale_day, sale_price) -> list:
     return out
 
 
-def realised_by_year(trades: Sequence[Mapping], lot_method="fifo") -> dict:
-    """{year: {st_gains, st_losses, lt_gains, lt_losses, wash_sale_disallowed}} (integration.py:113-226)"""
+_YEAR_KEYS = ("st_gains", "st_losses", "lt_gains", "lt_losses", "wash_sale_disallowed")
+
+
+def realised_by_year_native(trades: Sequence[Mapping], lot_method="fifo"):
+    """`realised_by_year` through the library's host routine (csrc/letf_tax.cu: the same bookkeeping, operation for operation);
+    None when the journal is not plain BUY / SELL entries or the library is not built (the Python statement below is then used)."""
+    n = len(trades)
+    if n == 0 or any(t["action"] not in ("BUY", "SELL") for t in trades):
+        return None
+    try:
+        from .abi import load_engine_library
+        lib = load_engine_library()
+    except Exception:
+        return None
+    ids = {}
+    day = np.fromiter((t["day_index"] for t in trades), np.int32, n)
+    if day.min() < 0:
+        return None
+    asset = np.fromiter((ids.setdefault(t["asset"], len(ids)) for t in trades), np.int32, n)
+    action = np.fromiter((1 if t["action"] == "BUY" else 0 for t in trades), np.int32, n)
+    price = np.fromiter((t["price"] for t in trades), np.float64, n)
+    shares = np.fromiter((t["shares"] if "shares" in t else t["dollar_amount"] / t["price"] for t in trades), np.float64, n)
+    n_years = int(day.max()) // DAYS_PER_YEAR + 1
+    out = np.zeros((n_years, 5))
+    rc = lib.letf_tax_realised_by_year(day.ctypes.data, asset.ctypes.data, action.ctypes.data, shares.ctypes.data,
+                                       price.ctypes.data, n, LOT_METHODS.index(lot_method), n_years, out.ctypes.data)
+    if rc != 0:
+        return None
+    years = defaultdict(lambda: {k: 0 for k in _YEAR_KEYS})
+    for y in np.unique(day // DAYS_PER_YEAR).tolist():          # the years the journal touches, like the Python statement
+        years[int(y)] = dict(zip(_YEAR_KEYS, out[int(y)].tolist()))
+    return years
+
+
+def realised_by_year(trades: Sequence[Mapping], lot_method="fifo", native: bool | None = None) -> dict:
+    """{year: {st_gains, st_losses, lt_gains, lt_losses, wash_sale_disallowed}} (integration.py:113-226).
+    native: None = the library's host routine when it applies (journals of a few hundred trades and more), True / False force it"""
+    if native or (native is None and len(trades) >= 64):
+        r = realised_by_year_native(trades, lot_method)
+        if r is not None:
+            return r
+        if native:
+            raise RuntimeError("native tax bookkeeping unavailable for this journal")
     basis_adj, hold = wash_sale_adjustments(trades)
     buy_days = defaultdict(list)
     for t in trades:

@@ -96,3 +96,27 @@ def test_default_tax_fn_is_the_in_tree_engine():
     tl = [{"day_index": 10, "asset": "TQQQ", "action": "BUY", "shares": 100.0, "price": 50.0, "dollar_amount": 5000.0},
           {"day_index": 300, "asset": "TQQQ", "action": "SELL", "shares": 100.0, "price": 400.0, "dollar_amount": 40000.0}]
     assert fn(tl, 2, 10000.0, "S7_bulk", None) == te.process_trades(tl, 2, 10000.0)["total_tax"] > 0
+
+
+def test_native_bookkeeping_equals_the_python_statement():
+    """csrc/letf_tax.cu (host routine of the library) against `realised_by_year`'s Python statement: every lot method on the
+    stress journals (incl. the four 30-year ones with thousands of trades), value for value"""
+    from oracle.make_tax_engine_golden import trade_list
+    doc = json.load(open(os.path.join(GOLD, "engine_cases.json")))
+    checked = 0
+    for d in doc["cases"]:
+        c = d["case"]
+        tl = trade_list(c["seed"], c["years"], c["n_assets"], c["n_trades"])
+        for m in (te.LOT_METHODS if c["n_trades"] <= 400 else (c["lots"], "mintax")):
+            a = te.realised_by_year(tl, m, native=True)
+            b = te.realised_by_year(tl, m, native=False)
+            assert sorted(a) == sorted(b)
+            for y in b:
+                for k, v in b[y].items():
+                    assert a[y][k] == pytest.approx(v, rel=1e-13, abs=1e-9), (c, m, y, k)
+            checked += 1
+    assert checked >= 48 * 8
+    # journals the routine does not take (lower-case actions are wash-sale buys but not lots in the reference): Python statement
+    odd = [dict(t, action=t["action"].lower()) for t in trade_list(1003, 3, 2, 40)]
+    assert te.realised_by_year_native(odd) is None
+    assert te.process_trades(odd, 3, 10000.0)["total_tax"] >= 0.0
