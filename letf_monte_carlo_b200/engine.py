@@ -30,13 +30,11 @@ class NonFiniteTrials(ValueError):
     out of the trial (engine.py:486-498)."""
 
 
-def _trade_dicts(day, asset, action, shares, price, n: int) -> list[dict]:
-    """rows of the reference's Trade_List (trade.py:83-91) from the replay buffers; .tolist() converts in C"""
-    names = abi.ASSET_NAMES
-    return [{"day_index": d, "asset": names[a], "action": "BUY" if t > 0 else "SELL", "shares": s, "price": p,
-             "dollar_amount": s * p}
-            for d, a, t, s, p in zip(day[:n].tolist(), asset[:n].tolist(), action[:n].tolist(), shares[:n].tolist(),
-                                     price[:n].tolist())]
+def _trade_dicts(day, asset, action, shares, price, n: int):
+    """the reference's Trade_List (trade.py:83-91) over the replay buffers: a `TradeList` (reads like the list of dicts, keeps
+    the columns)"""
+    from .trade import TradeList
+    return TradeList(day[:n].copy(), asset[:n].copy(), action[:n].copy(), shares[:n].copy(), price[:n].copy(), abi.ASSET_NAMES)
 
 
 def default_device() -> int:

@@ -262,22 +262,31 @@ _YEAR_KEYS = ("st_gains", "st_losses", "lt_gains", "lt_losses", "wash_sale_disal
 def realised_by_year_native(trades: Sequence[Mapping], lot_method="fifo"):
     """`realised_by_year` through the library's host routine (csrc/letf_tax.cu: the same bookkeeping, operation for operation);
     None when the journal is not plain BUY / SELL entries or the library is not built (the Python statement below is then used)."""
+    from .trade import TradeList
     n = len(trades)
-    if n == 0 or any(t["action"] not in ("BUY", "SELL") for t in trades):
+    columns = isinstance(trades, TradeList)            # a replayed journal: its columns as they are
+    if n == 0 or (not columns and any(t["action"] not in ("BUY", "SELL") for t in trades)):
         return None
     try:
         from .abi import load_engine_library
         lib = load_engine_library()
     except Exception:
         return None
-    ids = {}
-    day = np.fromiter((t["day_index"] for t in trades), np.int32, n)
-    if day.min() < 0:
+    if columns:
+        day = np.ascontiguousarray(trades.day, np.int32)
+        asset = np.ascontiguousarray(trades.asset, np.int32)
+        action = np.ascontiguousarray((np.asarray(trades.action) > 0).astype(np.int32))
+        price = np.ascontiguousarray(trades.price, np.float64)
+        shares = np.ascontiguousarray(trades.shares, np.float64)
+    else:
+        ids = {}
+        day = np.fromiter((t["day_index"] for t in trades), np.int32, n)
+        asset = np.fromiter((ids.setdefault(t["asset"], len(ids)) for t in trades), np.int32, n)
+        action = np.fromiter((1 if t["action"] == "BUY" else 0 for t in trades), np.int32, n)
+        price = np.fromiter((t["price"] for t in trades), np.float64, n)
+        shares = np.fromiter((t["shares"] if "shares" in t else t["dollar_amount"] / t["price"] for t in trades), np.float64, n)
+    if day.min() < 0 or asset.min() < 0:
         return None
-    asset = np.fromiter((ids.setdefault(t["asset"], len(ids)) for t in trades), np.int32, n)
-    action = np.fromiter((1 if t["action"] == "BUY" else 0 for t in trades), np.int32, n)
-    price = np.fromiter((t["price"] for t in trades), np.float64, n)
-    shares = np.fromiter((t["shares"] if "shares" in t else t["dollar_amount"] / t["price"] for t in trades), np.float64, n)
     n_years = int(day.max()) // DAYS_PER_YEAR + 1
     out = np.zeros((n_years, 5))
     rc = lib.letf_tax_realised_by_year(day.ctypes.data, asset.ctypes.data, action.ctypes.data, shares.ctypes.data,

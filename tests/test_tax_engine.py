@@ -120,3 +120,27 @@ def test_native_bookkeeping_equals_the_python_statement():
     odd = [dict(t, action=t["action"].lower()) for t in trade_list(1003, 3, 2, 40)]
     assert te.realised_by_year_native(odd) is None
     assert te.process_trades(odd, 3, 10000.0)["total_tax"] >= 0.0
+
+
+def test_trade_list_columns_read_like_the_reference_list_of_dicts():
+    """`TradeList` (what the device replays return): list-of-dict behaviour for the reference's consumers, and the tax engine
+    takes its columns directly - same totals as the same journal given as dicts"""
+    from letf_monte_carlo_b200 import abi
+    from letf_monte_carlo_b200.trade import TradeList
+    from oracle.make_tax_engine_golden import trade_list
+    dicts = [t for t in trade_list(2001, 30, 2, 5000)]
+    for t in dicts:
+        t.setdefault("shares", t["dollar_amount"] / t["price"])
+        t["dollar_amount"] = t["shares"] * t["price"]
+    names = abi.ASSET_NAMES
+    tl = TradeList(np.array([t["day_index"] for t in dicts], np.int32), np.array([names.index(t["asset"]) for t in dicts], np.int32),
+                   np.array([1 if t["action"] == "BUY" else -1 for t in dicts], np.int32), np.array([t["shares"] for t in dicts]),
+                   np.array([t["price"] for t in dicts]), names)
+    assert len(tl) == len(dicts) and bool(tl) and tl == dicts and not (tl == dicts[:-1])
+    assert tl[0] == dicts[0] and tl[-1] == dicts[-1] and tl[3:6] == dicts[3:6] and list(tl)[17] == dicts[17]
+    with pytest.raises(IndexError):
+        tl[len(dicts)]
+    a = te.process_trades(tl, 30, 10000.0)
+    b = te.process_trades(dicts, 30, 10000.0)
+    assert a["total_tax"] == pytest.approx(b["total_tax"], rel=1e-13) and a["total_tax"] > 0
+    assert not TradeList(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), np.zeros(0), names)
