@@ -373,6 +373,13 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
                           int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price,
                           int32_t* count);
 
+/* Same across SEVERAL strategies: item j re-simulates trial trials[j] and logs strategy strategies[j].  The whole sampled-trial
+ * tax table (13 taxable strategies x 50 trials, reporting.py:408-560) is then ONE launch: the replay is bound by the latency of
+ * a single thread walking its path, so 650 items cost what 50 do.  Items whose strategy is not taxable come back empty. */
+int letf_trade_lists_multi_host(LetfEngine* e, uint64_t seed, const int64_t* trials, const int32_t* strategies, int n, int cap,
+                                int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price,
+                                int32_t* count);
+
 /* Daily equity curve of ONE trial / ONE strategy - the Series run_strategy_fixed returns (strategy.py:55-1277; its last
  * element is Final_Wealth, engine.py:578): the trial is re-simulated with the curve log on.  curve: host double[T]. */
 int letf_equity_curve_host(LetfEngine* e, uint64_t seed, int64_t trial, int strategy, int rng_mode,

@@ -185,7 +185,7 @@ ENGINE_SYMBOLS = (
     "letf_run_host", "letf_summary_reset", "letf_reduce", "letf_trade_list_host", "letf_trade_lists_host",
     "letf_equity_curve_host", "letf_run_strategy_curve_host", "letf_launch_info",
     "letf_run_strategies", "letf_nearest_psd3", "letf_summary_words", "letf_summary_combine", "letf_market_returns_host",
-    "letf_tax_realised_by_year",
+    "letf_tax_realised_by_year", "letf_trade_lists_multi_host",
 )
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -243,6 +243,8 @@ def load_engine_library(path: str | None = None):
     lib.letf_nearest_psd3.restype = i32
     lib.letf_tax_realised_by_year.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.letf_tax_realised_by_year.restype = i32
+    lib.letf_trade_lists_multi_host.argtypes = [vp, u64, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.letf_trade_lists_multi_host.restype = i32
     lib.letf_market_returns_host.argtypes = [vp, u64, i64, i32, C.POINTER(Tape), vp]
     lib.letf_market_returns_host.restype = i32
     lib.letf_summary_words.argtypes = [i32]

@@ -136,6 +136,7 @@ namespace letf {
 
 struct LogArgs {
   const int64_t* trial_ids = nullptr;       // device: batch replay (letf_trade_lists_host)
+  const int32_t* strategies = nullptr;      // device: its per-item strategies (letf_trade_lists_multi_host)
   int64_t trial = -1; int strategy = -1; int cap = 0;
   int32_t* count = nullptr; int32_t* day = nullptr; int32_t* asset = nullptr; int32_t* action = nullptr;
   double* shares = nullptr; double* price = nullptr;
@@ -341,7 +342,7 @@ static int launch_typed(LetfEngine* e, const KernelEntry* ke, cudaStream_t st, u
   ka.out = *out;
   ka.seed = seed; ka.first_trial = first; ka.n_trials = n; ka.tape_first = 0;
   ka.rng_mode = rng_mode; ka.nthreads = nthreads;
-  ka.trial_ids = lg.trial_ids;
+  ka.trial_ids = lg.trial_ids; ka.log_strategies = lg.strategies;
   ka.log_trial = lg.trial; ka.log_strategy = lg.strategy; ka.log_cap = lg.cap;
   ka.log_count = lg.count; ka.log_day = lg.day; ka.log_asset = lg.asset; ka.log_action = lg.action;
   ka.log_shares = lg.shares; ka.log_price = lg.price; ka.log_curve = lg.curve; ka.log_market = lg.market;
@@ -1130,14 +1131,39 @@ int letf_trade_list_host(LetfEngine* e, uint64_t seed, int64_t trial, int strate
   return LETF_OK;
 }
 
+static int trade_lists_impl(LetfEngine* e, uint64_t seed, const int64_t* trials, const int32_t* strategies, int n, int strategy, int cap,
+                            int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count);
+
 int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, int n, int strategy, int cap,
                           int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count) {
+  if (!e) return fail(LETF_ERR_INVALID, "null argument");
+  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  return trade_lists_impl(e, seed, trials, nullptr, n, strategy, cap, day, asset, action, shares, price, count);
+}
+
+int letf_trade_lists_multi_host(LetfEngine* e, uint64_t seed, const int64_t* trials, const int32_t* strategies, int n, int cap,
+                                int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count) {
+  if (!e || (n > 0 && !strategies)) return fail(LETF_ERR_INVALID, "null argument");
+  for (int j = 0; j < n; j++)
+    if (strategies[j] < 0 || strategies[j] >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
+  return trade_lists_impl(e, seed, trials, strategies, n, -1, cap, day, asset, action, shares, price, count);
+}
+
+static int trade_lists_impl(LetfEngine* e, uint64_t seed, const int64_t* trials, const int32_t* strategies, int n, int strategy, int cap,
+                            int32_t* day, int32_t* asset, int32_t* action, double* shares, double* price, int32_t* count) {
   if (!e || !count || (n > 0 && !trials)) return fail(LETF_ERR_INVALID, "null argument");
   if (n < 0) return fail(LETF_ERR_INVALID, "negative trial count");
-  if (strategy < 0 || strategy >= e->params.n_strategies) return fail(LETF_ERR_INVALID, "strategy out of range");
   if (cap < 0 || (cap > 0 && (!day || !asset || !action || !shares || !price))) return fail(LETF_ERR_INVALID, "bad log buffers");
   for (int j = 0; j < n; j++) { count[j] = 0; if (trials[j] < 0) return fail(LETF_ERR_INVALID, "negative trial id"); }
-  if (n == 0 || !e->params.strategies[strategy].taxable) return LETF_OK;     // engine.py:571: journal only for TAXABLE_IDS
+  if (n == 0) return LETF_OK;
+  // engine.py:571: journal only for TAXABLE_IDS (a non-taxable strategy's rows stay empty)
+  std::vector<int32_t> strat_host;
+  if (strategies) {
+    strat_host.assign(strategies, strategies + n);
+    bool any = false;
+    for (int j = 0; j < n; j++) { if (e->params.strategies[strat_host[j]].taxable) any = true; else strat_host[j] = -1; }
+    if (!any) return LETF_OK;
+  } else if (!e->params.strategies[strategy].taxable) return LETF_OK;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   const int S = e->params.n_strategies;
@@ -1145,7 +1171,7 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
   const size_t o_ids = 0, o_cnt = o_ids + align256(8 * m), o_day = o_cnt + align256(4 * m), o_asset = o_day + align256(4 * c * m),
                o_act = o_asset + align256(4 * c * m), o_sh = o_act + align256(4 * c * m), o_pr = o_sh + align256(8 * c * m),
                o_fw = o_pr + align256(8 * c * m), o_dd = o_fw + align256(8 * S * m), o_nt = o_dd + align256(8 * S * m),
-               o_fl = o_nt + align256(4 * S * m), total = o_fl + align256(4 * m);
+               o_fl = o_nt + align256(4 * S * m), o_st = o_fl + align256(4 * m), total = o_st + align256(4 * m);
   cudaError_t ce = e->stage_log.reserve(total);
   if (ce != cudaSuccess) { cudaGetLastError(); return fail(LETF_ERR_NOMEM, "log staging"); }
   char* base = (char*)e->stage_log.p;
@@ -1153,6 +1179,10 @@ int letf_trade_lists_host(LetfEngine* e, uint64_t seed, const int64_t* trials, i
   CK(cudaMemset(base + o_cnt, 0, 4 * m));
   LogArgs lg;
   lg.trial_ids = (const int64_t*)(base + o_ids); lg.trial = -1; lg.strategy = strategy; lg.cap = cap;
+  if (strategies) {
+    CK(cudaMemcpy(base + o_st, strat_host.data(), 4 * m, cudaMemcpyHostToDevice));
+    lg.strategies = (const int32_t*)(base + o_st);
+  }
   lg.count = (int32_t*)(base + o_cnt); lg.day = (int32_t*)(base + o_day); lg.asset = (int32_t*)(base + o_asset);
   lg.action = (int32_t*)(base + o_act); lg.shares = (double*)(base + o_sh); lg.price = (double*)(base + o_pr);
   LetfOutputs dout; memset(&dout, 0, sizeof(dout));

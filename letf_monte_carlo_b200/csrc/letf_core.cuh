@@ -41,6 +41,7 @@ template <typename R, int NS, int NA> struct KArgs {
   // optional journal log of ONE strategy (Trade_List replay): of the single trial log_trial, or - when trial_ids is
   // set - of every launched trial (work item j simulates trial_ids[j] and logs into row j of the [n][log_cap] buffers)
   const int64_t* trial_ids;
+  const int32_t* log_strategies;   // batch replay over several strategies: work item j logs strategy log_strategies[j] (nullptr: log_strategy)
   int64_t log_trial; int log_strategy; int log_cap;
   int32_t* log_count; int32_t* log_day; int32_t* log_asset; int32_t* log_action; double* log_shares; double* log_price;
   double* log_curve;        // [T] daily equity of (log_trial, log_strategy): the Series run_strategy_fixed returns
@@ -701,7 +702,8 @@ struct Trial {
     double ch = target - j.pos[which];
     if (::fabs(ch) < 0.001) return;
     double sh = ch > 0 ? ch : ::fabs(ch);
-    if (TAPEIO && ka.log_count && (ka.trial_ids || ka.log_trial == k) && ka.log_strategy == s) {
+    if (TAPEIO && ka.log_count && (ka.trial_ids || ka.log_trial == k) &&
+        ((ka.trial_ids && ka.log_strategies) ? ka.log_strategies[col] : ka.log_strategy) == s) {
       const int64_t row = ka.trial_ids ? col : 0;
       int n = ka.log_count[row];
       if (n < ka.log_cap) {

@@ -285,6 +285,31 @@ class PathEngine:
             cap = int(cnt.max())
         return [_trade_dicts(day[j], asset[j], action[j], shares[j], price[j], int(cnt[j])) for j in range(n)]
 
+    def trade_lists_multi(self, trials, strategies, *, seed: int = 0, cap: int = 2048) -> list:
+        """`Trade_List`s of (trial, strategy) pairs in ONE launch - the whole sampled-trial tax table (<= 50 trials for each
+        of the taxable strategies, reporting.py:457-467) at the cost of one replay: a replay is bound by the latency of a single
+        thread walking its path, not by the number of threads."""
+        ids = np.ascontiguousarray(np.asarray(list(trials), dtype=np.int64))
+        st = np.ascontiguousarray(np.asarray(list(strategies), dtype=np.int32))
+        n = len(ids)
+        if n != len(st):
+            raise ValueError("trials and strategies must have the same length")
+        if n == 0:
+            return []
+        while True:
+            day, asset, action = (np.zeros((n, cap), np.int32) for _ in range(3))
+            shares, price = np.zeros((n, cap)), np.zeros((n, cap))
+            cnt = np.zeros(n, np.int32)
+            rc = self._lib.letf_trade_lists_multi_host(self._h, seed, ids.ctypes.data, st.ctypes.data, n, cap, day.ctypes.data,
+                                                       asset.ctypes.data, action.ctypes.data, shares.ctypes.data,
+                                                       price.ctypes.data, cnt.ctypes.data)
+            self._check(rc)
+            self.launches += 1
+            if cnt.max(initial=0) <= cap:
+                break
+            cap = int(cnt.max())
+        return [_trade_dicts(day[j], asset[j], action[j], shares[j], price[j], int(cnt[j])) for j in range(n)]
+
     def equity_curve(self, trial: int, strategy: int, *, seed: int = 0, rng_mode: int = abi.RNG_PHILOX,
                      tape: HostTape | None = None) -> np.ndarray:
         """daily equity of one trial / one strategy (the Series `run_strategy_fixed` returns), by replaying the trial"""

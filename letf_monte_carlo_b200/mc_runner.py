@@ -162,6 +162,18 @@ class MonteCarloRun(dict):
             self._summary = MonteCarloSummary(self, benchmark_id)
         return self._summary
 
+    def trade_lists_multi(self, wanted):
+        """{sid: [trial indices]} -> {sid: [Trade_List ...]} in ONE device launch (engine.trade_lists_multi)"""
+        sids = [sid for sid in wanted if len(wanted[sid])]
+        trials = [self.first_trial + int(i) for sid in sids for i in wanted[sid]]
+        strategies = [self[sid].s for sid in sids for _ in wanted[sid]]
+        flat = self.engine.trade_lists_multi(trials, strategies, seed=self.seed)
+        out, k = {sid: [] for sid in wanted}, 0
+        for sid in sids:
+            out[sid] = flat[k:k + len(wanted[sid])]
+            k += len(wanted[sid])
+        return out
+
     def taxable_summary(self, tax_fn=None, tax_config=None, cfg=None, **kw):
         """Rows of the reference's taxable-brokerage table (reporting.py:399-560): <= 50 wealth-ranked trials per
         strategy are replayed on the device for their Trade_List and taxed by `tax_fn` (tax_sampling.py)."""

@@ -57,13 +57,15 @@ def _trade_list(results, i):
 
 
 def interpolated_tax(results, sid: str, time_horizon, tax_fn: Callable, tax_config: Mapping | None,
-                     initial_capital: float = 10000.0, max_tax_sims: int = MAX_TAX_SIMS):
-    """-> (tax of every trial, sampled trial indices, their taxes); reporting.py:469-506."""
+                     initial_capital: float = 10000.0, max_tax_sims: int = MAX_TAX_SIMS, lists=None):
+    """-> (tax of every trial, sampled trial indices, their taxes); reporting.py:469-506.
+    lists: the sampled trials' Trade_Lists when the caller already replayed them (one launch for all strategies)"""
     wealth = _wealth_of(results)
     n = len(wealth)
     idx = tax_sample_indices(wealth, max_tax_sims)
     taxes = []
-    lists = results.trade_lists(idx) if hasattr(results, "trade_lists") else [_trade_list(results, i) for i in idx]
+    if lists is None:
+        lists = results.trade_lists(idx) if hasattr(results, "trade_lists") else [_trade_list(results, i) for i in idx]
     for i, tl in zip(idx, lists):
         taxes.append(float(tax_fn(tl, time_horizon, initial_capital, f"{sid}_bulk", tax_config)) if tl else 0.0)
     sw, st = wealth[idx], np.array(taxes)
@@ -93,12 +95,19 @@ def taxable_summary(mc_results: Mapping, time_horizon, tax_fn: Callable | None =
                 if tl:
                     spy_post[i] = spy_pre[i] - float(tax_fn(tl, time_horizon, initial_capital, "SPY_tax", tax_config))
     rows = []
+    # device-backed results: the sampled trials of ALL taxable strategies are replayed in one launch
+    replayed = {}
+    if hasattr(mc_results, "trade_lists_multi"):
+        wanted = {sid: tax_sample_indices(_wealth_of(mc_results[sid]), max_tax_sims)
+                  for sid in taxable_ids if sid in mc_results and len(mc_results[sid])}
+        replayed = mc_results.trade_lists_multi(wanted) if wanted else {}
     for sid in taxable_ids:
         if sid not in mc_results or not len(mc_results[sid]):
             continue
         results = mc_results[sid]
         wealth = _wealth_of(results)
-        all_tax, idx, st = interpolated_tax(results, sid, time_horizon, tax_fn, tax_config, initial_capital, max_tax_sims)
+        all_tax, idx, st = interpolated_tax(results, sid, time_horizon, tax_fn, tax_config, initial_capital, max_tax_sims,
+                                            lists=replayed.get(sid))
         post = wealth - all_tax
         pcts = {}
         for pname, pval in PCTS:

@@ -1113,3 +1113,25 @@ def test_split_launches_are_chunk_invariant(engine_lib, monkeypatch):
         assert eng.launch_info()["kernel_launches"] == 8
     for k in ("final_wealth", "max_dd", "num_trades", "flags", "regime_days"):
         np.testing.assert_array_equal(getattr(b, k), getattr(a, k))
+
+
+def test_trade_lists_of_several_strategies_in_one_launch(engine_lib):
+    """the sampled-trial tax table replays the <= 50 trials of EVERY taxable strategy in one launch
+    (letf_trade_lists_multi_host): same journals as the per-strategy batch and as the single-trial replay"""
+    from letf_monte_carlo_b200 import parallel_monte_carlo_fixed
+    ns = synthetic.config_namespace()
+    ns.NUM_SIMULATIONS = 120
+    sids = ["S2", "S4", "S7", "S9", "S19"]
+    run = parallel_monte_carlo_fixed(sids, 2, synthetic.fallback_regime_model("default"), {}, cfg=ns, verbose=False)
+    wanted = {"S7": [3, 50, 119], "S19": [0, 7], "S4": [5], "S9": []}          # S4 is not a taxable id: empty journal
+    before = run.engine.launches
+    multi = run.trade_lists_multi(wanted)
+    assert run.engine.launches == before + 1
+    assert [len(multi[s]) for s in wanted] == [3, 2, 1, 0]
+    assert len(multi["S4"][0]) == 0
+    for sid in ("S7", "S19"):
+        batch = run[sid].trade_lists(wanted[sid])
+        for a, b, i in zip(multi[sid], batch, wanted[sid]):
+            assert len(a) > 0 and a == b and a == run[sid].trade_list(i)
+    rows = run.taxable_summary()
+    assert {r["id"] for r in rows} == {"S7", "S9", "S19"} and all(np.isfinite(r["sampled_tax"]).all() for r in rows)
