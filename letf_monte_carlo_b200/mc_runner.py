@@ -258,12 +258,16 @@ class MonteCarloSummary:
 
 
 _ENGINES: dict = {}      # (parameter bytes, precision, device) -> PathEngine; the handle owns device scratch worth reusing
+_FRAME_ENGINES: dict = {}          # single-frame engines of run_strategy_fixed (strategy.py), one per (strategy id, frame length)
+_FRAME_ENGINE_CACHE_MAX = 64
 _ENGINE_CACHE_MAX = 8
 
 
-def _engine_for(params, keep, precision, device):
+def _engine_for(params, keep, precision, device, cache=None):
     """Engines are pure functions of their parameter block, so repeated calls (one per horizon in
-    letf.run(), letf/__init__.py:150-162) reuse the handle instead of re-creating device state."""
+    letf.run(), letf/__init__.py:150-162) reuse the handle instead of re-creating device state.
+    cache: another cache than the Monte Carlo engines' (the single-frame `run_strategy_fixed` engines hold next to no device
+    memory but come one per strategy id: they get a larger cache of their own, `_FRAME_ENGINES`)"""
     import ctypes as C
     from .engine import PathEngine, default_device
     dev = default_device() if device is None else int(device)
@@ -289,13 +293,14 @@ def _engine_for(params, keep, precision, device):
         probe.boot.hist_spy = probe.boot.hist_qqq = probe.boot.hist_tlt = None
         durs.append(h.digest())
     key = (bytes(probe), tuple(durs), str(precision), dev)
-    eng = _ENGINES.get(key)
+    engines, limit = (_ENGINES, _ENGINE_CACHE_MAX) if cache is None else cache
+    eng = engines.get(key)
     if eng is None or eng._h is None:
-        while len(_ENGINES) >= _ENGINE_CACHE_MAX:
+        while len(engines) >= limit:
             # drop the cache entry only: earlier MonteCarloRun objects may still hold the engine for their lazy Trade_List /
             # summary calls; the handle is destroyed when the last reference goes (PathEngine.__del__)
-            _ENGINES.pop(next(iter(_ENGINES)))
-        eng = _ENGINES[key] = PathEngine(params, keep, precision=precision, device=dev)
+            engines.pop(next(iter(engines)))
+        eng = engines[key] = PathEngine(params, keep, precision=precision, device=dev)
     return eng
 
 

@@ -24,7 +24,7 @@ def run_strategy_fixed(df, strategy_id, regime_path, correlation_matrices=None, 
     """-> (equity_curve: pandas.Series[T], num_trades: int); signature of strategy.py:55 (`correlation_matrices` is
     accepted and unused, as in the reference)."""
     import pandas as pd
-    from .mc_runner import _engine_for
+    from .mc_runner import _FRAME_ENGINE_CACHE_MAX, _FRAME_ENGINES, _engine_for
     from .utils import regime_path_for_frame
     cfg = _default_cfg if cfg is None else cfg
     T = len(df)
@@ -36,7 +36,8 @@ def run_strategy_fixed(df, strategy_id, regime_path, correlation_matrices=None, 
     frame = {a: df[f"{a}_Ret"].fillna(0).to_numpy() for a in abi.ASSET_NAMES if f"{a}_Ret" in df.columns}
     if "SPY" not in frame:
         raise KeyError("run_strategy_fixed needs SPY_Ret (the trend / momentum signals read SPY_Price)")
-    eng = _engine_for(params, keep, precision, device if device is not None else getattr(cfg, "GPU_DEVICE", None))
+    eng = _engine_for(params, keep, precision, device if device is not None else getattr(cfg, "GPU_DEVICE", None),
+                      cache=(_FRAME_ENGINES, _FRAME_ENGINE_CACHE_MAX))
     curve, n_trades, trades = eng.run_strategy_curve(
         frame, 0,
         tlt_ret=df["TLT_Ret"].fillna(0).to_numpy() if "TLT_Ret" in df.columns else None,
