@@ -26,6 +26,17 @@ struct Lot { double shares, basis; int start; };
 
 // lot_selection.py: indices of `lots` to draw from, in order, until `need` shares are covered
 static void lots_to_sell(const std::vector<Lot>& lots, double need, int method, int sale_day, double sale_price, std::vector<int>& out) {
+  if (method == 0) {          // fifo (the default election): the book's own order - no candidate list to build
+    out.clear();
+    double left = need;
+    for (int i = 0; i < (int)lots.size(); i++) {
+      if (!(lots[i].shares > kEpsShares)) continue;
+      if (left <= kEpsShares) break;
+      out.push_back(i);
+      left -= lots[i].shares;
+    }
+    return;
+  }
   std::vector<int> live;
   for (int i = 0; i < (int)lots.size(); i++) if (lots[i].shares > kEpsShares) live.push_back(i);
   auto age = [&](int i) { return sale_day - lots[i].start; };
